@@ -1,0 +1,410 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, kind::f16, fp32 accumulation
+// in TMEM) for the RP-Net conv stacks: every 3x3 / dilated 3x3 / 1x1 / sub-pixel 2x2 "tap list"
+// convolution of the U-Net / VGG encoders and of the context-relation encoder.
+//
+//   reference ops replaced: nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU (+ nn.MaxPool2d(2,2),
+//   + torch.cat on channels, + nn.Upsample(x2) via sub-pixel taps)
+//   net/modules.py:42-75, net/unet.py:435-467, net/vgg.py:22-58, net/rp_net.py:50-69.
+//
+// GEMM view: M = output pixels (128 per tile: a bn x bh x bw box of the NHWC activation),
+//            N = output channels (BN per tile), K = taps x input channels (64 per k-block).
+// A operand: fp16 NHWC activations; one TMA box load per (tap, 64-channel chunk) at the tap-shifted
+//            pixel origin — TMA out-of-bounds zero fill IS the conv zero padding.
+// B operand: fp16 weights packed [tap][cout][cin] (K-major); one TMA box per k-block.
+// Both land in 128B-swizzled K-major shared-memory tiles consumed directly by tcgen05.mma.
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer, warps 2..5 = epilogue (TMEM -> registers -> scale/shift/ReLU [-> 2x2 max-pool via
+// warp shuffles] -> fp16/fp32 NHWC stores).  Two TMEM accumulator buffers overlap the epilogue of
+// tile i with the main loop of tile i+1.
+#include "common.cuh"
+
+#include <mutex>
+
+namespace rpnet {
+
+constexpr int kBM = 128;          // pixels per tile (UMMA M)
+constexpr int kBK = 64;           // fp16 channels per k-block = one 128-byte swizzle row
+constexpr int kMaxTaps = 9;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct ConvParams {
+  int N, H, W;                    // pixel grid of the conv (input == output grid, stride 1)
+  int bw_log2, bh_log2;           // tile box: bw x bh x bn pixels, bn = 128 / (bw * bh)
+  int tiles_x, tiles_y, tiles_n;  // pixel tiles
+  int n_tiles_c;                  // cout / BN
+  int chunks0, chunks1;           // 64-channel chunks of source 0 / source 1 (channel concat)
+  int ntaps;
+  int dy[kMaxTaps], dx[kMaxTaps];
+  const float* scale;             // per-cout epilogue: y = acc * scale + shift
+  const float* shift;
+  int relu;
+  // fp16 NHWC output; pixel (n, y, x) of the conv grid lands at (n, y*oy_mul+oy_off, x*ox_mul+ox_off)
+  __half* out;
+  int out_H, out_W, out_C, out_coff;
+  int oy_mul, oy_off, ox_mul, ox_off;
+  __half* out_pool;               // optional 2x2/stride-2 max-pooled fp16 NHWC output (N, H/2, W/2, pool_C)
+  int pool_C;
+  float* out_f32;                 // optional fp32 NHWC output (N, H, W, f32_C)
+  int f32_C;
+};
+
+template <int BN>
+struct ConvCfg {
+  static constexpr int kABytes = kBM * kBK * 2;                  // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
+                  const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
+  using Cfg = ConvCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);   // [2][BN]
+  float* s_shift = s_scale + 2 * BN;                                               // [2][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 2 * BN);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kblocks_per_tap = p.chunks0 + p.chunks1;
+  const int num_kb = p.ntaps * kblocks_per_tap;
+  const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int num_tiles = num_m_tiles * p.n_tiles_c;
+  const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
+  const int bn = kBM >> (p.bw_log2 + p.bh_log2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_src0);
+    tma_prefetch_desc(&tm_src1);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);     // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int ct = tile % p.n_tiles_c;
+        int mt = tile / p.n_tiles_c;
+        const int tx = mt % p.tiles_x;  mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int tn = mt / p.tiles_y;
+        const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
+          for (int kc = 0; kc < kblocks_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
+            uint8_t* b_dst = a_dst + Cfg::kABytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            if (kc < p.chunks0) tma_load_4d(&tm_src0, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
+            else                tma_load_4d(&tm_src1, &full_bar[stage], a_dst, (kc - p.chunks0) * kBK, xs, ys, n0);
+            tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);           // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);                        // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;                                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                          // accumulator row == pixel within the tile
+    const int px = row & (bw - 1);
+    const int py = (row >> p.bw_log2) & (bh - 1);
+    const int pn = row >> (p.bw_log2 + p.bh_log2);
+    const int et = threadIdx.x - 64;                        // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int ct = tile % p.n_tiles_c;
+      int mt = tile / p.n_tiles_c;
+      const int tx = mt % p.tiles_x;  mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int tn = mt / p.tiles_y;
+      const int x = tx * bw + px, y = ty * bh + py, n = tn * bn + pn;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      // stage this tile's per-channel scale/shift (buffer `as`: the other buffer may still be in use)
+      float* sc = s_scale + as * BN;
+      float* sh = s_shift + as * BN;
+      for (int i = et; i < BN; i += 128) {
+        sc[i] = __ldg(p.scale + ct * BN + i);
+        sh[i] = __ldg(p.shift + ct * BN + i);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      __half* o16 = nullptr;
+      __half* opool = nullptr;
+      float* o32 = nullptr;
+      if (p.out)
+        o16 = p.out + (static_cast<size_t>(n * p.out_H + y * p.oy_mul + p.oy_off) * p.out_W + x * p.ox_mul + p.ox_off) *
+                          p.out_C + p.out_coff + ct * BN;
+      if (p.out_pool)
+        opool = p.out_pool + (static_cast<size_t>(n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_C + ct * BN;
+      if (p.out_f32) o32 = p.out_f32 + (static_cast<size_t>(n * p.H + y) * p.W + x) * p.f32_C + ct * BN;
+      const bool pool_writer = valid && ((x & 1) == 0) && ((y & 1) == 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]);
+          v[j] = p.relu ? fmaxf(t, 0.f) : t;
+        }
+        if (o32 && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o32 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (o16 && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(o16 + c0 + j) = u;
+          }
+        }
+        if (p.out_pool) {      // 2x2 max over (x, x^1) and (y, y^1): partner lanes lane^1 and lane^bw
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, bw));
+          }
+          if (pool_writer) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+              __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(opool + c0 + j) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// fp16 tensor map with 128B swizzle; dims/box innermost first; strides in elements for dims 1..rank-1.
+static int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                         const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return RPNET_ERR_DRIVER;
+  }
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return RPNET_ERR_DRIVER;
+  }
+  return 0;
+}
+
+static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+static int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& tw, const ConvParams& p,
+                  cudaStream_t stream) {
+  using Cfg = ConvCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_c;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, tw, p);
+  return check_cuda(cudaGetLastError(), "conv_igemm_kernel launch");
+}
+
+}  // namespace rpnet
+
+using namespace rpnet;
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
+                                    const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
+                                    const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
+                                    int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                                    void* out_pool_f16, float* out_f32, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
+  RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
+  RPNET_REQUIRE(c1 == 0 || src1, "conv_igemm: src1 is null but c1 = %d", c1);
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv_igemm: bad grid %d x %d x %d", n, h, w);
+  RPNET_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "conv_igemm: ntaps %d out of range [1, %d]", ntaps, kMaxTaps);
+  RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_igemm: cout must be a multiple of 64 (got %d)", cout);
+  RPNET_REQUIRE(out_f16 || out_pool_f16 || out_f32, "conv_igemm: no output requested");
+  RPNET_REQUIRE(!out_pool_f16 || (h % 2 == 0 && w % 2 == 0), "conv_igemm: fused 2x2 max-pool needs even H, W (got %d x %d)", h, w);
+  const int BN = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+
+  ConvParams p{};
+  p.N = n; p.H = h; p.W = w;
+  const int bw = pow2_floor(w < 16 ? w : 16);
+  const int bh = pow2_floor(h < kBM / bw ? h : kBM / bw);
+  const int bn = kBM / (bw * bh);
+  RPNET_REQUIRE(!out_pool_f16 || (bw >= 2 && bh >= 2), "conv_igemm: fused pooling needs a tile of at least 2x2 pixels");
+  p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh);
+  p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh; p.tiles_n = (n + bn - 1) / bn;
+  p.n_tiles_c = cout / BN;
+  p.chunks0 = c0 / kBK; p.chunks1 = c1 / kBK;
+  p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; }
+  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.out = static_cast<__half*>(out_f16);
+  p.out_H = out_h; p.out_W = out_w; p.out_C = out_c; p.out_coff = out_coff;
+  p.oy_mul = oy_mul; p.oy_off = oy_off; p.ox_mul = ox_mul; p.ox_off = ox_off;
+  p.out_pool = static_cast<__half*>(out_pool_f16); p.pool_C = cout;
+  p.out_f32 = out_f32; p.f32_C = cout;
+  if (out_f16) {
+    RPNET_REQUIRE(out_c % 8 == 0 && out_coff % 8 == 0 && out_coff + cout <= out_c, "conv_igemm: bad output channel window (%d + %d in %d)", out_coff, cout, out_c);
+    RPNET_REQUIRE((h - 1) * oy_mul + oy_off < out_h && (w - 1) * ox_mul + ox_off < out_w && oy_off >= 0 && ox_off >= 0,
+                  "conv_igemm: output mapping exceeds the %d x %d output", out_h, out_w);
+  }
+
+  CUtensorMap t0, t1, tw;
+  const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  {
+    const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
+    int rc = make_tmap_f16(&t0, src0, 4, dims, str, abox);
+    if (rc) return rc;
+  }
+  if (c1 > 0) {
+    const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
+    int rc = make_tmap_f16(&t1, src1, 4, dims, str, abox);
+    if (rc) return rc;
+  } else {
+    t1 = t0;
+  }
+  {
+    const uint64_t cin = (uint64_t)(c0 + c1);
+    const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
+    const uint64_t str[2] = {cin, cin * cout};
+    const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
+    int rc = make_tmap_f16(&tw, wpack, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  switch (BN) {
+    case 256: return launch<256>(t0, t1, tw, p, stream);
+    case 128: return launch<128>(t0, t1, tw, p, stream);
+    default:  return launch<64>(t0, t1, tw, p, stream);
+  }
+}

@@ -1,0 +1,126 @@
+"""conv_block / up_conv with the reference's constructor signatures and state_dict layout
+(net/modules.py:42-75).  The nn.Sequential children are parameter containers only: forward() never calls
+them — it runs the tcgen05 implicit-GEMM kernel through the C ABI (rpnet_b200.engine)."""
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+
+bn_momentum = 0.1
+affine = True
+
+
+def _check_eval(mod):
+    if mod.training:
+        raise NotImplementedError('%s: train-mode (batch-statistics BatchNorm + backward) kernels are not built yet; '
+                                  'call .eval() — the B200 path has no PyTorch fallback' % type(mod).__name__)
+
+
+def _check_norm(normalization_type):
+    if normalization_type != 'BatchNorm2d':
+        raise NotImplementedError("unet_normalize_type=%r: only 'BatchNorm2d' (yamls/example.yml:40) has a B200 kernel"
+                                  % (normalization_type,))
+
+
+class _PackedModule(nn.Module):
+    """Caches packed fp16 weights / folded BN; invalidated when any parameter or buffer changes."""
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _packs(self):
+        sig = self._signature()
+        if getattr(self, '_pack_sig', None) != sig:
+            self._pack_cache = self._build_packs()
+            self._pack_sig = sig
+        return self._pack_cache
+
+    def _workspace(self):
+        if not hasattr(self, '_ws'):
+            self._ws = engine.Workspace()
+        return self._ws
+
+
+def run_conv_any(conv, bn, x_nhwc_or_img, ws, name, pack, relu=True, **kw):
+    """Dispatch one conv(+BN+ReLU): Cin in {1, 3} fp32 NCHW images go to the streaming first-conv kernel,
+    everything else to the tensor-core implicit GEMM."""
+    if pack is None:        # first conv, fp32 NCHW image input
+        scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) \
+            if bn is not None else engine.fold_bn(conv.bias)
+        n, _, h, w = x_nhwc_or_img.shape
+        out = ws.get(name, (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device)
+        ops.conv3x3_first(x_nhwc_or_img.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, relu, out)
+        return out, None
+    return engine.run_conv(pack, x_nhwc_or_img, ws, name, **kw)
+
+
+class conv_block(_PackedModule):
+    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1):
+        super(conv_block, self).__init__()
+        _check_norm(normalization_type)
+        if kernel != 3 or padding != 1:
+            raise NotImplementedError('conv_block: only kernel=3, padding=1 is used by RP-Net')
+        self.ch_in = ch_in
+        self.ch_out = ch_out
+        self.conv = nn.Sequential(
+            nn.Conv2d(ch_in, ch_out, kernel_size=kernel, stride=1, padding=padding, bias=True),
+            getattr(nn, normalization_type)(ch_out),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(ch_out, ch_out, kernel_size=kernel, stride=1, padding=padding, bias=True),
+            getattr(nn, normalization_type)(ch_out),
+            nn.ReLU(inplace=True)
+        )
+
+    def _build_packs(self):
+        first = None if self.ch_in in (1, 3) else engine.conv_bn_pack(self.conv[0], self.conv[1])
+        if first is None and self.ch_out != 64:
+            raise NotImplementedError('conv_block: a %d-channel image input needs ch_out == 64' % self.ch_in)
+        return first, engine.conv_bn_pack(self.conv[3], self.conv[4])
+
+    def run_nhwc(self, x, ws, name, x1=None, want_out=True, want_pool=False):
+        """x: fp16 NHWC (or the fp32 NCHW image for the first block); x1: optional second source (channel concat).
+        Returns (out, pooled)."""
+        _check_eval(self)
+        p0, p1 = self._packs()
+        if p0 is None:
+            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', None)
+        else:
+            a, _ = engine.run_conv(p0, x, ws, name + '.0', src1=x1)
+        return engine.run_conv(p1, a, ws, name + '.3', want_out=want_out, want_pool=want_pool)
+
+    def forward(self, x):
+        """NCHW fp32 in / out like the reference module (layout conversion at the boundary only)."""
+        ws = self._workspace()
+        xin = x if self.ch_in in (1, 3) else engine.nchw_f32_to_nhwc_f16(x)
+        out, _ = self.run_nhwc(xin, ws, 'cb')
+        return engine.nhwc_to_nchw_f32(out)
+
+
+class up_conv(_PackedModule):
+    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1):
+        super(up_conv, self).__init__()
+        _check_norm(normalization_type)
+        if kernel != 3 or padding != 1:
+            raise NotImplementedError('up_conv: only kernel=3, padding=1 is used by RP-Net')
+        self.ch_in = ch_in
+        self.ch_out = ch_out
+        self.up = nn.Sequential(
+            nn.Upsample(scale_factor=2),
+            nn.Conv2d(ch_in, ch_out, kernel_size=kernel, stride=1, padding=padding, bias=True),
+            getattr(nn, normalization_type)(ch_out),
+            nn.ReLU(inplace=True)
+        )
+
+    def _build_packs(self):
+        conv, bn = self.up[1], self.up[2]
+        scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        return engine.pack_upsample_phases(conv.weight), scale, shift
+
+    def run_nhwc(self, x, ws, name):
+        _check_eval(self)
+        phases, scale, shift = self._packs()
+        return engine.run_upconv(phases, scale, shift, x, ws, name)
+
+    def forward(self, x):
+        out = self.run_nhwc(engine.nchw_f32_to_nhwc_f16(x), self._workspace(), 'uc')
+        return engine.nhwc_to_nchw_f32(out)

@@ -1,0 +1,258 @@
+"""RP_Net with the reference's constructor / forward() / helper-method signatures and state_dict keys
+(net/rp_net.py:184-440), running on the rpnet_b200 C-ABI kernels.
+
+Differences from the reference that are visible to a caller (all documented in DESIGN.md):
+  * Wa ways x Sh shots work (the reference raises IndexError beyond 1-way 1-shot) using the
+    "oracle-ext" generalisation: cre per (way, shot); recurrent mask = sum of fg-class probabilities > 0.5.
+  * prototypes are computed once per forward (they are loop invariant).
+  * `backbone: vgg` runs (the reference raises TypeError, D1) when the yaml also sets `scale: 8`.
+  * train mode is not built yet and raises NotImplementedError (no PyTorch fallback).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import engine, ops
+from .modules import _PackedModule, _check_eval
+from .unet import U_Net
+from .vgg import Encoder
+
+
+class ContextCorrelationEncoder(_PackedModule):
+    """net/rp_net.py:45-84.  w_context / out exist for state_dict compatibility only (never used: SURVEY D4)."""
+
+    def __init__(self, cfg, in_channels=3, radius=5):
+        super().__init__()
+        self.radius = cfg['mask_refinement_correlation_radius']
+        num_feat = 64
+        self.in_channels = in_channels
+
+        def cbr(cin, cout, k):
+            return nn.Sequential(nn.Conv2d(cin, cout, k, padding=k // 2), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+        self.w_k = cbr(in_channels, in_channels, 3)
+        self.w_q = cbr(in_channels, in_channels, 3)
+        self.w_context = cbr(in_channels * 2, in_channels, 1)
+        self.q = cbr(in_channels + (self.radius * 2 + 1) ** 2, num_feat, 1)
+        self.out = cbr(2 * in_channels, num_feat, 1)
+        self._ws = engine.Workspace()
+
+    @property
+    def corr_channels(self):
+        k = (2 * self.radius + 1) ** 2
+        return (k + 63) // 64 * 64          # correlation volume padded to the 64-channel K granule
+
+    def _build_packs(self):
+        pk = engine.conv_bn_pack(self.w_k[0], self.w_k[1])
+        pq = engine.conv_bn_pack(self.w_q[0], self.w_q[1])
+        # 1x1 conv over cat([corr, fm1]) (net/rp_net.py:81): pad the corr block of input channels with zeros
+        k = (2 * self.radius + 1) ** 2
+        w = self.q[0].weight.detach()                                   # [64, k + C, 1, 1]
+        wpad = torch.zeros(w.shape[0], self.corr_channels + self.in_channels, 1, 1, device=w.device, dtype=w.dtype)
+        wpad[:, :k] = w[:, :k]
+        wpad[:, self.corr_channels:] = w[:, k:]
+        wp, taps = engine.pack_weight_taps(wpad)
+        scale, shift = engine.fold_bn(self.q[0].bias, self.q[1].weight, self.q[1].bias, self.q[1].running_mean,
+                                      self.q[1].running_var, self.q[1].eps)
+        return pk, pq, engine.ConvPack(wp, taps, scale, shift, True)
+
+    def run_nhwc(self, x, mask, tag):
+        """x fp16 NHWC [n, h, w, C]; mask fp32 [n, h, w] -> fp32 NHWC [n, h, w, 64] (cre(x*m, x*(1-m)))."""
+        _check_eval(self)
+        ws = self._ws
+        pk, pq, pqq = self._packs()
+        dev = x.device
+        xfg = ws.get(tag + '.xfg', x.shape, torch.float16, dev)
+        xbg = ws.get(tag + '.xbg', x.shape, torch.float16, dev)
+        ops.premask(x, mask, xfg, xbg)
+        return self.run_pair_nhwc(xfg, xbg, tag)
+
+    def run_pair_nhwc(self, xfg, xbg, tag):
+        ws = self._ws
+        pk, pq, pqq = self._packs()
+        n, h, w, _ = xfg.shape
+        fm1, _ = engine.run_conv(pk, xfg, ws, tag + '.fm1')
+        fm2, _ = engine.run_conv(pq, xbg, ws, tag + '.fm2')
+        corr = ws.get(tag + '.corr', (n, h, w, self.corr_channels), torch.float16, xfg.device)
+        ops.local_corr(fm1, fm2, self.radius, corr)
+        return engine.run_conv(pqq, corr, ws, tag + '.q', src1=fm1, out_f32=True)
+
+    def forward(self, fm1, fm2):
+        """Reference signature (net/rp_net.py:77-84): NCHW fp32 in, NCHW fp32 out."""
+        out = self.run_pair_nhwc(engine.nchw_f32_to_nhwc_f16(fm1), engine.nchw_f32_to_nhwc_f16(fm2), 'fwd')
+        return out.permute(0, 3, 1, 2).contiguous()
+
+
+def Correlation(fmap1, fmap2, r=3):
+    """net/rp_net.py:153-181.  NCHW fp32 in -> [B, (2r+1)^2, H, W] fp32 (operands rounded to fp16, fp32 accumulate)."""
+    b, c, h, w = fmap1.shape
+    k = (2 * r + 1) ** 2
+    kc = (k + 7) // 8 * 8
+    out = torch.empty(b, h, w, kc, dtype=torch.float16, device=fmap1.device)
+    ops.local_corr(engine.nchw_f32_to_nhwc_f16(fmap1), engine.nchw_f32_to_nhwc_f16(fmap2), r, out)
+    return out[..., :k].permute(0, 3, 1, 2).float().contiguous()
+
+
+def dice_loss_softmax(logits, true, eps=1e-7):
+    """net/rp_net.py:87-120 (plain torch: loss plumbing outside the inference hot path; eye on logits.device, D10)."""
+    num_classes = logits.shape[1]
+    if num_classes == 1:
+        one_hot = torch.eye(2, device=logits.device)[true].permute(0, 3, 1, 2).float()
+        one_hot = torch.cat([one_hot[:, 1:2], one_hot[:, 0:1]], dim=1)
+        pos = torch.sigmoid(logits)
+        probas = torch.cat([pos, 1 - pos], dim=1)
+    else:
+        one_hot = torch.eye(num_classes, device=logits.device)[true].permute(0, 3, 1, 2).float()
+        probas = F.softmax(logits, dim=1)
+    one_hot = one_hot.type(logits.type())
+    dims = (0,) + tuple(range(2, true.ndimension() + 1))
+    intersection = torch.sum(probas * one_hot, dims)
+    cardinality = torch.sum(probas + one_hot, dims)
+    return 1 - (2. * intersection / (cardinality + eps)).mean()
+
+
+def dice_ce(logits, true, eps=1e-7):
+    """net/rp_net.py:123-127."""
+    return dice_loss_softmax(logits, true, eps) + nn.CrossEntropyLoss()(logits, true)
+
+
+class _VggAsPyramid(nn.Module):
+    """Wiring for `backbone: vgg`: expose the VGG stack through the {'d4': ...} pyramid interface."""
+
+    def __init__(self, enc):
+        super().__init__()
+        self.enc = enc
+
+
+class RP_Net(nn.Module):
+    """Few-shot segmentation model (net/rp_net.py:184-350)."""
+
+    def __init__(self, in_channels=3, pretrained_path=None, cfg=None, backbone_cfg=None):
+        super().__init__()
+        self.pretrained_path = pretrained_path
+        self.config = cfg or {'align': False}
+        self.backbone_cfg = backbone_cfg
+        self.scale = backbone_cfg.get('scale', 4)
+        self.num_iter = backbone_cfg['n_iter_refinement']
+        self.use_relation_enc = backbone_cfg.get('use_relation_enc', 'relation')
+        if self.use_relation_enc != 'relation':
+            # net/rp_net.py:223-224 references an undefined SimpleConcat
+            raise NotImplementedError("use_relation_enc=%r: only 'relation' exists" % (self.use_relation_enc,))
+
+        if self.config['backbone'] == 'vgg':
+            self.encoder = Encoder(in_channels, self.pretrained_path)
+            num_feat = 512
+        elif self.config['backbone'] == 'UNet':
+            self.encoder = U_Net(backbone_cfg)
+            num_feat = 256
+            if pretrained_path:
+                dic = torch.load(self.pretrained_path, map_location='cpu')['state_dict']
+                self.load_state_dict(dic)
+        else:
+            # 'resnet' (torchvision BasicBlock stack) is a "next" row, not built
+            raise NotImplementedError(self.config['backbone'])
+
+        self.cre = ContextCorrelationEncoder(backbone_cfg, in_channels=num_feat)
+        self._ws = engine.Workspace()
+
+    # ------------------------------------------------------------------ hot path
+    def _encode(self, imgs, tag):
+        if self.config['backbone'] == 'vgg':
+            if imgs.shape[1] == 1:
+                imgs = imgs.expand(-1, 3, -1, -1)                      # net/rp_net.py:246-247
+            return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)
+        return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)
+
+    def forward(self, supp_imgs, fore_mask, back_mask, qry_imgs, registration_field=None, grid=None, query_labels=None,
+                appr_query_labels=None):
+        """
+        supp_imgs: way x shot x [B x C x H x W]; fore_mask / back_mask: way x shot x [B x H x W];
+        qry_imgs: N x [B x C x H x W] (N == 1); appr_query_labels: B x H x W (required, net/rp_net.py:269).
+        registration_field, grid, query_labels are accepted and ignored like the reference (net/rp_net.py:226).
+        Returns {'output': (N*B) x (1+Wa) x H x W logits, 'align_loss': scalar, 'refinement': {i: logits}}.
+        """
+        if self.training:
+            raise NotImplementedError('RP_Net train-mode forward/backward kernels are not built yet (call .eval())')
+        n_ways, n_shots = len(supp_imgs), len(supp_imgs[0])
+        n_queries = len(qry_imgs)
+        if n_queries != 1:
+            raise NotImplementedError('the reference forward only consumes qry_imgs[0] (net/rp_net.py:283)')
+        B = supp_imgs[0][0].shape[0]
+        H, W = qry_imgs[0].shape[-2:]
+        S = self.scale
+        ws = self._ws
+        qmask_in = appr_query_labels.unsqueeze(1)          # AttributeError on None, like the reference (:269)
+        dev = qry_imgs[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU')
+
+        # ---- encoder: support and query images in ONE batch (eval-mode BN is per-sample; the reference runs two
+        #      passes, net/rp_net.py:245-262 — identical results)
+        n_supp = n_ways * n_shots * B
+        imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0)
+        d4 = self._encode(imgs, 'enc')                                   # [(Wa*Sh+1)*B, h, w, C] fp16 NHWC
+        h, w = d4.shape[1:3]
+        if h * S != H or w * S != W:
+            raise ValueError('scale=%d does not match the encoder stride (%d x %d features for a %d x %d image); '
+                             "set `scale: %d` in the yaml" % (S, h, w, H, W, H // h))
+        supp_d4, qry_d4 = d4[:n_supp], d4[n_supp:]
+
+        fore = torch.stack([torch.stack(way, dim=0) for way in fore_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
+        back = torch.stack([torch.stack(way, dim=0) for way in back_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
+
+        # ---- support branch: cre per (way, shot) with its own pooled fore mask (net/rp_net.py:271-275)
+        supp_m = ws.get('supp_m', (n_supp, h, w), torch.float32, dev)
+        ops.avgpool_mask(fore, S, supp_m)
+        supp_feat = self.cre.run_nhwc(supp_d4, supp_m, 'supp')           # fp32 NHWC [n_supp, h, w, 64]
+
+        # ---- prototypes, hoisted out of the T loop (net/rp_net.py:288-299)
+        raw = ws.get('proto_raw', (n_ways, n_shots, B, 2, 64), torch.float32, dev)
+        ops.masked_avg_pool(supp_feat, fore, back, raw.view(n_supp, 2, 64))
+        protos = ws.get('protos', (B, 1 + n_ways, 64), torch.float32, dev)
+        ops.proto_finalize(raw, protos)
+
+        # ---- recurrent refinement (net/rp_net.py:280-312)
+        qm = ws.get('qry_m', (B, h, w), torch.float32, dev)
+        ops.avgpool_mask(qmask_in.reshape(B, H, W).float().contiguous(), S, qm)
+        pred = ws.get('pred', (B, 1 + n_ways, h, w), torch.float32, dev)
+        refinement = {}
+        logits = None
+        for i in range(self.num_iter):
+            qfeat = self.cre.run_nhwc(qry_d4, qm, 'qry')
+            ops.cos_sim(qfeat, protos, pred, 20.0)
+            logits = torch.empty(B, 1 + n_ways, H, W, dtype=torch.float32, device=dev)
+            ops.upsample_tail(pred, logits, qm, S, bool(self.backbone_cfg['soft_mask']))
+            refinement[i] = logits
+
+        # the reference's final block recomputes the last iteration bit-for-bit (net/rp_net.py:314-346);
+        # align_loss is 0 outside training (net/rp_net.py:340)
+        output = logits.clone()
+        return {'output': output, 'align_loss': 0 / B, 'refinement': refinement}
+
+    # ------------------------------------------------------------------ reference helper methods
+    def calDist(self, fts, prototype, scaler=20):
+        """fts N x C x H x W, prototype 1 x C -> N x H x W   (net/rp_net.py:353-363; C must be 64)."""
+        n, c, h, w = fts.shape
+        feat = fts.detach().float().permute(0, 2, 3, 1).contiguous()
+        protos = prototype.detach().float().reshape(1, 1, c).expand(n, 1, c).contiguous()
+        pred = torch.empty(n, 1, h, w, dtype=torch.float32, device=fts.device)
+        ops.cos_sim(feat, protos, pred, float(scaler))
+        return pred[:, 0]
+
+    def getFeatures(self, fts, mask):
+        """fts 1 x C x H' x W', mask 1 x H x W -> 1 x C   (net/rp_net.py:366-376; C <= 64)."""
+        n, c, h, w = fts.shape
+        feat = fts.detach().float().permute(0, 2, 3, 1).contiguous()
+        m = mask.detach().float().contiguous()
+        out = torch.empty(n, 2, c, dtype=torch.float32, device=fts.device)
+        ops.masked_avg_pool(feat, m, m, out)
+        return out[:, 0]
+
+    def getPrototype(self, fg_fts, bg_fts):
+        """net/rp_net.py:379-391 (list plumbing on 64-vectors; the fused path uses rpnet_proto_finalize_f32)."""
+        n_ways, n_shots = len(fg_fts), len(fg_fts[0])
+        fg_prototypes = [sum(way) / n_shots for way in fg_fts]
+        bg_prototype = sum([sum(way) / n_shots for way in bg_fts]) / n_ways
+        return fg_prototypes, bg_prototype
+
+    def alignLoss(self, qry_fts, pred, supp_fts, fore_mask, back_mask):
+        raise NotImplementedError('alignLoss is train-only (net/rp_net.py:340); train-mode kernels are not built yet')
