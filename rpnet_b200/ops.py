@@ -11,6 +11,38 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- launch accounting (bench.py): number of kernels launched and, optionally, per-kernel CUDA-event timing on
+# the launching stream.  _PROFILE maps kernel name -> list of (start_event, end_event, work) tuples.
+LAUNCHES = 0
+_PROFILE = None
+
+
+def set_profiler(store):
+    """store: dict to fill (or None to switch off)."""
+    global _PROFILE
+    _PROFILE = store
+
+
+class _Timed:
+    __slots__ = ('name', 'work', 'n', 'e0')
+
+    def __init__(self, name, work=0.0, n=1):
+        self.name, self.work, self.n = name, work, n
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.n
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROFILE.setdefault(self.name, []).append((self.e0, e1, self.work))
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -53,9 +85,10 @@ def conv_igemm(src0, wpack, taps, scale, shift, relu=True, src1=None, out=None, 
     if out_f32 is not None:
         _req(out_f32, torch.float32, 'out_f32')
         assert tuple(out_f32.shape) == (n, h, w, cout)
-    rc = lib.rpnet_conv_igemm_f16(_ptr(src0), c0, _ptr(src1), c1, n, h, w, _ptr(wpack), ntaps, dy, dx, cout, _ptr(scale),
-                                  _ptr(shift), int(bool(relu)), _ptr(out), oh, ow, oc, out_coff, om[0], om[1], om[2], om[3],
-                                  _ptr(out_pool), _ptr(out_f32), _stream())
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_igemm_f16(_ptr(src0), c0, _ptr(src1), c1, n, h, w, _ptr(wpack), ntaps, dy, dx, cout, _ptr(scale),
+                                      _ptr(shift), int(bool(relu)), _ptr(out), oh, ow, oc, out_coff, om[0], om[1], om[2], om[3],
+                                      _ptr(out_pool), _ptr(out_f32), _stream())
     _lib.check(rc, 'rpnet_conv_igemm_f16')
 
 
@@ -64,8 +97,9 @@ def conv3x3_first(img, weight, scale, shift, relu, out):
     _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')
     n, cin, h, w = img.shape
     assert tuple(weight.shape) == (64, cin, 3, 3) and tuple(out.shape) == (n, h, w, 64)
-    rc = lib.rpnet_conv3x3_first_f16(_ptr(img), n, cin, h, w, _ptr(weight), _ptr(_req(scale, torch.float32, 'scale')),
-                                     _ptr(_req(shift, torch.float32, 'shift')), int(bool(relu)), _ptr(out), _stream())
+    with _Timed('conv3x3_first', float(img.numel() * 4 + out.numel() * 2)):
+        rc = lib.rpnet_conv3x3_first_f16(_ptr(img), n, cin, h, w, _ptr(weight), _ptr(_req(scale, torch.float32, 'scale')),
+                                         _ptr(_req(shift, torch.float32, 'shift')), int(bool(relu)), _ptr(out), _stream())
     _lib.check(rc, 'rpnet_conv3x3_first_f16')
 
 
@@ -74,7 +108,8 @@ def avgpool_mask(mask, s, out):
     _req(mask, torch.float32, 'mask'); _req(out, torch.float32, 'out')
     n, h, w = mask.shape
     assert tuple(out.shape) == (n, h // s, w // s)
-    _lib.check(lib.rpnet_avgpool_mask_f32(_ptr(mask), _ptr(out), n, h, w, s, _stream()), 'rpnet_avgpool_mask_f32')
+    with _Timed('avgpool_mask', float(mask.numel() * 4 + out.numel() * 4)):
+        _lib.check(lib.rpnet_avgpool_mask_f32(_ptr(mask), _ptr(out), n, h, w, s, _stream()), 'rpnet_avgpool_mask_f32')
 
 
 def premask(x, m, x_fg, x_bg):
@@ -83,7 +118,8 @@ def premask(x, m, x_fg, x_bg):
     c = x.shape[-1]
     pixels = x.numel() // c
     assert m.numel() == pixels and x_fg.shape == x.shape and x_bg.shape == x.shape
-    _lib.check(lib.rpnet_premask_f16(_ptr(x), _ptr(m), _ptr(x_fg), _ptr(x_bg), pixels, c, _stream()), 'rpnet_premask_f16')
+    with _Timed('premask', float(x.numel() * 6 + m.numel() * 4)):
+        _lib.check(lib.rpnet_premask_f16(_ptr(x), _ptr(m), _ptr(x_fg), _ptr(x_bg), pixels, c, _stream()), 'rpnet_premask_f16')
 
 
 def local_corr(f1, f2, radius, out):
@@ -91,8 +127,9 @@ def local_corr(f1, f2, radius, out):
     _req(f1, torch.float16, 'f1'); _req(f2, torch.float16, 'f2'); _req(out, torch.float16, 'out')
     n, h, w, c = f1.shape
     assert f2.shape == f1.shape and tuple(out.shape[:3]) == (n, h, w)
-    _lib.check(lib.rpnet_local_corr_f16(_ptr(f1), _ptr(f2), _ptr(out), n, h, w, c, radius, out.shape[3], _stream()),
-               'rpnet_local_corr_f16')
+    with _Timed('local_corr', float(f1.numel() * 4 + out.numel() * 2)):
+        _lib.check(lib.rpnet_local_corr_f16(_ptr(f1), _ptr(f2), _ptr(out), n, h, w, c, radius, out.shape[3], _stream()),
+                   'rpnet_local_corr_f16')
 
 
 def masked_avg_pool(feat, mask0, mask1, out):
@@ -101,8 +138,9 @@ def masked_avg_pool(feat, mask0, mask1, out):
     _req(out, torch.float32, 'out')
     n, h, w, c = feat.shape
     assert mask0.shape == mask1.shape and mask0.shape[0] == n and tuple(out.shape) == (n, 2, c)
-    _lib.check(lib.rpnet_masked_avg_pool_f32(_ptr(feat), _ptr(mask0), _ptr(mask1), _ptr(out), n, h, w, c, mask0.shape[1],
-                                             mask0.shape[2], _stream()), 'rpnet_masked_avg_pool_f32')
+    with _Timed('masked_avg_pool', float(feat.numel() * 8 + mask0.numel() * 8)):
+        _lib.check(lib.rpnet_masked_avg_pool_f32(_ptr(feat), _ptr(mask0), _ptr(mask1), _ptr(out), n, h, w, c, mask0.shape[1],
+                                                 mask0.shape[2], _stream()), 'rpnet_masked_avg_pool_f32')
 
 
 def proto_finalize(raw, protos):
@@ -110,7 +148,8 @@ def proto_finalize(raw, protos):
     _req(raw, torch.float32, 'raw'); _req(protos, torch.float32, 'protos')
     ways, shots, batch, two, c = raw.shape
     assert two == 2 and tuple(protos.shape) == (batch, 1 + ways, c)
-    _lib.check(lib.rpnet_proto_finalize_f32(_ptr(raw), _ptr(protos), ways, shots, batch, c, _stream()), 'rpnet_proto_finalize_f32')
+    with _Timed('proto_finalize', float(raw.numel() * 4)):
+        _lib.check(lib.rpnet_proto_finalize_f32(_ptr(raw), _ptr(protos), ways, shots, batch, c, _stream()), 'rpnet_proto_finalize_f32')
 
 
 def cos_sim(feat, protos, pred, scaler=20.0):
@@ -119,7 +158,8 @@ def cos_sim(feat, protos, pred, scaler=20.0):
     b, h, w, c = feat.shape
     p = protos.shape[1]
     assert tuple(protos.shape) == (b, p, c) and tuple(pred.shape) == (b, p, h, w)
-    _lib.check(lib.rpnet_cos_sim_f32(_ptr(feat), _ptr(protos), _ptr(pred), b, h * w, c, p, float(scaler), _stream()), 'rpnet_cos_sim_f32')
+    with _Timed('cos_sim', float(feat.numel() * 4 + pred.numel() * 4)):
+        _lib.check(lib.rpnet_cos_sim_f32(_ptr(feat), _ptr(protos), _ptr(pred), b, h * w, c, p, float(scaler), _stream()), 'rpnet_cos_sim_f32')
 
 
 def upsample_tail(pred, logits, mask_out, scale, soft_mask):
@@ -127,8 +167,9 @@ def upsample_tail(pred, logits, mask_out, scale, soft_mask):
     _req(pred, torch.float32, 'pred'); _req(logits, torch.float32, 'logits'); _req(mask_out, torch.float32, 'mask_out')
     b, p, h, w = pred.shape
     assert tuple(logits.shape) == (b, p, h * scale, w * scale) and mask_out.numel() == b * h * w
-    _lib.check(lib.rpnet_upsample_tail_f32(_ptr(pred), _ptr(logits), _ptr(mask_out), b, p, h, w, scale, int(bool(soft_mask)),
-                                           _stream()), 'rpnet_upsample_tail_f32')
+    with _Timed('upsample_tail', float(pred.numel() * 4 + logits.numel() * 4 + mask_out.numel() * 4)):
+        _lib.check(lib.rpnet_upsample_tail_f32(_ptr(pred), _ptr(logits), _ptr(mask_out), b, p, h, w, scale, int(bool(soft_mask)),
+                                               _stream()), 'rpnet_upsample_tail_f32')
 
 
 def maxpool(x, k, stride, pad, out):
@@ -137,4 +178,6 @@ def maxpool(x, k, stride, pad, out):
     n, h, w, c = x.shape
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     assert tuple(out.shape) == (n, ho, wo, c)
-    _lib.check(lib.rpnet_maxpool_f16(_ptr(x), _ptr(out), n, h, w, c, k, stride, pad, _stream()), 'rpnet_maxpool_f16')
+    with _Timed('maxpool', float(x.numel() * 2 + out.numel() * 2)):
+        _lib.check(lib.rpnet_maxpool_f16(_ptr(x), _ptr(out), n, h, w, c, k, stride, pad, _stream()), 'rpnet_maxpool_f16')
+    
