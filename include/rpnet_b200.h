@@ -100,6 +100,135 @@ int rpnet_upsample_tail_f32(const float* pred, float* logits, float* mask_out, i
 int rpnet_maxpool_f16(const void* in, void* out, int n, int h, int w, int c, int k, int stride, int pad,
                       void* stream);
 
+/* ===================================================================================================
+ * Training path.  The reference trains through torch autograd (it ships no backward code and no train
+ * script — SURVEY D9); each entry point cites the forward op whose forward/backward it restates.
+ * Activation gradients are bf16 NHWC; weight gradients, BN statistics, prototypes and losses are fp32.
+ * BatchNorm "call groups": images [group_start[g], group_start[g+1]) of a batched launch form one
+ * nn.BatchNorm2d call of the reference (own batch statistics and running-stat update);
+ * group_start is a HOST int array of groups + 1 entries.
+ * =================================================================================================== */
+
+/* Same contract as rpnet_conv_igemm_f16 with bf16 operands (src0/src1/wpack) and bf16 outputs: the data-gradient
+ * of a conv is the conv of dZ with the transposed weights [tap][cin][cout] and the negated tap list. */
+int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
+                          const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
+                          const float* scale, const float* shift, int relu, void* out_bf16, int out_h, int out_w,
+                          int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                          void* out_pool_bf16, float* out_f32, void* stream);
+
+/* Bytes of scratch rpnet_conv_wgrad needs for this shape (negative = bad argument). */
+long long rpnet_conv_wgrad_workspace_bytes(int c0, int c1, int n, int h, int w, int ntaps, int cout);
+
+/* fp16 -> bf16 copy of n elements (n % 8 == 0): the weight-gradient GEMM needs both operands in one format. */
+int rpnet_cvt_f16_to_bf16(const void* in_f16, void* out_bf16, long long n, void* stream);
+
+/* Weight gradient of a tap-list conv on tcgen05 tensor cores (MN-major operands, split-K over pixels, deterministic):
+ *   grad[co][ci][tap] (+)= sum_{n,y,x} dz[n,y,x,co] * x[n, y+dy[tap], x+dx[tap], ci]        (nn.Conv2d weight layout)
+ * x0/x1: bf16 NHWC activations (x_bf16 must be 1: kind::f16 rejects mixed fp16 x bf16 operands — measured), channel
+ * concat like the forward; dz_bf16: bf16 NHWC [n][h][w][cout].
+ * Packed input channels [hole_start, hole_start+hole_len) are padding and are skipped in `grad`.
+ * Replaces autograd's conv weight gradient for net/modules.py:47-54,66-71 and net/rp_net.py:50-69. */
+int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
+                     int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
+                     int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream);
+
+/* Weight gradient of the Cin = 1 first conv: grad[64][1][3][3] += sum dz * img.  net/unet.py:405 (encoder.Conv1.conv.0). */
+int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream);
+
+/* fp32 [cout][cin_real][taps] -> fp16 [taps][cout][cin] (forward pack) and/or bf16 [taps][cin][cout] (dgrad pack);
+ * cin = cin_real + hole_len with zero padding channels at [hole_start, hole_start+hole_len). */
+int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
+                           void* w_fwd_f16, void* w_dgrad_bf16, void* stream);
+
+/* Train-mode nn.BatchNorm2d (net/modules.py:49,52,69; net/rp_net.py:52,57,67), statistics pass:
+ * sums[g][c] = {sum z, sum z^2} over the images of call group g.  z fp16 NHWC. */
+int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+                       void* stream);
+
+/* stats[g][c] = {mean, rstd, a = rstd*gamma, b = beta - mean*a}; running_mean/var (momentum, unbiased var) updated once
+ * per call group in order, num_batches_tracked += groups.  conv_bias: the bias the conv kernel dropped (it cancels in
+ * train-mode BN but is part of the running mean).  hw = pixels per image. */
+int rpnet_bn_finalize_f32(const float* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
+                          const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
+                          float* running_var, long long* num_batches_tracked, float* stats, void* stream);
+
+/* y = relu?(a*z + b): fp16 NHWC and/or fp32 NHWC and/or the 2x2 max-pooled fp16 copy (nn.MaxPool2d(2,2), net/unet.py:397). */
+int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups,
+                       int relu, void* y_f16, void* y_pool_f16, float* y_f32, void* stream);
+
+/* Backward of BatchNorm(batch stats) + ReLU: dz (bf16 NHWC) from the gradient of the activation, which is the sum of
+ *   g_direct : bf16 (fp32 if d_is_f32) NHWC with pixel pitch d_ld, channel offset d_off          (may be null)
+ *   g_pool   : bf16 NHWC [n][h/2][w/2] gradient of the max-pooled copy, routed to the window's first max (may be null)
+ *   g_up     : bf16 NHWC [n][2h][2w] gradient of the nearest-x2 upsampled copy, summed per 2x2     (may be null)
+ * dgamma[c] += sum dy*x_hat, dbeta[c] += sum dy (fp32, may be null).  scratch: fp32 [groups][c][4]. */
+int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups, int relu,
+                 const void* g_direct, int d_ld, int d_off, int d_is_f32, const void* g_pool_bf16, int p_ld, int p_off,
+                 const void* g_up_bf16, int u_ld, int u_off, float* dgamma, float* dbeta, float* scratch,
+                 void* dz_bf16, void* stream);
+
+/* nn.Upsample(scale_factor=2) nearest, fp16 NHWC [n][h][w][c] -> [n][2h][2w][c].  net/modules.py:67. */
+int rpnet_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, void* stream);
+
+/* Backward of the pre-mask (net/rp_net.py:275,283) summed over `iters` uses of the same features:
+ * dx[p][c] = sum_i dxfg[i][p][c]*mask[i][p] + dxbg[i][p][c]*(1 - mask[i][p]);  bf16 in / out, mask fp32 [iters][pixels]. */
+int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask, int iters, long long pixels, int c,
+                           void* dx, void* stream);
+
+/* Backward of Correlation (net/rp_net.py:153-181).  dq_bf16 NHWC [n][h][w][ld]: channels [0,(2r+1)^2) = d corr,
+ * [add_off, add_off+c) = the direct gradient of fm1 from cat([corr, fm1]) (net/rp_net.py:81), added into df1. */
+int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const void* dq_bf16, int ld, int add_off, void* df1_bf16,
+                         void* df2_bf16, int n, int h, int w, int c, int radius, void* stream);
+
+/* Backward of calDist (net/rp_net.py:353-363).  feat fp32 [n][hw][64]; protos fp32 [proto_sets][p][64], image i uses
+ * set i % proto_sets; dpred fp32 [n][p][hw]; dfeat (= or += when accumulate); dprotos += (caller zeroes; may be null). */
+int rpnet_cos_sim_bwd_f32(const float* feat, const float* protos, const float* dpred, int n, int hw, int c, int n_protos,
+                          int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, void* stream);
+
+/* Adjoint of F.interpolate(bilinear, align_corners=False): out[n][i][j] = sum_{Y,X} wy(Y,i) wx(X,j) in[n][Y][X].
+ * (a) masked-average-pool weights U^T mask (net/rp_net.py:373-376), (b) backward of the logit upsample (:303,337).
+ * sums (optional) [n] = sum of in[n]. */
+int rpnet_bilinear_adjoint_f32(const float* in, float* out, float* sums, int n, int in_h, int in_w, int out_h, int out_w,
+                               void* stream);
+
+/* getFeatures for a fore and a back mask from their adjoint maps: out[n][k][c] = sum_p feat[n][p][c]*wmap_k[n][p] /
+ * (msum_k[n] + 1e-5).  feat fp32 [n][hw][c], c <= 64.  net/rp_net.py:366-376. */
+int rpnet_weighted_pool_f32(const float* feat, const float* wmap0, const float* wmap1, const float* msum0, const float* msum1,
+                            float* out, int n, int hw, int c, void* stream);
+int rpnet_weighted_pool_bwd_f32(const float* dout, const float* wmap0, const float* wmap1, const float* msum0,
+                                const float* msum1, float* dfeat, int accumulate, int n, int hw, int c, void* stream);
+
+/* Backward of getPrototype (net/rp_net.py:379-391): dprotos [batch][1+ways][c] -> draw [ways][shots][batch][2][c]. */
+int rpnet_proto_finalize_bwd_f32(const float* dprotos, float* draw, int ways, int shots, int batch, int c, void* stream);
+
+/* dice_ce (net/rp_net.py:87-127) for `groups` logit tensors sharing the labels: logits fp32 [groups][batch][classes][hw],
+ * labels int64 [batch][hw]; loss[g] = dice + CE; dlogits (optional) = grad_scale * dloss_g/dlogits.
+ * sums: fp32 scratch [groups][2*classes+1]. */
+int rpnet_dice_ce_f32(const float* logits, const long long* labels, int groups, int batch, int n_classes, long long hw,
+                      float eps, float grad_scale, float* sums, float* dlogits, float* loss, void* stream);
+
+/* alignLoss pieces (net/rp_net.py:394-440).  class_pool: argmax over pred [batch][classes][hw] -> per-class masked mean
+ * of feat [batch][hw][64] -> qproto [batch][classes][64], counts [batch][classes], amax int32 [batch][hw]. */
+int rpnet_class_pool_f32(const float* feat, const float* pred, int batch, int hw, int c, int n_classes, float* qproto,
+                         float* counts, void* amax_i32, void* stream);
+int rpnet_class_pool_bwd_f32(const float* dqproto, const float* counts, const void* amax_i32, int batch, int hw, int c, int n_classes,
+                             float* dfeat, void* stream);
+/* protos_s[w][s][b] = [qproto[b][0], qproto[b][1+w]]; weight[w][s][b] = (counts[b][1+w] > 0) * scaler / (shots*ways*batch). */
+int rpnet_align_gather_f32(const float* qproto, const float* counts, int ways, int shots, int batch, float scaler,
+                           float* protos_s, float* weight, void* stream);
+int rpnet_align_scatter_f32(const float* dprotos_s, int ways, int shots, int batch, float* dqproto, void* stream);
+/* Cross entropy with ignore over 2-class logits [n][2][hw]; label = 1 where fore == 1, else 0 where back == 1, else
+ * ignored; *loss = sum_n weight[n] * mean_valid(nll_n); dlogits (optional) = grad_scale * dloss.  sums: scratch [n][2]. */
+int rpnet_ce_mask_f32(const float* logits, const float* fore, const float* back, const float* weight, int n, long long hw,
+                      float grad_scale, float* sums, float* dlogits, float* loss, void* stream);
+/* F.interpolate(bilinear, align_corners=False) of fp32 maps [n][h][w] -> [n][out_h][out_w]  (net/rp_net.py:430). */
+int rpnet_bilinear_up_f32(const float* in, float* out, int n, int h, int w, int out_h, int out_w, void* stream);
+
+/* torch.optim.Adam step (L2 weight decay added to the gradient; yamls/example.yml:64-67) on flat fp32 buffers;
+ * the gradient is multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 // thin inline-PTX wrappers (mbarrier, TMA, tcgen05/TMEM).  No CUTLASS dependency.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,6 +30,14 @@ int check_cuda(cudaError_t e, const char* what);
 
 enum { RPNET_OK = 0, RPNET_ERR_CUDA = -1, RPNET_ERR_ARG = -2, RPNET_ERR_DRIVER = -3 };
 
+// host helpers shared by the tensor-core kernels (defined in conv_igemm.cu)
+// 2-byte (fp16 / bf16) tensor map with 128B swizzle; dims/box innermost first; strides in elements for dims 1..rank-1.
+int make_tmap_2b(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                 const uint32_t* box, bool bf16);
+int num_sms();
+int pow2_floor(int v);
+int ilog2(int v);
+
 #ifdef __CUDACC__
 // ---- generic -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -40,6 +49,40 @@ __device__ __forceinline__ bool elect_one() {
       "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---- 8-wide packing: fp32 registers <-> one 16-byte vector of fp16 / bf16 ------------------------
+__device__ __forceinline__ uint4 pack8_f16(const float* v) {
+  __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+  __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+  u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+  return u;
+}
+__device__ __forceinline__ void unpack8_f16(const uint4& u, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
 }
 
 // ---- mbarrier ------------------------------------------------------------------------------------
@@ -141,7 +184,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) |
          (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand (the M/N index is contiguous: 64 elements = one 128-byte swizzle row per K index), 128-byte swizzle.
+// Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: `lbo_bytes` = distance between consecutive
+// 64-element chunks along M/N, `sbo_bytes` = distance between groups of 8 K rows (1024 B when rows are dense).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // Instruction descriptor: fp16 x fp16 -> fp32, both operands K-major, dense.
+// Modifiers: bit 7 / bit 10 = A / B operand is bf16; bit 15 / bit 16 = A / B operand is MN-major.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }

@@ -39,6 +39,8 @@ struct ConvParams {
   const float* scale;             // per-cout epilogue: y = acc * scale + shift
   const float* shift;
   int relu;
+  int in_bf16;                    // operands (activations AND weights) are bf16 instead of fp16 (dgrad path)
+  int out_bf16;                   // `out` / `out_pool` are bf16 instead of fp16
   // fp16 NHWC output; pixel (n, y, x) of the conv grid lands at (n, y*oy_mul+oy_off, x*ox_mul+ox_off)
   __half* out;
   int out_H, out_W, out_C, out_coff;
@@ -135,7 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      const uint32_t idesc = umma_idesc_f16(kBM, BN) | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -219,14 +221,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         }
         if (o16 && valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(o16 + c0 + j) = u;
-          }
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(o16 + c0 + j) = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
         }
         if (p.out_pool) {      // 2x2 max over (x, x^1) and (y, y^1): partner lanes lane^1 and lane^bw
 #pragma unroll
@@ -236,14 +232,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           }
           if (pool_writer) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-              __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(opool + c0 + j) = u;
-            }
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(opool + c0 + j) = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
           }
         }
       }
@@ -280,9 +270,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// fp16 tensor map with 128B swizzle; dims/box innermost first; strides in elements for dims 1..rank-1.
-static int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                         const uint32_t* box) {
+// fp16 / bf16 tensor map with 128B swizzle; dims/box innermost first; strides in elements for dims 1..rank-1.
+int make_tmap_2b(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                 const uint32_t* box, bool bf16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -292,7 +282,7 @@ static int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -304,11 +294,11 @@ static int make_tmap_f16(CUtensorMap* m, const void* base, int rank, const uint6
   return 0;
 }
 
-static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
-static int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -337,12 +327,11 @@ static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMa
 
 using namespace rpnet;
 
-// See include/rpnet_b200.h for the contract.
-RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
-                                    const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
-                                    const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
-                                    int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
-                                    void* out_pool_f16, float* out_f32, void* stream_) {
+static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
+                           const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
+                           const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
+                           int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                           void* out_pool_f16, float* out_f32, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -367,6 +356,7 @@ RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, i
   p.ntaps = ntaps;
   for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; }
   p.scale = scale; p.shift = shift; p.relu = relu;
+  p.in_bf16 = bf16 ? 1 : 0; p.out_bf16 = bf16 ? 1 : 0;
   p.out = static_cast<__half*>(out_f16);
   p.out_H = out_h; p.out_W = out_w; p.out_C = out_c; p.out_coff = out_coff;
   p.oy_mul = oy_mul; p.oy_off = oy_off; p.ox_mul = ox_mul; p.ox_off = ox_off;
@@ -383,13 +373,13 @@ RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, i
   {
     const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
-    int rc = make_tmap_f16(&t0, src0, 4, dims, str, abox);
+    int rc = make_tmap_2b(&t0, src0, 4, dims, str, abox, bf16);
     if (rc) return rc;
   }
   if (c1 > 0) {
     const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
-    int rc = make_tmap_f16(&t1, src1, 4, dims, str, abox);
+    int rc = make_tmap_2b(&t1, src1, 4, dims, str, abox, bf16);
     if (rc) return rc;
   } else {
     t1 = t0;
@@ -399,7 +389,7 @@ RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, i
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
     const uint64_t str[2] = {cin, cin * cout};
     const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
-    int rc = make_tmap_f16(&tw, wpack, 3, dims, str, box);
+    int rc = make_tmap_2b(&tw, wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
   }
   switch (BN) {
@@ -407,4 +397,23 @@ RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, i
     case 128: return launch<128>(t0, t1, tw, p, stream);
     default:  return launch<64>(t0, t1, tw, p, stream);
   }
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
+                                    const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
+                                    const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
+                                    int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                                    void* out_pool_f16, float* out_f32, void* stream_) {
+  return conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_f16,
+                         out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off, out_pool_f16, out_f32, stream_);
+}
+
+RPNET_API int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
+                                     const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
+                                     const float* scale, const float* shift, int relu, void* out_bf16, int out_h, int out_w,
+                                     int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                                     void* out_pool_bf16, float* out_f32, void* stream_) {
+  return conv_igemm_impl(true, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_bf16,
+                         out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off, out_pool_bf16, out_f32, stream_);
 }

@@ -1,0 +1,353 @@
+// Weight gradient of the tap-list convolutions on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp32
+// accumulation in TMEM), reading BOTH operands straight from the NHWC tensors as MN-major UMMA tiles:
+//
+//   dW[tap][ci][co] = sum_{pixels p} X[p + tap][ci] * dZ[p][co]
+//
+// GEMM view: M = (tap, ci) rows — one M tile is two "X boxes" (tap, 64-channel chunk) = 128 rows;
+//            N = co (BN per tile);  K = pixels (64 per stage: a bn x bh x bw box of the activation).
+// A operand: X (forward activations as bf16, optional two-source channel concat), TMA box at the tap-shifted
+//            pixel origin — out-of-bounds zero fill is the conv zero padding, exactly like the forward.
+// B operand: dZ (bf16 gradient of the conv output), TMA box at the unshifted origin.
+// A pixel row of 64 channels is one 128-byte swizzle row, so the TMA tile IS the canonical MN-major
+// SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)): LBO = box bytes (next 64-channel chunk),
+// SBO = 1024 B (next 8 pixels).  Both operands must share one element format (a mixed fp16 x bf16 descriptor
+// traps with an illegal instruction on B200), so the fp16 forward activations are converted to bf16 first.
+//
+// The K (pixel) range is split over CTAs (few output tiles, millions of pixels); each work item writes an
+// fp32 partial tile, and wgrad_reduce_kernel sums the splits in a fixed order (deterministic) into the
+// PyTorch-layout gradient [cout][cin][kh][kw] (+= so that a weight used by several calls accumulates).
+//
+// Replaces autograd's conv2d weight gradient for nn.Conv2d in net/modules.py:47-54,66-71 and
+// net/rp_net.py:50-69 (the reference trains through torch autograd; it ships no backward code).
+#include "common.cuh"
+
+namespace rpnet {
+
+constexpr int kWgPix = 64;                         // pixels (K) per stage
+constexpr int kWgBoxBytes = kWgPix * 128;          // one [64 ch x 64 px] box = 8 KB
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxTaps = 9;
+constexpr int kWgSmemBudget = 200 * 1024;
+
+struct WgradParams {
+  int N, H, W;
+  int bw_log2, bh_log2;
+  int tiles_x, tiles_y, tiles_n, ptiles;
+  int chunks0, chunks1;
+  int ntaps;
+  int dy[kWgMaxTaps], dx[kWgMaxTaps];
+  int n_boxes, n_mtiles, n_ntiles, splits;
+  int rows;                                        // ntaps * cin
+  int cout;
+  int x_bf16, dz_bf16;
+  float* partial;                                  // [splits][rows][cout]
+};
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * kWgBoxBytes;
+  static constexpr int kBBytes = (BN / 64) * kWgBoxBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kWgSmemBudget / kStageBytes) > 8 ? 8 : (kWgSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                  const __grid_constant__ CUtensorMap tm_dz, const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_mn = p.n_mtiles * p.n_ntiles;
+  const int num_items = tiles_mn * p.splits;
+  const int nch = p.chunks0 + p.chunks1;
+  const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
+  const int bn = kWgPix >> (p.bw_log2 + p.bh_log2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x0);
+    tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_dz);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / tiles_mn;
+        const int rem = item % tiles_mn;
+        const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        int bx[2];
+        bx[0] = 2 * mt;
+        bx[1] = (2 * mt + 1 < p.n_boxes) ? 2 * mt + 1 : 2 * mt;      // odd box count: duplicate (rows discarded)
+        for (int pt = k0; pt < k1; ++pt) {
+          int t = pt;
+          const int tx = t % p.tiles_x;  t /= p.tiles_x;
+          const int ty = t % p.tiles_y;
+          const int tn = t / p.tiles_y;
+          const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
+          uint8_t* b_dst = a_dst + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int tap = bx[j] / nch, c = bx[j] % nch;
+            const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
+            if (c < p.chunks0) tma_load_4d(&tm_x0, &full_bar[stage], a_dst + j * kWgBoxBytes, c * 64, xs, ys, n0);
+            else               tma_load_4d(&tm_x1, &full_bar[stage], a_dst + j * kWgBoxBytes, (c - p.chunks0) * 64, xs, ys, n0);
+          }
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(&tm_dz, &full_bar[stage], b_dst + j * kWgBoxBytes, nt * BN + j * 64, x0, y0, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16) | (p.x_bf16 ? (1u << 7) : 0u) |
+                             (p.dz_bf16 ? (1u << 10) : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int split = item / tiles_mn;
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int pt = k0; pt < k1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            // 16 pixels (K) = 16 swizzle rows = 2048 B further into every box
+            const uint64_t a_desc = umma_desc_sw128_mn(a_addr + k * 2048, kWgBoxBytes, 1024);
+            const uint64_t b_desc = umma_desc_sw128_mn(b_addr + k * 2048, kWgBoxBytes, 1024);
+            umma_f16(d_tmem, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5): TMEM -> fp32 partial tile =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int split = item / tiles_mn;
+      const int rem = item % tiles_mn;
+      const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int r = mt * 128 + row;
+      const bool valid = r < p.rows;
+      float* dst = p.partial + ((size_t)split * p.rows + (valid ? r : 0)) * p.cout + nt * BN;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// grad[co][ci_real][tap] (beta * old +) = sum_split partial[split][tap * cin + ci][co].
+// Packed input channels [hole_start, hole_start + hole_len) are padding (skipped); later channels shift down.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int ntaps, int cin, int cout,
+                    int hole_start, int hole_len, int accumulate) {
+  const long long total = (long long)ntaps * cin * cout;
+  const int cin_real = cin - hole_len;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % cout);
+    const int r = (int)(i / cout);
+    const int ci = r % cin, tap = r / cin;
+    if (ci >= hole_start && ci < hole_start + hole_len) continue;
+    const int cr = ci < hole_start ? ci : ci - hole_len;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + (size_t)sp * total + i);
+    float* g = grad + ((size_t)co * cin_real + cr) * ntaps + tap;
+    *g = accumulate ? (*g + s) : s;
+  }
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& tx0, const CUtensorMap& tx1, const CUtensorMap& tdz, const WgradParams& p, int grid,
+                        cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  conv_wgrad_kernel<BN><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tx0, tx1, tdz, p);
+  return check_cuda(cudaGetLastError(), "conv_wgrad_kernel launch");
+}
+
+struct WgradPlan {
+  int BN, bw, bh, bn, tiles_x, tiles_y, tiles_n, ptiles, n_boxes, n_mtiles, n_ntiles, splits, rows;
+};
+
+static WgradPlan plan_wgrad(int c0, int c1, int n, int h, int w, int ntaps, int cout) {
+  WgradPlan pl;
+  pl.BN = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  pl.bw = pow2_floor(w < 16 ? w : 16);
+  pl.bh = pow2_floor(h < kWgPix / pl.bw ? h : kWgPix / pl.bw);
+  pl.bn = kWgPix / (pl.bw * pl.bh);
+  pl.tiles_x = (w + pl.bw - 1) / pl.bw;
+  pl.tiles_y = (h + pl.bh - 1) / pl.bh;
+  pl.tiles_n = (n + pl.bn - 1) / pl.bn;
+  pl.ptiles = pl.tiles_x * pl.tiles_y * pl.tiles_n;
+  const int cin = c0 + c1;
+  pl.rows = ntaps * cin;
+  pl.n_boxes = ntaps * (cin / 64);
+  pl.n_mtiles = (pl.n_boxes + 1) / 2;
+  pl.n_ntiles = cout / pl.BN;
+  const int tiles_mn = pl.n_mtiles * pl.n_ntiles;
+  // split K so that the grid is ~2 waves of work items, but keep >= 8 pixel tiles (512 px) per item
+  int splits = (2 * num_sms() + tiles_mn - 1) / tiles_mn;
+  const int max_splits = pl.ptiles / 8 > 0 ? pl.ptiles / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  pl.splits = splits;
+  return pl;
+}
+
+}  // namespace rpnet
+
+using namespace rpnet;
+
+RPNET_API long long rpnet_conv_wgrad_workspace_bytes(int c0, int c1, int n, int h, int w, int ntaps, int cout) {
+  if (c0 <= 0 || c0 % 64 || c1 < 0 || c1 % 64 || n <= 0 || h <= 0 || w <= 0 || ntaps < 1 || ntaps > kWgMaxTaps || cout < 64 ||
+      cout % 64) {
+    set_error("conv_wgrad_workspace_bytes: bad shape");
+    return RPNET_ERR_ARG;
+  }
+  const WgradPlan pl = plan_wgrad(c0, c1, n, h, w, ntaps, cout);
+  return (long long)pl.splits * pl.rows * cout * 4;
+}
+
+RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
+                               int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
+                               int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(x0 && dz_bf16 && grad && workspace, "conv_wgrad: null pointer argument");
+  RPNET_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0, "conv_wgrad: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
+  RPNET_REQUIRE(c1 == 0 || x1, "conv_wgrad: x1 is null but c1 = %d", c1);
+  RPNET_REQUIRE(x_bf16, "conv_wgrad: activations must be bf16 (tcgen05 kind::f16 rejects mixed fp16 x bf16 operands)");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv_wgrad: bad grid %d x %d x %d", n, h, w);
+  RPNET_REQUIRE(ntaps >= 1 && ntaps <= kWgMaxTaps, "conv_wgrad: ntaps %d out of range [1, %d]", ntaps, kWgMaxTaps);
+  RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_wgrad: cout must be a multiple of 64 (got %d)", cout);
+  RPNET_REQUIRE(hole_len >= 0 && hole_start >= 0 && hole_start + hole_len <= c0 + c1, "conv_wgrad: bad padding hole [%d, +%d)", hole_start, hole_len);
+  const WgradPlan pl = plan_wgrad(c0, c1, n, h, w, ntaps, cout);
+  const long long need = (long long)pl.splits * pl.rows * cout * 4;
+  RPNET_REQUIRE(workspace_bytes >= need, "conv_wgrad: workspace too small (%lld < %lld bytes)", workspace_bytes, need);
+
+  WgradParams p{};
+  p.N = n; p.H = h; p.W = w;
+  p.bw_log2 = ilog2(pl.bw); p.bh_log2 = ilog2(pl.bh);
+  p.tiles_x = pl.tiles_x; p.tiles_y = pl.tiles_y; p.tiles_n = pl.tiles_n; p.ptiles = pl.ptiles;
+  p.chunks0 = c0 / 64; p.chunks1 = c1 / 64;
+  p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; }
+  p.n_boxes = pl.n_boxes; p.n_mtiles = pl.n_mtiles; p.n_ntiles = pl.n_ntiles; p.splits = pl.splits;
+  p.rows = pl.rows; p.cout = cout;
+  p.x_bf16 = x_bf16 ? 1 : 0; p.dz_bf16 = 1;
+  p.partial = static_cast<float*>(workspace);
+
+  CUtensorMap tx0, tx1, tdz;
+  const uint32_t box[4] = {64u, (uint32_t)pl.bw, (uint32_t)pl.bh, (uint32_t)pl.bn};
+  {
+    const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
+    int rc = make_tmap_2b(&tx0, x0, 4, dims, str, box, x_bf16 != 0);
+    if (rc) return rc;
+  }
+  if (c1 > 0) {
+    const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
+    int rc = make_tmap_2b(&tx1, x1, 4, dims, str, box, x_bf16 != 0);
+    if (rc) return rc;
+  } else {
+    tx1 = tx0;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t str[3] = {(uint64_t)cout, (uint64_t)cout * w, (uint64_t)cout * w * h};
+    int rc = make_tmap_2b(&tdz, dz_bf16, 4, dims, str, box, true);
+    if (rc) return rc;
+  }
+  const int items = pl.n_mtiles * pl.n_ntiles * pl.splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  int rc;
+  switch (pl.BN) {
+    case 256: rc = launch_wgrad<256>(tx0, tx1, tdz, p, grid, stream); break;
+    case 128: rc = launch_wgrad<128>(tx0, tx1, tdz, p, grid, stream); break;
+    default:  rc = launch_wgrad<64>(tx0, tx1, tdz, p, grid, stream); break;
+  }
+  if (rc) return rc;
+  const long long total = (long long)pl.rows * cout;
+  long long g = (total + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.partial, grad, pl.splits, ntaps, c0 + c1, cout, hole_start, hole_len,
+                                                   accumulate);
+  return check_cuda(cudaGetLastError(), "wgrad_reduce_kernel launch");
+}

@@ -1,0 +1,770 @@
+// Training kernels of the prototype-match / refinement tail and the losses (CUDA cores, fp32 math):
+// local-correlation backward, cosine-similarity backward, the bilinear adjoint (masked-average-pool
+// weights and upsample backward), weighted pooling fwd/bwd, prototype averaging backward, dice_ce and the
+// PANet-style alignment loss pieces.  Each kernel cites the reference forward op whose gradient (taken by
+// torch autograd in the reference) it restates.
+#include "common.cuh"
+
+namespace rpnet {
+
+static int grid_for(long long total, int block, int cap_mult = 16) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * cap_mult;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward of the local correlation (Correlation, net/rp_net.py:153-181; forward in stream_kernels.cu):
+//   corr[p, a*K+b] = s * sum_c f1[p,c] * f2[p + (b-r, a-r), c]          (row offset b-r, column offset a-r)
+//   d f1[p,c]  = s * sum_{a,b} dcorr[p, a*K+b] * f2[p + (b-r, a-r), c]  (+ add[p,c]: the direct path of cat([corr, fm1]))
+//   d f2[q,c]  = s * sum_{a,b} dcorr[q - (b-r, a-r), a*K+b] * f1[q - (b-r, a-r), c]
+// dq: bf16 NHWC [n,h,w,ld]; channels [0,K*K) = dcorr, [add_off, add_off+C) = direct gradient of fm1.
+// Block = 8x16 pixel tile, 512 threads = 128 pixels x 4 groups of 8 channels; 32-channel chunks staged in smem.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kCbTH = 8, kCbTW = 16, kCbCC = 32;
+
+template <int R, int WHICH>     // WHICH 1: d f1, 2: d f2
+__global__ void __launch_bounds__(512)
+local_corr_bwd_kernel(const __half* __restrict__ f1, const __half* __restrict__ f2, const __nv_bfloat16* __restrict__ dq, int ld,
+                      int add_off, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C, float scale) {
+  constexpr int K = 2 * R + 1, KK = K * K;
+  constexpr int HW_ = kCbTW + 2 * R, HH_ = kCbTH + 2 * R, NH = HW_ * HH_;
+  extern __shared__ __align__(16) uint8_t smem_cb[];
+  // WHICH 1: dcorr of the tile, fp32 [128][KK+?]; WHICH 2: dcorr of the halo, bf16 [NH][KKP]
+  constexpr int KKP = (KK + 1) | 1;                       // odd pitch (elements)
+  float* s_dc32 = reinterpret_cast<float*>(smem_cb);
+  __nv_bfloat16* s_dc16 = reinterpret_cast<__nv_bfloat16*>(smem_cb);
+  constexpr size_t dc_bytes = WHICH == 1 ? (size_t)128 * KKP * 4 : (((size_t)NH * KKP * 2 + 15) & ~(size_t)15);
+  uint4* s_f = reinterpret_cast<uint4*>(smem_cb + dc_bytes);   // halo features [NH][4] uint4 (32 fp16 channels per pixel)
+
+  const int tiles_x = (W + kCbTW - 1) / kCbTW, tiles_y = (H + kCbTH - 1) / kCbTH;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = tx * kCbTW, y0 = ty * kCbTH;
+  const int tid = threadIdx.x;
+  const int g = tid & 3, pix = tid >> 2;
+  const int px = pix % kCbTW, py = pix / kCbTW;
+  const bool inside = (x0 + px < W) && (y0 + py < H);
+
+  if (WHICH == 1) {
+    for (int i = tid; i < 128 * KK; i += 512) {
+      const int p = i / KK, k = i % KK;
+      const int gx = x0 + p % kCbTW, gy = y0 + p / kCbTW;
+      float v = 0.f;
+      if (gx < W && gy < H) v = __bfloat162float(dq[((size_t)(n * H + gy) * W + gx) * ld + k]) * scale;
+      s_dc32[p * KKP + k] = v;
+    }
+  } else {
+    for (int i = tid; i < NH * KK; i += 512) {
+      const int p = i / KK, k = i % KK;
+      const int gx = x0 + p % HW_ - R, gy = y0 + p / HW_ - R;
+      __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H) v = dq[((size_t)(n * H + gy) * W + gx) * ld + k];
+      s_dc16[p * KKP + k] = v;
+    }
+  }
+  const __half* fsrc = WHICH == 1 ? f2 : f1;
+  for (int cc = 0; cc < C; cc += kCbCC) {
+    __syncthreads();
+    for (int i = tid; i < NH * 4; i += 512) {
+      const int part = i & 3, p = i >> 2;
+      const int gx = x0 + p % HW_ - R, gy = y0 + p / HW_ - R;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (gx >= 0 && gx < W && gy >= 0 && gy < H)
+        u = __ldg(reinterpret_cast<const uint4*>(fsrc + ((size_t)(n * H + gy) * W + gx) * C + cc + part * 8));
+      s_f[i] = u;
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int a = 0; a < K; ++a) {
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        int hp;
+        float dc;
+        if (WHICH == 1) {
+          hp = (py + b) * HW_ + (px + a);                               // p + (b-r, a-r) in halo coordinates
+          dc = s_dc32[pix * KKP + a * K + b];
+        } else {
+          hp = (py + 2 * R - b) * HW_ + (px + 2 * R - a);               // q - (b-r, a-r) in halo coordinates
+          dc = __bfloat162float(s_dc16[hp * KKP + a * K + b]);
+        }
+        float f[8];
+        unpack8_f16(s_f[hp * 4 + g], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(dc, f[j], acc[j]);
+      }
+    }
+    if (inside) {
+      const size_t o = ((size_t)(n * H + y0 + py) * W + x0 + px);
+      if (WHICH == 1) {
+        float d[8];
+        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(dq + o * ld + add_off + cc + g * 8)), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += d[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= scale;
+      }
+      *reinterpret_cast<uint4*>(out + o * C + cc + g * 8) = pack8_bf16(acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward of calDist (net/rp_net.py:353-363): pred = scaler * <x/max(|x|,eps), p/max(|p|,eps)>.
+// feat fp32 [n][hw][64]; protos fp32 [n_p][P][64] with image i using prototype set (i % n_p);
+// dpred fp32 [n][P][hw].  dfeat (=|+=), dprotos += (atomics; caller zeroes).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxP = 8;
+__global__ void __launch_bounds__(256)
+cos_sim_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ protos, const float* __restrict__ dpred, int hw, int P,
+                   int n_p, float scaler, float* __restrict__ dfeat, int accumulate, float* __restrict__ dprotos) {
+  __shared__ float s_p[kMaxP][64];
+  __shared__ float s_pn[kMaxP];
+  __shared__ float s_dp[16][kMaxP][64];
+  const int b = blockIdx.y;
+  const int pb = b % n_p;
+  for (int i = threadIdx.x; i < P * 64; i += blockDim.x) s_p[i / 64][i % 64] = protos[(size_t)pb * P * 64 + i];
+  __syncthreads();
+  if (threadIdx.x < P) {
+    float s = 0.f;
+    for (int c = 0; c < 64; ++c) s = fmaf(s_p[threadIdx.x][c], s_p[threadIdx.x][c], s);
+    s_pn[threadIdx.x] = sqrtf(s);
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  float dpa[kMaxP][4];
+#pragma unroll
+  for (int p = 0; p < kMaxP; ++p)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dpa[p][j] = 0.f;
+  for (int pix = blockIdx.x * 16 + grp; pix < hw; pix += gridDim.x * 16) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(feat + ((size_t)b * hw + pix) * 64) + sub);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float nn = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float dots[kMaxP];
+#pragma unroll
+    for (int p = 0; p < kMaxP; ++p) {
+      dots[p] = 0.f;
+      if (p < P) {
+        const float* pp = &s_p[p][sub * 4];
+        dots[p] = v.x * pp[0] + v.y * pp[1] + v.z * pp[2] + v.w * pp[3];
+      }
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
+#pragma unroll
+      for (int p = 0; p < kMaxP; ++p) dots[p] += __shfl_xor_sync(0xffffffffu, dots[p], o);
+    }
+    const float xn = sqrtf(nn);
+    const float xnc = fmaxf(xn, 1e-8f);
+    float dx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int p = 0; p < kMaxP; ++p) {
+      if (p < P) {
+        const float gp = scaler * __ldg(dpred + ((size_t)b * P + p) * hw + pix);
+        const float pn = s_pn[p], pnc = fmaxf(pn, 1e-8f);
+        const float inv = 1.f / (xnc * pnc);
+        const float kx = xn >= 1e-8f ? dots[p] / (xn * xn * xn * pnc) : 0.f;
+        const float kp = pn >= 1e-8f ? dots[p] / (xnc * pn * pn * pn) : 0.f;
+        const float* pp = &s_p[p][sub * 4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dx[j] += gp * (pp[j] * inv - kx * x[j]);
+          dpa[p][j] += gp * (x[j] * inv - kp * pp[j]);
+        }
+      }
+    }
+    float4* d = reinterpret_cast<float4*>(dfeat + ((size_t)b * hw + pix) * 64) + sub;
+    if (accumulate) {
+      const float4 o = *d;
+      *d = make_float4(o.x + dx[0], o.y + dx[1], o.z + dx[2], o.w + dx[3]);
+    } else {
+      *d = make_float4(dx[0], dx[1], dx[2], dx[3]);
+    }
+  }
+  if (dprotos) {
+#pragma unroll
+    for (int p = 0; p < kMaxP; ++p)
+      if (p < P)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_dp[grp][p][sub * 4 + j] = dpa[p][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < P * 64; i += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += s_dp[k][i / 64][i % 64];
+      atomicAdd(dprotos + (size_t)pb * P * 64 + i, s);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Adjoint of F.interpolate(., size=(H,W), mode='bilinear', align_corners=False):
+//   out[n][i][j] = sum_{Y,X} wy(Y,i) * wx(X,j) * in[n][Y][X]
+// Used (a) on the support masks: getFeatures' sum_{Y,X} up(f)*m == sum_{y,x} f * (U^T m)  (net/rp_net.py:373-376),
+// (b) as the backward of the logits upsample (net/rp_net.py:303,337).  Optional sums[n] = sum of in[n] (needs H = S*h).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilin_src(int o, float rscale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = rscale * (o + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i0 = i0 < in_size - 1 ? i0 : in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__global__ void __launch_bounds__(128)
+bilinear_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ sums, int H, int W, int h, int w) {
+  const int n = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* src = in + (size_t)n * H * W;
+  const float rsy = (float)h / (float)H, rsx = (float)w / (float)W;
+  const int sy = (H + h - 1) / h, sx = (W + w - 1) / w;
+  float own = 0.f;
+  if (o < h * w) {
+    const int i = o / w, j = o % w;
+    float acc = 0.f;
+    const int Y0 = max(0, sy * (i - 1)), Y1 = min(H, sy * (i + 2));
+    const int X0 = max(0, sx * (j - 1)), X1 = min(W, sx * (j + 2));
+    for (int Y = Y0; Y < Y1; ++Y) {
+      int i0, i1; float l0, l1;
+      bilin_src(Y, rsy, h, i0, i1, l0, l1);
+      const float wy = (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+      const bool mine_y = (Y >= sy * i) && (Y < sy * (i + 1));
+      if (wy == 0.f && !(sums && mine_y)) continue;
+      float racc = 0.f;
+      for (int X = X0; X < X1; ++X) {
+        int j0, j1; float m0, m1;
+        bilin_src(X, rsx, w, j0, j1, m0, m1);
+        const float wx = (j0 == j ? m0 : 0.f) + (j1 == j ? m1 : 0.f);
+        const float v = __ldg(src + (size_t)Y * W + X);
+        racc = fmaf(wx, v, racc);
+        if (mine_y && X >= sx * j && X < sx * (j + 1)) own += v;
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+    out[(size_t)n * h * w + o] = acc;
+  }
+  if (sums) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) own += __shfl_xor_sync(0xffffffffu, own, s);
+    if ((threadIdx.x & 31) == 0 && own != 0.f) atomicAdd(sums + n, own);
+  }
+}
+
+// out[n][k][c] = sum_p feat[n][p][c] * wmap_k[n][p] / (msum_k[n] + 1e-5), k in {0,1}   (getFeatures for fore & back mask)
+__global__ void __launch_bounds__(256)
+weighted_pool_kernel(const float* __restrict__ feat, const float* __restrict__ wmap0, const float* __restrict__ wmap1,
+                     const float* __restrict__ msum0, const float* __restrict__ msum1, float* __restrict__ out, int hw, int C) {
+  __shared__ float s_red[256];
+  const int n = blockIdx.x, k = blockIdx.y;
+  const float* wm = (k == 0 ? wmap0 : wmap1) + (size_t)n * hw;
+  const float ms = (k == 0 ? msum0 : msum1)[n];
+  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < C) {
+    const float* f = feat + (size_t)n * hw * C + c;
+    for (int o = part; o < hw; o += 4) acc = fmaf(__ldg(f + (size_t)o * C), __ldg(wm + o), acc);
+  }
+  s_red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64 && threadIdx.x < C) {
+    const float t = (s_red[threadIdx.x] + s_red[threadIdx.x + 64]) + (s_red[threadIdx.x + 128] + s_red[threadIdx.x + 192]);
+    out[((size_t)n * 2 + k) * C + threadIdx.x] = t / (ms + 1e-5f);
+  }
+}
+
+// dfeat[n][p][c] (=|+=) sum_k dout[n][k][c] * wmap_k[n][p] / (msum_k[n] + 1e-5)
+__global__ void weighted_pool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ wmap0, const float* __restrict__ wmap1,
+                                         const float* __restrict__ msum0, const float* __restrict__ msum1, float* __restrict__ dfeat,
+                                         int accumulate, int N, int hw, int C) {
+  const int c4 = C / 4;
+  const long long total = (long long)N * hw * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c4);
+    const long long np = i / c4;
+    const int n = (int)(np / hw);
+    const float w0 = __ldg(wmap0 + np) / (__ldg(msum0 + n) + 1e-5f);
+    const float w1 = __ldg(wmap1 + np) / (__ldg(msum1 + n) + 1e-5f);
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(dout + ((size_t)n * 2) * C) + v);
+    const float4 d1 = __ldg(reinterpret_cast<const float4*>(dout + ((size_t)n * 2 + 1) * C) + v);
+    float4 r = make_float4(d0.x * w0 + d1.x * w1, d0.y * w0 + d1.y * w1, d0.z * w0 + d1.z * w1, d0.w * w0 + d1.w * w1);
+    float4* d = reinterpret_cast<float4*>(dfeat) + i;
+    if (accumulate) { const float4 o = *d; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+    *d = r;
+  }
+}
+
+// Backward of getPrototype (net/rp_net.py:379-391): draw[w][s][b][0=fg] = dprotos[b][1+w]/Sh, [1=bg] = dprotos[b][0]/(Sh*Wa)
+__global__ void proto_finalize_bwd_kernel(const float* __restrict__ dprotos, float* __restrict__ draw, int Wa, int Sh, int B, int C) {
+  const long long total = (long long)Wa * Sh * B * 2 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int k = (int)((i / C) % 2);
+    const int b = (int)((i / (2 * C)) % B);
+    const int w = (int)(i / ((long long)2 * C * B * Sh));
+    draw[i] = k == 0 ? dprotos[((size_t)b * (1 + Wa) + 1 + w) * C + c] / (float)Sh
+                     : dprotos[((size_t)b * (1 + Wa)) * C + c] / (float)(Sh * Wa);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dice_ce (net/rp_net.py:87-127), multi-class branch, for G independent logit tensors that share the labels:
+//   loss_g = 1 - mean_k( 2 I_k / (Card_k + eps) ) + mean_pix( -log softmax(logits)[label] )
+// logits fp32 [G][B][P][HW], labels int64 [B][HW].  sums[g] = {I_0..I_{P-1}, Card_0..Card_{P-1}, ce_sum}.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dice_ce_reduce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int P, long long HW,
+                      float* __restrict__ sums) {
+  __shared__ float s_red[8][2 * kMaxP + 1];
+  const int g = blockIdx.y;
+  const float* lg = logits + (size_t)g * B * P * HW;
+  float I[kMaxP], Cd[kMaxP], ce = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxP; ++k) { I[k] = 0.f; Cd[k] = 0.f; }
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, pix = i % HW;
+    const int lab = (int)__ldg(labels + i);
+    float v[kMaxP], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) { v[k] = __ldg(lg + ((size_t)b * P + k) * HW + pix); mx = fmaxf(mx, v[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) { v[k] = expf(v[k] - mx); den += v[k]; }
+    const float inv = 1.f / den;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) {
+        const float pk = v[k] * inv;
+        const float oh = (k == lab) ? 1.f : 0.f;
+        I[k] += pk * oh;
+        Cd[k] += pk + oh;
+        if (k == lab) ce -= logf(fmaxf(pk, 1e-38f));
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kMaxP; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      I[k] += __shfl_xor_sync(0xffffffffu, I[k], o);
+      Cd[k] += __shfl_xor_sync(0xffffffffu, Cd[k], o);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ce += __shfl_xor_sync(0xffffffffu, ce, o);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k) { s_red[warp][k] = I[k]; s_red[warp][kMaxP + k] = Cd[k]; }
+    s_red[warp][2 * kMaxP] = ce;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMaxP + 1) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += s_red[wv][threadIdx.x];
+    const int k = threadIdx.x;
+    if (k < kMaxP) { if (k < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + k, s); }
+    else if (k < 2 * kMaxP) { if (k - kMaxP < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + P + (k - kMaxP), s); }
+    else atomicAdd(sums + (size_t)g * (2 * P + 1) + 2 * P, s);
+  }
+}
+
+// dlogits = grad_scale * d loss_g / d logits;  loss[g] written by block (0, g).
+__global__ void __launch_bounds__(256)
+dice_ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ sums, int B,
+                    int P, long long HW, float eps, float grad_scale, float* __restrict__ dlogits, float* __restrict__ loss) {
+  const int g = blockIdx.y;
+  const float* lg = logits + (size_t)g * B * P * HW;
+  float* dl = dlogits + (size_t)g * B * P * HW;
+  const float* sm = sums + (size_t)g * (2 * P + 1);
+  const float npix = (float)((long long)B * HW);
+  float cA[kMaxP], cB[kMaxP];        // d dice / d p_k = -(1/P) * (2 oh_k / (Card_k+eps) - 2 I_k / (Card_k+eps)^2) = oh_k * cA[k] + cB[k]
+  float dice = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxP; ++k) {
+    cA[k] = 0.f; cB[k] = 0.f;
+    if (k < P) {
+      const float I = sm[k], Cd = sm[P + k] + eps;
+      cA[k] = -2.f / (Cd * (float)P);
+      cB[k] = 2.f * I / (Cd * Cd * (float)P);
+      dice += 2.f * I / Cd;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[g] = 1.f - dice / (float)P + sm[2 * P] / npix;
+  const long long total = dlogits ? (long long)B * HW : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, pix = i % HW;
+    const int lab = (int)__ldg(labels + i);
+    float v[kMaxP], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) { v[k] = __ldg(lg + ((size_t)b * P + k) * HW + pix); mx = fmaxf(mx, v[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) { v[k] = expf(v[k] - mx); den += v[k]; }
+    const float inv = 1.f / den;
+    float dot = 0.f, gk[kMaxP];
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) {
+        v[k] *= inv;
+        gk[k] = ((k == lab) ? cA[k] : 0.f) + cB[k];
+        dot += gk[k] * v[k];
+      }
+#pragma unroll
+    for (int k = 0; k < kMaxP; ++k)
+      if (k < P) {
+        const float oh = (k == lab) ? 1.f : 0.f;
+        dl[((size_t)b * P + k) * HW + pix] = grad_scale * (v[k] * (gk[k] - dot) + (v[k] - oh) / npix);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Alignment loss pieces (alignLoss, net/rp_net.py:394-440).
+// (1) class_pool: argmax over the low-resolution prediction -> per-class masked average of the query features.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+class_pool_kernel(const float* __restrict__ feat /*[B][hw][64]*/, const float* __restrict__ pred /*[B][P][hw]*/, int hw, int P,
+                  float* __restrict__ qproto /*[B][P][64]*/, float* __restrict__ counts /*[B][P]*/, int* __restrict__ amax /*[B][hw]*/) {
+  __shared__ float s_acc[4][kMaxP][64];
+  __shared__ float s_cnt[kMaxP];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 4 * kMaxP * 64; i += 256) (&s_acc[0][0][0])[i] = 0.f;
+  if (threadIdx.x < kMaxP) s_cnt[threadIdx.x] = 0.f;
+  __syncthreads();
+  for (int p = threadIdx.x; p < hw; p += 256) {
+    int best = 0;
+    float bv = __ldg(pred + ((size_t)b * P) * hw + p);
+    for (int k = 1; k < P; ++k) {
+      const float v = __ldg(pred + ((size_t)b * P + k) * hw + p);
+      if (v > bv) { bv = v; best = k; }
+    }
+    amax[(size_t)b * hw + p] = best;
+    atomicAdd(&s_cnt[best], 1.f);
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  for (int p = part; p < hw; p += 4) {
+    const int k = amax[(size_t)b * hw + p];
+    s_acc[part][k][c] += __ldg(feat + ((size_t)b * hw + p) * 64 + c);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P * 64; i += 256) {
+    const int k = i / 64, cc = i % 64;
+    const float t = (s_acc[0][k][cc] + s_acc[1][k][cc]) + (s_acc[2][k][cc] + s_acc[3][k][cc]);
+    qproto[((size_t)b * P + k) * 64 + cc] = t / (s_cnt[k] + 1e-5f);
+  }
+  if (threadIdx.x < P) counts[(size_t)b * P + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+__global__ void class_pool_bwd_kernel(const float* __restrict__ dqproto, const float* __restrict__ counts, const int* __restrict__ amax,
+                                      int B, int hw, int P, float* __restrict__ dfeat) {
+  const long long total = (long long)B * hw * 16;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i & 15);
+    const long long bp = i >> 4;
+    const int b = (int)(bp / hw);
+    const int k = amax[bp];
+    const float inv = 1.f / (counts[(size_t)b * P + k] + 1e-5f);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dqproto + ((size_t)b * P + k) * 64) + v);
+    float4* o = reinterpret_cast<float4*>(dfeat) + i;
+    const float4 cur = *o;
+    *o = make_float4(cur.x + d.x * inv, cur.y + d.y * inv, cur.z + d.z * inv, cur.w + d.w * inv);
+  }
+}
+
+// (2) per support image (w, s, b): prototype pair [query bg proto, query fg_w proto] and the loss weight
+//     active(w, b) * scaler / (Sh * Wa * B)   (skip_ways: a way whose class is absent from the prediction, :414).
+__global__ void align_gather_kernel(const float* __restrict__ qproto, const float* __restrict__ counts, int Wa, int Sh, int B, float scaler,
+                                    float* __restrict__ protos_s /*[Wa][Sh][B][2][64]*/, float* __restrict__ weight /*[Wa][Sh][B]*/) {
+  const int total = Wa * Sh * B * 2 * 64;
+  const int P = 1 + Wa;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % 64, k = (i / 64) % 2, b = (i / 128) % B, w = i / (128 * B * Sh);
+    protos_s[i] = qproto[((size_t)b * P + (k == 0 ? 0 : w + 1)) * 64 + c];
+    if (c == 0 && k == 0) weight[i / 128] = (counts[(size_t)b * P + w + 1] > 0.f ? 1.f : 0.f) * scaler / (float)(Sh * Wa * B);
+  }
+}
+
+__global__ void align_scatter_kernel(const float* __restrict__ dprotos_s, int Wa, int Sh, int B, float* __restrict__ dqproto /*[B][P][64]*/) {
+  const int P = 1 + Wa;
+  const int total = B * P * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % 64, k = (i / 64) % P, b = i / (64 * P);
+    float s = 0.f;
+    for (int w = 0; w < Wa; ++w) {
+      if (k != 0 && k != w + 1) continue;
+      for (int sh = 0; sh < Sh; ++sh) s += dprotos_s[((((size_t)w * Sh + sh) * B + b) * 2 + (k == 0 ? 0 : 1)) * 64 + c];
+    }
+    dqproto[i] = s;
+  }
+}
+
+// (3) cross entropy with ignore_index over 2-class logits [n][2][HW]; label 1 where fore == 1, else 0 where back == 1,
+//     else ignored (net/rp_net.py:432-438).  sums[n] = {sum nll, valid count}.
+__global__ void __launch_bounds__(256)
+ce_mask_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ fore, const float* __restrict__ back, long long HW,
+                      float* __restrict__ sums) {
+  __shared__ float s_red[8][2];
+  const int n = blockIdx.y;
+  float nll = 0.f, cnt = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float f = __ldg(fore + (size_t)n * HW + i), bk = __ldg(back + (size_t)n * HW + i);
+    const int lab = (f == 1.f) ? 1 : ((bk == 1.f) ? 0 : 255);
+    if (lab == 255) continue;
+    const float l0 = __ldg(logits + ((size_t)n * 2) * HW + i), l1 = __ldg(logits + ((size_t)n * 2 + 1) * HW + i);
+    const float mx = fmaxf(l0, l1);
+    const float lse = mx + logf(expf(l0 - mx) + expf(l1 - mx));
+    nll += lse - (lab ? l1 : l0);
+    cnt += 1.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nll += __shfl_xor_sync(0xffffffffu, nll, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = nll; s_red[threadIdx.x >> 5][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += s_red[wv][threadIdx.x];
+    atomicAdd(sums + (size_t)n * 2 + threadIdx.x, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_mask_grad_kernel(const float* __restrict__ logits, const float* __restrict__ fore, const float* __restrict__ back,
+                    const float* __restrict__ sums, const float* __restrict__ weight, int N, long long HW, float grad_scale,
+                    float* __restrict__ dlogits, float* __restrict__ loss) {
+  const int n = blockIdx.y;
+  const float cnt = sums[(size_t)n * 2 + 1];
+  const float wgt = weight[n];
+  const float k = (cnt > 0.f) ? grad_scale * wgt / cnt : 0.f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && loss) {
+    float s = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float c = sums[(size_t)i * 2 + 1];
+      if (weight[i] != 0.f && c > 0.f) s += weight[i] * sums[(size_t)i * 2] / c;
+    }
+    *loss = s;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+    const float f = __ldg(fore + (size_t)n * HW + i), bk = __ldg(back + (size_t)n * HW + i);
+    const int lab = (f == 1.f) ? 1 : ((bk == 1.f) ? 0 : 255);
+    float d0 = 0.f, d1 = 0.f;
+    if (lab != 255 && k != 0.f) {
+      const float l0 = __ldg(logits + ((size_t)n * 2) * HW + i), l1 = __ldg(logits + ((size_t)n * 2 + 1) * HW + i);
+      const float mx = fmaxf(l0, l1);
+      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+      const float inv = 1.f / (e0 + e1);
+      d0 = k * (e0 * inv - (lab == 0 ? 1.f : 0.f));
+      d1 = k * (e1 * inv - (lab == 1 ? 1.f : 0.f));
+    }
+    dlogits[((size_t)n * 2) * HW + i] = d0;
+    dlogits[((size_t)n * 2 + 1) * HW + i] = d1;
+  }
+}
+
+// Plain bilinear upsample of fp32 maps [n][h][w] -> [n][h*S][w*S] (align loss: supp_pred upsample, :430)
+__global__ void bilinear_up_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int h, int w, int H, int W) {
+  const long long total = (long long)N * H * W;
+  const float rsy = (float)h / (float)H, rsx = (float)w / (float)W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)((i / W) % H);
+    const long long n = i / ((long long)W * H);
+    int i0, i1, j0, j1; float ly0, ly1, lx0, lx1;
+    bilin_src(Y, rsy, h, i0, i1, ly0, ly1);
+    bilin_src(X, rsx, w, j0, j1, lx0, lx1);
+    const float* s = in + n * h * w;
+    out[i] = ly0 * (lx0 * __ldg(s + i0 * w + j0) + lx1 * __ldg(s + i0 * w + j1)) +
+             ly1 * (lx0 * __ldg(s + i1 * w + j0) + lx1 * __ldg(s + i1 * w + j1));
+  }
+}
+
+}  // namespace rpnet
+
+using namespace rpnet;
+
+template <int R>
+static int launch_corr_bwd(const void* f1, const void* f2, const void* dq, int ld, int add_off, void* df1, void* df2, int n, int h,
+                           int w, int c, cudaStream_t stream) {
+  constexpr int K = 2 * R + 1, KK = K * K, KKP = (KK + 1) | 1;
+  constexpr int NH = (kCbTW + 2 * R) * (kCbTH + 2 * R);
+  const size_t smem1 = (size_t)128 * KKP * 4 + (size_t)NH * 64;
+  const size_t smem2 = (((size_t)NH * KKP * 2 + 15) & ~(size_t)15) + (size_t)NH * 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(local_corr_bwd_kernel<R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    RPNET_CUDA_OK(cudaFuncSetAttribute(local_corr_bwd_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    attr_set = true;
+  }
+  const int tiles = ((w + kCbTW - 1) / kCbTW) * ((h + kCbTH - 1) / kCbTH) * n;
+  const float scale = 1.0f / sqrtf((float)c);
+  local_corr_bwd_kernel<R, 1><<<tiles, 512, smem1, stream>>>(static_cast<const __half*>(f1), static_cast<const __half*>(f2),
+                                                             static_cast<const __nv_bfloat16*>(dq), ld, add_off,
+                                                             static_cast<__nv_bfloat16*>(df1), n, h, w, c, scale);
+  RPNET_CUDA_OK(cudaGetLastError());
+  local_corr_bwd_kernel<R, 2><<<tiles, 512, smem2, stream>>>(static_cast<const __half*>(f1), static_cast<const __half*>(f2),
+                                                             static_cast<const __nv_bfloat16*>(dq), ld, add_off,
+                                                             static_cast<__nv_bfloat16*>(df2), n, h, w, c, scale);
+  return check_cuda(cudaGetLastError(), "local_corr_bwd launch");
+}
+
+RPNET_API int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const void* dq_bf16, int ld, int add_off, void* df1_bf16,
+                                    void* df2_bf16, int n, int h, int w, int c, int radius, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(f1_f16 && f2_f16 && dq_bf16 && df1_bf16 && df2_bf16, "local_corr_bwd: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % kCbCC == 0, "local_corr_bwd: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  const int k = 2 * radius + 1;
+  RPNET_REQUIRE(ld % 8 == 0 && add_off % 8 == 0 && add_off >= k * k && add_off + c <= ld,
+                "local_corr_bwd: bad gradient layout ld=%d add_off=%d", ld, add_off);
+  switch (radius) {
+    case 1: return launch_corr_bwd<1>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
+    case 2: return launch_corr_bwd<2>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
+    case 3: return launch_corr_bwd<3>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
+    case 4: return launch_corr_bwd<4>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
+    case 5: return launch_corr_bwd<5>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
+    default:
+      set_error("local_corr_bwd: radius %d not supported (1..5)", radius);
+      return RPNET_ERR_ARG;
+  }
+}
+
+RPNET_API int rpnet_cos_sim_bwd_f32(const float* feat, const float* protos, const float* dpred, int n, int hw, int c, int n_protos,
+                                     int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(feat && protos && dpred && dfeat, "cos_sim_bwd: null pointer argument");
+  RPNET_REQUIRE(c == 64, "cos_sim_bwd: feature width must be 64 (got %d)", c);
+  RPNET_REQUIRE(n_protos >= 1 && n_protos <= kMaxP, "cos_sim_bwd: n_protos %d out of range [1, %d]", n_protos, kMaxP);
+  RPNET_REQUIRE(n > 0 && hw > 0 && proto_sets > 0 && n % proto_sets == 0, "cos_sim_bwd: bad shape n=%d sets=%d", n, proto_sets);
+  int bx = (hw + 16 * 8 - 1) / (16 * 8);
+  if (bx < 1) bx = 1;
+  cos_sim_bwd_kernel<<<dim3(bx, n), 256, 0, stream>>>(feat, protos, dpred, hw, n_protos, proto_sets, scaler, dfeat, accumulate, dprotos);
+  return check_cuda(cudaGetLastError(), "cos_sim_bwd launch");
+}
+
+RPNET_API int rpnet_bilinear_adjoint_f32(const float* in, float* out, float* sums, int n, int in_h, int in_w, int out_h, int out_w,
+                                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(in && out, "bilinear_adjoint: null pointer argument");
+  RPNET_REQUIRE(n > 0 && out_h > 0 && out_w > 0 && in_h >= out_h && in_w >= out_w, "bilinear_adjoint: bad shape");
+  RPNET_REQUIRE(!sums || (in_h % out_h == 0 && in_w % out_w == 0), "bilinear_adjoint: sums need an integer scale");
+  if (sums) RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)n * sizeof(float), stream));
+  bilinear_adjoint_kernel<<<dim3((out_h * out_w + 127) / 128, n), 128, 0, stream>>>(in, out, sums, in_h, in_w, out_h, out_w);
+  return check_cuda(cudaGetLastError(), "bilinear_adjoint launch");
+}
+
+RPNET_API int rpnet_weighted_pool_f32(const float* feat, const float* wmap0, const float* wmap1, const float* msum0, const float* msum1,
+                                       float* out, int n, int hw, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(feat && wmap0 && wmap1 && msum0 && msum1 && out, "weighted_pool: null pointer argument");
+  RPNET_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= 64, "weighted_pool: bad shape n=%d hw=%d c=%d (c <= 64)", n, hw, c);
+  weighted_pool_kernel<<<dim3(n, 2), 256, 0, stream>>>(feat, wmap0, wmap1, msum0, msum1, out, hw, c);
+  return check_cuda(cudaGetLastError(), "weighted_pool launch");
+}
+
+RPNET_API int rpnet_weighted_pool_bwd_f32(const float* dout, const float* wmap0, const float* wmap1, const float* msum0,
+                                           const float* msum1, float* dfeat, int accumulate, int n, int hw, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dout && wmap0 && wmap1 && msum0 && msum1 && dfeat, "weighted_pool_bwd: null pointer argument");
+  RPNET_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 4 == 0, "weighted_pool_bwd: bad shape");
+  weighted_pool_bwd_kernel<<<grid_for((long long)n * hw * (c / 4), 256), 256, 0, stream>>>(dout, wmap0, wmap1, msum0, msum1, dfeat,
+                                                                                          accumulate, n, hw, c);
+  return check_cuda(cudaGetLastError(), "weighted_pool_bwd launch");
+}
+
+RPNET_API int rpnet_proto_finalize_bwd_f32(const float* dprotos, float* draw, int ways, int shots, int batch, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dprotos && draw, "proto_finalize_bwd: null pointer argument");
+  RPNET_REQUIRE(ways > 0 && shots > 0 && batch > 0 && c > 0, "proto_finalize_bwd: bad shape");
+  proto_finalize_bwd_kernel<<<grid_for((long long)ways * shots * batch * 2 * c, 256), 256, 0, stream>>>(dprotos, draw, ways, shots, batch, c);
+  return check_cuda(cudaGetLastError(), "proto_finalize_bwd launch");
+}
+
+RPNET_API int rpnet_dice_ce_f32(const float* logits, const long long* labels, int groups, int batch, int n_classes, long long hw,
+                                 float eps, float grad_scale, float* sums, float* dlogits, float* loss, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(logits && labels && sums && loss, "dice_ce: null pointer argument");
+  RPNET_REQUIRE(groups > 0 && batch > 0 && hw > 0 && n_classes >= 2 && n_classes <= kMaxP, "dice_ce: bad shape (classes 2..%d)", kMaxP);
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * (2 * n_classes + 1) * sizeof(float), stream));
+  int bx = grid_for((long long)batch * hw, 256 * 4, 8);
+  bx = (bx + groups - 1) / groups;
+  if (bx < 1) bx = 1;
+  dice_ce_reduce_kernel<<<dim3(bx, groups), 256, 0, stream>>>(logits, labels, batch, n_classes, hw, sums);
+  RPNET_CUDA_OK(cudaGetLastError());
+  if (dlogits) {
+    dice_ce_grad_kernel<<<dim3(bx, groups), 256, 0, stream>>>(logits, labels, sums, batch, n_classes, hw, eps, grad_scale, dlogits, loss);
+  } else {
+    dice_ce_grad_kernel<<<dim3(1, groups), 32, 0, stream>>>(logits, labels, sums, batch, n_classes, hw, eps, grad_scale, nullptr, loss);
+  }
+  return check_cuda(cudaGetLastError(), "dice_ce launch");
+}
+
+RPNET_API int rpnet_class_pool_f32(const float* feat, const float* pred, int batch, int hw, int c, int n_classes, float* qproto,
+                                    float* counts, void* amax_i32, void* stream_) {
+  int* amax = static_cast<int*>(amax_i32);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(feat && pred && qproto && counts && amax, "class_pool: null pointer argument");
+  RPNET_REQUIRE(c == 64 && n_classes >= 1 && n_classes <= kMaxP && batch > 0 && hw > 0, "class_pool: bad shape (c == 64)");
+  class_pool_kernel<<<batch, 256, 0, stream>>>(feat, pred, hw, n_classes, qproto, counts, amax);
+  return check_cuda(cudaGetLastError(), "class_pool launch");
+}
+
+RPNET_API int rpnet_class_pool_bwd_f32(const float* dqproto, const float* counts, const void* amax_i32, int batch, int hw, int c,
+                                        int n_classes, float* dfeat, void* stream_) {
+  const int* amax = static_cast<const int*>(amax_i32);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dqproto && counts && amax && dfeat, "class_pool_bwd: null pointer argument");
+  RPNET_REQUIRE(c == 64 && batch > 0 && hw > 0 && n_classes >= 1, "class_pool_bwd: bad shape (c == 64)");
+  class_pool_bwd_kernel<<<grid_for((long long)batch * hw * 16, 256), 256, 0, stream>>>(dqproto, counts, amax, batch, hw, n_classes, dfeat);
+  return check_cuda(cudaGetLastError(), "class_pool_bwd launch");
+}
+
+RPNET_API int rpnet_align_gather_f32(const float* qproto, const float* counts, int ways, int shots, int batch, float scaler,
+                                      float* protos_s, float* weight, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(qproto && counts && protos_s && weight, "align_gather: null pointer argument");
+  RPNET_REQUIRE(ways > 0 && shots > 0 && batch > 0, "align_gather: bad shape");
+  align_gather_kernel<<<grid_for((long long)ways * shots * batch * 128, 256), 256, 0, stream>>>(qproto, counts, ways, shots, batch, scaler,
+                                                                                              protos_s, weight);
+  return check_cuda(cudaGetLastError(), "align_gather launch");
+}
+
+RPNET_API int rpnet_align_scatter_f32(const float* dprotos_s, int ways, int shots, int batch, float* dqproto, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dprotos_s && dqproto, "align_scatter: null pointer argument");
+  RPNET_REQUIRE(ways > 0 && shots > 0 && batch > 0, "align_scatter: bad shape");
+  align_scatter_kernel<<<grid_for((long long)batch * (1 + ways) * 64, 256), 256, 0, stream>>>(dprotos_s, ways, shots, batch, dqproto);
+  return check_cuda(cudaGetLastError(), "align_scatter launch");
+}
+
+RPNET_API int rpnet_ce_mask_f32(const float* logits, const float* fore, const float* back, const float* weight, int n, long long hw,
+                                 float grad_scale, float* sums, float* dlogits, float* loss, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(logits && fore && back && weight && sums && loss, "ce_mask: null pointer argument");
+  RPNET_REQUIRE(n > 0 && hw > 0, "ce_mask: bad shape");
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)n * 2 * sizeof(float), stream));
+  int bx = grid_for(hw, 256 * 4, 2);
+  ce_mask_reduce_kernel<<<dim3(bx, n), 256, 0, stream>>>(logits, fore, back, hw, sums);
+  RPNET_CUDA_OK(cudaGetLastError());
+  if (dlogits) ce_mask_grad_kernel<<<dim3(bx, n), 256, 0, stream>>>(logits, fore, back, sums, weight, n, hw, grad_scale, dlogits, loss);
+  else         ce_mask_grad_kernel<<<dim3(1, 1), 32, 0, stream>>>(logits, fore, back, sums, weight, n, 0, grad_scale, nullptr, loss);
+  return check_cuda(cudaGetLastError(), "ce_mask launch");
+}
+
+RPNET_API int rpnet_bilinear_up_f32(const float* in, float* out, int n, int h, int w, int out_h, int out_w, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(in && out, "bilinear_up: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && out_h >= h && out_w >= w, "bilinear_up: bad shape");
+  bilinear_up_kernel<<<grid_for((long long)n * out_h * out_w, 256), 256, 0, stream>>>(in, out, n, h, w, out_h, out_w);
+  return check_cuda(cudaGetLastError(), "bilinear_up launch");
+}

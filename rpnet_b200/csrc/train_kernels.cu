@@ -1,0 +1,619 @@
+// Train-mode streaming kernels of the RP-Net conv stacks (HBM-bound, CUDA cores): batch-statistics
+// BatchNorm2d (+ReLU, + fused 2x2 max-pool) forward and backward, weight packing, nearest x2 upsample,
+// pre-mask backward, the Cin=1 first-conv weight gradient and the fused Adam step.
+// The reference trains through torch autograd over nn.BatchNorm2d / nn.ReLU / nn.MaxPool2d / nn.Upsample
+// (net/modules.py:42-75, net/unet.py:435-467); these kernels restate those ops' forward/backward on
+// NHWC fp16 activations and NHWC bf16 activation gradients.
+//
+// BatchNorm call groups: images [start[g], start[g+1]) of a batched launch form one BatchNorm *call* of the
+// reference (own batch statistics, own running-stat update — SURVEY D14).
+#include "common.cuh"
+
+namespace rpnet {
+
+constexpr int kMaxGroups = 64;
+struct Groups {
+  int G;
+  int start[kMaxGroups + 1];
+};
+__device__ __forceinline__ int group_of(const Groups& gr, int n) {
+  int g = 0;
+  while (g + 1 < gr.G && n >= gr.start[g + 1]) ++g;
+  return g;
+}
+
+static int make_groups(Groups* gr, const int* group_start, int groups, int n) {
+  RPNET_REQUIRE(groups >= 1 && groups <= kMaxGroups && group_start, "bn: groups %d out of range [1, %d]", groups, kMaxGroups);
+  gr->G = groups;
+  for (int g = 0; g <= groups; ++g) gr->start[g] = group_start[g];
+  RPNET_REQUIRE(gr->start[0] == 0 && gr->start[groups] == n, "bn: group_start must span [0, %d]", n);
+  for (int g = 0; g < groups; ++g) RPNET_REQUIRE(gr->start[g + 1] > gr->start[g], "bn: empty BatchNorm call group %d", g);
+  return 0;
+}
+
+static int grid_for(long long total, int block, int cap_mult = 16) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * cap_mult;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bn_stats: per (call group, channel) sum and sum of squares of the raw conv output z (fp16 NHWC).
+// Block = (C/8) channel vectors x (256 / (C/8)) pixel lanes; fp32 per-thread partials, shared-memory
+// tree over the pixel lanes, one atomicAdd per channel per block.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, float* __restrict__ sums /*[G][C][2]*/) {
+  __shared__ float s_red[256 * 16];
+  const int g = blockIdx.y;
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const long long p0 = (long long)gr.start[g] * HW, p1 = (long long)gr.start[g + 1] * HW;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (long long p = p0 + (long long)blockIdx.x * lanes + pl; p < p1; p += (long long)gridDim.x * lanes) {
+    float f[8];
+    unpack8_f16(__ldg(z + p * c8 + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  __syncthreads();
+  for (int s = lanes >> 1; s > 0; s >>= 1) {
+    if (pl < s) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s_red[threadIdx.x * 16 + j] += s_red[(threadIdx.x + s * c8) * 16 + j];
+    }
+    __syncthreads();
+  }
+  if (pl == 0) {
+    float* dst = sums + ((size_t)g * c8 * 8 + v * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
+      atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+    }
+  }
+}
+
+// bn_finalize: mean / rstd / folded (a, b) per (group, channel) + the running-statistics update of
+// nn.BatchNorm2d (momentum, unbiased running_var), applied once per call group IN ORDER.  `conv_bias` is the
+// bias the conv kernel dropped (it cancels inside train-mode BN but belongs to the running mean).
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, Groups gr, int C, int HW, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
+                                   float* running_mean, float* running_var, long long* num_batches_tracked,
+                                   float* __restrict__ stats /*[G][C][4]*/) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += gr.G;
+  if (c >= C) return;
+  float rm = running_mean ? running_mean[c] : 0.f, rv = running_var ? running_var[c] : 0.f;
+  const float ga = gamma[c], be = beta[c], cb = conv_bias ? conv_bias[c] : 0.f;
+  for (int g = 0; g < gr.G; ++g) {
+    const float cnt = (float)(gr.start[g + 1] - gr.start[g]) * (float)HW;
+    const float mean = sums[((size_t)g * C + c) * 2] / cnt;
+    float var = sums[((size_t)g * C + c) * 2 + 1] / cnt - mean * mean;
+    var = var > 0.f ? var : 0.f;
+    const float rstd = rsqrtf(var + eps);
+    float* st = stats + ((size_t)g * C + c) * 4;
+    st[0] = mean; st[1] = rstd; st[2] = rstd * ga; st[3] = be - mean * rstd * ga;
+    rm = (1.f - momentum) * rm + momentum * (mean + cb);
+    rv = (1.f - momentum) * rv + momentum * (cnt > 1.f ? var * cnt / (cnt - 1.f) : var);
+  }
+  if (running_mean) running_mean[c] = rm;
+  if (running_var) running_var[c] = rv;
+}
+
+// bn_apply: y = act(a * z + b) -> fp16 NHWC (optional), fp32 NHWC (optional), 2x2 max-pooled fp16 (optional).
+template <bool POOL>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Groups gr, int N, int H, int W, int c8, int relu,
+                uint4* __restrict__ y16, float* __restrict__ y32, uint4* __restrict__ ypool) {
+  const int C = c8 * 8;
+  const int Hs = POOL ? H / 2 : H, Ws = POOL ? W / 2 : W;
+  const long long total = (long long)N * Hs * Ws * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long t = i / c8;
+    const int xs = (int)(t % Ws);  t /= Ws;
+    const int ys = (int)(t % Hs);
+    const int n = (int)(t / Hs);
+    const int g = group_of(gr, n);
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+      a[j] = st.z; b[j] = st.w;
+    }
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
+      const int y = POOL ? ys * 2 + (q >> 1) : ys, x = POOL ? xs * 2 + (q & 1) : xs;
+      const long long pix = ((long long)n * H + y) * W + x;
+      float f[8];
+      unpack8_f16(__ldg(z + pix * c8 + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float r = fmaf(f[j], a[j], b[j]);
+        r = relu ? fmaxf(r, 0.f) : r;
+        f[j] = r;
+        best[j] = fmaxf(best[j], r);
+      }
+      if (y16) y16[pix * c8 + v] = pack8_f16(f);
+      if (y32) {
+        float4* d = reinterpret_cast<float4*>(y32 + (pix * c8 + v) * 8);
+        d[0] = make_float4(f[0], f[1], f[2], f[3]);
+        d[1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    }
+    if (POOL) ypool[i] = pack8_f16(best);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BatchNorm + ReLU (+ max-pool / nearest-upsample consumers) backward.
+// The gradient w.r.t. the activation y = relu(a*z+b) arrives from up to three places:
+//   direct : bf16 (or fp32) NHWC [n,h,w] with pixel pitch d_ld, channel offset d_off  (next conv's dgrad / concat slice)
+//   pooled : bf16 NHWC [n,h/2,w/2]: gradient of the 2x2 max-pooled copy, routed to the FIRST max of the window
+//            (nn.MaxPool2d backward; y is recomputed from z so the argmax is the forward's)
+//   up     : bf16 NHWC [n,2h,2w]: gradient of the nearest x2 upsampled copy, summed over its 2x2 block.
+// ---------------------------------------------------------------------------------------------------
+struct GradSrc {
+  const void* direct; int d_ld, d_off, d_f32;
+  const __nv_bfloat16* pooled; int p_ld, p_off;
+  const __nv_bfloat16* up; int u_ld, u_off;
+};
+
+__device__ __forceinline__ void load_grad8(const GradSrc& s, int n, int y, int x, int H, int W, int c, float* g) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  const long long pix = ((long long)n * H + y) * W + x;
+  if (s.direct) {
+    if (s.d_f32) {
+      const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(s.direct) + pix * s.d_ld + s.d_off + c);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+    } else {
+      unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(s.direct) + pix * s.d_ld + s.d_off + c)), g);
+    }
+  }
+  if (s.up) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long up = ((long long)n * (2 * H) + 2 * y + (q >> 1)) * (2 * W) + 2 * x + (q & 1);
+      float t[8];
+      unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(s.up + up * s.u_ld + s.u_off + c)), t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += t[j];
+    }
+  }
+}
+
+// Work unit: one 2x2 pixel window (WIN) or one pixel (!WIN) x 8 channels.  MODE 0: reduce (sum dy_hat, sum dy_hat*x_hat
+// per group/channel); MODE 1: apply (write dz).
+template <bool WIN, int MODE>
+__global__ void __launch_bounds__(256)
+bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N, int H,
+              int W, int c8, int relu, GradSrc src, float* __restrict__ sums, uint4* __restrict__ dz) {
+  __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
+  const int C = c8 * 8;
+  const int Hs = WIN ? H / 2 : H, Ws = WIN ? W / 2 : W;
+  // MODE 0: grid = (blocks, G): a block stays inside one call group so that its partial sums are per group
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  int n_begin = 0, n_end = N;
+  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
+  const long long units = (long long)(n_end - n_begin) * Hs * Ws;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (long long u = (long long)blockIdx.x * lanes + pl; u < units; u += (long long)gridDim.x * lanes) {
+    long long t = u;
+    const int xs = (int)(t % Ws);  t /= Ws;
+    const int ys = (int)(t % Hs);
+    const int n = n_begin + (int)(t / Hs);
+    const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, n);
+    float mean[8], rstd[8], a[8], b[8], m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+      mean[j] = st.x; rstd[j] = st.y; a[j] = st.z; b[j] = st.w;
+      if (MODE == 1) {
+        const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);
+        m1[j] = cf.x; m2[j] = cf.y;
+      }
+    }
+    float zf[WIN ? 4 : 1][8];
+    int win_arg[8];
+    float pg[8];
+    if (WIN) {
+      float best[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; win_arg[j] = 0; }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long pix = ((long long)n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1);
+        unpack8_f16(__ldg(z + pix * c8 + v), zf[q]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float r = fmaf(zf[q][j], a[j], b[j]);
+          r = relu ? fmaxf(r, 0.f) : r;
+          if (r > best[j]) { best[j] = r; win_arg[j] = q; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pg[j] = 0.f;
+      if (src.pooled) {
+        const long long pp = ((long long)n * Hs + ys) * Ws + xs;
+        unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(src.pooled + pp * src.p_ld + src.p_off + v * 8)), pg);
+      }
+    } else {
+      const long long pix = ((long long)n * H + ys) * W + xs;
+      unpack8_f16(__ldg(z + pix * c8 + v), zf[0]);
+    }
+#pragma unroll
+    for (int q = 0; q < (WIN ? 4 : 1); ++q) {
+      const int y = WIN ? ys * 2 + (q >> 1) : ys, x = WIN ? xs * 2 + (q & 1) : xs;
+      float gy[8];
+      load_grad8(src, n, y, x, H, W, v * 8, gy);
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = gy[j];
+        if (WIN && win_arg[j] == q) d += pg[j];
+        const float r = fmaf(zf[q][j], a[j], b[j]);
+        if (relu && !(r > 0.f)) d = 0.f;
+        const float xh = (zf[q][j] - mean[j]) * rstd[j];
+        if (MODE == 0) {
+          s1[j] += d;
+          s2[j] = fmaf(d, xh, s2[j]);
+        } else {
+          out[j] = a[j] * (d - m1[j] - xh * m2[j]);
+        }
+      }
+      if (MODE == 1) dz[(((long long)n * H + y) * W + x) * c8 + v] = pack8_bf16(out);
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    __syncthreads();
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+      if (pl < s) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_red[threadIdx.x * 16 + j] += s_red[(threadIdx.x + s * c8) * 16 + j];
+      }
+      __syncthreads();
+    }
+    if (pl == 0) {
+      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+      }
+    }
+  }
+}
+
+// coef[g][c] = (mean of dy_hat, mean of dy_hat * x_hat);  dgamma[c] += sum_g S2, dbeta[c] += sum_g S1
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, Groups gr, int C, int HW, float* dgamma, float* dbeta,
+                                       float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float dg = 0.f, db = 0.f;
+  for (int g = 0; g < gr.G; ++g) {
+    const float cnt = (float)(gr.start[g + 1] - gr.start[g]) * (float)HW;
+    const float S1 = sums[((size_t)g * C + c) * 2], S2 = sums[((size_t)g * C + c) * 2 + 1];
+    coef[((size_t)g * C + c) * 2] = S1 / cnt;
+    coef[((size_t)g * C + c) * 2 + 1] = S2 / cnt;
+    db += S1;
+    dg += S2;
+  }
+  if (dgamma) dgamma[c] += dg;
+  if (dbeta) dbeta[c] += db;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// nn.Upsample(scale_factor=2) (nearest), fp16 NHWC.  net/modules.py:67 (train path: the up-sampled map is
+// materialised so that the weight gradient is a plain 3x3 tap-list GEMM).
+// ---------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int c8) {
+  const long long total = (long long)N * 2 * H * 2 * W * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % c8);
+    long long t = i / c8;
+    const int xo = (int)(t % (2 * W));  t /= 2 * W;
+    const int yo = (int)(t % (2 * H));
+    const int n = (int)(t / (2 * H));
+    y[i] = __ldg(x + (((long long)n * H + (yo >> 1)) * W + (xo >> 1)) * c8 + v);
+  }
+}
+
+// fp16 -> bf16 copy: tcgen05 kind::f16 wants one element format for both operands, and the weight-gradient GEMM's
+// other operand is the bf16 activation gradient.
+__global__ void cvt_f16_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8_f16(__ldg(in + i), f);
+    out[i] = pack8_bf16(f);
+  }
+}
+
+// d(x) for x_fg = x*m, x_bg = x*(1-m) (net/rp_net.py:275,283), summed over `iters` uses of the same x:
+//   dx[p][c] = sum_i dxfg[i][p][c] * m[i][p] + dxbg[i][p][c] * (1 - m[i][p])
+__global__ void premask_bwd_kernel(const uint4* __restrict__ dxfg, const uint4* __restrict__ dxbg, const float* __restrict__ m,
+                                   int iters, long long pixels, int c8, uint4* __restrict__ dx) {
+  const long long total = pixels * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / c8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      const float mk = __ldg(m + (long long)it * pixels + pix);
+      float a[8], b[8];
+      unpack8_bf16(__ldg(dxfg + (long long)it * total + i), a);
+      unpack8_bf16(__ldg(dxbg + (long long)it * total + i), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j] * mk + b[j] * (1.f - mk);
+    }
+    dx[i] = pack8_bf16(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight repack (every optimizer step): fp32 [cout][cin_real][taps] ->
+//   forward  fp16 [taps][cout][cin]   (K-major B operand of conv_igemm)
+//   dgrad    bf16 [taps][cin][cout]   (transposed; used with the negated tap list)
+// `cin` = cin_real + hole_len: packed input channels [hole_start, hole_start+hole_len) are zero padding.
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
+                                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = (long long)ntaps * cout * cin;
+  const int cin_real = cin - hole_len;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % cout);
+    const int t = (int)(i / ((long long)cin * cout));
+    float val = 0.f;
+    if (ci < hole_start || ci >= hole_start + hole_len) {
+      const int cr = ci < hole_start ? ci : ci - hole_len;
+      val = __ldg(w + ((size_t)co * cin_real + cr) * ntaps + t);
+    }
+    if (wf) wf[i] = __float2half_rn(val);
+    if (wd) wd[((size_t)t * cin + ci) * cout + co] = __float2bfloat16_rn(val);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the Cin = 1 first conv (encoder.Conv1.conv.0): grad[co][ky][kx] += sum_p dz[p][co] * img[p + tap].
+// One warp per run of pixels; lane = 2 output channels; 9 broadcast image loads + one coalesced 128 B dz row per pixel.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv3x3_first_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat162* __restrict__ dz, int N, int H, int W,
+                           float* __restrict__ grad /*[64][9]*/) {
+  __shared__ float s_acc[8][64 * 9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc0[9], acc1[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
+  const long long total = (long long)N * H * W;
+  const long long wid = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+  for (long long p = wid; p < total; p += nw) {
+    const int x = (int)(p % W), y = (int)((p / W) % H);
+    const long long base = p - (long long)y * W - x;            // n * H * W
+    const float2 d = __bfloat1622float2(dz[p * 32 + lane]);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + base + (long long)yy * W + xx) : 0.f;
+        acc0[ky * 3 + kx] = fmaf(d.x, v, acc0[ky * 3 + kx]);
+        acc1[ky * 3 + kx] = fmaf(d.y, v, acc1[ky * 3 + kx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    s_acc[warp][(2 * lane) * 9 + t] = acc0[t];
+    s_acc[warp][(2 * lane + 1) * 9 + t] = acc1[t];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += s_acc[k][i];
+    atomicAdd(grad + i, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// torch.optim.Adam (weight_decay = L2 added to the gradient, yamls/example.yml:64-67) on flat fp32 buffers.
+// ---------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    const float gi = fmaf(wd, pi, g[i] * grad_scale);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace rpnet
+
+using namespace rpnet;
+
+RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(z && sums, "bn_stats: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 64 && c % 8 == 0 && 256 % (c / 8) == 0, "bn_stats: bad shape n=%d h=%d w=%d c=%d (c in {64..2048}, power of two)", n, h, w, c);
+  Groups gr;
+  int rc = make_groups(&gr, group_start, groups, n);
+  if (rc) return rc;
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
+  const int lanes = 256 / (c / 8);
+  int max_imgs = 0;
+  for (int g = 0; g < groups; ++g) max_imgs = gr.start[g + 1] - gr.start[g] > max_imgs ? gr.start[g + 1] - gr.start[g] : max_imgs;
+  long long blocks = ((long long)max_imgs * h * w + lanes * 8 - 1) / (lanes * 8);
+  const long long cap = (148LL * 8 + groups - 1) / groups;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  bn_stats_kernel<<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(static_cast<const uint4*>(z), gr, h * w, c / 8, sums);
+  return check_cuda(cudaGetLastError(), "bn_stats launch");
+}
+
+RPNET_API int rpnet_bn_finalize_f32(const float* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
+                                     const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
+                                     float* running_var, long long* num_batches_tracked, float* stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(sums && gamma && beta && stats, "bn_finalize: null pointer argument");
+  RPNET_REQUIRE(c > 0 && hw > 0, "bn_finalize: bad shape");
+  Groups gr;
+  int rc = make_groups(&gr, group_start, groups, group_start ? group_start[groups > 0 ? groups : 0] : 0);
+  if (rc) return rc;
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, gr, c, hw, gamma, beta, conv_bias, eps, momentum, running_mean,
+                                                          running_var, num_batches_tracked, stats);
+  return check_cuda(cudaGetLastError(), "bn_finalize launch");
+}
+
+RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups,
+                                  int relu, void* y_f16, void* y_pool_f16, float* y_f32, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(z && stats, "bn_apply: null pointer argument");
+  RPNET_REQUIRE(y_f16 || y_pool_f16 || y_f32, "bn_apply: no output requested");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bn_apply: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  RPNET_REQUIRE(!y_pool_f16 || (h % 2 == 0 && w % 2 == 0), "bn_apply: fused 2x2 max-pool needs even H, W (got %d x %d)", h, w);
+  Groups gr;
+  int rc = make_groups(&gr, group_start, groups, n);
+  if (rc) return rc;
+  if (y_pool_f16) {
+    const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+    bn_apply_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
+                                                                    static_cast<uint4*>(y_f16), y_f32, static_cast<uint4*>(y_pool_f16));
+  } else {
+    const long long total = (long long)n * h * w * (c / 8);
+    bn_apply_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
+                                                                     static_cast<uint4*>(y_f16), y_f32, nullptr);
+  }
+  return check_cuda(cudaGetLastError(), "bn_apply launch");
+}
+
+// Backward of BatchNorm(batch stats)+ReLU for dz, in three launches: reduce -> finalize (dgamma, dbeta) -> apply.
+RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups, int relu,
+                           const void* g_direct, int d_ld, int d_off, int d_is_f32, const void* g_pool_bf16, int p_ld, int p_off,
+                           const void* g_up_bf16, int u_ld, int u_off, float* dgamma, float* dbeta, float* scratch /*[G][C][4]*/,
+                           void* dz_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(z && stats && scratch && dz_bf16, "bn_bwd: null pointer argument");
+  RPNET_REQUIRE(g_direct || g_pool_bf16 || g_up_bf16, "bn_bwd: no gradient source");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 64 && c % 8 == 0 && 256 % (c / 8) == 0, "bn_bwd: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  RPNET_REQUIRE(!g_pool_bf16 || (h % 2 == 0 && w % 2 == 0), "bn_bwd: max-pool routing needs even H, W (got %d x %d)", h, w);
+  RPNET_REQUIRE(d_ld % 8 == 0 && d_off % 8 == 0 && p_ld % 8 == 0 && p_off % 8 == 0 && u_ld % 8 == 0 && u_off % 8 == 0,
+                "bn_bwd: gradient pitches / offsets must be multiples of 8 channels");
+  Groups gr;
+  int rc = make_groups(&gr, group_start, groups, n);
+  if (rc) return rc;
+  GradSrc src;
+  src.direct = g_direct; src.d_ld = d_ld; src.d_off = d_off; src.d_f32 = d_is_f32;
+  src.pooled = static_cast<const __nv_bfloat16*>(g_pool_bf16); src.p_ld = p_ld; src.p_off = p_off;
+  src.up = static_cast<const __nv_bfloat16*>(g_up_bf16); src.u_ld = u_ld; src.u_off = u_off;
+  float* sums = scratch;                                  // [G][C][2]
+  float* coef = scratch + (size_t)groups * c * 2;         // [G][C][2]
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
+  const bool win = g_pool_bf16 != nullptr;
+  const int c8 = c / 8, lanes = 256 / c8;
+  int max_imgs = 0;
+  for (int g = 0; g < groups; ++g) max_imgs = gr.start[g + 1] - gr.start[g] > max_imgs ? gr.start[g + 1] - gr.start[g] : max_imgs;
+  const long long units_g = (long long)max_imgs * (win ? (h / 2) * (w / 2) : h * w);
+  long long blocks = (units_g + lanes * 4 - 1) / (lanes * 4);
+  const long long cap = (148LL * 8 + groups - 1) / groups;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const uint4* zz = static_cast<const uint4*>(z);
+  if (win) bn_bwd_kernel<true, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
+  else     bn_bwd_kernel<false, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
+  RPNET_CUDA_OK(cudaGetLastError());
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, gr, c, h * w, dgamma, dbeta, coef);
+  RPNET_CUDA_OK(cudaGetLastError());
+  const long long units = (long long)n * (win ? (h / 2) * (w / 2) : h * w);
+  long long blocks2 = (units + lanes - 1) / lanes;
+  if (blocks2 > 148LL * 16) blocks2 = 148LL * 16;
+  if (win) bn_bwd_kernel<true, 1><<<(unsigned)blocks2, 256, 0, stream>>>(zz, stats, coef, gr, n, h, w, c8, relu, src, nullptr, static_cast<uint4*>(dz_bf16));
+  else     bn_bwd_kernel<false, 1><<<(unsigned)blocks2, 256, 0, stream>>>(zz, stats, coef, gr, n, h, w, c8, relu, src, nullptr, static_cast<uint4*>(dz_bf16));
+  return check_cuda(cudaGetLastError(), "bn_bwd launch");
+}
+
+RPNET_API int rpnet_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(x && y, "upsample2x: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "upsample2x: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  const long long total = (long long)n * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n, h, w, c / 8);
+  return check_cuda(cudaGetLastError(), "upsample2x launch");
+}
+
+RPNET_API int rpnet_cvt_f16_to_bf16(const void* in_f16, void* out_bf16, long long n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(in_f16 && out_bf16, "cvt_f16_to_bf16: null pointer argument");
+  RPNET_REQUIRE(n > 0 && n % 8 == 0, "cvt_f16_to_bf16: element count must be a positive multiple of 8 (got %lld)", n);
+  cvt_f16_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const uint4*>(in_f16), static_cast<uint4*>(out_bf16), n / 8);
+  return check_cuda(cudaGetLastError(), "cvt_f16_to_bf16 launch");
+}
+
+RPNET_API int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask, int iters, long long pixels, int c,
+                                      void* dx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dxfg && dxbg && mask && dx, "premask_bwd: null pointer argument");
+  RPNET_REQUIRE(iters >= 1 && pixels > 0 && c > 0 && c % 8 == 0, "premask_bwd: bad shape iters=%d pixels=%lld c=%d", iters, pixels, c);
+  premask_bwd_kernel<<<grid_for(pixels * (c / 8), 256), 256, 0, stream>>>(static_cast<const uint4*>(dxfg), static_cast<const uint4*>(dxbg),
+                                                                            mask, iters, pixels, c / 8, static_cast<uint4*>(dx));
+  return check_cuda(cudaGetLastError(), "premask_bwd launch");
+}
+
+RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len, void* w_fwd_f16,
+                                      void* w_dgrad_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(w && (w_fwd_f16 || w_dgrad_bf16), "pack_conv_weight: null pointer argument");
+  RPNET_REQUIRE(cout > 0 && cin_real > 0 && ntaps > 0 && hole_len >= 0 && hole_start >= 0 && hole_start <= cin_real,
+                "pack_conv_weight: bad shape");
+  const int cin = cin_real + hole_len;
+  pack_conv_weight_kernel<<<grid_for((long long)ntaps * cout * cin, 256), 256, 0, stream>>>(
+      w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16), static_cast<__nv_bfloat16*>(w_dgrad_bf16));
+  return check_cuda(cudaGetLastError(), "pack_conv_weight launch");
+}
+
+RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(img && dz_bf16 && grad, "conv3x3_first_wgrad: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first_wgrad: bad shape");
+  const long long total = (long long)n * h * w;
+  long long blocks = (total + 8 * 64 - 1) / (8 * 64);
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const __nv_bfloat162*>(dz_bf16), n, h, w, grad);
+  return check_cuda(cudaGetLastError(), "conv3x3_first_wgrad launch");
+}
+
+RPNET_API int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam: null pointer argument");
+  RPNET_REQUIRE(n > 0 && step >= 1, "adam: bad arguments n=%lld step=%d", n, step);
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                    sqrtf(bc2), grad_scale);
+  return check_cuda(cudaGetLastError(), "adam launch");
+}

@@ -181,3 +181,330 @@ def maxpool(x, k, stride, pad, out):
     with _Timed('maxpool', float(x.numel() * 2 + out.numel() * 2)):
         _lib.check(lib.rpnet_maxpool_f16(_ptr(x), _ptr(out), n, h, w, c, k, stride, pad, _stream()), 'rpnet_maxpool_f16')
     
+
+# =====================================================================================================
+# training entry points (include/rpnet_b200.h, "Training path")
+# =====================================================================================================
+bf16 = torch.bfloat16
+
+
+def _groups(group_start):
+    g = [int(v) for v in group_start]
+    return (ctypes.c_int * len(g))(*g), len(g) - 1
+
+
+def _taps(taps):
+    n = len(taps)
+    return (ctypes.c_int * n)(*[int(t[0]) for t in taps]), (ctypes.c_int * n)(*[int(t[1]) for t in taps])
+
+
+def conv_dgrad(dz, wpack_t, taps, out, out_coff=0):
+    """Data gradient of a tap-list conv: dz bf16 NHWC [n,h,w,cout], wpack_t bf16 [ntaps, cin, cout] (transposed pack),
+    taps = the FORWARD tap list (negated here); out bf16 NHWC [n,h,w,>=cin]."""
+    lib = _lib.load()
+    _req(dz, bf16, 'dz'); _req(wpack_t, bf16, 'wpack_t'); _req(out, bf16, 'out')
+    n, h, w, cout = dz.shape
+    ntaps, cin, cout2 = wpack_t.shape
+    assert cout2 == cout and ntaps == len(taps) and out.shape[:3] == dz.shape[:3]
+    dy, dx = _taps([(-t[0], -t[1]) for t in taps])
+    one, zero = _const_vec(cin, 1.0, dz.device), _const_vec(cin, 0.0, dz.device)
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_igemm_bf16(_ptr(dz), cout, None, 0, n, h, w, _ptr(wpack_t), ntaps, dy, dx, cin, _ptr(one), _ptr(zero), 0,
+                                       _ptr(out), h, w, out.shape[3], out_coff, 1, 0, 1, 0, None, None, _stream())
+    _lib.check(rc, 'rpnet_conv_igemm_bf16')
+
+
+_CONST = {}
+
+
+def _const_vec(n, val, device):
+    key = (n, val, str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.full((n,), val, dtype=torch.float32, device=device)
+        _CONST[key] = t
+    return t
+
+
+def conv_wgrad_workspace_bytes(c0, c1, n, h, w, ntaps, cout):
+    r = _lib.load().rpnet_conv_wgrad_workspace_bytes(c0, c1, n, h, w, ntaps, cout)
+    if r < 0:
+        _lib.check(int(r), 'rpnet_conv_wgrad_workspace_bytes')
+    return int(r)
+
+
+def cvt_f16_to_bf16(x, out):
+    lib = _lib.load()
+    _req(x, torch.float16, 'x'); _req(out, bf16, 'out')
+    assert out.numel() >= x.numel()
+    with _Timed('cvt_f16_to_bf16', float(x.numel() * 4)):
+        _lib.check(lib.rpnet_cvt_f16_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), 'rpnet_cvt_f16_to_bf16')
+
+
+_CVT = {}
+
+
+def _as_bf16(x, slot):
+    """fp16 activations -> bf16 copy in a persistent scratch buffer (one per operand slot, grown on demand)."""
+    if x is None or x.dtype == bf16:
+        return x
+    key = (slot, str(x.device))
+    buf = _CVT.get(key)
+    if buf is None or buf.numel() < x.numel():
+        buf = torch.empty(x.numel(), dtype=bf16, device=x.device)
+        _CVT[key] = buf
+    out = buf[:x.numel()].view(x.shape)
+    cvt_f16_to_bf16(x, out)
+    return out
+
+
+def conv_wgrad(x0, dz, taps, grad, workspace, x1=None, hole=(0, 0), accumulate=True):
+    """grad fp32 [cout, cin_real, kh, kw] (+)= sum dz * shifted x.  x0/x1 fp16 or bf16 NHWC (fp16 is converted to a bf16
+    scratch copy first: the tensor-core GEMM needs one operand format), dz bf16 NHWC."""
+    lib = _lib.load()
+    _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
+    if x0.dtype not in (torch.float16, bf16) or not x0.is_contiguous():
+        raise _lib.RpnetError('conv_wgrad: x0 must be contiguous fp16/bf16')
+    x0, x1 = _as_bf16(x0, 0), _as_bf16(x1, 1)
+    n, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[3]
+    cout = dz.shape[3]
+    assert tuple(dz.shape[:3]) == (n, h, w) and grad.numel() == cout * (c0 + c1 - hole[1]) * len(taps)
+    dy, dx = _taps(taps)
+    with _Timed('conv_wgrad', 2.0 * n * h * w * cout * (c0 + c1) * len(taps), n=2):
+        rc = lib.rpnet_conv_wgrad(_ptr(x0), c0, _ptr(x1), c1, int(x0.dtype == bf16), _ptr(dz), n, h, w, len(taps), dy, dx, cout,
+                                  _ptr(grad), hole[0], hole[1], int(bool(accumulate)), _ptr(workspace),
+                                  workspace.numel() * workspace.element_size(), _stream())
+    _lib.check(rc, 'rpnet_conv_wgrad')
+
+
+def conv3x3_first_wgrad(img, dz, grad):
+    lib = _lib.load()
+    _req(img, torch.float32, 'img'); _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
+    n, cin, h, w = img.shape
+    assert cin == 1 and tuple(dz.shape) == (n, h, w, 64) and grad.numel() == 64 * 9
+    with _Timed('conv3x3_first_wgrad', float(img.numel() * 4 + dz.numel() * 2)):
+        _lib.check(lib.rpnet_conv3x3_first_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _stream()), 'rpnet_conv3x3_first_wgrad')
+
+
+def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0)):
+    """w fp32 [cout, cin_real, kh, kw] -> w_fwd fp16 [taps, cout, cin] / w_dgrad bf16 [taps, cin, cout]."""
+    lib = _lib.load()
+    _req(w, torch.float32, 'w')
+    cout, cin_real = w.shape[:2]
+    ntaps = w.shape[2] * w.shape[3]
+    with _Timed('pack_conv_weight', float(w.numel() * 8)):
+        _lib.check(lib.rpnet_pack_conv_weight(_ptr(w), cout, cin_real, ntaps, hole[0], hole[1], _ptr(w_fwd), _ptr(w_dgrad), _stream()),
+                   'rpnet_pack_conv_weight')
+
+
+def bn_stats(z, group_start, sums):
+    lib = _lib.load()
+    _req(z, torch.float16, 'z'); _req(sums, torch.float32, 'sums')
+    n, h, w, c = z.shape
+    gs, g = _groups(group_start)
+    assert sums.numel() >= g * c * 2
+    with _Timed('bn_stats', float(z.numel() * 2)):
+        _lib.check(lib.rpnet_bn_stats_f16(_ptr(z), n, h, w, c, gs, g, _ptr(sums), _stream()), 'rpnet_bn_stats_f16')
+
+
+def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, running_var, nbt, stats, eps=1e-5, momentum=0.1):
+    lib = _lib.load()
+    gs, g = _groups(group_start)
+    assert stats.numel() >= g * c * 4 and stats.dtype == torch.float32
+    with _Timed('bn_finalize', float(g * c * 24)):
+        _lib.check(lib.rpnet_bn_finalize_f32(_ptr(sums), gs, g, c, hw, _ptr(gamma), _ptr(beta), _ptr(conv_bias), float(eps),
+                                             float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats), _stream()),
+                   'rpnet_bn_finalize_f32')
+
+
+def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None):
+    lib = _lib.load()
+    _req(z, torch.float16, 'z')
+    n, h, w, c = z.shape
+    gs, g = _groups(group_start)
+    nb = z.numel() * 2 + sum(t.numel() * t.element_size() for t in (y, y_pool, y_f32) if t is not None)
+    with _Timed('bn_apply', float(nb)):
+        _lib.check(lib.rpnet_bn_apply_f16(_ptr(z), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(y), _ptr(y_pool), _ptr(y_f32),
+                                          _stream()), 'rpnet_bn_apply_f16')
+
+
+def bn_bwd(z, stats, group_start, dz, scratch, relu=True, direct=None, d_off=0, pooled=None, p_off=0, up=None, u_off=0,
+           dgamma=None, dbeta=None):
+    """direct: bf16/fp32 NHWC tensor [n,h,w,ld]; pooled: bf16 [n,h/2,w/2,ld]; up: bf16 [n,2h,2w,ld]."""
+    lib = _lib.load()
+    _req(z, torch.float16, 'z'); _req(dz, bf16, 'dz')
+    n, h, w, c = z.shape
+    gs, g = _groups(group_start)
+    assert scratch.numel() >= g * c * 4
+    d_ld = direct.shape[-1] if direct is not None else 0
+    p_ld = pooled.shape[-1] if pooled is not None else 0
+    u_ld = up.shape[-1] if up is not None else 0
+    if direct is not None:
+        assert direct.dtype in (bf16, torch.float32) and direct.is_contiguous() and direct.numel() == n * h * w * d_ld
+    if pooled is not None:
+        assert pooled.dtype == bf16 and pooled.is_contiguous() and pooled.numel() == n * (h // 2) * (w // 2) * p_ld
+    if up is not None:
+        assert up.dtype == bf16 and up.is_contiguous() and up.numel() == n * 4 * h * w * u_ld
+    with _Timed('bn_bwd', float(z.numel() * 2 * 5), n=3):
+        rc = lib.rpnet_bn_bwd(_ptr(z), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(direct), d_ld, d_off,
+                              int(direct is not None and direct.dtype == torch.float32), _ptr(pooled), p_ld, p_off, _ptr(up), u_ld,
+                              u_off, _ptr(dgamma), _ptr(dbeta), _ptr(scratch), _ptr(dz), _stream())
+    _lib.check(rc, 'rpnet_bn_bwd')
+
+
+def upsample2x(x, y):
+    lib = _lib.load()
+    _req(x, torch.float16, 'x'); _req(y, torch.float16, 'y')
+    n, h, w, c = x.shape
+    assert tuple(y.shape) == (n, 2 * h, 2 * w, c)
+    with _Timed('upsample2x', float(x.numel() * 2 + y.numel() * 2)):
+        _lib.check(lib.rpnet_upsample2x_f16(_ptr(x), _ptr(y), n, h, w, c, _stream()), 'rpnet_upsample2x_f16')
+
+
+def premask_bwd(dxfg, dxbg, mask, dx, iters=1):
+    lib = _lib.load()
+    _req(dxfg, bf16, 'dxfg'); _req(dxbg, bf16, 'dxbg'); _req(mask, torch.float32, 'mask'); _req(dx, bf16, 'dx')
+    c = dx.shape[-1]
+    pixels = dx.numel() // c
+    assert dxfg.numel() == iters * pixels * c and dxbg.numel() == dxfg.numel() and mask.numel() == iters * pixels
+    with _Timed('premask_bwd', float(dxfg.numel() * 4 + dx.numel() * 2)):
+        _lib.check(lib.rpnet_premask_bwd_bf16(_ptr(dxfg), _ptr(dxbg), _ptr(mask), iters, pixels, c, _ptr(dx), _stream()), 'rpnet_premask_bwd_bf16')
+
+
+def local_corr_bwd(f1, f2, dq, add_off, radius, df1, df2):
+    lib = _lib.load()
+    _req(f1, torch.float16, 'f1'); _req(f2, torch.float16, 'f2'); _req(dq, bf16, 'dq'); _req(df1, bf16, 'df1'); _req(df2, bf16, 'df2')
+    n, h, w, c = f1.shape
+    assert f2.shape == f1.shape and df1.shape == f1.shape and df2.shape == f1.shape and tuple(dq.shape[:3]) == (n, h, w)
+    with _Timed('local_corr_bwd', float(f1.numel() * 8 + dq.numel() * 2), n=2):
+        _lib.check(lib.rpnet_local_corr_bwd(_ptr(f1), _ptr(f2), _ptr(dq), dq.shape[3], add_off, _ptr(df1), _ptr(df2), n, h, w, c, radius,
+                                            _stream()), 'rpnet_local_corr_bwd')
+
+
+def cos_sim_bwd(feat, protos, dpred, dfeat, dprotos=None, scaler=20.0, accumulate=False):
+    lib = _lib.load()
+    _req(feat, torch.float32, 'feat'); _req(protos, torch.float32, 'protos'); _req(dpred, torch.float32, 'dpred'); _req(dfeat, torch.float32, 'dfeat')
+    n, h, w, c = feat.shape
+    sets, p = protos.shape[0], protos.shape[1]
+    assert tuple(dpred.shape) == (n, p, h, w) and dfeat.shape == feat.shape
+    with _Timed('cos_sim_bwd', float(feat.numel() * 8 + dpred.numel() * 4)):
+        _lib.check(lib.rpnet_cos_sim_bwd_f32(_ptr(feat), _ptr(protos), _ptr(dpred), n, h * w, c, p, sets, float(scaler), _ptr(dfeat),
+                                             int(bool(accumulate)), _ptr(dprotos), _stream()), 'rpnet_cos_sim_bwd_f32')
+
+
+def bilinear_adjoint(x, out, sums=None):
+    """x fp32 [n,H,W] -> out fp32 [n,h,w] = U^T x; sums [n] (optional) = x.sum((1,2))."""
+    lib = _lib.load()
+    _req(x, torch.float32, 'x'); _req(out, torch.float32, 'out')
+    n, H, W = x.shape
+    assert out.shape[0] == n
+    with _Timed('bilinear_adjoint', float(x.numel() * 4 + out.numel() * 4)):
+        _lib.check(lib.rpnet_bilinear_adjoint_f32(_ptr(x), _ptr(out), _ptr(sums), n, H, W, out.shape[1], out.shape[2], _stream()),
+                   'rpnet_bilinear_adjoint_f32')
+
+
+def weighted_pool(feat, wmap0, wmap1, msum0, msum1, out):
+    lib = _lib.load()
+    _req(feat, torch.float32, 'feat'); _req(out, torch.float32, 'out')
+    n, h, w, c = feat.shape
+    assert wmap0.numel() == n * h * w and wmap1.numel() == n * h * w and tuple(out.shape) == (n, 2, c)
+    with _Timed('weighted_pool', float(feat.numel() * 8)):
+        _lib.check(lib.rpnet_weighted_pool_f32(_ptr(feat), _ptr(wmap0), _ptr(wmap1), _ptr(msum0), _ptr(msum1), _ptr(out), n, h * w, c,
+                                               _stream()), 'rpnet_weighted_pool_f32')
+
+
+def weighted_pool_bwd(dout, wmap0, wmap1, msum0, msum1, dfeat, accumulate=False):
+    lib = _lib.load()
+    _req(dout, torch.float32, 'dout'); _req(dfeat, torch.float32, 'dfeat')
+    n, h, w, c = dfeat.shape
+    with _Timed('weighted_pool_bwd', float(dfeat.numel() * 4)):
+        _lib.check(lib.rpnet_weighted_pool_bwd_f32(_ptr(dout), _ptr(wmap0), _ptr(wmap1), _ptr(msum0), _ptr(msum1), _ptr(dfeat),
+                                                   int(bool(accumulate)), n, h * w, c, _stream()), 'rpnet_weighted_pool_bwd_f32')
+
+
+def proto_finalize_bwd(dprotos, draw):
+    lib = _lib.load()
+    _req(dprotos, torch.float32, 'dprotos'); _req(draw, torch.float32, 'draw')
+    ways, shots, batch, two, c = draw.shape
+    assert tuple(dprotos.shape) == (batch, 1 + ways, c)
+    with _Timed('proto_finalize_bwd', float(draw.numel() * 4)):
+        _lib.check(lib.rpnet_proto_finalize_bwd_f32(_ptr(dprotos), _ptr(draw), ways, shots, batch, c, _stream()), 'rpnet_proto_finalize_bwd_f32')
+
+
+def dice_ce(logits, labels, sums, loss, dlogits=None, grad_scale=1.0, eps=1e-7):
+    """logits fp32 [G,B,P,H,W]; labels int64 [B,H,W]; loss fp32 [G]; dlogits like logits (optional)."""
+    lib = _lib.load()
+    _req(logits, torch.float32, 'logits'); _req(labels, torch.int64, 'labels'); _req(loss, torch.float32, 'loss')
+    g, b, p, h, w = logits.shape
+    assert tuple(labels.shape) == (b, h, w) and sums.numel() >= g * (2 * p + 1) and loss.numel() >= g
+    with _Timed('dice_ce', float(logits.numel() * (12 if dlogits is not None else 4)), n=2):
+        _lib.check(lib.rpnet_dice_ce_f32(_ptr(logits), _ptr(labels), g, b, p, h * w, float(eps), float(grad_scale), _ptr(sums),
+                                         _ptr(dlogits), _ptr(loss), _stream()), 'rpnet_dice_ce_f32')
+
+
+def class_pool(feat, pred, qproto, counts, amax):
+    lib = _lib.load()
+    _req(feat, torch.float32, 'feat'); _req(pred, torch.float32, 'pred'); _req(amax, torch.int32, 'amax')
+    b, h, w, c = feat.shape
+    p = pred.shape[1]
+    assert tuple(qproto.shape) == (b, p, c) and counts.numel() == b * p and amax.numel() == b * h * w
+    with _Timed('class_pool', float(feat.numel() * 4)):
+        _lib.check(lib.rpnet_class_pool_f32(_ptr(feat), _ptr(pred), b, h * w, c, p, _ptr(qproto), _ptr(counts), _ptr(amax), _stream()),
+                   'rpnet_class_pool_f32')
+
+
+def class_pool_bwd(dqproto, counts, amax, dfeat):
+    lib = _lib.load()
+    _req(dqproto, torch.float32, 'dqproto'); _req(dfeat, torch.float32, 'dfeat')
+    b, h, w, c = dfeat.shape
+    with _Timed('class_pool_bwd', float(dfeat.numel() * 8)):
+        _lib.check(lib.rpnet_class_pool_bwd_f32(_ptr(dqproto), _ptr(counts), _ptr(amax), b, h * w, c, dqproto.shape[1], _ptr(dfeat),
+                                                _stream()), 'rpnet_class_pool_bwd_f32')
+
+
+def align_gather(qproto, counts, ways, shots, scaler, protos_s, weight):
+    lib = _lib.load()
+    b = qproto.shape[0]
+    assert protos_s.numel() == ways * shots * b * 128 and weight.numel() == ways * shots * b
+    with _Timed('align_gather', float(protos_s.numel() * 8)):
+        _lib.check(lib.rpnet_align_gather_f32(_ptr(qproto), _ptr(counts), ways, shots, b, float(scaler), _ptr(protos_s), _ptr(weight),
+                                              _stream()), 'rpnet_align_gather_f32')
+
+
+def align_scatter(dprotos_s, ways, shots, dqproto):
+    lib = _lib.load()
+    b = dqproto.shape[0]
+    with _Timed('align_scatter', float(dprotos_s.numel() * 4)):
+        _lib.check(lib.rpnet_align_scatter_f32(_ptr(dprotos_s), ways, shots, b, _ptr(dqproto), _stream()), 'rpnet_align_scatter_f32')
+
+
+def ce_mask(logits, fore, back, weight, sums, loss, dlogits=None, grad_scale=1.0):
+    lib = _lib.load()
+    _req(logits, torch.float32, 'logits'); _req(fore, torch.float32, 'fore'); _req(back, torch.float32, 'back')
+    n, two, h, w = logits.shape
+    assert two == 2 and fore.numel() == n * h * w and back.numel() == n * h * w and weight.numel() == n and sums.numel() >= 2 * n
+    with _Timed('ce_mask', float(logits.numel() * (12 if dlogits is not None else 4)), n=2):
+        _lib.check(lib.rpnet_ce_mask_f32(_ptr(logits), _ptr(fore), _ptr(back), _ptr(weight), n, h * w, float(grad_scale), _ptr(sums),
+                                         _ptr(dlogits), _ptr(loss), _stream()), 'rpnet_ce_mask_f32')
+
+
+def bilinear_up(x, out):
+    lib = _lib.load()
+    _req(x, torch.float32, 'x'); _req(out, torch.float32, 'out')
+    n, h, w = x.shape
+    assert out.shape[0] == n
+    with _Timed('bilinear_up', float(x.numel() * 4 + out.numel() * 4)):
+        _lib.check(lib.rpnet_bilinear_up_f32(_ptr(x), _ptr(out), n, h, w, out.shape[1], out.shape[2], _stream()), 'rpnet_bilinear_up_f32')
+
+
+def adam(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    lib = _lib.load()
+    for t, nm in ((param, 'param'), (grad, 'grad'), (exp_avg, 'exp_avg'), (exp_avg_sq, 'exp_avg_sq')):
+        _req(t, torch.float32, nm)
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    with _Timed('adam', float(n * 28)):
+        _lib.check(lib.rpnet_adam_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr), float(betas[0]),
+                                      float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), _stream()),
+                   'rpnet_adam_f32')

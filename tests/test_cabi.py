@@ -16,7 +16,7 @@ def _header_decls():
     src = open(os.path.join(ROOT, 'include', 'rpnet_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     decls = {}
-    for m in re.finditer(r'(?:int|const char\s*\*)\s+(rpnet_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'(?:long long|int|const char\s*\*)\s+(rpnet_\w+)\s*\(([^;]*?)\)\s*;', src, flags=re.S):
         args = [a.strip() for a in m.group(2).replace('\n', ' ').split(',')]
         decls[m.group(1)] = [] if args == ['void'] else args
     return decls
