@@ -8,6 +8,9 @@ import torch
 from . import ops
 
 BN_EPS = 1e-5
+# bumped by every optimizer step that updates the parameters through raw pointers (rpnet_b200.train): packed-weight
+# caches key on it because such updates do not touch torch's tensor version counters
+WEIGHTS_EPOCH = 0
 TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 

@@ -26,7 +26,7 @@ class _PackedModule(nn.Module):
     """Caches packed fp16 weights / folded BN; invalidated when any parameter or buffer changes."""
 
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return (engine.WEIGHTS_EPOCH,) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def _packs(self):
         sig = self._signature()

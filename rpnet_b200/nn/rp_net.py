@@ -6,7 +6,8 @@ Differences from the reference that are visible to a caller (all documented in D
     "oracle-ext" generalisation: cre per (way, shot); recurrent mask = sum of fg-class probabilities > 0.5.
   * prototypes are computed once per forward (they are loop invariant).
   * `backbone: vgg` runs (the reference raises TypeError, D1) when the yaml also sets `scale: 8`.
-  * train mode is not built yet and raises NotImplementedError (no PyTorch fallback).
+  * train mode (`net.train()`) runs the batch-statistics forward of rpnet_b200.train and is attached to autograd
+    through one custom Function whose backward is the hand-scheduled kernel backward (UNet backbone, hard masks).
 """
 import torch
 import torch.nn as nn
@@ -171,7 +172,7 @@ class RP_Net(nn.Module):
         Returns {'output': (N*B) x (1+Wa) x H x W logits, 'align_loss': scalar, 'refinement': {i: logits}}.
         """
         if self.training:
-            raise NotImplementedError('RP_Net train-mode forward/backward kernels are not built yet (call .eval())')
+            return self._forward_train(supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_labels)
         n_ways, n_shots = len(supp_imgs), len(supp_imgs[0])
         n_queries = len(qry_imgs)
         if n_queries != 1:
@@ -228,6 +229,19 @@ class RP_Net(nn.Module):
         output = logits.clone()
         return {'output': output, 'align_loss': 0 / B, 'refinement': refinement}
 
+    def _forward_train(self, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_labels):
+        """Train-mode forward (BatchNorm batch statistics per reference call; alignLoss when cfg['align']):
+        rpnet_b200.train.TrainEngine behind one autograd node."""
+        from .. import train
+        appr_query_labels.unsqueeze                      # AttributeError on None, like the reference (:269)
+        if qry_imgs[0].device.type != 'cuda':
+            raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU')
+        d = {'supp_imgs': supp_imgs, 'fore_mask': fore_mask, 'back_mask': back_mask, 'qry_imgs': qry_imgs,
+             'appr_query_labels': appr_query_labels}
+        logits, align = train.train_forward(self, d)
+        T = logits.shape[0]
+        return {'output': logits[T - 1], 'align_loss': align[0], 'refinement': {i: logits[i] for i in range(T)}}
+
     # ------------------------------------------------------------------ reference helper methods
     def calDist(self, fts, prototype, scaler=20):
         """fts N x C x H x W, prototype 1 x C -> N x H x W   (net/rp_net.py:353-363; C must be 64)."""
@@ -255,4 +269,27 @@ class RP_Net(nn.Module):
         return fg_prototypes, bg_prototype
 
     def alignLoss(self, qry_fts, pred, supp_fts, fore_mask, back_mask):
-        raise NotImplementedError('alignLoss is train-only (net/rp_net.py:340); train-mode kernels are not built yet')
+        """net/rp_net.py:394-440 for one episode (value only; the differentiable path is the train-mode forward).
+        qry_fts 1 x C x h x w, pred 1 x (1+Wa) x h x w, supp_fts Wa x Sh x C x h x w, masks Wa x Sh x H x W; C == 64."""
+        n_ways, n_shots = len(fore_mask), len(fore_mask[0])
+        _, c, h, w = qry_fts.shape
+        H, W = fore_mask.shape[-2:]
+        dev = qry_fts.device
+        P, n = 1 + n_ways, n_ways * n_shots
+        qf = qry_fts.detach().float().permute(0, 2, 3, 1).contiguous()
+        sf = supp_fts.detach().float().reshape(n, c, h, w).permute(0, 2, 3, 1).contiguous()
+        fore = fore_mask.detach().float().reshape(n, H, W).contiguous()
+        back = back_mask.detach().float().reshape(n, H, W).contiguous()
+        f32 = torch.float32
+        qproto, counts = torch.empty(1, P, c, dtype=f32, device=dev), torch.empty(1, P, dtype=f32, device=dev)
+        amax = torch.empty(1, h, w, dtype=torch.int32, device=dev)
+        ops.class_pool(qf, pred.detach().float().contiguous(), qproto, counts, amax)
+        ps, wgt = torch.empty(n, 2, c, dtype=f32, device=dev), torch.empty(n, dtype=f32, device=dev)
+        ops.align_gather(qproto, counts, n_ways, n_shots, 1.0, ps, wgt)
+        pred_s = torch.empty(n, 2, h, w, dtype=f32, device=dev)
+        ops.cos_sim(sf, ps, pred_s, 20.0)
+        lg = torch.empty(n, 2, H, W, dtype=f32, device=dev)
+        ops.bilinear_up(pred_s.view(n * 2, h, w), lg.view(n * 2, H, W))
+        loss = torch.empty(1, dtype=f32, device=dev)
+        ops.ce_mask(lg, fore, back, wgt, torch.empty(n, 2, dtype=f32, device=dev), loss)
+        return loss[0]

@@ -1,0 +1,570 @@
+"""Train step of the RP-Net hot path on the C-ABI kernels: train-mode forward (batch-statistics BatchNorm per reference
+call), the hand-scheduled backward of every op on the path, the data-parallel gradient exchange and Adam.
+
+The reference trains through torch autograd over `RP_Net.forward` (net/rp_net.py:226-350) and ships no train script
+(SURVEY D9); the step reconstructed in SURVEY §3.5 is
+    loss = sum_i dice_ce(out['refinement'][i], query_labels) + align_loss_scaler * out['align_loss']
+    Adam(lr 1e-5, weight_decay 1e-4)                                  (yamls/example.yml:64-67,94,115)
+`TrainEngine.forward()/backward()` restate exactly the graph autograd would build for that forward; `TrainStep` adds
+the loss kernel, the bucketed NCCL all-reduce of the flat gradient buffer and the fused Adam kernel.
+
+Layout: activations fp16 NHWC, activation gradients bf16 NHWC, everything else fp32.  Parameters,
+gradients and Adam moments live in flat fp32 buffers; the nn.Parameters of the model are re-pointed into the flat
+parameter buffer (state_dict / load_state_dict keep working) and their `.grad` are views of the flat gradient buffer.
+
+With `soft_mask: False` the thresholded mask cuts the graph between refinement iterations (net/rp_net.py:309-311), so
+the T query `cre` calls are independent in the backward and are processed as ONE batched launch per kernel
+(T call groups); `soft_mask: True` training (back-propagation through the mask) is not built and raises.
+"""
+import torch
+
+from . import engine, ops
+
+bf16 = torch.bfloat16
+f16 = torch.float16
+f32 = torch.float32
+
+UNUSED_PREFIXES = ('cre.w_context.', 'cre.out.')        # never used by the reference forward: grad None
+
+
+def used_parameters(net):
+    return [(n, p) for n, p in net.named_parameters() if not n.startswith(UNUSED_PREFIXES)]
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient / Adam-moment buffers; model parameters become views of `param`."""
+
+    def __init__(self, net):
+        named = used_parameters(net)
+        dev = named[0][1].device
+        self.names = [n for n, _ in named]
+        self.offsets = {}
+        off = 0
+        for n, p in named:
+            self.offsets[n] = (off, p.numel())
+            off += (p.numel() + 3) // 4 * 4                      # keep every tensor 16-byte aligned
+        self.numel = off
+        self.param = torch.zeros(off, dtype=f32, device=dev)
+        self.grad = torch.zeros(off, dtype=f32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=f32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=f32, device=dev)
+        for n, p in named:
+            o, k = self.offsets[n]
+            self.param[o:o + k].copy_(p.data.reshape(-1))
+            p.data = self.param[o:o + k].view(p.shape)
+        self._named = named
+        self._first = named[0][1]
+        self._by_id = {id(p): n for n, p in named}
+
+    def grad_of(self, p):
+        """View of the flat gradient buffer that belongs to parameter `p`."""
+        o, k = self.offsets[self._by_id[id(p)]]
+        return self.grad[o:o + k].view(p.shape)
+
+    def alias_grads(self):
+        """p.grad = view of the flat gradient buffer (TrainStep: what loss.backward() would leave behind, without copies)."""
+        for n, p in self._named:
+            if p.grad is None or p.grad.data_ptr() != self.grad_of(p).data_ptr():
+                p.grad = self.grad_of(p)
+
+    def unalias_grads(self):
+        for n, p in self._named:
+            if p.grad is not None and p.grad.data_ptr() == self.grad_of(p).data_ptr():
+                p.grad = None
+
+    def attached(self):
+        return self._first.data_ptr() == self.param.data_ptr()
+
+    def span(self, prefixes):
+        """[lo, hi) of the flat range covering every parameter whose name starts with one of `prefixes`."""
+        lo, hi = self.numel, 0
+        for n in self.names:
+            if n.startswith(tuple(prefixes)):
+                o, k = self.offsets[n]
+                lo, hi = min(lo, o), max(hi, (o + k + 3) // 4 * 4)
+        return lo, hi
+
+
+# Gradient buckets in the order the backward finishes them (reverse of the forward / flat order).
+BUCKET_GROUPS = [('cre.',), ('encoder.Up_conv4.', 'encoder.Up4.'), ('encoder.Up_conv5.', 'encoder.Up5.'),
+                 ('encoder.Conv5.',), ('encoder.Conv4.', 'encoder.Conv3.', 'encoder.Conv2.', 'encoder.Conv1.')]
+
+
+class GradBuckets:
+    """Bucketed sum all-reduce of the flat gradient buffer (the one exchange step of the path).
+    `ready(i)` is called when bucket i's last gradient kernel has been enqueued; on CUDA the collective runs on a side
+    stream behind an event so that it overlaps the rest of the backward; `finish()` joins.  The 1/world averaging is
+    folded into the Adam kernel's grad_scale."""
+
+    def __init__(self, flat, world_size, group=None):
+        self.flat, self.world, self.group = flat, world_size, group
+        self.ranges = [flat.span(g) for g in BUCKET_GROUPS]
+        covered = sorted(self.ranges)
+        assert covered[0][0] == 0 and covered[-1][1] == flat.numel and all(a[1] == b[0] for a, b in zip(covered, covered[1:])), \
+            'gradient buckets must tile the flat buffer exactly once: %r' % (covered,)
+        self.cuda = flat.grad.is_cuda
+        self.stream = torch.cuda.Stream() if (self.cuda and world_size > 1) else None
+        self.pending = []
+
+    def ready(self, i):
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        lo, hi = self.ranges[i]
+        view = self.flat.grad[lo:hi]
+        if self.stream is None:
+            dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self.pending.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
+def shard_range(total, rank, world):
+    """Contiguous slice [lo, hi) of `total` independent slices owned by `rank`."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _ConvBN:
+    """One conv (bias dropped: it cancels in train-mode BN) + BatchNorm(batch stats) + ReLU of the path."""
+
+    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0)):
+        self.name, self.conv, self.bn, self.first, self.hole = name, conv, bn, first, hole
+        self.gw, self.ggamma, self.gbeta = flat.grad_of(conv.weight), flat.grad_of(bn.weight), flat.grad_of(bn.bias)
+        k = conv.kernel_size[0]
+        d = conv.dilation[0]
+        self.taps = [((ky - k // 2) * d, (kx - k // 2) * d) for ky in range(k) for kx in range(k)]
+        self.cout = conv.out_channels
+        self.cin_pack = conv.in_channels + hole[1]
+        dev = conv.weight.device
+        if not first:
+            self.wf = torch.empty(len(self.taps), self.cout, self.cin_pack, dtype=f16, device=dev)
+            self.wd = torch.empty(len(self.taps), self.cin_pack, self.cout, dtype=bf16, device=dev)
+        self.ones = torch.ones(self.cout, dtype=f32, device=dev)
+        self.zeros = torch.zeros(self.cout, dtype=f32, device=dev)
+
+    def pack(self):
+        if not self.first:
+            ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole)
+
+    def conv_fwd(self, x0, x1, z):
+        if self.first:
+            ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z)
+        else:
+            ops.conv_igemm(x0, self.wf, self.taps, self.ones, self.zeros, False, src1=x1, out=z)
+
+    def bn_fwd(self, z, gs, sums, stats, y=None, pool=None, y32=None):
+        n, h, w, c = z.shape
+        bn = self.bn
+        ops.bn_stats(z, gs, sums)
+        ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
+        ops.bn_apply(z, stats, gs, True, y=y, y_pool=pool, y_f32=y32)
+
+    def bwd(self, eng, x0, x1, z, stats, gs, dx=None, **src):
+        """BN+ReLU backward -> dz; weight gradient; data gradient into `dx` (bf16 [n,h,w,cin_pack]) when given."""
+        n, h, w, c = z.shape
+        dz = eng.scratch('dz', n * h * w * c, bf16).view(n, h, w, c)
+        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 4, f32), True,
+                   dgamma=self.ggamma, dbeta=self.gbeta, **src)
+        if self.first:
+            ops.conv3x3_first_wgrad(x0, dz, self.gw)
+        else:
+            c0 = x0.shape[3]
+            c1 = 0 if x1 is None else x1.shape[3]
+            nb = ops.conv_wgrad_workspace_bytes(c0, c1, n, h, w, len(self.taps), self.cout)
+            ops.conv_wgrad(x0, dz, self.taps, self.gw, eng.scratch('wgrad', nb // 4, f32), x1=x1, hole=self.hole,
+                           accumulate=False)
+            if dx is not None:
+                ops.conv_dgrad(dz, self.wd, self.taps, dx)
+        return dx
+
+
+class TrainEngine:
+    """Train-mode forward + backward of RP_Net (U-Net backbone) on the C-ABI kernels."""
+
+    def __init__(self, net):
+        from .nn.unet import U_Net
+        if not isinstance(net.encoder, U_Net):
+            raise NotImplementedError("training is built for backbone 'UNet' (the reference cannot train 'vgg': SURVEY D1)")
+        if net.backbone_cfg['soft_mask']:
+            raise NotImplementedError('soft_mask: True training (gradient through the recurrent mask) is not built')
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
+        self.net, self.dev = net, dev
+        self.flat = FlatParams(net)
+        e, c = net.encoder, net.cre
+        L = {}
+        for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
+                        ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
+            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'))
+            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat)
+        k = (2 * c.radius + 1) ** 2
+        self.kcorr, self.corr_c = k, c.corr_channels
+        L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
+        L['wq'] = _ConvBN('wq', c.w_q[0], c.w_q[1], self.flat)
+        L['q'] = _ConvBN('q', c.q[0], c.q[1], self.flat, hole=(k, self.corr_c - k))
+        self.L = L
+        self.ws = engine.Workspace()
+        self._scratch = {}
+        self.saved = None
+
+    @staticmethod
+    def of(net):
+        """The (cached) engine of `net`; rebuilt when the parameters were moved (e.g. net.to(other_device))."""
+        eng = net.__dict__.get('_b200_train_engine')
+        if eng is None or not eng.flat.attached():
+            eng = TrainEngine(net)
+            net.__dict__['_b200_train_engine'] = eng
+        return eng
+
+    # ------------------------------------------------------------------ buffers
+    def buf(self, name, shape, dtype):
+        return self.ws.get(name, shape, dtype, self.dev)
+
+    def scratch(self, name, numel, dtype):
+        """Grow-only scratch (contents dead after the call that uses it)."""
+        t = self._scratch.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(int(numel), dtype=dtype, device=self.dev)
+            self._scratch[name] = t
+        return t[:numel]
+
+    def pack_weights(self):
+        for l in self.L.values():
+            l.pack()
+
+    # ------------------------------------------------------------------ encoder
+    def _layer_fwd(self, key, x0, x1, gs, want_y=True, want_pool=False):
+        l = self.L[key]
+        n, h, w = (x0.shape[0], x0.shape[2], x0.shape[3]) if l.first else x0.shape[:3]
+        c = l.cout
+        z = self.buf(key + '.z', (n, h, w, c), f16)
+        stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
+        y = self.buf(key + '.y', (n, h, w, c), f16) if want_y else None
+        pool = self.buf(key + '.pool', (n, h // 2, w // 2, c), f16) if want_pool else None
+        l.conv_fwd(x0, x1, z)
+        l.bn_fwd(z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, f32), stats, y=y, pool=pool)
+        self.act[key] = dict(x0=x0, x1=x1, z=z, stats=stats, gs=gs)
+        return y, pool
+
+    def _encoder_fwd(self, imgs, gs):
+        """net/unet.py:435-467 in train mode; `gs` = BatchNorm call groups (support pass, query pass: net/rp_net.py:248,257)."""
+        f = self._layer_fwd
+        a, _ = f('c1a', imgs, None, gs)
+        _, p1 = f('c1b', a, None, gs, want_y=False, want_pool=True)
+        a, _ = f('c2a', p1, None, gs)
+        _, p2 = f('c2b', a, None, gs, want_y=False, want_pool=True)
+        a, _ = f('c3a', p2, None, gs)
+        x3, p3 = f('c3b', a, None, gs, want_pool=True)
+        a, _ = f('c4a', p3, None, gs)
+        x4, p4 = f('c4b', a, None, gs, want_pool=True)
+        a, _ = f('c5a', p4, None, gs)
+        x5, _ = f('c5b', a, None, gs)
+        n = imgs.shape[0]
+        u = self.buf('up5.in', (n, x5.shape[1] * 2, x5.shape[2] * 2, x5.shape[3]), f16)
+        ops.upsample2x(x5, u)                                         # net/modules.py:67
+        u5, _ = f('up5', u, None, gs)
+        a, _ = f('uc5a', x4, u5, gs)                                  # torch.cat((x4, d5), dim=1)  net/unet.py:460
+        d5, _ = f('uc5b', a, None, gs)
+        u = self.buf('up4.in', (n, d5.shape[1] * 2, d5.shape[2] * 2, d5.shape[3]), f16)
+        ops.upsample2x(d5, u)
+        u4, _ = f('up4', u, None, gs)
+        a, _ = f('uc4a', x3, u4, gs)                                  # torch.cat((x3, d4), dim=1)  net/unet.py:464
+        d4, _ = f('uc4b', a, None, gs)
+        return d4
+
+    def _layer_bwd(self, key, dx_shape=None, **src):
+        a = self.act[key]
+        dx = self.buf(key + '.dx', dx_shape, bf16) if dx_shape is not None else None
+        return self.L[key].bwd(self, a['x0'], a['x1'], a['z'], a['stats'], a['gs'], dx=dx, **src)
+
+    def _encoder_bwd(self, g_d4, buckets=None):
+        b = self._layer_bwd
+        A = self.act
+        shp = lambda key: tuple(A[key]['x0'].shape)
+        cat = lambda key: tuple(A[key]['x0'].shape[:3]) + (A[key]['x0'].shape[3] + A[key]['x1'].shape[3],)
+        g = b('uc4b', shp('uc4b'), direct=g_d4)
+        dcat4 = b('uc4a', cat('uc4a'), direct=g)
+        c3 = A['uc4a']['x0'].shape[3]
+        du = b('up4', shp('up4'), direct=dcat4, d_off=c3)
+        if buckets:
+            buckets.ready(1)
+        g = b('uc5b', shp('uc5b'), up=du)
+        dcat5 = b('uc5a', cat('uc5a'), direct=g)
+        c4 = A['uc5a']['x0'].shape[3]
+        du = b('up5', shp('up5'), direct=dcat5, d_off=c4)
+        if buckets:
+            buckets.ready(2)
+        g = b('c5b', shp('c5b'), up=du)
+        dp4 = b('c5a', shp('c5a'), direct=g)
+        if buckets:
+            buckets.ready(3)
+        g = b('c4b', shp('c4b'), direct=dcat5, d_off=0, pooled=dp4)
+        dp3 = b('c4a', shp('c4a'), direct=g)
+        g = b('c3b', shp('c3b'), direct=dcat4, d_off=0, pooled=dp3)
+        dp2 = b('c3a', shp('c3a'), direct=g)
+        g = b('c2b', shp('c2b'), pooled=dp2)
+        dp1 = b('c2a', shp('c2a'), direct=g)
+        n, _, H, W = A['c1a']['x0'].shape
+        g = b('c1b', (n, H, W, 64), pooled=dp1)
+        b('c1a', None, direct=g)
+        if buckets:
+            buckets.ready(4)
+
+    # ------------------------------------------------------------------ context-relation encoder
+    def _cre_fwd(self, d4, mask, lo, hi, g0, gs):
+        """ContextCorrelationEncoder.forward (net/rp_net.py:77-84) in train mode on images [lo, hi) of the batched cre
+        buffers; `gs` = call groups relative to lo, stored from stats row g0."""
+        S = self.cre
+        L = self.L
+        n = hi - lo
+        xfg, xbg = S['xfg'][lo:hi], S['xbg'][lo:hi]
+        ops.premask(d4, mask, xfg, xbg)
+        G = len(gs) - 1
+        sums = self.scratch('bn_sums', G * 256 * 2, f32)
+        L['wk'].conv_fwd(xfg, None, S['z1'][lo:hi])
+        L['wk'].bn_fwd(S['z1'][lo:hi], gs, sums, S['st1'][g0:g0 + G], y=S['fm1'][lo:hi])
+        L['wq'].conv_fwd(xbg, None, S['z2'][lo:hi])
+        L['wq'].bn_fwd(S['z2'][lo:hi], gs, sums, S['st2'][g0:g0 + G], y=S['fm2'][lo:hi])
+        ops.local_corr(S['fm1'][lo:hi], S['fm2'][lo:hi], self.net.cre.radius, S['corr'][lo:hi])
+        L['q'].conv_fwd(S['corr'][lo:hi], S['fm1'][lo:hi], S['z3'][lo:hi])
+        L['q'].bn_fwd(S['z3'][lo:hi], gs, sums, S['st3'][g0:g0 + G], y32=S['feat'][lo:hi])
+        return S['feat'][lo:hi]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, d):
+        """d: dict with the RP_Net.forward arguments (supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_labels) on the
+        device.  Returns (logits [T, B, 1+Wa, H, W] fp32 = out['refinement'][i], align_loss [1] fp32 tensor)."""
+        net = self.net
+        if not self.flat.attached():
+            raise RuntimeError('model parameters were moved after TrainEngine was created; build a new TrainEngine')
+        supp_imgs, qry_imgs = d['supp_imgs'], d['qry_imgs']
+        Wa, Sh = len(supp_imgs), len(supp_imgs[0])
+        if len(qry_imgs) != 1:
+            raise NotImplementedError('the reference forward only consumes qry_imgs[0] (net/rp_net.py:283)')
+        B = supp_imgs[0][0].shape[0]
+        H, W = qry_imgs[0].shape[-2:]
+        S, T, P = net.scale, net.num_iter, 1 + Wa
+        n_supp = Wa * Sh * B
+        n_img = n_supp + B
+        self.act = {}
+        engine.WEIGHTS_EPOCH += 1          # BN running statistics are updated through raw pointers below
+
+        imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
+        d4 = self._encoder_fwd(imgs, [0, n_supp, n_img])             # two BN calls: support pass, query pass (D14)
+        h, w, C = d4.shape[1:]
+        if h * S != H or w * S != W:
+            raise ValueError('scale=%d does not match the encoder stride' % S)
+        fore = torch.stack([torch.stack(way, dim=0) for way in d['fore_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
+        back = torch.stack([torch.stack(way, dim=0) for way in d['back_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
+
+        n_tot = n_supp + T * B
+        G_tot = Wa * Sh + T
+        buf = self.buf
+        self.cre = dict(
+            xfg=buf('cre.xfg', (n_tot, h, w, C), f16), xbg=buf('cre.xbg', (n_tot, h, w, C), f16),
+            z1=buf('cre.z1', (n_tot, h, w, C), f16), z2=buf('cre.z2', (n_tot, h, w, C), f16),
+            fm1=buf('cre.fm1', (n_tot, h, w, C), f16), fm2=buf('cre.fm2', (n_tot, h, w, C), f16),
+            corr=buf('cre.corr', (n_tot, h, w, self.corr_c), f16), z3=buf('cre.z3', (n_tot, h, w, 64), f16),
+            feat=buf('cre.feat', (n_tot, h, w, 64), f32),
+            st1=buf('cre.st1', (G_tot, C, 4), f32), st2=buf('cre.st2', (G_tot, C, 4), f32), st3=buf('cre.st3', (G_tot, 64, 4), f32))
+
+        # support branch: one cre CALL per (way, shot) (net/rp_net.py:271-275; oracle-ext), batched as Wa*Sh call groups
+        supp_m = buf('supp_m', (n_supp, h, w), f32)
+        ops.avgpool_mask(fore, S, supp_m)
+        supp_feat = self._cre_fwd(d4[:n_supp], supp_m, 0, n_supp, 0, [i * B for i in range(Wa * Sh + 1)])
+
+        # prototypes (net/rp_net.py:288-299, 366-391), hoisted out of the T loop (D6)
+        wf, wb = buf('wmap_f', (n_supp, h, w), f32), buf('wmap_b', (n_supp, h, w), f32)
+        sf, sb = buf('msum_f', (n_supp,), f32), buf('msum_b', (n_supp,), f32)
+        ops.bilinear_adjoint(fore, wf, sf)
+        ops.bilinear_adjoint(back, wb, sb)
+        raw = buf('proto_raw', (Wa, Sh, B, 2, 64), f32)
+        ops.weighted_pool(supp_feat, wf, wb, sf, sb, raw.view(n_supp, 2, 64))
+        protos = buf('protos', (B, P, 64), f32)
+        ops.proto_finalize(raw, protos)
+
+        # recurrent refinement (net/rp_net.py:280-312)
+        qm = buf('qry_m', (T + 1, B, h, w), f32)
+        ops.avgpool_mask(d['appr_query_labels'].reshape(B, H, W).float().contiguous(), S, qm[0])
+        pred = buf('pred', (T, B, P, h, w), f32)
+        logits = buf('logits', (T, B, P, H, W), f32)
+        qd4 = d4[n_supp:]
+        for i in range(T):
+            lo = n_supp + i * B
+            qfeat = self._cre_fwd(qd4, qm[i], lo, lo + B, Wa * Sh + i, [0, B])
+            ops.cos_sim(qfeat, protos, pred[i], 20.0)
+            ops.upsample_tail(pred[i], logits[i], qm[i + 1], S, False)
+
+        # alignLoss (net/rp_net.py:340-343, 394-440) on the last iteration's features / prediction (D5)
+        align = buf('align', (1,), f32)
+        use_align = bool(net.config.get('align', False))
+        if use_align:
+            lo = n_supp + (T - 1) * B
+            qproto, counts = buf('al.qproto', (B, P, 64), f32), buf('al.counts', (B, P), f32)
+            amax = buf('al.amax', (B, h, w), torch.int32)
+            ops.class_pool(self.cre['feat'][lo:lo + B], pred[T - 1], qproto, counts, amax)
+            ps, wgt = buf('al.ps', (n_supp, 2, 64), f32), buf('al.w', (n_supp,), f32)
+            ops.align_gather(qproto, counts, Wa, Sh, 1.0, ps, wgt)
+            pred_s = buf('al.pred_s', (n_supp, 2, h, w), f32)
+            ops.cos_sim(supp_feat, ps, pred_s, 20.0)
+            lg = buf('al.lg', (n_supp, 2, H, W), f32)
+            ops.bilinear_up(pred_s.view(n_supp * 2, h, w), lg.view(n_supp * 2, H, W))
+            self._align_args = (lg, fore, back, wgt)
+            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, f32), align)
+        else:
+            align.zero_()
+        self.saved = dict(Wa=Wa, Sh=Sh, B=B, H=H, W=W, h=h, w=w, C=C, T=T, P=P, n_supp=n_supp, n_tot=n_tot, d4=d4, supp_m=supp_m,
+                          wf=wf, wb=wb, sf=sf, sb=sb, protos=protos, qm=qm, pred=pred, logits=logits, use_align=use_align)
+        return logits, align
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogits, dalign=1.0, buckets=None):
+        """dlogits: fp32 [T, B, P, H, W] = d loss / d out['refinement'][i]; dalign = d loss / d out['align_loss'] (float).
+        Fills the flat gradient buffer (+=: zero it first with zero_grad())."""
+        s = self.saved
+        if s is None:
+            raise RuntimeError('backward() without forward()')
+        Wa, Sh, B, H, W, h, w, C, T, P = (s[k] for k in ('Wa', 'Sh', 'B', 'H', 'W', 'h', 'w', 'C', 'T', 'P'))
+        n_supp, n_tot = s['n_supp'], s['n_tot']
+        S, L, buf = self.cre, self.L, self.buf
+        G_tot = Wa * Sh + T
+        gs_all = [i * B for i in range(G_tot + 1)]
+
+        # logits -> pred (adjoint of the bilinear upsample, net/rp_net.py:303) -> query features / prototypes (calDist)
+        dpred = buf('b.dpred', (T, B, P, h, w), f32)
+        ops.bilinear_adjoint(dlogits.view(T * B * P, H, W), dpred.view(T * B * P, h, w))
+        dfeat = buf('b.dfeat', (n_tot, h, w, 64), f32)
+        dprotos = buf('b.dprotos', (B, P, 64), f32)
+        dprotos.zero_()
+        ops.cos_sim_bwd(S['feat'][n_supp:], s['protos'], dpred.view(T * B, P, h, w), dfeat[n_supp:], dprotos, 20.0)
+        if s['use_align'] and dalign != 0.0:
+            lg, fore, back, wgt = self._align_args
+            dlg = self.scratch('b.dlg', lg.numel(), f32).view(lg.shape)
+            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, f32), buf('b.align', (1,), f32), dlg, float(dalign))
+            dpred_s = buf('b.dpred_s', (n_supp, 2, h, w), f32)
+            ops.bilinear_adjoint(dlg.view(n_supp * 2, H, W), dpred_s.view(n_supp * 2, h, w))
+            dps = buf('b.dps', (n_supp, 2, 64), f32)
+            dps.zero_()
+            ops.cos_sim_bwd(S['feat'][:n_supp], buf('al.ps', (n_supp, 2, 64), f32), dpred_s, dfeat[:n_supp], dps, 20.0)
+            dqp = buf('b.dqp', (B, P, 64), f32)
+            ops.align_scatter(dps, Wa, Sh, dqp)
+            lo = n_supp + (T - 1) * B
+            ops.class_pool_bwd(dqp, buf('al.counts', (B, P), f32), buf('al.amax', (B, h, w), torch.int32), dfeat[lo:lo + B])
+            acc = True
+        else:
+            acc = False
+        draw = buf('b.draw', (Wa, Sh, B, 2, 64), f32)
+        ops.proto_finalize_bwd(dprotos, draw)
+        ops.weighted_pool_bwd(draw.view(n_supp, 2, 64), s['wf'], s['wb'], s['sf'], s['sb'], dfeat[:n_supp], accumulate=acc)
+
+        # cre backward, all Wa*Sh + T calls as one batched launch per kernel
+        dq = buf('b.dq', (n_tot, h, w, self.corr_c + C), bf16)
+        L['q'].bwd(self, S['corr'], S['fm1'], S['z3'], S['st3'], gs_all, dx=dq, direct=dfeat)
+        df1, df2 = buf('b.df1', (n_tot, h, w, C), bf16), buf('b.df2', (n_tot, h, w, C), bf16)
+        ops.local_corr_bwd(S['fm1'], S['fm2'], dq, self.corr_c, self.net.cre.radius, df1, df2)
+        dxfg, dxbg = buf('b.dxfg', (n_tot, h, w, C), bf16), buf('b.dxbg', (n_tot, h, w, C), bf16)
+        L['wk'].bwd(self, S['xfg'], None, S['z1'], S['st1'], gs_all, dx=dxfg, direct=df1)
+        L['wq'].bwd(self, S['xbg'], None, S['z2'], S['st2'], gs_all, dx=dxbg, direct=df2)
+        if buckets:
+            buckets.ready(0)
+        g_d4 = buf('b.g_d4', tuple(s['d4'].shape), bf16)
+        ops.premask_bwd(dxfg[:n_supp], dxbg[:n_supp], s['supp_m'], g_d4[:n_supp], iters=1)
+        ops.premask_bwd(dxfg[n_supp:], dxbg[n_supp:], s['qm'][:T], g_d4[n_supp:], iters=T)
+        self._encoder_bwd(g_d4, buckets)
+
+    def zero_grad(self):
+        self.flat.grad.zero_()
+
+
+class TrainStep:
+    """One optimisation step: pack weights -> forward -> dice_ce (+grad) -> backward -> all-reduce -> Adam."""
+
+    def __init__(self, net, world_size=1, lr=1e-5, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, align_loss_scaler=1.0,
+                 process_group=None):
+        self.eng = TrainEngine.of(net)
+        self.eng.flat.alias_grads()
+        self.net, self.world = net, world_size
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.align_scaler = float(align_loss_scaler)
+        self.buckets = GradBuckets(self.eng.flat, world_size, process_group)
+        self.t = 0
+        self.last = {}
+
+    def forward_backward(self, d):
+        """Loss + gradients (flat buffer / p.grad) without the optimizer: what loss.backward() leaves behind."""
+        eng = self.eng
+        eng.flat.alias_grads()
+        eng.zero_grad()
+        eng.pack_weights()
+        logits, align = eng.forward(d)
+        T, B, P, H, W = logits.shape
+        dlogits = eng.scratch('dlogits', logits.numel(), f32).view(logits.shape)
+        losses = eng.buf('losses', (T,), f32)
+        ops.dice_ce(logits, d['query_labels'].contiguous(), eng.scratch('dice.sums', T * (2 * P + 1), f32), losses, dlogits, 1.0)
+        eng.backward(dlogits, self.align_scaler, self.buckets)
+        self.buckets.finish()
+        loss = losses.sum() + self.align_scaler * align[0]
+        self.last = {'loss': loss, 'dice_ce': losses, 'align_loss': align, 'logits': logits}
+        return loss
+
+    def step(self, d):
+        loss = self.forward_backward(d)
+        self.t += 1
+        f = self.eng.flat
+        ops.adam(f.param, f.grad, f.exp_avg, f.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.wd, 1.0 / self.world)
+        engine.WEIGHTS_EPOCH += 1
+        return loss
+
+
+class _TrainForward(torch.autograd.Function):
+    """Autograd bridge for `RP_Net.forward` in train mode: the forward runs TrainEngine.forward, the backward runs the
+    hand-scheduled kernel backward and hands the per-parameter gradients to autograd (which accumulates them into
+    `p.grad` exactly as it does for the reference's graph).  `TrainStep` bypasses this bridge (no gradient copies)."""
+
+    @staticmethod
+    def forward(ctx, eng, d, *params):
+        eng.pack_weights()
+        logits, align = eng.forward(d)
+        ctx.eng = eng
+        ctx.token = eng.saved
+        return logits.clone(), align.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits, dalign):
+        eng = ctx.eng
+        if eng.saved is not ctx.token:
+            raise RuntimeError('rpnet_b200: backward through a train-mode forward that is not the most recent one of this '
+                               'model (activations are kept for one forward at a time)')
+        eng.flat.unalias_grads()
+        eng.zero_grad()
+        dl = torch.zeros_like(eng.saved['logits']) if dlogits is None else dlogits.contiguous().float()
+        da = 0.0 if dalign is None else float(dalign.reshape(-1)[0].item())
+        eng.backward(dl, da)
+        return (None, None) + tuple(eng.flat.grad_of(p).clone() for _, p in eng.flat._named)
+
+
+def train_forward(net, d):
+    """out['refinement'] logits [T, B, 1+Wa, H, W] and out['align_loss'] [1] of a train-mode RP_Net.forward, attached to
+    the autograd graph when gradients are enabled."""
+    eng = TrainEngine.of(net)
+    if torch.is_grad_enabled():
+        return _TrainForward.apply(eng, d, *[p for _, p in eng.flat._named])
+    eng.pack_weights()
+    logits, align = eng.forward(d)
+    return logits.clone(), align.clone()

@@ -1,0 +1,244 @@
+"""Train-step parity (rpnet_b200.train) against (a) the golden train step recorded from the unmodified reference
+(tests/golden/train_step.npz: loss, logits, per-parameter gradient norms / heads, BN running statistics) and (b) the CPU
+oracle + torch autograd on the same seeded inputs, incl. the Wa x Sh generalisation.
+
+Tolerances: train-mode logits rel-Linf 5e-3 — the pre-BN conv output z AND the activation y are each
+rounded to fp16 once per layer (eval mode rounds once: 1e-3), reproduced by rounding the oracle the same way
+(3.9e-3 on the golden case); loss rel 2e-3; per-parameter gradient rel-L2 3e-2 for tensors that carry signal (bf16
+gradient operands); BN running stats 1e-3.  The hard mask (net/rp_net.py:310) makes iteration i+1 discontinuous in
+iteration i's logits: when a near-tie pixel flips, later iterations are compared through the flipped fraction only."""
+LOGIT_TOL = 5e-3
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import _lib
+    _lib.load()
+    return torch.device('cuda:0')
+
+
+def _cfg(T):
+    return dict(unet_normalize_type='BatchNorm2d', final_activation='sigmoid', mask_feature_map=False,
+                n_iter_refinement=T, soft_mask=False, mask_refinement_correlation_radius=5)
+
+
+def _net(sd, T, dev):
+    from net.model import model_factory
+    net = model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=_cfg(T))
+    net.load_state_dict(sd)
+    return net.to(dev).train()
+
+
+def _oracle_step(sd, T, ep):
+    from oracle import rpnet_oracle as O
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    out = O.forward(sd, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'],
+                    training=True)
+    loss = O.train_loss(out, ep['query_labels'])
+    loss.backward()
+    return out, loss.detach(), params
+
+
+def _check_train_logits(got, refs):
+    """got: [T, B, P, H, W] device tensor; refs: list of T reference logits.  Strict per-iteration comparison while the
+    recurrent masks agree; after a near-tie flip only the flipped fraction is bounded."""
+    masks_agree = True
+    for i, ref in enumerate(refs):
+        g = got[i].float().cpu()
+        if masks_agree:
+            rel = ((g - ref).abs().max() / ref.abs().max()).item()
+            assert rel < LOGIT_TOL, ('logits', i, rel)
+        flipped = ((g[:, 1:].sum(1) > g[:, 0]) != (ref[:, 1:].sum(1) > ref[:, 0])) if g.shape[1] == 2 else (g.argmax(1) != ref.argmax(1))
+        assert flipped.float().mean().item() < 2e-3, ('mask flips', i, flipped.float().mean().item())
+        top2 = ref.topk(2, dim=1).values
+        assert not (flipped & ((top2[:, 0] - top2[:, 1]) > 4 * LOGIT_TOL * ref.abs().max())).any() or not masks_agree, \
+            'argmax differs away from ties at iteration %d' % i
+        masks_agree = masks_agree and not flipped.any()
+    return masks_agree
+
+
+def _check_grads(net, ref_grads, tol=3e-2):
+    """ref_grads: name -> tensor or None.  Gradients that are pure cancellation noise in the reference (conv biases in
+    front of train-mode BN: analytically zero) are compared on absolute scale."""
+    worst = 0.0
+    for name, p in net.named_parameters():
+        rg = ref_grads[name]
+        if rg is None:
+            assert name.startswith(('cre.w_context', 'cre.out')), name
+            assert p.grad is None, name
+            continue
+        g = p.grad.float().cpu()
+        if name.endswith('.bias') and ('.conv.0.' in name or '.conv.3.' in name or '.up.1.' in name or name in
+                                       ('cre.w_k.0.bias', 'cre.w_q.0.bias', 'cre.q.0.bias')):
+            # conv bias followed by batch-statistics BN: exact gradient is 0; the reference holds rounding noise
+            assert g.abs().max().item() <= 1e-6 + 10 * rg.abs().max().item(), name
+            continue
+        rel = ((g - rg).norm() / rg.norm().clamp_min(1e-12)).item()
+        worst = max(worst, rel)
+        assert rel < tol, '%s: gradient rel-L2 %.3e' % (name, rel)
+    return worst
+
+
+def test_train_step_vs_reference_golden(dev, golden):
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    g = golden('train_step')
+    T = int(g['T'])
+    sd = weights.unet_rpnet_state_dict(int(g['w_seed']))
+    ep = make_episode(int(g['B']), size=int(g['size']), seed=int(g['ep_seed']))
+    net = _net(sd, T, dev)
+    ts = TrainStep(net)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    _check_train_logits(ts.last['logits'], [torch.from_numpy(g['out%d' % i]) for i in range(T)])
+    ref_loss = float(g['loss'])
+    assert abs(loss.item() - ref_loss) / abs(ref_loss) < 2e-3, (loss.item(), ref_loss)
+    assert abs(ts.last['align_loss'].item() - float(g['align'])) < 2e-3 * max(1.0, abs(float(g['align'])))
+    named = dict(net.named_parameters())
+    for name, n_ref, head in zip(g['names'], g['grad_norm'], g['grad_head']):
+        p = named[str(name)]
+        if n_ref < 0:
+            assert p.grad is None, name
+            continue
+        if n_ref < 1e-6:                      # conv biases in front of BN: analytically zero
+            assert p.grad.norm().item() < 1e-5, name
+            continue
+        assert abs(p.grad.norm().item() - n_ref) / n_ref < 3e-2, (name, p.grad.norm().item(), n_ref)
+        h = p.grad.reshape(-1)[:4].cpu().numpy() if p.grad.numel() >= 4 else None
+        if h is not None:
+            assert np.abs(h - head).max() <= 6e-2 * max(np.abs(head).max(), n_ref / np.sqrt(p.numel())), (name, h, head)
+    bn = {k: v for k, v in net.state_dict().items() if 'running' in k or 'num_batches' in k}
+    assert list(g['bn_keys']) == list(bn.keys())
+    got = np.array([v.double().sum().item() for v in bn.values()])
+    np.testing.assert_allclose(got, g['bn_sums'], rtol=1e-3, atol=1e-3)
+    assert int(net.state_dict()['encoder.Conv1.conv.1.num_batches_tracked']) == 2       # D14
+    assert int(net.state_dict()['cre.w_k.1.num_batches_tracked']) == 1 + T
+
+
+@pytest.mark.parametrize('ways,shots,B,size,T', [(1, 1, 2, 64, 2), (2, 2, 2, 64, 2), (1, 5, 2, 64, 3), (1, 1, 1, 128, 1)])
+def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T):
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    sd = weights.unet_rpnet_state_dict(0)
+    ep = make_episode(B, ways, shots, size, seed=7)
+    net = _net({k: v.clone() for k, v in sd.items()}, T, dev)
+    ts = TrainStep(net)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    out, ref_loss, params = _oracle_step(sd, T, ep)
+    _check_train_logits(ts.last['logits'], [out['refinement'][i].detach() for i in range(T)])
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 2e-3
+    ref_grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
+    _check_grads(net, ref_grads)
+    for k, v in net.state_dict().items():
+        if 'running' in k:
+            torch.testing.assert_close(v.cpu(), sd[k], rtol=1e-3, atol=1e-3, msg=k)
+        elif 'num_batches' in k:
+            assert int(v) == int(sd[k]), k
+
+
+def test_adam_step_and_eval_after_training(dev):
+    """step() = forward_backward + Adam on the flat buffers (torch.optim.Adam semantics, yamls/example.yml:64-67); the eval
+    forward afterwards must see the updated weights and running statistics (packed-weight caches are invalidated)."""
+    from oracle import rpnet_oracle as O
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    T = 2
+    sd = weights.unet_rpnet_state_dict(0)
+    ep = make_episode(2, 1, 1, 64, seed=11)
+    d = to_device(ep, dev)
+    net = _net({k: v.clone() for k, v in sd.items()}, T, dev)
+    net.eval()
+    with torch.no_grad():
+        before = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])['output'].clone()
+    net.train()
+    ts = TrainStep(net, lr=1e-3, weight_decay=1e-4)
+    p0 = {n: p.detach().clone() for n, p in net.named_parameters()}
+    ts.step(d)
+    torch.cuda.synchronize()
+    g = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    for n, p in net.named_parameters():
+        if n not in g:
+            assert torch.equal(p, p0[n]), n                      # unused parameters are not touched (grad None in torch)
+            continue
+        ref = p0[n].clone().requires_grad_(True)
+        opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=1e-4)
+        ref.grad = g[n]
+        opt.step()
+        torch.testing.assert_close(p.detach(), ref.detach(), rtol=1e-5, atol=1e-7, msg=n)
+    # eval forward after the step == oracle eval forward on the updated state_dict
+    net.eval()
+    sd1 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        after = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])['output']
+        ref = O.forward(sd1, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'])['output']
+    assert not torch.equal(after, before)
+    rel = ((after.cpu() - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 1e-3, rel
+
+
+def test_loss_decreases_over_steps(dev):
+    """A few steps at a larger learning rate on one episode: the reconstructed loss goes down (end-to-end sanity of
+    forward + backward + Adam signs)."""
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    net = _net(weights.unet_rpnet_state_dict(0), 2, dev)
+    ts = TrainStep(net, lr=1e-4)
+    d = to_device(make_episode(2, 1, 2, 64, seed=5), dev)
+    losses = [ts.step(d).item() for _ in range(8)]
+    assert losses[-1] < losses[0], losses
+
+
+def test_module_train_forward_is_differentiable(dev):
+    """The reference's training surface: net.train(); out = net(...); loss(out).backward() through torch autograd
+    (net/rp_net.py:226-350 + dice_ce :123-127).  Gradients land in p.grad like the reference's and match the oracle."""
+    from net.rp_net import dice_ce
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    T = 2
+    sd = weights.unet_rpnet_state_dict(0)
+    ep = make_episode(2, 1, 2, 64, seed=9)
+    d = to_device(ep, dev)
+    net = _net({k: v.clone() for k, v in sd.items()}, T, dev)
+    out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], query_labels=d['query_labels'],
+              appr_query_labels=d['appr_query_labels'])
+    assert set(out.keys()) == {'output', 'align_loss', 'refinement'} and out['output'].requires_grad
+    assert torch.equal(out['output'], out['refinement'][T - 1])
+    loss = sum(dice_ce(out['refinement'][i], d['query_labels']) for i in range(T)) + 1.0 * out['align_loss']
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_out, ref_loss, params = _oracle_step(sd, T, ep)
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 2e-3
+    _check_grads(net, {k: p.grad for k, p in params.items()})
+    # a second backward pass accumulates into p.grad like autograd does for the reference
+    g1 = net.encoder.Conv3.conv[0].weight.grad.clone()
+    out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
+    out['output'].sum().backward()
+    assert not torch.equal(net.encoder.Conv3.conv[0].weight.grad, g1)
+    with pytest.raises(AttributeError):
+        net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'])           # appr_query_labels is required (:269)
+
+
+def test_align_loss_method_vs_reference_golden(dev, golden):
+    """RP_Net.alignLoss (net/rp_net.py:394-440) on the reference's golden case (Wa=2, Sh=2)."""
+    from oracle import weights
+    gz = golden('proto_loss')
+    net = _net(weights.unet_rpnet_state_dict(0), 1, dev)
+    t = lambda k: torch.from_numpy(gz[k]).to(dev)
+    got = net.alignLoss(t('a_q'), t('a_pred'), t('a_s'), t('a_f'), t('a_b'))
+    torch.testing.assert_close(got.cpu(), torch.from_numpy(gz['align']), rtol=1e-5, atol=1e-6)
