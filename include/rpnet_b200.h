@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header (bumped on any signature change). */
-int rpnet_abi_version(void);
+int rpnet_abi_version(void);   /* currently 3 */
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* rpnet_last_error(void);
@@ -145,6 +145,16 @@ int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, in
  * sums[g][c] = {sum z, sum z^2} over the images of call group g.  z fp16 NHWC. */
 int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
                        void* stream);
+
+/* Train-mode conv: z = conv(src0 | src1) without bias (it cancels inside batch-statistics BatchNorm) stored as fp16 NHWC
+ * [n][h][w][cout], and the BatchNorm statistics of z in the same launch: sums[g][cout] = {sum z, sum z^2} over call group g,
+ * accumulated from the fp32 accumulators in the conv epilogue (per-CTA shared-memory partials, one atomic flush per group;
+ * when a pixel tile would straddle two call groups — maps smaller than a tile — the statistics pass runs as
+ * rpnet_bn_stats_f16 instead).  ones / zeros: fp32 [cout] constant vectors (the epilogue's affine is the identity).
+ * Replaces nn.Conv2d + the statistics half of nn.BatchNorm2d(train): net/modules.py:47-54,66-71, net/rp_net.py:50-69. */
+int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack,
+                           int ntaps, const int* tap_dy, const int* tap_dx, int cout, const float* ones, const float* zeros,
+                           void* z_f16, const int* group_start, int groups, float* sums, void* stream);
 
 /* stats[g][c] = {mean, rstd, a = rstd*gamma, b = beta - mean*a}; running_mean/var (momentum, unbiased var) updated once
  * per call group in order, num_batches_tracked += groups.  conv_bias: the bias the conv kernel dropped (it cancels in

@@ -34,6 +34,49 @@ import torch.nn.functional as F
 BN_EPS = 1e-5       # nn.BatchNorm2d default, net/modules.py:49
 BN_MOMENTUM = 0.1   # nn.BatchNorm2d default
 
+# ----------------------------------------------------------------------------
+# storage emulation (tests only)
+# ----------------------------------------------------------------------------
+# STORAGE = None      : the reference's arithmetic, fp32 everywhere (the oracle proper).
+# STORAGE = 'b200'    : same algorithm, but every tensor the B200 path keeps in HBM as fp16 (conv weights, the pre-BN conv
+#                       output z, the activation y, masked inputs, the correlation volume) is rounded to fp16 at that point
+#                       (straight-through gradient), and — with GRAD_STORAGE = 'bf16' — activation gradients are rounded to
+#                       bf16 where the backward kernels store them.  It separates "what fp16/bf16 storage does to this
+#                       network" (the fp32 reference itself moves by that much under a 5e-4 relative perturbation of its
+#                       activations) from kernel errors.  Parity against the fp32 oracle is always reported as well.
+STORAGE = None
+GRAD_STORAGE = None
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _q(x):
+    """fp16 storage point of the B200 path (identity for the oracle proper)."""
+    return _RoundFwd.apply(x) if STORAGE == 'b200' else x
+
+
+def _qg(x):
+    """bf16 storage point of an activation gradient in the B200 backward (identity for the oracle proper)."""
+    return _RoundGrad.apply(x) if (STORAGE == 'b200' and GRAD_STORAGE == 'bf16' and x.requires_grad) else x
+
 
 # ----------------------------------------------------------------------------
 # conv / norm building blocks
@@ -46,6 +89,20 @@ def conv_bn_relu(x, sd, conv, bn, training=False, padding=1, dilation=1, relu=Tr
     exactly like nn.BatchNorm2d does (momentum 0.1, unbiased running_var) and
     ``num_batches_tracked`` is incremented.
     """
+    if STORAGE == 'b200' and training and bn is not None:
+        # B200 train path: fp16 weights (fp32 for the Cin=1 first conv), bias dropped in front of batch-statistics BN (it
+        # re-enters the running mean), z and y stored as fp16 (the fp32 head output of cre.q is not rounded)
+        w = sd[conv + '.weight']
+        first = x.shape[1] < 64
+        z = F.conv2d(x if first else _qg(x), w if first else _q(w), None, padding=padding, dilation=dilation)
+        z = _qg(_q(z))
+        sd[bn + '.num_batches_tracked'] += 1
+        with torch.no_grad():       # (1-m) * (rm + m/(1-m) * bias) + m * mean(z) == (1-m) * rm + m * (mean(z) + bias)
+            sd[bn + '.running_mean'].data.add_(BN_MOMENTUM / (1 - BN_MOMENTUM) * sd[conv + '.bias'].data)
+        y = F.batch_norm(z, sd[bn + '.running_mean'], sd[bn + '.running_var'], sd[bn + '.weight'], sd[bn + '.bias'], True,
+                         BN_MOMENTUM, BN_EPS)
+        y = F.relu(y) if relu else y
+        return y if conv.endswith('cre.q.0') else _q(y)
     y = F.conv2d(x, sd[conv + '.weight'], sd[conv + '.bias'], padding=padding, dilation=dilation)
     if bn is not None:
         if training and (bn + '.num_batches_tracked') in sd:
@@ -150,9 +207,9 @@ def correlation_local(fmap1, fmap2, r=3):
 def cre(x_fg, x_bg, sd, radius, prefix='cre.', training=False, allpairs=False, want=None):
     """ContextCorrelationEncoder.forward, net/rp_net.py:77-84.  (w_context / out are
     never used by the reference forward: SURVEY D4.)"""
-    fm1 = conv_bn_relu(x_fg, sd, prefix + 'w_k.0', prefix + 'w_k.1', training)
-    fm2 = conv_bn_relu(x_bg, sd, prefix + 'w_q.0', prefix + 'w_q.1', training)
-    corr = (correlation_allpairs if allpairs else correlation_local)(fm1, fm2, r=radius)
+    fm1 = conv_bn_relu(_q(x_fg), sd, prefix + 'w_k.0', prefix + 'w_k.1', training)
+    fm2 = conv_bn_relu(_q(x_bg), sd, prefix + 'w_q.0', prefix + 'w_q.1', training)
+    corr = _q((correlation_allpairs if allpairs else correlation_local)(fm1, fm2, r=radius))
     out = conv_bn_relu(torch.cat([corr, fm1], dim=1), sd, prefix + 'q.0', prefix + 'q.1', training, padding=0)
     if want is not None:
         want.update(fm1=fm1, fm2=fm2, corr=corr, out=out)

@@ -27,6 +27,8 @@ constexpr int kBK = 64;           // fp16 channels per k-block = one 128-byte sw
 constexpr int kMaxTaps = 9;
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kMaxBnGroups = 64;
+constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] floats
 
 struct ConvParams {
   int N, H, W;                    // pixel grid of the conv (input == output grid, stride 1)
@@ -49,6 +51,11 @@ struct ConvParams {
   int pool_C;
   float* out_f32;                 // optional fp32 NHWC output (N, H, W, f32_C)
   int f32_C;
+  // optional fused train-mode BatchNorm statistics: bn_sums[g][cout][2] += {sum, sum of squares} of the fp32 accumulators
+  // over the valid pixels of call group g (images [bn_start[g], bn_start[g+1])); a tile never straddles two groups
+  float* bn_sums;
+  int bn_groups;
+  int bn_start[kMaxBnGroups + 1];
 };
 
 template <int BN>
@@ -58,7 +65,8 @@ struct ConvCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
+                                    kMaxBnCout * 2 * 4 /*fused BN statistics*/;
 };
 
 template <int BN>
@@ -77,6 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   uint64_t* tfull_bar = empty_bar + kStages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bn = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,6 +181,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     const int py = (row >> p.bw_log2) & (bh - 1);
     const int pn = row >> (p.bw_log2 + p.bh_log2);
     const int et = threadIdx.x - 64;                        // 0..127
+    const int cout_all = p.n_tiles_c * BN;
+    int cur_g = -1;                                         // BatchNorm call group of the statistics held in s_bn
+    if (p.bn_sums) {
+      for (int i = et; i < cout_all * 2; i += 128) s_bn[i] = 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -183,6 +198,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       const int tn = mt / p.tiles_y;
       const int x = tx * bw + px, y = ty * bh + py, n = tn * bn + pn;
       const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      if (p.bn_sums) {
+        int g = 0;
+        while (g + 1 < p.bn_groups && tn * bn >= p.bn_start[g + 1]) ++g;
+        if (g != cur_g) {                                   // tiles are ordered by image: at most bn_groups flushes per CTA
+          if (cur_g >= 0) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < cout_all * 2; i += 128) {
+              atomicAdd(p.bn_sums + (size_t)cur_g * cout_all * 2 + i, s_bn[i]);
+              s_bn[i] = 0.f;
+            }
+          }
+          cur_g = g;
+        }
+      }
       // stage this tile's per-channel scale/shift (buffer `as`: the other buffer may still be in use)
       float* sc = s_scale + as * BN;
       float* sh = s_shift + as * BN;
@@ -214,6 +243,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]);
           v[j] = p.relu ? fmaxf(t, 0.f) : t;
         }
+        if (p.bn_sums) {
+          // per-channel sums over the 32 pixels of this warp: butterfly transpose-reduce (31 shuffles per array); lane l
+          // ends up with the sum of column c0 + l
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = valid ? v[j] : 0.f;
+            s1[j] = t;
+            s2[j] = t * t;
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float k1 = up ? s1[j + off] : s1[j], g1 = up ? s1[j] : s1[j + off];
+              const float k2 = up ? s2[j + off] : s2[j], g2 = up ? s2[j] : s2[j + off];
+              s1[j] = k1 + __shfl_xor_sync(0xffffffffu, g1, off);
+              s2[j] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
+            }
+          }
+          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2], s1[0]);
+          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2 + 1], s2[0]);
+        }
         if (o32 && valid) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -240,6 +293,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if (p.bn_sums && cur_g >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < cout_all * 2; i += 128) atomicAdd(p.bn_sums + (size_t)cur_g * cout_all * 2 + i, s_bn[i]);
     }
   }
   tc_fence_before();
@@ -327,11 +384,15 @@ static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMa
 
 using namespace rpnet;
 
+extern "C" int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+                                  void* stream);
+
 static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
                            const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
                            const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
                            int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
-                           void* out_pool_f16, float* out_f32, void* stream_) {
+                           void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
+                           int bn_groups = 0, float* bn_sums = nullptr, int* bn_fused = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -362,6 +423,21 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   p.oy_mul = oy_mul; p.oy_off = oy_off; p.ox_mul = ox_mul; p.ox_off = ox_off;
   p.out_pool = static_cast<__half*>(out_pool_f16); p.pool_C = cout;
   p.out_f32 = out_f32; p.f32_C = cout;
+  p.bn_sums = nullptr; p.bn_groups = 0;
+  if (bn_fused) *bn_fused = 0;
+  if (bn_sums) {
+    // fuse the statistics when no pixel tile straddles two call groups and the per-CTA accumulators fit
+    RPNET_REQUIRE(bn_groups >= 1 && bn_groups <= kMaxBnGroups && bn_group_start, "conv_igemm: bn groups %d out of range [1, %d]", bn_groups, kMaxBnGroups);
+    RPNET_REQUIRE(bn_group_start[0] == 0 && bn_group_start[bn_groups] == n, "conv_igemm: bn group_start must span [0, %d]", n);
+    bool ok = cout <= kMaxBnCout;
+    for (int g = 1; g < bn_groups; ++g) ok = ok && (bn_group_start[g] % bn == 0);
+    if (ok) {
+      p.bn_sums = bn_sums; p.bn_groups = bn_groups;
+      for (int g = 0; g <= bn_groups; ++g) p.bn_start[g] = bn_group_start[g];
+      RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(float), stream));
+      if (bn_fused) *bn_fused = 1;
+    }
+  }
   if (out_f16) {
     RPNET_REQUIRE(out_c % 8 == 0 && out_coff % 8 == 0 && out_coff + cout <= out_c, "conv_igemm: bad output channel window (%d + %d in %d)", out_coff, cout, out_c);
     RPNET_REQUIRE((h - 1) * oy_mul + oy_off < out_h && (w - 1) * ox_mul + ox_off < out_w && oy_off >= 0 && ox_off >= 0,
@@ -416,4 +492,18 @@ RPNET_API int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, 
                                      void* out_pool_bf16, float* out_f32, void* stream_) {
   return conv_igemm_impl(true, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_bf16,
                          out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off, out_pool_bf16, out_f32, stream_);
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack,
+                                      int ntaps, const int* tap_dy, const int* tap_dx, int cout, const float* ones,
+                                      const float* zeros, void* z_f16, const int* group_start, int groups, float* sums,
+                                      void* stream_) {
+  RPNET_REQUIRE(z_f16 && sums && group_start, "conv_bnstats: null pointer argument");
+  int fused = 0;
+  int rc = conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, ones, zeros, 0, z_f16, h, w, cout,
+                           0, 1, 0, 1, 0, nullptr, nullptr, stream_, group_start, groups, sums, &fused);
+  if (rc) return rc;
+  if (!fused) return rpnet_bn_stats_f16(z_f16, n, h, w, cout, group_start, groups, sums, stream_);   // tiny maps: separate pass
+  return 0;
 }

@@ -99,6 +99,63 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
   }
 }
 
+// Cin == 1 specialisation (encoder.Conv1.conv.0, net/unet.py:405): the 8 output channels a thread owns never change
+// (grid stride is a multiple of 8), so its 72 weights (scale folded in) live in registers; each thread produces two
+// horizontally adjacent pixels from a 3 x 4 image patch: 12 loads, 144 FMAs, two 16-byte stores.
+__global__ void __launch_bounds__(256)
+conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][1][3][3]*/,
+                        const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
+                        int N, int H, int W) {
+  const int cg = threadIdx.x & 7;
+  float wr[9][8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float sc = __ldg(scale + cg * 8 + j);
+    sh[j] = __ldg(shift + cg * 8 + j);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][j] = __ldg(wgt + (cg * 8 + j) * 9 + t) * sc;
+  }
+  const int Wp = (W + 1) >> 1;                                   // pixel pairs per row
+  const long long total = (long long)N * H * Wp * 8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
+    const long long pp = gid >> 3;
+    const int x = (int)(pp % Wp) * 2;
+    const int y = (int)((pp / Wp) % H);
+    const long long n = pp / ((long long)Wp * H);
+    const float* plane = img + n * H * W;
+    float v[3][4];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      const bool yok = yy >= 0 && yy < H;
+#pragma unroll
+      for (int kx = 0; kx < 4; ++kx) {
+        const int xx = x + kx - 1;
+        v[ky][kx] = (yok && xx >= 0 && xx < W) ? __ldg(plane + (long long)yy * W + xx) : 0.f;
+      }
+    }
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = sh[j]; a1[j] = sh[j]; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] = fmaf(v[ky][kx], wr[ky * 3 + kx][j], a0[j]);
+          a1[j] = fmaf(v[ky][kx + 1], wr[ky * 3 + kx][j], a1[j]);
+        }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a0[j] = fmaxf(a0[j], 0.f); a1[j] = fmaxf(a1[j], 0.f); }
+    }
+    const long long pix = (n * H + y) * W + x;
+    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = pack8(a0);
+    if (x + 1 < W) *reinterpret_cast<uint4*>(out + (pix + 1) * 64 + cg * 8) = pack8(a1);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // F.avg_pool2d(mask[:, None], s)  (net/rp_net.py:270,272).  fp32 [N,H,W] -> fp32 [N,H/s,W/s].
 // ---------------------------------------------------------------------------------------------------
@@ -478,7 +535,7 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 2; }
+RPNET_API int rpnet_abi_version(void) { return 3; }
 
 RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                        const float* shift, int relu, void* out_f16, void* stream_) {
@@ -489,7 +546,8 @@ RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, i
   const long long total = (long long)n * h * w * 8;
   const int grid = grid_for(total, 256);
   if (cin == 1)
-    conv3x3_first_kernel<1><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
+    conv3x3_first_c1_kernel<<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
+        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
   else
     conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");

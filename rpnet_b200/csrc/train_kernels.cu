@@ -113,28 +113,40 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Gr
   const int C = c8 * 8;
   const int Hs = POOL ? H / 2 : H, Ws = POOL ? W / 2 : W;
   const long long total = (long long)N * Hs * Ws * c8;
+  // 256 % c8 == 0 (host-checked), so the 8-channel vector a thread owns never changes: keep its (a, b) in registers and
+  // reload only when the image moves to another BatchNorm call group.
+  const int v = (int)(threadIdx.x % c8);
+  int cur_g = -1;
+  float a[8], b[8];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % c8);
     long long t = i / c8;
     const int xs = (int)(t % Ws);  t /= Ws;
     const int ys = (int)(t % Hs);
     const int n = (int)(t / Hs);
     const int g = group_of(gr, n);
-    float a[8], b[8];
+    if (g != cur_g) {
+      cur_g = g;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
-      a[j] = st.z; b[j] = st.w;
+      for (int j = 0; j < 8; ++j) {
+        const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+        a[j] = st.z; b[j] = st.w;
+      }
     }
     float best[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    uint4 zin[POOL ? 4 : 1];
+#pragma unroll
+    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
+      const int y = POOL ? ys * 2 + (q >> 1) : ys, x = POOL ? xs * 2 + (q & 1) : xs;
+      zin[q] = __ldg(z + (((long long)n * H + y) * W + x) * c8 + v);
+    }
 #pragma unroll
     for (int q = 0; q < (POOL ? 4 : 1); ++q) {
       const int y = POOL ? ys * 2 + (q >> 1) : ys, x = POOL ? xs * 2 + (q & 1) : xs;
       const long long pix = ((long long)n * H + y) * W + x;
       float f[8];
-      unpack8_f16(__ldg(z + pix * c8 + v), f);
+      unpack8_f16(zin[q], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float r = fmaf(f[j], a[j], b[j]);
@@ -192,86 +204,97 @@ __device__ __forceinline__ void load_grad8(const GradSrc& s, int n, int y, int x
   }
 }
 
-// Work unit: one 2x2 pixel window (WIN) or one pixel (!WIN) x 8 channels.  MODE 0: reduce (sum dy_hat, sum dy_hat*x_hat
-// per group/channel); MODE 1: apply (write dz).
+// Work unit: one 2x2 pixel window (WIN) or one pixel (!WIN) x 8 channels.
+// MODE 0 (reduce): per (group, channel) S1 = sum dy_hat, S2 = sum dy_hat * (z - mean)   [x_hat = (z - mean) * rstd]
+// MODE 1 (apply):  dz = a * (dy_hat - m1 - x_hat * m2) = a * dy_hat + k1 * z + k0 with per-channel constants
+//                  k1 = -a * m2 * rstd, k0 = -a * m1 - k1 * mean   (m1 = S1 / cnt, m2 = rstd * S2 / cnt)
+// where dy_hat = relu'(a*z+b) * (sum of the incoming gradients).  The 8-channel vector of a thread is fixed, so the
+// per-channel constants live in registers and are reloaded only when the image moves to another call group.
 template <bool WIN, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WIN ? 2 : 3)
 bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N, int H,
               int W, int c8, int relu, GradSrc src, float* __restrict__ sums, uint4* __restrict__ dz) {
   __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
   const int C = c8 * 8;
   const int Hs = WIN ? H / 2 : H, Ws = WIN ? W / 2 : W;
-  // MODE 0: grid = (blocks, G): a block stays inside one call group so that its partial sums are per group
   const int lanes = 256 / c8;
   const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
   int n_begin = 0, n_end = N;
-  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
+  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }   // a block stays inside one group
   const long long units = (long long)(n_end - n_begin) * Hs * Ws;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  int cur_g = -1;
+  float a[8], b[8], c1[8], c0[8];          // MODE 0: c1 = mean (c0 unused); MODE 1: c1 = k1, c0 = k0
   for (long long u = (long long)blockIdx.x * lanes + pl; u < units; u += (long long)gridDim.x * lanes) {
     long long t = u;
     const int xs = (int)(t % Ws);  t /= Ws;
     const int ys = (int)(t % Hs);
     const int n = n_begin + (int)(t / Hs);
     const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, n);
-    float mean[8], rstd[8], a[8], b[8], m1[8], m2[8];
+    if (g != cur_g) {
+      cur_g = g;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
-      mean[j] = st.x; rstd[j] = st.y; a[j] = st.z; b[j] = st.w;
-      if (MODE == 1) {
-        const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);
-        m1[j] = cf.x; m2[j] = cf.y;
-      }
-    }
-    float zf[WIN ? 4 : 1][8];
-    int win_arg[8];
-    float pg[8];
-    if (WIN) {
-      float best[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; win_arg[j] = 0; }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const long long pix = ((long long)n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1);
-        unpack8_f16(__ldg(z + pix * c8 + v), zf[q]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float r = fmaf(zf[q][j], a[j], b[j]);
-          r = relu ? fmaxf(r, 0.f) : r;
-          if (r > best[j]) { best[j] = r; win_arg[j] = q; }
+      for (int j = 0; j < 8; ++j) {
+        const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+        a[j] = st.z; b[j] = st.w;
+        if (MODE == 0) {
+          c1[j] = st.x; c0[j] = 0.f;
+        } else {
+          const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);   // (m1, m2)
+          c1[j] = -st.z * cf.y * st.y;
+          c0[j] = -st.z * cf.x - c1[j] * st.x;
         }
       }
+    }
+    uint4 zin[WIN ? 4 : 1];
+    uint32_t win_arg = 0;                  // 2 bits per channel: which pixel of the 2x2 window holds the (first) maximum
+    float pg[8];
+    if (WIN) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        zin[q] = __ldg(z + (((long long)n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1)) * c8 + v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) pg[j] = 0.f;
       if (src.pooled) {
         const long long pp = ((long long)n * Hs + ys) * Ws + xs;
         unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(src.pooled + pp * src.p_ld + src.p_off + v * 8)), pg);
       }
+      float best[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+        unpack8_f16(zin[q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float r = fmaf(f[j], a[j], b[j]);
+          r = relu ? fmaxf(r, 0.f) : r;
+          if (r > best[j]) { best[j] = r; win_arg = (win_arg & ~(3u << (2 * j))) | ((uint32_t)q << (2 * j)); }
+        }
+      }
     } else {
-      const long long pix = ((long long)n * H + ys) * W + xs;
-      unpack8_f16(__ldg(z + pix * c8 + v), zf[0]);
+      zin[0] = __ldg(z + (((long long)n * H + ys) * W + xs) * c8 + v);
     }
 #pragma unroll
     for (int q = 0; q < (WIN ? 4 : 1); ++q) {
       const int y = WIN ? ys * 2 + (q >> 1) : ys, x = WIN ? xs * 2 + (q & 1) : xs;
-      float gy[8];
+      float gy[8], f[8];
       load_grad8(src, n, y, x, H, W, v * 8, gy);
+      unpack8_f16(zin[q], f);
       float out[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float d = gy[j];
-        if (WIN && win_arg[j] == q) d += pg[j];
-        const float r = fmaf(zf[q][j], a[j], b[j]);
-        if (relu && !(r > 0.f)) d = 0.f;
-        const float xh = (zf[q][j] - mean[j]) * rstd[j];
+        if (WIN && ((win_arg >> (2 * j)) & 3u) == (uint32_t)q) d += pg[j];
+        if (relu && !(fmaf(f[j], a[j], b[j]) > 0.f)) d = 0.f;
         if (MODE == 0) {
           s1[j] += d;
-          s2[j] = fmaf(d, xh, s2[j]);
+          s2[j] = fmaf(d, f[j] - c1[j], s2[j]);
         } else {
-          out[j] = a[j] * (d - m1[j] - xh * m2[j]);
+          out[j] = fmaf(a[j], d, fmaf(c1[j], f[j], c0[j]));
         }
       }
       if (MODE == 1) dz[(((long long)n * H + y) * W + x) * c8 + v] = pack8_bf16(out);
@@ -299,15 +322,208 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
   }
 }
 
-// coef[g][c] = (mean of dy_hat, mean of dy_hat * x_hat);  dgamma[c] += sum_g S2, dbeta[c] += sum_g S1
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, Groups gr, int C, int HW, float* dgamma, float* dbeta,
-                                       float* __restrict__ coef) {
+// Direct-only specialisation (the gradient arrives as one bf16 NHWC tensor / channel slice: every conv that feeds another
+// conv): two pixels per thread and iteration with all four 16-byte loads issued before the math (memory-level parallelism).
+template <int MODE>
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N,
+                     int HW, int c8, int relu, const __nv_bfloat16* __restrict__ gdir, int d_ld, int d_off,
+                     float* __restrict__ sums, uint4* __restrict__ dz) {
+  __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
+  const int C = c8 * 8;
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  int n_begin = 0, n_end = N;
+  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
+  const long long p_begin = (long long)n_begin * HW, p_end = (long long)n_end * HW;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  int cur_g = -1;
+  float a[8], b[8], c1[8], c0[8];
+  const long long stride = (long long)gridDim.x * lanes;
+  for (long long p = p_begin + (long long)blockIdx.x * lanes + pl; p < p_end; p += 2 * stride) {
+    const long long pq[2] = {p, p + stride};
+    const bool ok1 = pq[1] < p_end;
+    uint4 zr[2], gr_[2];
+    zr[0] = __ldg(z + pq[0] * c8 + v);
+    gr_[0] = __ldg(reinterpret_cast<const uint4*>(gdir + pq[0] * d_ld + d_off + v * 8));
+    if (ok1) {
+      zr[1] = __ldg(z + pq[1] * c8 + v);
+      gr_[1] = __ldg(reinterpret_cast<const uint4*>(gdir + pq[1] * d_ld + d_off + v * 8));
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 1 && !ok1) break;
+      const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, (int)(pq[k] / HW));
+      if (g != cur_g) {
+        cur_g = g;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+          a[j] = st.z; b[j] = st.w;
+          if (MODE == 0) {
+            c1[j] = st.x; c0[j] = 0.f;
+          } else {
+            const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);
+            c1[j] = -st.z * cf.y * st.y;
+            c0[j] = -st.z * cf.x - c1[j] * st.x;
+          }
+        }
+      }
+      float f[8], d[8], out[8];
+      unpack8_f16(zr[k], f);
+      unpack8_bf16(gr_[k], d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dd = (relu && !(fmaf(f[j], a[j], b[j]) > 0.f)) ? 0.f : d[j];
+        if (MODE == 0) {
+          s1[j] += dd;
+          s2[j] = fmaf(dd, f[j] - c1[j], s2[j]);
+        } else {
+          out[j] = fmaf(a[j], dd, fmaf(c1[j], f[j], c0[j]));
+        }
+      }
+      if (MODE == 1) dz[pq[k] * c8 + v] = pack8_bf16(out);
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    __syncthreads();
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+      if (pl < s) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_red[threadIdx.x * 16 + j] += s_red[(threadIdx.x + s * c8) * 16 + j];
+      }
+      __syncthreads();
+    }
+    if (pl == 0) {
+      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+      }
+    }
+  }
+}
+
+// Pool-only specialisation (encoder.Conv1/Conv2 second convs: the activation feeds nothing but the 2x2 max-pool): the
+// incoming gradient is non-zero only at the window's (first) maximum, so the reduce pass touches one value per window and
+// the apply pass is one FMA per element plus the routed term.  Same MODE semantics as bn_bwd_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 0 ? 3 : 2)
+bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N,
+                   int H, int W, int c8, int relu, const __nv_bfloat16* __restrict__ pooled, int p_ld, int p_off,
+                   float* __restrict__ sums, uint4* __restrict__ dz) {
+  __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
+  const int C = c8 * 8;
+  const int Hs = H / 2, Ws = W / 2;
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  int n_begin = 0, n_end = N;
+  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
+  const long long units = (long long)(n_end - n_begin) * Hs * Ws;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  int cur_g = -1;
+  float a[8], b[8], c1[8], c0[8];
+  for (long long u = (long long)blockIdx.x * lanes + pl; u < units; u += (long long)gridDim.x * lanes) {
+    long long t = u;
+    const int xs = (int)(t % Ws);  t /= Ws;
+    const int ys = (int)(t % Hs);
+    const int n = n_begin + (int)(t / Hs);
+    const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, n);
+    if (g != cur_g) {
+      cur_g = g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+        a[j] = st.z; b[j] = st.w;
+        if (MODE == 0) {
+          c1[j] = st.x; c0[j] = 0.f;
+        } else {
+          const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);
+          c1[j] = -st.z * cf.y * st.y;
+          c0[j] = -st.z * cf.x - c1[j] * st.x;
+        }
+      }
+    }
+    uint4 zin[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      zin[q] = __ldg(z + (((long long)n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1)) * c8 + v);
+    float pg[8];
+    unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(pooled + (((long long)n * Hs + ys) * Ws + xs) * p_ld + p_off + v * 8)), pg);
+    float best[8], zbest[8];
+    int win[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; zbest[j] = 0.f; win[j] = 0; }
+    float f[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      unpack8_f16(zin[q], f[q]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float r = fmaf(f[q][j], a[j], b[j]);
+        r = relu ? fmaxf(r, 0.f) : r;
+        if (r > best[j]) { best[j] = r; zbest[j] = f[q][j]; win[j] = q; }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = (relu && !(best[j] > 0.f)) ? 0.f : pg[j];       // relu'(winner) * routed gradient
+      if (MODE == 0) {
+        s1[j] += d;
+        s2[j] = fmaf(d, zbest[j] - c1[j], s2[j]);
+      } else {
+        pg[j] = a[j] * d;
+      }
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = fmaf(c1[j], f[q][j], c0[j]) + (win[j] == q ? pg[j] : 0.f);
+        dz[(((long long)n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1)) * c8 + v] = pack8_bf16(out);
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+    __syncthreads();
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+      if (pl < s) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s_red[threadIdx.x * 16 + j] += s_red[(threadIdx.x + s * c8) * 16 + j];
+      }
+      __syncthreads();
+    }
+    if (pl == 0) {
+      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+      }
+    }
+  }
+}
+
+// coef[g][c] = (m1, m2) = (S1 / cnt, rstd * S2 / cnt);  dgamma[c] += sum_g rstd * S2, dbeta[c] += sum_g S1
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats, Groups gr, int C, int HW,
+                                       float* dgamma, float* dbeta, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float dg = 0.f, db = 0.f;
   for (int g = 0; g < gr.G; ++g) {
     const float cnt = (float)(gr.start[g + 1] - gr.start[g]) * (float)HW;
-    const float S1 = sums[((size_t)g * C + c) * 2], S2 = sums[((size_t)g * C + c) * 2 + 1];
+    const float rstd = stats[((size_t)g * C + c) * 4 + 1];
+    const float S1 = sums[((size_t)g * C + c) * 2], S2 = rstd * sums[((size_t)g * C + c) * 2 + 1];
     coef[((size_t)g * C + c) * 2] = S1 / cnt;
     coef[((size_t)g * C + c) * 2 + 1] = S2 / cnt;
     db += S1;
@@ -391,46 +607,52 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
 
 // ---------------------------------------------------------------------------------------------------
 // Weight gradient of the Cin = 1 first conv (encoder.Conv1.conv.0): grad[co][ky][kx] += sum_p dz[p][co] * img[p + tap].
-// One warp per run of pixels; lane = 2 output channels; 9 broadcast image loads + one coalesced 128 B dz row per pixel.
+// 8 threads per pixel, 8 output channels each (one 16-byte dz load), 72 register accumulators per thread; the four
+// pixel lanes of a warp are folded with shuffles, warps through shared-memory atomics, blocks through global atomics.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv3x3_first_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat162* __restrict__ dz, int N, int H, int W,
+conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restrict__ dz, int N, int H, int W,
                            float* __restrict__ grad /*[64][9]*/) {
-  __shared__ float s_acc[8][64 * 9];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc0[9], acc1[9];
+  __shared__ float s_acc[64 * 9];
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float acc[9][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
-  const long long total = (long long)N * H * W;
-  const long long wid = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
-  for (long long p = wid; p < total; p += nw) {
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long total = (long long)N * H * W * 8;
+  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
+    const long long p = gid >> 3;
     const int x = (int)(p % W), y = (int)((p / W) % H);
     const long long base = p - (long long)y * W - x;            // n * H * W
-    const float2 d = __bfloat1622float2(dz[p * 32 + lane]);
+    float d[8];
+    unpack8_bf16(__ldg(dz + gid), d);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int yy = y + ky - 1;
+      const bool yok = yy >= 0 && yy < H;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = x + kx - 1;
-        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + base + (long long)yy * W + xx) : 0.f;
-        acc0[ky * 3 + kx] = fmaf(d.x, v, acc0[ky * 3 + kx]);
-        acc1[ky * 3 + kx] = fmaf(d.y, v, acc1[ky * 3 + kx]);
+        const float v = (yok && xx >= 0 && xx < W) ? __ldg(img + base + (long long)yy * W + xx) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], v, acc[ky * 3 + kx][j]);
       }
     }
   }
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    s_acc[warp][(2 * lane) * 9 + t] = acc0[t];
-    s_acc[warp][(2 * lane + 1) * 9 + t] = acc1[t];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 9; i += 256) {
-    float s = 0.f;
+  for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += s_acc[k][i];
-    atomicAdd(grad + i, s);
-  }
+    for (int j = 0; j < 8; ++j) {
+      float a = acc[t][j];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(cg * 8 + j) * 9 + t], a);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) atomicAdd(grad + i, s_acc[i]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -543,10 +765,39 @@ RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const uint4* zz = static_cast<const uint4*>(z);
+  if (!win && g_direct && !d_is_f32 && !g_up_bf16) {       // direct-only bf16 gradient: specialised kernels
+    const __nv_bfloat16* gd = static_cast<const __nv_bfloat16*>(g_direct);
+    long long nb0 = ((long long)max_imgs * h * w + lanes * 8 - 1) / (lanes * 8);
+    if (nb0 > cap) nb0 = cap;
+    if (nb0 < 1) nb0 = 1;
+    bn_bwd_direct_kernel<0><<<dim3((unsigned)nb0, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h * w, c8, relu, gd, d_ld, d_off,
+                                                                            sums, nullptr);
+    RPNET_CUDA_OK(cudaGetLastError());
+    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
+    RPNET_CUDA_OK(cudaGetLastError());
+    long long nb1 = ((long long)n * h * w + lanes * 2 - 1) / (lanes * 2);
+    if (nb1 > 148LL * 12) nb1 = 148LL * 12;
+    bn_bwd_direct_kernel<1><<<(unsigned)nb1, 256, 0, stream>>>(zz, stats, coef, gr, n, h * w, c8, relu, gd, d_ld, d_off, nullptr,
+                                                              static_cast<uint4*>(dz_bf16));
+    return check_cuda(cudaGetLastError(), "bn_bwd(direct) launch");
+  }
+  if (win && !g_direct && !g_up_bf16) {       // pool-only consumers: specialised kernels
+    bn_bwd_pool_kernel<0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src.pooled,
+                                                                             p_ld, p_off, sums, nullptr);
+    RPNET_CUDA_OK(cudaGetLastError());
+    bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
+    RPNET_CUDA_OK(cudaGetLastError());
+    const long long units_all = (long long)n * (h / 2) * (w / 2);
+    long long nb = (units_all + lanes - 1) / lanes;
+    if (nb > 148LL * 12) nb = 148LL * 12;
+    bn_bwd_pool_kernel<1><<<(unsigned)nb, 256, 0, stream>>>(zz, stats, coef, gr, n, h, w, c8, relu, src.pooled, p_ld, p_off, nullptr,
+                                                           static_cast<uint4*>(dz_bf16));
+    return check_cuda(cudaGetLastError(), "bn_bwd(pool) launch");
+  }
   if (win) bn_bwd_kernel<true, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
   else     bn_bwd_kernel<false, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
   RPNET_CUDA_OK(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, gr, c, h * w, dgamma, dbeta, coef);
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
   RPNET_CUDA_OK(cudaGetLastError());
   const long long units = (long long)n * (win ? (h / 2) * (w / 2) : h * w);
   long long blocks2 = (units + lanes - 1) / lanes;
@@ -599,10 +850,11 @@ RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, i
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && dz_bf16 && grad, "conv3x3_first_wgrad: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first_wgrad: bad shape");
-  const long long total = (long long)n * h * w;
-  long long blocks = (total + 8 * 64 - 1) / (8 * 64);
-  if (blocks > 148LL * 8) blocks = 148LL * 8;
-  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const __nv_bfloat162*>(dz_bf16), n, h, w, grad);
+  const long long total = (long long)n * h * w * 8;
+  long long blocks = (total + 256 * 16 - 1) / (256 * 16);
+  if (blocks > 148LL * 4) blocks = 148LL * 4;
+  if (blocks < 1) blocks = 1;
+  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const uint4*>(dz_bf16), n, h, w, grad);
   return check_cuda(cudaGetLastError(), "conv3x3_first_wgrad launch");
 }
 

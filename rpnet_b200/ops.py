@@ -298,6 +298,29 @@ def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0)):
                    'rpnet_pack_conv_weight')
 
 
+def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None):
+    """Train-mode conv (no bias) -> z fp16 NHWC + BatchNorm statistics sums[g][cout][2] in the same launch."""
+    lib = _lib.load()
+    _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack'); _req(z, torch.float16, 'z'); _req(sums, torch.float32, 'sums')
+    n, h, w, c0 = src0.shape
+    c1 = 0
+    if src1 is not None:
+        _req(src1, torch.float16, 'src1')
+        assert src1.shape[:3] == src0.shape[:3]
+        c1 = src1.shape[3]
+    ntaps, cout, cin = wpack.shape
+    if cin != c0 + c1 or ntaps != len(taps) or tuple(z.shape) != (n, h, w, cout):
+        raise _lib.RpnetError('conv_bnstats: weight pack %s / output %s do not match the sources (%d + %d channels, %d taps)'
+                              % (tuple(wpack.shape), tuple(z.shape), c0, c1, len(taps)))
+    dy, dx = _taps(taps)
+    gs, g = _groups(group_start)
+    assert sums.numel() >= g * cout * 2
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_bnstats_f16(_ptr(src0), c0, _ptr(src1), c1, n, h, w, _ptr(wpack), ntaps, dy, dx, cout, _ptr(ones), _ptr(zeros),
+                                        _ptr(z), gs, g, _ptr(sums), _stream())
+    _lib.check(rc, 'rpnet_conv_bnstats_f16')
+
+
 def bn_stats(z, group_start, sums):
     lib = _lib.load()
     _req(z, torch.float16, 'z'); _req(sums, torch.float32, 'sums')

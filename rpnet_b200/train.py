@@ -158,16 +158,15 @@ class _ConvBN:
         if not self.first:
             ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole)
 
-    def conv_fwd(self, x0, x1, z):
-        if self.first:
-            ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z)
-        else:
-            ops.conv_igemm(x0, self.wf, self.taps, self.ones, self.zeros, False, src1=x1, out=z)
-
-    def bn_fwd(self, z, gs, sums, stats, y=None, pool=None, y32=None):
+    def fwd(self, x0, x1, z, gs, sums, stats, y=None, pool=None, y32=None):
+        """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) + ReLU."""
         n, h, w, c = z.shape
         bn = self.bn
-        ops.bn_stats(z, gs, sums)
+        if self.first:
+            ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z)
+            ops.bn_stats(z, gs, sums)
+        else:
+            ops.conv_bnstats(x0, self.wf, self.taps, self.ones, self.zeros, z, gs, sums, src1=x1)
         ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
         ops.bn_apply(z, stats, gs, True, y=y, y_pool=pool, y_f32=y32)
@@ -257,8 +256,7 @@ class TrainEngine:
         stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
         y = self.buf(key + '.y', (n, h, w, c), f16) if want_y else None
         pool = self.buf(key + '.pool', (n, h // 2, w // 2, c), f16) if want_pool else None
-        l.conv_fwd(x0, x1, z)
-        l.bn_fwd(z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, f32), stats, y=y, pool=pool)
+        l.fwd(x0, x1, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, f32), stats, y=y, pool=pool)
         self.act[key] = dict(x0=x0, x1=x1, z=z, stats=stats, gs=gs)
         return y, pool
 
@@ -337,13 +335,10 @@ class TrainEngine:
         ops.premask(d4, mask, xfg, xbg)
         G = len(gs) - 1
         sums = self.scratch('bn_sums', G * 256 * 2, f32)
-        L['wk'].conv_fwd(xfg, None, S['z1'][lo:hi])
-        L['wk'].bn_fwd(S['z1'][lo:hi], gs, sums, S['st1'][g0:g0 + G], y=S['fm1'][lo:hi])
-        L['wq'].conv_fwd(xbg, None, S['z2'][lo:hi])
-        L['wq'].bn_fwd(S['z2'][lo:hi], gs, sums, S['st2'][g0:g0 + G], y=S['fm2'][lo:hi])
+        L['wk'].fwd(xfg, None, S['z1'][lo:hi], gs, sums, S['st1'][g0:g0 + G], y=S['fm1'][lo:hi])
+        L['wq'].fwd(xbg, None, S['z2'][lo:hi], gs, sums, S['st2'][g0:g0 + G], y=S['fm2'][lo:hi])
         ops.local_corr(S['fm1'][lo:hi], S['fm2'][lo:hi], self.net.cre.radius, S['corr'][lo:hi])
-        L['q'].conv_fwd(S['corr'][lo:hi], S['fm1'][lo:hi], S['z3'][lo:hi])
-        L['q'].bn_fwd(S['z3'][lo:hi], gs, sums, S['st3'][g0:g0 + G], y32=S['feat'][lo:hi])
+        L['q'].fwd(S['corr'][lo:hi], S['fm1'][lo:hi], S['z3'][lo:hi], gs, sums, S['st3'][g0:g0 + G], y32=S['feat'][lo:hi])
         return S['feat'][lo:hi]
 
     # ------------------------------------------------------------------ forward

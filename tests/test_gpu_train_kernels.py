@@ -425,3 +425,36 @@ def test_adam_matches_torch(dev):
         ops.adam(pd, gr.to(dev), m, v, step, 1e-3, weight_decay=1e-4, grad_scale=0.5)
     torch.cuda.synchronize()
     torch.testing.assert_close(pd.cpu(), ref.detach(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize('case', [
+    # n, c0, c1, cout, h, w, k, group_start
+    (4, 64, 0, 64, 16, 32, 3, [0, 3, 4]),          # one image per tile: statistics fused into the conv epilogue
+    (3, 128, 64, 256, 24, 40, 3, [0, 1, 3]),       # ragged tiles (out-of-range pixels must not enter the statistics), BN=256
+    (6, 64, 0, 128, 8, 8, 1, [0, 2, 6]),           # two images per tile, boundaries aligned: still fused
+    (6, 64, 0, 64, 4, 4, 3, [0, 3, 6]),            # eight images per tile, boundary inside a tile: separate statistics pass
+    (2, 512, 0, 1024, 16, 16, 3, [0, 1, 2]),       # cout = 1024 (largest per-CTA accumulator)
+])
+def test_conv_bnstats(dev, case):
+    """rpnet_conv_bnstats_f16: z == conv (fp16-rounded) and sums == per-call-group {sum z, sum z^2} of the fp32 conv output."""
+    from rpnet_b200 import ops
+    n, c0, c1, cout, h, w, k, gs = case
+    g = _gen(sum(case[:7]))
+    cin = c0 + c1
+    x = torch.randn(n, cin, h, w, generator=g).half().float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).half().float()
+    want = F.conv2d(x, wt, None, padding=k // 2)
+    taps = [(ky - k // 2, kx - k // 2) for ky in range(k) for kx in range(k)]
+    wp = wt.permute(2, 3, 0, 1).reshape(k * k, cout, cin).half().contiguous().to(dev)
+    z = torch.empty(n, h, w, cout, dtype=torch.float16, device=dev)
+    G = len(gs) - 1
+    sums = torch.full((G, cout, 2), 7.0, device=dev)
+    ops.conv_bnstats(_nhwc(x[:, :c0], torch.float16, dev), wp, taps, torch.ones(cout, device=dev), torch.zeros(cout, device=dev), z, gs, sums,
+                     src1=_nhwc(x[:, c0:], torch.float16, dev) if c1 else None)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(_nchw(z), want, rtol=2e-3, atol=2e-3)
+    for i in range(G):
+        blk = want[gs[i]:gs[i + 1]]
+        s1, s2 = blk.sum((0, 2, 3)), (blk * blk).sum((0, 2, 3))
+        torch.testing.assert_close(sums[i, :, 0].cpu(), s1, rtol=2e-3, atol=2e-3 * blk[0, 0].numel() ** 0.5)
+        torch.testing.assert_close(sums[i, :, 1].cpu(), s2, rtol=2e-3, atol=1e-3)
