@@ -43,13 +43,16 @@ struct WgradParams {
   float* partial;                                  // [splits][rows][cout]
 };
 
+constexpr int kWgAcc = 2;                          // 128-row accumulators per work item (they share every dZ stage)
+constexpr int kWgBoxesPerItem = 2 * kWgAcc;        // M tile = 256 rows = 4 (tap, 64-channel chunk) boxes
+
 template <int BN>
 struct WgradCfg {
-  static constexpr int kABytes = 2 * kWgBoxBytes;
+  static constexpr int kABytes = kWgBoxesPerItem * kWgBoxBytes;
   static constexpr int kBBytes = (BN / 64) * kWgBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kWgSmemBudget / kStageBytes) > 8 ? 8 : (kWgSmemBudget / kStageBytes);
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = kWgAcc * BN;     // single-buffered: the K loop of an item is long, its epilogue short
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -106,9 +109,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
         const int k0 = (int)((long long)split * p.ptiles / p.splits);
         const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
-        int bx[2];
-        bx[0] = 2 * mt;
-        bx[1] = (2 * mt + 1 < p.n_boxes) ? 2 * mt + 1 : 2 * mt;      // odd box count: duplicate (rows discarded)
+        int bx[kWgBoxesPerItem];
+#pragma unroll
+        for (int j = 0; j < kWgBoxesPerItem; ++j)                   // ragged box count: duplicate the first box (rows discarded)
+          bx[j] = (kWgBoxesPerItem * mt + j < p.n_boxes) ? kWgBoxesPerItem * mt + j : kWgBoxesPerItem * mt;
         for (int pt = k0; pt < k1; ++pt) {
           int t = pt;
           const int tx = t % p.tiles_x;  t /= p.tiles_x;
@@ -120,7 +124,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
           uint8_t* b_dst = a_dst + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < kWgBoxesPerItem; ++j) {
             const int tap = bx[j] / nch, c = bx[j] % nch;
             const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
             if (c < p.chunks0) tma_load_4d(&tm_x0, &full_bar[stage], a_dst + j * kWgBoxBytes, c * 64, xs, ys, n0);
@@ -145,11 +149,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const int split = item / tiles_mn;
         const int k0 = (int)((long long)split * p.ptiles / p.splits);
         const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        const uint32_t aphase = it & 1;
+        mbar_wait(&tempty_bar[0], aphase ^ 1);            // the epilogue has drained the accumulators of the previous item
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
         for (int pt = k0; pt < k1; ++pt) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -158,14 +160,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kWgPix / 16; ++k) {
             // 16 pixels (K) = 16 swizzle rows = 2048 B further into every box
-            const uint64_t a_desc = umma_desc_sw128_mn(a_addr + k * 2048, kWgBoxBytes, 1024);
             const uint64_t b_desc = umma_desc_sw128_mn(b_addr + k * 2048, kWgBoxBytes, 1024);
-            umma_f16(d_tmem, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < kWgAcc; ++h) {
+              const uint64_t a_desc = umma_desc_sw128_mn(a_addr + h * 2 * kWgBoxBytes + k * 2048, kWgBoxBytes, 1024);
+              umma_f16(tmem_base + h * BN, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        umma_commit(&tfull_bar[0]);
       }
     }
   } else {
@@ -177,28 +182,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       const int split = item / tiles_mn;
       const int rem = item % tiles_mn;
       const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int r = mt * 128 + row;
-      const bool valid = r < p.rows;
-      float* dst = p.partial + ((size_t)split * p.rows + (valid ? r : 0)) * p.cout + nt * BN;
-      mbar_wait(&tfull_bar[as], aphase);
+      const uint32_t aphase = it & 1;
+      mbar_wait(&tfull_bar[0], aphase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
+      for (int h = 0; h < kWgAcc; ++h) {
+        const int r = (mt * kWgAcc + h) * 128 + row;
+        const bool valid = r < p.rows;
+        float* dst = p.partial + ((size_t)split * p.rows + (valid ? r : 0)) * p.cout + nt * BN;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive(&tempty_bar[0]);
     }
   }
   tc_fence_before();
@@ -259,14 +266,24 @@ static WgradPlan plan_wgrad(int c0, int c1, int n, int h, int w, int ntaps, int 
   const int cin = c0 + c1;
   pl.rows = ntaps * cin;
   pl.n_boxes = ntaps * (cin / 64);
-  pl.n_mtiles = (pl.n_boxes + 1) / 2;
+  pl.n_mtiles = (pl.n_boxes + kWgBoxesPerItem - 1) / kWgBoxesPerItem;
   pl.n_ntiles = cout / pl.BN;
   const int tiles_mn = pl.n_mtiles * pl.n_ntiles;
-  // split K so that the grid is ~2 waves of work items, but keep >= 8 pixel tiles (512 px) per item
-  int splits = (2 * num_sms() + tiles_mn - 1) / tiles_mn;
-  const int max_splits = pl.ptiles / 8 > 0 ? pl.ptiles / 8 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // Split K (pixels) over CTAs.  Work items run in waves of one per SM, so the cost of a choice is
+  //   waves(s) * ceil(ptiles / s) stages  +  the fp32 partial tiles every split writes and the reduce kernel re-reads;
+  // pick the split count that minimises it (a fixed "2 waves" rule left up to a third of the SMs idle in the last wave).
+  const int sms = num_sms();
+  const int max_splits = pl.ptiles / 8 > 0 ? pl.ptiles / 8 : 1;     // >= 8 pixel tiles (512 px) per item
+  const double stage_cyc = kWgAcc * 4.0 * (pl.BN / 2.0) / 0.65;     // 4 MMAs of K=16 per accumulator and 64-pixel stage
+  const double partial_cyc = (double)pl.rows * cout * 8.0 / 2100.0; // write + re-read of one split's partial tile, chip-wide
+  int splits = 1;
+  double best = 1e300;
+  for (int sp = 1; sp <= max_splits && sp <= 4096; ++sp) {
+    const long long items = (long long)tiles_mn * sp;
+    const long long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * ((pl.ptiles + sp - 1) / sp) * stage_cyc + sp * partial_cyc;
+    if (cost < best) { best = cost; splits = sp; }
+  }
   pl.splits = splits;
   return pl;
 }
