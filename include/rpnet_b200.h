@@ -187,8 +187,12 @@ int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask
 
 /* Backward of Correlation (net/rp_net.py:153-181).  dq_bf16 NHWC [n][h][w][ld]: channels [0,(2r+1)^2) = d corr,
  * [add_off, add_off+c) = the direct gradient of fm1 from cat([corr, fm1]) (net/rp_net.py:81), added into df1. */
+/* workspace (optional): rpnet_local_corr_bwd_workspace_bytes(n, h, w, radius) bytes of scratch enable the tensor-core
+ * band-GEMM path (c % 64 == 0, maps of at least (8+2r) x (16+2r) pixels); without it the CUDA-core kernels run. */
+long long rpnet_local_corr_bwd_workspace_bytes(int n, int h, int w, int radius);
 int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const void* dq_bf16, int ld, int add_off, void* df1_bf16,
-                         void* df2_bf16, int n, int h, int w, int c, int radius, void* stream);
+                         void* df2_bf16, int n, int h, int w, int c, int radius, void* workspace, long long workspace_bytes,
+                         void* stream);
 
 /* Backward of calDist (net/rp_net.py:353-363).  feat fp32 [n][hw][64]; protos fp32 [proto_sets][p][64], image i uses
  * set i % proto_sets; dpred fp32 [n][p][hw]; dfeat (= or += when accumulate); dprotos += (caller zeroes; may be null). */

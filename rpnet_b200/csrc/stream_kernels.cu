@@ -572,6 +572,10 @@ RPNET_API int rpnet_premask_f16(const void* x, const float* mask, void* x_fg, vo
   return check_cuda(cudaGetLastError(), "premask launch");
 }
 
+namespace rpnet {
+int local_corr_tc(const void* f1, const void* f2, void* out, int n, int h, int w, int c, int radius, int out_c, cudaStream_t stream);
+}
+
 template <int R>
 static int launch_corr(const void* f1, const void* f2, void* out, int n, int h, int w, int c, int out_c, cudaStream_t stream) {
   constexpr int K = 2 * R + 1;
@@ -598,6 +602,10 @@ RPNET_API int rpnet_local_corr_f16(const void* f1, const void* f2, void* out, in
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % kCorrCC == 0, "local_corr: bad shape n=%d h=%d w=%d c=%d (c %% 32 == 0)", n, h, w, c);
   const int k = 2 * radius + 1;
   RPNET_REQUIRE(out_c >= k * k && out_c % 8 == 0, "local_corr: out_c=%d must be >= %d and a multiple of 8", out_c, k * k);
+  if (c % 64 == 0 && w >= 8 + 2 * radius && h >= 16 + 2 * radius) {      // tcgen05 banded-GEMM path (local_corr_tc.cu)
+    const int rc = local_corr_tc(f1, f2, out, n, h, w, c, radius, out_c, stream);
+    if (rc <= 0) return rc;
+  }
   switch (radius) {
     case 1: return launch_corr<1>(f1, f2, out, n, h, w, c, out_c, stream);
     case 2: return launch_corr<2>(f1, f2, out, n, h, w, c, out_c, stream);

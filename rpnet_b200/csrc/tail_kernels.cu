@@ -619,14 +619,30 @@ static int launch_corr_bwd(const void* f1, const void* f2, const void* dq, int l
   return check_cuda(cudaGetLastError(), "local_corr_bwd launch");
 }
 
+namespace rpnet {
+int local_corr_bwd_tc(const void* f1, const void* f2, const void* dq, int ld, int add_off, void* df1, void* df2, void* scratch,
+                      int n, int h, int w, int c, int radius, cudaStream_t stream);
+}
+
+RPNET_API long long rpnet_local_corr_bwd_workspace_bytes(int n, int h, int w, int radius) {
+  (void)radius;
+  return (long long)n * h * w * 128 * 2;        // re-indexed correlation gradient, rows padded to 128 bf16
+}
+
 RPNET_API int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const void* dq_bf16, int ld, int add_off, void* df1_bf16,
-                                    void* df2_bf16, int n, int h, int w, int c, int radius, void* stream_) {
+                                    void* df2_bf16, int n, int h, int w, int c, int radius, void* workspace,
+                                    long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(f1_f16 && f2_f16 && dq_bf16 && df1_bf16 && df2_bf16, "local_corr_bwd: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % kCbCC == 0, "local_corr_bwd: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
   const int k = 2 * radius + 1;
   RPNET_REQUIRE(ld % 8 == 0 && add_off % 8 == 0 && add_off >= k * k && add_off + c <= ld,
                 "local_corr_bwd: bad gradient layout ld=%d add_off=%d", ld, add_off);
+  if (workspace && workspace_bytes >= rpnet_local_corr_bwd_workspace_bytes(n, h, w, radius) && c % 64 == 0 && w >= 8 + 2 * radius &&
+      h >= 16 + 2 * radius) {                                       // tcgen05 band-GEMM path (local_corr_tc.cu)
+    const int rc = local_corr_bwd_tc(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, workspace, n, h, w, c, radius, stream);
+    if (rc <= 0) return rc;
+  }
   switch (radius) {
     case 1: return launch_corr_bwd<1>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);
     case 2: return launch_corr_bwd<2>(f1_f16, f2_f16, dq_bf16, ld, add_off, df1_bf16, df2_bf16, n, h, w, c, stream);

@@ -395,14 +395,20 @@ def premask_bwd(dxfg, dxbg, mask, dx, iters=1):
         _lib.check(lib.rpnet_premask_bwd_bf16(_ptr(dxfg), _ptr(dxbg), _ptr(mask), iters, pixels, c, _ptr(dx), _stream()), 'rpnet_premask_bwd_bf16')
 
 
-def local_corr_bwd(f1, f2, dq, add_off, radius, df1, df2):
+def local_corr_bwd(f1, f2, dq, add_off, radius, df1, df2, workspace=None):
+    """workspace: optional uint8/any tensor of >= local_corr_bwd_workspace_bytes(...) bytes (enables the tensor-core path)."""
     lib = _lib.load()
     _req(f1, torch.float16, 'f1'); _req(f2, torch.float16, 'f2'); _req(dq, bf16, 'dq'); _req(df1, bf16, 'df1'); _req(df2, bf16, 'df2')
     n, h, w, c = f1.shape
     assert f2.shape == f1.shape and df1.shape == f1.shape and df2.shape == f1.shape and tuple(dq.shape[:3]) == (n, h, w)
     with _Timed('local_corr_bwd', float(f1.numel() * 8 + dq.numel() * 2), n=2):
         _lib.check(lib.rpnet_local_corr_bwd(_ptr(f1), _ptr(f2), _ptr(dq), dq.shape[3], add_off, _ptr(df1), _ptr(df2), n, h, w, c, radius,
+                                            _ptr(workspace), 0 if workspace is None else workspace.numel() * workspace.element_size(),
                                             _stream()), 'rpnet_local_corr_bwd')
+
+
+def local_corr_bwd_workspace_bytes(n, h, w, radius):
+    return int(_lib.load().rpnet_local_corr_bwd_workspace_bytes(n, h, w, radius))
 
 
 def cos_sim_bwd(feat, protos, dpred, dfeat, dprotos=None, scaler=20.0, accumulate=False):

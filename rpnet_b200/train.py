@@ -472,7 +472,9 @@ class TrainEngine:
         dq = buf('b.dq', (n_tot, h, w, self.corr_c + C), bf16)
         L['q'].bwd(self, S['corr'], S['fm1'], S['z3'], S['st3'], gs_all, dx=dq, direct=dfeat)
         df1, df2 = buf('b.df1', (n_tot, h, w, C), bf16), buf('b.df2', (n_tot, h, w, C), bf16)
-        ops.local_corr_bwd(S['fm1'], S['fm2'], dq, self.corr_c, self.net.cre.radius, df1, df2)
+        r = self.net.cre.radius
+        ops.local_corr_bwd(S['fm1'], S['fm2'], dq, self.corr_c, r, df1, df2,
+                           workspace=self.scratch('corr_bwd', ops.local_corr_bwd_workspace_bytes(n_tot, h, w, r) // 2, bf16))
         dxfg, dxbg = buf('b.dxfg', (n_tot, h, w, C), bf16), buf('b.dxbg', (n_tot, h, w, C), bf16)
         L['wk'].bwd(self, S['xfg'], None, S['z1'], S['st1'], gs_all, dx=dxfg, direct=df1)
         L['wq'].bwd(self, S['xbg'], None, S['z2'], S['st2'], gs_all, dx=dxbg, direct=df2)

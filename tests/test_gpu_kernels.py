@@ -286,3 +286,25 @@ def test_error_convention(dev):
         ops.conv_igemm(x, w, [(0, 0)], sc, sc, out=torch.empty(1, 8, 8, 64, dtype=torch.float16, device=dev))
     with pytest.raises(_lib.RpnetError):
         ops.conv_igemm(x.cpu(), w, [(0, 0)], sc, sc, out=torch.empty(1, 8, 8, 64, dtype=torch.float16, device=dev))
+
+
+@pytest.mark.parametrize('case', [(2, 256, 64, 64, 5), (1, 64, 26, 18, 5), (3, 128, 37, 29, 5), (1, 64, 40, 24, 3), (2, 64, 18, 10, 1),
+                                  (1, 128, 33, 50, 2), (1, 64, 30, 31, 4)])
+def test_local_corr_tensor_core_path(dev, case):
+    """Maps at least one halo window large (w >= 8 + 2r, h >= 16 + 2r, c % 64 == 0) take the tcgen05 banded-GEMM kernel
+    (local_corr_tc.cu): same contract as the CUDA-core kernel, incl. ragged tiles, zero padding at the map border, the RAFT
+    x/y channel order (D8) and zero-filled padding channels."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import ops
+    n, c, h, w, r = case
+    g = _gen(sum(case))
+    f1, f2 = torch.randn(n, c, h, w, generator=g), torch.randn(n, c, h, w, generator=g)
+    k = (2 * r + 1) ** 2
+    oc = (k + 7) // 8 * 8 if r < 5 else 128
+    out = torch.full((n, h, w, oc), 7.0, dtype=torch.float16, device=dev)
+    ops.local_corr(_nhwc16(f1, dev), _nhwc16(f2, dev), r, out)
+    torch.cuda.synchronize()
+    want = O.correlation_local(_h(f1), _h(f2), r)
+    got = _nchw32(out)
+    torch.testing.assert_close(got[:, :k], want, rtol=2e-3, atol=2e-3)
+    assert torch.count_nonzero(got[:, k:]) == 0

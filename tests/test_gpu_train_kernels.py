@@ -458,3 +458,30 @@ def test_conv_bnstats(dev, case):
         s1, s2 = blk.sum((0, 2, 3)), (blk * blk).sum((0, 2, 3))
         torch.testing.assert_close(sums[i, :, 0].cpu(), s1, rtol=2e-3, atol=2e-3 * blk[0, 0].numel() ** 0.5)
         torch.testing.assert_close(sums[i, :, 1].cpu(), s2, rtol=2e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize('case', [(2, 256, 64, 64, 5), (1, 64, 26, 18, 5), (2, 128, 37, 29, 5), (1, 64, 40, 24, 3)])
+def test_local_corr_bwd_tensor_core_path(dev, case):
+    """With a workspace and maps of at least one halo window the backward runs as two tcgen05 band GEMMs
+    (local_corr_tc.cu); same contract as the CUDA-core kernels.  Gradients span several orders of magnitude on purpose (the
+    band operand is fp16 with a per-tile power-of-two scale)."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import ops
+    n, c, h, w, r = case
+    g = _gen(sum(case))
+    k = (2 * r + 1) ** 2
+    f1 = torch.randn(n, c, h, w, generator=g).half().float().requires_grad_(True)
+    f2 = torch.randn(n, c, h, w, generator=g).half().float().requires_grad_(True)
+    ld, add_off = 128 + c, 128
+    dq = torch.randn(n, ld, h, w, generator=g)
+    dq[:, :k] *= 1e-6 * torch.exp(3 * torch.randn(n, 1, h, w, generator=g))        # tiny, pixel-dependent magnitudes
+    dq = dq.to(bf16).float()
+    corr = O.correlation_local(f1, f2, r)
+    ((corr * dq[:, :k]).sum() + (f1 * dq[:, add_off:add_off + c]).sum()).backward()
+    df1 = torch.empty(n, h, w, c, dtype=bf16, device=dev); df2 = torch.empty_like(df1)
+    ws = torch.empty(ops.local_corr_bwd_workspace_bytes(n, h, w, r), dtype=torch.uint8, device=dev)
+    ops.local_corr_bwd(_nhwc(f1.detach(), torch.float16, dev), _nhwc(f2.detach(), torch.float16, dev), _nhwc(dq, bf16, dev), add_off, r,
+                       df1, df2, workspace=ws)
+    torch.cuda.synchronize()
+    assert _rel(_nchw(df1), f1.grad) < 4e-3, _rel(_nchw(df1), f1.grad)
+    assert _rel(_nchw(df2), f2.grad) < 6e-3, _rel(_nchw(df2), f2.grad)
