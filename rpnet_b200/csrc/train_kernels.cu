@@ -9,13 +9,23 @@
 // reference (own batch statistics, own running-stat update — SURVEY D14).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace rpnet {
 
 constexpr int kMaxGroups = 64;
 struct Groups {
   int G;
   int start[kMaxGroups + 1];
+  int bstart[kMaxGroups + 1];     // reduction kernels: blocks [bstart[g], bstart[g+1]) of the 1-D grid work on call group g
 };
+// group / block-in-group / blocks-of-group of this block in a reduction launch planned by plan_group_blocks()
+__device__ __forceinline__ void group_block(const Groups& gr, int& g, int& bx, int& nbx) {
+  g = 0;
+  while (g + 1 < gr.G && (int)blockIdx.x >= gr.bstart[g + 1]) ++g;
+  bx = (int)blockIdx.x - gr.bstart[g];
+  nbx = gr.bstart[g + 1] - gr.bstart[g];
+}
 __device__ __forceinline__ int group_of(const Groups& gr, int n) {
   int g = 0;
   while (g + 1 < gr.G && n >= gr.start[g + 1]) ++g;
@@ -29,6 +39,48 @@ static int make_groups(Groups* gr, const int* group_start, int groups, int n) {
   RPNET_REQUIRE(gr->start[0] == 0 && gr->start[groups] == n, "bn: group_start must span [0, %d]", n);
   for (int g = 0; g < groups; ++g) RPNET_REQUIRE(gr->start[g + 1] > gr->start[g], "bn: empty BatchNorm call group %d", g);
   return 0;
+}
+
+// Blocks per call group proportional to the group's size (a support pass of 80 images next to a query pass of 16 must not
+// get the same number of blocks), at most `budget` in total; returns the grid size.
+static int plan_group_blocks(Groups* gr, long long units_per_img, long long units_per_block, int budget = 0) {
+  if (budget <= 0) {
+    static int env_budget = -1;
+    if (env_budget < 0) {
+      const char* e = getenv("RPNET_BN_BLOCKS");          // tuning knob (blocks of a reduction launch); default 3 per SM
+      env_budget = e ? atoi(e) : 148 * 2;
+      if (env_budget <= 0) env_budget = 148 * 2;
+    }
+    budget = env_budget;
+  }
+  long long total_units = 0, want_sum = 0;
+  for (int g = 0; g < gr->G; ++g) {
+    const long long u = (long long)(gr->start[g + 1] - gr->start[g]) * units_per_img;
+    total_units += u;
+    want_sum += (u + units_per_block - 1) / units_per_block;
+  }
+  int acc = 0;
+  for (int g = 0; g < gr->G; ++g) {
+    const long long u = (long long)(gr->start[g + 1] - gr->start[g]) * units_per_img;
+    long long b = (u + units_per_block - 1) / units_per_block;
+    if (want_sum > budget) b = (long long)budget * u / (total_units > 0 ? total_units : 1);
+    if (b < 1) b = 1;
+    gr->bstart[g] = acc;
+    acc += (int)b;
+  }
+  gr->bstart[gr->G] = acc;
+  return acc;
+}
+
+// blocks of an element-wise (apply) launch: a few resident waves of 2 blocks per SM; RPNET_BN_APPLY_BLOCKS overrides
+static int apply_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RPNET_BN_APPLY_BLOCKS");
+    v = e ? atoi(e) : 148 * 4;
+    if (v <= 0) v = 148 * 4;
+  }
+  return v;
 }
 
 static int grid_for(long long total, int block, int cap_mult = 16) {
@@ -45,14 +97,15 @@ static int grid_for(long long total, int block, int cap_mult = 16) {
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, float* __restrict__ sums /*[G][C][2]*/) {
   __shared__ float s_red[256 * 16];
-  const int g = blockIdx.y;
+  int g, bx, nbx;
+  group_block(gr, g, bx, nbx);
   const int lanes = 256 / c8;
   const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
   const long long p0 = (long long)gr.start[g] * HW, p1 = (long long)gr.start[g + 1] * HW;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (long long p = p0 + (long long)blockIdx.x * lanes + pl; p < p1; p += (long long)gridDim.x * lanes) {
+  for (long long p = p0 + (long long)bx * lanes + pl; p < p1; p += (long long)nbx * lanes) {
     float f[8];
     unpack8_f16(__ldg(z + p * c8 + v), f);
 #pragma unroll
@@ -106,62 +159,84 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, Groups gr, in
 }
 
 // bn_apply: y = act(a * z + b) -> fp16 NHWC (optional), fp32 NHWC (optional), 2x2 max-pooled fp16 (optional).
+// Thread (pl, v): pixel lane pl, fixed 8-channel vector v (its (a, b) stay in registers; reloaded when the image moves to
+// another call group — pixels are visited in increasing order, so the group only moves forward).  U units per iteration
+// with all loads issued before the math; 32-bit index arithmetic (n*h*w < 2^31).
 template <bool POOL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Groups gr, int N, int H, int W, int c8, int relu,
                 uint4* __restrict__ y16, float* __restrict__ y32, uint4* __restrict__ ypool) {
+  constexpr int U = POOL ? 2 : 4;
   const int C = c8 * 8;
-  const int Hs = POOL ? H / 2 : H, Ws = POOL ? W / 2 : W;
-  const long long total = (long long)N * Hs * Ws * c8;
-  // 256 % c8 == 0 (host-checked), so the 8-channel vector a thread owns never changes: keep its (a, b) in registers and
-  // reload only when the image moves to another BatchNorm call group.
-  const int v = (int)(threadIdx.x % c8);
-  int cur_g = -1;
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  const unsigned Hs = POOL ? H / 2 : H, Ws = POOL ? W / 2 : W;
+  const unsigned units = (unsigned)N * Hs * Ws;
+  const unsigned stride = gridDim.x * lanes;
+  int g = 0;
+  unsigned g_end = (unsigned)gr.start[1] * Hs * Ws;          // first unit of the next call group
   float a[8], b[8];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i / c8;
-    const int xs = (int)(t % Ws);  t /= Ws;
-    const int ys = (int)(t % Hs);
-    const int n = (int)(t / Hs);
-    const int g = group_of(gr, n);
-    if (g != cur_g) {
-      cur_g = g;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
-        a[j] = st.z; b[j] = st.w;
+  for (int j = 0; j < 8; ++j) {
+    const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)v * 8 + j);
+    a[j] = st.z; b[j] = st.w;
+  }
+  for (unsigned u0 = blockIdx.x * lanes + pl; u0 < units; u0 += U * stride) {
+    uint4 zin[U][POOL ? 4 : 1];
+    unsigned pix[U][POOL ? 4 : 1];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const unsigned u = u0 + k * stride;
+      if (u < units) {
+        if (POOL) {
+          const unsigned xs = u % Ws, t = u / Ws;
+          const unsigned ys = t % Hs, n = t / Hs;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            pix[k][q] = (n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1);
+            zin[k][q] = __ldg(z + (size_t)pix[k][q] * c8 + v);
+          }
+        } else {
+          pix[k][0] = u;
+          zin[k][0] = __ldg(z + (size_t)u * c8 + v);
+        }
       }
     }
-    float best[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
-    uint4 zin[POOL ? 4 : 1];
+    for (int k = 0; k < U; ++k) {
+      const unsigned u = u0 + k * stride;
+      if (u >= units) break;
+      if (u >= g_end) {
+        while (u >= g_end) { ++g; g_end = (unsigned)gr.start[g + 1] * Hs * Ws; }
 #pragma unroll
-    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
-      const int y = POOL ? ys * 2 + (q >> 1) : ys, x = POOL ? xs * 2 + (q & 1) : xs;
-      zin[q] = __ldg(z + (((long long)n * H + y) * W + x) * c8 + v);
-    }
-#pragma unroll
-    for (int q = 0; q < (POOL ? 4 : 1); ++q) {
-      const int y = POOL ? ys * 2 + (q >> 1) : ys, x = POOL ? xs * 2 + (q & 1) : xs;
-      const long long pix = ((long long)n * H + y) * W + x;
-      float f[8];
-      unpack8_f16(zin[q], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float r = fmaf(f[j], a[j], b[j]);
-        r = relu ? fmaxf(r, 0.f) : r;
-        f[j] = r;
-        best[j] = fmaxf(best[j], r);
+        for (int j = 0; j < 8; ++j) {
+          const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+          a[j] = st.z; b[j] = st.w;
+        }
       }
-      if (y16) y16[pix * c8 + v] = pack8_f16(f);
-      if (y32) {
-        float4* d = reinterpret_cast<float4*>(y32 + (pix * c8 + v) * 8);
-        d[0] = make_float4(f[0], f[1], f[2], f[3]);
-        d[1] = make_float4(f[4], f[5], f[6], f[7]);
+      float best[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < (POOL ? 4 : 1); ++q) {
+        float f[8];
+        unpack8_f16(zin[k][q], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float r = fmaf(f[j], a[j], b[j]);
+          r = relu ? fmaxf(r, 0.f) : r;
+          f[j] = r;
+          best[j] = fmaxf(best[j], r);
+        }
+        if (y16) y16[(size_t)pix[k][q] * c8 + v] = pack8_f16(f);
+        if (y32) {
+          float4* d = reinterpret_cast<float4*>(y32 + ((size_t)pix[k][q] * c8 + v) * 8);
+          d[0] = make_float4(f[0], f[1], f[2], f[3]);
+          d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
       }
+      if (POOL) ypool[(size_t)u * c8 + v] = pack8_f16(best);
     }
-    if (POOL) ypool[i] = pack8_f16(best);
   }
 }
 
@@ -220,19 +295,20 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
   const int lanes = 256 / c8;
   const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
   int n_begin = 0, n_end = N;
-  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }   // a block stays inside one group
+  int bg = 0, bx = blockIdx.x, nbx = gridDim.x;
+  if (MODE == 0) { group_block(gr, bg, bx, nbx); n_begin = gr.start[bg]; n_end = gr.start[bg + 1]; }   // a block stays inside one group
   const long long units = (long long)(n_end - n_begin) * Hs * Ws;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int cur_g = -1;
   float a[8], b[8], c1[8], c0[8];          // MODE 0: c1 = mean (c0 unused); MODE 1: c1 = k1, c0 = k0
-  for (long long u = (long long)blockIdx.x * lanes + pl; u < units; u += (long long)gridDim.x * lanes) {
+  for (long long u = (long long)bx * lanes + pl; u < units; u += (long long)nbx * lanes) {
     long long t = u;
     const int xs = (int)(t % Ws);  t /= Ws;
     const int ys = (int)(t % Hs);
     const int n = n_begin + (int)(t / Hs);
-    const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, n);
+    const int g = MODE == 0 ? bg : group_of(gr, n);
     if (g != cur_g) {
       cur_g = g;
 #pragma unroll
@@ -312,7 +388,7 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
@@ -323,57 +399,63 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
 }
 
 // Direct-only specialisation (the gradient arrives as one bf16 NHWC tensor / channel slice: every conv that feeds another
-// conv): two pixels per thread and iteration with all four 16-byte loads issued before the math (memory-level parallelism).
+// conv): U pixels per thread and iteration with all 2U 16-byte loads issued before the math (memory-level parallelism),
+// 32-bit index arithmetic, call group tracked by pixel boundaries (pixels are visited in increasing order).
 template <int MODE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N,
                      int HW, int c8, int relu, const __nv_bfloat16* __restrict__ gdir, int d_ld, int d_off,
                      float* __restrict__ sums, uint4* __restrict__ dz) {
+  constexpr int U = 4;
   __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
   const int C = c8 * 8;
   const int lanes = 256 / c8;
   const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
-  int n_begin = 0, n_end = N;
-  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
-  const long long p_begin = (long long)n_begin * HW, p_end = (long long)n_end * HW;
+  int bg = 0, bx = blockIdx.x, nbx = gridDim.x;
+  unsigned p_begin = 0, p_end = (unsigned)N * HW;
+  if (MODE == 0) { group_block(gr, bg, bx, nbx); p_begin = (unsigned)gr.start[bg] * HW; p_end = (unsigned)gr.start[bg + 1] * HW; }
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  int cur_g = -1;
-  float a[8], b[8], c1[8], c0[8];
-  const long long stride = (long long)gridDim.x * lanes;
-  for (long long p = p_begin + (long long)blockIdx.x * lanes + pl; p < p_end; p += 2 * stride) {
-    const long long pq[2] = {p, p + stride};
-    const bool ok1 = pq[1] < p_end;
-    uint4 zr[2], gr_[2];
-    zr[0] = __ldg(z + pq[0] * c8 + v);
-    gr_[0] = __ldg(reinterpret_cast<const uint4*>(gdir + pq[0] * d_ld + d_off + v * 8));
-    if (ok1) {
-      zr[1] = __ldg(z + pq[1] * c8 + v);
-      gr_[1] = __ldg(reinterpret_cast<const uint4*>(gdir + pq[1] * d_ld + d_off + v * 8));
+  int g = MODE == 0 ? bg : -1;
+  unsigned g_end = MODE == 0 ? p_end : 0u;
+  float a[8], b[8], c1[8], c0[8];          // MODE 0: c1 = mean; MODE 1: c1 = k1, c0 = k0
+  if (MODE == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)bg * C + v * 8 + j);
+      a[j] = st.z; b[j] = st.w; c1[j] = st.x; c0[j] = 0.f;
+    }
+  }
+  const unsigned stride = (unsigned)nbx * lanes;
+  for (unsigned p0 = p_begin + (unsigned)bx * lanes + pl; p0 < p_end; p0 += U * stride) {
+    uint4 zr[U], gq[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const unsigned p = p0 + k * stride;
+      if (p < p_end) {
+        zr[k] = __ldg(z + (size_t)p * c8 + v);
+        gq[k] = __ldg(reinterpret_cast<const uint4*>(gdir + (size_t)p * d_ld + d_off + v * 8));
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 1 && !ok1) break;
-      const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, (int)(pq[k] / HW));
-      if (g != cur_g) {
-        cur_g = g;
+    for (int k = 0; k < U; ++k) {
+      const unsigned p = p0 + k * stride;
+      if (p >= p_end) break;
+      if (MODE == 1 && p >= g_end) {
+        do { ++g; g_end = (unsigned)gr.start[g + 1] * HW; } while (p >= g_end);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + (size_t)g * C + v * 8 + j);
+          const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);   // (m1, m2)
           a[j] = st.z; b[j] = st.w;
-          if (MODE == 0) {
-            c1[j] = st.x; c0[j] = 0.f;
-          } else {
-            const float2 cf = __ldg(reinterpret_cast<const float2*>(coef) + (size_t)g * C + v * 8 + j);
-            c1[j] = -st.z * cf.y * st.y;
-            c0[j] = -st.z * cf.x - c1[j] * st.x;
-          }
+          c1[j] = -st.z * cf.y * st.y;
+          c0[j] = -st.z * cf.x - c1[j] * st.x;
         }
       }
       float f[8], d[8], out[8];
       unpack8_f16(zr[k], f);
-      unpack8_bf16(gr_[k], d);
+      unpack8_bf16(gq[k], d);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float dd = (relu && !(fmaf(f[j], a[j], b[j]) > 0.f)) ? 0.f : d[j];
@@ -384,7 +466,7 @@ bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stat
           out[j] = fmaf(a[j], dd, fmaf(c1[j], f[j], c0[j]));
         }
       }
-      if (MODE == 1) dz[pq[k] * c8 + v] = pack8_bf16(out);
+      if (MODE == 1) dz[(size_t)p * c8 + v] = pack8_bf16(out);
     }
   }
   if (MODE == 0) {
@@ -399,7 +481,7 @@ bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stat
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
@@ -423,19 +505,20 @@ bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats,
   const int lanes = 256 / c8;
   const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
   int n_begin = 0, n_end = N;
-  if (MODE == 0) { n_begin = gr.start[blockIdx.y]; n_end = gr.start[blockIdx.y + 1]; }
+  int bg = 0, bx = blockIdx.x, nbx = gridDim.x;
+  if (MODE == 0) { group_block(gr, bg, bx, nbx); n_begin = gr.start[bg]; n_end = gr.start[bg + 1]; }
   const long long units = (long long)(n_end - n_begin) * Hs * Ws;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int cur_g = -1;
   float a[8], b[8], c1[8], c0[8];
-  for (long long u = (long long)blockIdx.x * lanes + pl; u < units; u += (long long)gridDim.x * lanes) {
+  for (long long u = (long long)bx * lanes + pl; u < units; u += (long long)nbx * lanes) {
     long long t = u;
     const int xs = (int)(t % Ws);  t /= Ws;
     const int ys = (int)(t % Hs);
     const int n = n_begin + (int)(t / Hs);
-    const int g = MODE == 0 ? (int)blockIdx.y : group_of(gr, n);
+    const int g = MODE == 0 ? bg : group_of(gr, n);
     if (g != cur_g) {
       cur_g = g;
 #pragma unroll
@@ -504,7 +587,7 @@ bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats,
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)blockIdx.y * C + v * 8) * 2;
+      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
@@ -687,13 +770,8 @@ RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, cons
   if (rc) return rc;
   RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
   const int lanes = 256 / (c / 8);
-  int max_imgs = 0;
-  for (int g = 0; g < groups; ++g) max_imgs = gr.start[g + 1] - gr.start[g] > max_imgs ? gr.start[g + 1] - gr.start[g] : max_imgs;
-  long long blocks = ((long long)max_imgs * h * w + lanes * 8 - 1) / (lanes * 8);
-  const long long cap = (148LL * 8 + groups - 1) / groups;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  bn_stats_kernel<<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(static_cast<const uint4*>(z), gr, h * w, c / 8, sums);
+  const int grid = plan_group_blocks(&gr, (long long)h * w, (long long)lanes * 8);
+  bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(z), gr, h * w, c / 8, sums);
   return check_cuda(cudaGetLastError(), "bn_stats launch");
 }
 
@@ -721,15 +799,20 @@ RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h
   Groups gr;
   int rc = make_groups(&gr, group_start, groups, n);
   if (rc) return rc;
-  if (y_pool_f16) {
-    const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-    bn_apply_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
-                                                                    static_cast<uint4*>(y_f16), y_f32, static_cast<uint4*>(y_pool_f16));
-  } else {
-    const long long total = (long long)n * h * w * (c / 8);
-    bn_apply_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
-                                                                     static_cast<uint4*>(y_f16), y_f32, nullptr);
-  }
+  RPNET_REQUIRE(256 % (c / 8) == 0, "bn_apply: c = %d must be a power of two in [8, 2048]", c);
+  RPNET_REQUIRE((long long)n * h * w < (1LL << 31), "bn_apply: more than 2^31 pixels");
+  const int lanes = 256 / (c / 8);
+  const long long units = y_pool_f16 ? (long long)n * (h / 2) * (w / 2) : (long long)n * h * w;
+  const int per_block = lanes * (y_pool_f16 ? 2 : 4);
+  long long grid = (units + per_block - 1) / per_block;
+  const long long cap_a = (long long)apply_blocks() * (units >= (1LL << 21) ? 2 : 1);    // large maps: more blocks in flight
+  if (grid > cap_a) grid = cap_a;
+  if (y_pool_f16)
+    bn_apply_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
+                                                             static_cast<uint4*>(y_f16), y_f32, static_cast<uint4*>(y_pool_f16));
+  else
+    bn_apply_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
+                                                              static_cast<uint4*>(y_f16), y_f32, nullptr);
   return check_cuda(cudaGetLastError(), "bn_apply launch");
 }
 
@@ -757,32 +840,26 @@ RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int 
   RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
   const bool win = g_pool_bf16 != nullptr;
   const int c8 = c / 8, lanes = 256 / c8;
-  int max_imgs = 0;
-  for (int g = 0; g < groups; ++g) max_imgs = gr.start[g + 1] - gr.start[g] > max_imgs ? gr.start[g + 1] - gr.start[g] : max_imgs;
-  const long long units_g = (long long)max_imgs * (win ? (h / 2) * (w / 2) : h * w);
-  long long blocks = (units_g + lanes * 4 - 1) / (lanes * 4);
-  const long long cap = (148LL * 8 + groups - 1) / groups;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
+  // reduction launches: 1-D grid, blocks per call group proportional to the group's size
+  RPNET_REQUIRE((long long)n * h * w < (1LL << 31), "bn_bwd: more than 2^31 pixels");
+  const int grid0 = plan_group_blocks(&gr, win ? (long long)(h / 2) * (w / 2) : (long long)h * w, (long long)lanes * (win ? 4 : 8));
   const uint4* zz = static_cast<const uint4*>(z);
   if (!win && g_direct && !d_is_f32 && !g_up_bf16) {       // direct-only bf16 gradient: specialised kernels
     const __nv_bfloat16* gd = static_cast<const __nv_bfloat16*>(g_direct);
-    long long nb0 = ((long long)max_imgs * h * w + lanes * 8 - 1) / (lanes * 8);
-    if (nb0 > cap) nb0 = cap;
-    if (nb0 < 1) nb0 = 1;
-    bn_bwd_direct_kernel<0><<<dim3((unsigned)nb0, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h * w, c8, relu, gd, d_ld, d_off,
+    bn_bwd_direct_kernel<0><<<grid0, 256, 0, stream>>>(zz, stats, nullptr, gr, n, h * w, c8, relu, gd, d_ld, d_off,
                                                                             sums, nullptr);
     RPNET_CUDA_OK(cudaGetLastError());
     bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
     RPNET_CUDA_OK(cudaGetLastError());
-    long long nb1 = ((long long)n * h * w + lanes * 2 - 1) / (lanes * 2);
-    if (nb1 > 148LL * 12) nb1 = 148LL * 12;
+    long long nb1 = ((long long)n * h * w + lanes * 4 - 1) / (lanes * 4);
+    const long long cap1 = (long long)apply_blocks() * ((long long)n * h * w >= (1LL << 21) ? 2 : 1);
+    if (nb1 > cap1) nb1 = cap1;
     bn_bwd_direct_kernel<1><<<(unsigned)nb1, 256, 0, stream>>>(zz, stats, coef, gr, n, h * w, c8, relu, gd, d_ld, d_off, nullptr,
                                                               static_cast<uint4*>(dz_bf16));
     return check_cuda(cudaGetLastError(), "bn_bwd(direct) launch");
   }
   if (win && !g_direct && !g_up_bf16) {       // pool-only consumers: specialised kernels
-    bn_bwd_pool_kernel<0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src.pooled,
+    bn_bwd_pool_kernel<0><<<grid0, 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src.pooled,
                                                                              p_ld, p_off, sums, nullptr);
     RPNET_CUDA_OK(cudaGetLastError());
     bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
@@ -794,8 +871,8 @@ RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int 
                                                            static_cast<uint4*>(dz_bf16));
     return check_cuda(cudaGetLastError(), "bn_bwd(pool) launch");
   }
-  if (win) bn_bwd_kernel<true, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
-  else     bn_bwd_kernel<false, 0><<<dim3((unsigned)blocks, groups), 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
+  if (win) bn_bwd_kernel<true, 0><<<grid0, 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
+  else     bn_bwd_kernel<false, 0><<<grid0, 256, 0, stream>>>(zz, stats, nullptr, gr, n, h, w, c8, relu, src, sums, nullptr);
   RPNET_CUDA_OK(cudaGetLastError());
   bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(sums, stats, gr, c, h * w, dgamma, dbeta, coef);
   RPNET_CUDA_OK(cudaGetLastError());
