@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header (bumped on any signature change). */
-int rpnet_abi_version(void);   /* currently 3 */
+int rpnet_abi_version(void);   /* currently 4 */
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* rpnet_last_error(void);
@@ -142,8 +142,9 @@ int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, in
                            void* w_fwd_f16, void* w_dgrad_bf16, void* stream);
 
 /* Train-mode nn.BatchNorm2d (net/modules.py:49,52,69; net/rp_net.py:52,57,67), statistics pass:
- * sums[g][c] = {sum z, sum z^2} over the images of call group g.  z fp16 NHWC. */
-int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+ * sums[g][c] = {sum z, sum z^2} over the images of call group g, in fp64 (the variance is a difference of nearly equal
+ * numbers for channels whose mean dwarfs their spread).  z fp16 NHWC. */
+int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                        void* stream);
 
 /* Train-mode conv: z = conv(src0 | src1) without bias (it cancels inside batch-statistics BatchNorm) stored as fp16 NHWC
@@ -154,12 +155,12 @@ int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* gro
  * Replaces nn.Conv2d + the statistics half of nn.BatchNorm2d(train): net/modules.py:47-54,66-71, net/rp_net.py:50-69. */
 int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack,
                            int ntaps, const int* tap_dy, const int* tap_dx, int cout, const float* ones, const float* zeros,
-                           void* z_f16, const int* group_start, int groups, float* sums, void* stream);
+                           void* z_f16, const int* group_start, int groups, double* sums, void* stream);
 
 /* stats[g][c] = {mean, rstd, a = rstd*gamma, b = beta - mean*a}; running_mean/var (momentum, unbiased var) updated once
  * per call group in order, num_batches_tracked += groups.  conv_bias: the bias the conv kernel dropped (it cancels in
  * train-mode BN but is part of the running mean).  hw = pixels per image. */
-int rpnet_bn_finalize_f32(const float* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
+int rpnet_bn_finalize_f32(const double* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
                           const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                           float* running_var, long long* num_batches_tracked, float* stats, void* stream);
 

@@ -28,7 +28,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBnGroups = 64;
-constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] floats
+constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] doubles
 
 struct ConvParams {
   int N, H, W;                    // pixel grid of the conv (input == output grid, stride 1)
@@ -53,7 +53,7 @@ struct ConvParams {
   int f32_C;
   // optional fused train-mode BatchNorm statistics: bn_sums[g][cout][2] += {sum, sum of squares} of the fp32 accumulators
   // over the valid pixels of call group g (images [bn_start[g], bn_start[g+1])); a tile never straddles two groups
-  float* bn_sums;
+  double* bn_sums;                // fp64: the variance is a difference of nearly equal sums when |mean| >> std
   int bn_groups;
   int bn_start[kMaxBnGroups + 1];
 };
@@ -66,7 +66,7 @@ struct ConvCfg {
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
-                                    kMaxBnCout * 2 * 4 /*fused BN statistics*/;
+                                    kMaxBnCout * 2 * 8 /*fused BN statistics*/;
 };
 
 template <int BN>
@@ -85,7 +85,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   uint64_t* tfull_bar = empty_bar + kStages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_bn = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
+  double* s_bn = reinterpret_cast<double*>(smem + kStages * Cfg::kStageBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -184,7 +184,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     const int cout_all = p.n_tiles_c * BN;
     int cur_g = -1;                                         // BatchNorm call group of the statistics held in s_bn
     if (p.bn_sums) {
-      for (int i = et; i < cout_all * 2; i += 128) s_bn[i] = 0.f;
+      for (int i = et; i < cout_all * 2; i += 128) s_bn[i] = 0.0;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
@@ -206,8 +206,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = et; i < cout_all * 2; i += 128) {
               atomicAdd(p.bn_sums + (size_t)cur_g * cout_all * 2 + i, s_bn[i]);
-              s_bn[i] = 0.f;
+              s_bn[i] = 0.0;
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // nobody accumulates the new group before the reset
           }
           cur_g = g;
         }
@@ -264,8 +265,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
               s2[j] = k2 + __shfl_xor_sync(0xffffffffu, g2, off);
             }
           }
-          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2], s1[0]);
-          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2 + 1], s2[0]);
+          // fp32 sums of 32 pixels, accumulated across tiles / warps / CTAs in fp64
+          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2], (double)s1[0]);
+          atomicAdd(&s_bn[(ct * BN + c0 + lane) * 2 + 1], (double)s2[0]);
         }
         if (o32 && valid) {
 #pragma unroll
@@ -384,7 +386,7 @@ static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMa
 
 using namespace rpnet;
 
-extern "C" int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+extern "C" int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                                   void* stream);
 
 static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
@@ -392,7 +394,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
                            const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
                            int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                            void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
-                           int bn_groups = 0, float* bn_sums = nullptr, int* bn_fused = nullptr) {
+                           int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -434,7 +436,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     if (ok) {
       p.bn_sums = bn_sums; p.bn_groups = bn_groups;
       for (int g = 0; g <= bn_groups; ++g) p.bn_start[g] = bn_group_start[g];
-      RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(float), stream));
+      RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(double), stream));
       if (bn_fused) *bn_fused = 1;
     }
   }
@@ -497,7 +499,7 @@ RPNET_API int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, 
 // See include/rpnet_b200.h for the contract.
 RPNET_API int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack,
                                       int ntaps, const int* tap_dy, const int* tap_dx, int cout, const float* ones,
-                                      const float* zeros, void* z_f16, const int* group_start, int groups, float* sums,
+                                      const float* zeros, void* z_f16, const int* group_start, int groups, double* sums,
                                       void* stream_) {
   RPNET_REQUIRE(z_f16 && sums && group_start, "conv_bnstats: null pointer argument");
   int fused = 0;

@@ -535,7 +535,7 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 3; }
+RPNET_API int rpnet_abi_version(void) { return 4; }
 
 RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                        const float* shift, int relu, void* out_f16, void* stream_) {

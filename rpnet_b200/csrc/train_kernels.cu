@@ -95,7 +95,7 @@ static int grid_for(long long total, int block, int cap_mult = 16) {
 // tree over the pixel lanes, one atomicAdd per channel per block.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, float* __restrict__ sums /*[G][C][2]*/) {
+bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, double* __restrict__ sums /*[G][C][2]*/) {
   __shared__ float s_red[256 * 16];
   int g, bx, nbx;
   group_block(gr, g, bx, nbx);
@@ -122,11 +122,11 @@ bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, float* _
     __syncthreads();
   }
   if (pl == 0) {
-    float* dst = sums + ((size_t)g * c8 * 8 + v * 8) * 2;
+    double* dst = sums + ((size_t)g * c8 * 8 + v * 8) * 2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
-      atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+      atomicAdd(dst + 2 * j, (double)s_red[threadIdx.x * 16 + j]);
+      atomicAdd(dst + 2 * j + 1, (double)s_red[threadIdx.x * 16 + 8 + j]);
     }
   }
 }
@@ -134,7 +134,7 @@ bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, float* _
 // bn_finalize: mean / rstd / folded (a, b) per (group, channel) + the running-statistics update of
 // nn.BatchNorm2d (momentum, unbiased running_var), applied once per call group IN ORDER.  `conv_bias` is the
 // bias the conv kernel dropped (it cancels inside train-mode BN but belongs to the running mean).
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, Groups gr, int C, int HW, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, Groups gr, int C, int HW, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
                                    float* running_mean, float* running_var, long long* num_batches_tracked,
                                    float* __restrict__ stats /*[G][C][4]*/) {
@@ -145,8 +145,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, Groups gr, in
   const float ga = gamma[c], be = beta[c], cb = conv_bias ? conv_bias[c] : 0.f;
   for (int g = 0; g < gr.G; ++g) {
     const float cnt = (float)(gr.start[g + 1] - gr.start[g]) * (float)HW;
-    const float mean = sums[((size_t)g * C + c) * 2] / cnt;
-    float var = sums[((size_t)g * C + c) * 2 + 1] / cnt - mean * mean;
+    // E[z^2] - E[z]^2 in fp64: channels whose mean dwarfs their standard deviation lose all fp32 digits in the subtraction
+    const double dmean = sums[((size_t)g * C + c) * 2] / (double)cnt;
+    const double dvar = sums[((size_t)g * C + c) * 2 + 1] / (double)cnt - dmean * dmean;
+    const float mean = (float)dmean;
+    float var = (float)dvar;
     var = var > 0.f ? var : 0.f;
     const float rstd = rsqrtf(var + eps);
     float* st = stats + ((size_t)g * C + c) * 4;
@@ -760,7 +763,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 using namespace rpnet;
 
-RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, float* sums,
+RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                                   void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(z && sums, "bn_stats: null pointer argument");
@@ -768,14 +771,14 @@ RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, cons
   Groups gr;
   int rc = make_groups(&gr, group_start, groups, n);
   if (rc) return rc;
-  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(double), stream));
   const int lanes = 256 / (c / 8);
   const int grid = plan_group_blocks(&gr, (long long)h * w, (long long)lanes * 8);
   bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(z), gr, h * w, c / 8, sums);
   return check_cuda(cudaGetLastError(), "bn_stats launch");
 }
 
-RPNET_API int rpnet_bn_finalize_f32(const float* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
+RPNET_API int rpnet_bn_finalize_f32(const double* sums, const int* group_start, int groups, int c, int hw, const float* gamma,
                                      const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                                      float* running_var, long long* num_batches_tracked, float* stats, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

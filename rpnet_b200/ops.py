@@ -301,7 +301,7 @@ def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0)):
 def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None):
     """Train-mode conv (no bias) -> z fp16 NHWC + BatchNorm statistics sums[g][cout][2] in the same launch."""
     lib = _lib.load()
-    _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack'); _req(z, torch.float16, 'z'); _req(sums, torch.float32, 'sums')
+    _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack'); _req(z, torch.float16, 'z'); _req(sums, torch.float64, 'sums')
     n, h, w, c0 = src0.shape
     c1 = 0
     if src1 is not None:
@@ -323,7 +323,7 @@ def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None
 
 def bn_stats(z, group_start, sums):
     lib = _lib.load()
-    _req(z, torch.float16, 'z'); _req(sums, torch.float32, 'sums')
+    _req(z, torch.float16, 'z'); _req(sums, torch.float64, 'sums')
     n, h, w, c = z.shape
     gs, g = _groups(group_start)
     assert sums.numel() >= g * c * 2
@@ -334,7 +334,7 @@ def bn_stats(z, group_start, sums):
 def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, running_var, nbt, stats, eps=1e-5, momentum=0.1):
     lib = _lib.load()
     gs, g = _groups(group_start)
-    assert stats.numel() >= g * c * 4 and stats.dtype == torch.float32
+    assert stats.numel() >= g * c * 4 and stats.dtype == torch.float32 and sums.dtype == torch.float64
     with _Timed('bn_finalize', float(g * c * 24)):
         _lib.check(lib.rpnet_bn_finalize_f32(_ptr(sums), gs, g, c, hw, _ptr(gamma), _ptr(beta), _ptr(conv_bias), float(eps),
                                              float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(nbt), _ptr(stats), _stream()),

@@ -256,7 +256,7 @@ class TrainEngine:
         stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
         y = self.buf(key + '.y', (n, h, w, c), f16) if want_y else None
         pool = self.buf(key + '.pool', (n, h // 2, w // 2, c), f16) if want_pool else None
-        l.fwd(x0, x1, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, f32), stats, y=y, pool=pool)
+        l.fwd(x0, x1, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, torch.float64), stats, y=y, pool=pool)
         self.act[key] = dict(x0=x0, x1=x1, z=z, stats=stats, gs=gs)
         return y, pool
 
@@ -334,7 +334,7 @@ class TrainEngine:
         xfg, xbg = S['xfg'][lo:hi], S['xbg'][lo:hi]
         ops.premask(d4, mask, xfg, xbg)
         G = len(gs) - 1
-        sums = self.scratch('bn_sums', G * 256 * 2, f32)
+        sums = self.scratch('bn_sums', G * 256 * 2, torch.float64)
         L['wk'].fwd(xfg, None, S['z1'][lo:hi], gs, sums, S['st1'][g0:g0 + G], y=S['fm1'][lo:hi])
         L['wq'].fwd(xbg, None, S['z2'][lo:hi], gs, sums, S['st2'][g0:g0 + G], y=S['fm2'][lo:hi])
         ops.local_corr(S['fm1'][lo:hi], S['fm2'][lo:hi], self.net.cre.radius, S['corr'][lo:hi])

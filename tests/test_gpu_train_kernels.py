@@ -159,7 +159,7 @@ def test_bn_train_forward(dev, case):
     want = torch.cat(ys).detach()
     zd = _nhwc(z, torch.float16, dev)
     G = len(gs) - 1
-    sums = torch.empty(G, c, 2, device=dev); stats = torch.empty(G, c, 4, device=dev)
+    sums = torch.empty(G, c, 2, device=dev, dtype=torch.float64); stats = torch.empty(G, c, 4, device=dev)
     rmd, rvd, nbt = rm.to(dev), rv.to(dev), torch.zeros((), dtype=torch.int64, device=dev)
     ops.bn_stats(zd, gs, sums)
     ops.bn_finalize(sums, gs, c, h * w, gamma.to(dev), beta.to(dev), bias.to(dev), rmd, rvd, nbt, stats)
@@ -208,7 +208,7 @@ def test_bn_backward(dev, mode):
     loss.backward()
     zd = _nhwc(z.detach(), torch.float16, dev)
     G = len(gs) - 1
-    sums = torch.empty(G, c, 2, device=dev); stats = torch.empty(G, c, 4, device=dev)
+    sums = torch.empty(G, c, 2, device=dev, dtype=torch.float64); stats = torch.empty(G, c, 4, device=dev)
     ops.bn_stats(zd, gs, sums)
     ops.bn_finalize(sums, gs, c, h * w, gamma.detach().to(dev), beta.detach().to(dev), None, None, None, None, stats)
     dz = torch.empty(n, h, w, c, dtype=bf16, device=dev)
@@ -448,7 +448,7 @@ def test_conv_bnstats(dev, case):
     wp = wt.permute(2, 3, 0, 1).reshape(k * k, cout, cin).half().contiguous().to(dev)
     z = torch.empty(n, h, w, cout, dtype=torch.float16, device=dev)
     G = len(gs) - 1
-    sums = torch.full((G, cout, 2), 7.0, device=dev)
+    sums = torch.full((G, cout, 2), 7.0, device=dev, dtype=torch.float64)
     ops.conv_bnstats(_nhwc(x[:, :c0], torch.float16, dev), wp, taps, torch.ones(cout, device=dev), torch.zeros(cout, device=dev), z, gs, sums,
                      src1=_nhwc(x[:, c0:], torch.float16, dev) if c1 else None)
     torch.cuda.synchronize()
@@ -456,8 +456,8 @@ def test_conv_bnstats(dev, case):
     for i in range(G):
         blk = want[gs[i]:gs[i + 1]]
         s1, s2 = blk.sum((0, 2, 3)), (blk * blk).sum((0, 2, 3))
-        torch.testing.assert_close(sums[i, :, 0].cpu(), s1, rtol=2e-3, atol=2e-3 * blk[0, 0].numel() ** 0.5)
-        torch.testing.assert_close(sums[i, :, 1].cpu(), s2, rtol=2e-3, atol=1e-3)
+        torch.testing.assert_close(sums[i, :, 0].float().cpu(), s1, rtol=2e-3, atol=2e-3 * blk[0, 0].numel() ** 0.5)
+        torch.testing.assert_close(sums[i, :, 1].float().cpu(), s2, rtol=2e-3, atol=1e-3)
 
 
 @pytest.mark.parametrize('case', [(2, 256, 64, 64, 5), (1, 64, 26, 18, 5), (2, 128, 37, 29, 5), (1, 64, 40, 24, 3)])
