@@ -33,6 +33,12 @@ WORKLOADS = {
     # BASELINE.json configs[2] (the configuration the metric is quoted on)
     'train': dict(name='cfg3: 5-shot 1-way, batch 16x256x256, T=4, train step (fwd+bwd+Adam)', ways=1, shots=5, batch=16,
                   size=256, T=4, train=True),
+    # BASELINE.json configs[3]: global batch 32 = 4 slices per GPU at 8 GPUs (weak scaling: 4 per rank at every N)
+    'cfg4': dict(name='cfg4: 5-shot 4-way, 4x256x256 per GPU (global 32 at 8 GPUs), T=6, train step (fwd+bwd+all-reduce+Adam)', ways=4,
+                 shots=5, batch=4, size=256, T=6, train=True),
+    # BASELINE.json configs[4]: one 96-slice volume, slices sharded over the ranks (strong scaling), eval loop of test_rpnet.py
+    'volume': dict(name='cfg5: 3D volume 96x256x256, sliding-window inference in batches of 16 slices, slice-sharded, T=4', ways=1,
+                   shots=1, batch=16, slices=96, size=256, T=4, train=False, volume=True),
 }
 
 
@@ -191,7 +197,20 @@ def main():
     net.load_state_dict(sd)
     net = net.to(dev)
     B = wl['batch']
-    ep = make_episode(B, wl['ways'], wl['shots'], wl['size'], seed=1000 * rank)     # per-rank shard (weak scaling)
+    if wl.get('volume'):
+        # one volume, this rank's contiguous slice range (strong scaling); a "step" = one pass over the rank's slices
+        from rpnet_b200 import volume as rp_volume
+        from rpnet_b200.train import shard_range
+        item = rp_volume.make_synthetic_volume(wl['slices'], wl['size'], wl['ways'], wl['shots'], seed=0)
+        lo, hi = shard_range(wl['slices'], rank, world)
+        cutv = lambda t: t[lo:hi].contiguous()
+        ep = {'supp_imgs': [[cutv(t) for t in way] for way in item['support_images']],
+              'fore_mask': [[cutv(t) for t in way] for way in item['support_fg']],
+              'back_mask': [[cutv(t) for t in way] for way in item['support_bg']], 'qry_imgs': [cutv(item['query_images'])],
+              'query_labels': cutv(item['query_labels']), 'appr_query_labels': cutv(item['appr_query_labels'])}
+        B = hi - lo                                   # slices this rank processes per step
+    else:
+        ep = make_episode(B, wl['ways'], wl['shots'], wl['size'], seed=1000 * rank)     # per-rank shard (weak scaling)
 
     # pinned host buffers (e2e) and resident device copies (value)
     def pin(t):
@@ -216,7 +235,8 @@ def main():
         return x.numel() * x.element_size()
     h2d = sum(nbytes(v) for v in host.values())
     resident = upload(host)
-    out_host = torch.empty(B, 1 + wl['ways'], wl['size'], wl['size'], dtype=torch.float32).pin_memory()
+    out_host = (torch.empty(B, wl['size'], wl['size'], dtype=torch.uint8) if wl.get('volume') else
+                torch.empty(B, 1 + wl['ways'], wl['size'], wl['size'], dtype=torch.float32)).pin_memory()
 
     if wl['train']:
         from rpnet_b200 import train as rp_train
@@ -225,6 +245,13 @@ def main():
 
         def step(d):
             return stepper.step(d)                   # returns the loss tensor (device)
+    elif wl.get('volume'):
+        net.eval()
+
+        def step(d):
+            r = rp_volume.segment_volume(net, d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'][0], d['appr_query_labels'],
+                                         batch_size=wl['batch'], rank=0, world=1)       # d already holds this rank's slices
+            return r['mask']
     else:
         net.eval()
 
@@ -275,7 +302,7 @@ def main():
     for _ in range(2):
         e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
-    d2h = 4 if wl['train'] else out_host.numel() * 4
+    d2h = 4 if wl['train'] else out_host.numel() * out_host.element_size()
 
     if rank != 0:
         if world > 1:
@@ -327,16 +354,17 @@ def main():
                          'flow incl. all-pairs correlation), %.0f ms/step' % (sample, ms)}
 
     ms_step = ms_total / args.steps
-    line = {'metric': METRIC, 'value': world * B / (ms_step * 1e-3), 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    total_units = wl['slices'] if wl.get('volume') else world * B
+    line = {'metric': METRIC, 'value': total_units / (ms_step * 1e-3), 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong' if wl.get('volume') else 'weak', 'vs_baseline': None,
             'dtype': 'fp16 operands, fp32 accumulate (tensor-core convs); fp32 elsewhere', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'ways': wl['ways'], 'shots': wl['shots'], 'batch_per_gpu': B,
-                       'global_batch': world * B, 'size': wl['size'], 'T': wl['T'], 'backbone': 'UNet',
+                       'global_batch': total_units, 'size': wl['size'], 'T': wl['T'], 'backbone': 'UNet',
                        'parallelism': 'dp%d (slices sharded, no data-path collective%s)' % (
                            world, '; NCCL grad all-reduce' if wl['train'] else ''),
                        'l2': 'per-step activation traffic (>1 GB) exceeds the 126 MB L2; no explicit flush'},
             'clocks': clk,
-            'e2e': {'value': world * B / (ms_e2e / args.steps * 1e-3), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d,
+            'e2e': {'value': total_units / (ms_e2e / args.steps * 1e-3), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': stream_kernels}
     print(json.dumps(line), flush=True)

@@ -115,3 +115,16 @@ def test_cpu_tensors_are_rejected_not_silently_computed():
     ep = make_episode(1, size=64)
     with pytest.raises(RuntimeError, match='CUDA'):
         net(ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], appr_query_labels=ep['appr_query_labels'])
+
+
+def test_volume_helpers_cpu():
+    """Host-side pieces of the slice-sharded volume loop (no kernels): Dice as utils/util.py:379-390, synthetic item shapes."""
+    import torch
+    from rpnet_b200 import volume as V
+    p = torch.tensor([[1, 1, 0, 0]]); t = torch.tensor([[1, 0, 1, 0]])
+    assert V.dice_from_sums(V.dice_sums(p, t)) == 0.5
+    assert V.dice_from_sums(V.dice_sums(torch.zeros(2, 2), torch.zeros(2, 2))) is None
+    item = V.make_synthetic_volume(6, 32, ways=1, shots=2, seed=1)
+    assert item['query_images'].shape == (6, 1, 32, 32) and item['query_labels'].shape == (6, 32, 32)
+    assert len(item['support_images']) == 1 and len(item['support_images'][0]) == 2
+    assert torch.equal(item['support_bg'][0][0], 1 - item['support_fg'][0][0])
