@@ -44,9 +44,12 @@ class _PackedModule(nn.Module):
 def run_conv_any(conv, bn, x_nhwc_or_img, ws, name, pack, relu=True, **kw):
     """Dispatch one conv(+BN+ReLU): Cin in {1, 3} fp32 NCHW images go to the streaming first-conv kernel,
     everything else to the tensor-core implicit GEMM."""
-    if pack is None:        # first conv, fp32 NCHW image input
-        scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) \
-            if bn is not None else engine.fold_bn(conv.bias)
+    if pack is None or isinstance(pack, tuple):        # first conv, fp32 NCHW image input
+        if isinstance(pack, tuple):
+            scale, shift = pack                          # folded once per weight version (conv_block._build_packs)
+        else:
+            scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) \
+                if bn is not None else engine.fold_bn(conv.bias)
         n, _, h, w = x_nhwc_or_img.shape
         out = ws.get(name, (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device)
         ops.conv3x3_first(x_nhwc_or_img.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, relu, out)
@@ -72,9 +75,13 @@ class conv_block(_PackedModule):
         )
 
     def _build_packs(self):
-        first = None if self.ch_in in (1, 3) else engine.conv_bn_pack(self.conv[0], self.conv[1])
-        if first is None and self.ch_out != 64:
-            raise NotImplementedError('conv_block: a %d-channel image input needs ch_out == 64' % self.ch_in)
+        if self.ch_in in (1, 3):
+            if self.ch_out != 64:
+                raise NotImplementedError('conv_block: a %d-channel image input needs ch_out == 64' % self.ch_in)
+            c, b = self.conv[0], self.conv[1]
+            first = engine.fold_bn(c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)    # (scale, shift) tuple
+        else:
+            first = engine.conv_bn_pack(self.conv[0], self.conv[1])
         return first, engine.conv_bn_pack(self.conv[3], self.conv[4])
 
     def run_nhwc(self, x, ws, name, x1=None, want_out=True, want_pool=False):
@@ -82,8 +89,8 @@ class conv_block(_PackedModule):
         Returns (out, pooled)."""
         _check_eval(self)
         p0, p1 = self._packs()
-        if p0 is None:
-            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', None)
+        if isinstance(p0, tuple):
+            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', p0)
         else:
             a, _ = engine.run_conv(p0, x, ws, name + '.0', src1=x1)
         return engine.run_conv(p1, a, ws, name + '.3', want_out=want_out, want_pool=want_pool)
