@@ -115,13 +115,12 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[t][j] = __ldg(wgt + (cg * 8 + j) * 9 + t) * sc;
   }
-  const int Wp = (W + 1) >> 1;                                   // pixel pairs per row
-  const long long total = (long long)N * H * Wp * 8;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
-    const long long pp = gid >> 3;
+  const unsigned Wp = (unsigned)(W + 1) >> 1;                    // pixel pairs per row
+  const unsigned total = (unsigned)N * H * Wp;                   // pixel pairs (< 2^31, host-checked)
+  for (unsigned pp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; pp < total; pp += (gridDim.x * blockDim.x) >> 3) {
     const int x = (int)(pp % Wp) * 2;
-    const int y = (int)((pp / Wp) % H);
-    const long long n = pp / ((long long)Wp * H);
+    const int y = (int)((pp / Wp) % (unsigned)H);
+    const long long n = pp / (Wp * (unsigned)H);
     const float* plane = img + n * H * W;
     float v[3][4];
 #pragma unroll

@@ -300,17 +300,17 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
   int n_begin = 0, n_end = N;
   int bg = 0, bx = blockIdx.x, nbx = gridDim.x;
   if (MODE == 0) { group_block(gr, bg, bx, nbx); n_begin = gr.start[bg]; n_end = gr.start[bg + 1]; }   // a block stays inside one group
-  const long long units = (long long)(n_end - n_begin) * Hs * Ws;
+  const unsigned units = (unsigned)(n_end - n_begin) * Hs * Ws;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int cur_g = -1;
   float a[8], b[8], c1[8], c0[8];          // MODE 0: c1 = mean (c0 unused); MODE 1: c1 = k1, c0 = k0
-  for (long long u = (long long)bx * lanes + pl; u < units; u += (long long)nbx * lanes) {
-    long long t = u;
-    const int xs = (int)(t % Ws);  t /= Ws;
-    const int ys = (int)(t % Hs);
-    const int n = n_begin + (int)(t / Hs);
+  for (unsigned u = (unsigned)bx * lanes + pl; u < units; u += (unsigned)nbx * lanes) {
+    unsigned t = u;
+    const int xs = (int)(t % (unsigned)Ws);  t /= (unsigned)Ws;
+    const int ys = (int)(t % (unsigned)Hs);
+    const int n = n_begin + (int)(t / (unsigned)Hs);
     const int g = MODE == 0 ? bg : group_of(gr, n);
     if (g != cur_g) {
       cur_g = g;
@@ -510,17 +510,17 @@ bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats,
   int n_begin = 0, n_end = N;
   int bg = 0, bx = blockIdx.x, nbx = gridDim.x;
   if (MODE == 0) { group_block(gr, bg, bx, nbx); n_begin = gr.start[bg]; n_end = gr.start[bg + 1]; }
-  const long long units = (long long)(n_end - n_begin) * Hs * Ws;
+  const unsigned units = (unsigned)(n_end - n_begin) * Hs * Ws;
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int cur_g = -1;
   float a[8], b[8], c1[8], c0[8];
-  for (long long u = (long long)bx * lanes + pl; u < units; u += (long long)nbx * lanes) {
-    long long t = u;
-    const int xs = (int)(t % Ws);  t /= Ws;
-    const int ys = (int)(t % Hs);
-    const int n = n_begin + (int)(t / Hs);
+  for (unsigned u = (unsigned)bx * lanes + pl; u < units; u += (unsigned)nbx * lanes) {
+    unsigned t = u;
+    const int xs = (int)(t % (unsigned)Ws);  t /= (unsigned)Ws;
+    const int ys = (int)(t % (unsigned)Hs);
+    const int n = n_begin + (int)(t / (unsigned)Hs);
     const int g = MODE == 0 ? bg : group_of(gr, n);
     if (g != cur_g) {
       cur_g = g;
@@ -708,21 +708,21 @@ conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restric
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-  const long long total = (long long)N * H * W * 8;
-  for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total; gid += (long long)gridDim.x * blockDim.x) {
-    const long long p = gid >> 3;
-    const int x = (int)(p % W), y = (int)((p / W) % H);
-    const long long base = p - (long long)y * W - x;            // n * H * W
+  const unsigned total = (unsigned)N * H * W;                    // pixels (< 2^31, host-checked)
+  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < total; p += (gridDim.x * blockDim.x) >> 3) {
+    const unsigned x = p % (unsigned)W, y = (p / (unsigned)W) % (unsigned)H;
+    const unsigned base = p - y * W - x;                          // n * H * W
+    const size_t gid = (size_t)p * 8 + cg;
     float d[8];
     unpack8_bf16(__ldg(dz + gid), d);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
+      const int yy = (int)y + ky - 1;
       const bool yok = yy >= 0 && yy < H;
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        const float v = (yok && xx >= 0 && xx < W) ? __ldg(img + base + (long long)yy * W + xx) : 0.f;
+        const int xx = (int)x + kx - 1;
+        const float v = (yok && xx >= 0 && xx < W) ? __ldg(img + base + (unsigned)(yy * W + xx)) : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], v, acc[ky * 3 + kx][j]);
       }
@@ -929,7 +929,7 @@ RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int
 RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && dz_bf16 && grad, "conv3x3_first_wgrad: null pointer argument");
-  RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first_wgrad: bad shape");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && (long long)n * h * w < (1LL << 31), "conv3x3_first_wgrad: bad shape");
   const long long total = (long long)n * h * w * 8;
   long long blocks = (total + 256 * 16 - 1) / (256 * 16);
   if (blocks > 148LL * 4) blocks = 148LL * 4;
