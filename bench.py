@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--workload', default=os.environ.get('RPNET_BENCH_WORKLOAD', 'train'), choices=sorted(WORKLOADS),
                     help="'train' = BASELINE.json configs[2], the configuration the metric is quoted on (default); 'infer' = configs[1]")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true', help='inference workloads: launch every kernel from Python')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
@@ -247,6 +248,7 @@ def main():
             return stepper.step(d)                   # returns the loss tensor (device)
     elif wl.get('volume'):
         net.eval()
+        net.enable_cuda_graph(not args.no_cuda_graph)
 
         def step(d):
             r = rp_volume.segment_volume(net, d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'][0], d['appr_query_labels'],
@@ -254,6 +256,7 @@ def main():
             return r['mask']
     else:
         net.eval()
+        net.enable_cuda_graph(not args.no_cuda_graph)
 
         def step(d):
             with torch.no_grad():
@@ -287,8 +290,21 @@ def main():
     if rank == 0:
         clocks.start()
     prof = {}
-    ms_total, launches = timed(lambda: step(resident), args.steps, prof)
-    clk = clocks.stop() if rank == 0 else None
+    graphed = (not wl['train']) and not args.no_cuda_graph
+    if graphed:
+        # the timed region replays CUDA graphs (no per-kernel events possible); the per-kernel CUDA-event timing for the
+        # roofline comes from a second pass of the same K steps with every kernel launched from Python
+        ms_total, _ = timed(lambda: step(resident), args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        net.enable_cuda_graph(False)
+        for _ in range(2):
+            step(resident)
+        _, launches = timed(lambda: step(resident), args.steps, prof)
+        net.enable_cuda_graph(True)
+        step(resident)
+    else:
+        ms_total, launches = timed(lambda: step(resident), args.steps, prof)
+        clk = clocks.stop() if rank == 0 else None
 
     # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the result, every step
     def e2e_step():
@@ -334,6 +350,8 @@ def main():
                 'algorithmic_flops_per_step': algo, 'launches_per_step': kern['conv_igemm']['launches'], 'kernel_ms_per_step': conv_ms,
                 'executed_tflops': kern['conv_igemm']['work_per_step'] / (conv_ms * 1e-3) / 1e12,
                 'kernel_share_of_step': conv_ms / (ms_total / args.steps)}
+    if graphed:
+        roofline['note'] = 'kernel times from a second pass without CUDA-graph replay; value / ms_per_step from graph replay'
     if 'conv_wgrad' in kern:
         wg_ms = kern['conv_wgrad']['ms_per_step']
         roofline['wgrad'] = {'kernel': 'conv_wgrad_kernel (tcgen05, MN-major operands, split-K)', 'achieved': fwd_algo / (wg_ms * 1e-3) / 1e12,
@@ -346,7 +364,7 @@ def main():
                       for k, v in kern.items()}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (rank 0's host cores)
         sample = 2 if not wl['train'] else 1
         val, ms, cores = cpu_reference(wl, 3, 1, sample)
         cpu = {'value': val, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',

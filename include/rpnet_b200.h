@@ -51,6 +51,15 @@ int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int
                          int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                          void* out_pool_f16, float* out_f32, void* stream);
 
+/* A 64-output-channel tap-list conv (same operands as rpnet_conv_igemm_f16) whose epilogue also evaluates calDist
+ * (net/rp_net.py:353-363) on the activated output: pred[i][p][pixel] = scaler * cos(y[i,pixel,:], protos[i % proto_sets][p][:])
+ * with torch's per-norm 1e-8 clamp.  protos fp32 [proto_sets][n_protos][64], pred fp32 [n][n_protos][h*w]; out_f32 (optional)
+ * fp32 NHWC [n][h][w][64] = the features themselves.  Fuses cre.q (net/rp_net.py:65-69,81) with the prototype match
+ * (:287-303) in the eval forward: the 64-channel features never travel to HBM. */
+int rpnet_conv_cos_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack, int ntaps,
+                       const int* tap_dy, const int* tap_dx, const float* scale, const float* shift, int relu,
+                       const float* protos, int n_protos, int proto_sets, float scaler, float* pred, float* out_f32, void* stream);
+
 /* First encoder conv: fp32 NCHW image [n][cin][h][w] (cin 1 or 3) -> 64 channels, 3x3 pad 1, fused
  * affine (+ReLU), fp16 NHWC out [n][h][w][64].  weight fp32 [64][cin][3][3] (PyTorch layout).
  * Replaces encoder.Conv1.conv.0-2 (net/modules.py:48-50 via net/unet.py:405) and VGG features.0.0

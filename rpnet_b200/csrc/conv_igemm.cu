@@ -28,6 +28,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBnGroups = 64;
+constexpr int kMaxCosP = 8;       // prototypes of the fused calDist epilogue (1 + ways)
 constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] doubles
 
 struct ConvParams {
@@ -51,6 +52,12 @@ struct ConvParams {
   int pool_C;
   float* out_f32;                 // optional fp32 NHWC output (N, H, W, f32_C)
   int f32_C;
+  // optional fused calDist (net/rp_net.py:353-363) on the activated output of a 64-channel conv (the whole feature vector of
+  // a pixel sits in one accumulator row): cos_pred[n][p][pixel] = cos_scaler * cos(y[n,pixel,:], cos_protos[n % cos_sets][p][:])
+  const float* cos_protos;
+  float* cos_pred;
+  int cos_P, cos_sets;
+  float cos_scaler;
   // optional fused train-mode BatchNorm statistics: bn_sums[g][cout][2] += {sum, sum of squares} of the fp32 accumulators
   // over the valid pixels of call group g (images [bn_start[g], bn_start[g+1])); a tile never straddles two groups
   double* bn_sums;                // fp64: the variance is a difference of nearly equal sums when |mean| >> std
@@ -234,6 +241,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         opool = p.out_pool + (static_cast<size_t>(n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_C + ct * BN;
       if (p.out_f32) o32 = p.out_f32 + (static_cast<size_t>(n * p.H + y) * p.W + x) * p.f32_C + ct * BN;
       const bool pool_writer = valid && ((x & 1) == 0) && ((y & 1) == 0);
+      float cos_nn = 0.f, cos_pn[kMaxCosP], cos_dot[kMaxCosP];
+#pragma unroll
+      for (int q2 = 0; q2 < kMaxCosP; ++q2) { cos_pn[q2] = 0.f; cos_dot[q2] = 0.f; }
+      const float* cos_pr = p.cos_pred ? p.cos_protos + (size_t)((valid ? n : 0) % p.cos_sets) * p.cos_P * 64 : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -243,6 +254,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         for (int j = 0; j < 32; ++j) {
           float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]);
           v[j] = p.relu ? fmaxf(t, 0.f) : t;
+        }
+        if (BN == 64 && p.cos_pred) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cos_nn = fmaf(v[j], v[j], cos_nn);
+#pragma unroll
+          for (int q2 = 0; q2 < kMaxCosP; ++q2) {
+            if (q2 < p.cos_P) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 pr = __ldg(reinterpret_cast<const float4*>(cos_pr + q2 * 64 + c0 + j));
+                cos_dot[q2] = fmaf(v[j], pr.x, fmaf(v[j + 1], pr.y, fmaf(v[j + 2], pr.z, fmaf(v[j + 3], pr.w, cos_dot[q2]))));
+                cos_pn[q2] = fmaf(pr.x, pr.x, fmaf(pr.y, pr.y, fmaf(pr.z, pr.z, fmaf(pr.w, pr.w, cos_pn[q2]))));
+              }
+            }
+          }
         }
         if (p.bn_sums) {
           // per-channel sums over the 32 pixels of this warp: butterfly transpose-reduce (31 shuffles per array); lane l
@@ -291,6 +317,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
               *reinterpret_cast<uint4*>(opool + c0 + j) = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
           }
         }
+      }
+      if (BN == 64 && p.cos_pred && valid) {
+        // torch's cosine_similarity: each norm clamped at 1e-8 separately
+        const float xn = fmaxf(sqrtf(cos_nn), 1e-8f);
+        const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+        for (int q2 = 0; q2 < kMaxCosP; ++q2)
+          if (q2 < p.cos_P)
+            p.cos_pred[((size_t)n * p.cos_P + q2) * hw + (size_t)y * p.W + x] =
+                p.cos_scaler * (cos_dot[q2] / (xn * fmaxf(sqrtf(cos_pn[q2]), 1e-8f)));
       }
       tc_fence_before();
       __syncwarp();
@@ -394,7 +430,8 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
                            const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
                            int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                            void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
-                           int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr) {
+                           int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr, const float* cos_protos = nullptr,
+                           int cos_P = 0, int cos_sets = 0, float cos_scaler = 0.f, float* cos_pred = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -402,7 +439,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv_igemm: bad grid %d x %d x %d", n, h, w);
   RPNET_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "conv_igemm: ntaps %d out of range [1, %d]", ntaps, kMaxTaps);
   RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_igemm: cout must be a multiple of 64 (got %d)", cout);
-  RPNET_REQUIRE(out_f16 || out_pool_f16 || out_f32, "conv_igemm: no output requested");
+  RPNET_REQUIRE(out_f16 || out_pool_f16 || out_f32 || cos_pred, "conv_igemm: no output requested");
   RPNET_REQUIRE(!out_pool_f16 || (h % 2 == 0 && w % 2 == 0), "conv_igemm: fused 2x2 max-pool needs even H, W (got %d x %d)", h, w);
   const int BN = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
 
@@ -427,6 +464,12 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   p.out_f32 = out_f32; p.f32_C = cout;
   p.bn_sums = nullptr; p.bn_groups = 0;
   if (bn_fused) *bn_fused = 0;
+  p.cos_pred = nullptr; p.cos_protos = nullptr; p.cos_P = 0; p.cos_sets = 1; p.cos_scaler = 0.f;
+  if (cos_pred) {
+    RPNET_REQUIRE(cout == 64 && cos_protos && cos_P >= 1 && cos_P <= kMaxCosP && cos_sets >= 1,
+                  "conv_igemm: the fused calDist epilogue needs cout == 64 and 1..%d prototypes (got cout=%d, P=%d)", kMaxCosP, cout, cos_P);
+    p.cos_pred = cos_pred; p.cos_protos = cos_protos; p.cos_P = cos_P; p.cos_sets = cos_sets; p.cos_scaler = cos_scaler;
+  }
   if (bn_sums) {
     // fuse the statistics when no pixel tile straddles two call groups and the per-CTA accumulators fit
     RPNET_REQUIRE(bn_groups >= 1 && bn_groups <= kMaxBnGroups && bn_group_start, "conv_igemm: bn groups %d out of range [1, %d]", bn_groups, kMaxBnGroups);
@@ -508,4 +551,14 @@ RPNET_API int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1,
   if (rc) return rc;
   if (!fused) return rpnet_bn_stats_f16(z_f16, n, h, w, cout, group_start, groups, sums, stream_);   // tiny maps: separate pass
   return 0;
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_cos_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack, int ntaps,
+                                  const int* tap_dy, const int* tap_dx, const float* scale, const float* shift, int relu,
+                                  const float* protos, int n_protos, int proto_sets, float scaler, float* pred, float* out_f32,
+                                  void* stream_) {
+  RPNET_REQUIRE(protos && pred, "conv_cos: null pointer argument");
+  return conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, 64, scale, shift, relu, nullptr, h, w, 64, 0, 1,
+                         0, 1, 0, nullptr, out_f32, stream_, nullptr, 0, nullptr, nullptr, protos, n_protos, proto_sets, scaler, pred);
 }

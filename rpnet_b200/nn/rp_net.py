@@ -56,8 +56,10 @@ class ContextCorrelationEncoder(_PackedModule):
                                       self.q[1].running_var, self.q[1].eps)
         return pk, pq, engine.ConvPack(wp, taps, scale, shift, True)
 
-    def run_nhwc(self, x, mask, tag):
-        """x fp16 NHWC [n, h, w, C]; mask fp32 [n, h, w] -> fp32 NHWC [n, h, w, 64] (cre(x*m, x*(1-m)))."""
+    def run_nhwc(self, x, mask, tag, cos=None):
+        """x fp16 NHWC [n, h, w, C]; mask fp32 [n, h, w] -> fp32 NHWC [n, h, w, 64] (cre(x*m, x*(1-m))).
+        cos = (protos fp32 [sets, P, 64], pred fp32 [n, P, h, w], scaler): the prototype match (calDist, net/rp_net.py:353-363)
+        runs in the epilogue of the last conv and the features are not written at all (returns None)."""
         _check_eval(self)
         ws = self._ws
         pk, pq, pqq = self._packs()
@@ -65,9 +67,9 @@ class ContextCorrelationEncoder(_PackedModule):
         xfg = ws.get(tag + '.xfg', x.shape, torch.float16, dev)
         xbg = ws.get(tag + '.xbg', x.shape, torch.float16, dev)
         ops.premask(x, mask, xfg, xbg)
-        return self.run_pair_nhwc(xfg, xbg, tag)
+        return self.run_pair_nhwc(xfg, xbg, tag, cos)
 
-    def run_pair_nhwc(self, xfg, xbg, tag):
+    def run_pair_nhwc(self, xfg, xbg, tag, cos=None):
         ws = self._ws
         pk, pq, pqq = self._packs()
         n, h, w, _ = xfg.shape
@@ -75,6 +77,10 @@ class ContextCorrelationEncoder(_PackedModule):
         fm2, _ = engine.run_conv(pq, xbg, ws, tag + '.fm2')
         corr = ws.get(tag + '.corr', (n, h, w, self.corr_channels), torch.float16, xfg.device)
         ops.local_corr(fm1, fm2, self.radius, corr)
+        if cos is not None:
+            protos, pred, scaler = cos
+            ops.conv_cos(corr, pqq.wpack, pqq.taps, pqq.scale, pqq.shift, protos, pred, relu=True, src1=fm1, scaler=scaler)
+            return None
         return engine.run_conv(pqq, corr, ws, tag + '.q', src1=fm1, out_f32=True)
 
     def forward(self, fm1, fm2):
@@ -186,10 +192,29 @@ class RP_Net(nn.Module):
         if dev.type != 'cuda':
             raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU')
 
+        # ---- the four input tensors of the kernel schedule (list plumbing of net/rp_net.py:245-267)
+        n_supp = n_ways * n_shots * B
+        imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
+        fore = torch.stack([torch.stack(way, dim=0) for way in fore_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
+        back = torch.stack([torch.stack(way, dim=0) for way in back_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
+        appr = qmask_in.reshape(B, H, W).float().contiguous()
+        if getattr(self, '_use_graph', False):
+            logits = self._forward_eval_graphed(imgs, fore, back, appr, n_ways, n_shots, B)
+        else:
+            logits = self._forward_eval(imgs, fore, back, appr, n_ways, n_shots, B)
+        refinement = {i: logits[i] for i in range(self.num_iter)}
+        # the reference's final block recomputes the last iteration bit-for-bit (net/rp_net.py:314-346, SURVEY D5);
+        # align_loss is 0 outside training (net/rp_net.py:340)
+        return {'output': logits[self.num_iter - 1].clone(), 'align_loss': 0 / B, 'refinement': refinement}
+
+    def _forward_eval(self, imgs, fore, back, appr, n_ways, n_shots, B):
+        """The eval kernel schedule on plain tensors: imgs [(Wa*Sh+1)*B, C, H, W] (support images first), fore / back
+        [Wa*Sh*B, H, W], appr [B, H, W] -> logits [T, B, 1+Wa, H, W] (= out['refinement'][i])."""
+        S, ws, dev = self.scale, self._ws, imgs.device
+        H, W = imgs.shape[-2:]
+        n_supp = n_ways * n_shots * B
         # ---- encoder: support and query images in ONE batch (eval-mode BN is per-sample; the reference runs two
         #      passes, net/rp_net.py:245-262 — identical results)
-        n_supp = n_ways * n_shots * B
-        imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0)
         d4 = self._encode(imgs, 'enc')                                   # [(Wa*Sh+1)*B, h, w, C] fp16 NHWC
         h, w = d4.shape[1:3]
         if h * S != H or w * S != W:
@@ -197,37 +222,64 @@ class RP_Net(nn.Module):
                              "set `scale: %d` in the yaml" % (S, h, w, H, W, H // h))
         supp_d4, qry_d4 = d4[:n_supp], d4[n_supp:]
 
-        fore = torch.stack([torch.stack(way, dim=0) for way in fore_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
-        back = torch.stack([torch.stack(way, dim=0) for way in back_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
-
         # ---- support branch: cre per (way, shot) with its own pooled fore mask (net/rp_net.py:271-275)
         supp_m = ws.get('supp_m', (n_supp, h, w), torch.float32, dev)
         ops.avgpool_mask(fore, S, supp_m)
         supp_feat = self.cre.run_nhwc(supp_d4, supp_m, 'supp')           # fp32 NHWC [n_supp, h, w, 64]
 
         # ---- prototypes, hoisted out of the T loop (net/rp_net.py:288-299)
+        # getFeatures through the adjoint of the bilinear upsample: sum(up(f) * m) == sum(f * U^T m)  (no H x W feature temp)
         raw = ws.get('proto_raw', (n_ways, n_shots, B, 2, 64), torch.float32, dev)
-        ops.masked_avg_pool(supp_feat, fore, back, raw.view(n_supp, 2, 64))
+        wf, wb = ws.get('wmap_f', (n_supp, h, w), torch.float32, dev), ws.get('wmap_b', (n_supp, h, w), torch.float32, dev)
+        sf, sb = ws.get('msum_f', (n_supp,), torch.float32, dev), ws.get('msum_b', (n_supp,), torch.float32, dev)
+        ops.bilinear_adjoint(fore, wf, sf)
+        ops.bilinear_adjoint(back, wb, sb)
+        ops.weighted_pool(supp_feat, wf, wb, sf, sb, raw.view(n_supp, 2, 64))
         protos = ws.get('protos', (B, 1 + n_ways, 64), torch.float32, dev)
         ops.proto_finalize(raw, protos)
 
         # ---- recurrent refinement (net/rp_net.py:280-312)
         qm = ws.get('qry_m', (B, h, w), torch.float32, dev)
-        ops.avgpool_mask(qmask_in.reshape(B, H, W).float().contiguous(), S, qm)
+        ops.avgpool_mask(appr, S, qm)
         pred = ws.get('pred', (B, 1 + n_ways, h, w), torch.float32, dev)
-        refinement = {}
-        logits = None
+        logits = torch.empty(self.num_iter, B, 1 + n_ways, H, W, dtype=torch.float32, device=dev)
         for i in range(self.num_iter):
-            qfeat = self.cre.run_nhwc(qry_d4, qm, 'qry')
-            ops.cos_sim(qfeat, protos, pred, 20.0)
-            logits = torch.empty(B, 1 + n_ways, H, W, dtype=torch.float32, device=dev)
-            ops.upsample_tail(pred, logits, qm, S, bool(self.backbone_cfg['soft_mask']))
-            refinement[i] = logits
+            self.cre.run_nhwc(qry_d4, qm, 'qry', cos=(protos, pred, 20.0))       # cre + calDist (fused epilogue)
+            ops.upsample_tail(pred, logits[i], qm, S, bool(self.backbone_cfg['soft_mask']))
+        return logits
 
-        # the reference's final block recomputes the last iteration bit-for-bit (net/rp_net.py:314-346, SURVEY D5);
-        # align_loss is 0 outside training (net/rp_net.py:340)
-        output = logits.clone()
-        return {'output': output, 'align_loss': 0 / B, 'refinement': refinement}
+    # ------------------------------------------------------------------ CUDA-graph replay of the eval schedule
+    def enable_cuda_graph(self, flag=True):
+        """Replay the eval forward as one CUDA graph per input shape (the recurrent loop is ~60 small launches per
+        iteration: launch latency dominates at small batches).  Captured graphs are dropped when the
+        weights change.  The returned logits are copies, so results stay valid across calls."""
+        self._use_graph = bool(flag)
+        self._graphs = {}
+        return self
+
+    def _forward_eval_graphed(self, imgs, fore, back, appr, n_ways, n_shots, B):
+        sig = tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        key = (tuple(imgs.shape), n_ways, n_shots, B, engine.WEIGHTS_EPOCH)
+        entry = self._graphs.get(key)
+        if entry is not None and entry['sig'] != sig:
+            entry = None
+        if entry is None:
+            self._graphs = {k: v for k, v in self._graphs.items() if v['sig'] == sig}        # drop stale captures
+            static = [imgs.clone(), fore.clone(), back.clone(), appr.clone()]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                    # warm-up outside capture: packs, workspaces, func attributes
+                self._forward_eval(*static, n_ways, n_shots, B)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_eval(*static, n_ways, n_shots, B)
+            entry = {'graph': graph, 'static': static, 'out': out, 'sig': sig}
+            self._graphs[key] = entry
+        for dst, src in zip(entry['static'], (imgs, fore, back, appr)):
+            dst.copy_(src, non_blocking=True)
+        entry['graph'].replay()
+        return entry['out'].clone()
 
     def _forward_train(self, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_labels):
         """Train-mode forward (BatchNorm batch statistics per reference call; alignLoss when cfg['align']):

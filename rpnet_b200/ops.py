@@ -92,6 +92,26 @@ def conv_igemm(src0, wpack, taps, scale, shift, relu=True, src1=None, out=None, 
     _lib.check(rc, 'rpnet_conv_igemm_f16')
 
 
+def conv_cos(src0, wpack, taps, scale, shift, protos, pred, relu=True, src1=None, scaler=20.0, out_f32=None):
+    """64-channel conv + fused calDist epilogue: pred fp32 [n, P, h, w] from protos fp32 [sets, P, 64] (image i -> set i % sets)."""
+    lib = _lib.load()
+    _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack'); _req(protos, torch.float32, 'protos'); _req(pred, torch.float32, 'pred')
+    n, h, w, c0 = src0.shape
+    c1 = 0
+    if src1 is not None:
+        _req(src1, torch.float16, 'src1')
+        c1 = src1.shape[3]
+    ntaps, cout, cin = wpack.shape
+    sets, P = protos.shape[0], protos.shape[1]
+    if cout != 64 or cin != c0 + c1 or ntaps != len(taps) or tuple(pred.shape) != (n, P, h, w) or protos.shape[2] != 64:
+        raise _lib.RpnetError('conv_cos: shapes do not match (wpack %s, pred %s, protos %s)' % (tuple(wpack.shape), tuple(pred.shape), tuple(protos.shape)))
+    dy, dx = _taps(taps)
+    with _Timed('conv_cos', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_cos_f16(_ptr(src0), c0, _ptr(src1), c1, n, h, w, _ptr(wpack), ntaps, dy, dx, _ptr(scale), _ptr(shift),
+                                    int(bool(relu)), _ptr(protos), P, sets, float(scaler), _ptr(pred), _ptr(out_f32), _stream())
+    _lib.check(rc, 'rpnet_conv_cos_f16')
+
+
 def conv3x3_first(img, weight, scale, shift, relu, out):
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')

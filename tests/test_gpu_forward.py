@@ -150,3 +150,32 @@ def test_vgg_backbone_through_rpnet(dev):
     out = _run(net.to(dev).eval(), ep, dev)
     for i in range(2):
         _check_logits(out['refinement'][i], ref['refinement'][i], 'vgg refinement[%d]' % i)
+
+
+def test_cuda_graph_replay_equals_eager(dev):
+    """enable_cuda_graph(): the eval schedule replayed as one CUDA graph gives bit-identical logits, follows new inputs,
+    and is re-captured after the weights change."""
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, perturb_bn_stats, to_device
+    sd = perturb_bn_stats(weights.unet_rpnet_state_dict(0))
+    net = _model(sd, _cfg(2), dev)
+    eps = [to_device(make_episode(2, 1, 2, 64, seed=s), dev) for s in (1, 2)]
+
+    def run(d):
+        with torch.no_grad():
+            return net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
+    eager = [run(d) for d in eps]
+    net.enable_cuda_graph(True)
+    for rep in range(2):
+        for d, ref in zip(eps, eager):
+            out = run(d)
+            assert torch.equal(out['output'], ref['output'])
+            assert all(torch.equal(out['refinement'][i], ref['refinement'][i]) for i in range(2))
+    first = run(eps[0])['output'].clone()
+    run(eps[1])
+    assert torch.equal(first, eager[0]['output'])                      # returned tensors are not aliased by later replays
+    with torch.no_grad():
+        net.cre.q[0].weight.mul_(1.5)                                   # weight change -> stale capture must not be replayed
+    changed = run(eps[0])['output']
+    net.enable_cuda_graph(False)
+    assert torch.equal(changed, run(eps[0])['output']) and not torch.equal(changed, eager[0]['output'])

@@ -308,3 +308,31 @@ def test_local_corr_tensor_core_path(dev, case):
     got = _nchw32(out)
     torch.testing.assert_close(got[:, :k], want, rtol=2e-3, atol=2e-3)
     assert torch.count_nonzero(got[:, k:]) == 0
+
+
+@pytest.mark.parametrize('case', [(3, 128, 256, 16, 24, 1, 2, 3), (4, 64, 0, 32, 32, 3, 5, 2), (2, 128, 64, 8, 8, 1, 3, 1)])
+def test_conv_cos_fused_epilogue(dev, case):
+    """rpnet_conv_cos_f16: 64-channel conv (+affine+ReLU) with calDist (net/rp_net.py:353-363) in the epilogue == the conv
+    followed by F.cosine_similarity * 20 against the per-image prototype set (image i -> set i % sets), incl. an all-zero
+    feature vector (cosine 0) and the optional fp32 feature output."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import ops
+    n, c0, c1, h, w, k, P, sets = case
+    g = _gen(sum(case))
+    cin = c0 + c1
+    x = torch.randn(n, cin, h, w, generator=g).half().float()
+    wt = (torch.randn(64, cin, k, k, generator=g) / (cin * k * k) ** 0.5).half().float()
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    shift[:] -= 0.1
+    protos = torch.randn(sets, P, 64, generator=g)
+    y = torch.relu(F.conv2d(x, wt, None, padding=k // 2) * scale[None, :, None, None] + shift[None, :, None, None])
+    want = torch.stack([torch.stack([O.cal_dist(y[i:i + 1], protos[i % sets, p][None])[0] for p in range(P)]) for i in range(n)])
+    taps = [(ky - k // 2, kx - k // 2) for ky in range(k) for kx in range(k)]
+    wp = wt.permute(2, 3, 0, 1).reshape(k * k, 64, cin).half().contiguous().to(dev)
+    pred = torch.full((n, P, h, w), 7.0, device=dev)
+    feat = torch.empty(n, h, w, 64, device=dev)
+    ops.conv_cos(_nhwc16(x[:, :c0], dev), wp, taps, scale.to(dev), shift.to(dev), protos.to(dev), pred, relu=True,
+                 src1=_nhwc16(x[:, c0:], dev) if c1 else None, scaler=20.0, out_f32=feat)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(feat.cpu().permute(0, 3, 1, 2), y, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(pred.cpu(), want, rtol=2e-3, atol=2e-2)
