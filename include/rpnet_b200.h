@@ -81,6 +81,15 @@ int rpnet_premask_f16(const void* x, const float* mask, void* x_fg, void* x_bg, 
 int rpnet_local_corr_f16(const void* f1, const void* f2, void* out, int n, int h, int w, int c, int radius,
                          int out_c, void* stream);
 
+/* Fused relation head of the eval forward: Correlation(f1, f2, r) -> cat([corr, f1]) -> cre.q 1x1 conv + folded BN + ReLU ->
+ * calDist against the prototypes (net/rp_net.py:79-84, 287-303), one tcgen05 kernel; only pred leaves the SM.
+ * f1, f2 fp16 NHWC [n][h][w][c]; wq_pack fp16 [1][64][128 + c] (the corr block of the input channels padded to 128);
+ * scale / shift fp32 [64]; protos fp32 [proto_sets][n_protos][64] (image i uses set i % proto_sets); pred fp32 [n][n_protos][h*w].
+ * Returns -2 for shapes the fused kernel does not cover (callers then run rpnet_local_corr_f16 + rpnet_conv_cos_f16). */
+int rpnet_relation_head_f16(const void* f1, const void* f2, const void* wq_pack, const float* scale, const float* shift,
+                            const float* protos, int n_protos, int proto_sets, float scaler, float* pred, int n, int h, int w,
+                            int c, int radius, void* stream);
+
 /* getFeatures (net/rp_net.py:366-376) for two masks at once:
  *   out[i][k][ch] = sum_{Y,X} bilinear_up(feat[i])[ch,Y,X] * mask_k[i][Y,X] / (sum mask_k[i] + 1e-5)
  * feat fp32 NHWC [n][h][w][c] (c <= 64), mask0/mask1 fp32 [n][mask_h][mask_w], out fp32 [n][2][c]. */

@@ -17,6 +17,12 @@
 namespace rpnet {
 
 constexpr int kLcTW = 8, kLcTH = 16;        // pixel tile
+
+// 2-byte store through the shared window (32-bit address arithmetic, STS instead of a generic ST)
+__device__ __forceinline__ void sts_f16(uint32_t saddr, float v) {
+  const __half h = __float2half_rn(v);
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+}
 constexpr int kLcThreads = 192;
 constexpr int kLcStages = 2;
 constexpr int kLcMaxOutC = 128;
@@ -127,7 +133,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
     const int px = row & (kLcTW - 1), py = row >> 3;         // py = 4q + (lane >> 3)
     const int et = threadIdx.x - 64;
     const int pairs = p.out_c >> 1;                          // 32-bit words per output pixel
-    __half* s_row = reinterpret_cast<__half*>(s_out + row * Cfg::kOutPitch);
+    const uint32_t s_row = smem_u32(s_out + row * Cfg::kOutPitch);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -136,7 +142,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       const int n = t / p.tiles_y;
       const int x0 = tx * kLcTW, y0 = ty * kLcTH;
       // padding channels [K*K, out_c) are zero by contract
-      for (int c = Cfg::K * Cfg::K; c < p.out_c; ++c) s_row[c] = __float2half(0.f);
+      for (int c = Cfg::K * Cfg::K; c < p.out_c; ++c) sts_f16(s_row + 2 * c, 0.f);
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
@@ -149,10 +155,10 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         tmem_ld_wait();
         const unsigned b = (unsigned)(hy - py);
         if (b < (unsigned)Cfg::K) {
-          __half* dst = s_row + b - px * Cfg::K;            // + a * K with a = j - px
+          const uint32_t dst = s_row + 2 * ((int)b - px * Cfg::K);   // + 2 * a * K with a = j - px
 #pragma unroll
           for (int j = 0; j < Cfg::HW; ++j) {
-            if ((unsigned)(j - px) < (unsigned)Cfg::K) dst[j * Cfg::K] = __float2half_rn(v[j] * p.scale);
+            if ((unsigned)(j - px) < (unsigned)Cfg::K) sts_f16(dst + 2 * j * Cfg::K, v[j] * p.scale);
           }
         }
       }
@@ -220,6 +226,290 @@ int local_corr_tc(const void* f1, const void* f2, void* out, int n, int h, int w
   }
 }
 
+
+// =====================================================================================================================
+// Fused relation head of the eval forward (net/rp_net.py:77-84 tail + :287-303): local correlation -> cat([corr, fm1]) ->
+// cre.q 1x1 conv + folded BN + ReLU -> calDist against the prototypes, one kernel, nothing but the (1+Wa) cosine maps leaves
+// the SM.  Per 8 x 16 pixel tile:
+//   phase 1  D1[128 px][NH] = F1 * F2halo^T over the 64-channel chunks (as local_corr_tc_kernel);
+//   extract  the band of D1 -> fp16 K-major swizzled operand tile in shared memory (the corr block of the concat);
+//   phase 2  D2[128 px][64] = [corr | fm1] * Wq^T: the f1 chunks are re-fetched (L2-hot) and Wq arrives into the two pipeline
+//            slots the main loop has just drained; D2 reuses TMEM columns 0..63;
+//   epilogue affine + ReLU + cosine vs prototypes -> pred[n][p][pixel].
+// =====================================================================================================================
+struct RhParams {
+  int N, H, W, chunks;
+  int tiles_x, tiles_y;
+  float corr_scale;
+  const float* scale;       // folded BN of cre.q: y = relu(acc * scale + shift)
+  const float* shift;
+  const float* protos;      // [sets][P][64]
+  int P, sets;
+  float cos_scaler;
+  float* pred;              // [n][P][h*w]
+};
+
+template <int R>
+__global__ void __launch_bounds__(kLcThreads, 1)
+relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_constant__ CUtensorMap tm_f2,
+                     const __grid_constant__ CUtensorMap tm_w, const RhParams p) {
+  using Cfg = LcCfg<R>;
+  constexpr int kMaxP = 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_corr = tiles + kLcStages * Cfg::kStageBytes;                     // 2 x [128 rows x 64 K] fp16, K-major SW128
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_corr + 2 * 16384);
+  uint64_t* empty_bar = full_bar + kLcStages;
+  uint64_t* tfull_bar = empty_bar + kLcStages;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint64_t* corr_bar = tempty_bar + 1;
+  uint64_t* d2_bar = corr_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_x * p.tiles_y * p.N;
+  const int kq = 2 + p.chunks;                                               // 64-wide K chunks of the 1x1 conv
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_f1);
+    tma_prefetch_desc(&tm_f2);
+    tma_prefetch_desc(&tm_w);
+    for (int i = 0; i < kLcStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    mbar_init(corr_bar, 1);
+    mbar_init(d2_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.tiles_x;  t /= p.tiles_x;
+        const int ty = t % p.tiles_y;
+        const int n = t / p.tiles_y;
+        const int x0 = tx * kLcTW, y0 = ty * kLcTH;
+        for (int kc = 0; kc < p.chunks; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::NH * 128);
+          tma_load_4d(&tm_f1, &full_bar[stage], a_dst, kc * 64, x0, y0, n);
+          tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
+          if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+        }
+        // phase 2, slot A: all f1 chunks of the tile again (the A operand of the fm1 half of the 1x1 conv)
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], p.chunks * Cfg::kABytes);
+        for (int kc = 0; kc < p.chunks; ++kc)
+          tma_load_4d(&tm_f1, &full_bar[stage], tiles + stage * Cfg::kStageBytes + kc * Cfg::kABytes, kc * 64, x0, y0, n);
+        if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+        // phase 2, slot B: the packed 1x1 weights [64 cout][64 K] per K chunk
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], kq * 8192);
+        for (int kc = 0; kc < kq; ++kc)
+          tma_load_3d(&tm_w, &full_bar[stage], tiles + stage * Cfg::kStageBytes + kc * 8192, kc * 64, 0, 0);
+        if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_f16(128, Cfg::NMMA);
+      const uint32_t idesc2 = umma_idesc_f16(128, 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(tempty_bar, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < p.chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
+#pragma unroll
+          for (int half = 0; half < Cfg::NPAD / Cfg::NMMA; ++half) {
+            const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + half * Cfg::NMMA * 128, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(tmem_base + half * Cfg::NMMA, a_desc + 2 * k, b_desc + 2 * k, idesc1, (kc | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar);
+        // ---- phase 2
+        const int sa = stage;
+        const uint32_t pa = phase;
+        if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+        const int sb = stage;
+        const uint32_t pb = phase;
+        if (++stage == kLcStages) { stage = 0; phase ^= 1; }
+        mbar_wait(&full_bar[sa], pa);
+        mbar_wait(&full_bar[sb], pb);
+        mbar_wait(corr_bar, it & 1);                     // band extracted (D1 fully read) and staged as an operand tile
+        tc_fence_after();
+        const uint32_t f1_addr = smem_u32(tiles + sa * Cfg::kStageBytes);
+        const uint32_t w_addr = smem_u32(tiles + sb * Cfg::kStageBytes);
+        const uint32_t c_addr = smem_u32(s_corr);
+        for (int kc = 0; kc < kq; ++kc) {
+          const uint64_t a_desc = umma_desc_sw128(kc < 2 ? c_addr + kc * 16384 : f1_addr + (kc - 2) * Cfg::kABytes, 1024);
+          const uint64_t b_desc = umma_desc_sw128(w_addr + kc * 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc2, (kc | k) != 0);
+        }
+        umma_commit(&empty_bar[sa]);
+        umma_commit(&empty_bar[sb]);
+        umma_commit(d2_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int px = row & (kLcTW - 1), py = row >> 3;
+    const uint32_t s_crow = smem_u32(s_corr) + row * 128;
+    const int sw = row & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int tx = t % p.tiles_x;  t /= p.tiles_x;
+      const int ty = t % p.tiles_y;
+      const int n = t / p.tiles_y;
+      const int x = tx * kLcTW + px, y = ty * kLcTH + py;
+      const bool valid = x < p.W && y < p.H;
+      mbar_wait(tfull_bar, it & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      // padding channels [K*K, 128) of the corr operand are zero
+#pragma unroll
+      for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch)
+        sts_f16(s_crow + (ch >> 6) * 16384 + ((((ch & 63) >> 3) ^ sw) << 4) + (ch & 7) * 2, 0.f);
+#pragma unroll 1
+      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; ++hy) {
+        float v[32];
+        tmem_ld32(t_addr + hy * Cfg::HW, v);
+        tmem_ld_wait();
+        const unsigned b = (unsigned)(hy - py);
+        if (b < (unsigned)Cfg::K) {
+          const int off = (int)b - px * Cfg::K;                 // channel = j * K + off with a = j - px
+#pragma unroll
+          for (int j = 0; j < Cfg::HW; ++j) {
+            if ((unsigned)(j - px) < (unsigned)Cfg::K) {
+              const int ch = j * Cfg::K + off;
+              sts_f16(s_crow + (ch >> 6) * 16384 + ((((ch & 63) >> 3) ^ sw) << 4) + (ch & 7) * 2, v[j] * p.corr_scale);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) mbar_arrive(corr_bar);
+      // ---- phase-2 epilogue: affine + ReLU + cosine against the prototypes of this image
+      mbar_wait(d2_bar, it & 1);
+      tc_fence_after();
+      float nn = 0.f, pn[kMaxP], dot[kMaxP];
+#pragma unroll
+      for (int k = 0; k < kMaxP; ++k) { pn[k] = 0.f; dot[k] = 0.f; }
+      const float* pr_base = p.protos + (size_t)(n % p.sets) * p.P * 64;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + c0 + j), __ldg(p.shift + c0 + j)), 0.f);
+          nn = fmaf(v[j], v[j], nn);
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxP; ++k) {
+          if (k < p.P) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 pr = __ldg(reinterpret_cast<const float4*>(pr_base + k * 64 + c0 + j));
+              dot[k] = fmaf(v[j], pr.x, fmaf(v[j + 1], pr.y, fmaf(v[j + 2], pr.z, fmaf(v[j + 3], pr.w, dot[k]))));
+              pn[k] = fmaf(pr.x, pr.x, fmaf(pr.y, pr.y, fmaf(pr.z, pr.z, fmaf(pr.w, pr.w, pn[k]))));
+            }
+          }
+        }
+      }
+      if (valid) {
+        const float xn = fmaxf(sqrtf(nn), 1e-8f);
+        const size_t hw = (size_t)p.H * p.W;
+#pragma unroll
+        for (int k = 0; k < kMaxP; ++k)
+          if (k < p.P) p.pred[((size_t)n * p.P + k) * hw + (size_t)y * p.W + x] = p.cos_scaler * (dot[k] / (xn * fmaxf(sqrtf(pn[k]), 1e-8f)));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int R>
+static int launch_relation_head(const void* f1, const void* f2, const void* wq, const float* scale, const float* shift,
+                                const float* protos, int P, int sets, float cos_scaler, float* pred, int n, int h, int w, int c,
+                                cudaStream_t stream) {
+  using Cfg = LcCfg<R>;
+  constexpr int kSmem = kLcStages * Cfg::kStageBytes + 2 * 16384 + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(relation_head_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_set = true;
+  }
+  const int chunks = c / 64;
+  if (chunks * Cfg::kABytes > Cfg::kStageBytes || (2 + chunks) * 8192 > Cfg::kStageBytes) return 1;   // phase-2 tiles must fit a slot
+  CUtensorMap t1, t2, tw;
+  const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  const uint64_t str[3] = {(uint64_t)c, (uint64_t)c * w, (uint64_t)c * w * h};
+  const uint32_t box1[4] = {64u, (uint32_t)kLcTW, (uint32_t)kLcTH, 1u};
+  const uint32_t box2[4] = {64u, (uint32_t)Cfg::HW, (uint32_t)Cfg::HH, 1u};
+  int rc = make_tmap_2b(&t1, f1, 4, dims, str, box1, false);
+  if (rc) return rc;
+  rc = make_tmap_2b(&t2, f2, 4, dims, str, box2, false);
+  if (rc) return rc;
+  const uint64_t cin = 128 + (uint64_t)c;
+  const uint64_t wdims[3] = {cin, 64, 1};
+  const uint64_t wstr[2] = {cin, cin * 64};
+  const uint32_t wbox[3] = {64u, 64u, 1u};
+  rc = make_tmap_2b(&tw, wq, 3, wdims, wstr, wbox, false);
+  if (rc) return rc;
+  RhParams p{};
+  p.N = n; p.H = h; p.W = w; p.chunks = chunks;
+  p.tiles_x = (w + kLcTW - 1) / kLcTW; p.tiles_y = (h + kLcTH - 1) / kLcTH;
+  p.corr_scale = 1.0f / sqrtf((float)c);
+  p.scale = scale; p.shift = shift; p.protos = protos; p.P = P; p.sets = sets; p.cos_scaler = cos_scaler; p.pred = pred;
+  const int tiles = p.tiles_x * p.tiles_y * n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  relation_head_kernel<R><<<grid, kLcThreads, kSmem, stream>>>(t1, t2, tw, p);
+  return check_cuda(cudaGetLastError(), "relation_head launch");
+}
+
+// Dispatch for rpnet_relation_head_f16 (stream_kernels.cu).  Returns 1 if the shape is not eligible.
+int relation_head_tc(const void* f1, const void* f2, const void* wq, const float* scale, const float* shift, const float* protos,
+                     int P, int sets, float cos_scaler, float* pred, int n, int h, int w, int c, int radius, cudaStream_t stream) {
+  if (c % 64 != 0 || P < 1 || P > 8 || (2 * radius + 1) * (2 * radius + 1) > 128) return 1;
+  switch (radius) {
+    case 3: return launch_relation_head<3>(f1, f2, wq, scale, shift, protos, P, sets, cos_scaler, pred, n, h, w, c, stream);
+    case 5: return launch_relation_head<5>(f1, f2, wq, scale, shift, protos, P, sets, cos_scaler, pred, n, h, w, c, stream);
+    default: return 1;
+  }
+}
 
 // =====================================================================================================================
 // Backward of the local correlation on tensor cores.
@@ -359,6 +649,7 @@ local_corr_band_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid
     const int row = q * 32 + lane;
     const int px = row & (kLcTW - 1), py = row >> 3;
     const int et = threadIdx.x - 64;
+    const uint32_t s_a32 = smem_u32(s_a);
     int it = 0, g = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -402,8 +693,7 @@ local_corr_band_kernel(const __grid_constant__ CUtensorMap tm_full, const __grid
           for (int b = 0; b < Cfg::K; ++b) {
             const float v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(raw)[a * Cfg::K + b]) * up;
             const int nn = (py + b) * Cfg::HW + px + a;                    // halo pixel index = K index
-            uint8_t* dst = s_a + (nn >> 6) * 16384 + row * 128 + ((((nn & 63) >> 3) ^ (row & 7)) << 4) + (nn & 7) * 2;
-            *reinterpret_cast<__half*>(dst) = __float2half_rn(v);
+            sts_f16(s_a32 + (nn >> 6) * 16384 + row * 128 + ((((nn & 63) >> 3) ^ (row & 7)) << 4) + (nn & 7) * 2, v);
           }
         }
       }

@@ -572,6 +572,8 @@ RPNET_API int rpnet_premask_f16(const void* x, const float* mask, void* x_fg, vo
 }
 
 namespace rpnet {
+int relation_head_tc(const void* f1, const void* f2, const void* wq, const float* scale, const float* shift, const float* protos,
+                     int P, int sets, float cos_scaler, float* pred, int n, int h, int w, int c, int radius, cudaStream_t stream);
 int local_corr_tc(const void* f1, const void* f2, void* out, int n, int h, int w, int c, int radius, int out_c, cudaStream_t stream);
 }
 
@@ -615,6 +617,21 @@ RPNET_API int rpnet_local_corr_f16(const void* f1, const void* f2, void* out, in
       set_error("local_corr: radius %d not supported (1..5)", radius);
       return RPNET_ERR_ARG;
   }
+}
+
+RPNET_API int rpnet_relation_head_f16(const void* f1, const void* f2, const void* wq_pack, const float* scale, const float* shift,
+                                       const float* protos, int n_protos, int proto_sets, float scaler, float* pred, int n, int h,
+                                       int w, int c, int radius, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(f1 && f2 && wq_pack && scale && shift && protos && pred, "relation_head: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0, "relation_head: bad shape");
+  if (w >= 8 + 2 * radius && h >= 16 + 2 * radius) {
+    const int rc = relation_head_tc(f1, f2, wq_pack, scale, shift, protos, n_protos, proto_sets, scaler, pred, n, h, w, c, radius, stream);
+    if (rc <= 0) return rc;
+  }
+  set_error("relation_head: shape not supported by the fused kernel (c %% 64 == 0, c <= 256, radius 3 or 5, maps >= (8+2r) x (16+2r)): "
+            "run rpnet_local_corr_f16 + rpnet_conv_cos_f16 instead");
+  return RPNET_ERR_ARG;
 }
 
 RPNET_API int rpnet_masked_avg_pool_f32(const float* feat, const float* mask0, const float* mask1, float* out, int n, int h,

@@ -257,24 +257,49 @@ bilinear_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, f
 }
 
 // out[n][k][c] = sum_p feat[n][p][c] * wmap_k[n][p] / (msum_k[n] + 1e-5), k in {0,1}   (getFeatures for fore & back mask)
-__global__ void __launch_bounds__(256)
+// One block of 1024 threads per image: 16 lanes x float4 cover the (<= 64) channels of a pixel, 64 pixels per step, both
+// masks in the same pass over feat; ordered shared-memory tree (deterministic).
+__global__ void __launch_bounds__(1024)
 weighted_pool_kernel(const float* __restrict__ feat, const float* __restrict__ wmap0, const float* __restrict__ wmap1,
                      const float* __restrict__ msum0, const float* __restrict__ msum1, float* __restrict__ out, int hw, int C) {
-  __shared__ float s_red[256];
-  const int n = blockIdx.x, k = blockIdx.y;
-  const float* wm = (k == 0 ? wmap0 : wmap1) + (size_t)n * hw;
-  const float ms = (k == 0 ? msum0 : msum1)[n];
-  const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
-  float acc = 0.f;
-  if (c < C) {
-    const float* f = feat + (size_t)n * hw * C + c;
-    for (int o = part; o < hw; o += 4) acc = fmaf(__ldg(f + (size_t)o * C), __ldg(wm + o), acc);
+  __shared__ float4 s_red[2][1024];
+  const int n = blockIdx.x;
+  const int v = threadIdx.x & 15, part = threadIdx.x >> 4;         // channel quad, pixel lane (64 lanes)
+  const float* w0 = wmap0 + (size_t)n * hw;
+  const float* w1 = wmap1 + (size_t)n * hw;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  if (v * 4 < C) {
+    const float* f = feat + (size_t)n * hw * C + v * 4;
+    for (int o = part; o < hw; o += 64) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(f + (size_t)o * C));
+      const float m0 = __ldg(w0 + o), m1 = __ldg(w1 + o);
+      a0.x = fmaf(x.x, m0, a0.x); a0.y = fmaf(x.y, m0, a0.y); a0.z = fmaf(x.z, m0, a0.z); a0.w = fmaf(x.w, m0, a0.w);
+      a1.x = fmaf(x.x, m1, a1.x); a1.y = fmaf(x.y, m1, a1.y); a1.z = fmaf(x.z, m1, a1.z); a1.w = fmaf(x.w, m1, a1.w);
+    }
   }
-  s_red[threadIdx.x] = acc;
+  s_red[0][threadIdx.x] = a0;
+  s_red[1][threadIdx.x] = a1;
   __syncthreads();
-  if (threadIdx.x < 64 && threadIdx.x < C) {
-    const float t = (s_red[threadIdx.x] + s_red[threadIdx.x + 64]) + (s_red[threadIdx.x + 128] + s_red[threadIdx.x + 192]);
-    out[((size_t)n * 2 + k) * C + threadIdx.x] = t / (ms + 1e-5f);
+  for (int s = 32; s > 0; s >>= 1) {
+    if (part < s) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float4 x = s_red[k][threadIdx.x];
+        const float4 y = s_red[k][threadIdx.x + s * 16];
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        s_red[k][threadIdx.x] = x;
+      }
+    }
+    __syncthreads();
+  }
+  if (part == 0 && v * 4 < C) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float inv = 1.f / ((k == 0 ? msum0 : msum1)[n] + 1e-5f);
+      const float4 x = s_red[k][v];
+      float* o = out + ((size_t)n * 2 + k) * C + v * 4;
+      o[0] = x.x * inv; if (v * 4 + 1 < C) o[1] = x.y * inv; if (v * 4 + 2 < C) o[2] = x.z * inv; if (v * 4 + 3 < C) o[3] = x.w * inv;
+    }
   }
 }
 
@@ -683,8 +708,8 @@ RPNET_API int rpnet_weighted_pool_f32(const float* feat, const float* wmap0, con
                                        float* out, int n, int hw, int c, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(feat && wmap0 && wmap1 && msum0 && msum1 && out, "weighted_pool: null pointer argument");
-  RPNET_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= 64, "weighted_pool: bad shape n=%d hw=%d c=%d (c <= 64)", n, hw, c);
-  weighted_pool_kernel<<<dim3(n, 2), 256, 0, stream>>>(feat, wmap0, wmap1, msum0, msum1, out, hw, c);
+  RPNET_REQUIRE(n > 0 && hw > 0 && c > 0 && c <= 64 && c % 4 == 0, "weighted_pool: bad shape n=%d hw=%d c=%d (c <= 64, c %% 4 == 0)", n, hw, c);
+  weighted_pool_kernel<<<n, 1024, 0, stream>>>(feat, wmap0, wmap1, msum0, msum1, out, hw, c);
   return check_cuda(cudaGetLastError(), "weighted_pool launch");
 }
 

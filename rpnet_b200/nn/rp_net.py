@@ -75,6 +75,10 @@ class ContextCorrelationEncoder(_PackedModule):
         n, h, w, _ = xfg.shape
         fm1, _ = engine.run_conv(pk, xfg, ws, tag + '.fm1')
         fm2, _ = engine.run_conv(pq, xbg, ws, tag + '.fm2')
+        if cos is not None and self.corr_channels == 128 and ops.relation_head_supported(fm1, self.radius):
+            protos, pred, scaler = cos          # correlation + cre.q + calDist in one kernel: only pred is written
+            ops.relation_head(fm1, fm2, pqq.wpack, pqq.scale, pqq.shift, protos, pred, self.radius, scaler)
+            return None
         corr = ws.get(tag + '.corr', (n, h, w, self.corr_channels), torch.float16, xfg.device)
         ops.local_corr(fm1, fm2, self.radius, corr)
         if cos is not None:

@@ -152,6 +152,26 @@ def local_corr(f1, f2, radius, out):
                    'rpnet_local_corr_f16')
 
 
+def relation_head_supported(f1, radius):
+    n, h, w, c = f1.shape
+    return c % 64 == 0 and c <= 256 and radius in (3, 5) and w >= 8 + 2 * radius and h >= 16 + 2 * radius
+
+
+def relation_head(f1, f2, wq_pack, scale, shift, protos, pred, radius, scaler=20.0):
+    """Fused eval tail: corr(f1, f2) -> [corr | f1] -> 1x1 conv + affine + ReLU -> cosine vs protos -> pred fp32 [n, P, h, w]."""
+    lib = _lib.load()
+    _req(f1, torch.float16, 'f1'); _req(f2, torch.float16, 'f2'); _req(wq_pack, torch.float16, 'wq_pack')
+    _req(protos, torch.float32, 'protos'); _req(pred, torch.float32, 'pred')
+    n, h, w, c = f1.shape
+    sets, P = protos.shape[0], protos.shape[1]
+    if tuple(wq_pack.shape) != (1, 64, 128 + c) or tuple(pred.shape) != (n, P, h, w) or f2.shape != f1.shape:
+        raise _lib.RpnetError('relation_head: shapes do not match (wq %s, pred %s)' % (tuple(wq_pack.shape), tuple(pred.shape)))
+    with _Timed('relation_head', float(f1.numel() * 4 + pred.numel() * 4)):
+        rc = lib.rpnet_relation_head_f16(_ptr(f1), _ptr(f2), _ptr(wq_pack), _ptr(scale), _ptr(shift), _ptr(protos), P, sets, float(scaler),
+                                         _ptr(pred), n, h, w, c, radius, _stream())
+    _lib.check(rc, 'rpnet_relation_head_f16')
+
+
 def masked_avg_pool(feat, mask0, mask1, out):
     lib = _lib.load()
     _req(feat, torch.float32, 'feat'); _req(mask0, torch.float32, 'mask0'); _req(mask1, torch.float32, 'mask1')

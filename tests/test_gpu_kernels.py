@@ -336,3 +336,31 @@ def test_conv_cos_fused_epilogue(dev, case):
     torch.cuda.synchronize()
     torch.testing.assert_close(feat.cpu().permute(0, 3, 1, 2), y, rtol=2e-3, atol=2e-3)
     torch.testing.assert_close(pred.cpu(), want, rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize('case', [(2, 256, 64, 64, 2, 2), (3, 128, 37, 29, 3, 1), (1, 64, 26, 18, 5, 1)])
+def test_relation_head_fused(dev, case):
+    """rpnet_relation_head_f16 == Correlation -> cat([corr, fm1]) -> 1x1 conv + affine + ReLU -> calDist (net/rp_net.py:79-84,
+    287-303), incl. ragged tiles and per-image prototype sets."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import ops
+    n, c, h, w, P, sets = case
+    r, k = 5, 121
+    g = _gen(sum(case))
+    f1 = torch.randn(n, c, h, w, generator=g).relu().half().float()
+    f2 = torch.randn(n, c, h, w, generator=g).relu().half().float()
+    wq = (torch.randn(64, k + c, 1, 1, generator=g) / (k + c) ** 0.5).half().float()
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.2
+    protos = torch.randn(sets, P, 64, generator=g)
+    corr = O.correlation_local(f1, f2, r).half().float()                   # the unfused path stores corr as fp16 too
+    y = torch.relu(F.conv2d(torch.cat([corr, f1], 1), wq) * scale[None, :, None, None] + shift[None, :, None, None])
+    want = torch.stack([torch.stack([O.cal_dist(y[i:i + 1], protos[i % sets, p][None])[0] for p in range(P)]) for i in range(n)])
+    wpad = torch.zeros(64, 128 + c)
+    wpad[:, :k] = wq[:, :k, 0, 0]
+    wpad[:, 128:] = wq[:, k:, 0, 0]
+    pred = torch.full((n, P, h, w), 7.0, device=dev)
+    assert ops.relation_head_supported(_nhwc16(f1, dev), r)
+    ops.relation_head(_nhwc16(f1, dev), _nhwc16(f2, dev), wpad.half().reshape(1, 64, 128 + c).contiguous().to(dev), scale.to(dev),
+                      shift.to(dev), protos.to(dev), pred, r, 20.0)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(pred.cpu(), want, rtol=2e-3, atol=3e-2)
