@@ -21,6 +21,8 @@
 // net/rp_net.py:50-69 (the reference trains through torch autograd; it ships no backward code).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace rpnet {
 
 constexpr int kWgPix = 64;                         // pixels (K) per stage
@@ -216,6 +218,160 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Halo-sharing variant for 3x3 (dilation 1) convs with few output channels (cout <= 128: the full-resolution layers,
+// where the generic kernel is operand-feed bound: every tap is its own 8 KB box and dZ is re-read per M tile).
+// Work item = (64-channel input chunk, 64-wide cout tile, pixel split).  Per 8 x 8 pixel tile (K = 64) the stage holds
+//   three x boxes [64 ch x 8 px x 10 rows], one per column offset dx (shifted by TMA, out-of-bounds = zero padding), and
+//   one dZ box [64 cout x 8 x 8];
+// the row offset dy of a tap is a 1024-byte (8-pixel) shift of the MN-major descriptor inside its dx box, so all nine
+// taps are served by 30 KB instead of 72 KB, and all nine share the one dZ box.  M = 9 taps x 64 channels = five 128-row
+// accumulators (taps in (dx, dy) order so that the second 64-row chunk of a descriptor lies at a positive offset; the last
+// accumulator holds tap 8 twice, the duplicate rows are dropped).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWhBoxA = 64 * 2 * 8 * 10;            // 10240 B: one dx box (80 pixel rows of 128 B)
+constexpr int kWhBoxB = 64 * 2 * 64;                // 8192 B
+constexpr int kWhStageBytes = 3 * kWhBoxA + kWhBoxB;  // 38912 B (multiple of 1024)
+constexpr int kWhStages = 5;
+constexpr int kWhSmemBytes = kWhStages * kWhStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
+                       const __grid_constant__ CUtensorMap tm_dz, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kWhStages * kWhStageBytes);
+  uint64_t* empty_bar = full_bar + kWhStages;
+  uint64_t* tfull_bar = empty_bar + kWhStages;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = p.chunks0 + p.chunks1;
+  const int tiles_mn = nch * p.n_ntiles;                // (input chunk, cout tile) pairs
+  const int num_items = tiles_mn * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x0);
+    tma_prefetch_desc(&tm_x1);
+    tma_prefetch_desc(&tm_dz);
+    for (int i = 0; i < kWhStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / tiles_mn;
+        const int rem = item % tiles_mn;
+        const int kc = rem / p.n_ntiles, nt = rem % p.n_ntiles;
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        const CUtensorMap* tmx = kc < p.chunks0 ? &tm_x0 : &tm_x1;
+        const int cx = (kc < p.chunks0 ? kc : kc - p.chunks0) * 64;
+        for (int pt = k0; pt < k1; ++pt) {
+          int t = pt;
+          const int tx = t % p.tiles_x;  t /= p.tiles_x;
+          const int ty = t % p.tiles_y;
+          const int tn = t / p.tiles_y;
+          const int x0 = tx * 8, y0 = ty * 8;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = tiles + stage * kWhStageBytes;
+          mbar_expect_tx(&full_bar[stage], kWhStageBytes);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) tma_load_4d(tmx, &full_bar[stage], a_dst + d * kWhBoxA, cx, x0 + d - 1, y0 - 1, tn);
+          tma_load_4d(&tm_dz, &full_bar[stage], a_dst + 3 * kWhBoxA, nt * 64, x0, y0, tn);
+          if (++stage == kWhStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, 64) | (1u << 15) | (1u << 16) | (1u << 7) | (1u << 10);   // MN-major, bf16
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int split = item / tiles_mn;
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        mbar_wait(tempty_bar, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int pt = k0; pt < k1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * kWhStageBytes);
+          const uint32_t b_addr = a_addr + 3 * kWhBoxA;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                                   // 16 pixels (two image rows of the tile) per MMA
+            const uint64_t b_desc = umma_desc_sw128_mn(b_addr + k * 2048, kWhBoxB, 1024);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              // sorted tap s = dxi * 3 + dyi lives at dxi * kWhBoxA + dyi * 1024 (row offset dy = one 8-pixel group)
+              const int sa = 2 * j, sb = 2 * j + 1 < 9 ? 2 * j + 1 : 2 * j;
+              const uint32_t off_a = (sa / 3) * kWhBoxA + (sa % 3) * 1024, off_b = (sb / 3) * kWhBoxA + (sb % 3) * 1024;
+              const uint64_t a_desc = umma_desc_sw128_mn(a_addr + off_a + k * 2048, off_b - off_a, 1024);
+              umma_f16(tmem_base + j * 64, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kWhStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int cin = nch * 64;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int split = item / tiles_mn;
+      const int rem = item % tiles_mn;
+      const int kc = rem / p.n_ntiles, nt = rem % p.n_ntiles;
+      mbar_wait(tfull_bar, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 5; ++j) {
+        const int s = 2 * j + (row >> 6);                               // sorted tap of this accumulator row
+        const bool valid = s < 9;
+        const int tap = valid ? (s % 3) * 3 + s / 3 : 0;                // natural tap index (dy + 1) * 3 + (dx + 1)
+        float* dst = p.partial + ((size_t)split * p.rows + (size_t)tap * cin + kc * 64 + (row & 63)) * p.cout + nt * 64;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // grad[co][ci_real][tap] (beta * old +) = sum_split partial[split][tap * cin + ci][co].
 // Packed input channels [hole_start, hole_start + hole_len) are padding (skipped); later channels shift down.
 __global__ void __launch_bounds__(256)
@@ -288,6 +444,43 @@ static WgradPlan plan_wgrad(int c0, int c1, int n, int h, int w, int ntaps, int 
   return pl;
 }
 
+// Plan of the halo-sharing variant (8 x 8 pixel tiles, items = (input chunk, 64-wide cout tile, split)).
+static bool halo_eligible(int n, int h, int w, int ntaps, int cout) {
+  return ntaps == 9 && cout <= 128 && h >= 8 && w >= 8 && n > 0;
+}
+static WgradPlan plan_wgrad_halo(int c0, int c1, int n, int h, int w, int cout) {
+  WgradPlan pl{};
+  pl.BN = 64; pl.bw = 8; pl.bh = 8; pl.bn = 1;
+  pl.tiles_x = (w + 7) / 8; pl.tiles_y = (h + 7) / 8; pl.tiles_n = n;
+  pl.ptiles = pl.tiles_x * pl.tiles_y * pl.tiles_n;
+  const int cin = c0 + c1;
+  pl.rows = 9 * cin;
+  pl.n_boxes = 9 * (cin / 64);
+  pl.n_mtiles = cin / 64;
+  pl.n_ntiles = cout / 64;
+  const int tiles_mn = pl.n_mtiles * pl.n_ntiles;
+  const int sms = num_sms();
+  const int max_splits = pl.ptiles / 8 > 0 ? pl.ptiles / 8 : 1;
+  const double stage_cyc = 5 * 4.0 * 32.0 / 0.65;
+  const double partial_cyc = (double)pl.rows * cout * 8.0 / 2100.0 / (tiles_mn > 0 ? tiles_mn : 1) * tiles_mn;
+  int splits = 1;
+  double best = 1e300;
+  for (int sp = 1; sp <= max_splits && sp <= 4096; ++sp) {
+    const long long items = (long long)tiles_mn * sp;
+    const long long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * ((pl.ptiles + sp - 1) / sp) * stage_cyc + sp * partial_cyc;
+    if (cost < best) { best = cost; splits = sp; }
+  }
+  pl.splits = splits;
+  return pl;
+}
+static bool taps_are_3x3(int ntaps, const int* dy, const int* dx) {
+  if (ntaps != 9) return false;
+  for (int t = 0; t < 9; ++t)
+    if (dy[t] != t / 3 - 1 || dx[t] != t % 3 - 1) return false;
+  return true;
+}
+
 }  // namespace rpnet
 
 using namespace rpnet;
@@ -299,7 +492,13 @@ RPNET_API long long rpnet_conv_wgrad_workspace_bytes(int c0, int c1, int n, int 
     return RPNET_ERR_ARG;
   }
   const WgradPlan pl = plan_wgrad(c0, c1, n, h, w, ntaps, cout);
-  return (long long)pl.splits * pl.rows * cout * 4;
+  long long bytes = (long long)pl.splits * pl.rows * cout * 4;
+  if (halo_eligible(n, h, w, ntaps, cout)) {                 // the 3x3 halo-sharing variant may be chosen at call time
+    const WgradPlan ph = plan_wgrad_halo(c0, c1, n, h, w, cout);
+    const long long b2 = (long long)ph.splits * ph.rows * cout * 4;
+    if (b2 > bytes) bytes = b2;
+  }
+  return bytes;
 }
 
 RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
@@ -314,6 +513,54 @@ RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, i
   RPNET_REQUIRE(ntaps >= 1 && ntaps <= kWgMaxTaps, "conv_wgrad: ntaps %d out of range [1, %d]", ntaps, kWgMaxTaps);
   RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_wgrad: cout must be a multiple of 64 (got %d)", cout);
   RPNET_REQUIRE(hole_len >= 0 && hole_start >= 0 && hole_start + hole_len <= c0 + c1, "conv_wgrad: bad padding hole [%d, +%d)", hole_start, hole_len);
+  if (halo_eligible(n, h, w, ntaps, cout) && taps_are_3x3(ntaps, tap_dy, tap_dx) && !getenv("RPNET_WGRAD_NO_HALO")) {
+    const WgradPlan ph = plan_wgrad_halo(c0, c1, n, h, w, cout);
+    const long long need_h = (long long)ph.splits * ph.rows * cout * 4;
+    RPNET_REQUIRE(workspace_bytes >= need_h, "conv_wgrad: workspace too small (%lld < %lld bytes)", workspace_bytes, need_h);
+    WgradParams p{};
+    p.N = n; p.H = h; p.W = w;
+    p.tiles_x = ph.tiles_x; p.tiles_y = ph.tiles_y; p.tiles_n = ph.tiles_n; p.ptiles = ph.ptiles;
+    p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.ntaps = 9;
+    p.n_boxes = ph.n_boxes; p.n_mtiles = ph.n_mtiles; p.n_ntiles = ph.n_ntiles; p.splits = ph.splits;
+    p.rows = ph.rows; p.cout = cout; p.x_bf16 = 1; p.dz_bf16 = 1;
+    p.partial = static_cast<float*>(workspace);
+    CUtensorMap tx0, tx1, tdz;
+    const uint32_t box_a[4] = {64u, 8u, 10u, 1u}, box_b[4] = {64u, 8u, 8u, 1u};
+    {
+      const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
+      int rc = make_tmap_2b(&tx0, x0, 4, dims, str, box_a, true);
+      if (rc) return rc;
+    }
+    if (c1 > 0) {
+      const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
+      int rc = make_tmap_2b(&tx1, x1, 4, dims, str, box_a, true);
+      if (rc) return rc;
+    } else {
+      tx1 = tx0;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)cout, (uint64_t)cout * w, (uint64_t)cout * w * h};
+      int rc = make_tmap_2b(&tdz, dz_bf16, 4, dims, str, box_b, true);
+      if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+      RPNET_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWhSmemBytes));
+      attr_set = true;
+    }
+    const int items = ph.n_mtiles * ph.n_ntiles * ph.splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    conv_wgrad_halo_kernel<<<grid, kWgThreads, kWhSmemBytes, stream>>>(tx0, tx1, tdz, p);
+    RPNET_CUDA_OK(cudaGetLastError());
+    const long long total = (long long)ph.rows * cout;
+    long long g = (total + 255) / 256;
+    if (g > 148LL * 16) g = 148LL * 16;
+    wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.partial, grad, ph.splits, 9, c0 + c1, cout, hole_start, hole_len, accumulate);
+    return check_cuda(cudaGetLastError(), "wgrad_reduce_kernel launch");
+  }
   const WgradPlan pl = plan_wgrad(c0, c1, n, h, w, ntaps, cout);
   const long long need = (long long)pl.splits * pl.rows * cout * 4;
   RPNET_REQUIRE(workspace_bytes >= need, "conv_wgrad: workspace too small (%lld < %lld bytes)", workspace_bytes, need);
