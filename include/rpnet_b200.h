@@ -262,6 +262,22 @@ int rpnet_bilinear_up_f32(const float* in, float* out, int n, int h, int w, int 
 int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* ===================================================================================================
+ * "Next" row N1: batched affine registration in front of the hot path.
+ * =================================================================================================== */
+
+/* AffineRegistration.train_registraion (net/registration.py:316-357) as driven by get_registration_field
+ * (dataset/few_shot_reader.py:109-198) for n slice pairs in one launch: theta = identity, then `iters` times
+ *   warped = F.grid_sample(moving, F.affine_grid(theta, size))   (bilinear, zero padding, align_corners=False)
+ *   loss = mean((warped - fixed)^2); Adam(lr, beta1, beta2, eps).step() on the six parameters.
+ * moving / fixed fp32 [n][h][w]; theta fp32 [n][2][3] (out); loss_curve (optional) fp32 [n][iters]. */
+int rpnet_affine_register_f32(const float* moving, const float* fixed, int n, int h, int w, int iters, float lr, float beta1,
+                              float beta2, float eps, float* theta, float* loss_curve, void* stream);
+
+/* AffineRegistration.forward (net/registration.py:337-344): out[n][c] = grid_sample(x[n][c], affine_grid(theta[n])).
+ * x, out fp32 [n][c][h][w]; theta fp32 [n][2][3]. */
+int rpnet_affine_warp_f32(const float* x, const float* theta, float* out, int n, int c, int h, int w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

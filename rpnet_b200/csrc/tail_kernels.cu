@@ -809,3 +809,139 @@ RPNET_API int rpnet_bilinear_up_f32(const float* in, float* out, int n, int h, i
   bilinear_up_kernel<<<grid_for((long long)n * out_h * out_w, 256), 256, 0, stream>>>(in, out, n, h, w, out_h, out_w);
   return check_cuda(cudaGetLastError(), "bilinear_up launch");
 }
+
+// =====================================================================================================================
+// "Next" row N1: the per-slice affine registration that produces the warped support image / label in front of
+// the hot path — AffineRegistration (net/registration.py:316-357) driven by get_registration_field
+// (dataset/few_shot_reader.py:109-198): theta = identity; 50 x { warped = grid_sample(moving, affine_grid(theta));
+// loss = mean((warped - fixed)^2); loss.backward(); Adam(lr 0.01).step() }, one slice after the other, ~10 launches per
+// iteration.  Here: ONE launch for all slices, one CTA per slice runs every iteration — the bilinear warp, the loss, the
+// analytic gradient of the six parameters (the backward of grid_sample o affine_grid, align_corners = False, zero
+// padding), an ordered block reduction and the Adam update stay inside the kernel.
+// =====================================================================================================================
+namespace rpnet {
+
+constexpr int kRegThreads = 1024;
+
+struct Bilin {
+  float v, dvdx, dvdy;      // sample and its derivative w.r.t. the (unnormalised) source coordinates
+};
+
+// F.grid_sample(bilinear, padding_mode='zeros', align_corners=False) at source pixel coordinates (ix, iy)
+__device__ __forceinline__ Bilin bilinear_zero(const float* __restrict__ img, int H, int W, float ix, float iy) {
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float tx = ix - fx, ty = iy - fy;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x1 >= 0 && x1 < W, yin0 = y0 >= 0 && y0 < H, yin1 = y1 >= 0 && y1 < H;
+  const float v00 = (xin0 && yin0) ? __ldg(img + y0 * W + x0) : 0.f;
+  const float v01 = (xin1 && yin0) ? __ldg(img + y0 * W + x1) : 0.f;
+  const float v10 = (xin0 && yin1) ? __ldg(img + y1 * W + x0) : 0.f;
+  const float v11 = (xin1 && yin1) ? __ldg(img + y1 * W + x1) : 0.f;
+  Bilin r;
+  r.v = (v00 * (1.f - tx) + v01 * tx) * (1.f - ty) + (v10 * (1.f - tx) + v11 * tx) * ty;
+  r.dvdx = (v01 - v00) * (1.f - ty) + (v11 - v10) * ty;
+  r.dvdy = (v10 - v00) * (1.f - tx) + (v11 - v01) * tx;
+  return r;
+}
+
+__global__ void __launch_bounds__(kRegThreads)
+affine_register_kernel(const float* __restrict__ moving, const float* __restrict__ fixed, int H, int W, int iters, float lr,
+                       float beta1, float beta2, float eps, float* __restrict__ theta_out /*[n][6]*/,
+                       float* __restrict__ loss_out /*[n][iters] or null*/) {
+  __shared__ float s_theta[6], s_m[6], s_v[6];
+  __shared__ float s_part[kRegThreads / 32][7];
+  const int n = blockIdx.x;
+  const float* mov = moving + (size_t)n * H * W;
+  const float* fix = fixed + (size_t)n * H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 6) {
+    s_theta[threadIdx.x] = (threadIdx.x == 0 || threadIdx.x == 4) ? 1.f : 0.f;       // identity (net/registration.py:320-322)
+    s_m[threadIdx.x] = 0.f;
+    s_v[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int total = H * W;
+  const float inv_n = 1.f / (float)total;
+  for (int it = 1; it <= iters; ++it) {
+    const float t0 = s_theta[0], t1 = s_theta[1], t2 = s_theta[2], t3 = s_theta[3], t4 = s_theta[4], t5 = s_theta[5];
+    float acc[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+    for (int p = threadIdx.x; p < total; p += kRegThreads) {
+      const int i = p / W, j = p - i * W;
+      const float xn = (2.f * j + 1.f) / (float)W - 1.f, yn = (2.f * i + 1.f) / (float)H - 1.f;   // affine_grid, align_corners=False
+      const float gx = t0 * xn + t1 * yn + t2, gy = t3 * xn + t4 * yn + t5;
+      const float ix = ((gx + 1.f) * (float)W - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
+      const Bilin s = bilinear_zero(mov, H, W, ix, iy);
+      const float r = s.v - __ldg(fix + p);
+      const float g = 2.f * r * inv_n;
+      const float gxg = g * s.dvdx * (0.5f * (float)W), gyg = g * s.dvdy * (0.5f * (float)H);
+      acc[0] = fmaf(gxg, xn, acc[0]); acc[1] = fmaf(gxg, yn, acc[1]); acc[2] += gxg;
+      acc[3] = fmaf(gyg, xn, acc[3]); acc[4] = fmaf(gyg, yn, acc[4]); acc[5] += gyg;
+      acc[6] = fmaf(r, r, acc[6]);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) s_part[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+      float s = 0.f;
+      for (int wv = 0; wv < kRegThreads / 32; ++wv) s += s_part[wv][threadIdx.x];        // fixed order: deterministic
+      if (threadIdx.x == 6) {
+        if (loss_out) loss_out[(size_t)n * iters + it - 1] = s * inv_n;
+      } else {
+        // torch.optim.Adam (no weight decay, no amsgrad)
+        const float m = beta1 * s_m[threadIdx.x] + (1.f - beta1) * s;
+        const float v = beta2 * s_v[threadIdx.x] + (1.f - beta2) * s * s;
+        s_m[threadIdx.x] = m;
+        s_v[threadIdx.x] = v;
+        const float bc1 = 1.f - powf(beta1, (float)it), bc2 = 1.f - powf(beta2, (float)it);
+        const float denom = sqrtf(v) / sqrtf(bc2) + eps;
+        s_theta[threadIdx.x] -= (lr / bc1) * (m / denom);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) theta_out[(size_t)n * 6 + threadIdx.x] = s_theta[threadIdx.x];
+}
+
+// out[n][c][i][j] = grid_sample(x[n][c], affine_grid(theta[n]))  (bilinear, zeros, align_corners=False): AffineRegistration.forward
+__global__ void affine_warp_kernel(const float* __restrict__ x, const float* __restrict__ theta, float* __restrict__ out, int N, int C,
+                                   int H, int W) {
+  const long long total = (long long)N * C * H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % W), i = (int)((idx / W) % H);
+    const long long nc = idx / ((long long)W * H);
+    const int n = (int)(nc / C);
+    const float* th = theta + (size_t)n * 6;
+    const float xn = (2.f * j + 1.f) / (float)W - 1.f, yn = (2.f * i + 1.f) / (float)H - 1.f;
+    const float gx = th[0] * xn + th[1] * yn + th[2], gy = th[3] * xn + th[4] * yn + th[5];
+    const float ix = ((gx + 1.f) * (float)W - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
+    out[idx] = bilinear_zero(x + nc * H * W, H, W, ix, iy).v;
+  }
+}
+
+}  // namespace rpnet
+
+RPNET_API int rpnet_affine_register_f32(const float* moving, const float* fixed, int n, int h, int w, int iters, float lr, float beta1,
+                                         float beta2, float eps, float* theta, float* loss_curve, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(moving && fixed && theta, "affine_register: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && iters >= 0 && (long long)h * w < (1LL << 30), "affine_register: bad shape");
+  rpnet::affine_register_kernel<<<n, rpnet::kRegThreads, 0, stream>>>(moving, fixed, h, w, iters, lr, beta1, beta2, eps, theta, loss_curve);
+  return check_cuda(cudaGetLastError(), "affine_register launch");
+}
+
+RPNET_API int rpnet_affine_warp_f32(const float* x, const float* theta, float* out, int n, int c, int h, int w, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(x && theta && out, "affine_warp: null pointer argument");
+  RPNET_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "affine_warp: bad shape");
+  rpnet::affine_warp_kernel<<<grid_for((long long)n * c * h * w, 256), 256, 0, stream>>>(x, theta, out, n, c, h, w);
+  return check_cuda(cudaGetLastError(), "affine_warp launch");
+}

@@ -577,3 +577,30 @@ def adam(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-
         _lib.check(lib.rpnet_adam_f32(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr), float(betas[0]),
                                       float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), _stream()),
                    'rpnet_adam_f32')
+
+
+# =====================================================================================================
+# "next" row N1: batched affine registration (include/rpnet_b200.h, last section)
+# =====================================================================================================
+def affine_register(moving, fixed, theta, iters=50, lr=0.01, betas=(0.9, 0.999), eps=1e-8, loss_curve=None):
+    """moving / fixed fp32 [n, h, w]; theta fp32 [n, 2, 3] (out); loss_curve fp32 [n, iters] (optional)."""
+    lib = _lib.load()
+    _req(moving, torch.float32, 'moving'); _req(fixed, torch.float32, 'fixed'); _req(theta, torch.float32, 'theta')
+    n, h, w = moving.shape
+    assert fixed.shape == moving.shape and tuple(theta.shape) == (n, 2, 3)
+    if loss_curve is not None:
+        _req(loss_curve, torch.float32, 'loss_curve')
+        assert tuple(loss_curve.shape) == (n, iters)
+    with _Timed('affine_register', float(moving.numel() * 8 * iters)):
+        _lib.check(lib.rpnet_affine_register_f32(_ptr(moving), _ptr(fixed), n, h, w, int(iters), float(lr), float(betas[0]), float(betas[1]),
+                                                 float(eps), _ptr(theta), _ptr(loss_curve), _stream()), 'rpnet_affine_register_f32')
+
+
+def affine_warp(x, theta, out):
+    """x, out fp32 [n, c, h, w]; theta fp32 [n, 2, 3]: F.grid_sample(x, F.affine_grid(theta, x.size()))."""
+    lib = _lib.load()
+    _req(x, torch.float32, 'x'); _req(theta, torch.float32, 'theta'); _req(out, torch.float32, 'out')
+    n, c, h, w = x.shape
+    assert out.shape == x.shape and tuple(theta.shape) == (n, 2, 3)
+    with _Timed('affine_warp', float(x.numel() * 8)):
+        _lib.check(lib.rpnet_affine_warp_f32(_ptr(x), _ptr(theta), _ptr(out), n, c, h, w, _stream()), 'rpnet_affine_warp_f32')

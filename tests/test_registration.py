@@ -1,0 +1,70 @@
+"""Affine registration in front of the hot path ("next" row N1).
+CPU: the oracle restatement against golden vectors recorded from the reference's AffineRegistration
+(tests/golden/registration.npz).  GPU: the one-launch batched kernel against the same golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+
+def _inputs(g):
+    from rpnet_b200.synthetic import _slice
+    S, size = int(g['S']), int(g['size'])
+    src = torch.stack([_slice(int(g['src_seed']) + s, size, 1)[0] for s in range(S)])
+    lab = torch.stack([(_slice(int(g['src_seed']) + s, size, 1)[1] > 0).float() for s in range(S)])
+    return src, lab, torch.from_numpy(g['dst'])
+
+
+def test_oracle_affine_registration_vs_reference_golden(golden):
+    from oracle import registration_oracle as R
+    g = golden('registration')
+    src, lab, dst = _inputs(g)
+    for s in range(int(g['S'])):
+        theta, curve = R.affine_register(((src[s] + 1) / 2)[None, None], ((dst[s] + 1) / 2)[None, None], int(g['iters']))
+        np.testing.assert_allclose(theta[0].numpy(), g['theta'][s], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(np.array(curve), g['loss'][s], rtol=1e-5, atol=1e-9)
+    th, wl, ws = R.get_affine_registration(dst[:, None], [[src[:, None]]], [[lab]], int(g['iters']))
+    n = wl.numel()
+    assert np.array_equal(np.packbits(wl[:, 0].numpy().astype(np.uint8)), g['warped_label'])
+    np.testing.assert_allclose(ws[:, ::2, ::2].numpy(), g['warped_src'], atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_affine_registration_kernel_vs_reference_golden(golden):
+    """One launch registers all slices (one CTA per slice, every Adam iteration inside the kernel).  The optimisation is
+    smooth (6 parameters, MSE): the only difference to the reference is the summation order of the gradient (1e-6 relative),
+    which Adam's normalised steps keep small: theta within 2e-3 after 50 iterations, loss curve within 1e-3 relative."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import registration as RG
+    g = golden('registration')
+    src, lab, dst = _inputs(g)
+    dev = torch.device('cuda:0')
+    iters = int(g['iters'])
+    theta, curve = RG.affine_register(((src + 1) / 2).to(dev), ((dst + 1) / 2).to(dev), iters=iters, return_loss=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(curve.cpu().numpy()[:, 0], g['loss'][:, 0], rtol=1e-5)          # identity warp: same loss
+    np.testing.assert_allclose(curve.cpu().numpy(), g['loss'], rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(theta.cpu().numpy(), g['theta'], rtol=0, atol=2e-3)
+    th, wl, ws = RG.get_affine_registration(dst[:, None].to(dev), [[src[:, None].to(dev)]], [[lab.to(dev)]], iters)
+    ref_wl = np.unpackbits(g['warped_label'])[:wl.numel()].reshape(wl[:, 0].shape)
+    assert (wl[:, 0].cpu().numpy().astype(np.uint8) != ref_wl).mean() < 2e-3                      # label edge pixels only
+    np.testing.assert_allclose(ws.cpu().numpy()[:, ::2, ::2], g['warped_src'], atol=2e-2)
+    # the warp kernel alone, with the reference's theta: exact up to fp32 rounding
+    tref = torch.from_numpy(g['theta']).to(dev)
+    w2 = RG.affine_warp(((src + 1) / 2)[:, None].to(dev), tref)[:, 0] * 2 - 1
+    np.testing.assert_allclose(w2.cpu().numpy()[:, ::2, ::2], g['warped_src'], atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_affine_registration_batched_equals_per_slice():
+    """Slices are independent: registering a batch == registering each slice on its own (bit for bit), any image size."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import registration as RG
+    gen = torch.Generator().manual_seed(3)
+    mov = torch.rand(5, 48, 80, generator=gen).cuda()
+    fix = torch.roll(mov, shifts=(2, -3), dims=(1, 2)) * 0.9 + 0.05
+    th = RG.affine_register(mov, fix, iters=20)
+    for s in range(5):
+        assert torch.equal(RG.affine_register(mov[s:s + 1], fix[s:s + 1], iters=20)[0], th[s])
+    assert th.shape == (5, 2, 3) and torch.isfinite(th).all()
