@@ -278,6 +278,10 @@ int rpnet_affine_register_f32(const float* moving, const float* fixed, int n, in
  * x, out fp32 [n][c][h][w]; theta fp32 [n][2][3]. */
 int rpnet_affine_warp_f32(const float* x, const float* theta, float* out, int n, int c, int h, int w, void* stream);
 
+/* NCC (net/registration.py:157-160; printed by the eval driver, test_rpnet.py:229-230) of two fp32 arrays of n elements:
+ * -cov(f, m) / sqrt(var(f) * var(m) * n^2 ... + 1e-10) exactly as the reference's sums; scratch5: 5 doubles; out: 1 float. */
+int rpnet_ncc_f32(const float* moving, const float* fixed, long long n, double* scratch5, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -945,3 +945,50 @@ RPNET_API int rpnet_affine_warp_f32(const float* x, const float* theta, float* o
   rpnet::affine_warp_kernel<<<grid_for((long long)n * c * h * w, 256), 256, 0, stream>>>(x, theta, out, n, c, h, w);
   return check_cuda(cudaGetLastError(), "affine_warp launch");
 }
+
+// ---------------------------------------------------------------------------------------------------
+// NCC (net/registration.py:157-160), the similarity the eval driver prints next to Dice (test_rpnet.py:229-230):
+//   -sum((f - mean f) * (m - mean m)) / sqrt(sum((f - mean f)^2) * sum((m - mean m)^2) + 1e-10)
+// one pass: the five raw moments in fp64 (per-thread fp32 partials over a few elements, fp64 across threads / blocks).
+// ---------------------------------------------------------------------------------------------------
+namespace rpnet {
+__global__ void __launch_bounds__(256)
+ncc_moments_kernel(const float* __restrict__ m, const float* __restrict__ f, long long n, double* __restrict__ sums /*[5]*/) {
+  __shared__ double s_red[8][5];
+  double acc[5] = {0, 0, 0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double a = (double)__ldg(m + i), b = (double)__ldg(f + i);
+    acc[0] += a; acc[1] += b; acc[2] += a * a; acc[3] += b * b; acc[4] += a * b;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0;
+    for (int wv = 0; wv < 8; ++wv) s += s_red[wv][threadIdx.x];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+__global__ void ncc_finalize_kernel(const double* __restrict__ sums, long long n, float* __restrict__ out) {
+  const double N = (double)n, sm = sums[0], sf = sums[1];
+  const double cov = sums[4] - sm * sf / N, vm = sums[2] - sm * sm / N, vf = sums[3] - sf * sf / N;
+  *out = (float)(-cov / sqrt(vf * vm + 1e-10));
+}
+}  // namespace rpnet
+
+RPNET_API int rpnet_ncc_f32(const float* moving, const float* fixed, long long n, double* scratch5, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(moving && fixed && scratch5 && out && n > 0, "ncc: bad argument");
+  RPNET_CUDA_OK(cudaMemsetAsync(scratch5, 0, 5 * sizeof(double), stream));
+  rpnet::ncc_moments_kernel<<<grid_for(n, 256 * 8, 4), 256, 0, stream>>>(moving, fixed, n, scratch5);
+  RPNET_CUDA_OK(cudaGetLastError());
+  rpnet::ncc_finalize_kernel<<<1, 1, 0, stream>>>(scratch5, n, out);
+  return check_cuda(cudaGetLastError(), "ncc launch");
+}

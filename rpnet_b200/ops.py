@@ -604,3 +604,15 @@ def affine_warp(x, theta, out):
     assert out.shape == x.shape and tuple(theta.shape) == (n, 2, 3)
     with _Timed('affine_warp', float(x.numel() * 8)):
         _lib.check(lib.rpnet_affine_warp_f32(_ptr(x), _ptr(theta), _ptr(out), n, c, h, w, _stream()), 'rpnet_affine_warp_f32')
+
+
+def ncc(moving, fixed):
+    """NCC(moving, fixed) of net/registration.py:157-160 as a device scalar tensor [1]."""
+    lib = _lib.load()
+    _req(moving, torch.float32, 'moving'); _req(fixed, torch.float32, 'fixed')
+    assert moving.numel() == fixed.numel()
+    scratch = torch.empty(5, dtype=torch.float64, device=moving.device)
+    out = torch.empty(1, dtype=torch.float32, device=moving.device)
+    with _Timed('ncc', float(moving.numel() * 8), n=2):
+        _lib.check(lib.rpnet_ncc_f32(_ptr(moving), _ptr(fixed), moving.numel(), _ptr(scratch), _ptr(out), _stream()), 'rpnet_ncc_f32')
+    return out

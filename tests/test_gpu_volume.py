@@ -72,3 +72,36 @@ def test_volume_inference_vs_oracle_and_sharding(dev):
     parts = [V.segment_volume(net, *args, batch_size=4, rank=r, world=3) for r in range(3)]
     assert [p['range'] for p in parts] == [(0, 4), (4, 7), (7, 10)]
     assert torch.equal(torch.cat([p['mask'] for p in parts]), full['mask'])
+
+
+def test_eval_driver_lines_and_metrics(dev):
+    """rpnet_b200.evaluate.eval_volumes (the loop of test_rpnet.py:151-258): Dice / NCC values against numpy restatements of
+    utils/util.py:379-390 and net/registration.py:157-160, and the reference's printed line format."""
+    from net.model import model_factory
+    from oracle import weights
+    from rpnet_b200 import evaluate, registration
+    from rpnet_b200 import volume as V
+    from rpnet_b200.synthetic import perturb_bn_stats
+    T, S, size = 2, 6, 64
+    sd = perturb_bn_stats(weights.unet_rpnet_state_dict(0))
+    net = model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=_cfg(T))
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    raw = V.make_synthetic_volume(S, size, 1, 1, seed=2)
+    q = raw['query_images'].to(dev)
+    theta, wl, ws = registration.get_affine_registration(q, [[raw['support_images'][0][0].to(dev)]], [[raw['support_fg'][0][0].to(dev)]], iters=10)
+    item = {'support_images': [[ws[:, None]]], 'support_labels': [[wl[:, 0]]], 'query_images': q, 'query_labels': raw['query_labels'],
+            'appr_query_labels': (wl[:, 0] > 0.5).float(), 'warped_supp': ws, 'class_id': 0, 'pid': 'p0', 'supp_pid': 's0'}
+    lines = []
+    aff, few, ref = evaluate.eval_volumes(net, [item], ['Liver'], batch_size=4, out=lines.append)
+    assert len(lines) == 2 and lines[0].startswith('0 p0 s0 affine (') and ' fewshot ' in lines[0] and 'ref 1 ' in lines[0]
+    assert lines[1].startswith('Liver, affine ')
+    tgt = (raw['query_labels'] > 0).numpy()
+    assert aff['Liver'][0] == _dice_ref(tgt, (item['appr_query_labels'] > 0).cpu().numpy())
+    res = V.segment_volume(net, item['support_images'], item['support_labels'], [[1 - wl[:, 0]]], q, item['appr_query_labels'], batch_size=4)
+    assert few['Liver'][0] == _dice_ref(tgt, res['mask'].cpu().numpy()) and ref['Liver'][T - 1][0] == few['Liver'][0]
+    # NCC against the reference formula in float64
+    f, m = q.cpu().double().numpy(), ws.cpu().double().numpy().reshape(q.shape)
+    want = -((f - f.mean()) * (m - m.mean())).sum() / np.sqrt(((f - f.mean()) ** 2).sum() * ((m - m.mean()) ** 2).sum() + 1e-10)
+    got = float(lines[0].split('affine (')[1].split(',')[0])
+    assert abs(got - want) < 1e-5
