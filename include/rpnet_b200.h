@@ -151,6 +151,26 @@ int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16,
                      int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
                      int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream);
 
+/* up_conv (nn.Upsample(x2, nearest) + 3x3 conv, net/modules.py:61-75) in sub-pixel form, train mode: output parity phase
+ * (py, px) of z is a 2x2-tap conv of the LOW-resolution input with row/column-summed weights (2.25x fewer MACs, and the
+ * up-sampled map is never materialised).
+ *   rpnet_pack_upconv_weight: w fp32 [cout][cin][3][3] -> wf fp16 [4 phases][4 taps][cout][cin] (forward) and
+ *                             w16 bf16 [16][cin][cout] (data gradient as a 4x4 stride-2 conv of dZ).
+ *   rpnet_upconv_phase_bnstats_f16: one phase of z [n][2h][2w][cout] from x_low [n][h][w][cin] with wphase = wf[py*2+px];
+ *                             BatchNorm statistics of z accumulate over the four launches (keep_sums = 0 on the first).
+ *                             -2 when the statistics cannot be fused for the shape (maps smaller than a pixel tile).
+ *   rpnet_upconv_dgrad_bf16:  dx_low [n][h][w][out_c] (channels [out_coff, +cin)) from dz bf16 [n][2h][2w][cout].
+ *   rpnet_upconv_wgrad:       grad [cout][cin][3][3] (=|+=) from x_low bf16 [n][h][w][cin] and dz bf16 [n][2h][2w][cout]. */
+int rpnet_pack_upconv_weight(const float* w, int cout, int cin, void* wf_f16, void* w16_bf16, void* stream);
+int rpnet_upconv_phase_bnstats_f16(const void* x_low, int cin, int n, int h, int w, const void* wphase, int py, int px, int cout,
+                                   const float* ones, const float* zeros, void* z_f16, const int* group_start, int groups,
+                                   double* sums, int keep_sums, void* stream);
+int rpnet_upconv_dgrad_bf16(const void* dz, int cout, int n, int h, int w, const void* w16, int cin, void* out, int out_c,
+                            int out_coff, const float* ones, const float* zeros, void* stream);
+long long rpnet_upconv_wgrad_workspace_bytes(int cin, int n, int h, int w, int cout);
+int rpnet_upconv_wgrad(const void* x_low_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
+                       int accumulate, void* workspace, long long workspace_bytes, void* stream);
+
 /* Weight gradient of the Cin = 1 first conv: grad[64][1][3][3] += sum dz * img.  net/unet.py:405 (encoder.Conv1.conv.0). */
 int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream);
 

@@ -24,7 +24,7 @@ namespace rpnet {
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
 constexpr int kBK = 64;           // fp16 channels per k-block = one 128-byte swizzle row
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 16;         // 3x3 tap lists, and the 4x4 stride-2 form of the up-conv data gradient (16 taps over 4 sources)
 constexpr int kNumThreads = 192;
 constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBnGroups = 64;
@@ -39,6 +39,7 @@ struct ConvParams {
   int chunks0, chunks1;           // 64-channel chunks of source 0 / source 1 (channel concat)
   int ntaps;
   int dy[kMaxTaps], dx[kMaxTaps];
+  int tap_src[kMaxTaps];          // -1: channel concat of source 0 | source 1 (default); 0..3: the tap reads that source only
   const float* scale;             // per-cout epilogue: y = acc * scale + shift
   const float* shift;
   int relu;
@@ -79,6 +80,7 @@ struct ConvCfg {
 template <int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
+                  const __grid_constant__ CUtensorMap tm_src2, const __grid_constant__ CUtensorMap tm_src3,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using Cfg = ConvCfg<BN>;
   constexpr int kStages = Cfg::kStages;
@@ -106,6 +108,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_src0);
     tma_prefetch_desc(&tm_src1);
+    tma_prefetch_desc(&tm_src2);
+    tma_prefetch_desc(&tm_src3);
     tma_prefetch_desc(&tm_w);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -142,8 +146,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
             uint8_t* b_dst = a_dst + Cfg::kABytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            if (kc < p.chunks0) tma_load_4d(&tm_src0, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
-            else                tma_load_4d(&tm_src1, &full_bar[stage], a_dst, (kc - p.chunks0) * kBK, xs, ys, n0);
+            const int ts = p.tap_src[tap];
+            if (ts < 0) {
+              if (kc < p.chunks0) tma_load_4d(&tm_src0, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
+              else                tma_load_4d(&tm_src1, &full_bar[stage], a_dst, (kc - p.chunks0) * kBK, xs, ys, n0);
+            } else {
+              const CUtensorMap* tm = ts == 0 ? &tm_src0 : (ts == 1 ? &tm_src1 : (ts == 2 ? &tm_src2 : &tm_src3));
+              tma_load_4d(tm, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
+            }
             tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -404,8 +414,8 @@ int num_sms() {
 }
 
 template <int BN>
-static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& tw, const ConvParams& p,
-                  cudaStream_t stream) {
+static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
+                  const ConvParams& p, cudaStream_t stream) {
   using Cfg = ConvCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -414,7 +424,7 @@ static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMa
   }
   const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_c;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, tw, p);
+  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
   return check_cuda(cudaGetLastError(), "conv_igemm_kernel launch");
 }
 
@@ -431,7 +441,8 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
                            int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                            void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
                            int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr, const float* cos_protos = nullptr,
-                           int cos_P = 0, int cos_sets = 0, float cos_scaler = 0.f, float* cos_pred = nullptr) {
+                           int cos_P = 0, int cos_sets = 0, float cos_scaler = 0.f, float* cos_pred = nullptr, int bn_keep_sums = 0,
+                           const void* const* view_ptr = nullptr, const long long* view_strides = nullptr, const int* tap_src = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -454,7 +465,11 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   p.n_tiles_c = cout / BN;
   p.chunks0 = c0 / kBK; p.chunks1 = c1 / kBK;
   p.ntaps = ntaps;
-  for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; }
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; p.tap_src[i] = tap_src ? tap_src[i] : -1; }
+  if (tap_src) {
+    RPNET_REQUIRE(view_ptr && view_strides && c1 == 0, "conv_igemm: per-tap sources need the four views and no channel concat");
+    for (int i = 0; i < ntaps; ++i) RPNET_REQUIRE(tap_src[i] >= 0 && tap_src[i] < 4, "conv_igemm: tap source %d out of range", tap_src[i]);
+  }
   p.scale = scale; p.shift = shift; p.relu = relu;
   p.in_bf16 = bf16 ? 1 : 0; p.out_bf16 = bf16 ? 1 : 0;
   p.out = static_cast<__half*>(out_f16);
@@ -479,7 +494,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     if (ok) {
       p.bn_sums = bn_sums; p.bn_groups = bn_groups;
       for (int g = 0; g <= bn_groups; ++g) p.bn_start[g] = bn_group_start[g];
-      RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(double), stream));
+      if (!bn_keep_sums) RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(double), stream));
       if (bn_fused) *bn_fused = 1;
     }
   }
@@ -489,21 +504,34 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
                   "conv_igemm: output mapping exceeds the %d x %d output", out_h, out_w);
   }
 
-  CUtensorMap t0, t1, tw;
+  CUtensorMap t0, t1, t2, t3, tw;
   const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-  {
+  if (tap_src) {
+    // four strided views of one tensor (the parity phases of a 2x up-sampled map): same dims, custom pixel strides
+    CUtensorMap* tv[4] = {&t0, &t1, &t2, &t3};
     const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
-    int rc = make_tmap_2b(&t0, src0, 4, dims, str, abox, bf16);
-    if (rc) return rc;
-  }
-  if (c1 > 0) {
-    const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
-    int rc = make_tmap_2b(&t1, src1, 4, dims, str, abox, bf16);
-    if (rc) return rc;
+    const uint64_t str[3] = {(uint64_t)view_strides[0], (uint64_t)view_strides[1], (uint64_t)view_strides[2]};
+    for (int v = 0; v < 4; ++v) {
+      int rc = make_tmap_2b(tv[v], view_ptr[v], 4, dims, str, abox, bf16);
+      if (rc) return rc;
+    }
   } else {
-    t1 = t0;
+    {
+      const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
+      int rc = make_tmap_2b(&t0, src0, 4, dims, str, abox, bf16);
+      if (rc) return rc;
+    }
+    if (c1 > 0) {
+      const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
+      int rc = make_tmap_2b(&t1, src1, 4, dims, str, abox, bf16);
+      if (rc) return rc;
+    } else {
+      t1 = t0;
+    }
+    t2 = t0;
+    t3 = t0;
   }
   {
     const uint64_t cin = (uint64_t)(c0 + c1);
@@ -514,9 +542,9 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     if (rc) return rc;
   }
   switch (BN) {
-    case 256: return launch<256>(t0, t1, tw, p, stream);
-    case 128: return launch<128>(t0, t1, tw, p, stream);
-    default:  return launch<64>(t0, t1, tw, p, stream);
+    case 256: return launch<256>(t0, t1, t2, t3, tw, p, stream);
+    case 128: return launch<128>(t0, t1, t2, t3, tw, p, stream);
+    default:  return launch<64>(t0, t1, t2, t3, tw, p, stream);
   }
 }
 
@@ -561,4 +589,54 @@ RPNET_API int rpnet_conv_cos_f16(const void* src0, int c0, const void* src1, int
   RPNET_REQUIRE(protos && pred, "conv_cos: null pointer argument");
   return conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, 64, scale, shift, relu, nullptr, h, w, 64, 0, 1,
                          0, 1, 0, nullptr, out_f32, stream_, nullptr, 0, nullptr, nullptr, protos, n_protos, proto_sets, scaler, pred);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// up_conv in sub-pixel form (see conv_wgrad.cu for the tap tables), train mode.
+// ---------------------------------------------------------------------------------------------------
+// One output parity phase of z = conv3x3(upsample2x(x)): a 2x2-tap conv of the low-resolution x [n][h][w][cin] whose pixels
+// land at (2y + py, 2x + px) of z [n][2h][2w][cout]; the BatchNorm statistics of z accumulate over the four phase launches
+// (keep_sums = 0 on the first).  Returns -2 when the statistics cannot be fused for this shape (callers then materialise the
+// up-sampled map and run rpnet_conv_bnstats_f16).
+RPNET_API int rpnet_upconv_phase_bnstats_f16(const void* x_low, int cin, int n, int h, int w, const void* wphase /*[4][cout][cin]*/,
+                                              int py, int px, int cout, const float* ones, const float* zeros, void* z_f16,
+                                              const int* group_start, int groups, double* sums, int keep_sums, void* stream_) {
+  RPNET_REQUIRE(x_low && wphase && z_f16 && sums && group_start && (py | 1) == 1 && (px | 1) == 1, "upconv_phase: bad argument");
+  int dy[4], dx[4];
+  for (int t = 0; t < 4; ++t) {
+    dy[t] = (py == 0 ? -1 : 0) + (t >> 1);
+    dx[t] = (px == 0 ? -1 : 0) + (t & 1);
+  }
+  int fused = 0;
+  int rc = conv_igemm_impl(false, x_low, cin, nullptr, 0, n, h, w, wphase, 4, dy, dx, cout, ones, zeros, 0, z_f16, 2 * h, 2 * w, cout, 0, 2,
+                           py, 2, px, nullptr, nullptr, stream_, group_start, groups, sums, &fused, nullptr, 0, 0, 0.f, nullptr, keep_sums);
+  if (rc) return rc;
+  if (!fused) {
+    set_error("upconv_phase: BatchNorm statistics cannot be fused for %d x %d maps (tile straddles call groups)", h, w);
+    return RPNET_ERR_ARG;
+  }
+  return 0;
+}
+
+// Data gradient of the same op w.r.t. the LOW-resolution input: a 4x4 stride-2 conv of dZ [n][2h][2w][cout] (bf16),
+//   dx[y, x, ci] = sum_{oy, ox in -1..2} sum_co dZ[2y + oy, 2x + ox, co] * W4[oy][ox][ci][co],   W4 = row/column sums of w,
+// run as 16 taps over the four parity views of dZ (custom-stride tensor maps; out-of-bounds = zero).
+// w16: bf16 [16][cin][cout] with tap index (oy + 1) * 4 + (ox + 1).  out: bf16 [n][h][w][out_c], channels [out_coff, +cin).
+RPNET_API int rpnet_upconv_dgrad_bf16(const void* dz, int cout, int n, int h, int w, const void* w16, int cin, void* out, int out_c,
+                                       int out_coff, const float* ones, const float* zeros, void* stream_) {
+  RPNET_REQUIRE(dz && w16 && out, "upconv_dgrad: null pointer argument");
+  int dy[16], dx[16], src[16];
+  for (int t = 0; t < 16; ++t) {
+    const int oy = t / 4 - 1, ox = t % 4 - 1;
+    const int py = oy & 1, px = ox & 1;
+    dy[t] = (oy - py) / 2;
+    dx[t] = (ox - px) / 2;
+    src[t] = py * 2 + px;
+  }
+  const void* views[4];
+  for (int v = 0; v < 4; ++v)
+    views[v] = static_cast<const __nv_bfloat16*>(dz) + ((size_t)(v >> 1) * (2 * w) + (v & 1)) * cout;
+  const long long strides[3] = {2LL * cout, 2LL * (2 * w) * cout, (long long)(2 * h) * (2 * w) * cout};
+  return conv_igemm_impl(true, views[0], cout, nullptr, 0, n, h, w, w16, 16, dy, dx, cin, ones, zeros, 0, out, h, w, out_c, out_coff, 1, 0, 1,
+                         0, nullptr, nullptr, stream_, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, views, strides, src);
 }

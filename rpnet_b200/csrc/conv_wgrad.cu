@@ -501,9 +501,11 @@ RPNET_API long long rpnet_conv_wgrad_workspace_bytes(int c0, int c1, int n, int 
   return bytes;
 }
 
-RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
-                               int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
-                               int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
+// dz_strides (optional): pixel strides {x, y, image} in elements of a strided view of the gradient tensor (the parity phases
+// of a 2x up-sampled map); null = dense [n][h][w][cout].
+static int wgrad_impl(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, const long long* dz_strides,
+                      int n, int h, int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
+                      int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(x0 && dz_bf16 && grad && workspace, "conv_wgrad: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0, "conv_wgrad: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -513,7 +515,7 @@ RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, i
   RPNET_REQUIRE(ntaps >= 1 && ntaps <= kWgMaxTaps, "conv_wgrad: ntaps %d out of range [1, %d]", ntaps, kWgMaxTaps);
   RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_wgrad: cout must be a multiple of 64 (got %d)", cout);
   RPNET_REQUIRE(hole_len >= 0 && hole_start >= 0 && hole_start + hole_len <= c0 + c1, "conv_wgrad: bad padding hole [%d, +%d)", hole_start, hole_len);
-  if (halo_eligible(n, h, w, ntaps, cout) && taps_are_3x3(ntaps, tap_dy, tap_dx) && !getenv("RPNET_WGRAD_NO_HALO")) {
+  if (!dz_strides && halo_eligible(n, h, w, ntaps, cout) && taps_are_3x3(ntaps, tap_dy, tap_dx) && !getenv("RPNET_WGRAD_NO_HALO")) {
     const WgradPlan ph = plan_wgrad_halo(c0, c1, n, h, w, cout);
     const long long need_h = (long long)ph.splits * ph.rows * cout * 4;
     RPNET_REQUIRE(workspace_bytes >= need_h, "conv_wgrad: workspace too small (%lld < %lld bytes)", workspace_bytes, need_h);
@@ -595,7 +597,8 @@ RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, i
   }
   {
     const uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t str[3] = {(uint64_t)cout, (uint64_t)cout * w, (uint64_t)cout * w * h};
+    uint64_t str[3] = {(uint64_t)cout, (uint64_t)cout * w, (uint64_t)cout * w * h};
+    if (dz_strides) { str[0] = (uint64_t)dz_strides[0]; str[1] = (uint64_t)dz_strides[1]; str[2] = (uint64_t)dz_strides[2]; }
     int rc = make_tmap_2b(&tdz, dz_bf16, 4, dims, str, box, true);
     if (rc) return rc;
   }
@@ -614,4 +617,73 @@ RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, i
   wgrad_reduce_kernel<<<(int)g, 256, 0, stream>>>(p.partial, grad, pl.splits, ntaps, c0 + c1, cout, hole_start, hole_len,
                                                    accumulate);
   return check_cuda(cudaGetLastError(), "wgrad_reduce_kernel launch");
+}
+
+RPNET_API int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
+                               int w, int ntaps, const int* tap_dy, const int* tap_dx, int cout, float* grad, int hole_start,
+                               int hole_len, int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
+  return wgrad_impl(x0, c0, x1, c1, x_bf16, dz_bf16, nullptr, n, h, w, ntaps, tap_dy, tap_dx, cout, grad, hole_start, hole_len, accumulate,
+                    workspace, workspace_bytes, stream_);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// up_conv (nn.Upsample(x2, nearest) + 3x3 conv, net/modules.py:61-75) in sub-pixel form: output parity phase (py, px) is a
+// 2x2 conv of the LOW-resolution input with row/column-summed weights (2.25x fewer MACs than the materialised form).
+//   rows(py = 0): tap 0 = offset -1 <- ky {0},   tap 1 = offset 0 <- ky {1, 2}
+//   rows(py = 1): tap 0 = offset  0 <- ky {0, 1}, tap 1 = offset +1 <- ky {2}          (same for columns)
+// Weight gradient: four 4-tap weight-gradient GEMMs (x = the low-resolution input, dZ = the phase's strided view of the
+// high-resolution gradient), then dW[ky][kx] = sum over the four phases of the phase tap that contains (ky, kx).
+// ---------------------------------------------------------------------------------------------------
+namespace rpnet {
+__device__ __host__ inline int upconv_tap_of(int parity, int k) {      // which of the phase's two taps holds kernel row/col k
+  return parity == 0 ? (k == 0 ? 0 : 1) : (k == 2 ? 1 : 0);
+}
+__global__ void upconv_wgrad_combine_kernel(const float* __restrict__ dwp /*[4 phases][cout][cin][4 taps]*/, float* __restrict__ grad,
+                                            long long cc /*cout * cin*/, int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cc * 9; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % 9);
+    const long long e = i / 9;
+    const int ky = k / 3, kx = k % 3;
+    float s = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      s += __ldg(dwp + ((size_t)ph * cc + e) * 4 + upconv_tap_of(py, ky) * 2 + upconv_tap_of(px, kx));
+    }
+    grad[i] = accumulate ? grad[i] + s : s;
+  }
+}
+}  // namespace rpnet
+
+RPNET_API long long rpnet_upconv_wgrad_workspace_bytes(int cin, int n, int h, int w, int cout) {
+  const long long part = rpnet_conv_wgrad_workspace_bytes(cin, 0, n, h, w, 4, cout);
+  if (part < 0) return part;
+  return part + 4LL * cout * cin * 4 * 4;
+}
+
+RPNET_API int rpnet_upconv_wgrad(const void* x_low_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
+                                 int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(x_low_bf16 && dz_bf16 && grad && workspace, "upconv_wgrad: null pointer argument");
+  const long long part = rpnet_conv_wgrad_workspace_bytes(cin, 0, n, h, w, 4, cout);
+  RPNET_REQUIRE(part >= 0 && workspace_bytes >= part + 4LL * cout * cin * 16, "upconv_wgrad: workspace too small");
+  float* dwp = reinterpret_cast<float*>(static_cast<char*>(workspace) + part);
+  const long long strides[3] = {2LL * cout, 2LL * (2 * w) * cout, (long long)(2 * h) * (2 * w) * cout};
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    int dy[4], dx[4];
+    for (int t = 0; t < 4; ++t) {
+      dy[t] = (py == 0 ? -1 : 0) + (t >> 1);
+      dx[t] = (px == 0 ? -1 : 0) + (t & 1);
+    }
+    const __nv_bfloat16* dzp = static_cast<const __nv_bfloat16*>(dz_bf16) + ((size_t)py * (2 * w) + px) * cout;
+    int rc = wgrad_impl(x_low_bf16, cin, nullptr, 0, 1, dzp, strides, n, h, w, 4, dy, dx, cout, dwp + (size_t)ph * cout * cin * 4, 0, 0, 0,
+                        workspace, part, stream_);
+    if (rc) return rc;
+  }
+  const long long cc = (long long)cout * cin;
+  long long g = (cc * 9 + 255) / 256;
+  if (g > 148LL * 16) g = 148LL * 16;
+  upconv_wgrad_combine_kernel<<<(int)g, 256, 0, stream>>>(dwp, grad, cc, accumulate);
+  return check_cuda(cudaGetLastError(), "upconv_wgrad_combine launch");
 }

@@ -148,18 +148,21 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       // the rows of this warp (py = 4q .. 4q+3) can need halo rows 4q .. 4q + 3 + 2R; one 32-column load per halo row
       // (columns hy*HW .. +HW-1 are that row): hx = j is a static register index, the band test is lane arithmetic
+      // two halo rows per step: both TMEM loads are in flight before the (independent) selection code of either row runs
 #pragma unroll 1
-      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; ++hy) {
-        float v[32];
-        tmem_ld32(t_addr + hy * Cfg::HW, v);
+      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; hy += 2) {
+        float v0[32], v1[32];
+        tmem_ld32(t_addr + hy * Cfg::HW, v0);
+        tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
         tmem_ld_wait();
-        const unsigned b = (unsigned)(hy - py);
-        if (b < (unsigned)Cfg::K) {
-          const uint32_t dst = s_row + 2 * ((int)b - px * Cfg::K);   // + 2 * a * K with a = j - px
+        const unsigned b0 = (unsigned)(hy - py), b1 = b0 + 1u;
+        const uint32_t dst0 = s_row + 2 * ((int)b0 - px * Cfg::K);   // + 2 * a * K with a = j - px
+        const bool r0 = b0 < (unsigned)Cfg::K, r1 = b1 < (unsigned)Cfg::K;
 #pragma unroll
-          for (int j = 0; j < Cfg::HW; ++j) {
-            if ((unsigned)(j - px) < (unsigned)Cfg::K) sts_f16(dst + 2 * j * Cfg::K, v[j] * p.scale);
-          }
+        for (int j = 0; j < Cfg::HW; ++j) {
+          const bool in = (unsigned)(j - px) < (unsigned)Cfg::K;
+          if (in && r0) sts_f16(dst0 + 2 * j * Cfg::K, v0[j] * p.scale);
+          if (in && r1) sts_f16(dst0 + 2 + 2 * j * Cfg::K, v1[j] * p.scale);
         }
       }
       tc_fence_before();
@@ -392,20 +395,20 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch)
         sts_f16(s_crow + (ch >> 6) * 16384 + ((((ch & 63) >> 3) ^ sw) << 4) + (ch & 7) * 2, 0.f);
 #pragma unroll 1
-      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; ++hy) {
-        float v[32];
-        tmem_ld32(t_addr + hy * Cfg::HW, v);
+      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; hy += 2) {
+        float v0[32], v1[32];
+        tmem_ld32(t_addr + hy * Cfg::HW, v0);
+        tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
         tmem_ld_wait();
-        const unsigned b = (unsigned)(hy - py);
-        if (b < (unsigned)Cfg::K) {
-          const int off = (int)b - px * Cfg::K;                 // channel = j * K + off with a = j - px
+        const unsigned b0 = (unsigned)(hy - py), b1 = b0 + 1u;
+        const bool r0 = b0 < (unsigned)Cfg::K, r1 = b1 < (unsigned)Cfg::K;
+        const int off = (int)b0 - px * Cfg::K;                    // channel = j * K + off (+1 for the second row) with a = j - px
 #pragma unroll
-          for (int j = 0; j < Cfg::HW; ++j) {
-            if ((unsigned)(j - px) < (unsigned)Cfg::K) {
-              const int ch = j * Cfg::K + off;
-              sts_f16(s_crow + (ch >> 6) * 16384 + ((((ch & 63) >> 3) ^ sw) << 4) + (ch & 7) * 2, v[j] * p.corr_scale);
-            }
-          }
+        for (int j = 0; j < Cfg::HW; ++j) {
+          const bool in = (unsigned)(j - px) < (unsigned)Cfg::K;
+          const int ch0 = j * Cfg::K + off, ch1 = ch0 + 1;
+          if (in && r0) sts_f16(s_crow + (ch0 >> 6) * 16384 + ((((ch0 & 63) >> 3) ^ sw) << 4) + (ch0 & 7) * 2, v0[j] * p.corr_scale);
+          if (in && r1) sts_f16(s_crow + (ch1 >> 6) * 16384 + ((((ch1 & 63) >> 3) ^ sw) << 4) + (ch1 & 7) * 2, v1[j] * p.corr_scale);
         }
       }
       tc_fence_before();

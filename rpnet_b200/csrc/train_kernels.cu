@@ -692,6 +692,57 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Sub-pixel packs of an up_conv weight (nn.Upsample(x2) + 3x3 conv, net/modules.py:61-75), every optimizer step:
+//   wf  fp16 [4 phases][4 taps][cout][cin] : forward, phase (py, px) = py * 2 + px, tap = ty * 2 + tx, row/column-summed
+//   w16 bf16 [16][cin][cout]               : data gradient (4x4 stride-2 form), tap = (oy + 1) * 4 + (ox + 1)
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout, int cin, __half* __restrict__ wf,
+                                          __nv_bfloat16* __restrict__ w16) {
+  const long long cc = (long long)cout * cin;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cc; e += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(e % cin), co = (int)(e / cin);
+    float k[3][3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) k[i / 3][i % 3] = __ldg(w + e * 9 + i);
+    // forward phases: rows(py=0) = {ky 0 | ky 1+2}, rows(py=1) = {ky 0+1 | ky 2}
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < 2; ++tx) {
+            float s = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const int ry = py == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0), rx = px == 0 ? (kx == 0 ? 0 : 1) : (kx == 2 ? 1 : 0);
+                if (ry == ty && rx == tx) s += k[ky][kx];
+              }
+            wf[(((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * cin + ci] = __float2half_rn(s);
+          }
+    // data gradient: S(-1) = {2}, S(0) = {1, 2}, S(1) = {0, 1}, S(2) = {0}
+#pragma unroll
+    for (int oy = -1; oy <= 2; ++oy)
+#pragma unroll
+      for (int ox = -1; ox <= 2; ++ox) {
+        float s = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const bool iny = (oy == -1 && ky == 2) || (oy == 0 && ky >= 1) || (oy == 1 && ky <= 1) || (oy == 2 && ky == 0);
+            const bool inx = (ox == -1 && kx == 2) || (ox == 0 && kx >= 1) || (ox == 1 && kx <= 1) || (ox == 2 && kx == 0);
+            if (iny && inx) s += k[ky][kx];
+          }
+        w16[((size_t)((oy + 1) * 4 + ox + 1) * cin + ci) * cout + co] = __float2bfloat16_rn(s);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Weight gradient of the Cin = 1 first conv (encoder.Conv1.conv.0): grad[co][ky][kx] += sum_p dz[p][co] * img[p + tap].
 // 8 threads per pixel, 8 output channels each (one 16-byte dz load), 72 register accumulators per thread; the four
 // pixel lanes of a warp are folded with shuffles, warps through shared-memory atomics, blocks through global atomics.
@@ -948,4 +999,12 @@ RPNET_API int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, fl
   adam_kernel<<<grid_for(n, 256), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1,
                                                     sqrtf(bc2), grad_scale);
   return check_cuda(cudaGetLastError(), "adam launch");
+}
+
+RPNET_API int rpnet_pack_upconv_weight(const float* w, int cout, int cin, void* wf_f16, void* w16_bf16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(w && wf_f16 && w16_bf16 && cout > 0 && cin > 0, "pack_upconv_weight: bad argument");
+  pack_upconv_weight_kernel<<<grid_for((long long)cout * cin, 256), 256, 0, stream>>>(w, cout, cin, static_cast<__half*>(wf_f16),
+                                                                                    static_cast<__nv_bfloat16*>(w16_bf16));
+  return check_cuda(cudaGetLastError(), "pack_upconv_weight launch");
 }

@@ -616,3 +616,80 @@ def ncc(moving, fixed):
     with _Timed('ncc', float(moving.numel() * 8), n=2):
         _lib.check(lib.rpnet_ncc_f32(_ptr(moving), _ptr(fixed), moving.numel(), _ptr(scratch), _ptr(out), _stream()), 'rpnet_ncc_f32')
     return out
+
+
+# =====================================================================================================
+# up_conv in sub-pixel form (train path)
+# =====================================================================================================
+def upconv_fusable(h, w):
+    """True when a 128-pixel tile of the low-resolution map never spans two images (the BatchNorm statistics of the phase
+    convs can then be accumulated in their epilogues)."""
+    def p2(v):
+        r = 1
+        while r * 2 <= v:
+            r *= 2
+        return r
+    bw = p2(min(w, 16))
+    bh = p2(min(h, 128 // bw))
+    return bw * bh == 128
+
+
+def pack_upconv_weight(w, wf, w16):
+    """w fp32 [cout, cin, 3, 3] -> wf fp16 [4, 4, cout, cin] (phase forward) and w16 bf16 [16, cin, cout] (data gradient)."""
+    lib = _lib.load()
+    _req(w, torch.float32, 'w'); _req(wf, torch.float16, 'wf'); _req(w16, bf16, 'w16')
+    cout, cin = w.shape[:2]
+    assert tuple(wf.shape) == (4, 4, cout, cin) and tuple(w16.shape) == (16, cin, cout)
+    with _Timed('pack_conv_weight', float(w.numel() * 12)):
+        _lib.check(lib.rpnet_pack_upconv_weight(_ptr(w), cout, cin, _ptr(wf), _ptr(w16), _stream()), 'rpnet_pack_upconv_weight')
+
+
+def upconv_fwd_bnstats(x_low, wf, ones, zeros, z, group_start, sums):
+    """z [n, 2h, 2w, cout] = conv3x3(upsample2x(x_low)) as four phase convs + BatchNorm statistics of z."""
+    lib = _lib.load()
+    _req(x_low, torch.float16, 'x_low'); _req(wf, torch.float16, 'wf'); _req(z, torch.float16, 'z'); _req(sums, torch.float64, 'sums')
+    n, h, w, cin = x_low.shape
+    cout = wf.shape[2]
+    assert tuple(z.shape) == (n, 2 * h, 2 * w, cout) and tuple(wf.shape) == (4, 4, cout, cin)
+    gs, g = _groups(group_start)
+    for ph in range(4):
+        with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * 4):
+            rc = lib.rpnet_upconv_phase_bnstats_f16(_ptr(x_low), cin, n, h, w, _ptr(wf[ph]), ph >> 1, ph & 1, cout, _ptr(ones), _ptr(zeros),
+                                                    _ptr(z), gs, g, _ptr(sums), int(ph > 0), _stream())
+        _lib.check(rc, 'rpnet_upconv_phase_bnstats_f16')
+
+
+def upconv_dgrad(dz, w16, out, out_coff=0):
+    """dx_low bf16 [n, h, w, >= cin] from dz bf16 [n, 2h, 2w, cout] (4x4 stride-2 conv over the four parity views of dz)."""
+    lib = _lib.load()
+    _req(dz, bf16, 'dz'); _req(w16, bf16, 'w16'); _req(out, bf16, 'out')
+    n, H, W, cout = dz.shape
+    h, w = H // 2, W // 2
+    cin = w16.shape[1]
+    assert tuple(w16.shape) == (16, cin, cout) and tuple(out.shape[:3]) == (n, h, w)
+    one, zero = _const_vec(cin, 1.0, dz.device), _const_vec(cin, 0.0, dz.device)
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * 16):
+        rc = lib.rpnet_upconv_dgrad_bf16(_ptr(dz), cout, n, h, w, _ptr(w16), cin, _ptr(out), out.shape[3], out_coff, _ptr(one), _ptr(zero),
+                                         _stream())
+    _lib.check(rc, 'rpnet_upconv_dgrad_bf16')
+
+
+def upconv_wgrad_workspace_bytes(cin, n, h, w, cout):
+    r = _lib.load().rpnet_upconv_wgrad_workspace_bytes(cin, n, h, w, cout)
+    if r < 0:
+        _lib.check(int(r), 'rpnet_upconv_wgrad_workspace_bytes')
+    return int(r)
+
+
+def upconv_wgrad(x_low, dz, grad, workspace, accumulate=False):
+    """grad fp32 [cout, cin, 3, 3] from x_low fp16/bf16 [n, h, w, cin] and dz bf16 [n, 2h, 2w, cout]."""
+    lib = _lib.load()
+    _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
+    x_low = _as_bf16(x_low, 0)
+    n, h, w, cin = x_low.shape
+    cout = dz.shape[3]
+    assert tuple(dz.shape) == (n, 2 * h, 2 * w, cout) and grad.numel() == cout * cin * 9
+    with _Timed('conv_wgrad', 2.0 * n * h * w * cout * cin * 16, n=9):
+        rc = lib.rpnet_upconv_wgrad(_ptr(x_low), _ptr(dz), n, h, w, cin, cout, _ptr(grad), int(bool(accumulate)), _ptr(workspace),
+                                    workspace.numel() * workspace.element_size(), _stream())
+    _lib.check(rc, 'rpnet_upconv_wgrad')

@@ -139,8 +139,8 @@ def shard_range(total, rank, world):
 class _ConvBN:
     """One conv (bias dropped: it cancels in train-mode BN) + BatchNorm(batch stats) + ReLU of the path."""
 
-    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0)):
-        self.name, self.conv, self.bn, self.first, self.hole = name, conv, bn, first, hole
+    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False):
+        self.name, self.conv, self.bn, self.first, self.hole, self.up = name, conv, bn, first, hole, up
         self.gw, self.ggamma, self.gbeta = flat.grad_of(conv.weight), flat.grad_of(bn.weight), flat.grad_of(bn.bias)
         k = conv.kernel_size[0]
         d = conv.dilation[0]
@@ -151,12 +151,38 @@ class _ConvBN:
         if not first:
             self.wf = torch.empty(len(self.taps), self.cout, self.cin_pack, dtype=f16, device=dev)
             self.wd = torch.empty(len(self.taps), self.cin_pack, self.cout, dtype=bf16, device=dev)
+        if up:      # up_conv in sub-pixel form: phase packs (forward) and the 4x4 stride-2 pack (data gradient)
+            self.wf_up = torch.empty(4, 4, self.cout, conv.in_channels, dtype=f16, device=dev)
+            self.w16_up = torch.empty(16, conv.in_channels, self.cout, dtype=bf16, device=dev)
         self.ones = torch.ones(self.cout, dtype=f32, device=dev)
         self.zeros = torch.zeros(self.cout, dtype=f32, device=dev)
 
     def pack(self):
         if not self.first:
             ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole)
+        if self.up:
+            ops.pack_upconv_weight(self.conv.weight.data, self.wf_up, self.w16_up)
+
+    def fwd_up(self, x_low, z, gs, sums, stats, y):
+        """z = conv3x3(upsample2x(x_low)) in sub-pixel form (four phase convs, statistics in their epilogues) + BN + ReLU."""
+        n, H, W, c = z.shape
+        bn = self.bn
+        ops.upconv_fwd_bnstats(x_low, self.wf_up, self.ones, self.zeros, z, gs, sums)
+        ops.bn_finalize(sums, gs, c, H * W, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
+        ops.bn_apply(z, stats, gs, True, y=y)
+
+    def bwd_up(self, eng, x_low, z, stats, gs, dx_low, **src):
+        """Backward of fwd_up: BN+ReLU backward -> dz (high resolution); weight gradient from the four phase GEMMs; data
+        gradient w.r.t. the LOW-resolution input (4x4 stride-2 conv of dz)."""
+        n, H, W, c = z.shape
+        dz = eng.scratch('dz', n * H * W * c, bf16).view(n, H, W, c)
+        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 4, f32), True, dgamma=self.ggamma, dbeta=self.gbeta, **src)
+        h, w, cin = x_low.shape[1:]
+        nb = ops.upconv_wgrad_workspace_bytes(cin, n, h, w, self.cout)
+        ops.upconv_wgrad(x_low, dz, self.gw, eng.scratch('wgrad', nb // 4, f32))
+        ops.upconv_dgrad(dz, self.w16_up, dx_low)
+        return dx_low
 
     def fwd(self, x0, x1, z, gs, sums, stats, y=None, pool=None, y32=None):
         """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) + ReLU."""
@@ -210,8 +236,8 @@ class TrainEngine:
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
             L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'))
             L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat)
-        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat)
-        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True)
         k = (2 * c.radius + 1) ** 2
         self.kcorr, self.corr_c = k, c.corr_channels
         L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
@@ -273,18 +299,42 @@ class TrainEngine:
         x4, p4 = f('c4b', a, None, gs, want_pool=True)
         a, _ = f('c5a', p4, None, gs)
         x5, _ = f('c5b', a, None, gs)
-        n = imgs.shape[0]
-        u = self.buf('up5.in', (n, x5.shape[1] * 2, x5.shape[2] * 2, x5.shape[3]), f16)
-        ops.upsample2x(x5, u)                                         # net/modules.py:67
-        u5, _ = f('up5', u, None, gs)
+        u5 = self._up_fwd('up5', x5, gs)                             # nn.Upsample(x2) + conv, net/modules.py:61-75
         a, _ = f('uc5a', x4, u5, gs)                                  # torch.cat((x4, d5), dim=1)  net/unet.py:460
         d5, _ = f('uc5b', a, None, gs)
-        u = self.buf('up4.in', (n, d5.shape[1] * 2, d5.shape[2] * 2, d5.shape[3]), f16)
-        ops.upsample2x(d5, u)
-        u4, _ = f('up4', u, None, gs)
+        u4 = self._up_fwd('up4', d5, gs)
         a, _ = f('uc4a', x3, u4, gs)                                  # torch.cat((x3, d4), dim=1)  net/unet.py:464
         d4, _ = f('uc4b', a, None, gs)
         return d4
+
+    def _up_fwd(self, key, x_low, gs):
+        """up_conv: sub-pixel form on the low-resolution input when the maps are at least one pixel tile large, else the
+        materialised nearest-x2 map + 3x3 conv."""
+        l = self.L[key]
+        n, h, w, cin = x_low.shape
+        if ops.upconv_fusable(h, w):
+            c = l.cout
+            z = self.buf(key + '.z', (n, 2 * h, 2 * w, c), f16)
+            stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
+            y = self.buf(key + '.y', (n, 2 * h, 2 * w, c), f16)
+            l.fwd_up(x_low, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, torch.float64), stats, y)
+            self.act[key] = dict(x0=x_low, x1=None, z=z, stats=stats, gs=gs, sub=True)
+            return y
+        u = self.buf(key + '.in', (n, 2 * h, 2 * w, cin), f16)
+        ops.upsample2x(x_low, u)                                      # net/modules.py:67
+        y, _ = self._layer_fwd(key, u, None, gs)
+        return y
+
+    def _up_bwd(self, key, below, **src):
+        """Backward of an up_conv layer followed by the BN backward of the layer `below` that produced its input: returns the
+        gradient w.r.t. the input of `below`'s conv."""
+        a = self.act[key]
+        if a.get('sub'):
+            dx_low = self.buf(key + '.dx', tuple(a['x0'].shape), bf16)
+            self.L[key].bwd_up(self, a['x0'], a['z'], a['stats'], a['gs'], dx_low, **src)
+            return self._layer_bwd(below, tuple(self.act[below]['x0'].shape), direct=dx_low)
+        du = self._layer_bwd(key, tuple(a['x0'].shape), **src)
+        return self._layer_bwd(below, tuple(self.act[below]['x0'].shape), up=du)
 
     def _layer_bwd(self, key, dx_shape=None, **src):
         a = self.act[key]
@@ -299,16 +349,14 @@ class TrainEngine:
         g = b('uc4b', shp('uc4b'), direct=g_d4)
         dcat4 = b('uc4a', cat('uc4a'), direct=g)
         c3 = A['uc4a']['x0'].shape[3]
-        du = b('up4', shp('up4'), direct=dcat4, d_off=c3)
+        g = self._up_bwd('up4', 'uc5b', direct=dcat4, d_off=c3)
         if buckets:
             buckets.ready(1)
-        g = b('uc5b', shp('uc5b'), up=du)
         dcat5 = b('uc5a', cat('uc5a'), direct=g)
         c4 = A['uc5a']['x0'].shape[3]
-        du = b('up5', shp('up5'), direct=dcat5, d_off=c4)
+        g = self._up_bwd('up5', 'c5b', direct=dcat5, d_off=c4)
         if buckets:
             buckets.ready(2)
-        g = b('c5b', shp('c5b'), up=du)
         dp4 = b('c5a', shp('c5a'), direct=g)
         if buckets:
             buckets.ready(3)

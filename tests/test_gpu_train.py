@@ -149,7 +149,7 @@ def test_train_step_vs_reference_golden(dev, golden):
     assert int(net.state_dict()['cre.w_k.1.num_batches_tracked']) == 1 + T
 
 
-@pytest.mark.parametrize('ways,shots,B,size,T', [(1, 1, 2, 64, 2), (2, 2, 2, 64, 2), (1, 5, 2, 64, 3), (1, 1, 1, 128, 1)])
+@pytest.mark.parametrize('ways,shots,B,size,T', [(1, 1, 2, 64, 2), (2, 2, 2, 64, 2), (1, 5, 2, 64, 3), (1, 1, 1, 128, 1), (1, 1, 1, 256, 1)])
 def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T):
     from oracle import weights
     from rpnet_b200.synthetic import make_episode, to_device

@@ -485,3 +485,42 @@ def test_local_corr_bwd_tensor_core_path(dev, case):
     torch.cuda.synchronize()
     assert _rel(_nchw(df1), f1.grad) < 4e-3, _rel(_nchw(df1), f1.grad)
     assert _rel(_nchw(df2), f2.grad) < 6e-3, _rel(_nchw(df2), f2.grad)
+
+
+@pytest.mark.parametrize('case', [(3, 128, 64, 16, 16, [0, 2, 3]), (2, 64, 128, 16, 32, [0, 2]), (1, 256, 256, 32, 32, [0, 1])])
+def test_upconv_subpixel_train_path(dev, case):
+    """up_conv (nn.Upsample(x2) + 3x3 conv, net/modules.py:61-75) in sub-pixel form: forward z + BatchNorm statistics from
+    four phase convs on the low-resolution input, data gradient as a 4x4 stride-2 conv of dZ, weight gradient from four
+    4-tap GEMMs + combine — all against torch autograd of the materialised form."""
+    from rpnet_b200 import ops
+    n, cin, cout, h, w, gs = case
+    g = _gen(sum(case[:5]))
+    x = torch.randn(n, cin, h, w, generator=g).to(bf16).float().requires_grad_(True)       # exact in fp16 and bf16
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).requires_grad_(True)
+    dz = (torch.randn(n, cout, 2 * h, 2 * w, generator=g) * 0.1).to(bf16).float()
+    z = F.conv2d(F.interpolate(x, scale_factor=2, mode='nearest'), wt, None, padding=1)
+    z.backward(dz)
+    wf = torch.empty(4, 4, cout, cin, dtype=torch.float16, device=dev)
+    w16 = torch.empty(16, cin, cout, dtype=bf16, device=dev)
+    ops.pack_upconv_weight(wt.detach().to(dev), wf, w16)
+    zd = torch.full((n, 2 * h, 2 * w, cout), 9.0, dtype=torch.float16, device=dev)
+    G = len(gs) - 1
+    sums = torch.full((G, cout, 2), 5.0, dtype=torch.float64, device=dev)
+    assert ops.upconv_fusable(h, w)
+    ops.upconv_fwd_bnstats(_nhwc(x.detach(), torch.float16, dev), wf, torch.ones(cout, device=dev), torch.zeros(cout, device=dev), zd, gs, sums)
+    torch.cuda.synchronize()
+    # forward: phase weights are sums of fp32 taps rounded to fp16 once (the dense form rounds every tap): 2e-3 of the scale
+    assert _rel(_nchw(zd), z.detach()) < 3e-3
+    for i in range(G):
+        blk = z.detach()[gs[i]:gs[i + 1]]
+        torch.testing.assert_close(sums[i, :, 0].float().cpu(), blk.sum((0, 2, 3)), rtol=5e-3, atol=5e-3 * blk[0, 0].numel() ** 0.5)
+        torch.testing.assert_close(sums[i, :, 1].float().cpu(), (blk * blk).sum((0, 2, 3)), rtol=5e-3, atol=1e-2)
+    dzd = _nhwc(dz, bf16, dev)
+    dx = torch.empty(n, h, w, cin, dtype=bf16, device=dev)
+    ops.upconv_dgrad(dzd, w16, dx)
+    grad = torch.full((cout, cin, 3, 3), 0.25, device=dev)
+    ws = torch.empty(ops.upconv_wgrad_workspace_bytes(cin, n, h, w, cout) // 4, device=dev)
+    ops.upconv_wgrad(_nhwc(x.detach(), torch.float16, dev), dzd, grad, ws, accumulate=True)
+    torch.cuda.synchronize()
+    assert _rel(_nchw(dx), x.grad) < 6e-3, _rel(_nchw(dx), x.grad)            # bf16 weights (summed taps) + bf16 output
+    assert _rel(grad.cpu() - 0.25, wt.grad) < 2e-5, _rel(grad.cpu() - 0.25, wt.grad)
