@@ -143,8 +143,9 @@ int rpnet_cvt_f16_to_bf16(const void* in_f16, void* out_bf16, long long n, void*
 
 /* Weight gradient of a tap-list conv on tcgen05 tensor cores (MN-major operands, split-K over pixels, deterministic):
  *   grad[co][ci][tap] (+)= sum_{n,y,x} dz[n,y,x,co] * x[n, y+dy[tap], x+dx[tap], ci]        (nn.Conv2d weight layout)
- * x0/x1: bf16 NHWC activations (x_bf16 must be 1: kind::f16 rejects mixed fp16 x bf16 operands — measured), channel
- * concat like the forward; dz_bf16: bf16 NHWC [n][h][w][cout].
+ * x0/x1: NHWC activations, bf16 (x_bf16 = 1) or fp16 (x_bf16 = 0: one tcgen05.mma takes a single operand format, so the
+ * epilogue warps convert the x boxes to bf16 in shared memory as they land — no separate conversion pass), channel concat
+ * like the forward; dz_bf16: bf16 NHWC [n][h][w][cout].
  * Packed input channels [hole_start, hole_start+hole_len) are padding and are skipped in `grad`.
  * Replaces autograd's conv weight gradient for net/modules.py:47-54,66-71 and net/rp_net.py:50-69. */
 int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16, const void* dz_bf16, int n, int h,
@@ -160,7 +161,7 @@ int rpnet_conv_wgrad(const void* x0, int c0, const void* x1, int c1, int x_bf16,
  *                             BatchNorm statistics of z accumulate over the four launches (keep_sums = 0 on the first).
  *                             -2 when the statistics cannot be fused for the shape (maps smaller than a pixel tile).
  *   rpnet_upconv_dgrad_bf16:  dx_low [n][h][w][out_c] (channels [out_coff, +cin)) from dz bf16 [n][2h][2w][cout].
- *   rpnet_upconv_wgrad:       grad [cout][cin][3][3] (=|+=) from x_low bf16 [n][h][w][cin] and dz bf16 [n][2h][2w][cout]. */
+ *   rpnet_upconv_wgrad:       grad [cout][cin][3][3] (=|+=) from x_low fp16/bf16 [n][h][w][cin] and dz bf16 [n][2h][2w][cout]. */
 int rpnet_pack_upconv_weight(const float* w, int cout, int cin, void* wf_f16, void* w16_bf16, void* stream);
 int rpnet_upconv_phase_bnstats_f16(const void* x_low, int cin, int n, int h, int w, const void* wphase, int py, int px, int cout,
                                    const float* ones, const float* zeros, void* z_f16, const int* group_start, int groups,
@@ -168,7 +169,7 @@ int rpnet_upconv_phase_bnstats_f16(const void* x_low, int cin, int n, int h, int
 int rpnet_upconv_dgrad_bf16(const void* dz, int cout, int n, int h, int w, const void* w16, int cin, void* out, int out_c,
                             int out_coff, const float* ones, const float* zeros, void* stream);
 long long rpnet_upconv_wgrad_workspace_bytes(int cin, int n, int h, int w, int cout);
-int rpnet_upconv_wgrad(const void* x_low_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
+int rpnet_upconv_wgrad(const void* x_low, int x_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
                        int accumulate, void* workspace, long long workspace_bytes, void* stream);
 
 /* Weight gradient of the Cin = 1 first conv: grad[64][1][3][3] += sum dz * img.  net/unet.py:405 (encoder.Conv1.conv.0). */

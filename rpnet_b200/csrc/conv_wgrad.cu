@@ -48,6 +48,19 @@ struct WgradParams {
 constexpr int kWgAcc = 2;                          // 128-row accumulators per work item (they share every dZ stage)
 constexpr int kWgBoxesPerItem = 2 * kWgAcc;        // M tile = 256 rows = 4 (tap, 64-channel chunk) boxes
 
+// In-place fp16 -> bf16 conversion of an operand region in shared memory by the 128 epilogue threads (they idle during the
+// K loop): the forward activations are fp16, the gradients bf16, and one tcgen05.mma takes a single operand format.
+// Element-wise, so the 128-byte swizzle of the TMA tile is irrelevant.  et = 0..127.
+__device__ __forceinline__ void cvt_smem_f16_to_bf16(uint8_t* base, int bytes, int et) {
+  uint4* v = reinterpret_cast<uint4*>(base);
+  for (int i = et; i < bytes / 16; i += 128) {
+    const uint4 u = v[i];
+    float f[8];
+    unpack8_f16(u, f);
+    v[i] = pack8_bf16(f);
+  }
+}
+
 template <int BN>
 struct WgradCfg {
   static constexpr int kABytes = kWgBoxesPerItem * kWgBoxBytes;
@@ -55,7 +68,7 @@ struct WgradCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kWgSmemBudget / kStageBytes) > 8 ? 8 : (kWgSmemBudget / kStageBytes);
   static constexpr int kTmemCols = kWgAcc * BN;     // single-buffered: the K loop of an item is long, its epilogue short
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
 };
 
 template <int BN>
@@ -70,7 +83,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* conv_bar = tempty_bar + 2;                   // [kStages] fp16 -> bf16 conversion of the x boxes done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,6 +101,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&conv_bar[i], 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -142,8 +157,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16) | (p.x_bf16 ? (1u << 7) : 0u) |
-                             (p.dz_bf16 ? (1u << 10) : 0u);
+      const uint32_t idesc = umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16) | (1u << 7) | (1u << 10);   // both operands bf16 at MMA time
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -155,7 +169,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         mbar_wait(&tempty_bar[0], aphase ^ 1);            // the epilogue has drained the accumulators of the previous item
         tc_fence_after();
         for (int pt = k0; pt < k1; ++pt) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(p.x_bf16 ? &full_bar[stage] : &conv_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -180,11 +194,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int it = 0;
+    int cstage = 0;
+    uint32_t cphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int split = item / tiles_mn;
       const int rem = item % tiles_mn;
       const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
       const uint32_t aphase = it & 1;
+      if (!p.x_bf16) {                                   // K loop: convert the x boxes of every stage as they land
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        for (int pt = k0; pt < k1; ++pt) {
+          mbar_wait(&full_bar[cstage], cphase);
+          cvt_smem_f16_to_bf16(tiles + cstage * Cfg::kStageBytes, Cfg::kABytes, threadIdx.x - 64);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv_bar[cstage]);
+          if (++cstage == kStages) { cstage = 0; cphase ^= 1; }
+        }
+      }
       mbar_wait(&tfull_bar[0], aphase);
       tc_fence_after();
 #pragma unroll 1
@@ -233,7 +261,7 @@ constexpr int kWhBoxA = 64 * 2 * 8 * 10;            // 10240 B: one dx box (80 p
 constexpr int kWhBoxB = 64 * 2 * 64;                // 8192 B
 constexpr int kWhStageBytes = 3 * kWhBoxA + kWhBoxB;  // 38912 B (multiple of 1024)
 constexpr int kWhStages = 5;
-constexpr int kWhSmemBytes = kWhStages * kWhStageBytes + 1024 + 256;
+constexpr int kWhSmemBytes = kWhStages * kWhStageBytes + 1024 + 512;
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
@@ -244,7 +272,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   uint64_t* empty_bar = full_bar + kWhStages;
   uint64_t* tfull_bar = empty_bar + kWhStages;
   uint64_t* tempty_bar = tfull_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+  uint64_t* conv_bar = tempty_bar + 1;                   // [kWhStages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kWhStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = p.chunks0 + p.chunks1;
@@ -255,7 +284,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     tma_prefetch_desc(&tm_x0);
     tma_prefetch_desc(&tm_x1);
     tma_prefetch_desc(&tm_dz);
-    for (int i = 0; i < kWhStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kWhStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&conv_bar[i], 4); }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 4);
     mbar_fence_init();
@@ -307,7 +336,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
         mbar_wait(tempty_bar, (it & 1) ^ 1);
         tc_fence_after();
         for (int pt = k0; pt < k1; ++pt) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(p.x_bf16 ? &full_bar[stage] : &conv_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * kWhStageBytes);
           const uint32_t b_addr = a_addr + 3 * kWhBoxA;
@@ -334,10 +363,24 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
     const int row = q * 32 + lane;
     const int cin = nch * 64;
     int it = 0;
+    int cstage = 0;
+    uint32_t cphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int split = item / tiles_mn;
       const int rem = item % tiles_mn;
       const int kc = rem / p.n_ntiles, nt = rem % p.n_ntiles;
+      if (!p.x_bf16) {                                   // K loop: convert the three x boxes of every stage as they land
+        const int k0 = (int)((long long)split * p.ptiles / p.splits);
+        const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
+        for (int pt = k0; pt < k1; ++pt) {
+          mbar_wait(&full_bar[cstage], cphase);
+          cvt_smem_f16_to_bf16(tiles + cstage * kWhStageBytes, 3 * kWhBoxA, threadIdx.x - 64);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv_bar[cstage]);
+          if (++cstage == kWhStages) { cstage = 0; cphase ^= 1; }
+        }
+      }
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -510,7 +553,6 @@ static int wgrad_impl(const void* x0, int c0, const void* x1, int c1, int x_bf16
   RPNET_REQUIRE(x0 && dz_bf16 && grad && workspace, "conv_wgrad: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0, "conv_wgrad: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
   RPNET_REQUIRE(c1 == 0 || x1, "conv_wgrad: x1 is null but c1 = %d", c1);
-  RPNET_REQUIRE(x_bf16, "conv_wgrad: activations must be bf16 (tcgen05 kind::f16 rejects mixed fp16 x bf16 operands)");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv_wgrad: bad grid %d x %d x %d", n, h, w);
   RPNET_REQUIRE(ntaps >= 1 && ntaps <= kWgMaxTaps, "conv_wgrad: ntaps %d out of range [1, %d]", ntaps, kWgMaxTaps);
   RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_wgrad: cout must be a multiple of 64 (got %d)", cout);
@@ -524,20 +566,20 @@ static int wgrad_impl(const void* x0, int c0, const void* x1, int c1, int x_bf16
     p.tiles_x = ph.tiles_x; p.tiles_y = ph.tiles_y; p.tiles_n = ph.tiles_n; p.ptiles = ph.ptiles;
     p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.ntaps = 9;
     p.n_boxes = ph.n_boxes; p.n_mtiles = ph.n_mtiles; p.n_ntiles = ph.n_ntiles; p.splits = ph.splits;
-    p.rows = ph.rows; p.cout = cout; p.x_bf16 = 1; p.dz_bf16 = 1;
+    p.rows = ph.rows; p.cout = cout; p.x_bf16 = x_bf16 ? 1 : 0; p.dz_bf16 = 1;
     p.partial = static_cast<float*>(workspace);
     CUtensorMap tx0, tx1, tdz;
     const uint32_t box_a[4] = {64u, 8u, 10u, 1u}, box_b[4] = {64u, 8u, 8u, 1u};
     {
       const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
       const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
-      int rc = make_tmap_2b(&tx0, x0, 4, dims, str, box_a, true);
+      int rc = make_tmap_2b(&tx0, x0, 4, dims, str, box_a, x_bf16 != 0);
       if (rc) return rc;
     }
     if (c1 > 0) {
       const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
       const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
-      int rc = make_tmap_2b(&tx1, x1, 4, dims, str, box_a, true);
+      int rc = make_tmap_2b(&tx1, x1, 4, dims, str, box_a, x_bf16 != 0);
       if (rc) return rc;
     } else {
       tx1 = tx0;
@@ -661,10 +703,10 @@ RPNET_API long long rpnet_upconv_wgrad_workspace_bytes(int cin, int n, int h, in
   return part + 4LL * cout * cin * 4 * 4;
 }
 
-RPNET_API int rpnet_upconv_wgrad(const void* x_low_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
+RPNET_API int rpnet_upconv_wgrad(const void* x_low, int x_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
                                  int accumulate, void* workspace, long long workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RPNET_REQUIRE(x_low_bf16 && dz_bf16 && grad && workspace, "upconv_wgrad: null pointer argument");
+  RPNET_REQUIRE(x_low && dz_bf16 && grad && workspace, "upconv_wgrad: null pointer argument");
   const long long part = rpnet_conv_wgrad_workspace_bytes(cin, 0, n, h, w, 4, cout);
   RPNET_REQUIRE(part >= 0 && workspace_bytes >= part + 4LL * cout * cin * 16, "upconv_wgrad: workspace too small");
   float* dwp = reinterpret_cast<float*>(static_cast<char*>(workspace) + part);
@@ -677,7 +719,7 @@ RPNET_API int rpnet_upconv_wgrad(const void* x_low_bf16, const void* dz_bf16, in
       dx[t] = (px == 0 ? -1 : 0) + (t & 1);
     }
     const __nv_bfloat16* dzp = static_cast<const __nv_bfloat16*>(dz_bf16) + ((size_t)py * (2 * w) + px) * cout;
-    int rc = wgrad_impl(x_low_bf16, cin, nullptr, 0, 1, dzp, strides, n, h, w, 4, dy, dx, cout, dwp + (size_t)ph * cout * cin * 4, 0, 0, 0,
+    int rc = wgrad_impl(x_low, cin, nullptr, 0, x_bf16, dzp, strides, n, h, w, 4, dy, dx, cout, dwp + (size_t)ph * cout * cin * 4, 0, 0, 0,
                         workspace, part, stream_);
     if (rc) return rc;
   }

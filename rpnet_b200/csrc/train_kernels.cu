@@ -673,21 +673,36 @@ __global__ void premask_bwd_kernel(const uint4* __restrict__ dxfg, const uint4* 
 //   dgrad    bf16 [taps][cin][cout]   (transposed; used with the negated tap list)
 // `cin` = cin_real + hole_len: packed input channels [hole_start, hole_start+hole_len) are zero padding.
 // ---------------------------------------------------------------------------------------------------
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
-                                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
-  const long long total = (long long)ntaps * cout * cin;
+// One block per 32 (cout) x 32 (cin) tile: the fp32 weights of the tile (32 x 32 x taps, contiguous runs of 32 * taps floats
+// per cout) are staged in shared memory, so that both packs leave as coalesced rows — wf rows run along cin, the transposed
+// wd rows along cout.
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
+                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  __shared__ float s_w[32][32 * 9 + 1];                           // [co][ci * ntaps + t]
   const int cin_real = cin - hole_len;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % cin);
-    const int co = (int)((i / cin) % cout);
-    const int t = (int)(i / ((long long)cin * cout));
+  const int tiles_ci = (cin + 31) / 32;
+  const int co0 = (blockIdx.x / tiles_ci) * 32, ci0 = (blockIdx.x % tiles_ci) * 32;
+  // stage: thread -> (co, element of the run); packed channel ci maps to the real channel (padding hole = zeros)
+  for (int i = threadIdx.x; i < 32 * 32 * ntaps; i += 256) {
+    const int co = i / (32 * ntaps), r = i % (32 * ntaps);
+    const int ci = ci0 + r / ntaps, t = r % ntaps;
     float val = 0.f;
-    if (ci < hole_start || ci >= hole_start + hole_len) {
+    if (co0 + co < cout && ci < cin && (ci < hole_start || ci >= hole_start + hole_len)) {
       const int cr = ci < hole_start ? ci : ci - hole_len;
-      val = __ldg(w + ((size_t)co * cin_real + cr) * ntaps + t);
+      val = __ldg(w + ((size_t)(co0 + co) * cin_real + cr) * ntaps + t);
     }
-    if (wf) wf[i] = __float2half_rn(val);
-    if (wd) wd[((size_t)t * cin + ci) * cout + co] = __float2bfloat16_rn(val);
+    s_w[co][r] = val;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, rowi = threadIdx.x >> 5;     // 8 rows per pass
+  for (int t = 0; t < ntaps; ++t) {
+    for (int r = rowi; r < 32; r += 8) {
+      if (wf && co0 + r < cout && ci0 + lane < cin)                // wf[t][co][ci]: lanes along ci
+        wf[((size_t)t * cout + co0 + r) * cin + ci0 + lane] = __float2half_rn(s_w[r][lane * ntaps + t]);
+      if (wd && ci0 + r < cin && co0 + lane < cout)                // wd[t][ci][co]: lanes along co
+        wd[((size_t)t * cin + ci0 + r) * cout + co0 + lane] = __float2bfloat16_rn(s_w[lane][r * ntaps + t]);
+    }
   }
 }
 
@@ -972,8 +987,10 @@ RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int
   RPNET_REQUIRE(cout > 0 && cin_real > 0 && ntaps > 0 && hole_len >= 0 && hole_start >= 0 && hole_start <= cin_real,
                 "pack_conv_weight: bad shape");
   const int cin = cin_real + hole_len;
-  pack_conv_weight_kernel<<<grid_for((long long)ntaps * cout * cin, 256), 256, 0, stream>>>(
-      w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16), static_cast<__nv_bfloat16*>(w_dgrad_bf16));
+  RPNET_REQUIRE(ntaps <= 9, "pack_conv_weight: at most 9 taps (got %d)", ntaps);
+  const int tiles = ((cout + 31) / 32) * ((cin + 31) / 32);
+  pack_conv_weight_kernel<<<tiles, 256, 0, stream>>>(w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16),
+                                                     static_cast<__nv_bfloat16*>(w_dgrad_bf16));
   return check_cuda(cudaGetLastError(), "pack_conv_weight launch");
 }
 

@@ -305,7 +305,8 @@ def conv_wgrad(x0, dz, taps, grad, workspace, x1=None, hole=(0, 0), accumulate=T
     _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
     if x0.dtype not in (torch.float16, bf16) or not x0.is_contiguous():
         raise _lib.RpnetError('conv_wgrad: x0 must be contiguous fp16/bf16')
-    x0, x1 = _as_bf16(x0, 0), _as_bf16(x1, 1)
+    if x1 is not None and x1.dtype != x0.dtype:
+        x0, x1 = _as_bf16(x0, 0), _as_bf16(x1, 1)        # mixed formats: fall back to explicit bf16 copies
     n, h, w, c0 = x0.shape
     c1 = 0 if x1 is None else x1.shape[3]
     cout = dz.shape[3]
@@ -685,11 +686,10 @@ def upconv_wgrad(x_low, dz, grad, workspace, accumulate=False):
     """grad fp32 [cout, cin, 3, 3] from x_low fp16/bf16 [n, h, w, cin] and dz bf16 [n, 2h, 2w, cout]."""
     lib = _lib.load()
     _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
-    x_low = _as_bf16(x_low, 0)
     n, h, w, cin = x_low.shape
     cout = dz.shape[3]
     assert tuple(dz.shape) == (n, 2 * h, 2 * w, cout) and grad.numel() == cout * cin * 9
     with _Timed('conv_wgrad', 2.0 * n * h * w * cout * cin * 16, n=9):
-        rc = lib.rpnet_upconv_wgrad(_ptr(x_low), _ptr(dz), n, h, w, cin, cout, _ptr(grad), int(bool(accumulate)), _ptr(workspace),
-                                    workspace.numel() * workspace.element_size(), _stream())
+        rc = lib.rpnet_upconv_wgrad(_ptr(x_low), int(x_low.dtype == bf16), _ptr(dz), n, h, w, cin, cout, _ptr(grad), int(bool(accumulate)),
+                                    _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     _lib.check(rc, 'rpnet_upconv_wgrad')
