@@ -60,6 +60,18 @@ int rpnet_conv_cos_f16(const void* src0, int c0, const void* src1, int c1, int n
                        const int* tap_dy, const int* tap_dx, const float* scale, const float* shift, int relu,
                        const float* protos, int n_protos, int proto_sets, float scaler, float* pred, float* out_f32, void* stream);
 
+/* "Next" row N3 (ResNet18 backbone, net/rp_net.py:19-42).
+ * rpnet_conv_res_f16: tap-list conv (as rpnet_conv_igemm_f16, one source, dense output) with a residual added after the affine
+ *   and before the ReLU: out = act(scale * conv(src) + shift + res) — torchvision BasicBlock's `out += identity; relu`.
+ *   res fp16 NHWC [n][h][w][cout] (null = no residual).
+ * rpnet_conv7x7s2_stem_f16: torchvision resnet18 conv1 (7x7, stride 2, pad 3, no bias) + folded bn1 + ReLU on a 3-channel fp32
+ *   NCHW image -> fp16 NHWC [n][(h-1)/2+1][(w-1)/2+1][64].  weight fp32 [64][3][7][7]. */
+int rpnet_conv_res_f16(const void* src, int cin, int n, int h, int w, const void* wpack, int ntaps, const int* tap_dy,
+                       const int* tap_dx, int cout, const float* scale, const float* shift, const void* res_f16, int relu,
+                       void* out_f16, void* stream);
+int rpnet_conv7x7s2_stem_f16(const float* img, int n, int h, int w, const float* weight, const float* scale, const float* shift,
+                             int relu, void* out_f16, void* stream);
+
 /* First encoder conv: fp32 NCHW image [n][cin][h][w] (cin 1 or 3) -> 64 channels, 3x3 pad 1, fused
  * affine (+ReLU), fp16 NHWC out [n][h][w][64].  weight fp32 [64][cin][3][3] (PyTorch layout).
  * Replaces encoder.Conv1.conv.0-2 (net/modules.py:48-50 via net/unet.py:405) and VGG features.0.0

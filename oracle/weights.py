@@ -46,6 +46,30 @@ def unet_rpnet_state_dict(seed=0, radius=5):
     return sd
 
 
+def resnet_rpnet_state_dict(seed=0, radius=5):
+    """RP_Net(backbone='resnet') state_dict with the reference's RNG consumption order (net/rp_net.py:214-216 ->
+    ResNet18.__init__ :20-37: a full torchvision resnet18 is constructed first, then the three custom stages; then the cre
+    with 512 input channels, :221)."""
+    import torchvision
+    from torchvision.models.resnet import BasicBlock
+    torch.manual_seed(seed)
+    sd = OrderedDict()
+    net = torchvision.models.resnet18()
+    modules = list(net.children())[:-5]
+    for cin, cout in ((64, 128), (128, 256), (256, 512)):
+        modules.append(nn.Sequential(BasicBlock(cin, cout, downsample=nn.Sequential(nn.Conv2d(cin, cout, 1), nn.BatchNorm2d(cout))),
+                                     BasicBlock(cout, cout)))
+    for k, v in nn.Sequential(*modules).state_dict().items():
+        sd['encoder.backbone.' + k] = v
+    c = 512
+    _conv_bn(sd, 'cre.w_k.0', 'cre.w_k.1', c, c, 3)
+    _conv_bn(sd, 'cre.w_q.0', 'cre.w_q.1', c, c, 3)
+    _conv_bn(sd, 'cre.w_context.0', 'cre.w_context.1', 2 * c, c, 1)
+    _conv_bn(sd, 'cre.q.0', 'cre.q.1', c + (2 * radius + 1) ** 2, 64, 1)
+    _conv_bn(sd, 'cre.out.0', 'cre.out.1', 2 * c, 64, 1)
+    return sd
+
+
 def vgg_state_dict(seed=0, in_channels=3):
     """net/vgg.py:22-63: 13 convs then kaiming_normal_ on every conv weight in module order."""
     torch.manual_seed(seed)

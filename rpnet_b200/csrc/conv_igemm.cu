@@ -53,6 +53,10 @@ struct ConvParams {
   int pool_C;
   float* out_f32;                 // optional fp32 NHWC output (N, H, W, f32_C)
   int f32_C;
+  // optional residual (torchvision BasicBlock: out = relu(bn2(conv2(.)) + identity)): fp16 NHWC [N][H][W][res_C], added after the
+  // affine and before the ReLU
+  const __half* res;
+  int res_C;
   // optional fused calDist (net/rp_net.py:353-363) on the activated output of a 64-channel conv (the whole feature vector of
   // a pixel sits in one accumulator row): cos_pred[n][p][pixel] = cos_scaler * cos(y[n,pixel,:], cos_protos[n % cos_sets][p][:])
   const float* cos_protos;
@@ -260,10 +264,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         float v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
+        if (p.res) {
+          float r[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]);
-          v[j] = p.relu ? fmaxf(t, 0.f) : t;
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
+          if (valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + (static_cast<size_t>(n * p.H + y) * p.W + x) * p.res_C + ct * BN + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack8_f16(__ldg(rp + j), r + 8 * j);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]) + r[j];
+            v[j] = p.relu ? fmaxf(t, 0.f) : t;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float t = fmaf(v[j], sc[c0 + j], sh[c0 + j]);
+            v[j] = p.relu ? fmaxf(t, 0.f) : t;
+          }
         }
         if (BN == 64 && p.cos_pred) {
 #pragma unroll
@@ -442,7 +462,8 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
                            void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
                            int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr, const float* cos_protos = nullptr,
                            int cos_P = 0, int cos_sets = 0, float cos_scaler = 0.f, float* cos_pred = nullptr, int bn_keep_sums = 0,
-                           const void* const* view_ptr = nullptr, const long long* view_strides = nullptr, const int* tap_src = nullptr) {
+                           const void* const* view_ptr = nullptr, const long long* view_strides = nullptr, const int* tap_src = nullptr,
+                           const void* res_f16 = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
@@ -479,6 +500,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   p.out_f32 = out_f32; p.f32_C = cout;
   p.bn_sums = nullptr; p.bn_groups = 0;
   if (bn_fused) *bn_fused = 0;
+  p.res = static_cast<const __half*>(res_f16); p.res_C = cout;
   p.cos_pred = nullptr; p.cos_protos = nullptr; p.cos_P = 0; p.cos_sets = 1; p.cos_scaler = 0.f;
   if (cos_pred) {
     RPNET_REQUIRE(cout == 64 && cos_protos && cos_P >= 1 && cos_P <= kMaxCosP && cos_sets >= 1,
@@ -639,4 +661,14 @@ RPNET_API int rpnet_upconv_dgrad_bf16(const void* dz, int cout, int n, int h, in
   const long long strides[3] = {2LL * cout, 2LL * (2 * w) * cout, (long long)(2 * h) * (2 * w) * cout};
   return conv_igemm_impl(true, views[0], cout, nullptr, 0, n, h, w, w16, 16, dy, dx, cin, ones, zeros, 0, out, h, w, out_c, out_coff, 1, 0, 1,
                          0, nullptr, nullptr, stream_, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, views, strides, src);
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_res_f16(const void* src, int cin, int n, int h, int w, const void* wpack, int ntaps, const int* tap_dy,
+                                  const int* tap_dx, int cout, const float* scale, const float* shift, const void* res_f16, int relu,
+                                  void* out_f16, void* stream_) {
+  RPNET_REQUIRE(out_f16, "conv_res: null output");
+  return conv_igemm_impl(false, src, cin, nullptr, 0, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_f16, h, w, cout, 0,
+                         1, 0, 1, 0, nullptr, nullptr, stream_, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, nullptr, nullptr,
+                         nullptr, res_f16);
 }

@@ -155,6 +155,47 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
   }
 }
 
+// ResNet stem (torchvision resnet18.conv1 + bn1 + relu, reached through net/rp_net.py:19-37): 7x7 stride-2 pad-3 conv of a
+// 3-channel fp32 NCHW image -> 64 channels, folded BN + ReLU, fp16 NHWC [n][H/2][W/2][64].  K = 147 per output: CUDA cores;
+// weights live in shared memory as [tap][64], 8 threads per output pixel x 8 channels each.
+__global__ void __launch_bounds__(256)
+conv7x7s2_stem_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][3][7][7]*/, const float* __restrict__ scale,
+                      const float* __restrict__ shift, int relu, __half* __restrict__ out, int N, int H, int W) {
+  __shared__ float s_w[147][64];
+  for (int i = threadIdx.x; i < 64 * 147; i += blockDim.x) s_w[i % 147][i / 147] = wgt[i];
+  __syncthreads();
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const int cg = threadIdx.x & 7;
+  const unsigned total = (unsigned)N * Ho * Wo;
+  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < total; p += (gridDim.x * blockDim.x) >> 3) {
+    const int xo = (int)(p % Wo), yo = (int)((p / Wo) % Ho), n = (int)(p / ((unsigned)Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* plane = img + ((size_t)n * 3 + ci) * H * W;
+      for (int ky = 0; ky < 7; ++ky) {
+        const int yy = yo * 2 + ky - 3;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int xx = xo * 2 + kx - 3;
+          const float v = (xx >= 0 && xx < W) ? __ldg(plane + (size_t)yy * W + xx) : 0.f;
+          const float* wr = &s_w[(ci * 7 + ky) * 7 + kx][cg * 8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(acc[j], __ldg(scale + cg * 8 + j), __ldg(shift + cg * 8 + j));
+      acc[j] = relu ? fmaxf(t, 0.f) : t;
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)p * 64 + cg * 8) = pack8(acc);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // F.avg_pool2d(mask[:, None], s)  (net/rp_net.py:270,272).  fp32 [N,H,W] -> fp32 [N,H/s,W/s].
 // ---------------------------------------------------------------------------------------------------
@@ -550,6 +591,17 @@ RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, i
   else
     conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");
+}
+
+RPNET_API int rpnet_conv7x7s2_stem_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
+                                        const float* shift, int relu, void* out_f16, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv7x7s2_stem: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h >= 7 && w >= 7 && (long long)n * h * w < (1LL << 31), "conv7x7s2_stem: bad shape %d x %d x %d", n, h, w);
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  conv7x7s2_stem_kernel<<<grid_for((long long)n * ho * wo * 8, 256), 256, 0, stream>>>(img, weight, scale, shift, relu,
+                                                                                    static_cast<__half*>(out_f16), n, h, w);
+  return check_cuda(cudaGetLastError(), "conv7x7s2_stem launch");
 }
 
 RPNET_API int rpnet_avgpool_mask_f32(const float* in, float* out, int n, int h, int w, int s, void* stream_) {

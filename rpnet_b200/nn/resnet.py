@@ -1,0 +1,76 @@
+"""ResNet18 backbone wrapper with the reference's structure and state_dict keys (net/rp_net.py:19-42): torchvision's
+resnet18 stem + layer1 (stride 4) followed by three custom stride-1 BasicBlock stages -> 512 channels at H/4.
+"Next" row N3 of SURVEY §8(f): eval forward only (training is built for the U-Net backbone).
+
+The torchvision modules are parameter containers: forward() never calls them — it runs the stem kernel, the max-pool kernel
+and the tcgen05 implicit-GEMM conv with the BasicBlock's residual add + ReLU fused into its epilogue."""
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+from .modules import _PackedModule
+
+
+class ResNet18(_PackedModule):
+    def __init__(self, use_pretrained=False):
+        super().__init__()
+        import torchvision
+        from torchvision.models.resnet import BasicBlock
+        if use_pretrained:
+            raise NotImplementedError('pretrained torchvision weights cannot be downloaded here; load a state_dict instead')
+        resnet_net = torchvision.models.resnet18()
+        modules = list(resnet_net.children())[:-5]                      # conv1, bn1, relu, maxpool, layer1
+        for cin, cout in ((64, 128), (128, 256), (256, 512)):           # net/rp_net.py:24-35
+            modules.append(nn.Sequential(
+                BasicBlock(cin, cout, downsample=nn.Sequential(nn.Conv2d(cin, cout, 1), nn.BatchNorm2d(cout))),
+                BasicBlock(cout, cout)))
+        self.backbone = nn.Sequential(*modules)
+        self.backbone.out_channels = 512
+        self._ws = engine.Workspace()
+
+    def _blocks(self):
+        return [blk for stage in list(self.backbone)[4:] for blk in stage]
+
+    def _build_packs(self):
+        conv1, bn1 = self.backbone[0], self.backbone[1]
+        zero = torch.zeros(64, device=conv1.weight.device)
+        stem = engine.fold_bn(zero, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.eps)
+        packs = []
+        for blk in self._blocks():
+            def cb(conv, bn, relu):
+                bias = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=conv.weight.device)
+                scale, shift = engine.fold_bn(bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+                wp, taps = engine.pack_weight_taps(conv.weight)
+                return engine.ConvPack(wp, taps, scale, shift, relu)
+            down = cb(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
+            packs.append((cb(blk.conv1, blk.bn1, True), cb(blk.conv2, blk.bn2, True), down))
+        return stem, packs
+
+    def encode_nhwc(self, x, tag='res'):
+        """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/4, W/4, 512]."""
+        if self.training:
+            raise NotImplementedError("backbone 'resnet' is built for eval only (SURVEY §8f N3)")
+        ws, dev = self._ws, x.device
+        (s_scale, s_shift), packs = self._packs()
+        n, _, H, W = x.shape
+        h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        stem = ws.get(tag + '.stem', (n, h2, w2, 64), torch.float16, dev)
+        ops.conv7x7s2_stem(x.float().contiguous(), self.backbone[0].weight.detach().float().contiguous(), s_scale, s_shift, stem)
+        h4, w4 = (h2 + 2 - 3) // 2 + 1, (w2 + 2 - 3) // 2 + 1
+        cur = ws.get(tag + '.pool', (n, h4, w4, 64), torch.float16, dev)
+        ops.maxpool(stem, 3, 2, 1, cur)                                  # nn.MaxPool2d(3, 2, 1)
+        for i, (p1, p2, down) in enumerate(packs):                       # BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)
+            a = ws.get('%s.b%d.a' % (tag, i), (n, h4, w4, p1.cout), torch.float16, dev)
+            ops.conv_res(cur, p1.wpack, p1.taps, p1.scale, p1.shift, a, relu=True)
+            identity = cur
+            if down is not None:
+                identity = ws.get('%s.b%d.d' % (tag, i), (n, h4, w4, down.cout), torch.float16, dev)
+                ops.conv_res(cur, down.wpack, down.taps, down.scale, down.shift, identity, relu=False)
+            out = ws.get('%s.b%d.o' % (tag, i), (n, h4, w4, p2.cout), torch.float16, dev)
+            ops.conv_res(a, p2.wpack, p2.taps, p2.scale, p2.shift, out, res=identity, relu=True)
+            cur = out
+        return cur
+
+    def forward(self, x, mask=None):
+        """Reference signature (net/rp_net.py:39-42): returns {'d4': NCHW fp32}."""
+        return {'d4': engine.nhwc_to_nchw_f32(self.encode_nhwc(x.float().contiguous(), 'fwd'))}

@@ -158,16 +158,19 @@ class RP_Net(nn.Module):
             if pretrained_path:
                 dic = torch.load(self.pretrained_path, map_location='cpu')['state_dict']
                 self.load_state_dict(dic)
+        elif self.config['backbone'] == 'resnet':
+            from .resnet import ResNet18
+            self.encoder = ResNet18(use_pretrained=False)                 # net/rp_net.py:208-209 (eval only here)
+            num_feat = 512
         else:
-            # 'resnet' (torchvision BasicBlock stack) is a "next" row, not built
-            raise NotImplementedError(self.config['backbone'])
+            raise NotImplementedError(self.config['backbone'])              # net/rp_net.py:218-219
 
         self.cre = ContextCorrelationEncoder(backbone_cfg, in_channels=num_feat)
         self._ws = engine.Workspace()
 
     # ------------------------------------------------------------------ hot path
     def _encode(self, imgs, tag):
-        if self.config['backbone'] == 'vgg':
+        if self.config['backbone'] in ('vgg', 'resnet'):
             if imgs.shape[1] == 1:
                 imgs = imgs.expand(-1, 3, -1, -1)                      # net/rp_net.py:246-247
             return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)

@@ -693,3 +693,35 @@ def upconv_wgrad(x_low, dz, grad, workspace, accumulate=False):
         rc = lib.rpnet_upconv_wgrad(_ptr(x_low), int(x_low.dtype == bf16), _ptr(dz), n, h, w, cin, cout, _ptr(grad), int(bool(accumulate)),
                                     _ptr(workspace), workspace.numel() * workspace.element_size(), _stream())
     _lib.check(rc, 'rpnet_upconv_wgrad')
+
+
+# =====================================================================================================
+# "next" row N3: ResNet18 backbone pieces
+# =====================================================================================================
+def conv_res(src, wpack, taps, scale, shift, out, res=None, relu=True):
+    """out = act(scale * conv(src) + shift (+ res)); src / res / out fp16 NHWC."""
+    lib = _lib.load()
+    _req(src, torch.float16, 'src'); _req(wpack, torch.float16, 'wpack'); _req(out, torch.float16, 'out')
+    n, h, w, cin = src.shape
+    ntaps, cout, cin2 = wpack.shape
+    if cin2 != cin or ntaps != len(taps) or tuple(out.shape) != (n, h, w, cout):
+        raise _lib.RpnetError('conv_res: shapes do not match')
+    if res is not None:
+        _req(res, torch.float16, 'res')
+        assert res.shape == out.shape
+    dy, dx = _taps(taps)
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_res_f16(_ptr(src), cin, n, h, w, _ptr(wpack), ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), _ptr(res),
+                                    int(bool(relu)), _ptr(out), _stream())
+    _lib.check(rc, 'rpnet_conv_res_f16')
+
+
+def conv7x7s2_stem(img, weight, scale, shift, out, relu=True):
+    """img fp32 NCHW [n, 3, H, W]; weight fp32 [64, 3, 7, 7]; out fp16 NHWC [n, (H-1)//2+1, (W-1)//2+1, 64]."""
+    lib = _lib.load()
+    _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')
+    n, c, h, w = img.shape
+    assert c == 3 and tuple(weight.shape) == (64, 3, 7, 7) and tuple(out.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
+    with _Timed('conv7x7s2_stem', float(img.numel() * 4 + out.numel() * 2)):
+        _lib.check(lib.rpnet_conv7x7s2_stem_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out),
+                                                _stream()), 'rpnet_conv7x7s2_stem_f16')
