@@ -48,6 +48,7 @@ struct LcParams {
   int out_c;
   float scale;
   __half* out;
+  int dbg;
 };
 
 template <int R>
@@ -93,9 +94,9 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         for (int kc = 0; kc < p.chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::NH * 128);
+          mbar_expect_tx(&full_bar[stage], (p.dbg & 4) ? Cfg::kABytes : Cfg::kABytes + Cfg::NH * 128);
           tma_load_4d(&tm_f1, &full_bar[stage], a_dst, kc * 64, x0, y0, n);
-          tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
+          if (!(p.dbg & 4)) tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
           if (++stage == kLcStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -116,6 +117,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
 #pragma unroll
           for (int half = 0; half < Cfg::NPAD / Cfg::NMMA; ++half) {
+            if (p.dbg & 2) break;
             const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + half * Cfg::NMMA * 128, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -150,7 +152,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       // (columns hy*HW .. +HW-1 are that row): hx = j is a static register index, the band test is lane arithmetic
       // two halo rows per step: both TMEM loads are in flight before the (independent) selection code of either row runs
 #pragma unroll 1
-      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; hy += 2) {
+      for (int hy = 4 * q; hy < ((p.dbg & 1) ? 0 : 4 * q + 4 + 2 * R); hy += 2) {
         float v0[32], v1[32];
         tmem_ld32(t_addr + hy * Cfg::HW, v0);
         tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
@@ -210,6 +212,7 @@ static int launch_corr_tc(const void* f1, const void* f2, void* out, int n, int 
   p.out_c = out_c;
   p.scale = 1.0f / sqrtf((float)c);
   p.out = static_cast<__half*>(out);
+  { const char* e = getenv("RPNET_LC_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int tiles = p.tiles_x * p.tiles_y * n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   local_corr_tc_kernel<R><<<grid, kLcThreads, Cfg::kSmemBytes, stream>>>(t1, t2, p);
@@ -250,6 +253,7 @@ struct RhParams {
   int P, sets;
   float cos_scaler;
   float* pred;              // [n][P][h*w]
+  int dbg;
 };
 
 template <int R>
@@ -261,7 +265,8 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_corr = tiles + kLcStages * Cfg::kStageBytes;                     // 2 x [128 rows x 64 K] fp16, K-major SW128
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_corr + 2 * 16384);
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_corr + 2 * 16384);        // [128 rows][65 words]: channel-linear fp16 rows
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stage + 128 * Cfg::kOutPitch);
   uint64_t* empty_bar = full_bar + kLcStages;
   uint64_t* tfull_bar = empty_bar + kLcStages;
   uint64_t* tempty_bar = tfull_bar + 1;
@@ -303,9 +308,9 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         for (int kc = 0; kc < p.chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::NH * 128);
+          mbar_expect_tx(&full_bar[stage], (p.dbg & 4) ? Cfg::kABytes : Cfg::kABytes + Cfg::NH * 128);
           tma_load_4d(&tm_f1, &full_bar[stage], a_dst, kc * 64, x0, y0, n);
-          tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
+          if (!(p.dbg & 4)) tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
           if (++stage == kLcStages) { stage = 0; phase ^= 1; }
         }
         // phase 2, slot A: all f1 chunks of the tile again (the A operand of the fm1 half of the 1x1 conv)
@@ -339,6 +344,7 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
 #pragma unroll
           for (int half = 0; half < Cfg::NPAD / Cfg::NMMA; ++half) {
+            if (p.dbg & 2) break;
             const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + half * Cfg::NMMA * 128, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -362,7 +368,7 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         const uint32_t f1_addr = smem_u32(tiles + sa * Cfg::kStageBytes);
         const uint32_t w_addr = smem_u32(tiles + sb * Cfg::kStageBytes);
         const uint32_t c_addr = smem_u32(s_corr);
-        for (int kc = 0; kc < kq; ++kc) {
+        for (int kc = 0; kc < ((p.dbg & 8) ? 0 : kq); ++kc) {
           const uint64_t a_desc = umma_desc_sw128(kc < 2 ? c_addr + kc * 16384 : f1_addr + (kc - 2) * Cfg::kABytes, 1024);
           const uint64_t b_desc = umma_desc_sw128(w_addr + kc * 8192, 1024);
 #pragma unroll
@@ -378,7 +384,9 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
     const int row = q * 32 + lane;
     const int px = row & (kLcTW - 1), py = row >> 3;
     const uint32_t s_crow = smem_u32(s_corr) + row * 128;
+    const uint32_t s_srow = smem_u32(s_stage + row * Cfg::kOutPitch);
     const int sw = row & 7;
+    for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch) sts_f16(s_srow + 2 * ch, 0.f);   // padding channels [K*K, 128): zero, never rewritten
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -390,26 +398,34 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      // padding channels [K*K, 128) of the corr operand are zero
-#pragma unroll
-      for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch)
-        sts_f16(s_crow + (ch >> 6) * 16384 + ((((ch & 63) >> 3) ^ sw) << 4) + (ch & 7) * 2, 0.f);
+      // band extraction into this lane's private staging row (channel-linear fp16, odd word pitch: conflict-free) ...
 #pragma unroll 1
-      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; hy += 2) {
+      for (int hy = 4 * q; hy < ((p.dbg & 1) ? 0 : 4 * q + 4 + 2 * R); hy += 2) {
         float v0[32], v1[32];
         tmem_ld32(t_addr + hy * Cfg::HW, v0);
         tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
         tmem_ld_wait();
         const unsigned b0 = (unsigned)(hy - py), b1 = b0 + 1u;
+        const uint32_t dst0 = s_srow + 2 * ((int)b0 - px * Cfg::K);   // channel = (j - px) * K + b
         const bool r0 = b0 < (unsigned)Cfg::K, r1 = b1 < (unsigned)Cfg::K;
-        const int off = (int)b0 - px * Cfg::K;                    // channel = j * K + off (+1 for the second row) with a = j - px
 #pragma unroll
         for (int j = 0; j < Cfg::HW; ++j) {
           const bool in = (unsigned)(j - px) < (unsigned)Cfg::K;
-          const int ch0 = j * Cfg::K + off, ch1 = ch0 + 1;
-          if (in && r0) sts_f16(s_crow + (ch0 >> 6) * 16384 + ((((ch0 & 63) >> 3) ^ sw) << 4) + (ch0 & 7) * 2, v0[j] * p.corr_scale);
-          if (in && r1) sts_f16(s_crow + (ch1 >> 6) * 16384 + ((((ch1 & 63) >> 3) ^ sw) << 4) + (ch1 & 7) * 2, v1[j] * p.corr_scale);
+          if (in && r0) sts_f16(dst0 + 2 * j * Cfg::K, v0[j] * p.corr_scale);
+          if (in && r1) sts_f16(dst0 + 2 + 2 * j * Cfg::K, v1[j] * p.corr_scale);
         }
+      }
+      // ... then the row moves into the K-major 128B-swizzled operand tile as 16-byte stores (8 lanes cover the 8 swizzle
+      // phases: conflict-free); the staging row is private to the lane, so program order is the only dependency
+#pragma unroll
+      for (int ck = 0; ck < 16; ++ck) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s_srow + ck * 16) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s_srow + ck * 16 + 4) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s_srow + ck * 16 + 8) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(s_srow + ck * 16 + 12) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_crow + (ck >> 3) * 16384 + (((ck & 7) ^ sw) << 4)), "r"(w0), "r"(w1),
+                     "r"(w2), "r"(w3) : "memory");
       }
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -418,29 +434,37 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       // ---- phase-2 epilogue: affine + ReLU + cosine against the prototypes of this image
       mbar_wait(d2_bar, it & 1);
       tc_fence_after();
+      // D2 leaves TMEM first (64 fp32 per lane) and the accumulator is handed back at once: the affine / cosine math below
+      // overlaps the next tile's correlation MMAs
+      float v[64];
+      if (!(p.dbg & 16)) {
+        tmem_ld32(t_addr, v);
+        tmem_ld32(t_addr + 32, v + 32);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = 0.f;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
       float nn = 0.f, pn[kMaxP], dot[kMaxP];
 #pragma unroll
       for (int k = 0; k < kMaxP; ++k) { pn[k] = 0.f; dot[k] = 0.f; }
       const float* pr_base = p.protos + (size_t)(n % p.sets) * p.P * 64;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
+      for (int j = 0; j < 64; ++j) {
+        v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + j), __ldg(p.shift + j)), 0.f);
+        nn = fmaf(v[j], v[j], nn);
+      }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = fmaxf(fmaf(v[j], __ldg(p.scale + c0 + j), __ldg(p.shift + c0 + j)), 0.f);
-          nn = fmaf(v[j], v[j], nn);
-        }
+      for (int k = 0; k < kMaxP; ++k) {
+        if (k < p.P) {
 #pragma unroll
-        for (int k = 0; k < kMaxP; ++k) {
-          if (k < p.P) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 pr = __ldg(reinterpret_cast<const float4*>(pr_base + k * 64 + c0 + j));
-              dot[k] = fmaf(v[j], pr.x, fmaf(v[j + 1], pr.y, fmaf(v[j + 2], pr.z, fmaf(v[j + 3], pr.w, dot[k]))));
-              pn[k] = fmaf(pr.x, pr.x, fmaf(pr.y, pr.y, fmaf(pr.z, pr.z, fmaf(pr.w, pr.w, pn[k]))));
-            }
+          for (int j = 0; j < 64; j += 4) {
+            const float4 pr = __ldg(reinterpret_cast<const float4*>(pr_base + k * 64 + j));
+            dot[k] = fmaf(v[j], pr.x, fmaf(v[j + 1], pr.y, fmaf(v[j + 2], pr.z, fmaf(v[j + 3], pr.w, dot[k]))));
+            pn[k] = fmaf(pr.x, pr.x, fmaf(pr.y, pr.y, fmaf(pr.z, pr.z, fmaf(pr.w, pr.w, pn[k]))));
           }
         }
       }
@@ -451,9 +475,6 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         for (int k = 0; k < kMaxP; ++k)
           if (k < p.P) p.pred[((size_t)n * p.P + k) * hw + (size_t)y * p.W + x] = p.cos_scaler * (dot[k] / (xn * fmaxf(sqrtf(pn[k]), 1e-8f)));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
     }
   }
   tc_fence_before();
@@ -469,7 +490,7 @@ static int launch_relation_head(const void* f1, const void* f2, const void* wq, 
                                 const float* protos, int P, int sets, float cos_scaler, float* pred, int n, int h, int w, int c,
                                 cudaStream_t stream) {
   using Cfg = LcCfg<R>;
-  constexpr int kSmem = kLcStages * Cfg::kStageBytes + 2 * 16384 + 1024 + 256;
+  constexpr int kSmem = kLcStages * Cfg::kStageBytes + 2 * 16384 + 128 * Cfg::kOutPitch * 4 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     RPNET_CUDA_OK(cudaFuncSetAttribute(relation_head_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
@@ -497,6 +518,7 @@ static int launch_relation_head(const void* f1, const void* f2, const void* wq, 
   p.tiles_x = (w + kLcTW - 1) / kLcTW; p.tiles_y = (h + kLcTH - 1) / kLcTH;
   p.corr_scale = 1.0f / sqrtf((float)c);
   p.scale = scale; p.shift = shift; p.protos = protos; p.P = P; p.sets = sets; p.cos_scaler = cos_scaler; p.pred = pred;
+  { const char* e = getenv("RPNET_LC_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int tiles = p.tiles_x * p.tiles_y * n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   relation_head_kernel<R><<<grid, kLcThreads, kSmem, stream>>>(t1, t2, tw, p);

@@ -468,68 +468,109 @@ cos_sim_kernel(const float* __restrict__ feat, const float* __restrict__ protos,
 // ---------------------------------------------------------------------------------------------------
 // Refinement tail (net/rp_net.py:303-312): bilinear upsample xS (align_corners=False) of the
 // (1+Wa)-class prediction -> logits (kept: refinement[i]) -> softmax fg probability -> (>0.5 | soft)
-// -> avg_pool2d(S) -> next query mask.  One thread per S x S output block (= one pooled mask pixel).
+// -> avg_pool2d(S) -> next query mask.  One thread per output row segment of S pixels: warp dy of the block owns row dy of 32
+// consecutive S x S blocks (a warp stores 32 * S * 4 contiguous bytes per class), the S row sums of a block meet in shared
+// memory.  The six source values a segment can touch (3 columns x 2 rows) are loaded once per class.
 // pred fp32 [B][P][h][w]; logits fp32 [B][P][h*S][w*S]; mask_out fp32 [B][h][w].
 // ---------------------------------------------------------------------------------------------------
 template <int S>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * S)
 upsample_tail_kernel(const float* __restrict__ pred, float* __restrict__ logits, float* __restrict__ mask_out, int B, int P, int h,
                      int w, int soft) {
+  __shared__ float s_row[S][32];
   const int H = h * S, W = w * S;
   const long long total = (long long)B * h * w;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int j = (int)(idx % w), i = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
-  const float rs = 1.f / (float)S;
+  const int lane = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const long long idx = (long long)blockIdx.x * 32 + lane;
+  const bool ok = idx < total;
   float msum = 0.f;
-#pragma unroll 1
-  for (int dy = 0; dy < S; ++dy) {
+  if (ok) {
+    const int j = (int)(idx % w), i = (int)((idx / w) % h), b = (int)(idx / ((long long)w * h));
+    // exact xS upsample, align_corners=False (ATen area_pixel_compute_source_index): output d of block j reads
+    // src = j + f(d), f(d) = (d + 0.5) / S - 0.5: f < 0 -> (j-1, j) with weights (-f, 1 + f), else (j, j+1) with (1 - f, f);
+    // the clamp at 0 makes the first half of block 0 read (src[0], src[1]) with weights (1, 0).  All weights are exact in fp32.
+    const float fy = ((float)dy + 0.5f) / (float)S - 0.5f;
+    const bool up = fy < 0.f;
+    const int i0 = up ? (i > 0 ? i - 1 : 0) : i;
+    const int i1 = up ? (i > 0 ? i : (h > 1 ? 1 : 0)) : (i < h - 1 ? i + 1 : h - 1);
+    const float ly1 = up ? (i > 0 ? 1.f + fy : 0.f) : fy, ly0 = 1.f - ly1;
+    const int jm = j > 0 ? j - 1 : 0, jp = j < w - 1 ? j + 1 : w - 1;
+    const bool left = j == 0;
     const int Y = i * S + dy;
-    int i0, i1; float ly0, ly1;
-    bilinear_src(Y, rs, h, i0, i1, ly0, ly1);
-    float mx[S], den[S], fg[S];
-#pragma unroll
-    for (int dx = 0; dx < S; ++dx) { mx[dx] = -INFINITY; den[dx] = 0.f; fg[dx] = 0.f; }
     float val[kMaxProtos][S];
 #pragma unroll
     for (int p = 0; p < kMaxProtos; ++p) {
       if (p < P) {
         const float* src = pred + ((size_t)b * P + p) * h * w;
+        const float a0 = __ldg(src + i0 * w + jm), a1 = __ldg(src + i0 * w + j), a2 = __ldg(src + i0 * w + jp);
+        const float c0 = __ldg(src + i1 * w + jm), c1 = __ldg(src + i1 * w + j), c2 = __ldg(src + i1 * w + jp);
 #pragma unroll
         for (int dx = 0; dx < S; ++dx) {
-          const int X = j * S + dx;
-          int j0, j1; float lx0, lx1;
-          bilinear_src(X, rs, w, j0, j1, lx0, lx1);
-          const float v = ly0 * (lx0 * __ldg(src + i0 * w + j0) + lx1 * __ldg(src + i0 * w + j1)) +
-                          ly1 * (lx0 * __ldg(src + i1 * w + j0) + lx1 * __ldg(src + i1 * w + j1));
+          constexpr float inv = 1.f / (float)S;
+          const float fx = ((float)dx + 0.5f) * inv - 0.5f;          // compile-time per dx
+          float v;
+          if (dx < S / 2) {
+            const float lx1 = left ? 0.f : 1.f + fx, lx0 = 1.f - lx1;
+            const float t0 = left ? a1 : a0, t1 = left ? a2 : a1, u0 = left ? c1 : c0, u1 = left ? c2 : c1;
+            v = ly0 * (lx0 * t0 + lx1 * t1) + ly1 * (lx0 * u0 + lx1 * u1);
+          } else {
+            v = ly0 * ((1.f - fx) * a1 + fx * a2) + ly1 * ((1.f - fx) * c1 + fx * c2);
+          }
           val[p][dx] = v;
-          mx[dx] = fmaxf(mx[dx], v);
         }
         float* dst = logits + (((size_t)b * P + p) * H + Y) * W + (size_t)j * S;
 #pragma unroll
         for (int dx = 0; dx < S; dx += 4)
-          *reinterpret_cast<float4*>(dst + dx) = make_float4(val[p][dx], val[p][dx + 1], val[p][dx + 2], val[p][dx + 3]);
+          __stcs(reinterpret_cast<float4*>(dst + dx), make_float4(val[p][dx], val[p][dx + 1], val[p][dx + 2], val[p][dx + 3]));
       }
     }
+    // softmax(dim=1)[:, 1] for Wa == 1 (sum over the fg classes for Wa > 1: oracle-ext)
+    if (P == 2) {
+      // two classes: the larger logit contributes exp(0) = 1, so one expf and one division per pixel give the same bits
 #pragma unroll
-    for (int p = 0; p < kMaxProtos; ++p) {
-      if (p < P) {
+      for (int dx = 0; dx < S; ++dx) {
+        const float d = val[1][dx] - val[0][dx];
+        const float e = expf(-fabsf(d));
+        const float den = 1.f + e;
+        const float prob = (d > 0.f ? 1.f : e) / den;
+        msum += soft ? prob : (prob > 0.5f ? 1.f : 0.f);
+      }
+    } else {
+      float mx[S], den[S], fg[S];
 #pragma unroll
-        for (int dx = 0; dx < S; ++dx) {
-          const float e = expf(val[p][dx] - mx[dx]);
-          den[dx] += e;
-          if (p >= 1) fg[dx] += e;
+      for (int dx = 0; dx < S; ++dx) { mx[dx] = -INFINITY; den[dx] = 0.f; fg[dx] = 0.f; }
+#pragma unroll
+      for (int p = 0; p < kMaxProtos; ++p)
+        if (p < P) {
+#pragma unroll
+          for (int dx = 0; dx < S; ++dx) mx[dx] = fmaxf(mx[dx], val[p][dx]);
+        }
+#pragma unroll
+      for (int p = 0; p < kMaxProtos; ++p) {
+        if (p < P) {
+#pragma unroll
+          for (int dx = 0; dx < S; ++dx) {
+            const float e = expf(val[p][dx] - mx[dx]);
+            den[dx] += e;
+            if (p >= 1) fg[dx] += e;
+          }
         }
       }
-    }
 #pragma unroll
-    for (int dx = 0; dx < S; ++dx) {
-      // softmax(dim=1)[:, 1] for Wa == 1 (sum over fg classes for Wa > 1: oracle-ext)
-      const float prob = fg[dx] / den[dx];
-      msum += soft ? prob : (prob > 0.5f ? 1.f : 0.f);
+      for (int dx = 0; dx < S; ++dx) {
+        const float prob = fg[dx] / den[dx];
+        msum += soft ? prob : (prob > 0.5f ? 1.f : 0.f);
+      }
     }
   }
-  mask_out[idx] = msum / (float)(S * S);
+  s_row[dy][lane] = msum;
+  __syncthreads();
+  if (dy == 0 && ok) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < S; ++k) t += s_row[k][lane];
+    mask_out[idx] = t / (float)(S * S);
+  }
 }
 
 
@@ -729,11 +770,11 @@ RPNET_API int rpnet_upsample_tail_f32(const float* pred, float* logits, float* m
   RPNET_REQUIRE(n_protos >= 2 && n_protos <= kMaxProtos, "upsample_tail: n_protos %d out of range [2, %d]", n_protos, kMaxProtos);
   RPNET_REQUIRE(batch > 0 && h > 0 && w > 0, "upsample_tail: bad shape");
   const long long total = (long long)batch * h * w;
-  const int grid = (int)((total + 127) / 128);
+  const int grid = (int)((total + 31) / 32);
   if (scale == 4)
     upsample_tail_kernel<4><<<grid, 128, 0, stream>>>(pred, logits, mask_out, batch, n_protos, h, w, soft_mask);
   else if (scale == 8)
-    upsample_tail_kernel<8><<<grid, 128, 0, stream>>>(pred, logits, mask_out, batch, n_protos, h, w, soft_mask);
+    upsample_tail_kernel<8><<<grid, 256, 0, stream>>>(pred, logits, mask_out, batch, n_protos, h, w, soft_mask);
   else {
     set_error("upsample_tail: scale %d not supported (4 or 8)", scale);
     return RPNET_ERR_ARG;
