@@ -48,7 +48,6 @@ struct LcParams {
   int out_c;
   float scale;
   __half* out;
-  int dbg;
 };
 
 template <int R>
@@ -94,9 +93,9 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         for (int kc = 0; kc < p.chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], (p.dbg & 4) ? Cfg::kABytes : Cfg::kABytes + Cfg::NH * 128);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::NH * 128);
           tma_load_4d(&tm_f1, &full_bar[stage], a_dst, kc * 64, x0, y0, n);
-          if (!(p.dbg & 4)) tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
+          tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
           if (++stage == kLcStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -117,7 +116,6 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
 #pragma unroll
           for (int half = 0; half < Cfg::NPAD / Cfg::NMMA; ++half) {
-            if (p.dbg & 2) break;
             const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + half * Cfg::NMMA * 128, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -152,7 +150,7 @@ local_corr_tc_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       // (columns hy*HW .. +HW-1 are that row): hx = j is a static register index, the band test is lane arithmetic
       // two halo rows per step: both TMEM loads are in flight before the (independent) selection code of either row runs
 #pragma unroll 1
-      for (int hy = 4 * q; hy < ((p.dbg & 1) ? 0 : 4 * q + 4 + 2 * R); hy += 2) {
+      for (int hy = 4 * q; hy < 4 * q + 4 + 2 * R; hy += 2) {
         float v0[32], v1[32];
         tmem_ld32(t_addr + hy * Cfg::HW, v0);
         tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
@@ -212,7 +210,6 @@ static int launch_corr_tc(const void* f1, const void* f2, void* out, int n, int 
   p.out_c = out_c;
   p.scale = 1.0f / sqrtf((float)c);
   p.out = static_cast<__half*>(out);
-  { const char* e = getenv("RPNET_LC_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int tiles = p.tiles_x * p.tiles_y * n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   local_corr_tc_kernel<R><<<grid, kLcThreads, Cfg::kSmemBytes, stream>>>(t1, t2, p);
@@ -253,11 +250,12 @@ struct RhParams {
   int P, sets;
   float cos_scaler;
   float* pred;              // [n][P][h*w]
-  int dbg;
 };
 
+constexpr int kRhThreads = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9: two epilogue warps per TMEM lane quarter
+
 template <int R>
-__global__ void __launch_bounds__(kLcThreads, 1)
+__global__ void __launch_bounds__(kRhThreads, 1)
 relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_constant__ CUtensorMap tm_f2,
                      const __grid_constant__ CUtensorMap tm_w, const RhParams p) {
   using Cfg = LcCfg<R>;
@@ -308,9 +306,9 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         for (int kc = 0; kc < p.chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], (p.dbg & 4) ? Cfg::kABytes : Cfg::kABytes + Cfg::NH * 128);
+          mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::NH * 128);
           tma_load_4d(&tm_f1, &full_bar[stage], a_dst, kc * 64, x0, y0, n);
-          if (!(p.dbg & 4)) tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
+          tma_load_4d(&tm_f2, &full_bar[stage], a_dst + Cfg::kABytes, kc * 64, x0 - R, y0 - R, n);
           if (++stage == kLcStages) { stage = 0; phase ^= 1; }
         }
         // phase 2, slot A: all f1 chunks of the tile again (the A operand of the fm1 half of the 1x1 conv)
@@ -344,7 +342,6 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
 #pragma unroll
           for (int half = 0; half < Cfg::NPAD / Cfg::NMMA; ++half) {
-            if (p.dbg & 2) break;
             const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + half * Cfg::NMMA * 128, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -368,7 +365,7 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
         const uint32_t f1_addr = smem_u32(tiles + sa * Cfg::kStageBytes);
         const uint32_t w_addr = smem_u32(tiles + sb * Cfg::kStageBytes);
         const uint32_t c_addr = smem_u32(s_corr);
-        for (int kc = 0; kc < ((p.dbg & 8) ? 0 : kq); ++kc) {
+        for (int kc = 0; kc < kq; ++kc) {
           const uint64_t a_desc = umma_desc_sw128(kc < 2 ? c_addr + kc * 16384 : f1_addr + (kc - 2) * Cfg::kABytes, 1024);
           const uint64_t b_desc = umma_desc_sw128(w_addr + kc * 8192, 1024);
 #pragma unroll
@@ -381,12 +378,15 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
     }
   } else {
     const int q = warp & 3;
+    const int part = (warp - 2) >> 2;                        // the two warps of a lane quarter split the halo rows and the chunks
     const int row = q * 32 + lane;
     const int px = row & (kLcTW - 1), py = row >> 3;
     const uint32_t s_crow = smem_u32(s_corr) + row * 128;
     const uint32_t s_srow = smem_u32(s_stage + row * Cfg::kOutPitch);
     const int sw = row & 7;
-    for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch) sts_f16(s_srow + 2 * ch, 0.f);   // padding channels [K*K, 128): zero, never rewritten
+    if (part == 0)
+      for (int ch = Cfg::K * Cfg::K; ch < 128; ++ch) sts_f16(s_srow + 2 * ch, 0.f);   // padding channels [K*K, 128): zero, never rewritten
+    constexpr int kSteps = (4 + 2 * R + 1) / 2, kSteps0 = (kSteps + 1) / 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
@@ -398,9 +398,10 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
       mbar_wait(tfull_bar, it & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      // band extraction into this lane's private staging row (channel-linear fp16, odd word pitch: conflict-free) ...
+      // band extraction into the pixel's staging row (channel-linear fp16, odd word pitch: conflict-free) ...
+      const int hy_lo = 4 * q + (part ? 2 * kSteps0 : 0), hy_hi = 4 * q + (part ? 4 + 2 * R : 2 * kSteps0);
 #pragma unroll 1
-      for (int hy = 4 * q; hy < ((p.dbg & 1) ? 0 : 4 * q + 4 + 2 * R); hy += 2) {
+      for (int hy = hy_lo; hy < hy_hi; hy += 2) {
         float v0[32], v1[32];
         tmem_ld32(t_addr + hy * Cfg::HW, v0);
         tmem_ld32(t_addr + (hy + 1) * Cfg::HW, v1);
@@ -415,36 +416,34 @@ relation_head_kernel(const __grid_constant__ CUtensorMap tm_f1, const __grid_con
           if (in && r1) sts_f16(dst0 + 2 + 2 * j * Cfg::K, v1[j] * p.corr_scale);
         }
       }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // both halves of every staging row are written
       // ... then the row moves into the K-major 128B-swizzled operand tile as 16-byte stores (8 lanes cover the 8 swizzle
-      // phases: conflict-free); the staging row is private to the lane, so program order is the only dependency
+      // phases: conflict-free); each warp of the pair moves one 64-channel K block
 #pragma unroll
-      for (int ck = 0; ck < 16; ++ck) {
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const int ck = part * 8 + c8;
         uint32_t w0, w1, w2, w3;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(s_srow + ck * 16) : "memory");
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(s_srow + ck * 16 + 4) : "memory");
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w2) : "r"(s_srow + ck * 16 + 8) : "memory");
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w3) : "r"(s_srow + ck * 16 + 12) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_crow + (ck >> 3) * 16384 + (((ck & 7) ^ sw) << 4)), "r"(w0), "r"(w1),
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(s_crow + part * 16384 + ((c8 ^ sw) << 4)), "r"(w0), "r"(w1),
                      "r"(w2), "r"(w3) : "memory");
       }
-      tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 64) mbar_arrive(corr_bar);
+      if (part) continue;                                     // the second warp of the pair goes on to wait for the next tile
       // ---- phase-2 epilogue: affine + ReLU + cosine against the prototypes of this image
       mbar_wait(d2_bar, it & 1);
       tc_fence_after();
       // D2 leaves TMEM first (64 fp32 per lane) and the accumulator is handed back at once: the affine / cosine math below
       // overlaps the next tile's correlation MMAs
       float v[64];
-      if (!(p.dbg & 16)) {
-        tmem_ld32(t_addr, v);
-        tmem_ld32(t_addr + 32, v + 32);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = 0.f;
-      }
+      tmem_ld32(t_addr, v);
+      tmem_ld32(t_addr + 32, v + 32);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar);
@@ -518,10 +517,9 @@ static int launch_relation_head(const void* f1, const void* f2, const void* wq, 
   p.tiles_x = (w + kLcTW - 1) / kLcTW; p.tiles_y = (h + kLcTH - 1) / kLcTH;
   p.corr_scale = 1.0f / sqrtf((float)c);
   p.scale = scale; p.shift = shift; p.protos = protos; p.P = P; p.sets = sets; p.cos_scaler = cos_scaler; p.pred = pred;
-  { const char* e = getenv("RPNET_LC_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int tiles = p.tiles_x * p.tiles_y * n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  relation_head_kernel<R><<<grid, kLcThreads, kSmem, stream>>>(t1, t2, tw, p);
+  relation_head_kernel<R><<<grid, kRhThreads, kSmem, stream>>>(t1, t2, tw, p);
   return check_cuda(cudaGetLastError(), "relation_head launch");
 }
 
