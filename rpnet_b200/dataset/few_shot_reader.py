@@ -1,0 +1,263 @@
+"""Episode builder for the eval driver ("next" row N4 of SURVEY §8f): the three nested readers of
+dataset/few_shot_reader.py restated for `mode='eval'`.
+
+    FewshotVolumeReader  (:233-409)  class CSVs -> (query volume, support volume) pairs; NRRD load, centre truncate,
+                                     pad to a multiple of 16, keep the annotated z range, centre crop/pad, HU normalise
+    FewshotSliceReader   (:448-589)  k-block slice matching: the query volume is cut into k z-blocks, every slice of block
+                                     j is paired with the support slice at the centre of the support's block j
+    FewshotRegReader     (:592-650)  per-slice registration of the support onto the query -> `appr_query_labels`, the
+                                     affine-warped support image/label the network consumes
+
+The item dicts carry the reference's keys, shapes and dtypes, and its quirks are kept because they change what the
+network sees (the last annotated slice is dropped, :21-27; only the last support volume and shot 0 survive the eval
+branch, :523-548; `k` shrinks persistently, :466; the label pad of make_support_query_same_size uses shape[1] twice,
+:101-104).  What differs is where the time goes: the reference registers slice by slice on the CPU inside __getitem__
+(50 Adam iterations of tiny ops each, :121-188); here all slices of the volume are registered by one kernel launch and the
+registration outputs stay on the device (`.cuda()` in the caller is then a no-op).
+
+`mode='train'` is not built: its augmentation calls `transforms.RandomAffine(..., fillcolor=None)` (:30-31), a keyword
+torchvision removed, so the reference's own train branch cannot run against the torchvision of this image and there is
+nothing to pin it to.  `do_deformable: True` raises NotImplementedError (rpnet_b200/registration.py)."""
+import csv
+import math
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import nrrd_io
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# volume preprocessing (utils/util.py:406-419,455-467; dataset/few_shot_reader.py:18-27,61-74,395-409)
+# ---------------------------------------------------------------------------------------------------------------------
+def pad2factor(volume, factor=16, pad_value=0):
+    """utils/util.py:406-419: pad D, H, W up to the next multiple of `factor` at the far end."""
+    pad = [(0, int(math.ceil(n / float(factor))) * factor - n) for n in volume.shape]
+    return np.pad(volume, pad, 'constant', constant_values=pad_value)
+
+
+def normalize(img, minimum=-1024, maximum=3076):
+    """utils/util.py:455-467: clip at the 99.5th percentile and at [minimum, maximum], map to [-1, 1]."""
+    img = np.array(img, copy=True)
+    hi = float(np.percentile(img, 100.0 - 0.5))
+    img[img > hi] = hi
+    img[img > maximum] = maximum
+    img[img < minimum] = minimum
+    img = (img - minimum) / max(1, (maximum - minimum))
+    return img * 2 - 1
+
+
+def keep_only_annotation_z_slices(img, mask):
+    """:18-27 — the slice range [first annotated, last annotated): the last annotated slice is dropped, as there."""
+    zs = np.where(mask)[1]
+    lo, hi = zs.min(), zs.max()
+    return img[:, lo:hi], mask[:, lo:hi]
+
+
+def crop(img, mask, crop_size, img_pad_value, mask_pad_value=0):
+    """:61-74 — centre crop to at most crop_size, then centre pad up to crop_size."""
+    h, w = mask.shape[2:]
+    ch, cw = crop_size
+    rh, rw = min(ch, h), min(cw, w)
+    y0, x0 = h // 2 - rh // 2, w // 2 - rw // 2
+    window = (Ellipsis, slice(y0, y0 + rh), slice(x0, x0 + rw))
+    pad = [(0, 0), (0, 0), ((ch - rh) // 2, (ch - rh) - (ch - rh) // 2), ((cw - rw) // 2, (cw - rw) - (cw - rw) // 2)]
+    return (np.pad(img[window], pad, 'constant', constant_values=img_pad_value),
+            np.pad(mask[window], pad, 'constant', constant_values=mask_pad_value))
+
+
+def make_support_query_same_size(support_images, support_labels, query_images, query_labels):
+    """:77-106 — pad support and query slices (bottom / right, with each array's minimum) to a common H x W.
+    1-way 1-shot: only support_images[0][0] / support_labels[0][0] are used."""
+    s_img, s_lab = support_images[0][0].numpy(), support_labels[0][0].numpy()
+    q_img, q_lab = query_images.numpy(), query_labels.numpy()
+    H, W = max(s_img.shape[2], q_img.shape[2]), max(s_img.shape[3], q_img.shape[3])
+
+    def pad_img(a):
+        return np.pad(a, [(0, 0), (0, 0), (0, H - a.shape[2]), (0, W - a.shape[3])], 'constant', constant_values=a.min())
+
+    def pad_lab(a):                                     # the reference subtracts shape[1] from W as well (:101,103)
+        return np.pad(a, [(0, 0), (0, H - a.shape[1]), (0, W - a.shape[1])], 'constant', constant_values=a.min())
+    return ([[torch.from_numpy(pad_img(s_img))]], [[torch.from_numpy(pad_lab(s_lab))]], torch.from_numpy(pad_img(q_img)),
+            torch.from_numpy(pad_lab(q_lab)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class FewshotVolumeReader(torch.utils.data.Dataset):
+    """:233-409.  `config` keys: class_csv_dir, eval_classes (train_classes), n_shot, n_way, num_slice, num_x, num_y,
+    pad_value, HU_range, crop_size (default [256, 256])."""
+
+    def __init__(self, data_dir, set_name, config, mode='eval'):
+        self.data_dir, self.cfg, self.mode = data_dir, config, mode
+        self.class_csv_dir = config['class_csv_dir']
+        if set_name.endswith('.csv'):
+            with open(set_name) as fh:
+                self.filenames = np.array([ln.strip() for ln in fh if ln.strip()], dtype=str)
+        elif set_name.endswith('.npy'):
+            self.filenames = np.load(set_name)
+        else:
+            raise ValueError('set_name must be a .csv or .npy list of patient ids (got %r)' % set_name)
+        if mode == 'train':
+            self.classes = config['train_classes']
+        elif mode == 'eval':
+            self.classes = config['eval_classes']
+        else:
+            raise NotImplementedError(mode)
+        self.read_data_meta()
+        self.init_pairs()
+
+    def read_data_meta(self):
+        """:364-383 — per class, the rows of <class_csv_dir>/<class>.csv whose pid is in the split, in file order."""
+        wanted = set(str(f) for f in self.filenames)
+        self.data_info, self.n_data = [], []
+        for roi in self.classes:
+            with open(os.path.join(self.class_csv_dir, '%s.csv' % roi), newline='') as fh:
+                rows = [{'pid': r['pid'], 'z_start': r['z_start'], 'z_end': r['z_end']} for r in csv.DictReader(fh)
+                        if r['pid'] in wanted]
+            self.data_info.append(rows)
+            self.n_data.append(len(rows))
+
+    def init_pairs(self):
+        self.indices = [(c, d) for c in range(len(self.classes)) for d in range(self.n_data[c])]
+
+    def __len__(self):
+        return len(self.indices)
+
+    def truncate_image(self, image):
+        """:395-409 — first num_slice slices, centre window of num_y x num_x."""
+        _, H, W = image.shape
+        nz, nx, ny = self.cfg['num_slice'], self.cfg['num_x'], self.cfg['num_y']
+        x1, x2 = max(0, W // 2 - nx // 2), min(W, W // 2 + nx // 2)
+        y1, y2 = max(0, H // 2 - ny // 2), min(H, H // 2 + ny // 2)
+        return image[:nz, y1:y2, x1:x2]
+
+    def load_image_and_mask(self, pid, roi_name):
+        """:325-346 — <pid>_<roi>.nrrd (mask) and <pid>_clean.nrrd (CT, HU), both [D, H, W] -> [1, D', h, w] float32."""
+        mask, _ = nrrd_io.read(os.path.join(self.data_dir, '%s_%s.nrrd' % (pid, roi_name)))
+        mask = pad2factor(self.truncate_image(mask.astype(np.float32)), factor=16, pad_value=0)[None]
+        imgs, _ = nrrd_io.read(os.path.join(self.data_dir, '%s_clean.nrrd' % pid))
+        imgs = pad2factor(self.truncate_image(imgs), factor=16, pad_value=self.cfg['pad_value'])[None].astype(np.float32)
+        imgs, mask = keep_only_annotation_z_slices(imgs, mask)
+        imgs, mask = crop(imgs, mask, self.cfg.get('crop_size', [256, 256]), self.cfg.get('pad_value', -1024), 0)
+        imgs = normalize(imgs, minimum=self.cfg['HU_range'][0], maximum=self.cfg['HU_range'][1])
+        return {'image': imgs, 'mask': mask}
+
+    def __getitem__(self, idx, supp_idx=None):
+        """:253-322 — query = item idx; supports = n_shot other volumes of the same class drawn with random.choices (the
+        module-level `random` state, as in the reference), or volume `supp_idx` when given."""
+        n_shots, n_ways = self.cfg['n_shot'], self.cfg['n_way']
+        c, d = self.indices[idx]
+        others = [i for i in range(self.n_data[c]) if i != d]
+        support_idx = [(c, i) for i in random.choices(others, k=n_shots)]
+        if supp_idx is not None:
+            support_idx = [(c, supp_idx)]
+        shots = [self.load_image_and_mask(self.data_info[ci][di]['pid'], self.classes[ci]) for ci, di in support_idx]
+        support_images = [[torch.from_numpy(shots[j]['image']) for j in range(n_shots)] for _ in range(n_ways)]
+        support_labels = [[torch.from_numpy(shots[j]['mask']) for j in range(n_shots)] for _ in range(n_ways)]
+        qry = self.load_image_and_mask(self.data_info[c][d]['pid'], self.classes[c])
+        return {'support_images': support_images, 'support_labels': support_labels,
+                'query_images': [[torch.from_numpy(qry['image'])]], 'query_labels': [[torch.from_numpy(qry['mask'])]],
+                'class_id': c, 'pid': self.data_info[c][d]['pid'], 'supp_pids': support_idx}
+
+
+class FewshotSliceReader(torch.utils.data.Dataset):
+    """:448-589, eval branch.  Extra config keys: k, test_shot, use_registration_loss, use_registration_mask, do_deformable."""
+
+    def __init__(self, data_dir, set_name, config, mode='eval'):
+        if mode != 'eval':
+            raise NotImplementedError("FewshotSliceReader: only mode='eval' is built (see the module docstring)")
+        self.cfg, self.k, self.mode = config, config['k'], mode
+        self.fewshot_volume_reader = FewshotVolumeReader(data_dir, set_name, config, mode=mode)
+
+    def __len__(self):
+        return len(self.fewshot_volume_reader)
+
+    @staticmethod
+    def slice_blocks(num_slices, k):
+        """:467-472 — centre slice of each of the k support blocks, and the k+1 query block boundaries."""
+        support = [np.floor(np.arange(n / k / 2, n, n / k)).astype(np.int32) for n in num_slices[:-1]]
+        nq = num_slices[-1]
+        query = np.floor(np.array(np.arange(0, nq, nq / k).tolist() + [nq])).astype(np.int32)
+        return support, query
+
+    def __getitem__(self, idx):
+        vol = self.fewshot_volume_reader[idx]
+        support_images, support_labels = vol['support_images'], vol['support_labels']
+        query_images, query_labels = vol['query_images'], vol['query_labels']
+        assert len(support_images) == 1
+        num_slices = [v.shape[1] for v in support_images[0]] + [v.shape[1] for v in query_images[0]]
+        self.k = min([self.k] + num_slices)                                     # persists across items, as in :466
+        k = self.k
+        s_idx, q_idx = self.slice_blocks(num_slices, k)
+        test_shot = self.cfg.get('test_shot', self.cfg['n_shot'])
+        new_query_images = query_images[0][0].permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1)
+        new_query_labels = query_labels[0][0][0]
+        for i in range(len(support_images[0])):                                # the last support volume wins (:523-548)
+            vol_i, lab_i = support_images[0][i], support_labels[0][i]
+            per_shot_img, per_shot_lab = [], []
+            for m in range(test_shot):
+                imgs, labs = [], []
+                for j in range(k):
+                    n = int(q_idx[j + 1] - q_idx[j])
+                    z = int(s_idx[i][j + (0 if j + m >= k else m)])
+                    imgs.append(vol_i[:, [z]].expand(n, 3, -1, -1))
+                    labs.append(lab_i[0, [z]].expand(n, -1, -1))
+                per_shot_img.append(torch.cat(imgs, dim=0).unsqueeze(0))
+                per_shot_lab.append(torch.cat(labs, dim=0).unsqueeze(0))
+            shot_images, shot_labels = torch.cat(per_shot_img, dim=0), torch.cat(per_shot_lab, dim=0)
+        new_support_images, new_support_labels, new_query_images, new_query_labels = make_support_query_same_size(
+            [shot_images], [shot_labels], new_query_images, new_query_labels)
+
+        if self.cfg.get('use_registration_loss', False):
+            from .. import registration
+            field, reg_pred, warped_src, affine_reg_pred, affine_warped_src = registration.get_registration_field(
+                new_query_images, new_support_images, new_support_labels, do_deformable=self.cfg.get('do_deformable', True))
+            if self.cfg.get('use_registration_mask', False):
+                new_support_images[0][0] = torch.cat((new_support_images[0][0], new_support_labels[0][0][:, None]), dim=1)
+                new_query_images = torch.cat((new_query_images.to(reg_pred.device), reg_pred), dim=1)
+        else:
+            field, reg_pred, affine_reg_pred = None, None, None
+            warped_src = affine_warped_src = new_support_images[0][0]
+        return {'support_images': new_support_images, 'support_labels': new_support_labels,
+                'query_images': new_query_images, 'query_labels': new_query_labels, 'class_id': vol['class_id'],
+                'registration_field': field,
+                'support_images_3D': vol['support_images'], 'support_labels_3D': vol['support_labels'],
+                'query_images_3D': vol['query_images'], 'query_labels_3D': vol['query_labels'],
+                'warped_supp': warped_src, 'warped_supp_label': reg_pred,
+                'affine_warped_supp': affine_warped_src, 'affine_warped_supp_label': affine_reg_pred,
+                'pid': vol['pid'], 'supp_pids': vol['supp_pids']}
+
+
+class FewshotRegReader(torch.utils.data.Dataset):
+    """:592-650 — the dataset test_rpnet.py:70 builds.  Needs `use_registration_loss: True` (as the reference does: it
+    indexes the registration outputs unconditionally)."""
+
+    def __init__(self, data_dir, set_name, config, mode='eval'):
+        self.config, self.mode = config, mode
+        self.fewshot_reader = FewshotSliceReader(data_dir, set_name, config, mode=mode)
+
+    def __len__(self):
+        return len(self.fewshot_reader)
+
+    def __getitem__(self, idx):
+        data = self.fewshot_reader[idx]
+        if data['registration_field'] is None:
+            raise TypeError("FewshotRegReader needs config['use_registration_loss'] = True")
+        grids = torch.cat([g for _, g in data['registration_field']], dim=0)
+        return {'support_images': [[data['affine_warped_supp'].unsqueeze(1)]],
+                'support_labels': [[data['affine_warped_supp_label'][:, 0]]],
+                'query_images': data['query_images'][:, [0]], 'query_labels': data['query_labels'],
+                'appr_query_labels': (data['warped_supp_label'][:, 0] > 0.5).float(),
+                'class_id': data['class_id'], 'registration_field': data['registration_field'],
+                'support_images_3D': data['support_images_3D'], 'support_labels_3D': data['support_labels_3D'],
+                'query_images_3D': data['query_images_3D'], 'query_labels_3D': data['query_labels_3D'],
+                'grid': grids, 'original_support_images': data['support_images'],
+                'original_support_labels': data['support_labels'], 'warped_supp': data['warped_supp'],
+                'pid': data['pid'], 'supp_pids': data['supp_pids']}
+
+
+def train_collate(batch):
+    """:653-654"""
+    return batch[0]

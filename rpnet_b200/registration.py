@@ -43,3 +43,49 @@ def get_affine_registration(query_images, support_images, support_labels, iters=
     warped_label = (affine_warp(lab, theta) > 0.1).float()                    # :171-172
     warped_src = affine_warp(src[:, None], theta)[:, 0] * 2 - 1               # :178-179, :196
     return theta, warped_label, warped_src
+
+
+def compute_grid(img_size, device=None):
+    """net/registration.py:171-186: the identity sampling grid [1, 2, H, W] (x first), normalised as 2 * (i / (n - 1) - 0.5)."""
+    h, w = int(img_size[0]), int(img_size[1])
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=device), torch.arange(w, dtype=torch.float32, device=device),
+                            indexing='ij')
+    return torch.stack([2 * (xs / (w - 1) - 0.5), 2 * (ys / (h - 1) - 0.5)])[None]
+
+
+def demons_identity_theta(n, h, w, device):
+    """What an untrained DemonsRegistration does to its input (net/registration.py:244-258 with flow == 0): it samples with
+    `compute_grid` — corner-aligned coordinates 2i/(n-1) - 1 — through F.grid_sample's default align_corners=False, i.e. a
+    zoom by n/(n-1) about the centre with zero padding.  In affine_grid/grid_sample(align_corners=False) terms that is
+    theta = diag(w/(w-1), h/(h-1))."""
+    t = torch.zeros(n, 2, 3, dtype=torch.float32, device=device)
+    t[:, 0, 0] = w / (w - 1.0)
+    t[:, 1, 1] = h / (h - 1.0)
+    return t
+
+
+def get_registration_field(query_images, support_images, support_labels, do_deformable=True):
+    """get_registration_field (dataset/few_shot_reader.py:109-198) for `do_deformable: False`, all slices in one launch.
+    Same return order as the reference:
+      registration_field        list of [theta_i [2, 3], grid [1, 2, H, W]] per slice (the reference keeps its nn.Module there;
+                                RP_Net.forward ignores the argument, net/rp_net.py:226)
+      py_reg_pred               [S, 1, H, W] {0, 1}: (demons(affine(label)) > 0.1) with the demons flow still zero (:168-170)
+      warped_src_list           [S, H, W] in [-1, 1]: demons(affine(src)) * 2 - 1 (:175-176, :191)
+      py_affine_reg_pred        [S, 1, H, W] {0, 1}: affine(label) > 0.1 (:171-173)
+      affine_warped_src_list    [S, H, W] in [-1, 1] (:178-179, :196)
+    The inputs may live on the host; the outputs stay on the CUDA device."""
+    if do_deformable:
+        raise NotImplementedError('the deformable (demons) refinement is not built: set do_deformable: False (yamls/example.yml)')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    src = (support_images[0][0][:, 0].to(dev, torch.float32) + 1) / 2.0
+    dst = (query_images[:, 0].to(dev, torch.float32) + 1) / 2.0
+    lab = support_labels[0][0].to(dev, torch.float32)[:, None]
+    n, h, w = src.shape
+    theta = affine_register(src, dst, iters=50, lr=0.01)
+    zoom = demons_identity_theta(n, h, w, dev)
+    aff_lab, aff_src = affine_warp(lab, theta), affine_warp(src[:, None], theta)
+    reg_pred = (affine_warp(aff_lab, zoom) > 0.1).float()
+    warped_src = affine_warp(aff_src, zoom)[:, 0] * 2 - 1
+    grid = compute_grid((h, w), dev)
+    field = [[theta[i], grid] for i in range(n)]
+    return field, reg_pred, warped_src, (aff_lab > 0.1).float(), aff_src[:, 0] * 2 - 1

@@ -3,6 +3,7 @@
 CUDA-graph replay) -> on-device Dice / NCC with the reference driver's printed lines (row N2).
 
     python tools/eval_synthetic.py [--volumes 4] [--slices 96] [--size 256] [--T 4]
+    python tools/eval_synthetic.py --on-disk [--volumes 4] [--size 256]      # NRRD files -> FewshotRegReader (row N4) -> same loop
 
 Random-init weights (no checkpoint ships with the reference), so the Dice values are those of an untrained model; the
 script exists to exercise and time the whole pipeline the reference runs in `python test_rpnet.py --yaml ...`."""
@@ -21,6 +22,7 @@ def main():
     ap.add_argument('--slices', type=int, default=96)
     ap.add_argument('--size', type=int, default=256)
     ap.add_argument('--T', type=int, default=4)
+    ap.add_argument('--on-disk', action='store_true', help='write a synthetic ABD-110-shaped NRRD dataset and read it back through the episode builder')
     args = ap.parse_args()
     import torch
     from net.model import model_factory
@@ -37,7 +39,25 @@ def main():
     items = []
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for v in range(args.volumes):
+    if args.on_disk:
+        import random
+        import tempfile
+        from rpnet_b200.dataset import FewshotRegReader
+        from rpnet_b200.dataset.synthetic_abd import make_synthetic_dataset
+        with tempfile.TemporaryDirectory() as tmp:
+            data_dir, set_name, dcfg = make_synthetic_dataset(tmp, n_patients=args.volumes, size=args.size + 8,
+                                                              depths=(40, 48, 44, 52))
+            dcfg.update(crop_size=[args.size, args.size], k=12)
+            t0 = time.perf_counter()
+            ds = FewshotRegReader(data_dir, set_name, dcfg, mode='eval')           # test_rpnet.py:70
+            random.seed(0)
+            for j in range(len(ds)):
+                it = ds[j]
+                c, si = it['supp_pids'][0]                                          # test_rpnet.py:182-183
+                it['supp_pid'] = ds.fewshot_reader.fewshot_volume_reader.data_info[c][si]['pid']
+                items.append(it)
+        args.slices = sum(it['query_images'].shape[0] for it in items) // max(1, len(items))
+    for v in range(0 if args.on_disk else args.volumes):
         raw = volume.make_synthetic_volume(args.slices, args.size, 1, 1, seed=100 * v)
         q = raw['query_images'].to(dev)
         s, l = [[raw['support_images'][0][0].to(dev)]], [[raw['support_fg'][0][0].to(dev)]]
