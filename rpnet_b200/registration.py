@@ -6,7 +6,9 @@ tiny launches (affine_grid, grid_sample, MSE, backward, Adam).  Here all slices 
 launch (one CTA per slice runs all iterations, ops.affine_register) and warped by one more (ops.affine_warp).
 
 The deformable refinement (DemonsRegistration, net/registration.py:221-313: dense flow field + NCC + scaling-and-squaring)
-is not built: this module reproduces the `do_deformable: False` behaviour, whose outputs are the affine ones."""
+is not built: this module reproduces the `do_deformable: False` behaviour (yamls/example.yml), in which the demons stage runs
+zero iterations but is still *applied* — with a zero flow it resamples by n/(n-1) (`demons_identity_theta`), which is what
+separates `warped_supp_label` / `appr_query_labels` from the affine outputs."""
 import torch
 
 from . import ops
@@ -48,9 +50,10 @@ def get_affine_registration(query_images, support_images, support_labels, iters=
 def compute_grid(img_size, device=None):
     """net/registration.py:171-186: the identity sampling grid [1, 2, H, W] (x first), normalised as 2 * (i / (n - 1) - 0.5)."""
     h, w = int(img_size[0]), int(img_size[1])
-    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32, device=device), torch.arange(w, dtype=torch.float32, device=device),
-                            indexing='ij')
-    return torch.stack([2 * (xs / (w - 1) - 0.5), 2 * (ys / (h - 1) - 0.5)])[None]
+    # built on the host like the reference's (CUDA divides by a scalar through its reciprocal: 1-ulp differences), then moved
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing='ij')
+    grid = torch.stack([2 * (xs / (w - 1) - 0.5), 2 * (ys / (h - 1) - 0.5)])[None]
+    return grid if device is None else grid.to(device)
 
 
 def demons_identity_theta(n, h, w, device):
