@@ -179,3 +179,40 @@ def test_cuda_graph_replay_equals_eager(dev):
     changed = run(eps[0])['output']
     net.enable_cuda_graph(False)
     assert torch.equal(changed, run(eps[0])['output']) and not torch.equal(changed, eager[0]['output'])
+
+
+def test_forward_edge_cases_vs_oracle(dev):
+    """Empty support mask on one slice, empty appr_query_labels on another (getFeatures' +1e-5 and the cosine eps clamp carry
+    the path, net/rp_net.py:362,373-376), a one-slice batch, and the reference's error behaviour."""
+    from oracle import rpnet_oracle as O
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, perturb_bn_stats
+    sd = perturb_bn_stats(weights.unet_rpnet_state_dict(0))
+    cfg = _cfg(2)
+    ep = make_episode(3, 1, 1, 64, seed=11)
+    ep['fore_mask'][0][0][0].zero_()                     # slice 0: no support foreground at all
+    ep['back_mask'][0][0][0].fill_(1)
+    ep['appr_query_labels'][1].zero_()                   # slice 1: empty registered label -> first query mask is empty
+    ep['fore_mask'][0][0][2].fill_(1)                    # slice 2: support foreground everywhere, background empty
+    ep['back_mask'][0][0][2].zero_()
+    net = _model(sd, cfg, dev)
+    with torch.no_grad():
+        ref = O.forward(sd, cfg, ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'])
+    out = _run(net, ep, dev)
+    assert torch.isfinite(out['output']).all()
+    for i in range(2):
+        _check_logits(out['refinement'][i], ref['refinement'][i], 'edge refinement[%d]' % i)
+    # B = 1
+    ep1 = make_episode(1, 1, 1, 64, seed=12)
+    with torch.no_grad():
+        ref1 = O.forward(sd, cfg, ep1['supp_imgs'], ep1['fore_mask'], ep1['back_mask'], ep1['qry_imgs'], ep1['appr_query_labels'])
+    _check_logits(_run(net, ep1, dev)['output'], ref1['output'], 'B=1 output')
+    # error behaviour of the reference: missing appr_query_labels -> AttributeError (net/rp_net.py:269); unknown backbone ->
+    # NotImplementedError (:218-219)
+    from rpnet_b200.synthetic import to_device
+    d = to_device(ep1, dev)
+    with pytest.raises(AttributeError):
+        net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'])
+    from net.model import model_factory
+    with pytest.raises(NotImplementedError):
+        model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'densenet'}, backbone_cfg=cfg)
