@@ -3,6 +3,8 @@
 // weights and upsample backward), weighted pooling fwd/bwd, prototype averaging backward, dice_ce and the
 // PANet-style alignment loss pieces.  Each kernel cites the reference forward op whose gradient (taken by
 // torch autograd in the reference) it restates.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace rpnet {
@@ -256,6 +258,58 @@ bilinear_adjoint_kernel(const float* __restrict__ in, float* __restrict__ out, f
   }
 }
 
+// Integer scale S (every use on the hot path: S = 4): output (i, j) can only receive from the 2S x 2S input window starting at
+// (S*i - S/2, S*j - S/2) — i0 == i for inputs [S*i + S/2, S*i + 3S/2), i1 == i for [S*i - S/2, S*i + S/2), and the border
+// clamps keep their inputs inside that window — so the column weights are computed once per thread and the row weight once
+// per input row instead of one source-index computation per (output, input) pair.
+template <int S>
+__global__ void __launch_bounds__(128)
+bilinear_adjoint_int_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ sums, int H, int W, int h, int w) {
+  const int n = blockIdx.y;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* src = in + (size_t)n * H * W;
+  const float rs = 1.f / (float)S;
+  float own = 0.f;
+  if (o < h * w) {
+    const int i = o / w, j = o % w;
+    const int X0 = S * j - S / 2, Y0 = S * i - S / 2;
+    float wx[2 * S];
+#pragma unroll
+    for (int t = 0; t < 2 * S; ++t) {
+      const int X = X0 + t;
+      int j0, j1; float m0, m1;
+      bilin_src(X < 0 ? 0 : X, rs, w, j0, j1, m0, m1);
+      wx[t] = (X >= 0 && X < W) ? (j0 == j ? m0 : 0.f) + (j1 == j ? m1 : 0.f) : 0.f;
+    }
+    float acc = 0.f;
+#pragma unroll 2
+    for (int ty = 0; ty < 2 * S; ++ty) {
+      const int Y = Y0 + ty;
+      if (Y < 0 || Y >= H) continue;
+      int i0, i1; float l0, l1;
+      bilin_src(Y, rs, h, i0, i1, l0, l1);
+      const float wy = (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+      const bool mine_y = sums != nullptr && ty >= S / 2 && ty < S / 2 + S;
+      const float* row = src + (size_t)Y * W + X0;
+      float racc = 0.f, rown = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2 * S; ++t) {
+        const float v = (X0 + t >= 0 && X0 + t < W) ? __ldg(row + t) : 0.f;
+        racc = fmaf(wx[t], v, racc);
+        if (t >= S / 2 && t < S / 2 + S) rown += v;
+      }
+      acc = fmaf(wy, racc, acc);
+      if (mine_y) own += rown;
+    }
+    out[(size_t)n * h * w + o] = acc;
+  }
+  if (sums) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) own += __shfl_xor_sync(0xffffffffu, own, s);
+    if ((threadIdx.x & 31) == 0 && own != 0.f) atomicAdd(sums + n, own);
+  }
+}
+
 // out[n][k][c] = sum_p feat[n][p][c] * wmap_k[n][p] / (msum_k[n] + 1e-5), k in {0,1}   (getFeatures for fore & back mask)
 // One block of 1024 threads per image: 16 lanes x float4 cover the (<= 64) channels of a pixel, 64 pixels per step, both
 // masks in the same pass over feat; ordered shared-memory tree (deterministic).
@@ -457,16 +511,26 @@ dice_ce_grad_kernel(const float* __restrict__ logits, const long long* __restric
 // Alignment loss pieces (alignLoss, net/rp_net.py:394-440).
 // (1) class_pool: argmax over the low-resolution prediction -> per-class masked average of the query features.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One thread-block cluster of kCpCluster CTAs per image: every CTA reduces a contiguous pixel range in a fixed order into its
+// own shared memory, rank 0 then adds the partials rank by rank through distributed shared memory (deterministic, no scratch).
+constexpr int kCpCluster = 8;
+
+__global__ void __cluster_dims__(kCpCluster, 1, 1) __launch_bounds__(256)
 class_pool_kernel(const float* __restrict__ feat /*[B][hw][64]*/, const float* __restrict__ pred /*[B][P][hw]*/, int hw, int P,
                   float* __restrict__ qproto /*[B][P][64]*/, float* __restrict__ counts /*[B][P]*/, int* __restrict__ amax /*[B][hw]*/) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float s_acc[4][kMaxP][64];
+  __shared__ float s_part[kMaxP][64];
   __shared__ float s_cnt[kMaxP];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
+  const int rank = (int)cluster.block_rank();
+  const int chunk = (hw + kCpCluster - 1) / kCpCluster;
+  const int p_lo = rank * chunk, p_hi = min(hw, p_lo + chunk);
   for (int i = threadIdx.x; i < 4 * kMaxP * 64; i += 256) (&s_acc[0][0][0])[i] = 0.f;
   if (threadIdx.x < kMaxP) s_cnt[threadIdx.x] = 0.f;
   __syncthreads();
-  for (int p = threadIdx.x; p < hw; p += 256) {
+  for (int p = p_lo + threadIdx.x; p < p_hi; p += 256) {
     int best = 0;
     float bv = __ldg(pred + ((size_t)b * P) * hw + p);
     for (int k = 1; k < P; ++k) {
@@ -474,21 +538,33 @@ class_pool_kernel(const float* __restrict__ feat /*[B][hw][64]*/, const float* _
       if (v > bv) { bv = v; best = k; }
     }
     amax[(size_t)b * hw + p] = best;
-    atomicAdd(&s_cnt[best], 1.f);
+    atomicAdd(&s_cnt[best], 1.f);                       // integer-valued: exact in any order
   }
   __syncthreads();
   const int c = threadIdx.x & 63, part = threadIdx.x >> 6;
-  for (int p = part; p < hw; p += 4) {
+  for (int p = p_lo + part; p < p_hi; p += 4) {
     const int k = amax[(size_t)b * hw + p];
     s_acc[part][k][c] += __ldg(feat + ((size_t)b * hw + p) * 64 + c);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < P * 64; i += 256) {
     const int k = i / 64, cc = i % 64;
-    const float t = (s_acc[0][k][cc] + s_acc[1][k][cc]) + (s_acc[2][k][cc] + s_acc[3][k][cc]);
-    qproto[((size_t)b * P + k) * 64 + cc] = t / (s_cnt[k] + 1e-5f);
+    s_part[k][cc] = (s_acc[0][k][cc] + s_acc[1][k][cc]) + (s_acc[2][k][cc] + s_acc[3][k][cc]);
   }
-  if (threadIdx.x < P) counts[(size_t)b * P + threadIdx.x] = s_cnt[threadIdx.x];
+  cluster.sync();
+  if (rank == 0) {
+    for (int i = threadIdx.x; i < P * 64; i += 256) {
+      const int k = i / 64, cc = i % 64;
+      float t = 0.f, n = 0.f;
+      for (int r = 0; r < kCpCluster; ++r) {
+        t += cluster.map_shared_rank(&s_part[0][0], r)[k * 64 + cc];
+        n += cluster.map_shared_rank(&s_cnt[0], r)[k];
+      }
+      qproto[((size_t)b * P + k) * 64 + cc] = t / (n + 1e-5f);
+      if (cc == 0) counts[(size_t)b * P + k] = n;
+    }
+  }
+  cluster.sync();                                        // the partials stay mapped until rank 0 has read them
 }
 
 __global__ void class_pool_bwd_kernel(const float* __restrict__ dqproto, const float* __restrict__ counts, const int* __restrict__ amax,
@@ -700,7 +776,13 @@ RPNET_API int rpnet_bilinear_adjoint_f32(const float* in, float* out, float* sum
   RPNET_REQUIRE(n > 0 && out_h > 0 && out_w > 0 && in_h >= out_h && in_w >= out_w, "bilinear_adjoint: bad shape");
   RPNET_REQUIRE(!sums || (in_h % out_h == 0 && in_w % out_w == 0), "bilinear_adjoint: sums need an integer scale");
   if (sums) RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)n * sizeof(float), stream));
-  bilinear_adjoint_kernel<<<dim3((out_h * out_w + 127) / 128, n), 128, 0, stream>>>(in, out, sums, in_h, in_w, out_h, out_w);
+  const dim3 grid((out_h * out_w + 127) / 128, n);
+  if (in_h == 4 * out_h && in_w == 4 * out_w)
+    bilinear_adjoint_int_kernel<4><<<grid, 128, 0, stream>>>(in, out, sums, in_h, in_w, out_h, out_w);
+  else if (in_h == 8 * out_h && in_w == 8 * out_w)
+    bilinear_adjoint_int_kernel<8><<<grid, 128, 0, stream>>>(in, out, sums, in_h, in_w, out_h, out_w);
+  else
+    bilinear_adjoint_kernel<<<grid, 128, 0, stream>>>(in, out, sums, in_h, in_w, out_h, out_w);
   return check_cuda(cudaGetLastError(), "bilinear_adjoint launch");
 }
 
@@ -756,7 +838,7 @@ RPNET_API int rpnet_class_pool_f32(const float* feat, const float* pred, int bat
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(feat && pred && qproto && counts && amax, "class_pool: null pointer argument");
   RPNET_REQUIRE(c == 64 && n_classes >= 1 && n_classes <= kMaxP && batch > 0 && hw > 0, "class_pool: bad shape (c == 64)");
-  class_pool_kernel<<<batch, 256, 0, stream>>>(feat, pred, hw, n_classes, qproto, counts, amax);
+  class_pool_kernel<<<dim3(kCpCluster, batch), 256, 0, stream>>>(feat, pred, hw, n_classes, qproto, counts, amax);
   return check_cuda(cudaGetLastError(), "class_pool launch");
 }
 
