@@ -775,23 +775,37 @@ conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restric
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   const unsigned total = (unsigned)N * H * W;                    // pixels (< 2^31, host-checked)
-  for (unsigned p = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p < total; p += (gridDim.x * blockDim.x) >> 3) {
-    const unsigned x = p % (unsigned)W, y = (p / (unsigned)W) % (unsigned)H;
-    const unsigned base = p - y * W - x;                          // n * H * W
-    const size_t gid = (size_t)p * 8 + cg;
-    float d[8];
-    unpack8_bf16(__ldg(dz + gid), d);
+  const unsigned stride = (gridDim.x * blockDim.x) >> 3;
+  constexpr int U = 2;                                           // pixels per iteration: all 2 x (1 + 9) loads go out before the math
+  for (unsigned p0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; p0 < total; p0 += U * stride) {
+    uint4 dq[U];
+    float v[U][9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = (int)y + ky - 1;
-      const bool yok = yy >= 0 && yy < H;
+    for (int u = 0; u < U; ++u) {
+      const unsigned p = p0 + u * stride;
+      const bool ok = p < total;
+      const unsigned x = p % (unsigned)W, y = (p / (unsigned)W) % (unsigned)H;
+      const unsigned base = p - y * W - x;                        // n * H * W
+      dq[u] = ok ? __ldg(dz + (size_t)p * 8 + cg) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = (int)x + kx - 1;
-        const float v = (yok && xx >= 0 && xx < W) ? __ldg(img + base + (unsigned)(yy * W + xx)) : 0.f;
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = (int)y + ky - 1;
+        const bool yok = ok && yy >= 0 && yy < H;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(d[j], v, acc[ky * 3 + kx][j]);
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = (int)x + kx - 1;
+          v[u][ky * 3 + kx] = (yok && xx >= 0 && xx < W) ? __ldg(img + base + (unsigned)(yy * W + xx)) : 0.f;
+        }
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float d[8];
+      unpack8_bf16(dq[u], d);
+#pragma unroll
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(d[j], v[u][t], acc[t][j]);
     }
   }
 #pragma unroll
