@@ -24,7 +24,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
-    from oracle import weights
     from rpnet_b200.nn.rp_net import RP_Net
     from rpnet_b200.synthetic import make_episode, to_device
     from rpnet_b200.train import TrainStep, shard_range
@@ -40,8 +39,8 @@ def main():
     d = to_device(shard, dev)
 
     def build():
+        torch.manual_seed(0)                          # the same initial weights on every rank and for every replica
         net = RP_Net(cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
-        net.load_state_dict(weights.unet_rpnet_state_dict(0))
         return net.to(dev).train()
 
     # (a) local gradients, no communication
