@@ -70,10 +70,13 @@ struct ConvParams {
   int bn_start[kMaxBnGroups + 1];
 };
 
-template <int BN>
+// CTAS == 2: a CTA pair runs one M = 256 tile pair (two pixel tiles, the same BN couts); every CTA stages its own A tile and
+// HALF of the weight tile, so a stage is 32 KB instead of 48 KB at BN = 256 and the shared-memory traffic per MMA (operand
+// reads + TMA writes, what bounds the single-CTA kernel at ~2/3 of the tensor peak) drops by a third.
+template <int BN, int CTAS = 1>
 struct ConvCfg {
   static constexpr int kABytes = kBM * kBK * 2;                  // 16 KB
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
@@ -81,12 +84,12 @@ struct ConvCfg {
                                     kMaxBnCout * 2 * 8 /*fused BN statistics*/;
 };
 
-template <int BN>
+template <int BN, int CTAS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                   const __grid_constant__ CUtensorMap tm_src2, const __grid_constant__ CUtensorMap tm_src3,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, CTAS>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,7 +108,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   const int kblocks_per_tap = p.chunks0 + p.chunks1;
   const int num_kb = p.ntaps * kblocks_per_tap;
   const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int num_tiles = num_m_tiles * p.n_tiles_c;
+  // work unit = CTAS consecutive pixel tiles x one cout tile; CTA `cta_rank` of the pair owns pixel tile unit * CTAS + cta_rank
+  // (past the end for the odd one out: its loads are out of bounds = zeros and its pixels fail the `valid` test)
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const int num_tiles = ((num_m_tiles + CTAS - 1) / CTAS) * p.n_tiles_c;
+  const int tile_first = CTAS == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTAS == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int bw = 1 << p.bw_log2, bh = 1 << p.bh_log2;
   const int bn = kBM >> (p.bw_log2 + p.bh_log2);
 
@@ -121,13 +129,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);     // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], 4 * CTAS);     // one arrive per epilogue warp (of both CTAs: the leader's barrier gates the MMAs)
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (CTAS == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
+    else           tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTAS == 2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them
+  else           __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -136,9 +149,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int ct = tile % p.n_tiles_c;
-        int mt = tile / p.n_tiles_c;
+        int mt = (tile / p.n_tiles_c) * CTAS + (int)cta_rank;
         const int tx = mt % p.tiles_x;  mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int tn = mt / p.tiles_y;
@@ -149,16 +162,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
             uint8_t* b_dst = a_dst + Cfg::kABytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             const int ts = p.tap_src[tap];
-            if (ts < 0) {
-              if (kc < p.chunks0) tma_load_4d(&tm_src0, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
-              else                tma_load_4d(&tm_src1, &full_bar[stage], a_dst, (kc - p.chunks0) * kBK, xs, ys, n0);
+            const CUtensorMap* tm = ts < 0 ? (kc < p.chunks0 ? &tm_src0 : &tm_src1)
+                                           : (ts == 0 ? &tm_src0 : (ts == 1 ? &tm_src1 : (ts == 2 ? &tm_src2 : &tm_src3)));
+            const int kch = (ts < 0 && kc >= p.chunks0) ? kc - p.chunks0 : kc;
+            if (CTAS == 2) {
+              // both CTAs' bytes complete on the leader's barrier; only the leader arrives on it
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              tma_load_4d_pair(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
+              tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN + (int)cta_rank * (BN / 2), tap);
             } else {
-              const CUtensorMap* tm = ts == 0 ? &tm_src0 : (ts == 1 ? &tm_src1 : (ts == 2 ? &tm_src2 : &tm_src3));
-              tma_load_4d(tm, &full_bar[stage], a_dst, kc * kBK, xs, ys, n0);
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_4d(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
+              tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
             }
-            tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -166,15 +183,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM, BN) | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(kBM * CTAS, BN) | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);           // epilogue has drained this accumulator
+        if (CTAS == 2) mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);
+        else           mbar_wait(&tempty_bar[as], aphase ^ 1);           // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -186,12 +204,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+          if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3);
+          else           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);                        // accumulator complete -> epilogue
+        if (CTAS == 2) umma_commit_pair(&tfull_bar[as], 3);  // accumulator complete -> the epilogue of each CTA
+        else           umma_commit(&tfull_bar[as]);
       }
     }
   } else {
@@ -209,11 +231,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int ct = tile % p.n_tiles_c;
-      int mt = tile / p.n_tiles_c;
+      int mt = (tile / p.n_tiles_c) * CTAS + (int)cta_rank;
       const int tx = mt % p.tiles_x;  mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int tn = mt / p.tiles_y;
@@ -360,7 +382,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_rank0(&tempty_bar[as]);
+        else           mbar_arrive(&tempty_bar[as]);
+      }
     }
     if (p.bn_sums && cur_g >= 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -368,10 +393,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if (CTAS == 2) cluster_sync_all();      // both CTAs are done with the pair's TMEM and with each other's barriers
+  else           __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CTAS == 2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else           tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -436,16 +464,46 @@ int num_sms() {
 template <int BN>
 static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
                   const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN>;
+  using Cfg = ConvCfg<BN, 1>;
   static bool attr_set = false;
   if (!attr_set) {
-    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_c;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_igemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
+  conv_igemm_kernel<BN, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
   return check_cuda(cudaGetLastError(), "conv_igemm_kernel launch");
+}
+
+// CTA-pair launch (BN = 256): clusters of two CTAs, one pair per TPC, persistent over the tile-pair units.
+static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
+                       const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<256, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int units = ((p.tiles_x * p.tiles_y * p.tiles_n + 1) / 2) * p.n_tiles_c;
+  const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<256, 2>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
+}
+
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RPNET_CONV_2CTA"); v = e ? atoi(e) : 1; }
+  return v != 0;
 }
 
 }  // namespace rpnet
@@ -555,14 +613,16 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     t2 = t0;
     t3 = t0;
   }
+  const bool pair = BN == 256 && pair_enabled() && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
   {
     const uint64_t cin = (uint64_t)(c0 + c1);
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
     const uint64_t str[2] = {cin, cin * cout};
-    const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
+    const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)(pair ? BN / 2 : BN), 1};
     int rc = make_tmap_2b(&tw, wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
   }
+  if (pair) return launch_pair(t0, t1, t2, t3, tw, p, stream);
   switch (BN) {
     case 256: return launch<256>(t0, t1, t2, t3, tw, p, stream);
     case 128: return launch<128>(t0, t1, t2, t3, tw, p, stream);
