@@ -476,13 +476,14 @@ static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMa
   return check_cuda(cudaGetLastError(), "conv_igemm_kernel launch");
 }
 
-// CTA-pair launch (BN = 256): clusters of two CTAs, one pair per TPC, persistent over the tile-pair units.
+// CTA-pair launch: clusters of two CTAs, one pair per TPC, persistent over the tile-pair units.
+template <int BN>
 static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
                        const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<256, 2>;
+  using Cfg = ConvCfg<BN, 2>;
   static bool attr_set = false;
   if (!attr_set) {
-    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int units = ((p.tiles_x * p.tiles_y * p.tiles_n + 1) / 2) * p.n_tiles_c;
@@ -497,13 +498,16 @@ static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUten
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<256, 2>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 2>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
 }
 
-static bool pair_enabled() {
+// RPNET_CONV_2CTA: bit mask of the cout tile widths that run as CTA pairs (1: 256, 2: 128, 4: 64).  Default 1: measured on
+// B200, pairs gain 10 % at BN = 256 (1344 -> 1479 TF/s) and nothing at 128 / 64 — those layers are bound by the L2 -> SM feed of
+// the nine per-tap activation boxes, not by MMA issue or operand reads.
+static bool pair_enabled(int BN) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("RPNET_CONV_2CTA"); v = e ? atoi(e) : 1; }
-  return v != 0;
+  return (v & (BN == 256 ? 1 : (BN == 128 ? 2 : 4))) != 0;
 }
 
 }  // namespace rpnet
@@ -613,7 +617,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     t2 = t0;
     t3 = t0;
   }
-  const bool pair = BN == 256 && pair_enabled() && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
+  const bool pair = pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
   {
     const uint64_t cin = (uint64_t)(c0 + c1);
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
@@ -622,7 +626,13 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     int rc = make_tmap_2b(&tw, wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
   }
-  if (pair) return launch_pair(t0, t1, t2, t3, tw, p, stream);
+  if (pair) {
+    switch (BN) {
+      case 256: return launch_pair<256>(t0, t1, t2, t3, tw, p, stream);
+      case 128: return launch_pair<128>(t0, t1, t2, t3, tw, p, stream);
+      default:  return launch_pair<64>(t0, t1, t2, t3, tw, p, stream);
+    }
+  }
   switch (BN) {
     case 256: return launch<256>(t0, t1, t2, t3, tw, p, stream);
     case 128: return launch<128>(t0, t1, t2, t3, tw, p, stream);
