@@ -73,35 +73,45 @@ struct ConvParams {
 // CTAS == 2: a CTA pair runs one M = 256 tile pair (two pixel tiles, the same BN couts); every CTA stages its own A tile and
 // HALF of the weight tile, so a stage is 32 KB instead of 48 KB at BN = 256 and the shared-memory traffic per MMA (operand
 // reads + TMA writes, what bounds the single-CTA kernel at ~2/3 of the tensor peak) drops by a third.
-template <int BN, int CTAS = 1>
+// WS == 1 (weights-stationary, single-cout-tile convs with at most kWsMaxKb k-blocks — the 64 -> 64 full-resolution layers):
+// the whole packed weight tensor is loaded ONCE per CTA into a resident region and the ring carries activations only.  Those
+// layers are bound by the L2 -> SM feed (ncu: 9.4 TB/s of TMA reads, a third of them the same 72 KB of weights re-fetched for
+// every pixel tile): 1118 -> 964 us on the 96 x 256 x 256 layer.  (Combined with CTA pairs: no further gain — at N = 64 the MMA rate
+// itself is the floor.)
+constexpr int kWsMaxKb = 9;
+template <int BN, int CTAS = 1, int WS = 0>
 struct ConvCfg {
   static constexpr int kABytes = kBM * kBK * 2;                  // 16 KB
   static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
+  static constexpr int kResidentBytes = WS ? kWsMaxKb * kBBytes : 0;
+  static constexpr int kStages = ((kSmemBudget - kResidentBytes) / kStageBytes) > 8 ? 8 : ((kSmemBudget - kResidentBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
+  static constexpr int kTileBytes = kStages * kStageBytes + kResidentBytes;
+  static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
                                     kMaxBnCout * 2 * 8 /*fused BN statistics*/;
 };
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, int WS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                   const __grid_constant__ CUtensorMap tm_src2, const __grid_constant__ CUtensorMap tm_src3,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
-  using Cfg = ConvCfg<BN, CTAS>;
+  using Cfg = ConvCfg<BN, CTAS, WS>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);   // [2][BN]
+  uint8_t* w_res = smem + kStages * Cfg::kStageBytes;                             // WS: all k-blocks of the packed weights
+  float* s_scale = reinterpret_cast<float*>(smem + Cfg::kTileBytes);              // [2][BN]
   float* s_shift = s_scale + 2 * BN;                                               // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + 2 * BN);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  double* s_bn = reinterpret_cast<double*>(smem + kStages * Cfg::kStageBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
+  uint64_t* ws_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ws_bar + 1);
+  double* s_bn = reinterpret_cast<double*>(smem + Cfg::kTileBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,6 +141,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4 * CTAS);     // one arrive per epilogue warp (of both CTAs: the leader's barrier gates the MMAs)
     }
+    mbar_init(ws_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -149,6 +160,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (WS) {                                            // the whole weight tensor, once (n_tiles_c == 1, num_kb <= kWsMaxKb)
+        if (CTAS == 2) {                                   // each CTA its half of the couts; both complete on the leader's barrier
+          if (cta_rank == 0) mbar_expect_tx(ws_bar, 2 * num_kb * Cfg::kBBytes);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_3d_pair(&tm_w, ws_bar, w_res + kb * Cfg::kBBytes, (kb % kblocks_per_tap) * kBK, (int)cta_rank * (BN / 2),
+                             kb / kblocks_per_tap);
+        } else {
+          mbar_expect_tx(ws_bar, num_kb * Cfg::kBBytes);
+          for (int kb = 0; kb < num_kb; ++kb)
+            tma_load_3d(&tm_w, ws_bar, w_res + kb * Cfg::kBBytes, (kb % kblocks_per_tap) * kBK, 0, kb / kblocks_per_tap);
+        }
+      }
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int ct = tile % p.n_tiles_c;
         int mt = (tile / p.n_tiles_c) * CTAS + (int)cta_rank;
@@ -170,11 +193,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
               // both CTAs' bytes complete on the leader's barrier; only the leader arrives on it
               if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
               tma_load_4d_pair(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
-              tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN + (int)cta_rank * (BN / 2), tap);
+              if (!WS) tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN + (int)cta_rank * (BN / 2), tap);
             } else {
               mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
               tma_load_4d(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
-              tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
+              if (!WS) tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -188,6 +211,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (WS) mbar_wait(ws_bar, 0);
       for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -200,7 +224,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
-          const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes, 1024);
+          const uint64_t b_desc = umma_desc_sw128(WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes, 1024);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
@@ -464,26 +488,41 @@ int num_sms() {
 template <int BN>
 static int launch(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
                   const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, 1>;
+  using Cfg = ConvCfg<BN, 1, 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_c;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_igemm_kernel<BN, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
+  conv_igemm_kernel<BN, 1, 0><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
   return check_cuda(cudaGetLastError(), "conv_igemm_kernel launch");
+}
+
+// Weights-stationary launch (cout == 64, at most kWsMaxKb k-blocks).
+static int launch_ws(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
+                     const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<64, 1, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_igemm_kernel<64, 1, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
+  return check_cuda(cudaGetLastError(), "conv_igemm_kernel (weights-stationary) launch");
 }
 
 // CTA-pair launch: clusters of two CTAs, one pair per TPC, persistent over the tile-pair units.
 template <int BN>
 static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
                        const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BN, 2>;
+  using Cfg = ConvCfg<BN, 2, 0>;
   static bool attr_set = false;
   if (!attr_set) {
-    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int units = ((p.tiles_x * p.tiles_y * p.tiles_n + 1) / 2) * p.n_tiles_c;
@@ -498,7 +537,7 @@ static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUten
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 2>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 2, 0>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
 }
 
 // RPNET_CONV_2CTA: bit mask of the cout tile widths that run as CTA pairs (1: 256, 2: 128, 4: 64).  Default 1: measured on
@@ -617,7 +656,9 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
     t2 = t0;
     t3 = t0;
   }
-  const bool pair = pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
+  const bool ws = cout == 64 && ntaps * (p.chunks0 + p.chunks1) <= kWsMaxKb && p.tiles_x * p.tiles_y * p.tiles_n >= 4 * num_sms() &&
+                  !getenv("RPNET_CONV_NO_WS");
+  const bool pair = !ws && pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
   {
     const uint64_t cin = (uint64_t)(c0 + c1);
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
@@ -633,6 +674,7 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
       default:  return launch_pair<64>(t0, t1, t2, t3, tw, p, stream);
     }
   }
+  if (ws) return launch_ws(t0, t1, t2, t3, tw, p, stream);
   switch (BN) {
     case 256: return launch<256>(t0, t1, t2, t3, tw, p, stream);
     case 128: return launch<128>(t0, t1, t2, t3, tw, p, stream);
