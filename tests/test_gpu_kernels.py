@@ -364,3 +364,41 @@ def test_relation_head_fused(dev, case):
                       shift.to(dev), protos.to(dev), pred, r, 20.0)
     torch.cuda.synchronize()
     torch.testing.assert_close(pred.cpu(), want, rtol=2e-3, atol=3e-2)
+
+
+_VARIANT_CHILD = r'''
+import hashlib, os, sys
+sys.path.insert(0, os.getcwd())
+import torch
+from rpnet_b200 import ops
+dev = torch.device('cuda:0')
+taps = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+# (n, h, w, c0, c1, cout): CTA-pair shapes (cout % 256 == 0; odd tile counts, ragged maps), weights-stationary shape (64 -> 64, many tiles)
+for (n, h, w, c0, c1, cout) in [(5, 64, 64, 256, 256, 256), (3, 24, 40, 64, 0, 512), (1, 16, 8, 128, 0, 256), (20, 256, 256, 64, 0, 64)]:
+    torch.manual_seed(1)
+    x0 = torch.randn(n, h, w, c0, device=dev).half()
+    x1 = torch.randn(n, h, w, c1, device=dev).half() if c1 else None
+    wf = (torch.randn(9, cout, c0 + c1, device=dev) * 0.05).half()
+    sc, sh = torch.rand(cout, device=dev) + 0.5, torch.randn(cout, device=dev)
+    out = torch.empty(n, h, w, cout, device=dev, dtype=torch.float16)
+    pool = torch.empty(n, h // 2, w // 2, cout, device=dev, dtype=torch.float16)
+    ops.conv_igemm(x0, wf, taps, sc, sh, True, src1=x1, out=out, out_pool=pool)
+    torch.cuda.synchronize()
+    print(hashlib.md5(out.cpu().numpy().tobytes()).hexdigest(), hashlib.md5(pool.cpu().numpy().tobytes()).hexdigest())
+'''
+
+
+def test_conv_variants_bit_identical(dev):
+    """The CTA-pair (cta_group::2) and weights-stationary variants of conv_igemm produce the same bits as the plain
+    single-CTA kernel (the variant is chosen per process: RPNET_CONV_2CTA / RPNET_CONV_NO_WS)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_extra in ({}, {'RPNET_CONV_2CTA': '0', 'RPNET_CONV_NO_WS': '1'}):
+        r = subprocess.run([sys.executable, '-c', _VARIANT_CHILD], cwd=root, env=dict(os.environ, **env_extra), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines())
+    assert len(outs[0]) == 4 and outs[0] == outs[1], (outs[0], outs[1])
