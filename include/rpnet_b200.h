@@ -44,7 +44,10 @@ const char* rpnet_last_error(void);
  * out_f16:   optional fp16 NHWC [n][out_h][out_w][out_c]; conv pixel (y, x) is stored at
  *            (y*oy_mul + oy_off, x*ox_mul + ox_off), channels [out_coff, out_coff + cout).
  * out_pool_f16: optional fp16 NHWC [n][h/2][w/2][cout] = 2x2/stride-2 max-pool of the activated output.
- * out_f32:   optional fp32 NHWC [n][h][w][cout]. */
+ * out_f32:   optional fp32 NHWC [n][h][w][cout].
+ * Kernel selection (same results bit for bit, tests/test_gpu_kernels.py::test_conv_variants_bit_identical): cout % 256 == 0 runs as
+ * CTA pairs (tcgen05 cta_group::2, M = 256; RPNET_CONV_2CTA=0 disables), cout == 64 with <= 9 k-blocks and many pixel tiles runs
+ * weights-stationary (RPNET_CONV_NO_WS=1 disables). */
 int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
                          const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
                          const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
