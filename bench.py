@@ -351,12 +351,12 @@ def main():
                 'algorithmic_flops_per_step': algo, 'launches_per_step': kern['conv_igemm']['launches'], 'kernel_ms_per_step': conv_ms,
                 'executed_tflops': kern['conv_igemm']['work_per_step'] / (conv_ms * 1e-3) / 1e12,
                 'kernel_share_of_step': conv_ms / (ms_total / args.steps)}
-    # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r01_ncu_conv_wgrad_igemm_uc4a.csv): one
-    # representative launch, Up_conv4.conv.0 forward at the cfg3 shape (96 x 64 x 64, 512 -> 256 channels)
-    roofline['traffic'] = 405.078272e6 + 173.753088e6
-    roofline['traffic_launch'] = {'layer': 'Up_conv4.conv.0 forward, 96x64x64, 512->256', 'dram_bytes': 405.078272e6 + 173.753088e6,
-                                  'algorithmic_bytes': 96 * 64 * 64 * (512 + 256) * 2 + 9 * 512 * 256 * 2, 'duration_us': 637.5,
-                                  'source': 'profiles/r01_ncu_conv_wgrad_igemm_uc4a.csv'}
+    # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r01_ncu_conv_pair_uc4a.csv): one
+    # representative launch, Up_conv4.conv.0 forward at the cfg3 shape (96 x 64 x 64, 512 -> 256 channels), CTA-pair kernel
+    roofline['traffic'] = 405.076224e6 + 171.506176e6
+    roofline['traffic_launch'] = {'layer': 'Up_conv4.conv.0 forward, 96x64x64, 512->256', 'dram_bytes': 405.076224e6 + 171.506176e6,
+                                  'algorithmic_bytes': 96 * 64 * 64 * (512 + 256) * 2 + 9 * 512 * 256 * 2, 'duration_us': 558.7,
+                                  'tensor_pipe_active_pct': 97.2, 'source': 'profiles/r01_ncu_conv_pair_uc4a.csv'}
     if graphed:
         roofline['note'] = 'kernel times from a second pass without CUDA-graph replay; value / ms_per_step from graph replay'
     if 'conv_wgrad' in kern:
