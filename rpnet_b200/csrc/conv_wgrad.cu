@@ -25,7 +25,10 @@
 
 namespace rpnet {
 
-constexpr int kWgPix = 64;                         // pixels (K) per stage
+#ifndef RPNET_WG_PIX
+#define RPNET_WG_PIX 64
+#endif
+constexpr int kWgPix = RPNET_WG_PIX;               // pixels (K) per stage
 constexpr int kWgBoxBytes = kWgPix * 128;          // one [64 ch x 64 px] box = 8 KB
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxTaps = 9;
@@ -126,30 +129,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
         const int mt = rem / p.n_ntiles, nt = rem % p.n_ntiles;
         const int k0 = (int)((long long)split * p.ptiles / p.splits);
         const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
-        int bx[kWgBoxesPerItem];
+        // everything that does not depend on the pixel tile is resolved once per item: the producer is ONE thread, and the per-stage
+        // divisions / parameter loads of its inner loop were what bounded the kernel (tensor pipe 60 % active)
+        const CUtensorMap* box_tm[kWgBoxesPerItem];
+        int box_c[kWgBoxesPerItem], box_dx[kWgBoxesPerItem], box_dy[kWgBoxesPerItem];
 #pragma unroll
-        for (int j = 0; j < kWgBoxesPerItem; ++j)                   // ragged box count: duplicate the first box (rows discarded)
-          bx[j] = (kWgBoxesPerItem * mt + j < p.n_boxes) ? kWgBoxesPerItem * mt + j : kWgBoxesPerItem * mt;
+        for (int j = 0; j < kWgBoxesPerItem; ++j) {                 // ragged box count: duplicate the first box (rows discarded)
+          const int b = (kWgBoxesPerItem * mt + j < p.n_boxes) ? kWgBoxesPerItem * mt + j : kWgBoxesPerItem * mt;
+          const int tap = b / nch, c = b % nch;
+          box_tm[j] = c < p.chunks0 ? &tm_x0 : &tm_x1;
+          box_c[j] = (c < p.chunks0 ? c : c - p.chunks0) * 64;
+          box_dx[j] = p.dx[tap];
+          box_dy[j] = p.dy[tap];
+        }
+        int tx = k0 % p.tiles_x, ty = (k0 / p.tiles_x) % p.tiles_y, tn = k0 / (p.tiles_x * p.tiles_y);
         for (int pt = k0; pt < k1; ++pt) {
-          int t = pt;
-          const int tx = t % p.tiles_x;  t /= p.tiles_x;
-          const int ty = t % p.tiles_y;
-          const int tn = t / p.tiles_y;
           const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
           uint8_t* b_dst = a_dst + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-          for (int j = 0; j < kWgBoxesPerItem; ++j) {
-            const int tap = bx[j] / nch, c = bx[j] % nch;
-            const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
-            if (c < p.chunks0) tma_load_4d(&tm_x0, &full_bar[stage], a_dst + j * kWgBoxBytes, c * 64, xs, ys, n0);
-            else               tma_load_4d(&tm_x1, &full_bar[stage], a_dst + j * kWgBoxBytes, (c - p.chunks0) * 64, xs, ys, n0);
-          }
+          for (int j = 0; j < kWgBoxesPerItem; ++j)
+            tma_load_4d(box_tm[j], &full_bar[stage], a_dst + j * kWgBoxBytes, box_c[j], x0 + box_dx[j], y0 + box_dy[j], n0);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
             tma_load_4d(&tm_dz, &full_bar[stage], b_dst + j * kWgBoxBytes, nt * BN + j * 64, x0, y0, n0);
+          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -307,11 +313,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
         const int k1 = (int)((long long)(split + 1) * p.ptiles / p.splits);
         const CUtensorMap* tmx = kc < p.chunks0 ? &tm_x0 : &tm_x1;
         const int cx = (kc < p.chunks0 ? kc : kc - p.chunks0) * 64;
+        int tx = k0 % p.tiles_x, ty = (k0 / p.tiles_x) % p.tiles_y, tn = k0 / (p.tiles_x * p.tiles_y);   // no division per stage
         for (int pt = k0; pt < k1; ++pt) {
-          int t = pt;
-          const int tx = t % p.tiles_x;  t /= p.tiles_x;
-          const int ty = t % p.tiles_y;
-          const int tn = t / p.tiles_y;
           const int x0 = tx * 8, y0 = ty * 8;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = tiles + stage * kWhStageBytes;
@@ -319,6 +322,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
 #pragma unroll
           for (int d = 0; d < 3; ++d) tma_load_4d(tmx, &full_bar[stage], a_dst + d * kWhBoxA, cx, x0 + d - 1, y0 - 1, tn);
           tma_load_4d(&tm_dz, &full_bar[stage], a_dst + 3 * kWhBoxA, nt * 64, x0, y0, tn);
+          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++tn; } }
           if (++stage == kWhStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -473,7 +477,7 @@ static WgradPlan plan_wgrad(int c0, int c1, int n, int h, int w, int ntaps, int 
   // pick the split count that minimises it (a fixed "2 waves" rule left up to a third of the SMs idle in the last wave).
   const int sms = num_sms();
   const int max_splits = pl.ptiles / 8 > 0 ? pl.ptiles / 8 : 1;     // >= 8 pixel tiles (512 px) per item
-  const double stage_cyc = kWgAcc * 4.0 * (pl.BN / 2.0) / 0.65;     // 4 MMAs of K=16 per accumulator and 64-pixel stage
+  const double stage_cyc = kWgAcc * (kWgPix / 16.0) * (pl.BN / 2.0) / 0.65;     // kWgPix / 16 MMAs of K=16 per accumulator and stage
   const double partial_cyc = (double)pl.rows * cout * 8.0 / 2100.0; // write + re-read of one split's partial tile, chip-wide
   int splits = 1;
   double best = 1e300;
