@@ -42,8 +42,6 @@ def run(n_demons):
 # flow is recorded half-way (tight check) and at the end (loose check)
 flow_half = run(iters // 2)[0].demons.flow.detach().numpy()
 r, regul = run(iters)
-if False:
-    r = None
 grid = reg.compute_grid((size, size))
 with torch.no_grad():
     affined = r.affine_reg(src01)
