@@ -139,10 +139,10 @@ class FewshotVolumeReader(torch.utils.data.Dataset):
         mask = pad2factor(self.truncate_image(mask.astype(np.float32)), factor=16, pad_value=0)[None]
         imgs, _ = nrrd_io.read(os.path.join(self.data_dir, '%s_clean.nrrd' % pid))
         imgs = pad2factor(self.truncate_image(imgs), factor=16, pad_value=self.cfg['pad_value'])[None].astype(np.float32)
-        imgs, mask = keep_only_annotation_z_slices(imgs, mask)
-        imgs, mask = crop(imgs, mask, self.cfg.get('crop_size', [256, 256]), self.cfg.get('pad_value', -1024), 0)
-        imgs = normalize(imgs, minimum=self.cfg['HU_range'][0], maximum=self.cfg['HU_range'][1])
-        return {'image': imgs, 'mask': mask}
+        ct, roi = keep_only_annotation_z_slices(imgs, mask)                      # annotated z range only (:342)
+        ct, roi = crop(ct, roi, self.cfg.get('crop_size', [256, 256]), img_pad_value=self.cfg.get('pad_value', -1024), mask_pad_value=0)
+        lo_hu, hi_hu = self.cfg['HU_range']
+        return {'image': normalize(ct, minimum=lo_hu, maximum=hi_hu), 'mask': roi}
 
     def __getitem__(self, idx, supp_idx=None):
         """:253-322 — query = item idx; supports = n_shot other volumes of the same class drawn with random.choices (the
@@ -191,13 +191,14 @@ class FewshotSliceReader(torch.utils.data.Dataset):
         self.k = min([self.k] + num_slices)                                     # persists across items, as in :466
         k = self.k
         s_idx, q_idx = self.slice_blocks(num_slices, k)
-        test_shot = self.cfg.get('test_shot', self.cfg['n_shot'])
-        new_query_images = query_images[0][0].permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1)
-        new_query_labels = query_labels[0][0][0]
+        n_test_shots = self.cfg.get('test_shot', self.cfg['n_shot'])
+        q_vol, q_lab = query_images[0][0], query_labels[0][0]                  # [1, D, H, W] each
+        new_query_images = q_vol.permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1)   # slices become the batch, 3 channels (:517)
+        new_query_labels = q_lab[0]
         for i in range(len(support_images[0])):                                # the last support volume wins (:523-548)
             vol_i, lab_i = support_images[0][i], support_labels[0][i]
             per_shot_img, per_shot_lab = [], []
-            for m in range(test_shot):
+            for m in range(n_test_shots):
                 imgs, labs = [], []
                 for j in range(k):
                     n = int(q_idx[j + 1] - q_idx[j])
