@@ -76,6 +76,14 @@ __device__ __forceinline__ void unpack8_f16(const uint4& u, float* v) {
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }
+// split-fp16 representation x = hi + lo: the fp16 residual of 8 fp32 values against their rounded fp16 vector `hi`
+__device__ __forceinline__ uint4 residual8_f16(const float* v, const uint4& hi) {
+  float r[8];
+  unpack8_f16(hi, r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i] - r[i];
+  return pack8_f16(r);
+}
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll

@@ -30,13 +30,19 @@ constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBnGroups = 64;
 constexpr int kMaxCosP = 8;       // prototypes of the fused calDist epilogue (1 + ways)
 constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] doubles
+constexpr int kMaxSeg = 6;        // K segments per tap (split-fp16 convs: hi.Wh, lo.Wh, hi.Wl for up to two concat sources)
 
 struct ConvParams {
   int N, H, W;                    // pixel grid of the conv (input == output grid, stride 1)
   int bw_log2, bh_log2;           // tile box: bw x bh x bn pixels, bn = 128 / (bw * bh)
   int tiles_x, tiles_y, tiles_n;  // pixel tiles
   int n_tiles_c;                  // cout / BN
-  int chunks0, chunks1;           // 64-channel chunks of source 0 / source 1 (channel concat)
+  // K loop of one tap = `nseg` segments; segment s reads seg_n[s] 64-channel chunks of tensor map seg_map[s] from chunk
+  // seg_ach[s] on, against the weight chunks seg_wch[s].. of the packed weights.  Plain conv: (src0 | src1) channel concat.
+  // Split-fp16 conv (x = hi + lo, w = Wh + Wl, all fp16): hi.Wh + lo.Wh + hi.Wl accumulated in fp32 — fp32-class products
+  // from the fp16 tensor pipe (the dropped lo.Wl term is 2^-22 relative).
+  int nseg, kblocks_per_tap;
+  int seg_map[kMaxSeg], seg_ach[kMaxSeg], seg_wch[kMaxSeg], seg_n[kMaxSeg];
   int ntaps;
   int dy[kMaxTaps], dx[kMaxTaps];
   int tap_src[kMaxTaps];          // -1: channel concat of source 0 | source 1 (default); 0..3: the tap reads that source only
@@ -51,6 +57,9 @@ struct ConvParams {
   int oy_mul, oy_off, ox_mul, ox_off;
   __half* out_pool;               // optional 2x2/stride-2 max-pooled fp16 NHWC output (N, H/2, W/2, pool_C)
   int pool_C;
+  // split-fp16 outputs: the residual fp16(v - fp16(v)) of what `out` / `out_pool` hold, same indexing (null = not written)
+  __half* out_lo;
+  __half* out_pool_lo;
   float* out_f32;                 // optional fp32 NHWC output (N, H, W, f32_C)
   int f32_C;
   // optional residual (torchvision BasicBlock: out = relu(bn2(conv2(.)) + identity)): fp16 NHWC [N][H][W][res_C], added after the
@@ -115,7 +124,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kblocks_per_tap = p.chunks0 + p.chunks1;
+  const int kblocks_per_tap = p.kblocks_per_tap;
   const int num_kb = p.ntaps * kblocks_per_tap;
   const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   // work unit = CTAS consecutive pixel tiles x one cout tile; CTA `cta_rank` of the pair owns pixel tile unit * CTAS + cta_rank
@@ -181,25 +190,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
-          for (int kc = 0; kc < kblocks_per_tap; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
-            uint8_t* b_dst = a_dst + Cfg::kABytes;
-            const int ts = p.tap_src[tap];
-            const CUtensorMap* tm = ts < 0 ? (kc < p.chunks0 ? &tm_src0 : &tm_src1)
-                                           : (ts == 0 ? &tm_src0 : (ts == 1 ? &tm_src1 : (ts == 2 ? &tm_src2 : &tm_src3)));
-            const int kch = (ts < 0 && kc >= p.chunks0) ? kc - p.chunks0 : kc;
-            if (CTAS == 2) {
-              // both CTAs' bytes complete on the leader's barrier; only the leader arrives on it
-              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-              tma_load_4d_pair(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
-              if (!WS) tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN + (int)cta_rank * (BN / 2), tap);
-            } else {
-              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_4d(tm, &full_bar[stage], a_dst, kch * kBK, xs, ys, n0);
-              if (!WS) tma_load_3d(&tm_w, &full_bar[stage], b_dst, kc * kBK, ct * BN, tap);
+          const int ts = p.tap_src[tap];
+          for (int s = 0; s < p.nseg; ++s) {
+            const int mi = ts >= 0 ? ts : p.seg_map[s];
+            const CUtensorMap* tm = mi == 0 ? &tm_src0 : (mi == 1 ? &tm_src1 : (mi == 2 ? &tm_src2 : &tm_src3));
+            const int ach0 = p.seg_ach[s], wch0 = p.seg_wch[s], sn = p.seg_n[s];
+            for (int j = 0; j < sn; ++j) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
+              uint8_t* b_dst = a_dst + Cfg::kABytes;
+              if (CTAS == 2) {
+                // both CTAs' bytes complete on the leader's barrier; only the leader arrives on it
+                if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                tma_load_4d_pair(tm, &full_bar[stage], a_dst, (ach0 + j) * kBK, xs, ys, n0);
+                if (!WS) tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst, (wch0 + j) * kBK, ct * BN + (int)cta_rank * (BN / 2), tap);
+              } else {
+                mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                tma_load_4d(tm, &full_bar[stage], a_dst, (ach0 + j) * kBK, xs, ys, n0);
+                if (!WS) tma_load_3d(&tm_w, &full_bar[stage], b_dst, (wch0 + j) * kBK, ct * BN, tap);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -292,13 +303,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
       __half* o16 = nullptr;
+      __half* o16lo = nullptr;
       __half* opool = nullptr;
+      __half* opoollo = nullptr;
       float* o32 = nullptr;
-      if (p.out)
-        o16 = p.out + (static_cast<size_t>(n * p.out_H + y * p.oy_mul + p.oy_off) * p.out_W + x * p.ox_mul + p.ox_off) *
-                          p.out_C + p.out_coff + ct * BN;
-      if (p.out_pool)
-        opool = p.out_pool + (static_cast<size_t>(n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_C + ct * BN;
+      if (p.out) {
+        const size_t off = (static_cast<size_t>(n * p.out_H + y * p.oy_mul + p.oy_off) * p.out_W + x * p.ox_mul + p.ox_off) *
+                               p.out_C + p.out_coff + ct * BN;
+        o16 = p.out + off;
+        if (p.out_lo) o16lo = p.out_lo + off;
+      }
+      if (p.out_pool) {
+        const size_t off = (static_cast<size_t>(n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) * p.pool_C + ct * BN;
+        opool = p.out_pool + off;
+        if (p.out_pool_lo) opoollo = p.out_pool_lo + off;
+      }
       if (p.out_f32) o32 = p.out_f32 + (static_cast<size_t>(n * p.H + y) * p.W + x) * p.f32_C + ct * BN;
       const bool pool_writer = valid && ((x & 1) == 0) && ((y & 1) == 0);
       float cos_nn = 0.f, cos_pn[kMaxCosP], cos_dot[kMaxCosP];
@@ -378,8 +397,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         }
         if (o16 && valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(o16 + c0 + j) = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 hi = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
+            *reinterpret_cast<uint4*>(o16 + c0 + j) = hi;
+            if (o16lo) *reinterpret_cast<uint4*>(o16lo + c0 + j) = residual8_f16(v + j, hi);
+          }
         }
         if (p.out_pool) {      // 2x2 max over (x, x^1) and (y, y^1): partner lanes lane^1 and lane^bw
 #pragma unroll
@@ -389,8 +411,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           }
           if (pool_writer) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(opool + c0 + j) = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 hi = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
+              *reinterpret_cast<uint4*>(opool + c0 + j) = hi;
+              if (opoollo) *reinterpret_cast<uint4*>(opoollo + c0 + j) = residual8_f16(v + j, hi);
+            }
           }
         }
       }
@@ -555,25 +580,49 @@ using namespace rpnet;
 
 extern "C" int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                                   void* stream);
+extern "C" int rpnet_bn_stats_split_f16(const void* z_hi, const void* z_lo, int n, int h, int w, int c, const int* group_start,
+                                        int groups, double* sums, void* stream);
 
-static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
-                           const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
-                           const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
-                           int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
-                           void* out_pool_f16, float* out_f32, void* stream_, const int* bn_group_start = nullptr,
-                           int bn_groups = 0, double* bn_sums = nullptr, int* bn_fused = nullptr, const float* cos_protos = nullptr,
-                           int cos_P = 0, int cos_sets = 0, float cos_scaler = 0.f, float* cos_pred = nullptr, int bn_keep_sums = 0,
-                           const void* const* view_ptr = nullptr, const long long* view_strides = nullptr, const int* tap_src = nullptr,
-                           const void* res_f16 = nullptr) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RPNET_REQUIRE(src0 && wpack && scale && shift, "conv_igemm: null pointer argument");
+namespace {
+// One launch of conv_igemm_kernel, as the C-ABI entry points describe it.
+struct ConvCall {
+  bool bf16 = false;
+  const void* src0 = nullptr; int c0 = 0;
+  const void* src1 = nullptr; int c1 = 0;
+  // split-fp16: residual planes of the sources (same shapes) and a weight pack [ntaps][cout][2 * (c0 + c1)] = Wh | Wl
+  const void* src0_lo = nullptr;
+  const void* src1_lo = nullptr;
+  bool w_split = false;
+  int n = 0, h = 0, w = 0;
+  const void* wpack = nullptr; int ntaps = 0; const int* tap_dy = nullptr; const int* tap_dx = nullptr; int cout = 0;
+  const float* scale = nullptr; const float* shift = nullptr; int relu = 0;
+  void* out = nullptr; void* out_lo = nullptr; int out_h = 0, out_w = 0, out_c = 0, out_coff = 0;
+  int oy_mul = 1, oy_off = 0, ox_mul = 1, ox_off = 0;
+  void* out_pool = nullptr; void* out_pool_lo = nullptr; float* out_f32 = nullptr;
+  void* stream = nullptr;
+  const int* bn_group_start = nullptr; int bn_groups = 0; double* bn_sums = nullptr; int* bn_fused = nullptr; int bn_keep_sums = 0;
+  const float* cos_protos = nullptr; int cos_P = 0, cos_sets = 0; float cos_scaler = 0.f; float* cos_pred = nullptr;
+  const void* const* view_ptr = nullptr; const long long* view_strides = nullptr; const int* tap_src = nullptr;
+  const void* res = nullptr;
+};
+}  // namespace
+
+static int conv_igemm_run(const ConvCall& a) {
+  cudaStream_t stream = static_cast<cudaStream_t>(a.stream);
+  const int c0 = a.c0, c1 = a.c1, n = a.n, h = a.h, w = a.w, ntaps = a.ntaps, cout = a.cout;
+  const bool bf16 = a.bf16;
+  RPNET_REQUIRE(a.src0 && a.wpack && a.scale && a.shift, "conv_igemm: null pointer argument");
   RPNET_REQUIRE(c0 > 0 && c0 % kBK == 0 && c1 >= 0 && c1 % kBK == 0, "conv_igemm: channel counts must be multiples of 64 (got %d, %d)", c0, c1);
-  RPNET_REQUIRE(c1 == 0 || src1, "conv_igemm: src1 is null but c1 = %d", c1);
+  RPNET_REQUIRE(c1 == 0 || a.src1, "conv_igemm: src1 is null but c1 = %d", c1);
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv_igemm: bad grid %d x %d x %d", n, h, w);
   RPNET_REQUIRE(ntaps >= 1 && ntaps <= kMaxTaps, "conv_igemm: ntaps %d out of range [1, %d]", ntaps, kMaxTaps);
   RPNET_REQUIRE(cout >= 64 && cout % 64 == 0, "conv_igemm: cout must be a multiple of 64 (got %d)", cout);
-  RPNET_REQUIRE(out_f16 || out_pool_f16 || out_f32 || cos_pred, "conv_igemm: no output requested");
-  RPNET_REQUIRE(!out_pool_f16 || (h % 2 == 0 && w % 2 == 0), "conv_igemm: fused 2x2 max-pool needs even H, W (got %d x %d)", h, w);
+  RPNET_REQUIRE(a.out || a.out_pool || a.out_f32 || a.cos_pred, "conv_igemm: no output requested");
+  RPNET_REQUIRE(!a.out_pool || (h % 2 == 0 && w % 2 == 0), "conv_igemm: fused 2x2 max-pool needs even H, W (got %d x %d)", h, w);
+  RPNET_REQUIRE((!a.out_lo || a.out) && (!a.out_pool_lo || a.out_pool), "conv_igemm: a residual output needs its main output");
+  const bool a_split = a.src0_lo != nullptr;
+  RPNET_REQUIRE(!a_split || c1 == 0 || a.src1_lo, "conv_igemm: split sources need both residual planes");
+  RPNET_REQUIRE(!(a_split || a.w_split) || (!a.tap_src && !bf16), "conv_igemm: split-fp16 operands are fp16, without per-tap views");
   const int BN = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
 
   ConvParams p{};
@@ -581,90 +630,104 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   const int bw = pow2_floor(w < 16 ? w : 16);
   const int bh = pow2_floor(h < kBM / bw ? h : kBM / bw);
   const int bn = kBM / (bw * bh);
-  RPNET_REQUIRE(!out_pool_f16 || (bw >= 2 && bh >= 2), "conv_igemm: fused pooling needs a tile of at least 2x2 pixels");
+  RPNET_REQUIRE(!a.out_pool || (bw >= 2 && bh >= 2), "conv_igemm: fused pooling needs a tile of at least 2x2 pixels");
   p.bw_log2 = ilog2(bw); p.bh_log2 = ilog2(bh);
   p.tiles_x = (w + bw - 1) / bw; p.tiles_y = (h + bh - 1) / bh; p.tiles_n = (n + bn - 1) / bn;
   p.n_tiles_c = cout / BN;
-  p.chunks0 = c0 / kBK; p.chunks1 = c1 / kBK;
+  {
+    // K segments of one tap: tensor maps 0 / 1 = the sources, 2 / 3 = their residual planes
+    const int n0 = c0 / kBK, n1 = c1 / kBK, ncin = n0 + n1;
+    int s = 0;
+    auto seg = [&](int map, int wch, int cnt) {
+      if (cnt > 0) { p.seg_map[s] = map; p.seg_ach[s] = 0; p.seg_wch[s] = wch; p.seg_n[s] = cnt; ++s; }
+    };
+    seg(0, 0, n0);
+    seg(1, n0, n1);
+    if (a_split) { seg(2, 0, n0); seg(3, n0, n1); }
+    if (a.w_split) { seg(0, ncin, n0); seg(1, ncin + n0, n1); }
+    p.nseg = s;
+    p.kblocks_per_tap = 0;
+    for (int i = 0; i < s; ++i) p.kblocks_per_tap += p.seg_n[i];
+  }
   p.ntaps = ntaps;
-  for (int i = 0; i < ntaps; ++i) { p.dy[i] = tap_dy[i]; p.dx[i] = tap_dx[i]; p.tap_src[i] = tap_src ? tap_src[i] : -1; }
-  if (tap_src) {
-    RPNET_REQUIRE(view_ptr && view_strides && c1 == 0, "conv_igemm: per-tap sources need the four views and no channel concat");
-    for (int i = 0; i < ntaps; ++i) RPNET_REQUIRE(tap_src[i] >= 0 && tap_src[i] < 4, "conv_igemm: tap source %d out of range", tap_src[i]);
+  for (int i = 0; i < ntaps; ++i) { p.dy[i] = a.tap_dy[i]; p.dx[i] = a.tap_dx[i]; p.tap_src[i] = a.tap_src ? a.tap_src[i] : -1; }
+  if (a.tap_src) {
+    RPNET_REQUIRE(a.view_ptr && a.view_strides && c1 == 0, "conv_igemm: per-tap sources need the four views and no channel concat");
+    for (int i = 0; i < ntaps; ++i) RPNET_REQUIRE(a.tap_src[i] >= 0 && a.tap_src[i] < 4, "conv_igemm: tap source %d out of range", a.tap_src[i]);
   }
-  p.scale = scale; p.shift = shift; p.relu = relu;
+  p.scale = a.scale; p.shift = a.shift; p.relu = a.relu;
   p.in_bf16 = bf16 ? 1 : 0; p.out_bf16 = bf16 ? 1 : 0;
-  p.out = static_cast<__half*>(out_f16);
-  p.out_H = out_h; p.out_W = out_w; p.out_C = out_c; p.out_coff = out_coff;
-  p.oy_mul = oy_mul; p.oy_off = oy_off; p.ox_mul = ox_mul; p.ox_off = ox_off;
-  p.out_pool = static_cast<__half*>(out_pool_f16); p.pool_C = cout;
-  p.out_f32 = out_f32; p.f32_C = cout;
+  p.out = static_cast<__half*>(a.out); p.out_lo = static_cast<__half*>(a.out_lo);
+  p.out_H = a.out_h; p.out_W = a.out_w; p.out_C = a.out_c; p.out_coff = a.out_coff;
+  p.oy_mul = a.oy_mul; p.oy_off = a.oy_off; p.ox_mul = a.ox_mul; p.ox_off = a.ox_off;
+  p.out_pool = static_cast<__half*>(a.out_pool); p.out_pool_lo = static_cast<__half*>(a.out_pool_lo); p.pool_C = cout;
+  p.out_f32 = a.out_f32; p.f32_C = cout;
   p.bn_sums = nullptr; p.bn_groups = 0;
-  if (bn_fused) *bn_fused = 0;
-  p.res = static_cast<const __half*>(res_f16); p.res_C = cout;
+  if (a.bn_fused) *a.bn_fused = 0;
+  p.res = static_cast<const __half*>(a.res); p.res_C = cout;
   p.cos_pred = nullptr; p.cos_protos = nullptr; p.cos_P = 0; p.cos_sets = 1; p.cos_scaler = 0.f;
-  if (cos_pred) {
-    RPNET_REQUIRE(cout == 64 && cos_protos && cos_P >= 1 && cos_P <= kMaxCosP && cos_sets >= 1,
-                  "conv_igemm: the fused calDist epilogue needs cout == 64 and 1..%d prototypes (got cout=%d, P=%d)", kMaxCosP, cout, cos_P);
-    p.cos_pred = cos_pred; p.cos_protos = cos_protos; p.cos_P = cos_P; p.cos_sets = cos_sets; p.cos_scaler = cos_scaler;
+  if (a.cos_pred) {
+    RPNET_REQUIRE(cout == 64 && a.cos_protos && a.cos_P >= 1 && a.cos_P <= kMaxCosP && a.cos_sets >= 1,
+                  "conv_igemm: the fused calDist epilogue needs cout == 64 and 1..%d prototypes (got cout=%d, P=%d)", kMaxCosP, cout, a.cos_P);
+    p.cos_pred = a.cos_pred; p.cos_protos = a.cos_protos; p.cos_P = a.cos_P; p.cos_sets = a.cos_sets; p.cos_scaler = a.cos_scaler;
   }
-  if (bn_sums) {
+  if (a.bn_sums) {
     // fuse the statistics when no pixel tile straddles two call groups and the per-CTA accumulators fit
-    RPNET_REQUIRE(bn_groups >= 1 && bn_groups <= kMaxBnGroups && bn_group_start, "conv_igemm: bn groups %d out of range [1, %d]", bn_groups, kMaxBnGroups);
-    RPNET_REQUIRE(bn_group_start[0] == 0 && bn_group_start[bn_groups] == n, "conv_igemm: bn group_start must span [0, %d]", n);
+    RPNET_REQUIRE(a.bn_groups >= 1 && a.bn_groups <= kMaxBnGroups && a.bn_group_start, "conv_igemm: bn groups %d out of range [1, %d]", a.bn_groups, kMaxBnGroups);
+    RPNET_REQUIRE(a.bn_group_start[0] == 0 && a.bn_group_start[a.bn_groups] == n, "conv_igemm: bn group_start must span [0, %d]", n);
     bool ok = cout <= kMaxBnCout;
-    for (int g = 1; g < bn_groups; ++g) ok = ok && (bn_group_start[g] % bn == 0);
+    for (int g = 1; g < a.bn_groups; ++g) ok = ok && (a.bn_group_start[g] % bn == 0);
     if (ok) {
-      p.bn_sums = bn_sums; p.bn_groups = bn_groups;
-      for (int g = 0; g <= bn_groups; ++g) p.bn_start[g] = bn_group_start[g];
-      if (!bn_keep_sums) RPNET_CUDA_OK(cudaMemsetAsync(bn_sums, 0, (size_t)bn_groups * cout * 2 * sizeof(double), stream));
-      if (bn_fused) *bn_fused = 1;
+      p.bn_sums = a.bn_sums; p.bn_groups = a.bn_groups;
+      for (int g = 0; g <= a.bn_groups; ++g) p.bn_start[g] = a.bn_group_start[g];
+      if (!a.bn_keep_sums) RPNET_CUDA_OK(cudaMemsetAsync(a.bn_sums, 0, (size_t)a.bn_groups * cout * 2 * sizeof(double), stream));
+      if (a.bn_fused) *a.bn_fused = 1;
     }
   }
-  if (out_f16) {
-    RPNET_REQUIRE(out_c % 8 == 0 && out_coff % 8 == 0 && out_coff + cout <= out_c, "conv_igemm: bad output channel window (%d + %d in %d)", out_coff, cout, out_c);
-    RPNET_REQUIRE((h - 1) * oy_mul + oy_off < out_h && (w - 1) * ox_mul + ox_off < out_w && oy_off >= 0 && ox_off >= 0,
-                  "conv_igemm: output mapping exceeds the %d x %d output", out_h, out_w);
+  if (a.out) {
+    RPNET_REQUIRE(a.out_c % 8 == 0 && a.out_coff % 8 == 0 && a.out_coff + cout <= a.out_c, "conv_igemm: bad output channel window (%d + %d in %d)", a.out_coff, cout, a.out_c);
+    RPNET_REQUIRE((h - 1) * a.oy_mul + a.oy_off < a.out_h && (w - 1) * a.ox_mul + a.ox_off < a.out_w && a.oy_off >= 0 && a.ox_off >= 0,
+                  "conv_igemm: output mapping exceeds the %d x %d output", a.out_h, a.out_w);
   }
 
   CUtensorMap t0, t1, t2, t3, tw;
   const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-  if (tap_src) {
+  if (a.tap_src) {
     // four strided views of one tensor (the parity phases of a 2x up-sampled map): same dims, custom pixel strides
     CUtensorMap* tv[4] = {&t0, &t1, &t2, &t3};
     const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-    const uint64_t str[3] = {(uint64_t)view_strides[0], (uint64_t)view_strides[1], (uint64_t)view_strides[2]};
+    const uint64_t str[3] = {(uint64_t)a.view_strides[0], (uint64_t)a.view_strides[1], (uint64_t)a.view_strides[2]};
     for (int v = 0; v < 4; ++v) {
-      int rc = make_tmap_2b(tv[v], view_ptr[v], 4, dims, str, abox, bf16);
+      int rc = make_tmap_2b(tv[v], a.view_ptr[v], 4, dims, str, abox, bf16);
       if (rc) return rc;
     }
   } else {
-    {
-      const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-      const uint64_t str[3] = {(uint64_t)c0, (uint64_t)c0 * w, (uint64_t)c0 * w * h};
-      int rc = make_tmap_2b(&t0, src0, 4, dims, str, abox, bf16);
+    auto dense = [&](CUtensorMap* m, const void* ptr, int c) {
+      const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+      const uint64_t str[3] = {(uint64_t)c, (uint64_t)c * w, (uint64_t)c * w * h};
+      return make_tmap_2b(m, ptr, 4, dims, str, abox, bf16);
+    };
+    int rc = dense(&t0, a.src0, c0);
+    if (rc) return rc;
+    if (c1 > 0) { rc = dense(&t1, a.src1, c1); if (rc) return rc; } else t1 = t0;
+    if (a_split) {
+      rc = dense(&t2, a.src0_lo, c0);
       if (rc) return rc;
-    }
-    if (c1 > 0) {
-      const uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-      const uint64_t str[3] = {(uint64_t)c1, (uint64_t)c1 * w, (uint64_t)c1 * w * h};
-      int rc = make_tmap_2b(&t1, src1, 4, dims, str, abox, bf16);
-      if (rc) return rc;
+      if (c1 > 0) { rc = dense(&t3, a.src1_lo, c1); if (rc) return rc; } else t3 = t2;
     } else {
-      t1 = t0;
+      t2 = t0;
+      t3 = t0;
     }
-    t2 = t0;
-    t3 = t0;
   }
-  const bool ws = cout == 64 && ntaps * (p.chunks0 + p.chunks1) <= kWsMaxKb && p.tiles_x * p.tiles_y * p.tiles_n >= 4 * num_sms() &&
-                  !getenv("RPNET_CONV_NO_WS");
+  const bool ws = cout == 64 && !a_split && !a.w_split && ntaps * p.kblocks_per_tap <= kWsMaxKb &&
+                  p.tiles_x * p.tiles_y * p.tiles_n >= 4 * num_sms() && !getenv("RPNET_CONV_NO_WS");
   const bool pair = !ws && pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
   {
-    const uint64_t cin = (uint64_t)(c0 + c1);
+    const uint64_t cin = (uint64_t)(c0 + c1) * (a.w_split ? 2 : 1);
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
     const uint64_t str[2] = {cin, cin * cout};
     const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)(pair ? BN / 2 : BN), 1};
-    int rc = make_tmap_2b(&tw, wpack, 3, dims, str, box, bf16);
+    int rc = make_tmap_2b(&tw, a.wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
   }
   if (pair) {
@@ -682,14 +745,28 @@ static int conv_igemm_impl(bool bf16, const void* src0, int c0, const void* src1
   }
 }
 
+// the argument block shared by the plain entry points
+static ConvCall plain_call(bool bf16, const void* src0, int c0, const void* src1, int c1, int n, int h, int w, const void* wpack,
+                           int ntaps, const int* tap_dy, const int* tap_dx, int cout, const float* scale, const float* shift, int relu,
+                           void* stream) {
+  ConvCall a;
+  a.bf16 = bf16; a.src0 = src0; a.c0 = c0; a.src1 = src1; a.c1 = c1; a.n = n; a.h = h; a.w = w; a.wpack = wpack; a.ntaps = ntaps;
+  a.tap_dy = tap_dy; a.tap_dx = tap_dx; a.cout = cout; a.scale = scale; a.shift = shift; a.relu = relu; a.stream = stream;
+  a.out_h = h; a.out_w = w; a.out_c = cout;
+  return a;
+}
+
 // See include/rpnet_b200.h for the contract.
 RPNET_API int rpnet_conv_igemm_f16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
                                     const void* wpack, int ntaps, const int* tap_dy, const int* tap_dx, int cout,
                                     const float* scale, const float* shift, int relu, void* out_f16, int out_h, int out_w,
                                     int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                                     void* out_pool_f16, float* out_f32, void* stream_) {
-  return conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_f16,
-                         out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off, out_pool_f16, out_f32, stream_);
+  ConvCall a = plain_call(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
+  a.out = out_f16; a.out_h = out_h; a.out_w = out_w; a.out_c = out_c; a.out_coff = out_coff;
+  a.oy_mul = oy_mul; a.oy_off = oy_off; a.ox_mul = ox_mul; a.ox_off = ox_off;
+  a.out_pool = out_pool_f16; a.out_f32 = out_f32;
+  return conv_igemm_run(a);
 }
 
 RPNET_API int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, int c1, int n, int h, int w,
@@ -697,8 +774,39 @@ RPNET_API int rpnet_conv_igemm_bf16(const void* src0, int c0, const void* src1, 
                                      const float* scale, const float* shift, int relu, void* out_bf16, int out_h, int out_w,
                                      int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                                      void* out_pool_bf16, float* out_f32, void* stream_) {
-  return conv_igemm_impl(true, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_bf16,
-                         out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off, out_pool_bf16, out_f32, stream_);
+  ConvCall a = plain_call(true, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
+  a.out = out_bf16; a.out_h = out_h; a.out_w = out_w; a.out_c = out_c; a.out_coff = out_coff;
+  a.oy_mul = oy_mul; a.oy_off = oy_off; a.ox_mul = ox_mul; a.ox_off = ox_off;
+  a.out_pool = out_pool_bf16; a.out_f32 = out_f32;
+  return conv_igemm_run(a);
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_split_f16(const void* src0_hi, const void* src0_lo, int c0, const void* src1_hi, const void* src1_lo, int c1,
+                                    int n, int h, int w, const void* wpack, int w_split, int ntaps, const int* tap_dy, const int* tap_dx,
+                                    int cout, const float* scale, const float* shift, int relu, void* out_hi, void* out_lo, int out_h,
+                                    int out_w, int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
+                                    void* out_pool_hi, void* out_pool_lo, float* out_f32, const int* group_start, int groups,
+                                    double* sums, int keep_sums, void* stream_) {
+  ConvCall a = plain_call(false, src0_hi, c0, src1_hi, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
+  a.src0_lo = src0_lo; a.src1_lo = src1_lo; a.w_split = w_split != 0;
+  a.out = out_hi; a.out_lo = out_lo; a.out_h = out_h; a.out_w = out_w; a.out_c = out_c; a.out_coff = out_coff;
+  a.oy_mul = oy_mul; a.oy_off = oy_off; a.ox_mul = ox_mul; a.ox_off = ox_off;
+  a.out_pool = out_pool_hi; a.out_pool_lo = out_pool_lo; a.out_f32 = out_f32;
+  if (!sums) return conv_igemm_run(a);
+  // train mode: BatchNorm statistics of the fp32 accumulators in the epilogue (dense identity-mapped or sub-pixel output)
+  RPNET_REQUIRE(out_hi && group_start, "conv_split: the BatchNorm statistics need the z output and the call groups");
+  int fused = 0;
+  a.bn_group_start = group_start; a.bn_groups = groups; a.bn_sums = sums; a.bn_fused = &fused; a.bn_keep_sums = keep_sums;
+  int rc = conv_igemm_run(a);
+  if (rc) return rc;
+  if (!fused) {
+    RPNET_REQUIRE(oy_mul == 1 && ox_mul == 1 && out_coff == 0 && out_c == cout && !keep_sums,
+                  "conv_split: BatchNorm statistics cannot be fused for this %d x %d sub-pixel launch", h, w);
+    return out_lo ? rpnet_bn_stats_split_f16(out_hi, out_lo, n, h, w, cout, group_start, groups, sums, stream_)
+                  : rpnet_bn_stats_f16(out_hi, n, h, w, cout, group_start, groups, sums, stream_);
+  }
+  return 0;
 }
 
 // See include/rpnet_b200.h for the contract.
@@ -708,8 +816,10 @@ RPNET_API int rpnet_conv_bnstats_f16(const void* src0, int c0, const void* src1,
                                       void* stream_) {
   RPNET_REQUIRE(z_f16 && sums && group_start, "conv_bnstats: null pointer argument");
   int fused = 0;
-  int rc = conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, ones, zeros, 0, z_f16, h, w, cout,
-                           0, 1, 0, 1, 0, nullptr, nullptr, stream_, group_start, groups, sums, &fused);
+  ConvCall a = plain_call(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, ones, zeros, 0, stream_);
+  a.out = z_f16;
+  a.bn_group_start = group_start; a.bn_groups = groups; a.bn_sums = sums; a.bn_fused = &fused;
+  int rc = conv_igemm_run(a);
   if (rc) return rc;
   if (!fused) return rpnet_bn_stats_f16(z_f16, n, h, w, cout, group_start, groups, sums, stream_);   // tiny maps: separate pass
   return 0;
@@ -721,8 +831,10 @@ RPNET_API int rpnet_conv_cos_f16(const void* src0, int c0, const void* src1, int
                                   const float* protos, int n_protos, int proto_sets, float scaler, float* pred, float* out_f32,
                                   void* stream_) {
   RPNET_REQUIRE(protos && pred, "conv_cos: null pointer argument");
-  return conv_igemm_impl(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, 64, scale, shift, relu, nullptr, h, w, 64, 0, 1,
-                         0, 1, 0, nullptr, out_f32, stream_, nullptr, 0, nullptr, nullptr, protos, n_protos, proto_sets, scaler, pred);
+  ConvCall a = plain_call(false, src0, c0, src1, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, 64, scale, shift, relu, stream_);
+  a.out_f32 = out_f32;
+  a.cos_protos = protos; a.cos_P = n_protos; a.cos_sets = proto_sets; a.cos_scaler = scaler; a.cos_pred = pred;
+  return conv_igemm_run(a);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -742,8 +854,10 @@ RPNET_API int rpnet_upconv_phase_bnstats_f16(const void* x_low, int cin, int n, 
     dx[t] = (px == 0 ? -1 : 0) + (t & 1);
   }
   int fused = 0;
-  int rc = conv_igemm_impl(false, x_low, cin, nullptr, 0, n, h, w, wphase, 4, dy, dx, cout, ones, zeros, 0, z_f16, 2 * h, 2 * w, cout, 0, 2,
-                           py, 2, px, nullptr, nullptr, stream_, group_start, groups, sums, &fused, nullptr, 0, 0, 0.f, nullptr, keep_sums);
+  ConvCall a = plain_call(false, x_low, cin, nullptr, 0, n, h, w, wphase, 4, dy, dx, cout, ones, zeros, 0, stream_);
+  a.out = z_f16; a.out_h = 2 * h; a.out_w = 2 * w; a.oy_mul = 2; a.oy_off = py; a.ox_mul = 2; a.ox_off = px;
+  a.bn_group_start = group_start; a.bn_groups = groups; a.bn_sums = sums; a.bn_fused = &fused; a.bn_keep_sums = keep_sums;
+  int rc = conv_igemm_run(a);
   if (rc) return rc;
   if (!fused) {
     set_error("upconv_phase: BatchNorm statistics cannot be fused for %d x %d maps (tile straddles call groups)", h, w);
@@ -771,8 +885,10 @@ RPNET_API int rpnet_upconv_dgrad_bf16(const void* dz, int cout, int n, int h, in
   for (int v = 0; v < 4; ++v)
     views[v] = static_cast<const __nv_bfloat16*>(dz) + ((size_t)(v >> 1) * (2 * w) + (v & 1)) * cout;
   const long long strides[3] = {2LL * cout, 2LL * (2 * w) * cout, (long long)(2 * h) * (2 * w) * cout};
-  return conv_igemm_impl(true, views[0], cout, nullptr, 0, n, h, w, w16, 16, dy, dx, cin, ones, zeros, 0, out, h, w, out_c, out_coff, 1, 0, 1,
-                         0, nullptr, nullptr, stream_, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, views, strides, src);
+  ConvCall a = plain_call(true, views[0], cout, nullptr, 0, n, h, w, w16, 16, dy, dx, cin, ones, zeros, 0, stream_);
+  a.out = out; a.out_c = out_c; a.out_coff = out_coff;
+  a.view_ptr = views; a.view_strides = strides; a.tap_src = src;
+  return conv_igemm_run(a);
 }
 
 // See include/rpnet_b200.h for the contract.
@@ -780,7 +896,8 @@ RPNET_API int rpnet_conv_res_f16(const void* src, int cin, int n, int h, int w, 
                                   const int* tap_dx, int cout, const float* scale, const float* shift, const void* res_f16, int relu,
                                   void* out_f16, void* stream_) {
   RPNET_REQUIRE(out_f16, "conv_res: null output");
-  return conv_igemm_impl(false, src, cin, nullptr, 0, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, out_f16, h, w, cout, 0,
-                         1, 0, 1, 0, nullptr, nullptr, stream_, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0.f, nullptr, 0, nullptr, nullptr,
-                         nullptr, res_f16);
+  ConvCall a = plain_call(false, src, cin, nullptr, 0, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
+  a.out = out_f16;
+  a.res = res_f16;
+  return conv_igemm_run(a);
 }

@@ -54,7 +54,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][CIN][3][3]*/,
                      const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
-                     int N, int H, int W) {
+                     __half* __restrict__ out_lo, int N, int H, int W) {
   __shared__ float s_w[9 * CIN][64];      // [tap*CIN + ci][co]
   __shared__ float s_sc[64], s_sh[64];
   for (int i = threadIdx.x; i < 64 * CIN * 9; i += blockDim.x) {
@@ -95,7 +95,9 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
       float t = fmaf(acc[j], s_sc[cg * 8 + j], s_sh[cg * 8 + j]);
       acc[j] = relu ? fmaxf(t, 0.f) : t;
     }
-    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = pack8(acc);
+    const uint4 hi = pack8(acc);
+    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = hi;
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 8) = residual8_f16(acc, hi);
   }
 }
 
@@ -105,7 +107,7 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
 __global__ void __launch_bounds__(256)
 conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][1][3][3]*/,
                         const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
-                        int N, int H, int W) {
+                        __half* __restrict__ out_lo, int N, int H, int W) {
   const int cg = threadIdx.x & 7;
   float wr[9][8], sh[8];
 #pragma unroll
@@ -150,8 +152,13 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
       for (int j = 0; j < 8; ++j) { a0[j] = fmaxf(a0[j], 0.f); a1[j] = fmaxf(a1[j], 0.f); }
     }
     const long long pix = (n * H + y) * W + x;
-    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = pack8(a0);
-    if (x + 1 < W) *reinterpret_cast<uint4*>(out + (pix + 1) * 64 + cg * 8) = pack8(a1);
+    const uint4 h0 = pack8(a0), h1 = pack8(a1);
+    *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = h0;
+    if (x + 1 < W) *reinterpret_cast<uint4*>(out + (pix + 1) * 64 + cg * 8) = h1;
+    if (out_lo) {                                                 // split-fp16 residual plane
+      *reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 8) = residual8_f16(a0, h0);
+      if (x + 1 < W) *reinterpret_cast<uint4*>(out_lo + (pix + 1) * 64 + cg * 8) = residual8_f16(a1, h1);
+    }
   }
 }
 
@@ -616,10 +623,18 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 4; }
+RPNET_API int rpnet_abi_version(void) { return 5; }
+
+RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
+                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_);
 
 RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                        const float* shift, int relu, void* out_f16, void* stream_) {
+  return rpnet_conv3x3_first_split_f16(img, n, cin, h, w, weight, scale, shift, relu, out_f16, nullptr, stream_);
+}
+
+RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
+                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv3x3_first: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first: bad shape %d x %d x %d", n, h, w);
@@ -628,9 +643,10 @@ RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, i
   const int grid = grid_for(total, 256);
   if (cin == 1)
     conv3x3_first_c1_kernel<<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
-        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
+        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), n, h, w);
   else
-    conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16), n, h, w);
+    conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
+                                                      static_cast<__half*>(out_lo_f16), n, h, w);
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");
 }
 

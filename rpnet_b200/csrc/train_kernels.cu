@@ -95,7 +95,8 @@ static int grid_for(long long total, int block, int cap_mult = 16) {
 // tree over the pixel lanes, one atomicAdd per channel per block.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, double* __restrict__ sums /*[G][C][2]*/) {
+bn_stats_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, Groups gr, int HW, int c8,
+                double* __restrict__ sums /*[G][C][2]*/) {
   __shared__ float s_red[256 * 16];
   int g, bx, nbx;
   group_block(gr, g, bx, nbx);
@@ -108,6 +109,12 @@ bn_stats_kernel(const uint4* __restrict__ z, Groups gr, int HW, int c8, double* 
   for (long long p = p0 + (long long)bx * lanes + pl; p < p1; p += (long long)nbx * lanes) {
     float f[8];
     unpack8_f16(__ldg(z + p * c8 + v), f);
+    if (z_lo) {                                   // split-fp16 z = hi + lo
+      float l[8];
+      unpack8_f16(__ldg(z_lo + p * c8 + v), l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += l[j];
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
   }
@@ -167,8 +174,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, Groups gr, i
 // with all loads issued before the math; 32-bit index arithmetic (n*h*w < 2^31).
 template <bool POOL>
 __global__ void __launch_bounds__(256, 2)
-bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Groups gr, int N, int H, int W, int c8, int relu,
-                uint4* __restrict__ y16, float* __restrict__ y32, uint4* __restrict__ ypool) {
+bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, const float* __restrict__ stats, Groups gr, int N, int H,
+                int W, int c8, int relu, uint4* __restrict__ y16, uint4* __restrict__ y16_lo, float* __restrict__ y32,
+                uint4* __restrict__ ypool, uint4* __restrict__ ypool_lo) {
   constexpr int U = POOL ? 2 : 4;
   const int C = c8 * 8;
   const int lanes = 256 / c8;
@@ -185,7 +193,7 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Gr
     a[j] = st.z; b[j] = st.w;
   }
   for (unsigned u0 = blockIdx.x * lanes + pl; u0 < units; u0 += U * stride) {
-    uint4 zin[U][POOL ? 4 : 1];
+    uint4 zin[U][POOL ? 4 : 1], zlo[U][POOL ? 4 : 1];
     unsigned pix[U][POOL ? 4 : 1];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
@@ -198,10 +206,12 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Gr
           for (int q = 0; q < 4; ++q) {
             pix[k][q] = (n * H + ys * 2 + (q >> 1)) * W + xs * 2 + (q & 1);
             zin[k][q] = __ldg(z + (size_t)pix[k][q] * c8 + v);
+            if (z_lo) zlo[k][q] = __ldg(z_lo + (size_t)pix[k][q] * c8 + v);
           }
         } else {
           pix[k][0] = u;
           zin[k][0] = __ldg(z + (size_t)u * c8 + v);
+          if (z_lo) zlo[k][0] = __ldg(z_lo + (size_t)u * c8 + v);
         }
       }
     }
@@ -224,6 +234,12 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Gr
       for (int q = 0; q < (POOL ? 4 : 1); ++q) {
         float f[8];
         unpack8_f16(zin[k][q], f);
+        if (z_lo) {                               // split-fp16 z = hi + lo
+          float l[8];
+          unpack8_f16(zlo[k][q], l);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += l[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float r = fmaf(f[j], a[j], b[j]);
@@ -231,14 +247,22 @@ bn_apply_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, Gr
           f[j] = r;
           best[j] = fmaxf(best[j], r);
         }
-        if (y16) y16[(size_t)pix[k][q] * c8 + v] = pack8_f16(f);
+        if (y16) {
+          const uint4 hi = pack8_f16(f);
+          y16[(size_t)pix[k][q] * c8 + v] = hi;
+          if (y16_lo) y16_lo[(size_t)pix[k][q] * c8 + v] = residual8_f16(f, hi);
+        }
         if (y32) {
           float4* d = reinterpret_cast<float4*>(y32 + ((size_t)pix[k][q] * c8 + v) * 8);
           d[0] = make_float4(f[0], f[1], f[2], f[3]);
           d[1] = make_float4(f[4], f[5], f[6], f[7]);
         }
       }
-      if (POOL) ypool[(size_t)u * c8 + v] = pack8_f16(best);
+      if (POOL) {
+        const uint4 hi = pack8_f16(best);
+        ypool[(size_t)u * c8 + v] = hi;
+        if (ypool_lo) ypool_lo[(size_t)u * c8 + v] = residual8_f16(best, hi);
+      }
     }
   }
 }
@@ -678,7 +702,7 @@ __global__ void premask_bwd_kernel(const uint4* __restrict__ dxfg, const uint4* 
 // wd rows along cout.
 __global__ void __launch_bounds__(256)
 pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
-                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int split) {
   __shared__ float s_w[32][32 * 9 + 1];                           // [co][ci * ntaps + t]
   const int cin_real = cin - hole_len;
   const int tiles_ci = (cin + 31) / 32;
@@ -698,8 +722,17 @@ pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntap
   const int lane = threadIdx.x & 31, rowi = threadIdx.x >> 5;     // 8 rows per pass
   for (int t = 0; t < ntaps; ++t) {
     for (int r = rowi; r < 32; r += 8) {
-      if (wf && co0 + r < cout && ci0 + lane < cin)                // wf[t][co][ci]: lanes along ci
-        wf[((size_t)t * cout + co0 + r) * cin + ci0 + lane] = __float2half_rn(s_w[r][lane * ntaps + t]);
+      if (wf && co0 + r < cout && ci0 + lane < cin) {              // wf[t][co][ci]: lanes along ci
+        const float val = s_w[r][lane * ntaps + t];
+        const __half hi = __float2half_rn(val);
+        if (split) {                                               // split-fp16 pack [t][co][Wh (cin) | Wl (cin)]
+          __half* row = wf + ((size_t)t * cout + co0 + r) * (2 * cin);
+          row[ci0 + lane] = hi;
+          row[cin + ci0 + lane] = __float2half_rn(val - __half2float(hi));
+        } else {
+          wf[((size_t)t * cout + co0 + r) * cin + ci0 + lane] = hi;
+        }
+      }
       if (wd && ci0 + r < cin && co0 + lane < cout)                // wd[t][ci][co]: lanes along co
         wd[((size_t)t * cin + ci0 + r) * cout + co0 + lane] = __float2bfloat16_rn(s_w[lane][r * ntaps + t]);
     }
@@ -712,7 +745,7 @@ pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntap
 //   w16 bf16 [16][cin][cout]               : data gradient (4x4 stride-2 form), tap = (oy + 1) * 4 + (ox + 1)
 // ---------------------------------------------------------------------------------------------------
 __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout, int cin, __half* __restrict__ wf,
-                                          __nv_bfloat16* __restrict__ w16) {
+                                          __nv_bfloat16* __restrict__ w16, int split) {
   const long long cc = (long long)cout * cin;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cc; e += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(e % cin), co = (int)(e / cin);
@@ -736,7 +769,14 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout,
                 const int ry = py == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0), rx = px == 0 ? (kx == 0 ? 0 : 1) : (kx == 2 ? 1 : 0);
                 if (ry == ty && rx == tx) s += k[ky][kx];
               }
-            wf[(((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * cin + ci] = __float2half_rn(s);
+            const __half hi = __float2half_rn(s);
+            if (split) {                                           // [phase][tap][co][Wh (cin) | Wl (cin)]
+              __half* row = wf + (((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * (2 * cin);
+              row[ci] = hi;
+              row[cin + ci] = __float2half_rn(s - __half2float(hi));
+            } else {
+              wf[(((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * cin + ci] = hi;
+            }
           }
     // data gradient: S(-1) = {2}, S(0) = {1, 2}, S(1) = {0, 1}, S(2) = {0}
 #pragma unroll
@@ -843,8 +883,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 using namespace rpnet;
 
+RPNET_API int rpnet_bn_stats_split_f16(const void* z, const void* z_lo, int n, int h, int w, int c, const int* group_start, int groups,
+                                        double* sums, void* stream_);
+RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
+                                        const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
+                                        void* y_pool_lo_f16, float* y_f32, void* stream_);
+
 RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                                   void* stream_) {
+  return rpnet_bn_stats_split_f16(z, nullptr, n, h, w, c, group_start, groups, sums, stream_);
+}
+
+RPNET_API int rpnet_bn_stats_split_f16(const void* z, const void* z_lo, int n, int h, int w, int c, const int* group_start, int groups,
+                                        double* sums, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(z && sums, "bn_stats: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 64 && c % 8 == 0 && 256 % (c / 8) == 0, "bn_stats: bad shape n=%d h=%d w=%d c=%d (c in {64..2048}, power of two)", n, h, w, c);
@@ -854,7 +905,7 @@ RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, cons
   RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(double), stream));
   const int lanes = 256 / (c / 8);
   const int grid = plan_group_blocks(&gr, (long long)h * w, (long long)lanes * 8);
-  bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(z), gr, h * w, c / 8, sums);
+  bn_stats_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), gr, h * w, c / 8, sums);
   return check_cuda(cudaGetLastError(), "bn_stats launch");
 }
 
@@ -874,7 +925,15 @@ RPNET_API int rpnet_bn_finalize_f32(const double* sums, const int* group_start, 
 
 RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups,
                                   int relu, void* y_f16, void* y_pool_f16, float* y_f32, void* stream_) {
+  return rpnet_bn_apply_split_f16(z, nullptr, stats, n, h, w, c, group_start, groups, relu, y_f16, nullptr, y_pool_f16, nullptr, y_f32,
+                                  stream_);
+}
+
+RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
+                                        const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
+                                        void* y_pool_lo_f16, float* y_f32, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE((!y_lo_f16 || y_f16) && (!y_pool_lo_f16 || y_pool_f16), "bn_apply: a residual output needs its main output");
   RPNET_REQUIRE(z && stats, "bn_apply: null pointer argument");
   RPNET_REQUIRE(y_f16 || y_pool_f16 || y_f32, "bn_apply: no output requested");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bn_apply: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
@@ -891,11 +950,13 @@ RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h
   const long long cap_a = (long long)apply_blocks() * (units >= (1LL << 21) ? 2 : 1);    // large maps: more blocks in flight
   if (grid > cap_a) grid = cap_a;
   if (y_pool_f16)
-    bn_apply_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
-                                                             static_cast<uint4*>(y_f16), y_f32, static_cast<uint4*>(y_pool_f16));
+    bn_apply_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
+                                                             h, w, c / 8, relu, static_cast<uint4*>(y_f16), static_cast<uint4*>(y_lo_f16),
+                                                             y_f32, static_cast<uint4*>(y_pool_f16), static_cast<uint4*>(y_pool_lo_f16));
   else
-    bn_apply_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), stats, gr, n, h, w, c / 8, relu,
-                                                              static_cast<uint4*>(y_f16), y_f32, nullptr);
+    bn_apply_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
+                                                              h, w, c / 8, relu, static_cast<uint4*>(y_f16),
+                                                              static_cast<uint4*>(y_lo_f16), y_f32, nullptr, nullptr);
   return check_cuda(cudaGetLastError(), "bn_apply launch");
 }
 
@@ -994,8 +1055,16 @@ RPNET_API int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const f
   return check_cuda(cudaGetLastError(), "premask_bwd launch");
 }
 
+RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
+                                            void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream_);
+
 RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len, void* w_fwd_f16,
                                       void* w_dgrad_bf16, void* stream_) {
+  return rpnet_pack_conv_weight_split(w, cout, cin_real, ntaps, hole_start, hole_len, w_fwd_f16, 0, w_dgrad_bf16, stream_);
+}
+
+RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
+                                            void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(w && (w_fwd_f16 || w_dgrad_bf16), "pack_conv_weight: null pointer argument");
   RPNET_REQUIRE(cout > 0 && cin_real > 0 && ntaps > 0 && hole_len >= 0 && hole_start >= 0 && hole_start <= cin_real,
@@ -1004,7 +1073,7 @@ RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int
   RPNET_REQUIRE(ntaps <= 9, "pack_conv_weight: at most 9 taps (got %d)", ntaps);
   const int tiles = ((cout + 31) / 32) * ((cin + 31) / 32);
   pack_conv_weight_kernel<<<tiles, 256, 0, stream>>>(w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16),
-                                                     static_cast<__nv_bfloat16*>(w_dgrad_bf16));
+                                                     static_cast<__nv_bfloat16*>(w_dgrad_bf16), split);
   return check_cuda(cudaGetLastError(), "pack_conv_weight launch");
 }
 
@@ -1032,10 +1101,16 @@ RPNET_API int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, fl
   return check_cuda(cudaGetLastError(), "adam launch");
 }
 
+RPNET_API int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream_);
+
 RPNET_API int rpnet_pack_upconv_weight(const float* w, int cout, int cin, void* wf_f16, void* w16_bf16, void* stream_) {
+  return rpnet_pack_upconv_weight_split(w, cout, cin, wf_f16, 0, w16_bf16, stream_);
+}
+
+RPNET_API int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(w && wf_f16 && w16_bf16 && cout > 0 && cin > 0, "pack_upconv_weight: bad argument");
   pack_upconv_weight_kernel<<<grid_for((long long)cout * cin, 256), 256, 0, stream>>>(w, cout, cin, static_cast<__half*>(wf_f16),
-                                                                                    static_cast<__nv_bfloat16*>(w16_bf16));
+                                                                                    static_cast<__nv_bfloat16*>(w16_bf16), split);
   return check_cuda(cudaGetLastError(), "pack_upconv_weight launch");
 }

@@ -13,6 +13,28 @@ BN_EPS = 1e-5
 WEIGHTS_EPOCH = 0
 TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
+# Arithmetic of the encoder convs (yaml key `b200_precision`, default from the environment variable RPNET_PRECISION):
+#   'split' (default): split-fp16 - every encoder activation and weight travels as hi + lo fp16 planes and the tensor cores
+#                      accumulate hi.Wh + lo.Wh + hi.Wl in fp32: logits within 1e-3 (rel-Linf) of the reference's fp32 forward;
+#   'fp16'           : single-term fp16 operands (the 11-bit significand of a TF32 cuDNN conv): 3x fewer tensor-core passes,
+#                      logits 2e-3 .. 5e-3 from the fp32 reference on unsaturated fixtures.
+PRECISIONS = ('split', 'fp16')
+
+
+def default_precision():
+    import os
+    p = os.environ.get('RPNET_PRECISION', 'split')
+    if p not in PRECISIONS:
+        raise ValueError('RPNET_PRECISION=%r (expected one of %r)' % (p, PRECISIONS))
+    return p
+
+
+def precision_of(cfg):
+    p = (cfg or {}).get('b200_precision') or default_precision()
+    if p not in PRECISIONS:
+        raise ValueError('b200_precision=%r (expected one of %r)' % (p, PRECISIONS))
+    return p
+
 
 class Workspace:
     """Named, shape-keyed persistent device buffers (stable pointers: CUDA-graph friendly)."""
@@ -33,12 +55,27 @@ class Workspace:
 
 
 class ConvPack:
-    """One tap-list conv ready for rpnet_conv_igemm_f16."""
-    __slots__ = ('wpack', 'taps', 'scale', 'shift', 'relu', 'cout', 'cin')
+    """One tap-list conv ready for rpnet_conv_igemm_f16 (split: rpnet_conv_split_f16, wpack = Wh | Wl along cin)."""
+    __slots__ = ('wpack', 'taps', 'scale', 'shift', 'relu', 'cout', 'cin', 'split')
 
-    def __init__(self, wpack, taps, scale, shift, relu):
-        self.wpack, self.taps, self.scale, self.shift, self.relu = wpack, taps, scale, shift, relu
-        self.cout, self.cin = wpack.shape[1], wpack.shape[2]
+    def __init__(self, wpack, taps, scale, shift, relu, split=False):
+        self.wpack, self.taps, self.scale, self.shift, self.relu, self.split = wpack, taps, scale, shift, relu, split
+        self.cout, self.cin = wpack.shape[1], wpack.shape[2] // (2 if split else 1)
+
+
+def split_f16(x):
+    """fp32 tensor -> (hi, lo) fp16 pair with hi + lo == x to ~2^-22 relative."""
+    hi = x.to(torch.float16)
+    return hi, (x - hi.float()).to(torch.float16)
+
+
+def hi_of(a):
+    """hi plane of an activation that is either a tensor or a (hi, lo) pair."""
+    return a[0] if isinstance(a, tuple) else a
+
+
+def lo_of(a):
+    return a[1] if isinstance(a, tuple) else None
 
 
 def fold_bn(conv_bias, bn_weight=None, bn_bias=None, running_mean=None, running_var=None, eps=BN_EPS):
@@ -52,15 +89,17 @@ def fold_bn(conv_bias, bn_weight=None, bn_bias=None, running_mean=None, running_
     return scale.contiguous(), shift.contiguous()
 
 
-def pack_weight_taps(weight, dilation=1):
-    """[cout, cin, k, k] fp32 -> fp16 [k*k, cout, cin] + tap offsets (cross-correlation, 'same' padding)."""
+def pack_weight_taps(weight, dilation=1, split=False):
+    """[cout, cin, k, k] fp32 -> fp16 [k*k, cout, cin] (split: [k*k, cout, 2*cin] = Wh | Wl) + tap offsets
+    (cross-correlation, 'same' padding)."""
     cout, cin, kh, kw = weight.shape
-    w = weight.detach().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(torch.float16).contiguous()
+    w32 = weight.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
+    w = (torch.cat(split_f16(w32), dim=2) if split else w32.to(torch.float16)).contiguous()
     taps = [((ky - kh // 2) * dilation, (kx - kw // 2) * dilation) for ky in range(kh) for kx in range(kw)]
     return w, taps
 
 
-def pack_upsample_phases(weight):
+def pack_upsample_phases(weight, split=False):
     """nn.Upsample(scale_factor=2, nearest) followed by a 3x3/pad-1 conv == four 2x2 convs on the
     low-resolution input, one per output parity (py, px), with row/column-summed weights:
       py = 0: rows {-1: w[0], 0: w[1] + w[2]};   py = 1: rows {0: w[0] + w[1], +1: w[2]}   (same for columns).
@@ -77,39 +116,58 @@ def pack_upsample_phases(weight):
                     m = sum(w[:, :, ky, kx] for ky in kys for kx in kxs)
                     taps.append((dy, dx))
                     mats.append(m)
-            wp = torch.stack(mats, dim=0).to(torch.float16).contiguous()
+            m = torch.stack(mats, dim=0)
+            wp = (torch.cat(split_f16(m), dim=2) if split else m.to(torch.float16)).contiguous()
             out.append((wp, taps, (py, px)))
     return out
 
 
-def conv_bn_pack(conv, bn, relu=True, dilation=1):
+def conv_bn_pack(conv, bn, relu=True, dilation=1, split=False):
     scale, shift = fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None \
         else fold_bn(conv.bias)
-    wp, taps = pack_weight_taps(conv.weight, dilation)
-    return ConvPack(wp, taps, scale, shift, relu)
+    wp, taps = pack_weight_taps(conv.weight, dilation, split)
+    return ConvPack(wp, taps, scale, shift, relu, split)
 
 
 def run_conv(pack, src0, ws, name, src1=None, want_out=True, want_pool=False, out_f32=False):
-    """Run one packed conv.  Returns (out, pooled) fp16 NHWC tensors (None when not requested) or the fp32 output."""
-    n, h, w, _ = src0.shape
-    dev = src0.device
-    out = ws.get(name, (n, h, w, pack.cout), torch.float16, dev) if (want_out and not out_f32) else None
-    pool = ws.get(name + '.pool', (n, h // 2, w // 2, pack.cout), torch.float16, dev) if want_pool else None
+    """Run one packed conv.  src0 / src1: fp16 NHWC tensors or (hi, lo) pairs.  Returns (out, pooled) - fp16 NHWC tensors, or
+    (hi, lo) pairs for a split pack (None when not requested) - or the fp32 output."""
+    n, h, w, _ = hi_of(src0).shape
+    dev = hi_of(src0).device
+    f16 = torch.float16
+    out = ws.get(name, (n, h, w, pack.cout), f16, dev) if (want_out and not out_f32) else None
+    pool = ws.get(name + '.pool', (n, h // 2, w // 2, pack.cout), f16, dev) if want_pool else None
     o32 = ws.get(name + '.f32', (n, h, w, pack.cout), torch.float32, dev) if out_f32 else None
-    ops.conv_igemm(src0, pack.wpack, pack.taps, pack.scale, pack.shift, pack.relu, src1=src1, out=out, out_pool=pool,
-                   out_f32=o32)
+    if pack.split:
+        out_lo = ws.get(name + '.lo', (n, h, w, pack.cout), f16, dev) if out is not None else None
+        pool_lo = ws.get(name + '.pool.lo', (n, h // 2, w // 2, pack.cout), f16, dev) if want_pool else None
+        ops.conv_split(hi_of(src0), pack.wpack, pack.taps, pack.scale, pack.shift, pack.relu, src0_lo=lo_of(src0),
+                       src1=None if src1 is None else hi_of(src1), src1_lo=None if src1 is None else lo_of(src1), out=out,
+                       out_lo=out_lo, out_pool=pool, out_pool_lo=pool_lo, out_f32=o32)
+        if out_f32:
+            return o32
+        return (None if out is None else (out, out_lo)), (None if pool is None else (pool, pool_lo))
+    ops.conv_igemm(hi_of(src0), pack.wpack, pack.taps, pack.scale, pack.shift, pack.relu, src1=None if src1 is None else hi_of(src1),
+                   out=out, out_pool=pool, out_f32=o32)
     if out_f32:
         return o32
     return out, pool
 
 
-def run_upconv(phases, scale, shift, src, ws, name):
+def run_upconv(phases, scale, shift, src, ws, name, split=False):
     """Sub-pixel form of up_conv: four phase convs scatter into the 2x resolution output."""
-    n, h, w, _ = src.shape
+    n, h, w, _ = hi_of(src).shape
     cout = phases[0][0].shape[1]
-    out = ws.get(name, (n, 2 * h, 2 * w, cout), torch.float16, src.device)
+    dev = hi_of(src).device
+    out = ws.get(name, (n, 2 * h, 2 * w, cout), torch.float16, dev)
+    if split:
+        out_lo = ws.get(name + '.lo', (n, 2 * h, 2 * w, cout), torch.float16, dev)
+        for wp, taps, (py, px) in phases:
+            ops.conv_split(hi_of(src), wp, taps, scale, shift, True, src0_lo=lo_of(src), out=out, out_lo=out_lo,
+                           out_map=(2, py, 2, px))
+        return out, out_lo
     for wp, taps, (py, px) in phases:
-        ops.conv_igemm(src, wp, taps, scale, shift, True, out=out, out_map=(2, py, 2, px))
+        ops.conv_igemm(hi_of(src), wp, taps, scale, shift, True, out=out, out_map=(2, py, 2, px))
     return out
 
 
@@ -118,4 +176,6 @@ def nchw_f32_to_nhwc_f16(x):
 
 
 def nhwc_to_nchw_f32(x):
+    if isinstance(x, tuple):                       # split-fp16 pair
+        x = x[0].float() + x[1].float() if x[1] is not None else x[0]
     return x.permute(0, 3, 1, 2).float().contiguous()

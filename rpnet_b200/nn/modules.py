@@ -52,15 +52,18 @@ def run_conv_any(conv, bn, x_nhwc_or_img, ws, name, pack, relu=True, **kw):
                 if bn is not None else engine.fold_bn(conv.bias)
         n, _, h, w = x_nhwc_or_img.shape
         out = ws.get(name, (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device)
-        ops.conv3x3_first(x_nhwc_or_img.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, relu, out)
-        return out, None
+        out_lo = ws.get(name + '.lo', (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device) if kw.get('split') else None
+        ops.conv3x3_first(x_nhwc_or_img.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, relu, out,
+                          out_lo=out_lo)
+        return ((out, out_lo) if out_lo is not None else out), None
     return engine.run_conv(pack, x_nhwc_or_img, ws, name, **kw)
 
 
 class conv_block(_PackedModule):
-    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1):
+    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1, precision=None):
         super(conv_block, self).__init__()
         _check_norm(normalization_type)
+        self.split = (precision or engine.default_precision()) == "split"     # engine.PRECISIONS
         if kernel != 3 or padding != 1:
             raise NotImplementedError('conv_block: only kernel=3, padding=1 is used by RP-Net')
         self.ch_in = ch_in
@@ -81,8 +84,8 @@ class conv_block(_PackedModule):
             c, b = self.conv[0], self.conv[1]
             first = engine.fold_bn(c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)    # (scale, shift) tuple
         else:
-            first = engine.conv_bn_pack(self.conv[0], self.conv[1])
-        return first, engine.conv_bn_pack(self.conv[3], self.conv[4])
+            first = engine.conv_bn_pack(self.conv[0], self.conv[1], split=self.split)
+        return first, engine.conv_bn_pack(self.conv[3], self.conv[4], split=self.split)
 
     def run_nhwc(self, x, ws, name, x1=None, want_out=True, want_pool=False):
         """x: fp16 NHWC (or the fp32 NCHW image for the first block); x1: optional second source (channel concat).
@@ -90,7 +93,7 @@ class conv_block(_PackedModule):
         _check_eval(self)
         p0, p1 = self._packs()
         if isinstance(p0, tuple):
-            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', p0)
+            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', p0, split=self.split)
         else:
             a, _ = engine.run_conv(p0, x, ws, name + '.0', src1=x1)
         return engine.run_conv(p1, a, ws, name + '.3', want_out=want_out, want_pool=want_pool)
@@ -104,9 +107,10 @@ class conv_block(_PackedModule):
 
 
 class up_conv(_PackedModule):
-    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1):
+    def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1, precision=None):
         super(up_conv, self).__init__()
         _check_norm(normalization_type)
+        self.split = (precision or engine.default_precision()) == "split"
         if kernel != 3 or padding != 1:
             raise NotImplementedError('up_conv: only kernel=3, padding=1 is used by RP-Net')
         self.ch_in = ch_in
@@ -121,12 +125,12 @@ class up_conv(_PackedModule):
     def _build_packs(self):
         conv, bn = self.up[1], self.up[2]
         scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-        return engine.pack_upsample_phases(conv.weight), scale, shift
+        return engine.pack_upsample_phases(conv.weight, self.split), scale, shift
 
     def run_nhwc(self, x, ws, name):
         _check_eval(self)
         phases, scale, shift = self._packs()
-        return engine.run_upconv(phases, scale, shift, x, ws, name)
+        return engine.run_upconv(phases, scale, shift, x, ws, name, self.split)
 
     def forward(self, x):
         out = self.run_nhwc(engine.nchw_f32_to_nhwc_f16(x), self._workspace(), 'uc')

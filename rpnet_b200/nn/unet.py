@@ -38,15 +38,16 @@ class U_Net(Unet_2D):
         self.Maxpool = nn.MaxPool2d(kernel_size=2, stride=2)     # fused into the preceding conv's epilogue
         num_feats = [64, 128, 256, 512, 1024]
         norm = cfg['unet_normalize_type']
-        self.Conv1 = conv_block(ch_in=self.img_ch, ch_out=num_feats[0], normalization_type=norm)
-        self.Conv2 = conv_block(ch_in=num_feats[0], ch_out=num_feats[1], normalization_type=norm)
-        self.Conv3 = conv_block(ch_in=num_feats[1], ch_out=num_feats[2], normalization_type=norm)
-        self.Conv4 = conv_block(ch_in=num_feats[2], ch_out=num_feats[3], normalization_type=norm)
-        self.Conv5 = conv_block(ch_in=num_feats[3], ch_out=num_feats[4], normalization_type=norm)
-        self.Up5 = up_conv(ch_in=num_feats[4], ch_out=num_feats[3], normalization_type=norm)
-        self.Up_conv5 = conv_block(ch_in=num_feats[3] * 2, ch_out=num_feats[3], normalization_type=norm)
-        self.Up4 = up_conv(ch_in=num_feats[3], ch_out=num_feats[2], normalization_type=norm)
-        self.Up_conv4 = conv_block(ch_in=num_feats[2] * 2, ch_out=num_feats[2], normalization_type=norm)
+        pr = engine.precision_of(cfg)          # 'split' (fp32-class, default) or 'fp16' (engine.PRECISIONS)
+        self.Conv1 = conv_block(ch_in=self.img_ch, ch_out=num_feats[0], normalization_type=norm, precision=pr)
+        self.Conv2 = conv_block(ch_in=num_feats[0], ch_out=num_feats[1], normalization_type=norm, precision=pr)
+        self.Conv3 = conv_block(ch_in=num_feats[1], ch_out=num_feats[2], normalization_type=norm, precision=pr)
+        self.Conv4 = conv_block(ch_in=num_feats[2], ch_out=num_feats[3], normalization_type=norm, precision=pr)
+        self.Conv5 = conv_block(ch_in=num_feats[3], ch_out=num_feats[4], normalization_type=norm, precision=pr)
+        self.Up5 = up_conv(ch_in=num_feats[4], ch_out=num_feats[3], normalization_type=norm, precision=pr)
+        self.Up_conv5 = conv_block(ch_in=num_feats[3] * 2, ch_out=num_feats[3], normalization_type=norm, precision=pr)
+        self.Up4 = up_conv(ch_in=num_feats[3], ch_out=num_feats[2], normalization_type=norm, precision=pr)
+        self.Up_conv4 = conv_block(ch_in=num_feats[2] * 2, ch_out=num_feats[2], normalization_type=norm, precision=pr)
         self._ws = engine.Workspace()
 
     def encode_nhwc(self, x, tag='enc'):
@@ -67,7 +68,7 @@ class U_Net(Unet_2D):
         d5, _ = self.Up_conv5.run_nhwc(x4, ws, tag + '.uc5', x1=u5)
         u4 = self.Up4.run_nhwc(d5, ws, tag + '.u4')
         d4, _ = self.Up_conv4.run_nhwc(x3, ws, tag + '.uc4', x1=u4)
-        return d4
+        return engine.hi_of(d4)                # the context-relation encoder consumes plain fp16 features
 
     def forward(self, x, mask, do_last_conv=True):
         """Reference signature (net/unet.py:435); `mask` is only read by the unsupported mask_feature_map variants."""

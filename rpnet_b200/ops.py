@@ -112,15 +112,78 @@ def conv_cos(src0, wpack, taps, scale, shift, protos, pred, relu=True, src1=None
     _lib.check(rc, 'rpnet_conv_cos_f16')
 
 
-def conv3x3_first(img, weight, scale, shift, relu, out):
+def conv3x3_first(img, weight, scale, shift, relu, out, out_lo=None):
+    """out_lo: optional residual plane fp16(y - fp16(y)) of the split-fp16 representation."""
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')
     n, cin, h, w = img.shape
     assert tuple(weight.shape) == (64, cin, 3, 3) and tuple(out.shape) == (n, h, w, 64)
-    with _Timed('conv3x3_first', float(img.numel() * 4 + out.numel() * 2)):
-        rc = lib.rpnet_conv3x3_first_f16(_ptr(img), n, cin, h, w, _ptr(weight), _ptr(_req(scale, torch.float32, 'scale')),
-                                         _ptr(_req(shift, torch.float32, 'shift')), int(bool(relu)), _ptr(out), _stream())
-    _lib.check(rc, 'rpnet_conv3x3_first_f16')
+    if out_lo is not None:
+        _req(out_lo, torch.float16, 'out_lo')
+        assert out_lo.shape == out.shape
+    with _Timed('conv3x3_first', float(img.numel() * 4 + out.numel() * (2 if out_lo is None else 4))):
+        rc = lib.rpnet_conv3x3_first_split_f16(_ptr(img), n, cin, h, w, _ptr(weight), _ptr(_req(scale, torch.float32, 'scale')),
+                                               _ptr(_req(shift, torch.float32, 'shift')), int(bool(relu)), _ptr(out), _ptr(out_lo),
+                                               _stream())
+    _lib.check(rc, 'rpnet_conv3x3_first_split_f16')
+
+
+def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=None, src1_lo=None, w_split=True, out=None,
+               out_lo=None, out_pool=None, out_pool_lo=None, out_f32=None, out_map=None, out_coff=0, group_start=None, sums=None,
+               keep_sums=False):
+    """Split-fp16 tap-list conv (include/rpnet_b200.h, rpnet_conv_split_f16): sources and outputs as hi / lo fp16 planes,
+    wpack fp16 [ntaps, cout, (c0 + c1) * (2 if w_split else 1)] = Wh | Wl.  sums (fp64) + group_start: train-mode BatchNorm
+    statistics of the fp32 accumulators (scale = 1, shift = 0, relu = False)."""
+    lib = _lib.load()
+    _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack')
+    _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
+    n, h, w, c0 = src0.shape
+    c1 = 0
+    for t, ref, nm in ((src0_lo, src0, 'src0_lo'), (src1_lo, src1, 'src1_lo')):
+        if t is not None:
+            _req(t, torch.float16, nm)
+            assert ref is not None and t.shape == ref.shape
+    if src1 is not None:
+        _req(src1, torch.float16, 'src1')
+        assert src1.shape[:3] == src0.shape[:3]
+        c1 = src1.shape[3]
+        assert (src0_lo is None) == (src1_lo is None)
+    ntaps, cout, cin_pack = wpack.shape
+    cin = c0 + c1
+    if cin_pack != cin * (2 if w_split else 1) or ntaps != len(taps) or scale.numel() != cout or shift.numel() != cout:
+        raise _lib.RpnetError('conv_split: weight pack %s does not match sources (%d + %d channels, %d taps, w_split=%s)'
+                              % (tuple(wpack.shape), c0, c1, len(taps), w_split))
+    dy, dx = _taps(taps)
+    oh = ow = oc = 0
+    om = out_map or (1, 0, 1, 0)
+    if out is not None:
+        _req(out, torch.float16, 'out')
+        assert out.shape[0] == n
+        oh, ow, oc = out.shape[1:]
+        if out_lo is not None:
+            _req(out_lo, torch.float16, 'out_lo')
+            assert out_lo.shape == out.shape
+    if out_pool is not None:
+        _req(out_pool, torch.float16, 'out_pool')
+        assert tuple(out_pool.shape) == (n, h // 2, w // 2, cout)
+        if out_pool_lo is not None:
+            _req(out_pool_lo, torch.float16, 'out_pool_lo')
+            assert out_pool_lo.shape == out_pool.shape
+    if out_f32 is not None:
+        _req(out_f32, torch.float32, 'out_f32')
+        assert tuple(out_f32.shape) == (n, h, w, cout)
+    gs, g = (None, 0)
+    if sums is not None:
+        _req(sums, torch.float64, 'sums')
+        gs, g = _groups(group_start)
+        assert sums.numel() >= g * cout * 2
+    # `work` stays the reference's (algorithmic) FLOPs of the conv; the kernel executes 1 + (lo planes) + (Wl) passes of them
+    with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
+        rc = lib.rpnet_conv_split_f16(_ptr(src0), _ptr(src0_lo), c0, _ptr(src1), _ptr(src1_lo), c1, n, h, w, _ptr(wpack), int(bool(w_split)),
+                                      ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out), _ptr(out_lo), oh, ow, oc,
+                                      out_coff, om[0], om[1], om[2], om[3], _ptr(out_pool), _ptr(out_pool_lo), _ptr(out_f32), gs, g,
+                                      _ptr(sums), int(bool(keep_sums)), _stream())
+    _lib.check(rc, 'rpnet_conv_split_f16')
 
 
 def avgpool_mask(mask, s, out):
@@ -328,15 +391,18 @@ def conv3x3_first_wgrad(img, dz, grad):
         _lib.check(lib.rpnet_conv3x3_first_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _stream()), 'rpnet_conv3x3_first_wgrad')
 
 
-def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0)):
-    """w fp32 [cout, cin_real, kh, kw] -> w_fwd fp16 [taps, cout, cin] / w_dgrad bf16 [taps, cin, cout]."""
+def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):
+    """w fp32 [cout, cin_real, kh, kw] -> w_fwd fp16 [taps, cout, cin] (split: [taps, cout, 2 * cin] = Wh | Wl) /
+    w_dgrad bf16 [taps, cin, cout]."""
     lib = _lib.load()
     _req(w, torch.float32, 'w')
     cout, cin_real = w.shape[:2]
     ntaps = w.shape[2] * w.shape[3]
+    if w_fwd is not None:
+        assert w_fwd.numel() == ntaps * cout * (cin_real + hole[1]) * (2 if split else 1)
     with _Timed('pack_conv_weight', float(w.numel() * 8)):
-        _lib.check(lib.rpnet_pack_conv_weight(_ptr(w), cout, cin_real, ntaps, hole[0], hole[1], _ptr(w_fwd), _ptr(w_dgrad), _stream()),
-                   'rpnet_pack_conv_weight')
+        _lib.check(lib.rpnet_pack_conv_weight_split(_ptr(w), cout, cin_real, ntaps, hole[0], hole[1], _ptr(w_fwd), int(bool(split)),
+                                                    _ptr(w_dgrad), _stream()), 'rpnet_pack_conv_weight_split')
 
 
 def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None):
@@ -362,14 +428,17 @@ def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None
     _lib.check(rc, 'rpnet_conv_bnstats_f16')
 
 
-def bn_stats(z, group_start, sums):
+def bn_stats(z, group_start, sums, z_lo=None):
     lib = _lib.load()
     _req(z, torch.float16, 'z'); _req(sums, torch.float64, 'sums')
     n, h, w, c = z.shape
     gs, g = _groups(group_start)
     assert sums.numel() >= g * c * 2
-    with _Timed('bn_stats', float(z.numel() * 2)):
-        _lib.check(lib.rpnet_bn_stats_f16(_ptr(z), n, h, w, c, gs, g, _ptr(sums), _stream()), 'rpnet_bn_stats_f16')
+    if z_lo is not None:
+        _req(z_lo, torch.float16, 'z_lo')
+        assert z_lo.shape == z.shape
+    with _Timed('bn_stats', float(z.numel() * (2 if z_lo is None else 4))):
+        _lib.check(lib.rpnet_bn_stats_split_f16(_ptr(z), _ptr(z_lo), n, h, w, c, gs, g, _ptr(sums), _stream()), 'rpnet_bn_stats_split_f16')
 
 
 def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, running_var, nbt, stats, eps=1e-5, momentum=0.1):
@@ -382,15 +451,20 @@ def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, 
                    'rpnet_bn_finalize_f32')
 
 
-def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None):
+def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None, z_lo=None, y_lo=None, y_pool_lo=None):
+    """z_lo / y_lo / y_pool_lo: residual planes of the split-fp16 representation (z = z + z_lo; y written as hi + lo)."""
     lib = _lib.load()
     _req(z, torch.float16, 'z')
     n, h, w, c = z.shape
     gs, g = _groups(group_start)
-    nb = z.numel() * 2 + sum(t.numel() * t.element_size() for t in (y, y_pool, y_f32) if t is not None)
+    for t, ref in ((z_lo, z), (y_lo, y), (y_pool_lo, y_pool)):
+        if t is not None:
+            _req(t, torch.float16, 'residual plane')
+            assert ref is not None and t.shape == ref.shape
+    nb = sum(t.numel() * t.element_size() for t in (z, z_lo, y, y_lo, y_pool, y_pool_lo, y_f32) if t is not None)
     with _Timed('bn_apply', float(nb)):
-        _lib.check(lib.rpnet_bn_apply_f16(_ptr(z), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(y), _ptr(y_pool), _ptr(y_f32),
-                                          _stream()), 'rpnet_bn_apply_f16')
+        _lib.check(lib.rpnet_bn_apply_split_f16(_ptr(z), _ptr(z_lo), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(y), _ptr(y_lo),
+                                                _ptr(y_pool), _ptr(y_pool_lo), _ptr(y_f32), _stream()), 'rpnet_bn_apply_split_f16')
 
 
 def bn_bwd(z, stats, group_start, dz, scratch, relu=True, direct=None, d_off=0, pooled=None, p_off=0, up=None, u_off=0,
@@ -635,14 +709,16 @@ def upconv_fusable(h, w):
     return bw * bh == 128
 
 
-def pack_upconv_weight(w, wf, w16):
-    """w fp32 [cout, cin, 3, 3] -> wf fp16 [4, 4, cout, cin] (phase forward) and w16 bf16 [16, cin, cout] (data gradient)."""
+def pack_upconv_weight(w, wf, w16, split=False):
+    """w fp32 [cout, cin, 3, 3] -> wf fp16 [4, 4, cout, cin] (phase forward; split: [4, 4, cout, 2 * cin] = Wh | Wl) and
+    w16 bf16 [16, cin, cout] (data gradient)."""
     lib = _lib.load()
     _req(w, torch.float32, 'w'); _req(wf, torch.float16, 'wf'); _req(w16, bf16, 'w16')
     cout, cin = w.shape[:2]
-    assert tuple(wf.shape) == (4, 4, cout, cin) and tuple(w16.shape) == (16, cin, cout)
+    assert tuple(wf.shape) == (4, 4, cout, cin * (2 if split else 1)) and tuple(w16.shape) == (16, cin, cout)
     with _Timed('pack_conv_weight', float(w.numel() * 12)):
-        _lib.check(lib.rpnet_pack_upconv_weight(_ptr(w), cout, cin, _ptr(wf), _ptr(w16), _stream()), 'rpnet_pack_upconv_weight')
+        _lib.check(lib.rpnet_pack_upconv_weight_split(_ptr(w), cout, cin, _ptr(wf), int(bool(split)), _ptr(w16), _stream()),
+                   'rpnet_pack_upconv_weight_split')
 
 
 def upconv_fwd_bnstats(x_low, wf, ones, zeros, z, group_start, sums):

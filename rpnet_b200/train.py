@@ -139,8 +139,10 @@ def shard_range(total, rank, world):
 class _ConvBN:
     """One conv (bias dropped: it cancels in train-mode BN) + BatchNorm(batch stats) + ReLU of the path."""
 
-    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False):
-        self.name, self.conv, self.bn, self.first, self.hole, self.up = name, conv, bn, first, hole, up
+    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False):
+        # split: the forward runs in split-fp16 (x = hi + lo planes, weights Wh | Wl, three tensor-core passes: fp32-class
+        # result); the backward is unchanged (it reads the hi planes).
+        self.name, self.conv, self.bn, self.first, self.hole, self.up, self.split = name, conv, bn, first, hole, up, split
         self.gw, self.ggamma, self.gbeta = flat.grad_of(conv.weight), flat.grad_of(bn.weight), flat.grad_of(bn.bias)
         k = conv.kernel_size[0]
         d = conv.dilation[0]
@@ -148,29 +150,38 @@ class _ConvBN:
         self.cout = conv.out_channels
         self.cin_pack = conv.in_channels + hole[1]
         dev = conv.weight.device
+        ks = 2 if split else 1
         if not first:
-            self.wf = torch.empty(len(self.taps), self.cout, self.cin_pack, dtype=f16, device=dev)
+            self.wf = torch.empty(len(self.taps), self.cout, self.cin_pack * ks, dtype=f16, device=dev)
             self.wd = torch.empty(len(self.taps), self.cin_pack, self.cout, dtype=bf16, device=dev)
         if up:      # up_conv in sub-pixel form: phase packs (forward) and the 4x4 stride-2 pack (data gradient)
-            self.wf_up = torch.empty(4, 4, self.cout, conv.in_channels, dtype=f16, device=dev)
+            self.wf_up = torch.empty(4, 4, self.cout, conv.in_channels * ks, dtype=f16, device=dev)
             self.w16_up = torch.empty(16, conv.in_channels, self.cout, dtype=bf16, device=dev)
         self.ones = torch.ones(self.cout, dtype=f32, device=dev)
         self.zeros = torch.zeros(self.cout, dtype=f32, device=dev)
 
     def pack(self):
         if not self.first:
-            ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole)
+            ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole, split=self.split)
         if self.up:
-            ops.pack_upconv_weight(self.conv.weight.data, self.wf_up, self.w16_up)
+            ops.pack_upconv_weight(self.conv.weight.data, self.wf_up, self.w16_up, split=self.split)
 
     def fwd_up(self, x_low, z, gs, sums, stats, y):
-        """z = conv3x3(upsample2x(x_low)) in sub-pixel form (four phase convs, statistics in their epilogues) + BN + ReLU."""
-        n, H, W, c = z.shape
+        """z = conv3x3(upsample2x(x_low)) in sub-pixel form (four phase convs, statistics in their epilogues) + BN + ReLU.
+        x_low, z, y: (hi, lo) plane pairs (lo None outside split mode)."""
+        n, H, W, c = z[0].shape
         bn = self.bn
-        ops.upconv_fwd_bnstats(x_low, self.wf_up, self.ones, self.zeros, z, gs, sums)
+        if self.split:
+            for ph in range(4):
+                py, px = ph >> 1, ph & 1
+                taps = [((-1 if py == 0 else 0) + (t >> 1), (-1 if px == 0 else 0) + (t & 1)) for t in range(4)]
+                ops.conv_split(x_low[0], self.wf_up[ph], taps, self.ones, self.zeros, False, src0_lo=x_low[1], out=z[0], out_lo=z[1],
+                               out_map=(2, py, 2, px), group_start=gs, sums=sums, keep_sums=ph > 0)
+        else:
+            ops.upconv_fwd_bnstats(x_low[0], self.wf_up, self.ones, self.zeros, z[0], gs, sums)
         ops.bn_finalize(sums, gs, c, H * W, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
-        ops.bn_apply(z, stats, gs, True, y=y)
+        ops.bn_apply(z[0], stats, gs, True, y=y[0], z_lo=z[1], y_lo=y[1])
 
     def bwd_up(self, eng, x_low, z, stats, gs, dx_low, **src):
         """Backward of fwd_up: BN+ReLU backward -> dz (high resolution); weight gradient from the four phase GEMMs; data
@@ -185,17 +196,23 @@ class _ConvBN:
         return dx_low
 
     def fwd(self, x0, x1, z, gs, sums, stats, y=None, pool=None, y32=None):
-        """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) + ReLU."""
-        n, h, w, c = z.shape
+        """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) + ReLU.
+        x0, x1, z, y, pool: (hi, lo) plane pairs (lo None outside split mode; x0 = the fp32 image for the first conv)."""
+        n, h, w, c = z[0].shape
         bn = self.bn
+        y = y or (None, None)
+        pool = pool or (None, None)
         if self.first:
-            ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z)
-            ops.bn_stats(z, gs, sums)
+            ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z[0], out_lo=z[1])
+            ops.bn_stats(z[0], gs, sums, z_lo=z[1])
+        elif self.split:
+            ops.conv_split(x0[0], self.wf, self.taps, self.ones, self.zeros, False, src0_lo=x0[1], src1=None if x1 is None else x1[0],
+                           src1_lo=None if x1 is None else x1[1], out=z[0], out_lo=z[1], group_start=gs, sums=sums)
         else:
-            ops.conv_bnstats(x0, self.wf, self.taps, self.ones, self.zeros, z, gs, sums, src1=x1)
+            ops.conv_bnstats(x0[0], self.wf, self.taps, self.ones, self.zeros, z[0], gs, sums, src1=None if x1 is None else x1[0])
         ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
-        ops.bn_apply(z, stats, gs, True, y=y, y_pool=pool, y_f32=y32)
+        ops.bn_apply(z[0], stats, gs, True, y=y[0], y_pool=pool[0], y_f32=y32, z_lo=z[1], y_lo=y[1], y_pool_lo=pool[1])
 
     def bwd(self, eng, x0, x1, z, stats, gs, dx=None, **src):
         """BN+ReLU backward -> dz; weight gradient; data gradient into `dx` (bf16 [n,h,w,cin_pack]) when given."""
@@ -231,13 +248,17 @@ class TrainEngine:
         self.net, self.dev = net, dev
         self.flat = FlatParams(net)
         e, c = net.encoder, net.cre
+        # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
+        # train-mode logits 2e-3 .. 5e-3 from the fp32 reference); the cre convs are single-term in both (their rounding moves
+        # the logits by ~1e-4)
+        self.split = sp = engine.precision_of(net.backbone_cfg) == 'split'
         L = {}
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
-            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'))
-            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat)
-        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True)
-        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True)
+            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'), split=sp)
+            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat, split=sp)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True, split=sp)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True, split=sp)
         k = (2 * c.radius + 1) ** 2
         self.kcorr, self.corr_c = k, c.corr_channels
         L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
@@ -274,16 +295,22 @@ class TrainEngine:
             l.pack()
 
     # ------------------------------------------------------------------ encoder
+    def pair(self, name, shape, lo):
+        """(hi, lo) fp16 planes of one activation; lo is None outside split mode."""
+        return (self.buf(name, shape, f16), self.buf(name + '.lo', shape, f16) if lo else None)
+
     def _layer_fwd(self, key, x0, x1, gs, want_y=True, want_pool=False):
+        """x0 / x1: (hi, lo) pairs (x0 = the fp32 image batch for the first conv).  Returns the (hi, lo) pairs of y and of
+        its 2x2 max-pooled copy.  The backward only keeps the hi planes."""
         l = self.L[key]
-        n, h, w = (x0.shape[0], x0.shape[2], x0.shape[3]) if l.first else x0.shape[:3]
+        n, h, w = (x0.shape[0], x0.shape[2], x0.shape[3]) if l.first else x0[0].shape[:3]
         c = l.cout
-        z = self.buf(key + '.z', (n, h, w, c), f16)
+        z = self.pair(key + '.z', (n, h, w, c), l.split)
         stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
-        y = self.buf(key + '.y', (n, h, w, c), f16) if want_y else None
-        pool = self.buf(key + '.pool', (n, h // 2, w // 2, c), f16) if want_pool else None
+        y = self.pair(key + '.y', (n, h, w, c), l.split) if want_y else None
+        pool = self.pair(key + '.pool', (n, h // 2, w // 2, c), l.split) if want_pool else None
         l.fwd(x0, x1, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, torch.float64), stats, y=y, pool=pool)
-        self.act[key] = dict(x0=x0, x1=x1, z=z, stats=stats, gs=gs)
+        self.act[key] = dict(x0=x0 if l.first else x0[0], x1=None if x1 is None else x1[0], z=z[0], stats=stats, gs=gs)
         return y, pool
 
     def _encoder_fwd(self, imgs, gs):
@@ -311,17 +338,19 @@ class TrainEngine:
         """up_conv: sub-pixel form on the low-resolution input when the maps are at least one pixel tile large, else the
         materialised nearest-x2 map + 3x3 conv."""
         l = self.L[key]
-        n, h, w, cin = x_low.shape
+        n, h, w, cin = x_low[0].shape
         if ops.upconv_fusable(h, w):
             c = l.cout
-            z = self.buf(key + '.z', (n, 2 * h, 2 * w, c), f16)
+            z = self.pair(key + '.z', (n, 2 * h, 2 * w, c), l.split)
             stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
-            y = self.buf(key + '.y', (n, 2 * h, 2 * w, c), f16)
+            y = self.pair(key + '.y', (n, 2 * h, 2 * w, c), l.split)
             l.fwd_up(x_low, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, torch.float64), stats, y)
-            self.act[key] = dict(x0=x_low, x1=None, z=z, stats=stats, gs=gs, sub=True)
+            self.act[key] = dict(x0=x_low[0], x1=None, z=z[0], stats=stats, gs=gs, sub=True)
             return y
-        u = self.buf(key + '.in', (n, 2 * h, 2 * w, cin), f16)
-        ops.upsample2x(x_low, u)                                      # net/modules.py:67
+        u = self.pair(key + '.in', (n, 2 * h, 2 * w, cin), l.split)
+        ops.upsample2x(x_low[0], u[0])                                # net/modules.py:67
+        if l.split:
+            ops.upsample2x(x_low[1], u[1])
         y, _ = self._layer_fwd(key, u, None, gs)
         return y
 
@@ -383,10 +412,11 @@ class TrainEngine:
         ops.premask(d4, mask, xfg, xbg)
         G = len(gs) - 1
         sums = self.scratch('bn_sums', G * 256 * 2, torch.float64)
-        L['wk'].fwd(xfg, None, S['z1'][lo:hi], gs, sums, S['st1'][g0:g0 + G], y=S['fm1'][lo:hi])
-        L['wq'].fwd(xbg, None, S['z2'][lo:hi], gs, sums, S['st2'][g0:g0 + G], y=S['fm2'][lo:hi])
+        P = lambda t: (t[lo:hi], None)                                # the cre convs are single-term fp16: no residual planes
+        L['wk'].fwd((xfg, None), None, P(S['z1']), gs, sums, S['st1'][g0:g0 + G], y=P(S['fm1']))
+        L['wq'].fwd((xbg, None), None, P(S['z2']), gs, sums, S['st2'][g0:g0 + G], y=P(S['fm2']))
         ops.local_corr(S['fm1'][lo:hi], S['fm2'][lo:hi], self.net.cre.radius, S['corr'][lo:hi])
-        L['q'].fwd(S['corr'][lo:hi], S['fm1'][lo:hi], S['z3'][lo:hi], gs, sums, S['st3'][g0:g0 + G], y32=S['feat'][lo:hi])
+        L['q'].fwd(P(S['corr']), P(S['fm1']), P(S['z3']), gs, sums, S['st3'][g0:g0 + G], y32=S['feat'][lo:hi])
         return S['feat'][lo:hi]
 
     # ------------------------------------------------------------------ forward
@@ -409,7 +439,7 @@ class TrainEngine:
         engine.WEIGHTS_EPOCH += 1          # BN running statistics are updated through raw pointers below
 
         imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
-        d4 = self._encoder_fwd(imgs, [0, n_supp, n_img])             # two BN calls: support pass, query pass (D14)
+        d4 = self._encoder_fwd(imgs, [0, n_supp, n_img])[0]          # two BN calls: support pass, query pass (D14); hi plane
         h, w, C = d4.shape[1:]
         if h * S != H or w * S != W:
             raise ValueError('scale=%d does not match the encoder stride' % S)

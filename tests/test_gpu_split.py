@@ -1,0 +1,189 @@
+"""Split-fp16 ("fp32-class") convolution path (include/rpnet_b200.h, rpnet_conv_split_f16 and friends) against torch fp32/fp64
+on UNROUNDED operands: the point of the path is that hi + lo planes and Wh | Wl packs reproduce the reference's fp32
+nn.Conv2d (net/modules.py:47-54) without the 2^-11 operand rounding of a single-term tensor-core product.
+Tolerance: 2e-5 relative to the output scale (fp32 accumulation order + the dropped lo.Wl term), i.e. ~50x tighter than the
+single-term kernel reaches on the same inputs (asserted below as a sanity check of the test itself)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import _lib
+    _lib.load()
+    return torch.device('cuda:0')
+
+
+def _gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _pair(x, dev):
+    """NCHW fp32 -> (hi, lo) fp16 NHWC planes on the device."""
+    from rpnet_b200 import engine
+    hi, lo = engine.split_f16(x.permute(0, 2, 3, 1).contiguous())
+    return hi.to(dev), lo.to(dev)
+
+
+def _join(hi, lo):
+    return (hi.float() + lo.float()).permute(0, 3, 1, 2).contiguous().cpu()
+
+
+CASES = [
+    # n, c0, c1, cout, h, w, k
+    (2, 64, 0, 64, 32, 32, 3),
+    (3, 128, 0, 256, 8, 8, 3),         # CTA-pair tiles, ragged batch tile
+    (2, 128, 64, 128, 24, 40, 3),      # channel concat of two split sources, ragged H / W
+    (1, 256, 256, 256, 16, 16, 3),     # the Up_conv4 shape class
+    (2, 192, 0, 64, 16, 16, 1),        # 1x1
+]
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_conv_split_vs_fp64(dev, case):
+    from rpnet_b200 import engine, ops
+    n, c0, c1, cout, h, w, k = case
+    g = _gen(sum(case))
+    x = torch.randn(n, c0 + c1, h, w, generator=g)
+    wt = torch.randn(cout, c0 + c1, k, k, generator=g) / math.sqrt((c0 + c1) * k * k)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    ref = (F.conv2d(x.double(), wt.double(), None, padding=k // 2) * scale[None, :, None, None].double()
+           + shift[None, :, None, None].double())
+    ref = F.relu(ref).float()
+    wp, taps = engine.pack_weight_taps(wt.to(dev), split=True)
+    assert tuple(wp.shape) == (k * k, cout, 2 * (c0 + c1))
+    a = _pair(x[:, :c0], dev)
+    b = _pair(x[:, c0:], dev) if c1 else (None, None)
+    out = torch.empty(n, h, w, cout, dtype=torch.float16, device=dev)
+    out_lo = torch.empty_like(out)
+    out32 = torch.empty(n, h, w, cout, dtype=torch.float32, device=dev)
+    pool = torch.empty(n, h // 2, w // 2, cout, dtype=torch.float16, device=dev)
+    pool_lo = torch.empty_like(pool)
+    ops.conv_split(a[0], wp, taps, scale.to(dev), shift.to(dev), True, src0_lo=a[1], src1=b[0], src1_lo=b[1], out=out, out_lo=out_lo,
+                   out_pool=pool, out_pool_lo=pool_lo, out_f32=out32)
+    torch.cuda.synchronize()
+    s = ref.abs().max().item()
+    err32 = (out32.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() / s
+    err_pair = (_join(out, out_lo) - ref).abs().max().item() / s
+    assert err32 < 2e-5, err32
+    assert err_pair < 2e-5, err_pair                       # the hi + lo output planes carry the fp32 result
+    assert torch.equal(out, out32.half())                 # hi plane = the plain fp16 rounding
+    got_pool = _join(pool, pool_lo)
+    assert (got_pool - F.max_pool2d(ref, 2, 2)).abs().max().item() / s < 2e-5
+    # the single-term kernel on the same (rounded) operands is two orders of magnitude further away: the test has teeth
+    wp1, _ = engine.pack_weight_taps(wt.to(dev))
+    o1 = torch.empty_like(out32)
+    ops.conv_igemm(a[0], wp1, taps, scale.to(dev), shift.to(dev), True, src1=b[0], out_f32=o1)
+    torch.cuda.synchronize()
+    err1 = (o1.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() / s
+    assert err1 > 10 * err32, (err1, err32)
+
+
+def test_conv_split_plain_sources_and_partial_split(dev):
+    """lo planes / Wl are optional: with neither the entry point is the single-term conv, bit for bit."""
+    from rpnet_b200 import engine, ops
+    g = _gen(5)
+    n, cin, cout, h, w = 2, 128, 128, 16, 16
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    one, zero = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+    a = _pair(x, dev)
+    wp1, taps = engine.pack_weight_taps(wt.to(dev))
+    o_ref = torch.empty(n, h, w, cout, dtype=torch.float32, device=dev)
+    ops.conv_igemm(a[0], wp1, taps, one, zero, False, out_f32=o_ref)
+    o = torch.empty_like(o_ref)
+    ops.conv_split(a[0], wp1, taps, one, zero, False, w_split=False, out_f32=o)
+    torch.cuda.synchronize()
+    assert torch.equal(o, o_ref)
+    # activations split, weights plain: exact activations x fp16 weights
+    ops.conv_split(a[0], wp1, taps, one, zero, False, src0_lo=a[1], w_split=False, out_f32=o)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.double(), wt.half().double(), None, padding=1).float()
+    assert (o.permute(0, 3, 1, 2).cpu() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+def test_conv_split_bnstats_and_bn_apply(dev):
+    """Train-mode split conv: z = hi + lo planes + BatchNorm statistics of the fp32 accumulators (two call groups), then
+    bn_apply on z_hi + z_lo writing y and the pooled y as hi / lo planes.  nn.BatchNorm2d batch statistics, net/modules.py:49."""
+    from rpnet_b200 import engine, ops
+    g = _gen(9)
+    n, cin, cout, h, w = 4, 64, 128, 16, 16
+    x = torch.randn(n, cin, h, w, generator=g) + 0.5
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    gs = [0, 3, 4]
+    a = _pair(x, dev)
+    wf = torch.empty(9, cout, 2 * cin, dtype=torch.float16, device=dev)
+    ops.pack_conv_weight(wt.to(dev), wf, None, split=True)
+    wp, taps = engine.pack_weight_taps(wt.to(dev), split=True)
+    assert torch.equal(wf, wp)                             # the device pack kernel and the torch pack agree bit for bit
+    one, zero = torch.ones(cout, device=dev), torch.zeros(cout, device=dev)
+    z, z_lo = (torch.empty(n, h, w, cout, dtype=torch.float16, device=dev) for _ in range(2))
+    sums = torch.zeros(2 * cout * 2, dtype=torch.float64, device=dev)
+    ops.conv_split(a[0], wf, taps, one, zero, False, src0_lo=a[1], out=z, out_lo=z_lo, group_start=gs, sums=sums)
+    stats = torch.empty(2, cout, 4, device=dev)
+    rm, rv, nbt = torch.zeros(cout, device=dev), torch.ones(cout, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+    ops.bn_finalize(sums, gs, cout, h * w, gamma.to(dev), beta.to(dev), zero, rm, rv, nbt, stats)
+    y, y_lo = torch.empty_like(z), torch.empty_like(z)
+    p, p_lo = (torch.empty(n, h // 2, w // 2, cout, dtype=torch.float16, device=dev) for _ in range(2))
+    ops.bn_apply(z, stats, gs, True, y=y, y_pool=p, z_lo=z_lo, y_lo=y_lo, y_pool_lo=p_lo)
+    torch.cuda.synchronize()
+    zr = F.conv2d(x.double(), wt.double(), None, padding=1)
+    ref = torch.cat([F.relu(F.batch_norm(zr[lo:hi], None, None, gamma.double(), beta.double(), True, 0.0, 1e-5))
+                     for lo, hi in ((0, 3), (3, 4))]).float()
+    assert (_join(z, z_lo) - zr.float()).abs().max().item() / zr.abs().max().item() < 2e-5
+    assert (_join(y, y_lo) - ref).abs().max().item() / ref.abs().max().item() < 5e-5
+    assert (_join(p, p_lo) - F.max_pool2d(ref, 2, 2)).abs().max().item() / ref.abs().max().item() < 5e-5
+    assert int(nbt) == 2
+    # bn_stats on the planes == the fused statistics
+    s2 = torch.zeros_like(sums)
+    ops.bn_stats(z, gs, s2, z_lo=z_lo)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(s2, sums, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('cin', [1, 3])
+def test_conv3x3_first_split(dev, cin):
+    from rpnet_b200 import ops
+    g = _gen(3 + cin)
+    n, h, w = 2, 40, 24
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(64, cin, 3, 3, generator=g) / 3
+    scale, shift = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.1
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, padding=1) * scale[None, :, None, None].double() + shift[None, :, None, None].double()).float()
+    out = torch.empty(n, h, w, 64, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(out)
+    ops.conv3x3_first(x.to(dev), wt.to(dev), scale.to(dev), shift.to(dev), True, out, out_lo=lo)
+    torch.cuda.synchronize()
+    assert (_join(out, lo) - ref).abs().max().item() / ref.abs().max().item() < 1e-5
+
+
+def test_upconv_split_phases(dev):
+    """nn.Upsample(x2, nearest) + 3x3 conv (net/modules.py:65-68) as four split-fp16 phase convs."""
+    from rpnet_b200 import engine, ops
+    g = _gen(11)
+    n, cin, cout, h, w = 2, 128, 64, 16, 8
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
+    scale, shift = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    ref = F.relu(F.conv2d(F.interpolate(x.double(), scale_factor=2, mode='nearest'), wt.double(), None, padding=1)
+                 * scale[None, :, None, None].double() + shift[None, :, None, None].double()).float()
+    phases = engine.pack_upsample_phases(wt.to(dev), split=True)
+    out = engine.run_upconv(phases, scale.to(dev), shift.to(dev), _pair(x, dev), engine.Workspace(), 't', split=True)
+    torch.cuda.synchronize()
+    assert (_join(*out) - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    # the device pack of the train path
+    wf = torch.empty(4, 4, cout, 2 * cin, dtype=torch.float16, device=dev)
+    w16 = torch.empty(16, cin, cout, dtype=torch.bfloat16, device=dev)
+    ops.pack_upconv_weight(wt.to(dev), wf, w16, split=True)
+    torch.cuda.synchronize()
+    for ph, (wp, taps, _) in enumerate(phases):
+        torch.testing.assert_close(wf[ph].float(), wp.float(), rtol=0, atol=2e-7)   # sums of taps in a different order

@@ -9,7 +9,7 @@ amplifies the rounding of z; rounding the oracle the same way reproduces the lev
 over the cases below; the statistics are accumulated with float atomics, so the last digits vary run to run); loss rel 2e-3; per-parameter gradient rel-L2 3e-2 for tensors that carry signal (bf16
 gradient operands) — measured against the conditioning of the problem, see _check_grads; BN running stats 1e-3.  The hard mask (net/rp_net.py:310) makes iteration i+1 discontinuous in
 iteration i's logits: when a near-tie pixel flips, later iterations are compared through the flipped fraction only."""
-LOGIT_TOL = 1e-2
+LOGIT_TOL = 1e-3
 import numpy as np
 import pytest
 import torch
