@@ -224,8 +224,13 @@ long long rpnet_upconv_wgrad_workspace_bytes(int cin, int n, int h, int w, int c
 int rpnet_upconv_wgrad(const void* x_low, int x_bf16, const void* dz_bf16, int n, int h, int w, int cin, int cout, float* grad,
                        int accumulate, void* workspace, long long workspace_bytes, void* stream);
 
-/* Weight gradient of the Cin = 1 first conv: grad[64][1][3][3] += sum dz * img.  net/unet.py:405 (encoder.Conv1.conv.0). */
-int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream);
+/* Weight gradient of the Cin = 1 first conv: grad[64][1][3][3] += sum dz * img.  net/unet.py:405 (encoder.Conv1.conv.0).
+ * scratch576: 576 doubles.  Determinism (this and every reduction of the training path below): per-thread / per-warp / per-block
+ * fp32 partial sums are formed in a fixed order and then accumulated in FP64 — adding fp32 addends into a double is exact, hence
+ * independent of the order in which warps and blocks arrive, unless an addend is below 2^-30 of the running sum — so two
+ * identical train steps produce bit-identical gradients. */
+int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch576,
+                              void* stream);
 
 /* fp32 [cout][cin_real][taps] -> fp16 [taps][cout][cin] (forward pack) and/or bf16 [taps][cin][cout] (dgrad pack);
  * cin = cin_real + hole_len with zero padding channels at [hole_start, hole_start+hole_len). */
@@ -263,7 +268,8 @@ int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h, int w, i
  *   g_direct : bf16 (fp32 if d_is_f32) NHWC with pixel pitch d_ld, channel offset d_off          (may be null)
  *   g_pool   : bf16 NHWC [n][h/2][w/2] gradient of the max-pooled copy, routed to the window's first max (may be null)
  *   g_up     : bf16 NHWC [n][2h][2w] gradient of the nearest-x2 upsampled copy, summed per 2x2     (may be null)
- * dgamma[c] += sum dy*x_hat, dbeta[c] += sum dy (fp32, may be null).  scratch: fp32 [groups][c][4]. */
+ * dgamma[c] += sum dy*x_hat, dbeta[c] += sum dy (fp32, may be null).  scratch: 8-byte aligned, groups*c*6 floats
+ * (fp64 sums [groups][c][2] followed by fp32 coefficients [groups][c][2]). */
 int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups, int relu,
                  const void* g_direct, int d_ld, int d_off, int d_is_f32, const void* g_pool_bf16, int p_ld, int p_off,
                  const void* g_up_bf16, int u_ld, int u_off, float* dgamma, float* dbeta, float* scratch,
@@ -287,9 +293,10 @@ int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const void* dq_
                          void* stream);
 
 /* Backward of calDist (net/rp_net.py:353-363).  feat fp32 [n][hw][64]; protos fp32 [proto_sets][p][64], image i uses
- * set i % proto_sets; dpred fp32 [n][p][hw]; dfeat (= or += when accumulate); dprotos += (caller zeroes; may be null). */
+ * set i % proto_sets; dpred fp32 [n][p][hw]; dfeat (= or += when accumulate); dprotos (may be null) = the prototype gradient,
+ * accumulated in the fp64 scratch dprotos_acc [proto_sets][p][64] (required with dprotos). */
 int rpnet_cos_sim_bwd_f32(const float* feat, const float* protos, const float* dpred, int n, int hw, int c, int n_protos,
-                          int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, void* stream);
+                          int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, double* dprotos_acc, void* stream);
 
 /* Adjoint of F.interpolate(bilinear, align_corners=False): out[n][i][j] = sum_{Y,X} wy(Y,i) wx(X,j) in[n][Y][X].
  * (a) masked-average-pool weights U^T mask (net/rp_net.py:373-376), (b) backward of the logit upsample (:303,337).
@@ -309,9 +316,9 @@ int rpnet_proto_finalize_bwd_f32(const float* dprotos, float* draw, int ways, in
 
 /* dice_ce (net/rp_net.py:87-127) for `groups` logit tensors sharing the labels: logits fp32 [groups][batch][classes][hw],
  * labels int64 [batch][hw]; loss[g] = dice + CE; dlogits (optional) = grad_scale * dloss_g/dlogits.
- * sums: fp32 scratch [groups][2*classes+1]. */
+ * sums: fp64 scratch [groups][2*classes+1]. */
 int rpnet_dice_ce_f32(const float* logits, const long long* labels, int groups, int batch, int n_classes, long long hw,
-                      float eps, float grad_scale, float* sums, float* dlogits, float* loss, void* stream);
+                      float eps, float grad_scale, double* sums, float* dlogits, float* loss, void* stream);
 
 /* alignLoss pieces (net/rp_net.py:394-440).  class_pool: argmax over pred [batch][classes][hw] -> per-class masked mean
  * of feat [batch][hw][64] -> qproto [batch][classes][64], counts [batch][classes], amax int32 [batch][hw]. */
@@ -324,9 +331,9 @@ int rpnet_align_gather_f32(const float* qproto, const float* counts, int ways, i
                            float* protos_s, float* weight, void* stream);
 int rpnet_align_scatter_f32(const float* dprotos_s, int ways, int shots, int batch, float* dqproto, void* stream);
 /* Cross entropy with ignore over 2-class logits [n][2][hw]; label = 1 where fore == 1, else 0 where back == 1, else
- * ignored; *loss = sum_n weight[n] * mean_valid(nll_n); dlogits (optional) = grad_scale * dloss.  sums: scratch [n][2]. */
+ * ignored; *loss = sum_n weight[n] * mean_valid(nll_n); dlogits (optional) = grad_scale * dloss.  sums: fp64 scratch [n][2]. */
 int rpnet_ce_mask_f32(const float* logits, const float* fore, const float* back, const float* weight, int n, long long hw,
-                      float grad_scale, float* sums, float* dlogits, float* loss, void* stream);
+                      float grad_scale, double* sums, float* dlogits, float* loss, void* stream);
 /* F.interpolate(bilinear, align_corners=False) of fp32 maps [n][h][w] -> [n][out_h][out_w]  (net/rp_net.py:430). */
 int rpnet_bilinear_up_f32(const float* in, float* out, int n, int h, int w, int out_h, int out_w, void* stream);
 

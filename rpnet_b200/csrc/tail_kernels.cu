@@ -121,7 +121,7 @@ local_corr_bwd_kernel(const __half* __restrict__ f1, const __half* __restrict__ 
 constexpr int kMaxP = 8;
 __global__ void __launch_bounds__(256)
 cos_sim_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ protos, const float* __restrict__ dpred, int hw, int P,
-                   int n_p, float scaler, float* __restrict__ dfeat, int accumulate, float* __restrict__ dprotos) {
+                   int n_p, float scaler, float* __restrict__ dfeat, int accumulate, double* __restrict__ dprotos) {
   __shared__ float s_p[kMaxP][64];
   __shared__ float s_pn[kMaxP];
   __shared__ float s_dp[16][kMaxP][64];
@@ -198,9 +198,14 @@ cos_sim_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ pro
       float s = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) s += s_dp[k][i / 64][i % 64];
-      atomicAdd(dprotos + (size_t)pb * P * 64 + i, s);
+      atomicAdd(dprotos + (size_t)pb * P * 64 + i, (double)s);    // fp32 partials in fp64: exact, order-independent
     }
   }
+}
+
+__global__ void cvt_f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -398,7 +403,7 @@ __global__ void proto_finalize_bwd_kernel(const float* __restrict__ dprotos, flo
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dice_ce_reduce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int P, long long HW,
-                      float* __restrict__ sums) {
+                      double* __restrict__ sums) {
   __shared__ float s_red[8][2 * kMaxP + 1];
   const int g = blockIdx.y;
   const float* lg = logits + (size_t)g * B * P * HW;
@@ -449,20 +454,21 @@ dice_ce_reduce_kernel(const float* __restrict__ logits, const long long* __restr
     float s = 0.f;
     for (int wv = 0; wv < 8; ++wv) s += s_red[wv][threadIdx.x];
     const int k = threadIdx.x;
-    if (k < kMaxP) { if (k < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + k, s); }
-    else if (k < 2 * kMaxP) { if (k - kMaxP < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + P + (k - kMaxP), s); }
-    else atomicAdd(sums + (size_t)g * (2 * P + 1) + 2 * P, s);
+    // fp32 block partials accumulated in fp64 (exact for fp32 addends: the result does not depend on the block order)
+    if (k < kMaxP) { if (k < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + k, (double)s); }
+    else if (k < 2 * kMaxP) { if (k - kMaxP < P) atomicAdd(sums + (size_t)g * (2 * P + 1) + P + (k - kMaxP), (double)s); }
+    else atomicAdd(sums + (size_t)g * (2 * P + 1) + 2 * P, (double)s);
   }
 }
 
 // dlogits = grad_scale * d loss_g / d logits;  loss[g] written by block (0, g).
 __global__ void __launch_bounds__(256)
-dice_ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ sums, int B,
+dice_ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const double* __restrict__ sums, int B,
                     int P, long long HW, float eps, float grad_scale, float* __restrict__ dlogits, float* __restrict__ loss) {
   const int g = blockIdx.y;
   const float* lg = logits + (size_t)g * B * P * HW;
   float* dl = dlogits + (size_t)g * B * P * HW;
-  const float* sm = sums + (size_t)g * (2 * P + 1);
+  const double* sm = sums + (size_t)g * (2 * P + 1);
   const float npix = (float)((long long)B * HW);
   float cA[kMaxP], cB[kMaxP];        // d dice / d p_k = -(1/P) * (2 oh_k / (Card_k+eps) - 2 I_k / (Card_k+eps)^2) = oh_k * cA[k] + cB[k]
   float dice = 0.f;
@@ -470,13 +476,13 @@ dice_ce_grad_kernel(const float* __restrict__ logits, const long long* __restric
   for (int k = 0; k < kMaxP; ++k) {
     cA[k] = 0.f; cB[k] = 0.f;
     if (k < P) {
-      const float I = sm[k], Cd = sm[P + k] + eps;
+      const float I = (float)sm[k], Cd = (float)sm[P + k] + eps;
       cA[k] = -2.f / (Cd * (float)P);
       cB[k] = 2.f * I / (Cd * Cd * (float)P);
       dice += 2.f * I / Cd;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[g] = 1.f - dice / (float)P + sm[2 * P] / npix;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss) loss[g] = 1.f - dice / (float)P + (float)sm[2 * P] / npix;
   const long long total = dlogits ? (long long)B * HW : 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long b = i / HW, pix = i % HW;
@@ -614,7 +620,7 @@ __global__ void align_scatter_kernel(const float* __restrict__ dprotos_s, int Wa
 //     else ignored (net/rp_net.py:432-438).  sums[n] = {sum nll, valid count}.
 __global__ void __launch_bounds__(256)
 ce_mask_reduce_kernel(const float* __restrict__ logits, const float* __restrict__ fore, const float* __restrict__ back, long long HW,
-                      float* __restrict__ sums) {
+                      double* __restrict__ sums) {
   __shared__ float s_red[8][2];
   const int n = blockIdx.y;
   float nll = 0.f, cnt = 0.f;
@@ -638,23 +644,23 @@ ce_mask_reduce_kernel(const float* __restrict__ logits, const float* __restrict_
   if (threadIdx.x < 2) {
     float s = 0.f;
     for (int wv = 0; wv < 8; ++wv) s += s_red[wv][threadIdx.x];
-    atomicAdd(sums + (size_t)n * 2 + threadIdx.x, s);
+    atomicAdd(sums + (size_t)n * 2 + threadIdx.x, (double)s);      // fp32 partials in fp64: exact, order-independent
   }
 }
 
 __global__ void __launch_bounds__(256)
 ce_mask_grad_kernel(const float* __restrict__ logits, const float* __restrict__ fore, const float* __restrict__ back,
-                    const float* __restrict__ sums, const float* __restrict__ weight, int N, long long HW, float grad_scale,
+                    const double* __restrict__ sums, const float* __restrict__ weight, int N, long long HW, float grad_scale,
                     float* __restrict__ dlogits, float* __restrict__ loss) {
   const int n = blockIdx.y;
-  const float cnt = sums[(size_t)n * 2 + 1];
+  const float cnt = (float)sums[(size_t)n * 2 + 1];
   const float wgt = weight[n];
   const float k = (cnt > 0.f) ? grad_scale * wgt / cnt : 0.f;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && loss) {
     float s = 0.f;
     for (int i = 0; i < N; ++i) {
-      const float c = sums[(size_t)i * 2 + 1];
-      if (weight[i] != 0.f && c > 0.f) s += weight[i] * sums[(size_t)i * 2] / c;
+      const float c = (float)sums[(size_t)i * 2 + 1];
+      if (weight[i] != 0.f && c > 0.f) s += weight[i] * (float)sums[(size_t)i * 2] / c;
     }
     *loss = s;
   }
@@ -757,15 +763,22 @@ RPNET_API int rpnet_local_corr_bwd(const void* f1_f16, const void* f2_f16, const
 }
 
 RPNET_API int rpnet_cos_sim_bwd_f32(const float* feat, const float* protos, const float* dpred, int n, int hw, int c, int n_protos,
-                                     int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, void* stream_) {
+                                     int proto_sets, float scaler, float* dfeat, int accumulate, float* dprotos, double* dprotos_acc,
+                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(feat && protos && dpred && dfeat, "cos_sim_bwd: null pointer argument");
+  RPNET_REQUIRE(!dprotos || dprotos_acc, "cos_sim_bwd: dprotos needs the fp64 accumulator scratch");
   RPNET_REQUIRE(c == 64, "cos_sim_bwd: feature width must be 64 (got %d)", c);
   RPNET_REQUIRE(n_protos >= 1 && n_protos <= kMaxP, "cos_sim_bwd: n_protos %d out of range [1, %d]", n_protos, kMaxP);
   RPNET_REQUIRE(n > 0 && hw > 0 && proto_sets > 0 && n % proto_sets == 0, "cos_sim_bwd: bad shape n=%d sets=%d", n, proto_sets);
   int bx = (hw + 16 * 8 - 1) / (16 * 8);
   if (bx < 1) bx = 1;
-  cos_sim_bwd_kernel<<<dim3(bx, n), 256, 0, stream>>>(feat, protos, dpred, hw, n_protos, proto_sets, scaler, dfeat, accumulate, dprotos);
+  const int np = proto_sets * n_protos * 64;
+  if (dprotos) RPNET_CUDA_OK(cudaMemsetAsync(dprotos_acc, 0, (size_t)np * sizeof(double), stream));
+  cos_sim_bwd_kernel<<<dim3(bx, n), 256, 0, stream>>>(feat, protos, dpred, hw, n_protos, proto_sets, scaler, dfeat, accumulate,
+                                                      dprotos ? dprotos_acc : nullptr);
+  RPNET_CUDA_OK(cudaGetLastError());
+  if (dprotos) cvt_f64_to_f32_kernel<<<(np + 255) / 256, 256, 0, stream>>>(dprotos_acc, dprotos, np);
   return check_cuda(cudaGetLastError(), "cos_sim_bwd launch");
 }
 
@@ -814,11 +827,11 @@ RPNET_API int rpnet_proto_finalize_bwd_f32(const float* dprotos, float* draw, in
 }
 
 RPNET_API int rpnet_dice_ce_f32(const float* logits, const long long* labels, int groups, int batch, int n_classes, long long hw,
-                                 float eps, float grad_scale, float* sums, float* dlogits, float* loss, void* stream_) {
+                                 float eps, float grad_scale, double* sums, float* dlogits, float* loss, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(logits && labels && sums && loss, "dice_ce: null pointer argument");
   RPNET_REQUIRE(groups > 0 && batch > 0 && hw > 0 && n_classes >= 2 && n_classes <= kMaxP, "dice_ce: bad shape (classes 2..%d)", kMaxP);
-  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * (2 * n_classes + 1) * sizeof(float), stream));
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * (2 * n_classes + 1) * sizeof(double), stream));
   int bx = grid_for((long long)batch * hw, 256 * 4, 8);
   bx = (bx + groups - 1) / groups;
   if (bx < 1) bx = 1;
@@ -871,11 +884,11 @@ RPNET_API int rpnet_align_scatter_f32(const float* dprotos_s, int ways, int shot
 }
 
 RPNET_API int rpnet_ce_mask_f32(const float* logits, const float* fore, const float* back, const float* weight, int n, long long hw,
-                                 float grad_scale, float* sums, float* dlogits, float* loss, void* stream_) {
+                                 float grad_scale, double* sums, float* dlogits, float* loss, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(logits && fore && back && weight && sums && loss, "ce_mask: null pointer argument");
   RPNET_REQUIRE(n > 0 && hw > 0, "ce_mask: bad shape");
-  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)n * 2 * sizeof(float), stream));
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)n * 2 * sizeof(double), stream));
   int bx = grid_for(hw, 256 * 4, 2);
   ce_mask_reduce_kernel<<<dim3(bx, n), 256, 0, stream>>>(logits, fore, back, hw, sums);
   RPNET_CUDA_OK(cudaGetLastError());

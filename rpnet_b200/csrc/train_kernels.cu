@@ -315,7 +315,7 @@ __device__ __forceinline__ void load_grad8(const GradSrc& s, int n, int y, int x
 template <bool WIN, int MODE>
 __global__ void __launch_bounds__(256, WIN ? 2 : 3)
 bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N, int H,
-              int W, int c8, int relu, GradSrc src, float* __restrict__ sums, uint4* __restrict__ dz) {
+              int W, int c8, int relu, GradSrc src, double* __restrict__ sums, uint4* __restrict__ dz) {
   __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
   const int C = c8 * 8;
   const int Hs = WIN ? H / 2 : H, Ws = WIN ? W / 2 : W;
@@ -415,11 +415,14 @@ bn_bwd_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, cons
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
+      // fp32 block partials (fixed summation order inside the block) accumulated in fp64: the addition of fp32 addends into
+      // a double is exact — hence independent of the order the blocks arrive in — unless an addend is below 2^-30 of the
+      // running sum; two identical runs give bit-identical gradients (tests/test_gpu_train.py::test_backward_is_deterministic)
+      double* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
-        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+        atomicAdd(dst + 2 * j, (double)s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, (double)s_red[threadIdx.x * 16 + 8 + j]);
       }
     }
   }
@@ -432,7 +435,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N,
                      int HW, int c8, int relu, const __nv_bfloat16* __restrict__ gdir, int d_ld, int d_off,
-                     float* __restrict__ sums, uint4* __restrict__ dz) {
+                     double* __restrict__ sums, uint4* __restrict__ dz) {
   constexpr int U = 4;
   __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
   const int C = c8 * 8;
@@ -508,11 +511,14 @@ bn_bwd_direct_kernel(const uint4* __restrict__ z, const float* __restrict__ stat
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
+      // fp32 block partials (fixed summation order inside the block) accumulated in fp64: the addition of fp32 addends into
+      // a double is exact — hence independent of the order the blocks arrive in — unless an addend is below 2^-30 of the
+      // running sum; two identical runs give bit-identical gradients (tests/test_gpu_train.py::test_backward_is_deterministic)
+      double* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
-        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+        atomicAdd(dst + 2 * j, (double)s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, (double)s_red[threadIdx.x * 16 + 8 + j]);
       }
     }
   }
@@ -525,7 +531,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 3 : 2)
 bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ coef, Groups gr, int N,
                    int H, int W, int c8, int relu, const __nv_bfloat16* __restrict__ pooled, int p_ld, int p_off,
-                   float* __restrict__ sums, uint4* __restrict__ dz) {
+                   double* __restrict__ sums, uint4* __restrict__ dz) {
   __shared__ float s_red[MODE == 0 ? 256 * 16 : 1];
   const int C = c8 * 8;
   const int Hs = H / 2, Ws = W / 2;
@@ -614,18 +620,21 @@ bn_bwd_pool_kernel(const uint4* __restrict__ z, const float* __restrict__ stats,
       __syncthreads();
     }
     if (pl == 0) {
-      float* dst = sums + ((size_t)bg * C + v * 8) * 2;
+      // fp32 block partials (fixed summation order inside the block) accumulated in fp64: the addition of fp32 addends into
+      // a double is exact — hence independent of the order the blocks arrive in — unless an addend is below 2^-30 of the
+      // running sum; two identical runs give bit-identical gradients (tests/test_gpu_train.py::test_backward_is_deterministic)
+      double* dst = sums + ((size_t)bg * C + v * 8) * 2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dst + 2 * j, s_red[threadIdx.x * 16 + j]);
-        atomicAdd(dst + 2 * j + 1, s_red[threadIdx.x * 16 + 8 + j]);
+        atomicAdd(dst + 2 * j, (double)s_red[threadIdx.x * 16 + j]);
+        atomicAdd(dst + 2 * j + 1, (double)s_red[threadIdx.x * 16 + 8 + j]);
       }
     }
   }
 }
 
 // coef[g][c] = (m1, m2) = (S1 / cnt, rstd * S2 / cnt);  dgamma[c] += sum_g rstd * S2, dbeta[c] += sum_g S1
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ stats, Groups gr, int C, int HW,
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ stats, Groups gr, int C, int HW,
                                        float* dgamma, float* dbeta, float* __restrict__ coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -633,7 +642,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, const flo
   for (int g = 0; g < gr.G; ++g) {
     const float cnt = (float)(gr.start[g + 1] - gr.start[g]) * (float)HW;
     const float rstd = stats[((size_t)g * C + c) * 4 + 1];
-    const float S1 = sums[((size_t)g * C + c) * 2], S2 = rstd * sums[((size_t)g * C + c) * 2 + 1];
+    const float S1 = (float)sums[((size_t)g * C + c) * 2], S2 = rstd * (float)sums[((size_t)g * C + c) * 2 + 1];
     coef[((size_t)g * C + c) * 2] = S1 / cnt;
     coef[((size_t)g * C + c) * 2 + 1] = S2 / cnt;
     db += S1;
@@ -804,9 +813,9 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout,
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restrict__ dz, int N, int H, int W,
-                           float* __restrict__ grad /*[64][9]*/) {
-  __shared__ float s_acc[64 * 9];
-  for (int i = threadIdx.x; i < 64 * 9; i += 256) s_acc[i] = 0.f;
+                           double* __restrict__ acc64 /*[64][9], zeroed*/) {
+  __shared__ double s_acc[64 * 9];      // fp32 warp partials added in fp64: exact, so the arrival order of warps / blocks is immaterial
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) s_acc[i] = 0.0;
   __syncthreads();
   const int cg = threadIdx.x & 7;
   float acc[9][8];
@@ -855,10 +864,15 @@ conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restric
       float a = acc[t][j];
       a += __shfl_xor_sync(0xffffffffu, a, 8);
       a += __shfl_xor_sync(0xffffffffu, a, 16);
-      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(cg * 8 + j) * 9 + t], a);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_acc[(cg * 8 + j) * 9 + t], (double)a);
     }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 9; i += 256) atomicAdd(grad + i, s_acc[i]);
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) atomicAdd(acc64 + i, (double)(float)s_acc[i]);
+}
+
+__global__ void add_f64_to_f32_kernel(const double* __restrict__ acc, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += (float)acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -963,7 +977,7 @@ RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const fl
 // Backward of BatchNorm(batch stats)+ReLU for dz, in three launches: reduce -> finalize (dgamma, dbeta) -> apply.
 RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups, int relu,
                            const void* g_direct, int d_ld, int d_off, int d_is_f32, const void* g_pool_bf16, int p_ld, int p_off,
-                           const void* g_up_bf16, int u_ld, int u_off, float* dgamma, float* dbeta, float* scratch /*[G][C][4]*/,
+                           const void* g_up_bf16, int u_ld, int u_off, float* dgamma, float* dbeta, float* scratch /*[G][C][6]*/,
                            void* dz_bf16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(z && stats && scratch && dz_bf16, "bn_bwd: null pointer argument");
@@ -979,9 +993,10 @@ RPNET_API int rpnet_bn_bwd(const void* z, const float* stats, int n, int h, int 
   src.direct = g_direct; src.d_ld = d_ld; src.d_off = d_off; src.d_f32 = d_is_f32;
   src.pooled = static_cast<const __nv_bfloat16*>(g_pool_bf16); src.p_ld = p_ld; src.p_off = p_off;
   src.up = static_cast<const __nv_bfloat16*>(g_up_bf16); src.u_ld = u_ld; src.u_off = u_off;
-  float* sums = scratch;                                  // [G][C][2]
-  float* coef = scratch + (size_t)groups * c * 2;         // [G][C][2]
-  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(float), stream));
+  RPNET_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 8 == 0, "bn_bwd: scratch must be 8-byte aligned");
+  double* sums = reinterpret_cast<double*>(scratch);      // [G][C][2] fp64
+  float* coef = scratch + (size_t)groups * c * 4;         // [G][C][2] fp32
+  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * c * 2 * sizeof(double), stream));
   const bool win = g_pool_bf16 != nullptr;
   const int c8 = c / 8, lanes = 256 / c8;
   // reduction launches: 1-D grid, blocks per call group proportional to the group's size
@@ -1077,15 +1092,19 @@ RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_rea
   return check_cuda(cudaGetLastError(), "pack_conv_weight launch");
 }
 
-RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, void* stream_) {
+RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch576,
+                                         void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RPNET_REQUIRE(img && dz_bf16 && grad, "conv3x3_first_wgrad: null pointer argument");
+  RPNET_REQUIRE(img && dz_bf16 && grad && scratch576, "conv3x3_first_wgrad: null pointer argument");
+  RPNET_CUDA_OK(cudaMemsetAsync(scratch576, 0, 576 * sizeof(double), stream));
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && (long long)n * h * w < (1LL << 31), "conv3x3_first_wgrad: bad shape");
   const long long total = (long long)n * h * w * 8;
   long long blocks = (total + 256 * 16 - 1) / (256 * 16);
   if (blocks > 148LL * 4) blocks = 148LL * 4;
   if (blocks < 1) blocks = 1;
-  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const uint4*>(dz_bf16), n, h, w, grad);
+  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const uint4*>(dz_bf16), n, h, w, scratch576);
+  RPNET_CUDA_OK(cudaGetLastError());
+  add_f64_to_f32_kernel<<<3, 192, 0, stream>>>(scratch576, grad, 576);
   return check_cuda(cudaGetLastError(), "conv3x3_first_wgrad launch");
 }
 

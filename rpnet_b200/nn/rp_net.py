@@ -350,5 +350,5 @@ class RP_Net(nn.Module):
         lg = torch.empty(n, 2, H, W, dtype=f32, device=dev)
         ops.bilinear_up(pred_s.view(n * 2, h, w), lg.view(n * 2, H, W))
         loss = torch.empty(1, dtype=f32, device=dev)
-        ops.ce_mask(lg, fore, back, wgt, torch.empty(n, 2, dtype=f32, device=dev), loss)
+        ops.ce_mask(lg, fore, back, wgt, torch.empty(n, 2, dtype=torch.float64, device=dev), loss)
         return loss[0]

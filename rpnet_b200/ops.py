@@ -382,13 +382,24 @@ def conv_wgrad(x0, dz, taps, grad, workspace, x1=None, hole=(0, 0), accumulate=T
     _lib.check(rc, 'rpnet_conv_wgrad')
 
 
+def _scratch64(n, device, slot):
+    """Small persistent fp64 scratch (reduction accumulators; contents dead after the call)."""
+    key = ('f64', slot, str(device))
+    t = _CONST.get(key)
+    if t is None or t.numel() < n:
+        t = torch.empty(max(int(n), 1024), dtype=torch.float64, device=device)
+        _CONST[key] = t
+    return t
+
+
 def conv3x3_first_wgrad(img, dz, grad):
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
     n, cin, h, w = img.shape
     assert cin == 1 and tuple(dz.shape) == (n, h, w, 64) and grad.numel() == 64 * 9
-    with _Timed('conv3x3_first_wgrad', float(img.numel() * 4 + dz.numel() * 2)):
-        _lib.check(lib.rpnet_conv3x3_first_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _stream()), 'rpnet_conv3x3_first_wgrad')
+    with _Timed('conv3x3_first_wgrad', float(img.numel() * 4 + dz.numel() * 2), n=2):
+        _lib.check(lib.rpnet_conv3x3_first_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _ptr(_scratch64(576, img.device, 'first_wgrad')),
+                                                 _stream()), 'rpnet_conv3x3_first_wgrad')
 
 
 def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):
@@ -474,7 +485,7 @@ def bn_bwd(z, stats, group_start, dz, scratch, relu=True, direct=None, d_off=0, 
     _req(z, torch.float16, 'z'); _req(dz, bf16, 'dz')
     n, h, w, c = z.shape
     gs, g = _groups(group_start)
-    assert scratch.numel() >= g * c * 4
+    assert scratch.dtype == torch.float32 and scratch.numel() >= g * c * 6 and scratch.data_ptr() % 8 == 0
     d_ld = direct.shape[-1] if direct is not None else 0
     p_ld = pooled.shape[-1] if pooled is not None else 0
     u_ld = up.shape[-1] if up is not None else 0
@@ -532,9 +543,10 @@ def cos_sim_bwd(feat, protos, dpred, dfeat, dprotos=None, scaler=20.0, accumulat
     n, h, w, c = feat.shape
     sets, p = protos.shape[0], protos.shape[1]
     assert tuple(dpred.shape) == (n, p, h, w) and dfeat.shape == feat.shape
-    with _Timed('cos_sim_bwd', float(feat.numel() * 8 + dpred.numel() * 4)):
+    acc = _scratch64(sets * p * c, feat.device, 'cos_sim_bwd') if dprotos is not None else None
+    with _Timed('cos_sim_bwd', float(feat.numel() * 8 + dpred.numel() * 4), n=1 if dprotos is None else 2):
         _lib.check(lib.rpnet_cos_sim_bwd_f32(_ptr(feat), _ptr(protos), _ptr(dpred), n, h * w, c, p, sets, float(scaler), _ptr(dfeat),
-                                             int(bool(accumulate)), _ptr(dprotos), _stream()), 'rpnet_cos_sim_bwd_f32')
+                                             int(bool(accumulate)), _ptr(dprotos), _ptr(acc), _stream()), 'rpnet_cos_sim_bwd_f32')
 
 
 def bilinear_adjoint(x, out, sums=None):
@@ -577,9 +589,10 @@ def proto_finalize_bwd(dprotos, draw):
 
 
 def dice_ce(logits, labels, sums, loss, dlogits=None, grad_scale=1.0, eps=1e-7):
-    """logits fp32 [G,B,P,H,W]; labels int64 [B,H,W]; loss fp32 [G]; dlogits like logits (optional)."""
+    """logits fp32 [G,B,P,H,W]; labels int64 [B,H,W]; loss fp32 [G]; dlogits like logits (optional); sums: fp64 scratch."""
     lib = _lib.load()
     _req(logits, torch.float32, 'logits'); _req(labels, torch.int64, 'labels'); _req(loss, torch.float32, 'loss')
+    _req(sums, torch.float64, 'sums')
     g, b, p, h, w = logits.shape
     assert tuple(labels.shape) == (b, h, w) and sums.numel() >= g * (2 * p + 1) and loss.numel() >= g
     with _Timed('dice_ce', float(logits.numel() * (12 if dlogits is not None else 4)), n=2):
@@ -626,6 +639,7 @@ def align_scatter(dprotos_s, ways, shots, dqproto):
 def ce_mask(logits, fore, back, weight, sums, loss, dlogits=None, grad_scale=1.0):
     lib = _lib.load()
     _req(logits, torch.float32, 'logits'); _req(fore, torch.float32, 'fore'); _req(back, torch.float32, 'back')
+    _req(sums, torch.float64, 'sums')
     n, two, h, w = logits.shape
     assert two == 2 and fore.numel() == n * h * w and back.numel() == n * h * w and weight.numel() == n and sums.numel() >= 2 * n
     with _Timed('ce_mask', float(logits.numel() * (12 if dlogits is not None else 4)), n=2):

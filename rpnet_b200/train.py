@@ -188,7 +188,7 @@ class _ConvBN:
         gradient w.r.t. the LOW-resolution input (4x4 stride-2 conv of dz)."""
         n, H, W, c = z.shape
         dz = eng.scratch('dz', n * H * W * c, bf16).view(n, H, W, c)
-        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 4, f32), True, dgamma=self.ggamma, dbeta=self.gbeta, **src)
+        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 6, f32), True, dgamma=self.ggamma, dbeta=self.gbeta, **src)
         h, w, cin = x_low.shape[1:]
         nb = ops.upconv_wgrad_workspace_bytes(cin, n, h, w, self.cout)
         ops.upconv_wgrad(x_low, dz, self.gw, eng.scratch('wgrad', nb // 4, f32))
@@ -218,7 +218,7 @@ class _ConvBN:
         """BN+ReLU backward -> dz; weight gradient; data gradient into `dx` (bf16 [n,h,w,cin_pack]) when given."""
         n, h, w, c = z.shape
         dz = eng.scratch('dz', n * h * w * c, bf16).view(n, h, w, c)
-        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 4, f32), True,
+        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 6, f32), True,
                    dgamma=self.ggamma, dbeta=self.gbeta, **src)
         if self.first:
             ops.conv3x3_first_wgrad(x0, dz, self.gw)
@@ -499,7 +499,7 @@ class TrainEngine:
             lg = buf('al.lg', (n_supp, 2, H, W), f32)
             ops.bilinear_up(pred_s.view(n_supp * 2, h, w), lg.view(n_supp * 2, H, W))
             self._align_args = (lg, fore, back, wgt)
-            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, f32), align)
+            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, torch.float64), align)
         else:
             align.zero_()
         self.saved = dict(Wa=Wa, Sh=Sh, B=B, H=H, W=W, h=h, w=w, C=C, T=T, P=P, n_supp=n_supp, n_tot=n_tot, d4=d4, supp_m=supp_m,
@@ -524,16 +524,14 @@ class TrainEngine:
         ops.bilinear_adjoint(dlogits.view(T * B * P, H, W), dpred.view(T * B * P, h, w))
         dfeat = buf('b.dfeat', (n_tot, h, w, 64), f32)
         dprotos = buf('b.dprotos', (B, P, 64), f32)
-        dprotos.zero_()
         ops.cos_sim_bwd(S['feat'][n_supp:], s['protos'], dpred.view(T * B, P, h, w), dfeat[n_supp:], dprotos, 20.0)
         if s['use_align'] and dalign != 0.0:
             lg, fore, back, wgt = self._align_args
             dlg = self.scratch('b.dlg', lg.numel(), f32).view(lg.shape)
-            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, f32), buf('b.align', (1,), f32), dlg, float(dalign))
+            ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, torch.float64), buf('b.align', (1,), f32), dlg, float(dalign))
             dpred_s = buf('b.dpred_s', (n_supp, 2, h, w), f32)
             ops.bilinear_adjoint(dlg.view(n_supp * 2, H, W), dpred_s.view(n_supp * 2, h, w))
             dps = buf('b.dps', (n_supp, 2, 64), f32)
-            dps.zero_()
             ops.cos_sim_bwd(S['feat'][:n_supp], buf('al.ps', (n_supp, 2, 64), f32), dpred_s, dfeat[:n_supp], dps, 20.0)
             dqp = buf('b.dqp', (B, P, 64), f32)
             ops.align_scatter(dps, Wa, Sh, dqp)
@@ -580,6 +578,20 @@ class TrainStep:
         self.buckets = GradBuckets(self.eng.flat, world_size, process_group)
         self.t = 0
         self.last = {}
+        if world_size > 1:
+            self.sync_from_rank0(process_group)
+
+    def sync_from_rank0(self, group=None):
+        """Rank 0's parameters, Adam moments and BatchNorm buffers on every rank (what torch DDP does at construction).
+        The BatchNorm running statistics then evolve rank-locally, like the reference without SyncBN; call this again (or
+        average them) before writing a checkpoint that should not depend on the rank that saves it."""
+        import torch.distributed as dist
+        f = self.eng.flat
+        for t in (f.param, f.exp_avg, f.exp_avg_sq):
+            dist.broadcast(t, src=0, group=group)
+        for b in self.net.buffers():
+            dist.broadcast(b, src=0, group=group)
+        engine.WEIGHTS_EPOCH += 1
 
     def forward_backward(self, d):
         """Loss + gradients (flat buffer / p.grad) without the optimizer: what loss.backward() leaves behind."""
@@ -591,7 +603,7 @@ class TrainStep:
         T, B, P, H, W = logits.shape
         dlogits = eng.scratch('dlogits', logits.numel(), f32).view(logits.shape)
         losses = eng.buf('losses', (T,), f32)
-        ops.dice_ce(logits, d['query_labels'].contiguous(), eng.scratch('dice.sums', T * (2 * P + 1), f32), losses, dlogits, 1.0)
+        ops.dice_ce(logits, d['query_labels'].contiguous(), eng.scratch('dice.sums', T * (2 * P + 1), torch.float64), losses, dlogits, 1.0)
         eng.backward(dlogits, self.align_scaler, self.buckets)
         self.buckets.finish()
         loss = losses.sum() + self.align_scaler * align[0]

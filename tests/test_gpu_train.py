@@ -273,3 +273,24 @@ def test_align_loss_method_vs_reference_golden(dev, golden):
     t = lambda k: torch.from_numpy(gz[k]).to(dev)
     got = net.alignLoss(t('a_q'), t('a_pred'), t('a_s'), t('a_f'), t('a_b'))
     torch.testing.assert_close(got.cpu(), torch.from_numpy(gz['align']), rtol=1e-5, atol=1e-6)
+
+
+def test_backward_is_deterministic(dev):
+    """Two identical train steps give bit-identical logits, loss and gradients: every reduction of the path forms fp32
+    partials in a fixed order and accumulates them in fp64 (exact for fp32 addends, so the arrival order of warps and
+    blocks does not matter) — no float atomics (include/rpnet_b200.h, rpnet_conv3x3_first_wgrad)."""
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    sd = weights.unet_rpnet_state_dict(0)
+    d = to_device(make_episode(2, 1, 2, 128, seed=3), dev)
+    runs = []
+    for _ in range(3):
+        net = _net({k: v.clone() for k, v in sd.items()}, 2, dev)
+        ts = TrainStep(net)
+        loss = ts.forward_backward(d)
+        torch.cuda.synchronize()
+        runs.append((ts.last['logits'].clone(), loss.clone(), ts.eng.flat.grad.clone()))
+    for lg, ls, g in runs[1:]:
+        assert torch.equal(lg, runs[0][0]) and torch.equal(ls, runs[0][1])
+        assert torch.equal(g, runs[0][2]), (g - runs[0][2]).abs().max().item()

@@ -213,7 +213,7 @@ def test_bn_backward(dev, mode):
     ops.bn_finalize(sums, gs, c, h * w, gamma.detach().to(dev), beta.detach().to(dev), None, None, None, None, stats)
     dz = torch.empty(n, h, w, c, dtype=bf16, device=dev)
     dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
-    ops.bn_bwd(zd, stats, gs, dz, torch.empty(G, c, 4, device=dev), True, dgamma=dg, dbeta=db, **kw)
+    ops.bn_bwd(zd, stats, gs, dz, torch.empty(G, c, 6, device=dev), True, dgamma=dg, dbeta=db, **kw)
     torch.cuda.synchronize()
     assert _rel(_nchw(dz), z.grad) < 5e-3, _rel(_nchw(dz), z.grad)        # bf16 output rounding
     assert _rel(dg.cpu(), gamma.grad) < 1e-4 and _rel(db.cpu(), beta.grad) < 1e-4
@@ -360,7 +360,7 @@ def test_dice_ce(dev, golden, P):
     losses = torch.stack([O.dice_ce(logits[i], lab) for i in range(2)])
     (losses[0] * 1.0 + losses[1] * 1.0).backward()
     ld = logits.detach().to(dev)
-    sums = torch.empty(2, 2 * P + 1, device=dev); loss = torch.empty(2, device=dev); dl = torch.empty_like(ld)
+    sums = torch.empty(2, 2 * P + 1, device=dev, dtype=torch.float64); loss = torch.empty(2, device=dev); dl = torch.empty_like(ld)
     ops.dice_ce(ld, lab.to(dev), sums, loss, dl)
     torch.cuda.synchronize()
     torch.testing.assert_close(loss.cpu()[0], torch.from_numpy(gz['dice_ce' if P == 2 else 'dice_ce5']), rtol=1e-5, atol=1e-6)
@@ -395,7 +395,7 @@ def test_align_loss_pipeline(dev, golden):
     ops.cos_sim(sf, ps, pred_s, 20.0)
     lg = torch.empty(n, 2, h * S, w * S, device=dev)
     ops.bilinear_up(pred_s.view(n * 2, h, w), lg.view(n * 2, h * S, w * S))
-    sums = torch.empty(n, 2, device=dev); loss = torch.empty(1, device=dev); dlg = torch.empty_like(lg)
+    sums = torch.empty(n, 2, device=dev, dtype=torch.float64); loss = torch.empty(1, device=dev); dlg = torch.empty_like(lg)
     ops.ce_mask(lg, fore, back, wgt, sums, loss, dlg)
     dpred_s = torch.empty(n, 2, h, w, device=dev)
     ops.bilinear_adjoint(dlg.view(n * 2, h * S, w * S), dpred_s.view(n * 2, h, w))
