@@ -82,3 +82,22 @@ def to_device(ep, device):
             'back_mask': [[mv(t) for t in way] for way in ep['back_mask']],
             'qry_imgs': [mv(t) for t in ep['qry_imgs']],
             'query_labels': mv(ep['query_labels']), 'appr_query_labels': mv(ep['appr_query_labels'])}
+
+
+def fitted_state_dict(net, make_batch, steps=30, lr=1e-3):
+    """Unsaturated, better-conditioned fixture for parity tests and bench.py's parity field: `steps` Adam steps of the
+    B200 train step (rpnet_b200.train.TrainStep, weight_decay 0) on `make_batch(i)` episodes.  After them the BatchNorm running
+    statistics describe the data (eval-mode logits are no longer pinned at the 20 * cos cap, where every implementation agrees)
+    and the weights have left the random initialisation where the reference's own gradient is ill-conditioned.  Returns a CPU
+    state_dict; lr = 0 only calibrates the running statistics."""
+    import torch as _t
+    from .train import TrainStep
+    was_training = net.training
+    net.train()
+    ts = TrainStep(net, lr=lr, weight_decay=0.0)
+    for i in range(steps):
+        ts.step(make_batch(i))
+    _t.cuda.synchronize()
+    ts.eng.flat.unalias_grads()
+    net.train(was_training)
+    return {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}

@@ -13,15 +13,17 @@ from .train import shard_range
 
 
 def dice_sums(pred, target):
-    """(2 * sum(t * p), sum(t) + sum(p)) on the device — the two sums of dice_score_seperate (utils/util.py:379-390)."""
+    """(2 * sum(t * p), sum(t) + sum(p), sum(t)) on the device — the sums of dice_score_seperate (utils/util.py:379-390)."""
     p, t = pred.float(), target.float()
-    return torch.stack([2.0 * (p * t).sum(), p.sum() + t.sum()])
+    return torch.stack([2.0 * (p * t).sum(), p.sum() + t.sum(), t.sum()])
 
 
-def dice_from_sums(sums):
-    """utils/util.py:379-390: 2*sum(t*p) / (sum(t)+sum(p)), rounded to 4 decimals; None for an empty target+prediction."""
+def dice_from_sums(sums, target_sum=None):
+    """utils/util.py:379-390: None when the TARGET is empty (whatever the prediction), else 2*sum(t*p) / (sum(t)+sum(p))
+    rounded to 4 decimals.  `sums` = dice_sums(...) (the target sum is its third entry unless given explicitly)."""
     num, den = float(sums[0]), float(sums[1])
-    return None if den == 0 else round(num / den, 4)
+    tsum = float(sums[2]) if target_sum is None else float(target_sum)
+    return None if tsum == 0 else round(num / den, 4)
 
 
 @torch.no_grad()

@@ -74,7 +74,7 @@ def test_cfg1_eval_vs_reference_golden(dev, golden):
     d4 = net.encoder(ep['qry_imgs'][0].to(dev), None)['d4'].cpu()
     want = torch.from_numpy(g['d4_qry'])
     err = (d4[:, ::8, ::2, ::2] - want).abs().max() / want.abs().max()
-    assert err < 1e-2, err
+    assert err < 1e-3, err
 
 
 @pytest.mark.parametrize('name', ['cfg1_T3', 'cfg1_T2_soft'])

@@ -43,7 +43,7 @@ def main():
 
     def evaluate(tag):
         net.eval()
-        sums = torch.zeros(2, device=dev)
+        sums = torch.zeros(3, device=dev)
         with torch.no_grad():
             for k in range(4):
                 d = to_device(make_episode(args.batch, 1, args.shots, args.size, seed=100000 + 17 * k), dev)
