@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — slices/sec of the RP-Net hot path on N B200s (one process per GPU), with roofline + CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train|cfg4|volume] [--impl reference|library]
 
 A "step" is one pass of the hot path (RP_Net.forward [+ backward + Adam for the train workload]) over one batch of
 synthetic CT-like slices per rank.  `value` times it with the inputs already resident in HBM; `e2e` times the same
@@ -133,22 +133,188 @@ def cpu_reference(wl, steps, warmup, sample_batch):
     return sample_batch * steps / dt, dt / steps * 1e3, cores
 
 
+def cpu_sample(wl):
+    """Slices per CPU step: the workload's own per-step batch when the host can hold it.  The 5-shot train workloads keep
+    (Wa*Sh + 1) encoder passes + (Wa*Sh + T) all-pairs correlation volumes per slice alive for autograd (~3.5 GB per slice of
+    cfg3, ~12 GB per slice of cfg4), so their CPU step is bounded to 4 / 1 slices; throughput is per slice either way."""
+    if not wl['train']:
+        return min(wl['batch'], 8)
+    return 4 if wl['ways'] == 1 else 1
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    sample = 2 if not wl['train'] else 1
-    steps, warmup = min(args.steps, 5), min(args.warmup, 1)
+    sample = cpu_sample(wl)
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
     val, ms, cores = cpu_reference(wl, steps, warmup, sample)
     line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'sample': '%d slices per step' % sample},
+            'config': {'workload': wl['name'], 'ways': wl['ways'], 'shots': wl['shots'], 'size': wl['size'], 'T': wl['T'],
+                       'backbone': 'UNet', 'sample': '%d slices per step (B200 arm: %d per GPU)' % (sample, wl['batch'])},
             'cpu_baseline': {'value': val, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d steps x %d slices of the workload (oracle restatement of the reference CPU '
                                        'data flow incl. all-pairs correlation), torch %d threads' % (steps, sample, cores)},
             'e2e': {'value': val, 'unit': 'slices/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- library arm
+def library_baseline(wl, dev, steps=5, warmup=2, batch=None):
+    """The "GPU library" baseline of SURVEY §8(d) / BASELINE.md §3: the reference's data flow (the oracle's functional torch
+    graph: nn.functional convs / batch_norm / bmm all-pairs correlation / grid_sample, torch autograd and torch.optim.Adam for
+    the train workloads) on the SAME B200 with stock PyTorch — cuDNN / cuBLAS kernels — on the same synthetic workload and
+    per-step batch.  Modes: 'tf32' = torch's defaults (cuDNN convs may use TF32, matmul fp32), 'tf32_channels_last' = the same
+    with channels-last images / weights, 'fp32' = TF32 off everywhere (the arithmetic the CPU reference performs).  Also
+    reports how far the TF32 modes' last-iteration logits are from the fp32 mode's (rel-Linf): the library's own default
+    arithmetic is TF32-class."""
+    import torch
+    from oracle import rpnet_oracle as O
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, perturb_bn_stats, to_device
+    B = batch or wl['batch']
+    cfg = model_cfg(wl['T'])
+    ep = to_device(make_episode(B, wl['ways'], wl['shots'], wl['size'], seed=0), dev)
+    res, logits = {}, {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ('tf32', 'tf32_channels_last', 'fp32'):
+            torch.backends.cudnn.allow_tf32 = mode != 'fp32'
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sd = weights.unet_rpnet_state_dict(0)
+            if not wl['train']:
+                sd = perturb_bn_stats(sd)
+            sd = {k: v.to(dev) for k, v in sd.items()}
+            d = ep
+            if mode == 'tf32_channels_last':
+                cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+                sd = {k: (cl(v) if v.dim() == 4 else v) for k, v in sd.items()}
+                d = dict(ep, supp_imgs=[[cl(t) for t in way] for way in ep['supp_imgs']], qry_imgs=[cl(t) for t in ep['qry_imgs']])
+            opt = None
+            if wl['train']:
+                params = [k for k, v in sd.items() if v.is_floating_point() and 'running' not in k]
+                for k in params:
+                    sd[k] = sd[k].clone().requires_grad_(True)
+                opt = torch.optim.Adam([sd[k] for k in params], lr=1e-5, weight_decay=1e-4)
+            last = {}
+
+            def step():
+                if wl['train']:
+                    opt.zero_grad(set_to_none=True)
+                    out = O.forward(sd, cfg, d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], d['appr_query_labels'],
+                                    training=True, allpairs=True)
+                    O.train_loss(out, d['query_labels']).backward()
+                    opt.step()
+                else:
+                    with torch.no_grad():
+                        out = O.forward(sd, cfg, d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], d['appr_query_labels'],
+                                        allpairs=True)
+                last['logits'] = out['refinement'][wl['T'] - 1].detach()
+            try:
+                step()
+                logits[mode] = last['logits'].float().clone()        # first step: identical weights in every mode
+                for _ in range(warmup - 1):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                res[mode] = {'value': B / (ms * 1e-3), 'unit': 'slices/s', 'ms_per_step': ms, 'batch': B}
+            except RuntimeError as e:                                  # e.g. out of memory in one mode: report, keep going
+                res[mode] = {'unavailable': str(e).splitlines()[0][:200]}
+            del sd, opt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    if 'fp32' in logits:
+        ref = logits['fp32']
+        for mode in ('tf32', 'tf32_channels_last'):
+            if mode in logits and 'value' in res.get(mode, {}):
+                res[mode]['logits_rel_linf_vs_fp32_mode'] = ((logits[mode] - ref).abs().max() / ref.abs().max()).item()
+    res['what'] = ('oracle functional graph (the reference data flow incl. all-pairs bmm correlation%s) with stock PyTorch %s on this GPU, '
+                   '%d timed steps after %d warm-up, CUDA events' % (', torch autograd + torch.optim.Adam' if wl['train'] else '',
+                                                                      torch.__version__, steps, warmup))
+    return res
+
+
+def run_library(args, wl):
+    """`--impl library`: one JSON line with the stock-PyTorch-on-B200 numbers (rank 0 only)."""
+    import torch
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    lib = library_baseline(wl, dev, steps=min(args.steps, 5), warmup=max(min(args.warmup, 2), 1))
+    best = max((v for v in lib.values() if isinstance(v, dict) and 'value' in v), key=lambda v: v['value'], default=None)
+    line = {'impl': 'library', 'metric': METRIC, 'value': best['value'] if best else None, 'unit': 'slices/s', 'n_gpus': 1,
+            'ms_per_step': best['ms_per_step'] if best else None, 'higher_is_better': True, 'data': 'synthetic',
+            'dtype': 'fp32 tensors; cuDNN convs TF32 (torch default) or fp32',
+            'config': {'workload': wl['name'], 'ways': wl['ways'], 'shots': wl['shots'], 'batch_per_gpu': wl['batch'], 'size': wl['size'],
+                       'T': wl['T'], 'backbone': 'UNet'}, 'library_baseline': lib}
+    print(json.dumps(line), flush=True)
+
+
+def parity_field(sd, wl, dev, precision):
+    """1-2 slices of the workload's shape through the CPU oracle and through the B200 path (outside every timed region) with
+    the state_dict the timed run ended with: rel-Linf / margin error / argmax mismatch / Dice-vs-reference of the last
+    refinement iteration (rpnet_b200/parity.py)."""
+    import torch
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import parity
+    from rpnet_b200.nn.rp_net import RP_Net
+    from rpnet_b200.synthetic import make_episode, to_device
+    B = 1 if wl['ways'] > 1 else 2
+    cfg = model_cfg(wl['T'])
+    ep = make_episode(B, wl['ways'], wl['shots'], wl['size'], seed=4242)
+    net = RP_Net(pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    d = to_device(ep, dev)
+    a = (ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'])
+    T = wl['T']
+    if wl['train']:
+        from rpnet_b200.train import TrainStep
+        net.train()
+        ts = TrainStep(net)
+        loss = ts.forward_backward(d)
+        torch.cuda.synchronize()
+        got = ts.last['logits'][T - 1].cpu()
+        with torch.no_grad():
+            out = O.forward({k: v.clone() for k, v in sd.items()}, cfg, *a, training=True)
+        ref_loss = O.train_loss(out, ep['query_labels']).item()
+        r = parity.compare_logits(got, out['refinement'][T - 1])
+        r['loss'] = {'b200': loss.item(), 'oracle': ref_loss}
+    else:
+        net.eval()
+        with torch.no_grad():
+            got = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])['output'].cpu()
+            out = O.forward({k: v.clone() for k, v in sd.items()}, cfg, *a)
+        r = parity.compare_logits(got, out['output'])
+    tgt = ep['query_labels'] > 0
+    dice = lambda m: (2.0 * (m & tgt).sum().item() / max(m.sum().item() + tgt.sum().item(), 1))
+    r['dice_vs_ground_truth'] = {'b200': dice(parity.fg_mask(got)), 'oracle': dice(parity.fg_mask(out['refinement'][T - 1]))}
+    r['what'] = ('%d slice(s) of the workload shape (%s mode), last refinement iteration, B200 path (%s) vs the fp32 CPU oracle on the '
+                 'state_dict the timed run ended with' % (B, 'train' if wl['train'] else 'eval', precision))
+    r['tolerance'] = {'rel_linf': 1e-3, 'margin_rel_err': 1e-3}
+    return r
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of the current build
+    (profiles/r02_ncu_conv_igemm_traffic.json, written by tools/summarize_ncu.py).  None when no capture is committed."""
+    path = os.path.join(ROOT, 'profiles', 'r02_ncu_conv_igemm_traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------------- B200 arm
@@ -157,15 +323,19 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'library'])
     ap.add_argument('--workload', default=os.environ.get('RPNET_BENCH_WORKLOAD', 'train'), choices=sorted(WORKLOADS),
                     help="'train' = BASELINE.json configs[2], the configuration the metric is quoted on (default); 'infer' = configs[1]")
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-library-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true', help='inference workloads: launch every kernel from Python')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
         return run_reference(args, wl)
+    if args.impl == 'library':
+        return run_library(args, wl)
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -185,16 +355,21 @@ def main():
     if world > 1:
         dist.barrier()
 
-    from rpnet_b200 import ops
+    from rpnet_b200 import engine, ops
     from rpnet_b200.nn.rp_net import RP_Net
-    from rpnet_b200.synthetic import make_episode, perturb_bn_stats
+    from rpnet_b200.synthetic import fitted_state_dict, make_episode, to_device
 
     cfg = model_cfg(wl['T'])
     torch.manual_seed(0)                            # random-init weights of the reference architecture (test_rpnet.py:8-10)
     net = RP_Net(pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
-    if not wl['train']:
-        perturb_bn_stats(net.state_dict())          # eval: non-trivial running statistics, so that BN folding is exercised
     net = net.to(dev)
+    precision = engine.precision_of(cfg)
+    if not wl['train']:
+        # eval: BatchNorm running statistics fitted to the synthetic data (lr = 0: weights stay at their random initialisation), so
+        # that BN folding is exercised and the logits are not pinned at the 20 * cos cap (the parity field below means something)
+        net.load_state_dict(fitted_state_dict(net, lambda i: to_device(make_episode(2, wl['ways'], wl['shots'], wl['size'], seed=9000 + i), dev),
+                                              steps=30, lr=0.0))
+        net = net.to(dev)
     B = wl['batch']
     if wl.get('volume'):
         # one volume, this rank's contiguous slice range (strong scaling); a "step" = one pass over the rank's slices
@@ -345,18 +520,26 @@ def main():
     algo = fwd_algo * (2 if wl['train'] else 1)
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     achieved = algo / (conv_ms * 1e-3) / 1e12
+    # executed tensor-core FLOPs: the split-fp16 encoder forward runs three passes (hi.Wh + lo.Wh + hi.Wl) of its algorithmic FLOPs
+    enc_fwd = n_img * (E_FLOPS - FIRST_CONV_FLOPS) * scale
+    executed = algo + (2 * enc_fwd if precision == 'split' else 0)
+    burst_tf = peaks.get('bf16_tflops', 1590.0)
     roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (tcgen05 implicit GEMM: forward%s)' % (' + data-gradient convs' if wl['train'] else ''),
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured' if peaks else 'fallback 1400 TF/s, of fallback',
+                'frac_of_burst_peak': achieved / burst_tf,
                 'algorithmic_flops_per_step': algo, 'launches_per_step': kern['conv_igemm']['launches'], 'kernel_ms_per_step': conv_ms,
-                'executed_tflops': kern['conv_igemm']['work_per_step'] / (conv_ms * 1e-3) / 1e12,
+                'executed_flops_per_step': executed, 'executed_tflops': executed / (conv_ms * 1e-3) / 1e12,
+                'executed_frac': executed / (conv_ms * 1e-3) / 1e12 / peak_tf, 'executed_frac_of_burst_peak': executed / (conv_ms * 1e-3) / 1e12 / burst_tf,
+                'precision': precision + (': split-fp16 encoder forward = 3 tensor-core passes per algorithmic FLOP (fp32-class result); '
+                                          '`achieved` counts the algorithmic FLOPs once' if precision == 'split' else ''),
                 'kernel_share_of_step': conv_ms / (ms_total / args.steps)}
-    # DRAM traffic of the kernel from the committed `ncu --set full` capture (profiles/r01_ncu_conv_pair_uc4a.csv): one
-    # representative launch, Up_conv4.conv.0 forward at the cfg3 shape (96 x 64 x 64, 512 -> 256 channels), CTA-pair kernel
-    roofline['traffic'] = 405.076224e6 + 171.506176e6
-    roofline['traffic_launch'] = {'layer': 'Up_conv4.conv.0 forward, 96x64x64, 512->256', 'dram_bytes': 405.076224e6 + 171.506176e6,
-                                  'algorithmic_bytes': 96 * 64 * 64 * (512 + 256) * 2 + 9 * 512 * 256 * 2, 'duration_us': 558.7,
-                                  'tensor_pipe_active_pct': 97.2, 'source': 'profiles/r01_ncu_conv_pair_uc4a.csv'}
+    # DRAM traffic per launch of the kernel: `dram__bytes_read.sum + dram__bytes_write.sum` from the committed `ncu --set full`
+    # capture of the current build over the launches of one step (profiles/r02_ncu_conv_igemm_traffic.json)
+    tr = ncu_traffic()
+    if tr and tr.get('workload') == args.workload and tr.get('precision') == precision:
+        roofline['traffic'] = tr['dram_bytes_per_launch']
+        roofline['traffic_capture'] = {k: tr[k] for k in ('launches', 'dram_bytes_per_step', 'algorithmic_bytes_per_step', 'source') if k in tr}
     if graphed:
         roofline['note'] = 'kernel times from a second pass without CUDA-graph replay; value / ms_per_step from graph replay'
     if 'conv_wgrad' in kern:
@@ -372,17 +555,25 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # reported at N=1 only (rank 0's host cores)
-        sample = 2 if not wl['train'] else 1
-        val, ms, cores = cpu_reference(wl, 3, 1, sample)
+        sample = cpu_sample(wl)
+        val, ms, cores = cpu_reference(wl, 2, 1, sample)
         cpu = {'value': val, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
-               'sample': '3 steps x %d slices of the workload after 1 warm-up (oracle restatement of the reference CPU data '
+               'sample': '2 steps x %d slices of the workload after 1 warm-up (oracle restatement of the reference CPU data '
                          'flow incl. all-pairs correlation), %.0f ms/step' % (sample, ms)}
+    lib = None
+    if not args.no_library_baseline and world == 1 and not wl.get('volume'):
+        lib = library_baseline(wl, dev)
+    par = None
+    if not args.no_parity and world == 1:
+        par = parity_field({k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, wl, dev, precision)
 
     ms_step = ms_total / args.steps
     total_units = wl['slices'] if wl.get('volume') else world * B
     line = {'metric': METRIC, 'value': total_units / (ms_step * 1e-3), 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong' if wl.get('volume') else 'weak', 'vs_baseline': None,
-            'dtype': 'fp16 operands, fp32 accumulate (tensor-core convs); fp32 elsewhere', 'data': 'synthetic',
+            'dtype': ('split-fp16 (hi + lo planes, 3 tensor-core passes) encoder forward, fp16 cre convs' if precision == 'split' else 'fp16 forward operands')
+                     + '; fp32 accumulate; activations stored fp16 (hi [+ lo]), activation gradients bf16, dgrad / wgrad operands bf16, '
+                       'BatchNorm statistics fp64, parameters / weight gradients / Adam / losses fp32', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'ways': wl['ways'], 'shots': wl['shots'], 'batch_per_gpu': B,
                        'global_batch': total_units, 'size': wl['size'], 'T': wl['T'], 'backbone': 'UNet',
                        'parallelism': 'dp%d (slices sharded, no data-path collective%s)' % (
@@ -391,7 +582,8 @@ def main():
             'clocks': clk,
             'e2e': {'value': total_units / (ms_e2e / args.steps * 1e-3), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': stream_kernels}
+            'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'library_baseline': lib, 'parity': par,
+            'precision': precision, 'kernels': stream_kernels}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -320,14 +320,30 @@ def dice_ce(logits, true, eps=1e-7):
 # ----------------------------------------------------------------------------
 # the forward
 # ----------------------------------------------------------------------------
+def recurrent_mask(logits, cfg, scale=4):
+    """The mask update of net/rp_net.py:308-311 (generalised to Wa ways as in the module docstring): logits B x (1+Wa) x H x W ->
+    the pooled mask B x 1 x H/scale x W/scale that the next refinement iteration consumes."""
+    n_ways = logits.shape[1] - 1
+    prob = logits.softmax(dim=1)[:, 1:, ...].sum(dim=1) if n_ways > 1 else logits.softmax(dim=1)[:, 1, ...]
+    if cfg['soft_mask'] == False:  # noqa: E712  (same test as the reference)
+        prob = (prob > 0.5).float()
+    return F.avg_pool2d(prob.unsqueeze(1), scale)
+
+
 def forward(sd, cfg, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_labels,
-            training=False, align=True, backbone='UNet', allpairs=False, want=None):
+            training=False, align=True, backbone='UNet', allpairs=False, want=None, mask_override=None):
     """RP_Net.forward, net/rp_net.py:226-350, generalised to Wa x Sh (module docstring).
 
     sd   : state_dict (name -> tensor); BN buffers are updated in place when training.
     cfg  : the flat yaml dict (keys n_iter_refinement, mask_refinement_correlation_radius,
            soft_mask, optional scale) — net/rp_net.py:200-202, :48, :309.
     Returns {'output', 'align_loss', 'refinement'} like the reference.
+
+    mask_override (tests only): {i: pooled mask B x 1 x H' x W'} replaces the recurrent mask that iteration i >= 1 consumes
+    ("teacher forcing").  The hard mask (:310) makes iteration i+1 a discontinuous function of iteration i's logits: one
+    near-tie pixel that another implementation thresholds the other way changes the next iteration's input by 1/16 at one
+    feature pixel.  Feeding the oracle the masks the implementation under test derived from ITS logits compares every iteration
+    on identical inputs; the flipped pixels themselves are counted separately.
     """
     n_ways, n_shots = len(supp_imgs), len(supp_imgs[0])
     n_queries = len(qry_imgs)
@@ -381,13 +397,12 @@ def forward(sd, cfg, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_label
     refinement = {}
     inter = q_fts
     for i in range(T):                                                            # :280-312
+        if mask_override is not None and i in mask_override:
+            qry_mask = mask_override[i]
         inter = cre(q_fts[0] * qry_mask, q_fts[0] * (1 - qry_mask), sd, radius, 'cre.', training, allpairs,
                     want if (want is not None and i == 0) else None)[None]
         logits, _ = match(inter)
-        prob = logits.softmax(dim=1)[:, 1:, ...].sum(dim=1) if n_ways > 1 else logits.softmax(dim=1)[:, 1, ...]
-        if cfg['soft_mask'] == False:  # noqa: E712  (same test as the reference)
-            prob = (prob > 0.5).float()
-        qry_mask = F.avg_pool2d(prob.unsqueeze(1), scale)
+        qry_mask = recurrent_mask(logits, cfg, scale)
         refinement[i] = logits
 
     # :314-346 the final block recomputes the last iteration (D5) and the align loss

@@ -8,6 +8,10 @@ margins span most of [-40, 40].  Gates (rpnet_b200/parity.py), per refinement it
   margin_rel_err  <= 1e-3   error of the decision margin relative to the range of the margin
   argmax          no mismatch away from reference near-ties (|margin| <= 2e-3 * max |logit|), mismatch fraction <= 1e-4
   dice_vs_ref     >= 0.999  Dice(our foreground mask, the oracle's)
+Iterations i >= 1 are compared with the oracle consuming the recurrent masks derived from OUR logits of iteration i - 1
+(oracle.forward(mask_override=...)): the hard threshold (net/rp_net.py:310) makes the next iteration's input discontinuous in
+the logits, so a single near-tie pixel thresholded the other way would otherwise be compared through different inputs.  The
+flipped pixels themselves are bounded by the argmax gate of every iteration.
 Train-mode cases also check the loss (rel 1e-3) and per-parameter gradients of the head.
 The CPU oracle needs 5 - 60 s per case on the GPU box's host cores."""
 import pytest
@@ -57,6 +61,13 @@ def _gate(got, ref, what):
     return r
 
 
+def _overrides(logits, T):
+    """{i: pooled mask from OUR logits of iteration i - 1} for the oracle's teacher-forced run."""
+    from oracle import rpnet_oracle as O
+    cfg = _cfg(T)
+    return {i: O.recurrent_mask(logits[i - 1].float().cpu(), cfg) for i in range(1, T)}
+
+
 def _eval_case(dev, ways, shots, B, size, T, seed):
     from oracle import rpnet_oracle as O
     from rpnet_b200.synthetic import make_episode, to_device
@@ -66,9 +77,9 @@ def _eval_case(dev, ways, shots, B, size, T, seed):
     d = to_device(ep, dev)
     with torch.no_grad():
         out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
+        torch.cuda.synchronize()
         ref = O.forward({k: v.clone() for k, v in sd.items()}, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'],
-                        ep['appr_query_labels'])
-    torch.cuda.synchronize()
+                        ep['appr_query_labels'], mask_override=_overrides(out['refinement'], T))
     return [_gate(out['refinement'][i], ref['refinement'][i], 'refinement[%d]' % i) for i in range(T)]
 
 
@@ -96,9 +107,11 @@ def test_cfg5_volume_32_slices(dev):
                            [[mv(t) for t in way] for way in item['support_bg']], mv(item['query_images']), mv(item['appr_query_labels']),
                            batch_size=16, keep_logits=True)
     torch.cuda.synchronize()
+    import torch.nn.functional as F
+    over = {i: F.avg_pool2d(res['masks_per_iter'][i - 1].cpu().float().unsqueeze(1), 4) for i in range(1, T)}
     with torch.no_grad():
         ref = O.forward({k: v.clone() for k, v in sd.items()}, _cfg(T), item['support_images'], item['support_fg'], item['support_bg'],
-                        [item['query_images']], item['appr_query_labels'])
+                        [item['query_images']], item['appr_query_labels'], mask_override=over)
     _gate(res['logits'], ref['output'], 'volume output')
     ref_mask = (ref['output'][:, 1] > ref['output'][:, 0])
     assert (res['mask'].cpu().bool() != ref_mask).float().mean().item() <= 1e-4
@@ -127,16 +140,12 @@ def test_train_step_at_config_shapes(dev, ways, shots, B, T):
         if v.is_floating_point() and 'running' not in k:
             sd[k] = v.clone().requires_grad_(True)
             params[k] = sd[k]
-    out = O.forward(sd, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'], training=True)
+    out = O.forward(sd, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'], training=True,
+                    mask_override=_overrides(ts.last['logits'], T))
     ref_loss = O.train_loss(out, ep['query_labels'])
     ref_loss.backward()
-    agree = True
     for i in range(T):
-        if not agree:                     # a near-tie flip of the hard mask changes the next iteration's input (net/rp_net.py:310)
-            break
-        r = _gate(ts.last['logits'][i], out['refinement'][i].detach(), 'train refinement[%d]' % i)
-        agree = r['argmax_mismatch'] == 0.0
-    assert agree, 'hard masks diverged before the last iteration'
+        _gate(ts.last['logits'][i], out['refinement'][i].detach(), 'train refinement[%d]' % i)
     assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
     for name in ('cre.q.0.weight', 'cre.q.1.weight', 'cre.w_k.0.weight', 'cre.w_q.0.weight', 'encoder.Up_conv4.conv.3.weight'):
         g, rg = dict(net.named_parameters())[name].grad.float().cpu(), params[name].grad
