@@ -200,10 +200,11 @@ def correlation_allpairs(fmap1, fmap2, r=3):
     corr = torch.matmul(fmap1.reshape(b, c, h * w).transpose(1, 2), fmap2.reshape(b, c, h * w))
     corr = corr / torch.sqrt(torch.tensor(c).float())
     corr = corr.reshape(b * h * w, 1, h, w)
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing='ij')
+    dev = fmap1.device                                                   # (the reference builds these on fmap1.device too, :131,171)
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing='ij')
     centre = torch.stack([xs, ys], dim=-1).float()                       # (x, y) per pixel, :130-133
     centre = centre[None].repeat(b, 1, 1, 1).reshape(b * h * w, 1, 1, 2)
-    d = torch.linspace(-r, r, 2 * r + 1)
+    d = torch.linspace(-r, r, 2 * r + 1, device=dev)
     delta = torch.stack(torch.meshgrid(d, d, indexing='ij'), dim=-1)     # [a, b'] -> (d[a], d[b']) added to (x, y): D8
     coords = centre + delta.view(1, 2 * r + 1, 2 * r + 1, 2)
     gx = 2 * coords[..., 0:1] / (w - 1) - 1                               # :139-141

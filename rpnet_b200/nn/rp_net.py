@@ -205,10 +205,14 @@ class RP_Net(nn.Module):
         fore = torch.stack([torch.stack(way, dim=0) for way in fore_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
         back = torch.stack([torch.stack(way, dim=0) for way in back_mask], dim=0).float().reshape(n_supp, H, W).contiguous()
         appr = qmask_in.reshape(B, H, W).float().contiguous()
-        if getattr(self, '_use_graph', False):
-            logits = self._forward_eval_graphed(imgs, fore, back, appr, n_ways, n_shots, B)
-        else:
-            logits = self._forward_eval(imgs, fore, back, appr, n_ways, n_shots, B)
+        pdev = next(self.parameters()).device
+        if pdev != dev:
+            raise RuntimeError('RP_Net parameters are on %s but the inputs are on %s' % (pdev, dev))
+        with torch.cuda.device(dev):             # kernels launch on the current device's stream: make the model's device current
+            if getattr(self, '_use_graph', False):
+                logits = self._forward_eval_graphed(imgs, fore, back, appr, n_ways, n_shots, B)
+            else:
+                logits = self._forward_eval(imgs, fore, back, appr, n_ways, n_shots, B)
         refinement = {i: logits[i] for i in range(self.num_iter)}
         # the reference's final block recomputes the last iteration bit-for-bit (net/rp_net.py:314-346);
         # align_loss is 0 outside training (net/rp_net.py:340)
@@ -297,7 +301,8 @@ class RP_Net(nn.Module):
             raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only: move the model and inputs to the GPU')
         d = {'supp_imgs': supp_imgs, 'fore_mask': fore_mask, 'back_mask': back_mask, 'qry_imgs': qry_imgs,
              'appr_query_labels': appr_query_labels}
-        logits, align = train.train_forward(self, d)
+        with torch.cuda.device(qry_imgs[0].device):
+            logits, align = train.train_forward(self, d)
         T = logits.shape[0]
         return {'output': logits[T - 1], 'align_loss': align[0], 'refinement': {i: logits[i] for i in range(T)}}
 

@@ -51,6 +51,11 @@ def _req(t, dtype, name):
     if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
         raise _lib.RpnetError('%s must be a contiguous CUDA %s tensor (got %s %s contiguous=%s)'
                               % (name, dtype, t.device, t.dtype, t.is_contiguous()))
+    if t.device.index != torch.cuda.current_device():
+        # kernels, TMA descriptors and function attributes belong to the CURRENT device and launch on its current stream
+        raise _lib.RpnetError('%s lives on %s but the current CUDA device is cuda:%d: run the call under `with torch.cuda.device(%d):` '
+                              '(RP_Net.forward / TrainEngine / segment_volume do this for the model\'s device)'
+                              % (name, t.device, torch.cuda.current_device(), t.device.index))
     return t
 
 

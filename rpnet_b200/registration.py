@@ -92,3 +92,24 @@ def get_registration_field(query_images, support_images, support_labels, do_defo
     grid = compute_grid((h, w), dev)
     field = [[theta[i], grid] for i in range(n)]
     return field, reg_pred, warped_src, (aff_lab > 0.1).float(), aff_src[:, 0] * 2 - 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The two similarity measures test_rpnet.py imports from net.registration (:32) with the reference's signatures.
+# ---------------------------------------------------------------------------------------------------------------------
+def NCC(moving_image_valid, fixed_image_valid, mask=None):
+    """net/registration.py:157-160: minus the normalised cross-correlation of the two tensors (`mask` is ignored there too).
+    CUDA inputs go through rpnet_ncc_f32 (one fused reduction); the result is a 0-dim tensor like the reference's."""
+    m, f = moving_image_valid, fixed_image_valid
+    if not (m.is_cuda and f.is_cuda):
+        raise RuntimeError('rpnet_b200 runs on CUDA only: move the images to the GPU (test_rpnet.py:229-230 passes CUDA tensors)')
+    with torch.cuda.device(m.device):
+        return ops.ncc(m.float().contiguous(), f.float().contiguous().reshape(m.shape))[0]
+
+
+def MSE(y_pred, y_true, mask=None):
+    """net/registration.py:147-154 (plain tensor arithmetic: loss plumbing of the registration, not on the hot path)."""
+    value = torch.mean((y_true - y_pred) ** 2)
+    if mask is not None:
+        return torch.masked_select(value, mask).mean()
+    return value

@@ -595,6 +595,10 @@ class TrainStep:
 
     def forward_backward(self, d):
         """Loss + gradients (flat buffer / p.grad) without the optimizer: what loss.backward() leaves behind."""
+        with torch.cuda.device(self.eng.dev):      # kernels launch on the current device's stream
+            return self._forward_backward(d)
+
+    def _forward_backward(self, d):
         eng = self.eng
         eng.flat.alias_grads()
         eng.zero_grad()
@@ -614,7 +618,8 @@ class TrainStep:
         loss = self.forward_backward(d)
         self.t += 1
         f = self.eng.flat
-        ops.adam(f.param, f.grad, f.exp_avg, f.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.wd, 1.0 / self.world)
+        with torch.cuda.device(self.eng.dev):
+            ops.adam(f.param, f.grad, f.exp_avg, f.exp_avg_sq, self.t, self.lr, self.betas, self.eps, self.wd, 1.0 / self.world)
         engine.WEIGHTS_EPOCH += 1
         return loss
 
@@ -635,6 +640,11 @@ class _TrainForward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits, dalign):
         eng = ctx.eng
+        with torch.cuda.device(eng.dev):
+            return _TrainForward._backward(ctx, eng, dlogits, dalign)
+
+    @staticmethod
+    def _backward(ctx, eng, dlogits, dalign):
         if eng.saved is not ctx.token:
             raise RuntimeError('rpnet_b200: backward through a train-mode forward that is not the most recent one of this '
                                'model (activations are kept for one forward at a time)')

@@ -45,7 +45,16 @@ def segment_volume(net, support_images, support_fg, support_bg, query_images, ap
     masks, per_iter, logits = [], [[] for _ in range(T)], []
     for b0 in range(lo, hi, batch_size):
         b1 = min(b0 + batch_size, hi)
-        cut = lambda t: t[b0:b1].contiguous()
+        nb = b1 - b0
+        # the last partial batch is padded to `batch_size` by repeating its last slice (slices are independent in the eval
+        # forward): one batch shape per volume = one set of workspace buffers and one captured CUDA graph, whatever the slice count
+        pad = batch_size - nb if (hi - lo) > batch_size else 0
+
+        def cut(t):
+            c = t[b0:b1]
+            if pad:
+                c = torch.cat([c, c[-1:].expand(pad, *c.shape[1:])], dim=0)
+            return c.contiguous()
         out = net([[cut(t) for t in way] for way in support_images], [[cut(t) for t in way] for way in support_fg],
                   [[cut(t) for t in way] for way in support_bg], [cut(query_images)], appr_query_labels=cut(appr_query_labels))
 
@@ -54,11 +63,11 @@ def segment_volume(net, support_images, support_fg, support_bg, query_images, ap
                 return (lg[:, 1] > lg[:, 0]).to(torch.uint8)
             p = lg.softmax(dim=1)
             return (p[:, 1:].sum(1) > 0.5).to(torch.uint8)
-        masks.append(to_mask(out['output']))
+        masks.append(to_mask(out['output'][:nb]))
         for k in range(T):
-            per_iter[k].append(to_mask(out['refinement'][k]))
+            per_iter[k].append(to_mask(out['refinement'][k][:nb]))
         if keep_logits:
-            logits.append(out['output'].clone())
+            logits.append(out['output'][:nb].clone())
     res = {'range': (lo, hi), 'mask': torch.cat(masks) if masks else None,
            'masks_per_iter': [torch.cat(m) if m else None for m in per_iter]}
     if keep_logits:
