@@ -87,7 +87,10 @@ def main():
         ours = []
         evaluate.eval_volumes(net, items, config['eval_classes'], batch_size=16, out=ours.append)
     vol = re.compile(r'^\d+ \S+ \S+ affine \(')
-    ref_lines = [l.rstrip() for l in ref_out.splitlines() if vol.match(l) or l.startswith(tuple(c + ', affine' for c in config['eval_classes']))]
+    # per-volume lines (:231-242) and the per-class summary of eval() (:246-251, the one with 'voxel morph'); the closing
+    # "Average performance" block of main() (:128-141) averages over n_runs and is not part of the loop being compared
+    ref_lines = [l.rstrip() for l in ref_out.splitlines() if vol.match(l) or (l.startswith(tuple(c + ', affine' for c in config['eval_classes']))
+                                                                               and 'voxel morph' in l)]
     our_lines = [l.rstrip() for l in ours]
     same = ref_lines == our_lines
     with open(args.log, 'a') as f:
