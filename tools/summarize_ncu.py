@@ -42,7 +42,10 @@ def traffic(rep, meta_json, dst, pattern='conv_igemm'):
     """Per-launch DRAM traffic of the dominant kernel over the launches of ONE step (an `ncu --set full` capture of
     tools/ncu_one_step.py) -> the JSON bench.py reads for `roofline.traffic`."""
     import json
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):                       # `ncu -i x.ncu-rep --page raw --csv` already exported on the GPU box
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[0]
     ki, ri, wi, ti = (hdr.index(k) for k in ('Kernel Name', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum'))
