@@ -118,6 +118,9 @@ int rpnet_bn_apply_split_f16(const void* z_hi, const void* z_lo, const float* st
 int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
                                  void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream);
 int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream);
+/* rpnet_maxpool_f16 on a split-fp16 activation: the maximum of hi + lo, written back as hi / lo planes (VGG pools between split convs). */
+int rpnet_maxpool_split_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int n, int h, int w, int c, int k,
+                            int stride, int pad, void* stream);
 
 /* F.avg_pool2d(mask[:, None], s): fp32 [n][h][w] -> fp32 [n][h/s][w/s].  net/rp_net.py:270,272. */
 int rpnet_avgpool_mask_f32(const float* in, float* out, int n, int h, int w, int s, void* stream);
@@ -361,6 +364,24 @@ int rpnet_affine_warp_f32(const float* x, const float* theta, float* out, int n,
 /* NCC (net/registration.py:157-160; printed by the eval driver, test_rpnet.py:229-230) of two fp32 arrays of n elements:
  * -cov(f, m) / sqrt(var(f) * var(m) * n^2 ... + 1e-10) exactly as the reference's sums; scratch5: 5 doubles; out: 1 float. */
 int rpnet_ncc_f32(const float* moving, const float* fixed, long long n, double* scratch5, float* out, void* stream);
+
+/* Deformable half of get_registration_field (`do_deformable: True`, dataset/few_shot_reader.py:137-170): DemonsRegistration with
+ * Diffeomorphic(10) — exp(flow) by scaling and squaring —, the NCC loss, torch.optim.Adam(lr) on the flow and the Gaussian
+ * regulariser after every step (net/registration.py:16-160, 190-313), for ALL slices in one launch (one CTA per slice runs every
+ * iteration: forward chain, NCC reduction, hand-derived backward, Adam, smoothing).
+ *   moving (already affinely warped), fixed: fp32 [n][h][w] in [0, 1];  gauss_host: HOST array [gauss_h][gauss_w] = the regulariser's
+ *   kernel (net/registration.py:16-51; 9 x 9 for sigma 2), odd sides up to 15;  scaling: number of compositions (10).
+ *   flow [n][2][h][w] (out): the trained DemonsRegistration.flow (channel 0 = x, normalised units);  disp [n][2][h][w] (out):
+ *   exp(flow), the displacement DemonsRegistration.forward adds to the identity grid;  loss_curve [n][iters] (optional).
+ *   workspace: rpnet_demons_workspace_bytes(n, h, w, scaling) bytes.
+ * rpnet_demons_warp_f32: DemonsRegistration.forward (:244-258) with that displacement: out = grid_sample(x, grid + disp), x / out
+ *   fp32 [n][c][h][w], torch's grid_sample defaults (bilinear, zeros, align_corners=False) on the corner-aligned compute_grid. */
+long long rpnet_demons_workspace_bytes(int n, int h, int w, int scaling);
+int rpnet_demons_register_f32(const float* moving, const float* fixed, int n, int h, int w, int iters, float lr, float beta1,
+                              float beta2, float eps, int scaling, const float* gauss_host, int gauss_h, int gauss_w,
+                              float* flow, float* disp, float* loss_curve, void* workspace, long long workspace_bytes,
+                              void* stream);
+int rpnet_demons_warp_f32(const float* x, const float* disp, float* out, int n, int c, int h, int w, void* stream);
 
 #ifdef __cplusplus
 }

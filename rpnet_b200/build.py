@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'librpnet_sm100.so')
-SOURCES = ['conv_igemm.cu', 'conv_wgrad.cu', 'local_corr_tc.cu', 'stream_kernels.cu', 'train_kernels.cu', 'tail_kernels.cu']
+SOURCES = ['conv_igemm.cu', 'conv_wgrad.cu', 'local_corr_tc.cu', 'stream_kernels.cu', 'train_kernels.cu', 'tail_kernels.cu', 'demons.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '-Xptxas', '-v']
 

@@ -585,8 +585,8 @@ upsample_tail_kernel(const float* __restrict__ pred, float* __restrict__ logits,
 // nn.MaxPool2d(k, stride, padding) with implicit -inf padding on fp16 NHWC (VGG: k3 s2 p1 and k3 s1 p1,
 // net/vgg.py:24-30).  One thread per output pixel x 8 channels.
 // ---------------------------------------------------------------------------------------------------
-__global__ void maxpool_f16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H, int W, int c8, int Ho,
-                                   int Wo, int k, int stride, int pad) {
+__global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, uint4* __restrict__ out,
+                                   uint4* __restrict__ out_lo, int N, int H, int W, int c8, int Ho, int Wo, int k, int stride, int pad) {
   const long long total = (long long)N * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % c8);
@@ -603,11 +603,19 @@ __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, uint4* __restri
         if (x < 0 || x >= W) continue;
         float v[8];
         unpack8(__ldg(in + ((long long)(n * H + y) * W + x) * c8 + cv), v);
+        if (in_lo) {                              // split-fp16: the value is hi + lo (exact in fp32)
+          float l[8];
+          unpack8(__ldg(in_lo + ((long long)(n * H + y) * W + x) * c8 + cv), l);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += l[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], v[j]);
       }
     }
-    out[i] = pack8(best);
+    const uint4 hi = pack8(best);
+    out[i] = hi;
+    if (out_lo) out_lo[i] = residual8_f16(best, hi);
   }
 }
 
@@ -798,14 +806,24 @@ RPNET_API int rpnet_upsample_tail_f32(const float* pred, float* logits, float* m
   return check_cuda(cudaGetLastError(), "upsample_tail launch");
 }
 
+RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
+                                       int stride, int pad, void* stream_);
+
 RPNET_API int rpnet_maxpool_f16(const void* in, void* out, int n, int h, int w, int c, int k, int stride, int pad, void* stream_) {
+  return rpnet_maxpool_split_f16(in, nullptr, out, nullptr, n, h, w, c, k, stride, pad, stream_);
+}
+
+RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
+                                       int stride, int pad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(in && out, "maxpool: null pointer argument");
+  RPNET_REQUIRE((in_lo == nullptr) == (out_lo == nullptr), "maxpool: residual planes go in and out together");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
   RPNET_REQUIRE(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k, "maxpool: bad window k=%d stride=%d pad=%d", k, stride, pad);
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
-  maxpool_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w,
-                                                                c / 8, ho, wo, k, stride, pad);
+  maxpool_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<const uint4*>(in_lo),
+                                                                static_cast<uint4*>(out), static_cast<uint4*>(out_lo), n, h, w, c / 8, ho,
+                                                                wo, k, stride, pad);
   return check_cuda(cudaGetLastError(), "maxpool launch");
 }

@@ -17,7 +17,7 @@ registration outputs stay on the device (`.cuda()` in the caller is then a no-op
 
 `mode='train'` is not built: its augmentation calls `transforms.RandomAffine(..., fillcolor=None)` (:30-31), a keyword
 torchvision removed, so the reference's own train branch cannot run against the torchvision of this image and there is
-nothing to pin it to.  `do_deformable: True` raises NotImplementedError (rpnet_b200/registration.py)."""
+nothing to pin it to.  `do_deformable: True` runs the one-launch demons registration (rpnet_b200/registration.py)."""
 import csv
 import math
 import os
@@ -246,7 +246,7 @@ class FewshotRegReader(torch.utils.data.Dataset):
         data = self.fewshot_reader[idx]
         if data['registration_field'] is None:
             raise TypeError("FewshotRegReader needs config['use_registration_loss'] = True")
-        grids = torch.cat([g for _, g in data['registration_field']], dim=0)
+        grids = torch.cat([f[1] for f in data['registration_field']], dim=0)
         return {'support_images': [[data['affine_warped_supp'].unsqueeze(1)]],
                 'support_labels': [[data['affine_warped_supp_label'][:, 0]]],
                 'query_images': data['query_images'][:, [0]], 'query_labels': data['query_labels'],

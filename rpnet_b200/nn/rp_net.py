@@ -151,6 +151,7 @@ class RP_Net(nn.Module):
 
         if self.config['backbone'] == 'vgg':
             self.encoder = Encoder(in_channels, self.pretrained_path)
+            self.encoder.split = engine.precision_of(backbone_cfg) == 'split'
             num_feat = 512
         elif self.config['backbone'] == 'UNet':
             self.encoder = U_Net(backbone_cfg)
@@ -173,7 +174,7 @@ class RP_Net(nn.Module):
         if self.config['backbone'] in ('vgg', 'resnet'):
             if imgs.shape[1] == 1:
                 imgs = imgs.expand(-1, 3, -1, -1)                      # net/rp_net.py:246-247
-            return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)
+            return engine.hi_of(self.encoder.encode_nhwc(imgs.float().contiguous(), tag))
         return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)
 
     def forward(self, supp_imgs, fore_mask, back_mask, qry_imgs, registration_field=None, grid=None, query_labels=None,

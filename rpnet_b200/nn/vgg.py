@@ -25,6 +25,9 @@ class Encoder(_PackedModule):
         )
         self._init_weights()
         self._ws = engine.Workspace()
+        # arithmetic of the 12 tensor-core convs: 'split' (fp32-class, default) or 'fp16' — engine.PRECISIONS; the reference's
+        # constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False`
+        self.split = engine.default_precision() == 'split'
 
     def _make_layer(self, n_convs, in_channels, out_channels, dilation=1, lastRelu=True):
         layer = []
@@ -62,8 +65,8 @@ class Encoder(_PackedModule):
                         plan.append(('first', m, None, relu))
                     else:
                         scale, shift = engine.fold_bn(m.bias)
-                        wp, taps = engine.pack_weight_taps(m.weight, m.dilation[0])
-                        plan.append(('conv', m, engine.ConvPack(wp, taps, scale, shift, relu), relu))
+                        wp, taps = engine.pack_weight_taps(m.weight, m.dilation[0], split=self.split)
+                        plan.append(('conv', m, engine.ConvPack(wp, taps, scale, shift, relu, split=self.split), relu))
         return plan
 
     def encode_nhwc(self, x, tag='vgg'):
@@ -77,16 +80,24 @@ class Encoder(_PackedModule):
                 scale, shift = engine.fold_bn(conv.bias)
                 n, _, h, w = x.shape
                 cur = ws.get(name, (n, h, w, 64), torch.float16, x.device)
-                ops.conv3x3_first(x.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, step[3], cur)
+                lo = ws.get(name + '.lo', (n, h, w, 64), torch.float16, x.device) if self.split else None
+                ops.conv3x3_first(x.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, step[3], cur, out_lo=lo)
+                cur = (cur, lo) if self.split else cur
             elif step[0] == 'conv':
                 cur, _ = engine.run_conv(step[2], cur, ws, name)
             else:
                 _, k, s, p = step
-                n, h, w, c = cur.shape
-                out = ws.get(name, (n, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1, c), torch.float16, cur.device)
-                ops.maxpool(cur, k, s, p, out)
-                cur = out
+                n, h, w, c = engine.hi_of(cur).shape
+                shp = (n, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1, c)
+                out = ws.get(name, shp, torch.float16, x.device)
+                if self.split:
+                    out_lo = ws.get(name + '.lo', shp, torch.float16, x.device)
+                    ops.maxpool(cur[0], k, s, p, out, x_lo=cur[1], out_lo=out_lo)
+                    cur = (out, out_lo)
+                else:
+                    ops.maxpool(cur, k, s, p, out)
+                    cur = out
         return cur
 
     def forward(self, x, mask=None):
-        return engine.nhwc_to_nchw_f32(self.encode_nhwc(x))
+        return engine.nhwc_to_nchw_f32(self.encode_nhwc(x))      # split mode: hi + lo planes joined in fp32

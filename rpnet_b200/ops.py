@@ -280,14 +280,19 @@ def upsample_tail(pred, logits, mask_out, scale, soft_mask):
                                                _stream()), 'rpnet_upsample_tail_f32')
 
 
-def maxpool(x, k, stride, pad, out):
+def maxpool(x, k, stride, pad, out, x_lo=None, out_lo=None):
+    """x_lo / out_lo: residual planes of a split-fp16 activation (max of hi + lo, re-split)."""
     lib = _lib.load()
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
     n, h, w, c = x.shape
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
-    assert tuple(out.shape) == (n, ho, wo, c)
-    with _Timed('maxpool', float(x.numel() * 2 + out.numel() * 2)):
-        _lib.check(lib.rpnet_maxpool_f16(_ptr(x), _ptr(out), n, h, w, c, k, stride, pad, _stream()), 'rpnet_maxpool_f16')
+    assert tuple(out.shape) == (n, ho, wo, c) and (x_lo is None) == (out_lo is None)
+    if x_lo is not None:
+        _req(x_lo, torch.float16, 'x_lo'); _req(out_lo, torch.float16, 'out_lo')
+        assert x_lo.shape == x.shape and out_lo.shape == out.shape
+    with _Timed('maxpool', float((x.numel() * 2 + out.numel() * 2) * (1 if x_lo is None else 2))):
+        _lib.check(lib.rpnet_maxpool_split_f16(_ptr(x), _ptr(x_lo), _ptr(out), _ptr(out_lo), n, h, w, c, k, stride, pad, _stream()),
+                   'rpnet_maxpool_split_f16')
     
 
 # =====================================================================================================
@@ -820,3 +825,41 @@ def conv7x7s2_stem(img, weight, scale, shift, out, relu=True):
     with _Timed('conv7x7s2_stem', float(img.numel() * 4 + out.numel() * 2)):
         _lib.check(lib.rpnet_conv7x7s2_stem_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out),
                                                 _stream()), 'rpnet_conv7x7s2_stem_f16')
+
+
+# =====================================================================================================
+# "next" row N1, deformable half: batched demons registration (include/rpnet_b200.h, last section)
+# =====================================================================================================
+def demons_register(moving, fixed, gauss, iters=50, lr=0.01, betas=(0.9, 0.999), eps=1e-8, scaling=10, loss_curve=None):
+    """moving / fixed fp32 [n, h, w] in [0, 1]; gauss: CPU fp32 tensor [kh, kw] (the regulariser's kernel).
+    Returns (flow [n, 2, h, w], disp = exp(flow) [n, 2, h, w])."""
+    lib = _lib.load()
+    _req(moving, torch.float32, 'moving'); _req(fixed, torch.float32, 'fixed')
+    n, h, w = moving.shape
+    assert fixed.shape == moving.shape and gauss.dim() == 2 and not gauss.is_cuda
+    flow = torch.empty(n, 2, h, w, dtype=torch.float32, device=moving.device)
+    disp = torch.empty_like(flow)
+    if loss_curve is not None:
+        _req(loss_curve, torch.float32, 'loss_curve')
+        assert tuple(loss_curve.shape) == (n, iters)
+    nb = int(lib.rpnet_demons_workspace_bytes(n, h, w, scaling))
+    if nb < 0:
+        _lib.check(nb, 'rpnet_demons_workspace_bytes')
+    ws = torch.empty(nb // 4, dtype=torch.float32, device=moving.device)
+    g = gauss.float().contiguous()
+    garr = (ctypes.c_float * g.numel())(*g.flatten().tolist())
+    with _Timed('demons_register', float(moving.numel() * 4 * 60 * max(iters, 1))):
+        _lib.check(lib.rpnet_demons_register_f32(_ptr(moving), _ptr(fixed), n, h, w, int(iters), float(lr), float(betas[0]), float(betas[1]),
+                                                 float(eps), int(scaling), ctypes.cast(garr, ctypes.c_void_p), g.shape[0], g.shape[1],
+                                                 _ptr(flow), _ptr(disp), _ptr(loss_curve), _ptr(ws), nb, _stream()), 'rpnet_demons_register_f32')
+    return flow, disp
+
+
+def demons_warp(x, disp, out):
+    """x, out fp32 [n, c, h, w]; disp fp32 [n, 2, h, w]: F.grid_sample(x, compute_grid + disp) (DemonsRegistration.forward)."""
+    lib = _lib.load()
+    _req(x, torch.float32, 'x'); _req(disp, torch.float32, 'disp'); _req(out, torch.float32, 'out')
+    n, c, h, w = x.shape
+    assert out.shape == x.shape and tuple(disp.shape) == (n, 2, h, w)
+    with _Timed('demons_warp', float(x.numel() * 8 + disp.numel() * 4)):
+        _lib.check(lib.rpnet_demons_warp_f32(_ptr(x), _ptr(disp), _ptr(out), n, c, h, w, _stream()), 'rpnet_demons_warp_f32')

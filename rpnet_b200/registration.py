@@ -5,10 +5,11 @@ The reference registers one slice at a time inside `Dataset.__getitem__`: per sl
 tiny launches (affine_grid, grid_sample, MSE, backward, Adam).  Here all slices of a volume are registered by ONE kernel
 launch (one CTA per slice runs all iterations, ops.affine_register) and warped by one more (ops.affine_warp).
 
-The deformable refinement (DemonsRegistration, net/registration.py:221-313: dense flow field + NCC + scaling-and-squaring)
-is not built: this module reproduces the `do_deformable: False` behaviour (yamls/example.yml), in which the demons stage runs
-zero iterations but is still *applied* — with a zero flow it resamples by n/(n-1) (`demons_identity_theta`), which is what
-separates `warped_supp_label` / `appr_query_labels` from the affine outputs."""
+The deformable refinement (DemonsRegistration, net/registration.py:221-313: dense flow field + NCC + scaling-and-squaring +
+Gaussian regulariser) is one more launch for all slices (ops.demons_register: one CTA per slice runs the 50 iterations).  With
+`do_deformable: False` (yamls/example.yml) the demons stage runs zero iterations but is still *applied* — with a zero flow it
+resamples by n/(n-1) (`demons_identity_theta`), which is what separates `warped_supp_label` / `appr_query_labels` from the
+affine outputs."""
 import torch
 
 from . import ops
@@ -67,8 +68,41 @@ def demons_identity_theta(n, h, w, device):
     return t
 
 
+def gaussian_kernel_2d(sigma=(2, 2)):
+    """The regulariser's kernel (net/registration.py:16-51): per axis size 2 * ceil(2 sigma) + 1 over linspace(-(size-1)//2, (size-1)//2),
+    each 1-D factor and the outer product normalised to sum 1.  CPU fp32 tensor [ky, kx]."""
+    import numpy as np
+
+    def k1(s):
+        size = int(2 * np.ceil(s * 2) + 1)
+        x = np.linspace(-(size - 1) // 2, (size - 1) // 2, num=size)
+        k = 1.0 / (s * np.sqrt(2 * np.pi)) * np.exp(-(x ** 2) / (2 * s ** 2))
+        return k / np.sum(k)
+    k = np.tensordot(k1(sigma[0]), k1(sigma[1]), 0)
+    return torch.tensor(k / np.sum(k), dtype=torch.float32)
+
+
+def demons_register(moving, fixed, iters=50, lr=0.01, sigma=(2, 2), return_loss=False):
+    """DemonsRegistration(use_diffeomorphic=True).train_registraion as get_registration_field drives it (few_shot_reader.py:137-163:
+    NCC loss, Adam(lr 0.01), GaussianRegulariser(sigma 2)) for a batch of slices: moving (affinely warped already), fixed
+    [n, h, w] or [n, 1, h, w] CUDA fp32 in [0, 1] -> (flow [n, 2, h, w], disp = exp(flow) [n, 2, h, w])."""
+    m = moving.reshape(moving.shape[0], moving.shape[-2], moving.shape[-1]).float().contiguous()
+    f = fixed.reshape(m.shape).float().contiguous()
+    curve = torch.empty(m.shape[0], iters, dtype=torch.float32, device=m.device) if return_loss else None
+    flow, disp = ops.demons_register(m, f, gaussian_kernel_2d(sigma), iters=iters, lr=lr, loss_curve=curve)
+    return (flow, disp, curve) if return_loss else (flow, disp)
+
+
+def demons_warp(x, disp):
+    """DemonsRegistration.forward (net/registration.py:244-258) for a batch: x [n, c, h, w], disp = exp(flow) [n, 2, h, w]."""
+    x = x.float().contiguous()
+    out = torch.empty_like(x)
+    ops.demons_warp(x, disp.contiguous(), out)
+    return out
+
+
 def get_registration_field(query_images, support_images, support_labels, do_deformable=True):
-    """get_registration_field (dataset/few_shot_reader.py:109-198) for `do_deformable: False`, all slices in one launch.
+    """get_registration_field (dataset/few_shot_reader.py:109-198), all slices in one launch per stage.
     Same return order as the reference:
       registration_field        list of [theta_i [2, 3], grid [1, 2, H, W]] per slice (the reference keeps its nn.Module there;
                                 RP_Net.forward ignores the argument, net/rp_net.py:226)
@@ -77,20 +111,25 @@ def get_registration_field(query_images, support_images, support_labels, do_defo
       py_affine_reg_pred        [S, 1, H, W] {0, 1}: affine(label) > 0.1 (:171-173)
       affine_warped_src_list    [S, H, W] in [-1, 1] (:178-179, :196)
     The inputs may live on the host; the outputs stay on the CUDA device."""
-    if do_deformable:
-        raise NotImplementedError('the deformable (demons) refinement is not built: set do_deformable: False (yamls/example.yml)')
     dev = torch.device('cuda', torch.cuda.current_device())
     src = (support_images[0][0][:, 0].to(dev, torch.float32) + 1) / 2.0
     dst = (query_images[:, 0].to(dev, torch.float32) + 1) / 2.0
     lab = support_labels[0][0].to(dev, torch.float32)[:, None]
     n, h, w = src.shape
     theta = affine_register(src, dst, iters=50, lr=0.01)
-    zoom = demons_identity_theta(n, h, w, dev)
     aff_lab, aff_src = affine_warp(lab, theta), affine_warp(src[:, None], theta)
-    reg_pred = (affine_warp(aff_lab, zoom) > 0.1).float()
-    warped_src = affine_warp(aff_src, zoom)[:, 0] * 2 - 1
     grid = compute_grid((h, w), dev)
-    field = [[theta[i], grid] for i in range(n)]
+    if do_deformable:
+        # :137-163 — 50 demons iterations on the affinely warped source; the trained module is then applied to label and source
+        flow, disp = demons_register(aff_src[:, 0], dst, iters=50, lr=0.01)
+        reg_pred = (demons_warp(aff_lab, disp) > 0.1).float()
+        warped_src = demons_warp(aff_src, disp)[:, 0] * 2 - 1
+        field = [[theta[i], grid, flow[i]] for i in range(n)]
+    else:
+        zoom = demons_identity_theta(n, h, w, dev)
+        reg_pred = (affine_warp(aff_lab, zoom) > 0.1).float()
+        warped_src = affine_warp(aff_src, zoom)[:, 0] * 2 - 1
+        field = [[theta[i], grid] for i in range(n)]
     return field, reg_pred, warped_src, (aff_lab > 0.1).float(), aff_src[:, 0] * 2 - 1
 
 

@@ -128,9 +128,9 @@ def test_vgg_encoder_vs_reference_golden(dev, golden):
     with torch.no_grad():
         y = enc(x.to(dev).contiguous()).cpu()
     ref = torch.from_numpy(g['out'])
-    # 13 stacked fp16-operand convs without normalisation: 1e-2 of the output scale
+    # split-fp16 convs (fp32-class): north_star's 1e-3 of the output scale holds for the standalone encoder too
     err = ((y - ref).abs().max() / ref.abs().max()).item()
-    assert y.shape == ref.shape and err < 1e-2, err
+    assert y.shape == ref.shape and err < 1e-3, err
 
 
 def test_vgg_backbone_through_rpnet(dev):

@@ -104,3 +104,63 @@ def test_demons_oracle_vs_reference_golden():
     np.testing.assert_allclose(warped[0, 0].numpy(), g['warped'], atol=2e-3)
     ref_wl = np.unpackbits(g['warped_label'])[:size * size].reshape(size, size)
     assert (wl[0, 0].numpy().astype(np.uint8) != ref_wl).mean() < 2e-3
+
+
+@pytest.mark.gpu
+def test_demons_kernel_vs_reference_golden():
+    """The one-launch demons registration (rpnet_demons_register_f32: exp(flow) by scaling and squaring, NCC, hand-derived
+    backward, Adam, Gaussian smoothing — net/registration.py:190-313 driven as in few_shot_reader.py:137-170) against the flow,
+    the warped image and the warped label recorded from the UNMODIFIED reference classes (tests/golden/demons.npz).  Same
+    tolerances as the oracle's own pin: tight half-way through the descent, 1 % of the flow scale at the end."""
+    import os
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import registration as RG
+    from rpnet_b200.synthetic import _slice
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'demons.npz'))
+    size, iters = int(g['size']), int(g['iters'])
+    dev = torch.device('cuda:0')
+    np.testing.assert_allclose(RG.gaussian_kernel_2d((2, 2)).numpy(), g['kernel'], rtol=0, atol=1e-9)
+    src = _slice(300, size, 1)[0]
+    lab = (_slice(300, size, 1)[1] > 0).float()
+    src01, dst01 = ((src + 1) / 2)[None].to(dev), ((torch.from_numpy(g['dst']) + 1) / 2)[None].to(dev)
+    theta = torch.from_numpy(g['theta']).to(dev)
+    affined = RG.affine_warp(src01[:, None], theta)                      # the affine stage is pinned in test_affine_* above
+    np.testing.assert_allclose(affined[0, 0].cpu().numpy(), g['affined'], atol=1e-5)
+    flow_half, _ = RG.demons_register(affined[:, 0], dst01, iters=iters // 2)
+    np.testing.assert_allclose(flow_half.cpu().numpy(), g['flow_half'], rtol=0, atol=5e-6)
+    flow, disp, curve = RG.demons_register(affined[:, 0], dst01, iters=iters, return_loss=True)
+    torch.cuda.synchronize()
+    assert curve[0, -1] < curve[0, 0]                                      # NCC improves
+    assert np.abs(flow.cpu().numpy() - g['flow']).max() < 0.01 * np.abs(g['flow']).max()
+    warped = RG.demons_warp(affined, disp)
+    np.testing.assert_allclose(warped[0, 0].cpu().numpy(), g['warped'], atol=2e-3)
+    wl = (RG.demons_warp(RG.affine_warp(lab[None, None].to(dev), theta), disp) > 0.1).float()
+    ref_wl = np.unpackbits(g['warped_label'])[:size * size].reshape(size, size)
+    assert (wl[0, 0].cpu().numpy().astype(np.uint8) != ref_wl).mean() < 2e-3
+    # zero iterations == the untrained module: a pure n / (n - 1) resampling (do_deformable: False, demons_identity_theta)
+    f0, d0 = RG.demons_register(affined[:, 0], dst01, iters=0)
+    assert float(f0.abs().max()) == 0.0 and float(d0.abs().max()) == 0.0
+    z = RG.affine_warp(affined, RG.demons_identity_theta(1, size, size, dev))
+    np.testing.assert_allclose(RG.demons_warp(affined, d0).cpu().numpy(), z.cpu().numpy(), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_demons_batch_vs_oracle_rectangular():
+    """Slices are independent (batch == per-slice results) and non-square images work: three 40 x 56 slices against the CPU
+    oracle (oracle/registration_oracle.py:demons_register) after 12 iterations."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from oracle import registration_oracle as R
+    from rpnet_b200 import registration as RG
+    gen = torch.Generator().manual_seed(5)
+    h, w, n, iters = 40, 56, 3, 12
+    base = torch.rand(n, 1, h // 4, w // 4, generator=gen)
+    mov = torch.nn.functional.interpolate(base, size=(h, w), mode='bilinear', align_corners=False)[:, 0]
+    fix = torch.roll(mov, shifts=(1, -2), dims=(1, 2)) * 0.95 + 0.02
+    flow, disp = RG.demons_register(mov.cuda(), fix.cuda(), iters=iters)
+    for s in range(n):
+        ref, _ = R.demons_register(mov[s][None, None], fix[s][None, None], iters)
+        assert (flow[s].cpu() - ref[0]).abs().max().item() < 2e-5 + 1e-3 * ref.abs().max().item(), s
+        one, _ = RG.demons_register(mov[s:s + 1].cuda(), fix[s:s + 1].cuda(), iters=iters)
+        assert (one[0] - flow[s]).abs().max().item() < 1e-6          # float atomics in the scatter: not bit-exact run to run
