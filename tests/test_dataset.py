@@ -128,8 +128,30 @@ def test_reg_reader_requires_registration_and_eval_mode(tmp_path):
     ds = FewshotRegReader(data_dir, set_name, dict(cfg, use_registration_loss=False), mode='eval')
     with pytest.raises(TypeError):
         ds[0]
-    with pytest.raises(NotImplementedError):                          # the deformable half is not built
-        FewshotRegReader(data_dir, set_name, dict(cfg, do_deformable=True), mode='eval')[0]
+
+
+@pytest.mark.gpu
+def test_reg_reader_deformable_item(tmp_path):
+    """`do_deformable: True` (the default of get_registration_field, dataset/few_shot_reader.py:109): same item contract, the demons
+    stage moves the warped support towards the query (NCC improves over the affine-only warp) and the fields carry the flow."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from rpnet_b200 import ops
+    data_dir, set_name, cfg = make_synthetic_dataset(str(tmp_path), n_patients=2)
+    random.seed(1)
+    a = FewshotRegReader(data_dir, set_name, dict(cfg, do_deformable=False), mode='eval')[0]
+    random.seed(1)
+    d = FewshotRegReader(data_dir, set_name, dict(cfg, do_deformable=True), mode='eval')[0]
+    assert set(a.keys()) == set(d.keys())
+    for k in ('support_images', 'support_labels'):
+        assert d[k][0][0].shape == a[k][0][0].shape
+    assert d['warped_supp'].shape == a['warped_supp'].shape and d['appr_query_labels'].shape == a['appr_query_labels'].shape
+    assert len(d['registration_field'][0]) == 3 and d['registration_field'][0][2].shape[0] == 2          # [theta, grid, flow]
+    q = d['query_images'].float().cuda().contiguous()
+    ncc = lambda w: ops.ncc(q, w.float().cuda().reshape(q.shape).contiguous()).item()
+    assert ncc(d['warped_supp']) < ncc(a['warped_supp'])                                                   # NCC is negated: lower is better
+    assert set(torch.unique(d['appr_query_labels']).tolist()) <= {0.0, 1.0}
 
 
 @pytest.mark.gpu
