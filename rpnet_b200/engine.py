@@ -36,6 +36,18 @@ def precision_of(cfg):
     return p
 
 
+def decoder_precision(p):
+    """Arithmetic of the decoder half of the U-Net (Up5, Up_conv5, Up4, Up_conv4 — 59 % of the encoder FLOPs) under precision
+    `p`.  In 'split' mode these layers keep the split ACTIVATIONS (hi + lo planes in and out) but use plain fp16 weights: two
+    tensor-core passes (hi.W + lo.W) instead of three.  Their weight rounding moves the logits by ~1.5e-4 (measured)
+    because every later stage averages it over thousands of terms, whereas the same rounding in Conv1-Conv5 costs 1e-3.
+    RPNET_SPLIT_DECODER=3 restores the full three-term product there."""
+    import os
+    if p != 'split':
+        return p
+    return 'split' if os.environ.get('RPNET_SPLIT_DECODER', '2') == '3' else 'split-a'
+
+
 class Workspace:
     """Named, shape-keyed persistent device buffers (stable pointers: CUDA-graph friendly)."""
 
@@ -56,11 +68,13 @@ class Workspace:
 
 class ConvPack:
     """One tap-list conv ready for rpnet_conv_igemm_f16 (split: rpnet_conv_split_f16, wpack = Wh | Wl along cin)."""
-    __slots__ = ('wpack', 'taps', 'scale', 'shift', 'relu', 'cout', 'cin', 'split')
+    __slots__ = ('wpack', 'taps', 'scale', 'shift', 'relu', 'cout', 'cin', 'split', 'w_split')
 
-    def __init__(self, wpack, taps, scale, shift, relu, split=False):
+    def __init__(self, wpack, taps, scale, shift, relu, split=False, w_split=None):
+        # split: activations travel as hi + lo planes; w_split: the pack carries Wl as well (three-term product)
         self.wpack, self.taps, self.scale, self.shift, self.relu, self.split = wpack, taps, scale, shift, relu, split
-        self.cout, self.cin = wpack.shape[1], wpack.shape[2] // (2 if split else 1)
+        self.w_split = split if w_split is None else w_split
+        self.cout, self.cin = wpack.shape[1], wpack.shape[2] // (2 if self.w_split else 1)
 
 
 def split_f16(x):
@@ -122,11 +136,12 @@ def pack_upsample_phases(weight, split=False):
     return out
 
 
-def conv_bn_pack(conv, bn, relu=True, dilation=1, split=False):
+def conv_bn_pack(conv, bn, relu=True, dilation=1, split=False, w_split=None):
     scale, shift = fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None \
         else fold_bn(conv.bias)
-    wp, taps = pack_weight_taps(conv.weight, dilation, split)
-    return ConvPack(wp, taps, scale, shift, relu, split)
+    w_split = split if w_split is None else w_split
+    wp, taps = pack_weight_taps(conv.weight, dilation, w_split)
+    return ConvPack(wp, taps, scale, shift, relu, split, w_split)
 
 
 def run_conv(pack, src0, ws, name, src1=None, want_out=True, want_pool=False, out_f32=False):
@@ -142,8 +157,8 @@ def run_conv(pack, src0, ws, name, src1=None, want_out=True, want_pool=False, ou
         out_lo = ws.get(name + '.lo', (n, h, w, pack.cout), f16, dev) if out is not None else None
         pool_lo = ws.get(name + '.pool.lo', (n, h // 2, w // 2, pack.cout), f16, dev) if want_pool else None
         ops.conv_split(hi_of(src0), pack.wpack, pack.taps, pack.scale, pack.shift, pack.relu, src0_lo=lo_of(src0),
-                       src1=None if src1 is None else hi_of(src1), src1_lo=None if src1 is None else lo_of(src1), out=out,
-                       out_lo=out_lo, out_pool=pool, out_pool_lo=pool_lo, out_f32=o32)
+                       src1=None if src1 is None else hi_of(src1), src1_lo=None if src1 is None else lo_of(src1), w_split=pack.w_split,
+                       out=out, out_lo=out_lo, out_pool=pool, out_pool_lo=pool_lo, out_f32=o32)
         if out_f32:
             return o32
         return (None if out is None else (out, out_lo)), (None if pool is None else (pool, pool_lo))
@@ -154,7 +169,7 @@ def run_conv(pack, src0, ws, name, src1=None, want_out=True, want_pool=False, ou
     return out, pool
 
 
-def run_upconv(phases, scale, shift, src, ws, name, split=False):
+def run_upconv(phases, scale, shift, src, ws, name, split=False, w_split=None):
     """Sub-pixel form of up_conv: four phase convs scatter into the 2x resolution output."""
     n, h, w, _ = hi_of(src).shape
     cout = phases[0][0].shape[1]
@@ -163,8 +178,8 @@ def run_upconv(phases, scale, shift, src, ws, name, split=False):
     if split:
         out_lo = ws.get(name + '.lo', (n, 2 * h, 2 * w, cout), torch.float16, dev)
         for wp, taps, (py, px) in phases:
-            ops.conv_split(hi_of(src), wp, taps, scale, shift, True, src0_lo=lo_of(src), out=out, out_lo=out_lo,
-                           out_map=(2, py, 2, px))
+            ops.conv_split(hi_of(src), wp, taps, scale, shift, True, src0_lo=lo_of(src), w_split=split if w_split is None else w_split,
+                           out=out, out_lo=out_lo, out_map=(2, py, 2, px))
         return out, out_lo
     for wp, taps, (py, px) in phases:
         ops.conv_igemm(hi_of(src), wp, taps, scale, shift, True, out=out, out_map=(2, py, 2, px))

@@ -63,7 +63,8 @@ class conv_block(_PackedModule):
     def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1, precision=None):
         super(conv_block, self).__init__()
         _check_norm(normalization_type)
-        self.split = (precision or engine.default_precision()) == "split"     # engine.PRECISIONS
+        pr = precision or engine.default_precision()                           # engine.PRECISIONS (+ 'split-a': fp16 weights)
+        self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
         if kernel != 3 or padding != 1:
             raise NotImplementedError('conv_block: only kernel=3, padding=1 is used by RP-Net')
         self.ch_in = ch_in
@@ -84,8 +85,8 @@ class conv_block(_PackedModule):
             c, b = self.conv[0], self.conv[1]
             first = engine.fold_bn(c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)    # (scale, shift) tuple
         else:
-            first = engine.conv_bn_pack(self.conv[0], self.conv[1], split=self.split)
-        return first, engine.conv_bn_pack(self.conv[3], self.conv[4], split=self.split)
+            first = engine.conv_bn_pack(self.conv[0], self.conv[1], split=self.split, w_split=self.w_split)
+        return first, engine.conv_bn_pack(self.conv[3], self.conv[4], split=self.split, w_split=self.w_split)
 
     def run_nhwc(self, x, ws, name, x1=None, want_out=True, want_pool=False):
         """x: fp16 NHWC (or the fp32 NCHW image for the first block); x1: optional second source (channel concat).
@@ -110,7 +111,8 @@ class up_conv(_PackedModule):
     def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1, precision=None):
         super(up_conv, self).__init__()
         _check_norm(normalization_type)
-        self.split = (precision or engine.default_precision()) == "split"
+        pr = precision or engine.default_precision()
+        self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
         if kernel != 3 or padding != 1:
             raise NotImplementedError('up_conv: only kernel=3, padding=1 is used by RP-Net')
         self.ch_in = ch_in
@@ -125,12 +127,12 @@ class up_conv(_PackedModule):
     def _build_packs(self):
         conv, bn = self.up[1], self.up[2]
         scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-        return engine.pack_upsample_phases(conv.weight, self.split), scale, shift
+        return engine.pack_upsample_phases(conv.weight, self.w_split), scale, shift
 
     def run_nhwc(self, x, ws, name):
         _check_eval(self)
         phases, scale, shift = self._packs()
-        return engine.run_upconv(phases, scale, shift, x, ws, name, self.split)
+        return engine.run_upconv(phases, scale, shift, x, ws, name, self.split, self.w_split)
 
     def forward(self, x):
         out = self.run_nhwc(engine.nchw_f32_to_nhwc_f16(x), self._workspace(), 'uc')

@@ -39,15 +39,16 @@ class U_Net(Unet_2D):
         num_feats = [64, 128, 256, 512, 1024]
         norm = cfg['unet_normalize_type']
         pr = engine.precision_of(cfg)          # 'split' (fp32-class, default) or 'fp16' (engine.PRECISIONS)
+        pd = engine.decoder_precision(pr)      # decoder half: split activations, fp16 weights (engine.decoder_precision)
         self.Conv1 = conv_block(ch_in=self.img_ch, ch_out=num_feats[0], normalization_type=norm, precision=pr)
         self.Conv2 = conv_block(ch_in=num_feats[0], ch_out=num_feats[1], normalization_type=norm, precision=pr)
         self.Conv3 = conv_block(ch_in=num_feats[1], ch_out=num_feats[2], normalization_type=norm, precision=pr)
         self.Conv4 = conv_block(ch_in=num_feats[2], ch_out=num_feats[3], normalization_type=norm, precision=pr)
         self.Conv5 = conv_block(ch_in=num_feats[3], ch_out=num_feats[4], normalization_type=norm, precision=pr)
-        self.Up5 = up_conv(ch_in=num_feats[4], ch_out=num_feats[3], normalization_type=norm, precision=pr)
-        self.Up_conv5 = conv_block(ch_in=num_feats[3] * 2, ch_out=num_feats[3], normalization_type=norm, precision=pr)
-        self.Up4 = up_conv(ch_in=num_feats[3], ch_out=num_feats[2], normalization_type=norm, precision=pr)
-        self.Up_conv4 = conv_block(ch_in=num_feats[2] * 2, ch_out=num_feats[2], normalization_type=norm, precision=pr)
+        self.Up5 = up_conv(ch_in=num_feats[4], ch_out=num_feats[3], normalization_type=norm, precision=pd)
+        self.Up_conv5 = conv_block(ch_in=num_feats[3] * 2, ch_out=num_feats[3], normalization_type=norm, precision=pd)
+        self.Up4 = up_conv(ch_in=num_feats[3], ch_out=num_feats[2], normalization_type=norm, precision=pd)
+        self.Up_conv4 = conv_block(ch_in=num_feats[2] * 2, ch_out=num_feats[2], normalization_type=norm, precision=pd)
         self._ws = engine.Workspace()
 
     def encode_nhwc(self, x, tag='enc'):

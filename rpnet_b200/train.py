@@ -139,10 +139,11 @@ def shard_range(total, rank, world):
 class _ConvBN:
     """One conv (bias dropped: it cancels in train-mode BN) + BatchNorm(batch stats) + ReLU of the path."""
 
-    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False):
-        # split: the forward runs in split-fp16 (x = hi + lo planes, weights Wh | Wl, three tensor-core passes: fp32-class
-        # result); the backward is unchanged (it reads the hi planes).
+    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False, w_split=None):
+        # split: the forward runs in split-fp16 (x = hi + lo planes; with w_split weights Wh | Wl: three tensor-core passes,
+        # fp32-class result; without: hi.W + lo.W); the backward is unchanged (it reads the hi planes).
         self.name, self.conv, self.bn, self.first, self.hole, self.up, self.split = name, conv, bn, first, hole, up, split
+        self.w_split = split if w_split is None else w_split
         self.gw, self.ggamma, self.gbeta = flat.grad_of(conv.weight), flat.grad_of(bn.weight), flat.grad_of(bn.bias)
         k = conv.kernel_size[0]
         d = conv.dilation[0]
@@ -150,7 +151,7 @@ class _ConvBN:
         self.cout = conv.out_channels
         self.cin_pack = conv.in_channels + hole[1]
         dev = conv.weight.device
-        ks = 2 if split else 1
+        ks = 2 if self.w_split else 1
         if not first:
             self.wf = torch.empty(len(self.taps), self.cout, self.cin_pack * ks, dtype=f16, device=dev)
             self.wd = torch.empty(len(self.taps), self.cin_pack, self.cout, dtype=bf16, device=dev)
@@ -162,9 +163,9 @@ class _ConvBN:
 
     def pack(self):
         if not self.first:
-            ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole, split=self.split)
+            ops.pack_conv_weight(self.conv.weight.data, self.wf, self.wd, hole=self.hole, split=self.w_split)
         if self.up:
-            ops.pack_upconv_weight(self.conv.weight.data, self.wf_up, self.w16_up, split=self.split)
+            ops.pack_upconv_weight(self.conv.weight.data, self.wf_up, self.w16_up, split=self.w_split)
 
     def fwd_up(self, x_low, z, gs, sums, stats, y):
         """z = conv3x3(upsample2x(x_low)) in sub-pixel form (four phase convs, statistics in their epilogues) + BN + ReLU.
@@ -175,8 +176,8 @@ class _ConvBN:
             for ph in range(4):
                 py, px = ph >> 1, ph & 1
                 taps = [((-1 if py == 0 else 0) + (t >> 1), (-1 if px == 0 else 0) + (t & 1)) for t in range(4)]
-                ops.conv_split(x_low[0], self.wf_up[ph], taps, self.ones, self.zeros, False, src0_lo=x_low[1], out=z[0], out_lo=z[1],
-                               out_map=(2, py, 2, px), group_start=gs, sums=sums, keep_sums=ph > 0)
+                ops.conv_split(x_low[0], self.wf_up[ph], taps, self.ones, self.zeros, False, src0_lo=x_low[1], w_split=self.w_split,
+                               out=z[0], out_lo=z[1], out_map=(2, py, 2, px), group_start=gs, sums=sums, keep_sums=ph > 0)
         else:
             ops.upconv_fwd_bnstats(x_low[0], self.wf_up, self.ones, self.zeros, z[0], gs, sums)
         ops.bn_finalize(sums, gs, c, H * W, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
@@ -207,7 +208,7 @@ class _ConvBN:
             ops.bn_stats(z[0], gs, sums, z_lo=z[1])
         elif self.split:
             ops.conv_split(x0[0], self.wf, self.taps, self.ones, self.zeros, False, src0_lo=x0[1], src1=None if x1 is None else x1[0],
-                           src1_lo=None if x1 is None else x1[1], out=z[0], out_lo=z[1], group_start=gs, sums=sums)
+                           src1_lo=None if x1 is None else x1[1], w_split=self.w_split, out=z[0], out_lo=z[1], group_start=gs, sums=sums)
         else:
             ops.conv_bnstats(x0[0], self.wf, self.taps, self.ones, self.zeros, z[0], gs, sums, src1=None if x1 is None else x1[0])
         ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
@@ -251,14 +252,17 @@ class TrainEngine:
         # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
         # train-mode logits 2e-3 .. 5e-3 from the fp32 reference); the cre convs are single-term in both (their rounding moves
         # the logits by ~1e-4)
-        self.split = sp = engine.precision_of(net.backbone_cfg) == 'split'
+        pr = engine.precision_of(net.backbone_cfg)
+        self.split = sp = pr == 'split'
+        wd = engine.decoder_precision(pr) == 'split'     # decoder half: split activations, fp16 weights unless RPNET_SPLIT_DECODER=3
         L = {}
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
-            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'), split=sp)
-            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat, split=sp)
-        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True, split=sp)
-        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True, split=sp)
+            ws = sp and (wd or not nm.startswith('uc'))
+            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'), split=sp, w_split=ws)
+            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat, split=sp, w_split=ws)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True, split=sp, w_split=sp and wd)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True, split=sp, w_split=sp and wd)
         k = (2 * c.radius + 1) ** 2
         self.kcorr, self.corr_c = k, c.corr_channels
         L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)

@@ -74,7 +74,8 @@ def main():
         net.eval()
         with torch.no_grad():
             got = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
-            ref = O.forward({k: v.clone() for k, v in sd.items()}, cfg, *a)
+            over = {i: O.recurrent_mask(got['refinement'][i - 1].float().cpu(), cfg) for i in range(1, args.T)}      # teacher forcing
+            ref = O.forward({k: v.clone() for k, v in sd.items()}, cfg, *a, mask_override=over)
         out['logits'] = logits_report([got['refinement'][i].cpu() for i in range(args.T)], [ref['refinement'][i] for i in range(args.T)])
     else:
         ts = TrainStep(net)
@@ -90,8 +91,9 @@ def main():
                     params[k] = v
                 sdo[k] = v
             cast = lambda x: [[t.to(dtype) for t in way] for way in x]
+            over = {i: O.recurrent_mask(ts.last['logits'][i - 1].float().cpu(), cfg).to(dtype) for i in range(1, args.T)}   # teacher forcing
             o = O.forward(sdo, cfg, cast(ep['supp_imgs']), cast(ep['fore_mask']), cast(ep['back_mask']), [t.to(dtype) for t in ep['qry_imgs']],
-                          ep['appr_query_labels'].to(dtype), training=True)
+                          ep['appr_query_labels'].to(dtype), training=True, mask_override=over)
             ls = O.train_loss(o, ep['query_labels'])
             ls.backward()
             return o, ls.detach(), params
