@@ -39,7 +39,7 @@ class U_Net(Unet_2D):
         num_feats = [64, 128, 256, 512, 1024]
         norm = cfg['unet_normalize_type']
         pr = engine.precision_of(cfg)          # 'split' (fp32-class, default) or 'fp16' (engine.PRECISIONS)
-        pd = engine.decoder_precision(pr)      # decoder half: split activations, fp16 weights (engine.decoder_precision)
+        pd = engine.decoder_precision(pr)      # decoder half: the same, or fp16 weights with RPNET_SPLIT_DECODER=2 (engine.decoder_precision)
         self.Conv1 = conv_block(ch_in=self.img_ch, ch_out=num_feats[0], normalization_type=norm, precision=pr)
         self.Conv2 = conv_block(ch_in=num_feats[0], ch_out=num_feats[1], normalization_type=norm, precision=pr)
         self.Conv3 = conv_block(ch_in=num_feats[1], ch_out=num_feats[2], normalization_type=norm, precision=pr)

@@ -254,7 +254,7 @@ class TrainEngine:
         # the logits by ~1e-4)
         pr = engine.precision_of(net.backbone_cfg)
         self.split = sp = pr == 'split'
-        wd = engine.decoder_precision(pr) == 'split'     # decoder half: split activations, fp16 weights unless RPNET_SPLIT_DECODER=3
+        wd = engine.decoder_precision(pr) == 'split'     # decoder half: RPNET_SPLIT_DECODER=2 -> split activations, fp16 weights
         L = {}
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
