@@ -261,7 +261,7 @@ def run_library(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def parity_field(sd, wl, dev, precision):
+def parity_field(sd, wl, dev, precision, cfg_extra=None):
     """1-2 slices of the workload's shape through the CPU oracle and through the B200 path (outside every timed region) with
     the state_dict the timed run ended with: rel-Linf / margin error / argmax mismatch / Dice-vs-reference of the last
     refinement iteration (rpnet_b200/parity.py)."""
@@ -272,6 +272,7 @@ def parity_field(sd, wl, dev, precision):
     from rpnet_b200.synthetic import make_episode, to_device
     B = 1 if wl['ways'] > 1 else 2
     cfg = model_cfg(wl['T'])
+    cfg.update(cfg_extra or {})
     ep = make_episode(B, wl['ways'], wl['shots'], wl['size'], seed=4242)
     net = RP_Net(pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
     net.load_state_dict(sd)
@@ -339,6 +340,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-library-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-fast-mode', action='store_true', help="skip the extra timing of `b200_precision: fp16` (TF32-class arithmetic)")
     ap.add_argument('--no-cuda-graph', action='store_true', help='inference workloads: launch every kernel from Python')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -576,6 +578,24 @@ def main():
     par = None
     if not args.no_parity and world == 1:
         par = parity_field({k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, wl, dev, precision)
+    fast = None
+    if not args.no_fast_mode and world == 1 and precision == 'split' and wl['train']:
+        # the same workload with `b200_precision: fp16`: single-term fp16 operands = the 11-bit significand of the library's
+        # default TF32 convs.  Reported beside the headline (which is the fp32-class split mode): what relaxing the arithmetic to
+        # the library's own default precision buys, and what it costs in parity.
+        cfg16 = dict(cfg, b200_precision='fp16')
+        torch.manual_seed(0)
+        net16 = RP_Net(pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg16).to(dev).train()
+        st16 = rp_train.TrainStep(net16, world_size=1)
+        for _ in range(args.warmup):
+            st16.step(resident)
+        ms16, _ = timed(lambda: st16.step(resident), args.steps)
+        fast = {'b200_precision': 'fp16', 'value': B / (ms16 / args.steps * 1e-3), 'unit': 'slices/s', 'ms_per_step': ms16 / args.steps,
+                'what': 'same workload, single-term fp16 conv operands (TF32-class, like the library default); device-timed, inputs resident'}
+        if not args.no_parity:
+            p16 = parity_field({k: v.detach().cpu().clone() for k, v in net16.state_dict().items()}, dict(wl), dev, 'fp16', cfg_extra={'b200_precision': 'fp16'})
+            fast['parity'] = {k: p16[k] for k in ('rel_linf', 'margin_rel_err', 'argmax_mismatch', 'dice_vs_ref')}
+        del net16, st16
 
     ms_step = ms_total / args.steps
     total_units = wl['slices'] if wl.get('volume') else world * B
@@ -593,7 +613,7 @@ def main():
             'e2e': {'value': total_units / (ms_e2e / args.steps * 1e-3), 'unit': 'slices/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'library_baseline': lib, 'parity': par,
-            'precision': precision, 'kernels': stream_kernels}
+            'precision': precision, 'tf32_class_mode': fast, 'kernels': stream_kernels}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
