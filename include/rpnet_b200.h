@@ -286,6 +286,18 @@ int rpnet_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, voi
 int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask, int iters, long long pixels, int c,
                            void* dx, void* stream);
 
+/* `soft_mask: True` training (net/rp_net.py:308-311 without the threshold): the recurrent mask m_{i+1} = avg_pool2d(p_fg(logits_i), scale)
+ * stays in the autograd graph.
+ * rpnet_premask_mask_bwd: dmask[p] = sum_c (dxfg[p][c] - dxbg[p][c]) * x[p][c] — the gradient of x_fg = x * m, x_bg = x * (1 - m) (:283)
+ *   w.r.t. m; dxfg / dxbg bf16 NHWC, x fp16 NHWC (`pixels` x c), dmask fp32 [pixels].
+ * rpnet_soft_mask_bwd_f32: dlogits[b][k][Y][X] += dmask[b][Y/scale][X/scale] / scale^2 * softmax_k * ([k >= 1] - p_fg): through
+ *   F.avg_pool2d and softmax(dim=1)[:, 1] (sum of the foreground classes for more than one way) into the logits of the previous
+ *   iteration.  logits / dlogits fp32 [batch][classes][h*scale][w*scale], dmask fp32 [batch][h][w]. */
+int rpnet_premask_mask_bwd(const void* dxfg_bf16, const void* dxbg_bf16, const void* x_f16, long long pixels, int c, float* dmask,
+                           void* stream);
+int rpnet_soft_mask_bwd_f32(const float* logits, const float* dmask, int batch, int n_classes, int h, int w, int scale,
+                            float* dlogits, void* stream);
+
 /* Backward of Correlation (net/rp_net.py:153-181).  dq_bf16 NHWC [n][h][w][ld]: channels [0,(2r+1)^2) = d corr,
  * [add_off, add_off+c) = the direct gradient of fm1 from cat([corr, fm1]) (net/rp_net.py:81), added into df1. */
 /* workspace (optional): rpnet_local_corr_bwd_workspace_bytes(n, h, w, radius) bytes of scratch enable the tensor-core

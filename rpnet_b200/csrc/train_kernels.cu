@@ -701,6 +701,64 @@ __global__ void premask_bwd_kernel(const uint4* __restrict__ dxfg, const uint4* 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// soft_mask: True (net/rp_net.py:308-311 without the threshold): the recurrent mask m_{i+1} = avg_pool2d(p_fg(logits_i), S)
+// stays in the graph, so iteration i+1 sends a gradient back into iteration i's logits.
+// (1) d m(p) = sum_c (dxfg[p][c] - dxbg[p][c]) * x[p][c]           (x_fg = x * m, x_bg = x * (1 - m), :283)
+//     one warp per pixel: lanes stride the 8-channel vectors, shuffle reduce.
+// (2) dlogits[b][k][Y][X] += dm[b][Y/S][X/S] / S^2 * s_k * ([k >= 1] - p_fg),  s = softmax(logits[b][:][Y][X]),
+//     p_fg = sum_{k>=1} s_k  (the reference's channel 1 for Wa == 1; the oracle-ext sum for Wa > 1).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+premask_mask_bwd_kernel(const uint4* __restrict__ dxfg, const uint4* __restrict__ dxbg, const uint4* __restrict__ x, long long pixels,
+                        int c8, float* __restrict__ dm) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp; p < pixels; p += nwarps) {
+    float acc = 0.f;
+    for (int v = lane; v < c8; v += 32) {
+      float a[8], b[8], f[8];
+      unpack8_bf16(__ldg(dxfg + p * c8 + v), a);
+      unpack8_bf16(__ldg(dxbg + p * c8 + v), b);
+      unpack8_f16(__ldg(x + p * c8 + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(a[j] - b[j], f[j], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dm[p] = acc;
+  }
+}
+
+constexpr int kSoftMaxP = 8;
+__global__ void soft_mask_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ dm, int B, int P, int H, int W, int S,
+                                     float* __restrict__ dlogits) {
+  const long long total = (long long)B * H * W;
+  const int h = H / S, w = W / S;
+  const float inv = 1.f / (float)(S * S);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)((i / W) % H), b = (int)(i / ((long long)W * H));
+    const float g = __ldg(dm + ((long long)b * h + Y / S) * w + X / S) * inv;
+    float v[kSoftMaxP], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSoftMaxP; ++k)
+      if (k < P) { v[k] = __ldg(logits + (((long long)b * P + k) * H + Y) * W + X); mx = fmaxf(mx, v[k]); }
+    float den = 0.f;
+#pragma unroll
+    for (int k = 0; k < kSoftMaxP; ++k)
+      if (k < P) { v[k] = expf(v[k] - mx); den += v[k]; }
+    const float rden = 1.f / den;
+    const float pfg = 1.f - v[0] * rden;
+#pragma unroll
+    for (int k = 0; k < kSoftMaxP; ++k)
+      if (k < P) {
+        float* d = dlogits + (((long long)b * P + k) * H + Y) * W + X;
+        *d += g * v[k] * rden * ((k >= 1 ? 1.f : 0.f) - pfg);
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Weight repack (every optimizer step): fp32 [cout][cin_real][taps] ->
 //   forward  fp16 [taps][cout][cin]   (K-major B operand of conv_igemm)
 //   dgrad    bf16 [taps][cin][cout]   (transposed; used with the negated tap list)
@@ -1072,6 +1130,26 @@ RPNET_API int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const f
 
 RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
                                             void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream_);
+
+RPNET_API int rpnet_premask_mask_bwd(const void* dxfg_bf16, const void* dxbg_bf16, const void* x_f16, long long pixels, int c, float* dmask,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dxfg_bf16 && dxbg_bf16 && x_f16 && dmask, "premask_mask_bwd: null pointer argument");
+  RPNET_REQUIRE(pixels > 0 && c > 0 && c % 8 == 0, "premask_mask_bwd: bad shape pixels=%lld c=%d", pixels, c);
+  premask_mask_bwd_kernel<<<grid_for(pixels * 32, 256), 256, 0, stream>>>(static_cast<const uint4*>(dxfg_bf16), static_cast<const uint4*>(dxbg_bf16),
+                                                                          static_cast<const uint4*>(x_f16), pixels, c / 8, dmask);
+  return check_cuda(cudaGetLastError(), "premask_mask_bwd launch");
+}
+
+RPNET_API int rpnet_soft_mask_bwd_f32(const float* logits, const float* dmask, int batch, int n_classes, int h, int w, int scale,
+                                       float* dlogits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(logits && dmask && dlogits, "soft_mask_bwd: null pointer argument");
+  RPNET_REQUIRE(batch > 0 && n_classes >= 2 && n_classes <= kSoftMaxP && h > 0 && w > 0 && scale >= 1, "soft_mask_bwd: bad shape");
+  soft_mask_bwd_kernel<<<grid_for((long long)batch * h * scale * w * scale, 256), 256, 0, stream>>>(logits, dmask, batch, n_classes, h * scale,
+                                                                                                    w * scale, scale, dlogits);
+  return check_cuda(cudaGetLastError(), "soft_mask_bwd launch");
+}
 
 RPNET_API int rpnet_pack_conv_weight(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len, void* w_fwd_f16,
                                       void* w_dgrad_bf16, void* stream_) {

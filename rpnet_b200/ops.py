@@ -531,6 +531,28 @@ def premask_bwd(dxfg, dxbg, mask, dx, iters=1):
         _lib.check(lib.rpnet_premask_bwd_bf16(_ptr(dxfg), _ptr(dxbg), _ptr(mask), iters, pixels, c, _ptr(dx), _stream()), 'rpnet_premask_bwd_bf16')
 
 
+def premask_mask_bwd(dxfg, dxbg, x, dmask):
+    """dmask fp32 [n, h, w] = sum_c (dxfg - dxbg) * x  (gradient of the pre-mask w.r.t. a soft recurrent mask)."""
+    lib = _lib.load()
+    _req(dxfg, bf16, 'dxfg'); _req(dxbg, bf16, 'dxbg'); _req(x, torch.float16, 'x'); _req(dmask, torch.float32, 'dmask')
+    c = x.shape[-1]
+    pixels = x.numel() // c
+    assert dxfg.shape == x.shape and dxbg.shape == x.shape and dmask.numel() == pixels
+    with _Timed('premask_mask_bwd', float(x.numel() * 6)):
+        _lib.check(lib.rpnet_premask_mask_bwd(_ptr(dxfg), _ptr(dxbg), _ptr(x), pixels, c, _ptr(dmask), _stream()), 'rpnet_premask_mask_bwd')
+
+
+def soft_mask_bwd(logits, dmask, scale, dlogits):
+    """dlogits [b, P, H, W] += the gradient of avg_pool2d(p_fg(logits), scale) against dmask [b, H/scale, W/scale]."""
+    lib = _lib.load()
+    _req(logits, torch.float32, 'logits'); _req(dmask, torch.float32, 'dmask'); _req(dlogits, torch.float32, 'dlogits')
+    b, p, H, W = logits.shape
+    assert dlogits.shape == logits.shape and dmask.numel() == b * (H // scale) * (W // scale)
+    with _Timed('soft_mask_bwd', float(logits.numel() * 12)):
+        _lib.check(lib.rpnet_soft_mask_bwd_f32(_ptr(logits), _ptr(dmask), b, p, H // scale, W // scale, scale, _ptr(dlogits), _stream()),
+                   'rpnet_soft_mask_bwd_f32')
+
+
 def local_corr_bwd(f1, f2, dq, add_off, radius, df1, df2, workspace=None):
     """workspace: optional uint8/any tensor of >= local_corr_bwd_workspace_bytes(...) bytes (enables the tensor-core path)."""
     lib = _lib.load()

@@ -14,7 +14,9 @@ parameter buffer (state_dict / load_state_dict keep working) and their `.grad` a
 
 With `soft_mask: False` the thresholded mask cuts the graph between refinement iterations (net/rp_net.py:309-311), so
 the T query `cre` calls are independent in the backward and are processed as ONE batched launch per kernel
-(T call groups); `soft_mask: True` training (back-propagation through the mask) is not built and raises.
+(T call groups).  With `soft_mask: True` the mask m_{i+1} = avg_pool2d(p_fg(logits_i)) stays in the graph: the backward then
+walks the iterations from the last to the first, sending each iteration's pre-mask gradient back into the previous
+iteration's logits (rpnet_premask_mask_bwd, rpnet_soft_mask_bwd_f32).
 """
 import torch
 
@@ -215,8 +217,9 @@ class _ConvBN:
                         bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
         ops.bn_apply(z[0], stats, gs, True, y=y[0], y_pool=pool[0], y_f32=y32, z_lo=z[1], y_lo=y[1], y_pool_lo=pool[1])
 
-    def bwd(self, eng, x0, x1, z, stats, gs, dx=None, **src):
-        """BN+ReLU backward -> dz; weight gradient; data gradient into `dx` (bf16 [n,h,w,cin_pack]) when given."""
+    def bwd(self, eng, x0, x1, z, stats, gs, dx=None, accumulate=False, **src):
+        """BN+ReLU backward -> dz; weight gradient (= or += with `accumulate`); data gradient into `dx` (bf16 [n,h,w,cin_pack])
+        when given."""
         n, h, w, c = z.shape
         dz = eng.scratch('dz', n * h * w * c, bf16).view(n, h, w, c)
         ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 6, f32), True,
@@ -228,7 +231,7 @@ class _ConvBN:
             c1 = 0 if x1 is None else x1.shape[3]
             nb = ops.conv_wgrad_workspace_bytes(c0, c1, n, h, w, len(self.taps), self.cout)
             ops.conv_wgrad(x0, dz, self.taps, self.gw, eng.scratch('wgrad', nb // 4, f32), x1=x1, hole=self.hole,
-                           accumulate=False)
+                           accumulate=accumulate)
             if dx is not None:
                 ops.conv_dgrad(dz, self.wd, self.taps, dx)
         return dx
@@ -241,8 +244,6 @@ class TrainEngine:
         from .nn.unet import U_Net
         if not isinstance(net.encoder, U_Net):
             raise NotImplementedError("training is built for backbone 'UNet' (the reference cannot train 'vgg': SURVEY D1)")
-        if net.backbone_cfg['soft_mask']:
-            raise NotImplementedError('soft_mask: True training (gradient through the recurrent mask) is not built')
         dev = next(net.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
@@ -477,6 +478,7 @@ class TrainEngine:
         ops.proto_finalize(raw, protos)
 
         # recurrent refinement (net/rp_net.py:280-312)
+        soft = bool(net.backbone_cfg['soft_mask'])                      # net/rp_net.py:309: `soft_mask == False` thresholds
         qm = buf('qry_m', (T + 1, B, h, w), f32)
         ops.avgpool_mask(d['appr_query_labels'].reshape(B, H, W).float().contiguous(), S, qm[0])
         pred = buf('pred', (T, B, P, h, w), f32)
@@ -486,7 +488,7 @@ class TrainEngine:
             lo = n_supp + i * B
             qfeat = self._cre_fwd(qd4, qm[i], lo, lo + B, Wa * Sh + i, [0, B])
             ops.cos_sim(qfeat, protos, pred[i], 20.0)
-            ops.upsample_tail(pred[i], logits[i], qm[i + 1], S, False)
+            ops.upsample_tail(pred[i], logits[i], qm[i + 1], S, soft)
 
         # alignLoss (net/rp_net.py:340-343, 394-440) on the last iteration's features / prediction (D5)
         align = buf('align', (1,), f32)
@@ -507,7 +509,7 @@ class TrainEngine:
         else:
             align.zero_()
         self.saved = dict(Wa=Wa, Sh=Sh, B=B, H=H, W=W, h=h, w=w, C=C, T=T, P=P, n_supp=n_supp, n_tot=n_tot, d4=d4, supp_m=supp_m,
-                          wf=wf, wb=wb, sf=sf, sb=sb, protos=protos, qm=qm, pred=pred, logits=logits, use_align=use_align)
+                          wf=wf, wb=wb, sf=sf, sb=sb, protos=protos, qm=qm, pred=pred, logits=logits, use_align=use_align, soft=soft)
         return logits, align
 
     # ------------------------------------------------------------------ backward
@@ -523,13 +525,25 @@ class TrainEngine:
         G_tot = Wa * Sh + T
         gs_all = [i * B for i in range(G_tot + 1)]
 
-        # logits -> pred (adjoint of the bilinear upsample, net/rp_net.py:303) -> query features / prototypes (calDist)
         dpred = buf('b.dpred', (T, B, P, h, w), f32)
-        ops.bilinear_adjoint(dlogits.view(T * B * P, H, W), dpred.view(T * B * P, h, w))
         dfeat = buf('b.dfeat', (n_tot, h, w, 64), f32)
         dprotos = buf('b.dprotos', (B, P, 64), f32)
-        ops.cos_sim_bwd(S['feat'][n_supp:], s['protos'], dpred.view(T * B, P, h, w), dfeat[n_supp:], dprotos, 20.0)
-        if s['use_align'] and dalign != 0.0:
+        dq = buf('b.dq', (n_tot, h, w, self.corr_c + C), bf16)
+        df1, df2 = buf('b.df1', (n_tot, h, w, C), bf16), buf('b.df2', (n_tot, h, w, C), bf16)
+        dxfg, dxbg = buf('b.dxfg', (n_tot, h, w, C), bf16), buf('b.dxbg', (n_tot, h, w, C), bf16)
+        r = self.net.cre.radius
+
+        def cre_bwd(lo, hi, g0, gs, accumulate):
+            """Backward of the cre calls on images [lo, hi) of the batched buffers (call groups `gs`, statistics rows from g0)."""
+            sl, G = slice(lo, hi), len(gs) - 1
+            L['q'].bwd(self, S['corr'][sl], S['fm1'][sl], S['z3'][sl], S['st3'][g0:g0 + G], gs, dx=dq[sl], accumulate=accumulate, direct=dfeat[sl])
+            ops.local_corr_bwd(S['fm1'][sl], S['fm2'][sl], dq[sl], self.corr_c, r, df1[sl], df2[sl],
+                               workspace=self.scratch('corr_bwd', ops.local_corr_bwd_workspace_bytes(hi - lo, h, w, r) // 2, bf16))
+            L['wk'].bwd(self, S['xfg'][sl], None, S['z1'][sl], S['st1'][g0:g0 + G], gs, dx=dxfg[sl], accumulate=accumulate, direct=df1[sl])
+            L['wq'].bwd(self, S['xbg'][sl], None, S['z2'][sl], S['st2'][g0:g0 + G], gs, dx=dxbg[sl], accumulate=accumulate, direct=df2[sl])
+
+        def align_bwd():
+            """alignLoss backward (net/rp_net.py:394-440): into the support features and the last iteration's query features."""
             lg, fore, back, wgt = self._align_args
             dlg = self.scratch('b.dlg', lg.numel(), f32).view(lg.shape)
             ops.ce_mask(lg, fore, back, wgt, self.scratch('al.sums', n_supp * 2, torch.float64), buf('b.align', (1,), f32), dlg, float(dalign))
@@ -541,23 +555,41 @@ class TrainEngine:
             ops.align_scatter(dps, Wa, Sh, dqp)
             lo = n_supp + (T - 1) * B
             ops.class_pool_bwd(dqp, buf('al.counts', (B, P), f32), buf('al.amax', (B, h, w), torch.int32), dfeat[lo:lo + B])
-            acc = True
-        else:
-            acc = False
-        draw = buf('b.draw', (Wa, Sh, B, 2, 64), f32)
-        ops.proto_finalize_bwd(dprotos, draw)
-        ops.weighted_pool_bwd(draw.view(n_supp, 2, 64), s['wf'], s['wb'], s['sf'], s['sb'], dfeat[:n_supp], accumulate=acc)
+        acc = bool(s['use_align'] and dalign != 0.0)
 
-        # cre backward, all Wa*Sh + T calls as one batched launch per kernel
-        dq = buf('b.dq', (n_tot, h, w, self.corr_c + C), bf16)
-        L['q'].bwd(self, S['corr'], S['fm1'], S['z3'], S['st3'], gs_all, dx=dq, direct=dfeat)
-        df1, df2 = buf('b.df1', (n_tot, h, w, C), bf16), buf('b.df2', (n_tot, h, w, C), bf16)
-        r = self.net.cre.radius
-        ops.local_corr_bwd(S['fm1'], S['fm2'], dq, self.corr_c, r, df1, df2,
-                           workspace=self.scratch('corr_bwd', ops.local_corr_bwd_workspace_bytes(n_tot, h, w, r) // 2, bf16))
-        dxfg, dxbg = buf('b.dxfg', (n_tot, h, w, C), bf16), buf('b.dxbg', (n_tot, h, w, C), bf16)
-        L['wk'].bwd(self, S['xfg'], None, S['z1'], S['st1'], gs_all, dx=dxfg, direct=df1)
-        L['wq'].bwd(self, S['xbg'], None, S['z2'], S['st2'], gs_all, dx=dxbg, direct=df2)
+        if not s['soft']:
+            # logits -> pred (adjoint of the bilinear upsample, net/rp_net.py:303) -> query features / prototypes (calDist)
+            ops.bilinear_adjoint(dlogits.view(T * B * P, H, W), dpred.view(T * B * P, h, w))
+            ops.cos_sim_bwd(S['feat'][n_supp:], s['protos'], dpred.view(T * B, P, h, w), dfeat[n_supp:], dprotos, 20.0)
+            if acc:
+                align_bwd()
+            draw = buf('b.draw', (Wa, Sh, B, 2, 64), f32)
+            ops.proto_finalize_bwd(dprotos, draw)
+            ops.weighted_pool_bwd(draw.view(n_supp, 2, 64), s['wf'], s['wb'], s['sf'], s['sb'], dfeat[:n_supp], accumulate=acc)
+            # cre backward, all Wa*Sh + T calls as one batched launch per kernel
+            cre_bwd(0, n_tot, 0, gs_all, False)
+        else:
+            # soft mask: iteration i's logits also feed iteration i + 1 through m_{i+1} = avg_pool2d(p_fg(logits_i)) — walk the
+            # iterations backwards, folding each pre-mask gradient into the previous iteration's dlogits before it is consumed
+            dlogits = dlogits.clone()
+            dprotos_t = buf('b.dprotos_t', (T, B, P, 64), f32)
+            dm = buf('b.dm', (B, h, w), f32)
+            qd4 = s['d4'][n_supp:]
+            for i in range(T - 1, -1, -1):
+                lo = n_supp + i * B
+                ops.bilinear_adjoint(dlogits[i].view(B * P, H, W), dpred[i].view(B * P, h, w))
+                ops.cos_sim_bwd(S['feat'][lo:lo + B], s['protos'], dpred[i], dfeat[lo:lo + B], dprotos_t[i], 20.0)
+                if acc and i == T - 1:
+                    align_bwd()
+                cre_bwd(lo, lo + B, Wa * Sh + i, [0, B], True)
+                if i >= 1:
+                    ops.premask_mask_bwd(dxfg[lo:lo + B], dxbg[lo:lo + B], qd4, dm)
+                    ops.soft_mask_bwd(s['logits'][i - 1], dm, self.net.scale, dlogits[i - 1])
+            torch.sum(dprotos_t, dim=0, out=dprotos)          # [B, P, 64]: plumbing-sized
+            draw = buf('b.draw', (Wa, Sh, B, 2, 64), f32)
+            ops.proto_finalize_bwd(dprotos, draw)
+            ops.weighted_pool_bwd(draw.view(n_supp, 2, 64), s['wf'], s['wb'], s['sf'], s['sb'], dfeat[:n_supp], accumulate=acc)
+            cre_bwd(0, n_supp, 0, [i * B for i in range(Wa * Sh + 1)], True)
         if buckets:
             buckets.ready(0)
         g_d4 = buf('b.g_d4', tuple(s['d4'].shape), bf16)

@@ -1,14 +1,17 @@
 """Train-step parity (rpnet_b200.train) against (a) the golden train step recorded from the unmodified reference
 (tests/golden/train_step.npz: loss, logits, per-parameter gradient norms / heads, BN running statistics) and (b) the CPU
-oracle + torch autograd on the same seeded inputs, incl. the Wa x Sh generalisation.
+oracle + torch autograd on the same seeded inputs, incl. the Wa x Sh generalisation and `soft_mask: True`.
 
-Tolerances: train-mode logits rel-Linf 1e-2 — the pre-BN conv output z AND the activation y are each
-rounded to fp16 once per layer (eval mode rounds once and holds 1e-3), and batch-statistics BatchNorm over these tiny test
-batches (down to 32 samples per channel) divides by per-channel standard deviations far below the channel means, which
-amplifies the rounding of z; rounding the oracle the same way reproduces the level (3.9e-3 on the golden case, 3e-3 to 6e-3
-over the cases below; the statistics are accumulated with float atomics, so the last digits vary run to run); loss rel 2e-3; per-parameter gradient rel-L2 3e-2 for tensors that carry signal (bf16
-gradient operands) — measured against the conditioning of the problem, see _check_grads; BN running stats 1e-3.  The hard mask (net/rp_net.py:310) makes iteration i+1 discontinuous in
-iteration i's logits: when a near-tie pixel flips, later iterations are compared through the flipped fraction only."""
+Tolerances: train-mode logits rel-Linf 1e-3 against the FP32 oracle (BASELINE.json north_star) — the encoder
+forward runs in split-fp16 (fp32-class); loss rel 1e-3; BN running statistics 1e-3.
+Gradients: the backward stores activation gradients as bf16 and reads the fp16 hi planes, so its per-tensor error is a few
+1e-3 of the gradient norm WHEN THE PROBLEM IS WELL CONDITIONED — test_train_grads_fitted_fixture asserts fixed bounds on such a
+fixture (weights after 100 Adam steps, 8 x 128 x 128; there the oracle's own fp32 and fp64 gradients agree to 1e-5).  At random
+initialisation on 2 x 64 x 64 batches the reference's gradient is ill conditioned (the oracle's fp32 and fp64 gradients differ
+by 2e-3 in the first layers: ReLU / max-pool gate flips on flat CT background, BatchNorm over 32 samples), so those fixtures
+assert the head tightly and the encoder loosely, with fixed bounds.  The hard mask (net/rp_net.py:310) makes iteration i+1
+discontinuous in iteration i's logits: the oracle consumes the masks derived from OUR logits (teacher forcing), the flipped
+pixels themselves are bounded."""
 LOGIT_TOL = 1e-3
 import numpy as np
 import pytest
@@ -26,90 +29,76 @@ def dev():
     return torch.device('cuda:0')
 
 
-def _cfg(T):
+def _cfg(T, soft=False):
     return dict(unet_normalize_type='BatchNorm2d', final_activation='sigmoid', mask_feature_map=False,
-                n_iter_refinement=T, soft_mask=False, mask_refinement_correlation_radius=5)
+                n_iter_refinement=T, soft_mask=soft, mask_refinement_correlation_radius=5)
 
 
-def _net(sd, T, dev):
+def _net(sd, T, dev, soft=False):
     from net.model import model_factory
-    net = model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=_cfg(T))
+    net = model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=_cfg(T, soft))
     net.load_state_dict(sd)
     return net.to(dev).train()
 
 
-def _oracle_step(sd, T, ep, storage=None):
-    """Oracle forward + autograd.  storage='b200': same algorithm with the B200 path's fp16 storage points emulated
-    (oracle/rpnet_oracle.py STORAGE) — used to measure how far fp16 storage alone moves the reference's gradients."""
+def _oracle_step(sd, T, ep, ours=None, soft=False, dtype=torch.float32):
+    """Oracle forward + autograd (fp32, or fp64 to measure the conditioning of a fixture).  ours: our logits [T, ...] — with the hard
+    mask the oracle then consumes the recurrent masks derived from them (teacher forcing, oracle.forward(mask_override=...))."""
     from oracle import rpnet_oracle as O
-    O.STORAGE = storage
-    try:
-        return _oracle_step_impl(O, sd, T, ep)
-    finally:
-        O.STORAGE = None
-
-
-def _oracle_step_impl(O, sd, T, ep):
+    cfg = _cfg(T, soft)
     params = {}
     for k, v in sd.items():
-        if v.is_floating_point() and 'running' not in k:
-            sd[k] = v.clone().requires_grad_(True)
-            params[k] = sd[k]
-    out = O.forward(sd, _cfg(T), ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'],
-                    training=True)
+        if v.is_floating_point():
+            v = v.clone().to(dtype)
+            if 'running' not in k:
+                v.requires_grad_(True)
+                params[k] = v
+            sd[k] = v
+    over = None
+    if ours is not None and not soft:
+        over = {i: O.recurrent_mask(ours[i - 1].float().cpu(), cfg).to(dtype) for i in range(1, T)}
+    cast = lambda x: [[t.to(dtype) for t in way] for way in x]
+    out = O.forward(sd, cfg, cast(ep['supp_imgs']), cast(ep['fore_mask']), cast(ep['back_mask']), [t.to(dtype) for t in ep['qry_imgs']],
+                    ep['appr_query_labels'].to(dtype), training=True, mask_override=over)
     loss = O.train_loss(out, ep['query_labels'])
     loss.backward()
     return out, loss.detach(), params
 
 
-def _check_train_logits(got, refs):
-    """got: [T, B, P, H, W] device tensor; refs: list of T reference logits.  Strict per-iteration comparison while the
-    recurrent masks agree; after a near-tie flip only the flipped fraction is bounded."""
-    masks_agree = True
+def _check_train_logits(got, refs, tol=LOGIT_TOL):
+    """got: [T, B, P, H, W] device tensor; refs: list of T (teacher-forced) reference logits: every iteration is gated."""
+    from rpnet_b200 import parity
     for i, ref in enumerate(refs):
-        g = got[i].float().cpu()
-        if masks_agree:
-            rel = ((g - ref).abs().max() / ref.abs().max()).item()
-            assert rel < LOGIT_TOL, ('logits', i, rel)
-        flipped = ((g[:, 1:].sum(1) > g[:, 0]) != (ref[:, 1:].sum(1) > ref[:, 0])) if g.shape[1] == 2 else (g.argmax(1) != ref.argmax(1))
-        assert flipped.float().mean().item() < 2e-3, ('mask flips', i, flipped.float().mean().item())
-        top2 = ref.topk(2, dim=1).values
-        assert not (flipped & ((top2[:, 0] - top2[:, 1]) > 4 * LOGIT_TOL * ref.abs().max())).any() or not masks_agree, \
-            'argmax differs away from ties at iteration %d' % i
-        masks_agree = masks_agree and not flipped.any()
-    return masks_agree
+        r = parity.compare_logits(got[i].float().cpu(), ref.float())
+        assert r['rel_linf'] < tol and r['margin_rel_err'] < 2 * tol, ('logits', i, r)
+        assert r['argmax_mismatch'] < 2e-3, ('mask flips', i, r)
+        top2 = ref.float().topk(2, dim=1).values
+        far = (top2[:, 0] - top2[:, 1]) > 4 * tol * ref.abs().max()
+        assert not ((got[i].float().cpu().argmax(1) != ref.argmax(1)) & far).any(), 'argmax differs away from ties at iteration %d' % i
 
 
-def _check_grads(net, ref_grads, cond_grads=None, tol=3e-2):
-    """ref_grads: name -> fp32-oracle gradient (or None).  cond_grads: name -> gradient of the storage-matched oracle.
-
-    The reference's gradient is ill-conditioned at random init (measured on the fp32 oracle itself, 2 x 64 x 64, T=2: a
-    1e-6 relative perturbation of its activations moves encoder weight gradients by 1e-3, 1e-5 moves them by 4e-2 and the
-    5e-4 of fp16 storage by 0.2-0.3 — ReLU / max-pool gate flips and near-constant BatchNorm channels).  A fixed tolerance
-    therefore says nothing; the bound used is the movement fp16 storage alone causes in the oracle:
-        |g - g_fp32| <= 1.5 * |g_storage16 - g_fp32| + tol * |g_fp32|        per parameter tensor,
-    plus cosine >= 0.9 and norm within 20 % everywhere.  Without cond_grads the plain `tol` bound applies.
+def _check_grads(net, ref_grads, enc_tol, head_tol, first_tol=None):
+    """Fixed per-tensor bounds on the gradient rel-L2 against the fp32 oracle: `head_tol` for cre.*, `enc_tol` for encoder.*
+    (`first_tol` for encoder.Conv1.*, the worst-conditioned layers), plus cosine >= 0.98 everywhere.
     Conv biases in front of batch-statistics BN have an exactly-zero gradient (the reference holds rounding noise)."""
-    worst = 0.0
+    worst = {}
     for name, p in net.named_parameters():
         rg = ref_grads[name]
         if rg is None:
             assert name.startswith(('cre.w_context', 'cre.out')), name           # SURVEY D4
             assert p.grad is None, name
             continue
-        g = p.grad.float().cpu()
+        g, rg = p.grad.float().cpu(), rg.float()
         if name.endswith('.bias') and ('.conv.0.' in name or '.conv.3.' in name or '.up.1.' in name or name in
                                        ('cre.w_k.0.bias', 'cre.w_q.0.bias', 'cre.q.0.bias')):
             assert g.abs().max().item() <= 1e-6 + 10 * rg.abs().max().item(), name
             continue
         rel = ((g - rg).norm() / rg.norm().clamp_min(1e-12)).item()
-        bound = tol
-        if cond_grads is not None:
-            bound = tol + 1.5 * ((cond_grads[name] - rg).norm() / rg.norm().clamp_min(1e-12)).item()
-        worst = max(worst, rel)
-        assert rel < bound, '%s: gradient rel-L2 %.3e (bound %.3e)' % (name, rel, bound)
+        tol = head_tol if name.startswith('cre.') else (first_tol if (first_tol and name.startswith('encoder.Conv1.')) else enc_tol)
+        worst[name] = rel
+        assert rel < tol, '%s: gradient rel-L2 %.3e (bound %.1e)' % (name, rel, tol)
         cos = (g.flatten() @ rg.flatten() / (g.norm() * rg.norm()).clamp_min(1e-30)).item()
-        assert cos > 0.9 and abs(g.norm().item() / rg.norm().item() - 1) < 0.2, (name, cos, g.norm().item(), rg.norm().item())
+        assert cos > 0.98, (name, cos)
     return worst
 
 
@@ -125,9 +114,16 @@ def test_train_step_vs_reference_golden(dev, golden):
     ts = TrainStep(net)
     loss = ts.forward_backward(to_device(ep, dev))
     torch.cuda.synchronize()
-    _check_train_logits(ts.last['logits'], [torch.from_numpy(g['out%d' % i]) for i in range(T)])
+    # the golden logits are the reference's free-running iterations: gate every iteration up to the first hard-mask flip
+    from rpnet_b200 import parity
+    for i in range(T):
+        ref = torch.from_numpy(g['out%d' % i])
+        r = parity.compare_logits(ts.last['logits'][i].float().cpu(), ref)
+        assert r['rel_linf'] < LOGIT_TOL, ('golden logits', i, r)
+        if r['argmax_mismatch'] > 0:
+            break
     ref_loss = float(g['loss'])
-    assert abs(loss.item() - ref_loss) / abs(ref_loss) < 2e-3, (loss.item(), ref_loss)
+    assert abs(loss.item() - ref_loss) / abs(ref_loss) < 1e-3, (loss.item(), ref_loss)
     assert abs(ts.last['align_loss'].item() - float(g['align'])) < 2e-3 * max(1.0, abs(float(g['align'])))
     named = dict(net.named_parameters())
     for name, n_ref, head in zip(g['names'], g['grad_norm'], g['grad_head']):
@@ -149,34 +145,78 @@ def test_train_step_vs_reference_golden(dev, golden):
     assert int(net.state_dict()['cre.w_k.1.num_batches_tracked']) == 1 + T
 
 
-@pytest.mark.parametrize('ways,shots,B,size,T', [(1, 1, 2, 64, 2), (2, 2, 2, 64, 2), (1, 5, 2, 64, 3), (1, 1, 1, 128, 1), (1, 1, 1, 256, 1)])
-def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T):
+@pytest.mark.parametrize('ways,shots,B,size,T,soft', [(1, 1, 2, 64, 2, False), (2, 2, 2, 64, 2, False), (1, 5, 2, 64, 3, False),
+                                                      (1, 1, 1, 128, 1, False), (1, 1, 1, 256, 1, False),
+                                                      (1, 1, 2, 64, 3, True), (2, 2, 2, 64, 2, True)])
+def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T, soft):
+    """Random-initialisation fixtures (ill conditioned, see the module docstring): logits 1e-3, loss 1e-3, running statistics,
+    head gradients 3e-2, encoder gradients 0.15 + cosine.  soft=True: `soft_mask: True` (the gradient also flows through the
+    recurrent mask, net/rp_net.py:308-311)."""
     from oracle import weights
     from rpnet_b200.synthetic import make_episode, to_device
     from rpnet_b200.train import TrainStep
     sd = weights.unet_rpnet_state_dict(0)
     ep = make_episode(B, ways, shots, size, seed=7)
+    net = _net({k: v.clone() for k, v in sd.items()}, T, dev, soft)
+    ts = TrainStep(net)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    out, ref_loss, params = _oracle_step(sd, T, ep, ours=ts.last['logits'], soft=soft)
+    _check_train_logits(ts.last['logits'], [out['refinement'][i].detach() for i in range(T)])
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-3
+    ref_grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
+    _check_grads(net, ref_grads, enc_tol=0.15, head_tol=3e-2)
+    for k, v in net.state_dict().items():
+        if 'running' in k:
+            torch.testing.assert_close(v.cpu(), sd[k].detach(), rtol=1e-3, atol=1e-3, msg=k)
+        elif 'num_batches' in k:
+            assert int(v) == int(sd[k]), k
+
+
+def test_soft_mask_gradient_differs_from_hard(dev):
+    """The soft-mask backward really carries the extra path: with identical inputs its encoder / cre gradients differ from the
+    hard-mask ones by far more than the parity tolerance (a backward that ignored the mask path would reproduce the hard one)."""
+    from oracle import weights
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    sd = weights.unet_rpnet_state_dict(0)
+    d = to_device(make_episode(2, 1, 1, 64, seed=7), dev)
+    grads = []
+    for soft in (False, True):
+        net = _net({k: v.clone() for k, v in sd.items()}, 3, dev, soft)
+        ts = TrainStep(net)
+        ts.forward_backward(d)
+        torch.cuda.synchronize()
+        grads.append(net.cre.w_k[0].weight.grad.clone())
+    assert ((grads[0] - grads[1]).norm() / grads[0].norm()).item() > 5e-2
+
+
+def test_train_grads_fitted_fixture(dev):
+    """Well-conditioned gradient fixture: weights after 100 Adam steps (lr 1e-3) of the B200 train step on other episodes,
+    8 x 128 x 128, T = 2.  First the conditioning itself: the oracle's fp32 and fp64 gradients agree to 1e-5 (2e-3 in
+    encoder.Conv1, whose flat-background ReLU / max-pool ties stay touchy).  Then fixed per-tensor bounds on ours against the
+    fp32 oracle: head (cre.*) 5e-3, encoder 1.5e-2, encoder.Conv1 4e-2 (measured: <= 3.6e-3 / 8.8e-3 / 2.7e-2)."""
+    from oracle import weights
+    from rpnet_b200.synthetic import fitted_state_dict, make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    T, B, size = 2, 8, 128
+    net0 = _net(weights.unet_rpnet_state_dict(0), T, dev)
+    sd = fitted_state_dict(net0, lambda i: to_device(make_episode(B, 1, 1, size, seed=1000 + i), dev), steps=100, lr=1e-3)
+    ep = make_episode(B, 1, 1, size, seed=7)
     net = _net({k: v.clone() for k, v in sd.items()}, T, dev)
     ts = TrainStep(net)
     loss = ts.forward_backward(to_device(ep, dev))
     torch.cuda.synchronize()
-    sd16 = {k: v.clone() for k, v in sd.items()}
-    out, ref_loss, params = _oracle_step(sd, T, ep)
-    out16, _, params16 = _oracle_step(sd16, T, ep, storage='b200')
-    agree = _check_train_logits(ts.last['logits'], [out['refinement'][i].detach() for i in range(T)])
-    if agree:       # storage-matched oracle: only accumulation order differs
-        for i in range(T):
-            ref = out16['refinement'][i].detach()
-            rel = ((ts.last['logits'][i].cpu() - ref).abs().max() / ref.abs().max()).item()
-            assert rel < 6e-3, ("logits vs storage-matched oracle", i, rel)
-    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 2e-3
-    ref_grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
-    _check_grads(net, ref_grads, {k: p.grad for k, p in params16.items()})
-    for k, v in net.state_dict().items():
-        if 'running' in k:
-            torch.testing.assert_close(v.cpu(), sd[k], rtol=1e-3, atol=1e-3, msg=k)
-        elif 'num_batches' in k:
-            assert int(v) == int(sd[k]), k
+    out, ref_loss, p32 = _oracle_step({k: v.clone() for k, v in sd.items()}, T, ep, ours=ts.last['logits'])
+    _, _, p64 = _oracle_step({k: v.clone() for k, v in sd.items()}, T, ep, ours=ts.last['logits'], dtype=torch.float64)
+    for k, p in p32.items():
+        if p.grad is None or p.grad.norm() < 1e-4:
+            continue
+        cond = ((p.grad.double() - p64[k].grad).norm() / p64[k].grad.norm()).item()
+        assert cond < (2e-3 if k.startswith('encoder.Conv1.') else 1e-5 * 5), ('fixture conditioning', k, cond)
+    _check_train_logits(ts.last['logits'], [out['refinement'][i].detach() for i in range(T)])
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-3
+    _check_grads(net, {k: p.grad for k, p in p32.items()}, enc_tol=1.5e-2, head_tol=5e-3, first_tol=4e-2)
 
 
 def test_adam_step_and_eval_after_training(dev):
@@ -251,11 +291,9 @@ def test_module_train_forward_is_differentiable(dev):
     loss = sum(dice_ce(out['refinement'][i], d['query_labels']) for i in range(T)) + 1.0 * out['align_loss']
     loss.backward()
     torch.cuda.synchronize()
-    sd16 = {k: v.clone() for k, v in sd.items()}
-    ref_out, ref_loss, params = _oracle_step(sd, T, ep)
-    _, _, params16 = _oracle_step(sd16, T, ep, storage='b200')
-    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 2e-3
-    _check_grads(net, {k: p.grad for k, p in params.items()}, {k: p.grad for k, p in params16.items()})
+    ref_out, ref_loss, params = _oracle_step(sd, T, ep, ours=[out['refinement'][i].detach() for i in range(T)])
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-3
+    _check_grads(net, {k: p.grad for k, p in params.items()}, enc_tol=0.15, head_tol=3e-2)
     # a second backward pass accumulates into p.grad like autograd does for the reference
     g1 = net.encoder.Conv3.conv[0].weight.grad.clone()
     out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
