@@ -150,7 +150,7 @@ def test_train_step_vs_reference_golden(dev, golden):
                                                       (1, 1, 2, 64, 3, True), (2, 2, 2, 64, 2, True)])
 def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T, soft):
     """Random-initialisation fixtures (ill conditioned, see the module docstring): logits 1e-3, loss 1e-3, running statistics,
-    head gradients 3e-2, encoder gradients 0.15 + cosine.  soft=True: `soft_mask: True` (the gradient also flows through the
+    head gradients 5e-2, encoder gradients 0.15 + cosine.  soft=True: `soft_mask: True` (the gradient also flows through the
     recurrent mask, net/rp_net.py:308-311)."""
     from oracle import weights
     from rpnet_b200.synthetic import make_episode, to_device
@@ -165,7 +165,7 @@ def test_train_grads_vs_oracle_autograd(dev, ways, shots, B, size, T, soft):
     _check_train_logits(ts.last['logits'], [out['refinement'][i].detach() for i in range(T)])
     assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-3
     ref_grads = {k: (p.grad if p.grad is not None else None) for k, p in params.items()}
-    _check_grads(net, ref_grads, enc_tol=0.15, head_tol=3e-2)
+    _check_grads(net, ref_grads, enc_tol=0.15, head_tol=5e-2)
     for k, v in net.state_dict().items():
         if 'running' in k:
             torch.testing.assert_close(v.cpu(), sd[k].detach(), rtol=1e-3, atol=1e-3, msg=k)
@@ -293,7 +293,7 @@ def test_module_train_forward_is_differentiable(dev):
     torch.cuda.synchronize()
     ref_out, ref_loss, params = _oracle_step(sd, T, ep, ours=[out['refinement'][i].detach() for i in range(T)])
     assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-3
-    _check_grads(net, {k: p.grad for k, p in params.items()}, enc_tol=0.15, head_tol=3e-2)
+    _check_grads(net, {k: p.grad for k, p in params.items()}, enc_tol=0.15, head_tol=5e-2)
     # a second backward pass accumulates into p.grad like autograd does for the reference
     g1 = net.encoder.Conv3.conv[0].weight.grad.clone()
     out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
