@@ -118,6 +118,13 @@ int rpnet_bn_apply_split_f16(const void* z_hi, const void* z_lo, const float* st
 int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
                                  void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream);
 int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream);
+/* rpnet_pack_conv_weight_split for every conv of the model in ONE launch (the packs follow every optimizer step): descs_host is
+ * a HOST array of n (<= 40) layer descriptors with the arguments of rpnet_pack_conv_weight_split (device pointers inside). */
+typedef struct {
+  const float* w; void* w_fwd_f16; void* w_dgrad_bf16;
+  int cout, cin_real, ntaps, hole_start, hole_len, split;
+} rpnet_pack_desc;
+int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, void* stream);
 /* rpnet_maxpool_f16 on a split-fp16 activation: the maximum of hi + lo, written back as hi / lo planes (VGG pools between split convs). */
 int rpnet_maxpool_split_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int n, int h, int w, int c, int k,
                             int stride, int pad, void* stream);

@@ -11,6 +11,14 @@
 
 #include <cstdlib>
 
+extern "C" {
+// include/rpnet_b200.h
+typedef struct {
+  const float* w; void* w_fwd_f16; void* w_dgrad_bf16;
+  int cout, cin_real, ntaps, hole_start, hole_len, split;
+} rpnet_pack_desc;
+}
+
 namespace rpnet {
 
 constexpr int kMaxGroups = 64;
@@ -767,13 +775,12 @@ __global__ void soft_mask_bwd_kernel(const float* __restrict__ logits, const flo
 // One block per 32 (cout) x 32 (cin) tile: the fp32 weights of the tile (32 x 32 x taps, contiguous runs of 32 * taps floats
 // per cout) are staged in shared memory, so that both packs leave as coalesced rows — wf rows run along cin, the transposed
 // wd rows along cout.
-__global__ void __launch_bounds__(256)
-pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
-                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int split) {
-  __shared__ float s_w[32][32 * 9 + 1];                           // [co][ci * ntaps + t]
+__device__ __forceinline__ void pack_conv_weight_tile(float (*s_w)[32 * 9 + 1], int tile, const float* __restrict__ w, int cout, int cin,
+                                                      int ntaps, int hole_start, int hole_len, __half* __restrict__ wf,
+                                                      __nv_bfloat16* __restrict__ wd, int split) {
   const int cin_real = cin - hole_len;
   const int tiles_ci = (cin + 31) / 32;
-  const int co0 = (blockIdx.x / tiles_ci) * 32, ci0 = (blockIdx.x % tiles_ci) * 32;
+  const int co0 = (tile / tiles_ci) * 32, ci0 = (tile % tiles_ci) * 32;
   // stage: thread -> (co, element of the run); packed channel ci maps to the real channel (padding hole = zeros)
   for (int i = threadIdx.x; i < 32 * 32 * ntaps; i += 256) {
     const int co = i / (32 * ntaps), r = i % (32 * ntaps);
@@ -804,6 +811,27 @@ pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntap
         wd[((size_t)t * cin + ci0 + r) * cout + co0 + lane] = __float2bfloat16_rn(s_w[lane][r * ntaps + t]);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int ntaps, int hole_start, int hole_len,
+                        __half* __restrict__ wf, __nv_bfloat16* __restrict__ wd, int split) {
+  __shared__ float s_w[32][32 * 9 + 1];                           // [co][ci * ntaps + t]
+  pack_conv_weight_tile(s_w, blockIdx.x, w, cout, cin, ntaps, hole_start, hole_len, wf, wd, split);
+}
+
+// Every conv of the model in ONE launch (the packs run after each optimizer step: twenty small launches were launch bound):
+// block b works on tile b - first_tile[l] of layer l.
+constexpr int kMaxPackLayers = 40;
+struct PackLayer { const float* w; __half* wf; __nv_bfloat16* wd; int cout, cin, ntaps, hole_start, hole_len, split, first_tile; };
+struct PackTable { int n; PackLayer l[kMaxPackLayers]; };
+__global__ void __launch_bounds__(256)
+pack_conv_weights_kernel(const __grid_constant__ PackTable t) {
+  __shared__ float s_w[32][32 * 9 + 1];
+  int l = 0;
+  while (l + 1 < t.n && (int)blockIdx.x >= t.l[l + 1].first_tile) ++l;
+  const PackLayer& L = t.l[l];
+  pack_conv_weight_tile(s_w, (int)blockIdx.x - L.first_tile, L.w, L.cout, L.cin, L.ntaps, L.hole_start, L.hole_len, L.wf, L.wd, L.split);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1168,6 +1196,27 @@ RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_rea
   pack_conv_weight_kernel<<<tiles, 256, 0, stream>>>(w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16),
                                                      static_cast<__nv_bfloat16*>(w_dgrad_bf16), split);
   return check_cuda(cudaGetLastError(), "pack_conv_weight launch");
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(descs_host && n >= 1 && n <= kMaxPackLayers, "pack_conv_weights: 1..%d layers (got %d)", kMaxPackLayers, n);
+  PackTable t;
+  t.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const rpnet_pack_desc& d = descs_host[i];
+    RPNET_REQUIRE(d.w && (d.w_fwd_f16 || d.w_dgrad_bf16) && d.cout > 0 && d.cin_real > 0 && d.ntaps > 0 && d.ntaps <= 9 && d.hole_len >= 0 &&
+                  d.hole_start >= 0 && d.hole_start <= d.cin_real, "pack_conv_weights: bad layer %d", i);
+    PackLayer& L = t.l[i];
+    L.w = d.w; L.wf = static_cast<__half*>(d.w_fwd_f16); L.wd = static_cast<__nv_bfloat16*>(d.w_dgrad_bf16);
+    L.cout = d.cout; L.cin = d.cin_real + d.hole_len; L.ntaps = d.ntaps; L.hole_start = d.hole_start; L.hole_len = d.hole_len;
+    L.split = d.split; L.first_tile = tiles;
+    tiles += ((L.cout + 31) / 32) * ((L.cin + 31) / 32);
+  }
+  pack_conv_weights_kernel<<<tiles, 256, 0, stream>>>(t);
+  return check_cuda(cudaGetLastError(), "pack_conv_weights launch");
 }
 
 RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch576,

@@ -442,6 +442,32 @@ def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):
                                                     _ptr(w_dgrad), _stream()), 'rpnet_pack_conv_weight_split')
 
 
+class _PackDesc(ctypes.Structure):          # rpnet_pack_desc of include/rpnet_b200.h
+    _fields_ = [('w', ctypes.c_void_p), ('w_fwd_f16', ctypes.c_void_p), ('w_dgrad_bf16', ctypes.c_void_p), ('cout', ctypes.c_int),
+                ('cin_real', ctypes.c_int), ('ntaps', ctypes.c_int), ('hole_start', ctypes.c_int), ('hole_len', ctypes.c_int),
+                ('split', ctypes.c_int)]
+
+
+def pack_conv_weights(layers):
+    """layers: list of (w fp32 [cout, cin_real, kh, kw], w_fwd fp16 or None, w_dgrad bf16 or None, hole (start, len), split) -> every
+    pack in one launch (rpnet_pack_conv_weights).  Returns the descriptor array (cache it: the pointers do not change)."""
+    arr = (_PackDesc * len(layers))()
+    nbytes = 0
+    for d, (w, wf, wd, hole, split) in zip(arr, layers):
+        _req(w, torch.float32, 'w')
+        d.w, d.w_fwd_f16, d.w_dgrad_bf16 = w.data_ptr(), (wf.data_ptr() if wf is not None else None), (wd.data_ptr() if wd is not None else None)
+        d.cout, d.cin_real, d.ntaps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+        d.hole_start, d.hole_len, d.split = int(hole[0]), int(hole[1]), int(bool(split))
+        nbytes += w.numel() * 8
+    return arr, nbytes
+
+
+def run_pack_conv_weights(arr, nbytes):
+    lib = _lib.load()
+    with _Timed('pack_conv_weight', float(nbytes)):
+        _lib.check(lib.rpnet_pack_conv_weights(ctypes.cast(arr, ctypes.c_void_p), len(arr), _stream()), 'rpnet_pack_conv_weights')
+
+
 def conv_bnstats(src0, wpack, taps, ones, zeros, z, group_start, sums, src1=None):
     """Train-mode conv (no bias) -> z fp16 NHWC + BatchNorm statistics sums[g][cout][2] in the same launch."""
     lib = _lib.load()

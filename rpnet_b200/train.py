@@ -298,8 +298,15 @@ class TrainEngine:
         return t[:numel]
 
     def pack_weights(self):
+        """fp32 parameters -> the fp16 (split: Wh | Wl) forward and bf16 data-gradient packs, after every optimizer step: all
+        tap-list convs in one launch, the two sub-pixel up-conv packs in one launch each."""
+        if getattr(self, '_pack_table', None) is None:
+            layers = [(l.conv.weight.data, l.wf, l.wd, l.hole, l.w_split) for l in self.L.values() if not l.first]
+            self._pack_table = ops.pack_conv_weights(layers)
+        ops.run_pack_conv_weights(*self._pack_table)
         for l in self.L.values():
-            l.pack()
+            if l.up:
+                ops.pack_upconv_weight(l.conv.weight.data, l.wf_up, l.w16_up, split=l.w_split)
 
     # ------------------------------------------------------------------ encoder
     def pair(self, name, shape, lo):
