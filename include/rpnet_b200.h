@@ -129,13 +129,6 @@ int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, void* stre
 int rpnet_maxpool_split_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int n, int h, int w, int c, int k,
                             int stride, int pad, void* stream);
 
-/* Train-mode first conv (Cin = 1, encoder.Conv1.conv.0, net/unet.py:405): z = conv(img) in fp32 -> hi (+ lo, may be null) fp16 NHWC
- * planes AND the BatchNorm statistics of the fp32 results (sums fp64 [groups][64][2], zeroed here) in the same launch — the
- * statistics pass over the largest activation of the network (rpnet_bn_stats_f16) is not needed.  w: multiple of 8. */
-int rpnet_conv3x3_first_bnstats_f16(const float* img, int n, int h, int w, const float* weight, const float* ones,
-                                    const float* zeros, void* z_f16, void* z_lo_f16, const int* group_start, int groups,
-                                    double* sums, void* stream);
-
 /* F.avg_pool2d(mask[:, None], s): fp32 [n][h][w] -> fp32 [n][h/s][w/s].  net/rp_net.py:270,272. */
 int rpnet_avgpool_mask_f32(const float* in, float* out, int n, int h, int w, int s, void* stream);
 

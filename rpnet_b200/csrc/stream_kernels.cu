@@ -104,35 +104,11 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
 // Cin == 1 specialisation (encoder.Conv1.conv.0, net/unet.py:405): the 8 output channels a thread owns never change
 // (grid stride is a multiple of 8), so its 72 weights (scale folded in) live in registers; each thread produces two
 // horizontally adjacent pixels from a 3 x 4 image patch: 12 loads, 144 FMAs, two 16-byte stores.
-// STATS (train mode, scale = 1, shift = 0, no ReLU: the output is the pre-BatchNorm z): the kernel also accumulates the
-// BatchNorm statistics of its fp32 results per call group (images [g_start[g], g_start[g + 1])): per-thread fp32 partial sums,
-// folded over the four pixel lanes of a warp with shuffles, then fp64 atomics (exact for fp32 addends: order independent).
-struct FirstGroups { int G; int start[65]; };
-template <bool STATS>
 __global__ void __launch_bounds__(256)
 conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][1][3][3]*/,
                         const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
-                        __half* __restrict__ out_lo, int N, int H, int W, FirstGroups gr, double* __restrict__ sums /*[G][64][2]*/) {
+                        __half* __restrict__ out_lo, int N, int H, int W) {
   const int cg = threadIdx.x & 7;
-  float s1[8], s2[8];
-  int cur_g = 0;
-  if (STATS) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  }
-  auto flush = [&](int g) {                       // warp-uniform: every lane of a warp works on the same image
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = s1[j], b = s2[j];
-      a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
-      if ((threadIdx.x & 31) < 8) {
-        atomicAdd(sums + ((size_t)g * 64 + cg * 8 + j) * 2, (double)a);
-        atomicAdd(sums + ((size_t)g * 64 + cg * 8 + j) * 2 + 1, (double)b);
-      }
-      s1[j] = 0.f; s2[j] = 0.f;
-    }
-  };
   float wr[9][8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -147,10 +123,6 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
     const int x = (int)(pp % Wp) * 2;
     const int y = (int)((pp / Wp) % (unsigned)H);
     const long long n = pp / (Wp * (unsigned)H);
-    if (STATS && n >= gr.start[cur_g + 1]) {
-      flush(cur_g);
-      while (n >= gr.start[cur_g + 1]) ++cur_g;
-    }
     const float* plane = img + n * H * W;
     float v[3][4];
 #pragma unroll
@@ -179,15 +151,6 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a0[j] = fmaxf(a0[j], 0.f); a1[j] = fmaxf(a1[j], 0.f); }
     }
-    if (STATS) {
-      const bool two = x + 1 < W;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += a0[j] + (two ? a1[j] : 0.f);
-        s2[j] = fmaf(a0[j], a0[j], s2[j]);
-        if (two) s2[j] = fmaf(a1[j], a1[j], s2[j]);
-      }
-    }
     const long long pix = (n * H + y) * W + x;
     const uint4 h0 = pack8(a0), h1 = pack8(a1);
     *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = h0;
@@ -197,7 +160,6 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
       if (x + 1 < W) *reinterpret_cast<uint4*>(out_lo + (pix + 1) * 64 + cg * 8) = residual8_f16(a1, h1);
     }
   }
-  if (STATS) flush(cur_g);
 }
 
 // ResNet stem (torchvision resnet18.conv1 + bn1 + relu, reached through net/rp_net.py:19-37): 7x7 stride-2 pad-3 conv of a
@@ -688,29 +650,12 @@ RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, in
   const long long total = (long long)n * h * w * 8;
   const int grid = grid_for(total, 256);
   if (cin == 1)
-    conv3x3_first_c1_kernel<false><<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
-        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), n, h, w, FirstGroups{}, nullptr);
+    conv3x3_first_c1_kernel<<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
+        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), n, h, w);
   else
     conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
                                                       static_cast<__half*>(out_lo_f16), n, h, w);
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");
-}
-
-// See include/rpnet_b200.h for the contract.
-RPNET_API int rpnet_conv3x3_first_bnstats_f16(const float* img, int n, int h, int w, const float* weight, const float* ones,
-                                               const float* zeros, void* z_f16, void* z_lo_f16, const int* group_start, int groups,
-                                               double* sums, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  RPNET_REQUIRE(img && weight && ones && zeros && z_f16 && group_start && sums, "conv3x3_first_bnstats: null pointer argument");
-  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && w % 8 == 0, "conv3x3_first_bnstats: bad shape %d x %d x %d (w must be a multiple of 8)", n, h, w);
-  RPNET_REQUIRE(groups >= 1 && groups <= 64 && group_start[0] == 0 && group_start[groups] == n, "conv3x3_first_bnstats: bad call groups");
-  FirstGroups gr;
-  gr.G = groups;
-  for (int g = 0; g <= groups; ++g) gr.start[g] = group_start[g];
-  RPNET_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)groups * 64 * 2 * sizeof(double), stream));
-  conv3x3_first_c1_kernel<true><<<grid_for((long long)n * h * (w / 2) * 8, 256), 256, 0, stream>>>(
-      img, weight, ones, zeros, 0, static_cast<__half*>(z_f16), static_cast<__half*>(z_lo_f16), n, h, w, gr, sums);
-  return check_cuda(cudaGetLastError(), "conv3x3_first_bnstats launch");
 }
 
 RPNET_API int rpnet_conv7x7s2_stem_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,

@@ -133,22 +133,6 @@ def conv3x3_first(img, weight, scale, shift, relu, out, out_lo=None):
     _lib.check(rc, 'rpnet_conv3x3_first_split_f16')
 
 
-def conv3x3_first_bnstats(img, weight, ones, zeros, z, group_start, sums, z_lo=None):
-    """Train-mode Cin = 1 first conv: z (hi / lo planes) + its BatchNorm statistics in one launch."""
-    lib = _lib.load()
-    _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(z, torch.float16, 'z'); _req(sums, torch.float64, 'sums')
-    n, cin, h, w = img.shape
-    assert cin == 1 and tuple(weight.shape) == (64, 1, 3, 3) and tuple(z.shape) == (n, h, w, 64)
-    if z_lo is not None:
-        _req(z_lo, torch.float16, 'z_lo')
-        assert z_lo.shape == z.shape
-    gs, g = _groups(group_start)
-    assert sums.numel() >= g * 64 * 2
-    with _Timed('conv3x3_first', float(img.numel() * 4 + z.numel() * (2 if z_lo is None else 4))):
-        _lib.check(lib.rpnet_conv3x3_first_bnstats_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(ones), _ptr(zeros), _ptr(z), _ptr(z_lo), gs, g,
-                                                       _ptr(sums), _stream()), 'rpnet_conv3x3_first_bnstats_f16')
-
-
 def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=None, src1_lo=None, w_split=True, out=None,
                out_lo=None, out_pool=None, out_pool_lo=None, out_f32=None, out_map=None, out_coff=0, group_start=None, sums=None,
                keep_sums=False):

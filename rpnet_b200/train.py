@@ -205,9 +205,7 @@ class _ConvBN:
         bn = self.bn
         y = y or (None, None)
         pool = pool or (None, None)
-        if self.first and x0.shape[1] == 1 and w % 8 == 0:
-            ops.conv3x3_first_bnstats(x0, self.conv.weight.data, self.ones, self.zeros, z[0], gs, sums, z_lo=z[1])
-        elif self.first:
+        if self.first:
             ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z[0], out_lo=z[1])
             ops.bn_stats(z[0], gs, sums, z_lo=z[1])
         elif self.split:

@@ -187,28 +187,3 @@ def test_upconv_split_phases(dev):
     torch.cuda.synchronize()
     for ph, (wp, taps, _) in enumerate(phases):
         torch.testing.assert_close(wf[ph].float(), wp.float(), rtol=0, atol=2e-7)   # sums of taps in a different order
-
-
-def test_conv3x3_first_bnstats(dev):
-    """Train-mode first conv with the BatchNorm statistics fused (rpnet_conv3x3_first_bnstats_f16): z planes as the plain kernel,
-    sums == the separate statistics pass over z_hi + z_lo (two call groups, the boundary inside the batch)."""
-    from rpnet_b200 import ops
-    g = _gen(21)
-    n, h, w = 5, 24, 40
-    x = torch.randn(n, 1, h, w, generator=g)
-    wt = torch.randn(64, 1, 3, 3, generator=g) / 3
-    one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
-    gs = [0, 3, 5]
-    z, zl = (torch.empty(n, h, w, 64, dtype=torch.float16, device=dev) for _ in range(2))
-    sums = torch.full((2 * 64 * 2,), 7.0, dtype=torch.float64, device=dev)
-    ops.conv3x3_first_bnstats(x.to(dev), wt.to(dev), one, zero, z, gs, sums, z_lo=zl)
-    z2, zl2 = torch.empty_like(z), torch.empty_like(z)
-    ops.conv3x3_first(x.to(dev), wt.to(dev), one, zero, False, z2, out_lo=zl2)
-    s2 = torch.empty_like(sums)
-    ops.bn_stats(z2, gs, s2, z_lo=zl2)
-    torch.cuda.synchronize()
-    assert torch.equal(z, z2) and torch.equal(zl, zl2)
-    ref = F.conv2d(x.double(), wt.double(), None, padding=1)
-    want = torch.stack([torch.stack([ref[a:b].sum((0, 2, 3)), (ref[a:b] ** 2).sum((0, 2, 3))], dim=-1) for a, b in ((0, 3), (3, 5))])
-    torch.testing.assert_close(sums.view(2, 64, 2).cpu(), want, rtol=2e-6, atol=1e-6)
-    torch.testing.assert_close(sums, s2, rtol=1e-6, atol=1e-6)
