@@ -114,17 +114,32 @@ bn_stats_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, Gro
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-  for (long long p = p0 + (long long)bx * lanes + pl; p < p1; p += (long long)nbx * lanes) {
-    float f[8];
-    unpack8_f16(__ldg(z + p * c8 + v), f);
-    if (z_lo) {                                   // split-fp16 z = hi + lo
-      float l[8];
-      unpack8_f16(__ldg(z_lo + p * c8 + v), l);
+  constexpr int U = 4;                          // pixels per thread and iteration: all loads go out before the math
+  const long long stride = (long long)nbx * lanes;
+  for (long long pb = p0 + (long long)bx * lanes + pl; pb < p1; pb += U * stride) {
+    uint4 zh[U], zl[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += l[j];
+    for (int k = 0; k < U; ++k) {
+      const long long p = pb + k * stride;
+      if (p < p1) {
+        zh[k] = __ldg(z + p * c8 + v);
+        if (z_lo) zl[k] = __ldg(z_lo + p * c8 + v);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+    for (int k = 0; k < U; ++k) {
+      if (pb + k * stride >= p1) break;
+      float f[8];
+      unpack8_f16(zh[k], f);
+      if (z_lo) {                                 // split-fp16 z = hi + lo
+        float l[8];
+        unpack8_f16(zl[k], l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += l[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] = fmaf(f[j], f[j], s2[j]); }
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s_red[threadIdx.x * 16 + j] = s1[j]; s_red[threadIdx.x * 16 + 8 + j] = s2[j]; }
