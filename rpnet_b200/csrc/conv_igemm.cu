@@ -46,6 +46,7 @@ struct ConvParams {
   int ntaps;
   int dy[kMaxTaps], dx[kMaxTaps];
   int tap_src[kMaxTaps];          // -1: channel concat of source 0 | source 1 (default); 0..3: the tap reads that source only
+  int halo_tap[9];                // HALO kernels: tap index of offset (dy, dx) = (i / 3 - 1, i % 3 - 1) in the weight pack
   const float* scale;             // per-cout epilogue: y = acc * scale + shift
   const float* shift;
   int relu;
@@ -87,12 +88,18 @@ struct ConvParams {
 // layers are bound by the L2 -> SM feed (ncu: 9.4 TB/s of TMA reads, a third of them the same 72 KB of weights re-fetched for
 // every pixel tile): 1118 -> 964 us on the 96 x 256 x 256 layer.  (Combined with CTA pairs: no further gain — at N = 64 the MMA rate
 // itself is the floor.)
+// HALO == 1 (full 3x3 tap sets on 16 x 8 pixel tiles, cout tiles of 64 / 128): a stage carries the activation box of ONE column
+// offset dx with a one-row halo above and below — (8 + 2) x 16 pixels x 64 channels — plus the three weight tiles of the taps
+// (dy, dx), dy = -1, 0, 1; the three row offsets are views of the same box 16 rows (2048 B, swizzle-atom aligned) apart.  A
+// pixel tile then pulls 3 x 20 KB of activations per 64-channel chunk through the L2 -> SM path instead of 9 x 16 KB: the
+// small-channel full-resolution layers (Conv1.conv.3, Conv2.*) are bound by exactly that feed, three-fold so in split-fp16.
 constexpr int kWsMaxKb = 9;
-template <int BN, int CTAS = 1, int WS = 0>
+constexpr int kHaloRows = (8 + 2) * 16;
+template <int BN, int CTAS = 1, int WS = 0, int HALO = 0>
 struct ConvCfg {
-  static constexpr int kABytes = kBM * kBK * 2;                  // 16 KB
+  static constexpr int kABytes = (HALO ? kHaloRows : kBM) * kBK * 2;   // 16 KB (20 KB with the halo rows)
   static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
-  static constexpr int kStageBytes = WS ? kABytes : kABytes + kBBytes;
+  static constexpr int kStageBytes = WS ? kABytes : kABytes + (HALO ? 3 : 1) * kBBytes;
   static constexpr int kResidentBytes = WS ? kWsMaxKb * kBBytes : 0;
   static constexpr int kStages = ((kSmemBudget - kResidentBytes) / kStageBytes) > 8 ? 8 : ((kSmemBudget - kResidentBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
@@ -101,12 +108,13 @@ struct ConvCfg {
                                     kMaxBnCout * 2 * 8 /*fused BN statistics*/;
 };
 
-template <int BN, int CTAS, int WS>
+template <int BN, int CTAS, int WS, int HALO = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_constant__ CUtensorMap tm_src1,
                   const __grid_constant__ CUtensorMap tm_src2, const __grid_constant__ CUtensorMap tm_src3,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
-  using Cfg = ConvCfg<BN, CTAS, WS>;
+  using Cfg = ConvCfg<BN, CTAS, WS, HALO>;
+  static_assert(!(HALO && WS), "the halo variant streams its weights");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -125,7 +133,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kblocks_per_tap = p.kblocks_per_tap;
-  const int num_kb = p.ntaps * kblocks_per_tap;
+  const int num_kb = (HALO ? 3 : p.ntaps) * kblocks_per_tap;      // stages per tile
   const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   // work unit = CTAS consecutive pixel tiles x one cout tile; CTA `cta_rank` of the pair owns pixel tile unit * CTAS + cta_rank
   // (past the end for the odd one out: its loads are out of bounds = zeros and its pixels fail the `valid` test)
@@ -188,6 +196,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         const int ty = mt % p.tiles_y;
         const int tn = mt / p.tiles_y;
         const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
+        if (HALO) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            for (int s = 0; s < p.nseg; ++s) {
+              const int mi = p.seg_map[s];
+              const CUtensorMap* tm = mi == 0 ? &tm_src0 : (mi == 1 ? &tm_src1 : (mi == 2 ? &tm_src2 : &tm_src3));
+              const int ach0 = p.seg_ach[s], wch0 = p.seg_wch[s], sn = p.seg_n[s];
+              for (int j = 0; j < sn; ++j) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_dst = tiles + stage * Cfg::kStageBytes;
+                uint8_t* b_dst = a_dst + Cfg::kABytes;
+                if (CTAS == 2) {
+                  if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                  tma_load_4d_pair(tm, &full_bar[stage], a_dst, (ach0 + j) * kBK, x0 + dxi - 1, y0 - 1, n0);
+#pragma unroll
+                  for (int dyi = 0; dyi < 3; ++dyi)
+                    tma_load_3d_pair(&tm_w, &full_bar[stage], b_dst + dyi * Cfg::kBBytes, (wch0 + j) * kBK,
+                                     ct * BN + (int)cta_rank * (BN / 2), p.halo_tap[dyi * 3 + dxi]);
+                } else {
+                  mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                  tma_load_4d(tm, &full_bar[stage], a_dst, (ach0 + j) * kBK, x0 + dxi - 1, y0 - 1, n0);
+#pragma unroll
+                  for (int dyi = 0; dyi < 3; ++dyi)
+                    tma_load_3d(&tm_w, &full_bar[stage], b_dst + dyi * Cfg::kBBytes, (wch0 + j) * kBK, ct * BN, p.halo_tap[dyi * 3 + dxi]);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+        } else
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
           const int ts = p.tap_src[tap];
@@ -234,6 +271,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
+          if (HALO) {
+            // three row offsets of the same halo box: 16 pixel rows = 2048 B apart (whole swizzle atoms), one weight tile each
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t a_desc = umma_desc_sw128(a_addr + dyi * 16 * 128, 1024);
+              const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + dyi * Cfg::kBBytes, 1024);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | dyi | k) != 0);
+                else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | dyi | k) != 0);
+              }
+            }
+          } else {
           const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
           const uint64_t b_desc = umma_desc_sw128(WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes, 1024);
 #pragma unroll
@@ -241,6 +291,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
             if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
             else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
           }
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
           if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3);
@@ -565,6 +616,44 @@ static int launch_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUten
   return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, 2, 0>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (CTA pair) launch");
 }
 
+// Halo launches: single CTA for 64-wide cout tiles, CTA pair for 128-wide ones (a pair halves the three weight tiles per CTA).
+static int launch_halo64(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
+                         const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<64, 1, 0, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles_c;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_igemm_kernel<64, 1, 0, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
+  return check_cuda(cudaGetLastError(), "conv_igemm_kernel (halo) launch");
+}
+
+static int launch_halo128_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3,
+                               const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<128, 2, 0, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128, 2, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int units = ((p.tiles_x * p.tiles_y * p.tiles_n + 1) / 2) * p.n_tiles_c;
+  const int pairs = units < num_sms() / 2 ? units : num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<128, 2, 0, 1>, t0, t1, t2, t3, tw, p), "conv_igemm_kernel (halo, CTA pair) launch");
+}
+
 // RPNET_CONV_2CTA: bit mask of the cout tile widths that run as CTA pairs (1: 256, 2: 128, 4: 64).  Default 1: measured on
 // B200, pairs gain 10 % at BN = 256 (1344 -> 1479 TF/s) and nothing at 128 / 64 — those layers are bound by the L2 -> SM feed of
 // the nine per-tap activation boxes, not by MMA issue or operand reads.
@@ -690,8 +779,20 @@ static int conv_igemm_run(const ConvCall& a) {
                   "conv_igemm: output mapping exceeds the %d x %d output", a.out_h, a.out_w);
   }
 
+  // halo variant: a full 3x3 tap set (any order / sign: forward and data-gradient packs) on 16 x 8 pixel tiles, cout tiles 64 / 128
+  bool halo = ntaps == 9 && !a.tap_src && bw == 16 && bh == 8 && bn == 1 && h >= bh + 2 && BN <= 128 && !a.res && !getenv("RPNET_CONV_NO_HALO");
+  if (halo) {
+    for (int i = 0; i < 9; ++i) p.halo_tap[i] = -1;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = a.tap_dy[t], dx = a.tap_dx[t];
+      if (dy < -1 || dy > 1 || dx < -1 || dx > 1) { halo = false; break; }
+      p.halo_tap[(dy + 1) * 3 + dx + 1] = t;
+    }
+    for (int i = 0; i < 9 && halo; ++i) halo = p.halo_tap[i] >= 0;
+    if (BN == 128 && p.tiles_x * p.tiles_y * p.tiles_n < 2) halo = false;
+  }
   CUtensorMap t0, t1, t2, t3, tw;
-  const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  const uint32_t abox[4] = {(uint32_t)kBK, (uint32_t)bw, (uint32_t)(halo ? bh + 2 : bh), (uint32_t)bn};
   if (a.tap_src) {
     // four strided views of one tensor (the parity phases of a 2x up-sampled map): same dims, custom pixel strides
     CUtensorMap* tv[4] = {&t0, &t1, &t2, &t3};
@@ -719,9 +820,9 @@ static int conv_igemm_run(const ConvCall& a) {
       t3 = t0;
     }
   }
-  const bool ws = cout == 64 && !a_split && !a.w_split && ntaps * p.kblocks_per_tap <= kWsMaxKb &&
+  const bool ws = !halo && cout == 64 && !a_split && !a.w_split && ntaps * p.kblocks_per_tap <= kWsMaxKb &&
                   p.tiles_x * p.tiles_y * p.tiles_n >= 4 * num_sms() && !getenv("RPNET_CONV_NO_WS");
-  const bool pair = !ws && pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2;
+  const bool pair = halo ? BN == 128 : (!ws && pair_enabled(BN) && p.tiles_x * p.tiles_y * p.tiles_n >= 2);
   {
     const uint64_t cin = (uint64_t)(c0 + c1) * (a.w_split ? 2 : 1);
     const uint64_t dims[3] = {cin, (uint64_t)cout, (uint64_t)ntaps};
@@ -730,6 +831,7 @@ static int conv_igemm_run(const ConvCall& a) {
     int rc = make_tmap_2b(&tw, a.wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
   }
+  if (halo) return BN == 128 ? launch_halo128_pair(t0, t1, t2, t3, tw, p, stream) : launch_halo64(t0, t1, t2, t3, tw, p, stream);
   if (pair) {
     switch (BN) {
       case 256: return launch_pair<256>(t0, t1, t2, t3, tw, p, stream);
