@@ -147,7 +147,7 @@ def test_conv_split_bnstats_and_bn_apply(dev):
     s2 = torch.zeros_like(sums)
     ops.bn_stats(z, gs, s2, z_lo=z_lo)
     torch.cuda.synchronize()
-    torch.testing.assert_close(s2, sums, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(s2, sums, rtol=2e-5, atol=2e-5)          # fp32 partial sums grouped differently
 
 
 @pytest.mark.parametrize('cin', [1, 3])
