@@ -12,8 +12,9 @@ affine = True
 
 def _check_eval(mod):
     if mod.training:
-        raise NotImplementedError('%s: train-mode (batch-statistics BatchNorm + backward) kernels are not built yet; '
-                                  'call .eval() — the B200 path has no PyTorch fallback' % type(mod).__name__)
+        raise NotImplementedError('%s.forward on its own runs in eval mode only: the train-mode kernels (batch-statistics BatchNorm + '
+                                  'backward) are scheduled for the whole model by RP_Net.forward / rpnet_b200.train.TrainStep; call '
+                                  '.eval() for a standalone block — the B200 path has no PyTorch fallback' % type(mod).__name__)
 
 
 def _check_norm(normalization_type):
