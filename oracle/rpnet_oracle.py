@@ -104,6 +104,11 @@ def conv_bn_relu(x, sd, conv, bn, training=False, padding=1, dilation=1, relu=Tr
         y = F.relu(y) if relu else y
         return y if conv.endswith('cre.q.0') else _q(y)
     y = F.conv2d(x, sd[conv + '.weight'], sd[conv + '.bias'], padding=padding, dilation=dilation)
+    if bn is not None and (bn + '.running_mean') not in sd:
+        # unet_normalize_type: InstanceNorm2d — nn.InstanceNorm2d(C) (net/modules.py:49,52,69 through getattr(nn, ...)): no affine
+        # parameters, no running statistics: per-(image, channel) statistics in train AND eval mode, eps 1e-5
+        y = F.instance_norm(y, eps=BN_EPS)
+        return F.relu(y) if relu else y
     if bn is not None:
         if training and (bn + '.num_batches_tracked') in sd:
             sd[bn + '.num_batches_tracked'] += 1
@@ -124,14 +129,22 @@ def up_conv(x, sd, p, training=False):
     return conv_bn_relu(x, sd, p + '.up.1', p + '.up.2', training)
 
 
-def unet_encoder(x, sd, prefix='encoder.', training=False, want=None):
-    """Truncated U-Net, returns d4 (256 ch @ H/4).  net/unet.py:435-467 with
-    mask_feature_map == False (yamls/example.yml:103 parses to False).
-    ``want`` may be a dict that receives the intermediate maps (tests)."""
+def unet_encoder(x, sd, prefix='encoder.', training=False, want=None, mask=None, mask_feature_map=False):
+    """Truncated U-Net, returns d4 (256 ch @ H/4).  net/unet.py:435-467.  mask_feature_map False (yamls/example.yml:103
+    parses to False) or 'x' / 'x2' / 'x3': ``mask`` [n, 1, H, W] (avg-pooled by 2 / 4) is concatenated to the
+    input of Conv1 / Conv2 / Conv3 (:437-449).  ``want`` may be a dict that receives the intermediate maps (tests)."""
     p = prefix
+    if mask_feature_map == 'x':
+        x = torch.cat([x, mask], dim=1)
     x1 = conv_block(x, sd, p + 'Conv1', training)
-    x2 = conv_block(F.max_pool2d(x1, 2, 2), sd, p + 'Conv2', training)
-    x3 = conv_block(F.max_pool2d(x2, 2, 2), sd, p + 'Conv3', training)
+    x2 = F.max_pool2d(x1, 2, 2)
+    if mask_feature_map == 'x2':
+        x2 = torch.cat([x2, F.avg_pool2d(mask, 2)], dim=1)
+    x2 = conv_block(x2, sd, p + 'Conv2', training)
+    x3 = F.max_pool2d(x2, 2, 2)
+    if mask_feature_map == 'x3':
+        x3 = torch.cat([x3, F.avg_pool2d(mask, 4)], dim=1)
+    x3 = conv_block(x3, sd, p + 'Conv3', training)
     x4 = conv_block(F.max_pool2d(x3, 2, 2), sd, p + 'Conv4', training)
     x5 = conv_block(F.max_pool2d(x4, 2, 2), sd, p + 'Conv5', training)
     d5 = up_conv(x5, sd, p + 'Up5', training)
@@ -357,7 +370,9 @@ def forward(sd, cfg, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_label
 
     def encode(x):
         if backbone == 'UNet':
-            return unet_encoder(x, sd, 'encoder.', training)
+            # net/rp_net.py:248,257: BOTH encoder passes receive fore_mask[0][0] (only read by the mask_feature_map variants)
+            return unet_encoder(x, sd, 'encoder.', training, mask=fore_mask[0][0].unsqueeze(1),
+                                mask_feature_map=cfg.get('mask_feature_map', False))
         if backbone == 'vgg':      # wiring per SURVEY D1: wrap as d4, caller passes scale=8
             return vgg_encoder(x.expand(-1, 3, -1, -1), sd, 'encoder.')
         if backbone == 'resnet':   # net/rp_net.py:246-249 (eval only in this oracle)

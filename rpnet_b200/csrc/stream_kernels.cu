@@ -646,12 +646,15 @@ RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, in
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv3x3_first: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first: bad shape %d x %d x %d", n, h, w);
-  RPNET_REQUIRE(cin == 1 || cin == 3, "conv3x3_first: cin must be 1 or 3 (got %d)", cin);
+  RPNET_REQUIRE(cin >= 1 && cin <= 3, "conv3x3_first: cin must be 1, 2 or 3 (got %d)", cin);
   const long long total = (long long)n * h * w * 8;
   const int grid = grid_for(total, 256);
   if (cin == 1)
     conv3x3_first_c1_kernel<<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
         img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), n, h, w);
+  else if (cin == 2)      // mask_feature_map: x (net/unet.py:401-402, 437-438): image + mask channel
+    conv3x3_first_kernel<2><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
+                                                      static_cast<__half*>(out_lo_f16), n, h, w);
   else
     conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
                                                       static_cast<__half*>(out_lo_f16), n, h, w);

@@ -136,11 +136,18 @@ def pack_upsample_phases(weight, split=False):
     return out
 
 
-def conv_bn_pack(conv, bn, relu=True, dilation=1, split=False, w_split=None):
+def conv_bn_pack(conv, bn, relu=True, dilation=1, split=False, w_split=None, pad_cin_to=None):
+    """pad_cin_to: zero-pad the input channels of the pack (a 65- / 129-channel conv of the mask_feature_map variants runs
+    as 128 / 192 packed channels: the extra source carries the mask in its first channel)."""
     scale, shift = fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps) if bn is not None \
         else fold_bn(conv.bias)
     w_split = split if w_split is None else w_split
-    wp, taps = pack_weight_taps(conv.weight, dilation, w_split)
+    w = conv.weight.detach()
+    if pad_cin_to is not None and pad_cin_to > w.shape[1]:
+        wpad = torch.zeros(w.shape[0], pad_cin_to, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+        wpad[:, :w.shape[1]] = w
+        w = wpad
+    wp, taps = pack_weight_taps(w, dilation, w_split)
     return ConvPack(wp, taps, scale, shift, relu, split, w_split)
 
 

@@ -18,9 +18,10 @@ def _check_eval(mod):
 
 
 def _check_norm(normalization_type):
-    if normalization_type != 'BatchNorm2d':
-        raise NotImplementedError("unet_normalize_type=%r: only 'BatchNorm2d' (yamls/example.yml:40) has a B200 kernel"
-                                  % (normalization_type,))
+    """'BatchNorm2d' (yamls/example.yml:40) or 'InstanceNorm2d' — nn.InstanceNorm2d(C): no parameters, per-image statistics in
+    train and eval mode; the U-Net then runs the two-pass schedule of rpnet_b200.train.EncoderEngine with one call group per image."""
+    if normalization_type not in ('BatchNorm2d', 'InstanceNorm2d'):
+        raise NotImplementedError("unet_normalize_type=%r: 'BatchNorm2d' and 'InstanceNorm2d' have B200 kernels" % (normalization_type,))
 
 
 class _PackedModule(nn.Module):
@@ -68,6 +69,7 @@ class conv_block(_PackedModule):
         self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
         if kernel != 3 or padding != 1:
             raise NotImplementedError('conv_block: only kernel=3, padding=1 is used by RP-Net')
+        self.inorm = normalization_type == 'InstanceNorm2d'
         self.ch_in = ch_in
         self.ch_out = ch_out
         self.conv = nn.Sequential(
@@ -80,13 +82,17 @@ class conv_block(_PackedModule):
         )
 
     def _build_packs(self):
-        if self.ch_in in (1, 3):
+        if self.inorm:
+            raise NotImplementedError('conv_block with InstanceNorm2d runs inside U_Net (per-image statistics need the two-pass schedule)')
+        if self.ch_in in (1, 2, 3):                                    # 2: image + mask channel (mask_feature_map: x)
             if self.ch_out != 64:
                 raise NotImplementedError('conv_block: a %d-channel image input needs ch_out == 64' % self.ch_in)
             c, b = self.conv[0], self.conv[1]
             first = engine.fold_bn(c.bias, b.weight, b.bias, b.running_mean, b.running_var, b.eps)    # (scale, shift) tuple
         else:
-            first = engine.conv_bn_pack(self.conv[0], self.conv[1], split=self.split, w_split=self.w_split)
+            # 65 / 129 input channels (mask_feature_map: x2 / x3): packed as 128 / 192, the mask travels in a 64-channel extra source
+            pad = (self.ch_in + 63) // 64 * 64 if self.ch_in % 64 else None
+            first = engine.conv_bn_pack(self.conv[0], self.conv[1], split=self.split, w_split=self.w_split, pad_cin_to=pad)
         return first, engine.conv_bn_pack(self.conv[3], self.conv[4], split=self.split, w_split=self.w_split)
 
     def run_nhwc(self, x, ws, name, x1=None, want_out=True, want_pool=False):
@@ -112,6 +118,7 @@ class up_conv(_PackedModule):
     def __init__(self, ch_in, ch_out, normalization_type, kernel=3, padding=1, precision=None):
         super(up_conv, self).__init__()
         _check_norm(normalization_type)
+        self.inorm = normalization_type == 'InstanceNorm2d'
         pr = precision or engine.default_precision()
         self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
         if kernel != 3 or padding != 1:
@@ -126,6 +133,8 @@ class up_conv(_PackedModule):
         )
 
     def _build_packs(self):
+        if self.inorm:
+            raise NotImplementedError('up_conv with InstanceNorm2d runs inside U_Net (per-image statistics need the two-pass schedule)')
         conv, bn = self.up[1], self.up[2]
         scale, shift = engine.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
         return engine.pack_upsample_phases(conv.weight, self.w_split), scale, shift

@@ -170,12 +170,24 @@ class RP_Net(nn.Module):
         self._ws = engine.Workspace()
 
     # ------------------------------------------------------------------ hot path
-    def _encode(self, imgs, tag):
+    def _encode(self, imgs, tag, mask=None):
         if self.config['backbone'] in ('vgg', 'resnet'):
             if imgs.shape[1] == 1:
                 imgs = imgs.expand(-1, 3, -1, -1)                      # net/rp_net.py:246-247
             return engine.hi_of(self.encoder.encode_nhwc(imgs.float().contiguous(), tag))
-        return self.encoder.encode_nhwc(imgs.float().contiguous(), tag)
+        return self.encoder.encode_nhwc(imgs.float().contiguous(), tag, mask=mask)
+
+    def _encoder_mask(self, fore, n_ways, n_shots, B):
+        """The `mask` argument of both encoder passes: fore_mask[0][0] (net/rp_net.py:248,257), only read by the mask_feature_map
+        variants of the U-Net.  The reference concatenates it to the whole support batch, which only has matching shapes for
+        1-way 1-shot; the support and the query pass then see the same B masks."""
+        if not getattr(self.encoder, 'mfm', False):
+            return None
+        if n_ways * n_shots != 1:
+            raise ValueError('mask_feature_map needs 1-way 1-shot: the reference concatenates fore_mask[0][0] (B masks) to the '
+                             'Wa*Sh*B support images (net/rp_net.py:248, net/unet.py:437-449)')
+        m = fore[:B].unsqueeze(1)
+        return torch.cat([m, m], dim=0).contiguous()
 
     def forward(self, supp_imgs, fore_mask, back_mask, qry_imgs, registration_field=None, grid=None, query_labels=None,
                 appr_query_labels=None):
@@ -227,7 +239,7 @@ class RP_Net(nn.Module):
         n_supp = n_ways * n_shots * B
         # ---- encoder: support and query images in ONE batch (eval-mode BN is per-sample; the reference runs two
         #      passes, net/rp_net.py:245-262 — identical results)
-        d4 = self._encode(imgs, 'enc')                                   # [(Wa*Sh+1)*B, h, w, C] fp16 NHWC
+        d4 = self._encode(imgs, 'enc', self._encoder_mask(fore, n_ways, n_shots, B))   # [(Wa*Sh+1)*B, h, w, C] fp16 NHWC
         h, w = d4.shape[1:3]
         if h * S != H or w * S != W:
             raise ValueError('scale=%d does not match the encoder stride (%d x %d features for a %d x %d image); '

@@ -19,6 +19,7 @@ walks the iterations from the last to the first, sending each iteration's pre-ma
 iteration's logits (rpnet_premask_mask_bwd, rpnet_soft_mask_bwd_f32).
 """
 import torch
+import torch.nn as nn
 
 from . import engine, ops
 
@@ -138,15 +139,32 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _NoAffineNorm:
+    """What the kernels see of an nn.InstanceNorm2d(C) (unet_normalize_type: InstanceNorm2d): gamma = 1, beta = 0, no running
+    statistics; the per-image statistics come from one BatchNorm call group per image."""
+
+    def __init__(self, c, dev, eps=1e-5):
+        from types import SimpleNamespace
+        self.weight = SimpleNamespace(data=torch.ones(c, dtype=f32, device=dev))
+        self.bias = SimpleNamespace(data=torch.zeros(c, dtype=f32, device=dev))
+        self.running_mean = self.running_var = self.num_batches_tracked = None
+        self.eps, self.momentum = eps, 0.1
+
+
 class _ConvBN:
-    """One conv (bias dropped: it cancels in train-mode BN) + BatchNorm(batch stats) + ReLU of the path."""
+    """One conv (bias dropped: it cancels in batch- / instance-statistics normalisation) + BatchNorm(batch stats) + ReLU of the path."""
 
     def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False, w_split=None):
         # split: the forward runs in split-fp16 (x = hi + lo planes; with w_split weights Wh | Wl: three tensor-core passes,
         # fp32-class result; without: hi.W + lo.W); the backward is unchanged (it reads the hi planes).
         self.name, self.conv, self.bn, self.first, self.hole, self.up, self.split = name, conv, bn, first, hole, up, split
         self.w_split = split if w_split is None else w_split
-        self.gw, self.ggamma, self.gbeta = flat.grad_of(conv.weight), flat.grad_of(bn.weight), flat.grad_of(bn.bias)
+        if not isinstance(bn, nn.BatchNorm2d):                 # nn.InstanceNorm2d: no parameters, no buffers
+            self.bn = bn = _NoAffineNorm(conv.out_channels, conv.weight.device, getattr(bn, 'eps', 1e-5))
+        affine = isinstance(bn, nn.BatchNorm2d)
+        self.gw = flat.grad_of(conv.weight) if flat is not None else None
+        self.ggamma = flat.grad_of(bn.weight) if (flat is not None and affine) else None
+        self.gbeta = flat.grad_of(bn.bias) if (flat is not None and affine) else None
         k = conv.kernel_size[0]
         d = conv.dilation[0]
         self.taps = [((ky - k // 2) * d, (kx - k // 2) * d) for ky in range(k) for kx in range(k)]
@@ -237,51 +255,69 @@ class _ConvBN:
         return dx
 
 
-class TrainEngine:
-    """Train-mode forward + backward of RP_Net (U-Net backbone) on the C-ABI kernels."""
+class EncoderEngine:
+    """The two-pass (statistics, then apply) schedule of the U-Net encoder on the C-ABI kernels: conv (split-fp16 or fp16) with the
+    normalisation statistics in its epilogue -> finalize -> apply (+ReLU, + fused 2x2 max-pool).  TrainEngine builds on it
+    (train-mode BatchNorm: one call group per reference call); on its own it is the eval forward of `unet_normalize_type:
+    InstanceNorm2d` (one call group per image, no running statistics)."""
+    MAX_GROUPS = 64                                    # kMaxGroups of the BatchNorm kernels
 
-    def __init__(self, net):
-        from .nn.unet import U_Net
-        if not isinstance(net.encoder, U_Net):
-            raise NotImplementedError("training is built for backbone 'UNet' (the reference cannot train 'vgg': SURVEY D1)")
-        dev = next(net.parameters()).device
+    def __init__(self, encoder, norm='batch', flat=None, cfg=None):
+        dev = next(encoder.parameters()).device
         if dev.type != 'cuda':
-            raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
-        self.net, self.dev = net, dev
-        self.flat = FlatParams(net)
-        e, c = net.encoder, net.cre
+            raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback')
+        if getattr(encoder, 'mfm', False):
+            raise NotImplementedError('mask_feature_map=%r is built for the eval forward with BatchNorm2d only' % (encoder.mfm,))
+        self.encoder, self.dev, self.norm, self.flat = encoder, dev, norm, flat
         # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
-        # train-mode logits 2e-3 .. 5e-3 from the fp32 reference); the cre convs are single-term in both (their rounding moves
-        # the logits by ~1e-4, DESIGN.md §2)
-        pr = engine.precision_of(net.backbone_cfg)
+        # train-mode logits 2e-3 .. 5e-3 from the fp32 reference)
+        pr = engine.precision_of(cfg if cfg is not None else encoder.cfg)
         self.split = sp = pr == 'split'
         wd = engine.decoder_precision(pr) == 'split'     # decoder half: RPNET_SPLIT_DECODER=2 -> split activations, fp16 weights
-        L = {}
+        e, L = encoder, {}
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
             ws = sp and (wd or not nm.startswith('uc'))
-            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], self.flat, first=(nm == 'c1'), split=sp, w_split=ws)
-            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], self.flat, split=sp, w_split=ws)
-        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], self.flat, up=True, split=sp, w_split=sp and wd)
-        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], self.flat, up=True, split=sp, w_split=sp and wd)
-        k = (2 * c.radius + 1) ** 2
-        self.kcorr, self.corr_c = k, c.corr_channels
-        L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
-        L['wq'] = _ConvBN('wq', c.w_q[0], c.w_q[1], self.flat)
-        L['q'] = _ConvBN('q', c.q[0], c.q[1], self.flat, hole=(k, self.corr_c - k))
+            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], flat, first=(nm == 'c1'), split=sp, w_split=ws)
+            L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], flat, split=sp, w_split=ws)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], flat, up=True, split=sp, w_split=sp and wd)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], flat, up=True, split=sp, w_split=sp and wd)
         self.L = L
         self.ws = engine.Workspace()
         self._scratch = {}
-        self.saved = None
+        self.act = {}
+        self._first = e.Conv1.conv[0].weight
+        self._first_ptr = self._first.data_ptr()
+        self._pack_sig = None
 
-    @staticmethod
-    def of(net):
-        """The (cached) engine of `net`; rebuilt when the parameters were moved (e.g. net.to(other_device))."""
-        eng = net.__dict__.get('_b200_train_engine')
-        if eng is None or not eng.flat.attached():
-            eng = TrainEngine(net)
-            net.__dict__['_b200_train_engine'] = eng
-        return eng
+    def attached(self):
+        """False once the encoder's parameters were moved (net.to(other_device)): build a new engine."""
+        return self._first.data_ptr() == self._first_ptr and self._first.device == self.dev
+
+    def groups_for(self, calls):
+        """BatchNorm2d: the call groups given (one per reference call); InstanceNorm2d: one group per image."""
+        if self.norm == 'instance':
+            n = calls[-1]
+            if n > self.MAX_GROUPS:
+                raise ValueError('InstanceNorm2d: at most %d images per encoder pass (got %d)' % (self.MAX_GROUPS, n))
+            return list(range(n + 1))
+        return calls
+
+    def encode(self, imgs):
+        """Eval forward (InstanceNorm2d): fp32 NCHW images -> d4 fp16 NHWC, in passes of at most MAX_GROUPS images."""
+        sig = (engine.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.encoder.parameters())
+        if sig != self._pack_sig:
+            self.pack_weights()
+            self._pack_sig = sig
+        n, _, H, W = imgs.shape
+        out = self.buf('encode.d4', (n, H // 4, W // 4, self.L['uc4b'].cout), f16)
+        for lo in range(0, n, self.MAX_GROUPS):
+            hi = min(n, lo + self.MAX_GROUPS)
+            self.act = {}
+            d4 = self._encoder_fwd(imgs[lo:hi].contiguous(), self.groups_for([0, hi - lo]))[0]
+            out[lo:hi].copy_(d4)
+        self.act = {}
+        return out
 
     # ------------------------------------------------------------------ buffers
     def buf(self, name, shape, dtype):
@@ -413,6 +449,38 @@ class TrainEngine:
         if buckets:
             buckets.ready(4)
 
+class TrainEngine(EncoderEngine):
+    """Train-mode forward + backward of RP_Net (U-Net backbone) on the C-ABI kernels."""
+
+    def __init__(self, net):
+        from .nn.unet import U_Net
+        if not isinstance(net.encoder, U_Net):
+            raise NotImplementedError("training is built for backbone 'UNet' (the reference cannot train 'vgg': SURVEY D1)")
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
+        self.net = net
+        flat = FlatParams(net)
+        # the cre convs are single-term fp16 in both precisions (their rounding moves the logits by ~1e-4, DESIGN.md §2) and
+        # always BatchNorm2d (net/rp_net.py:50-69)
+        super().__init__(net.encoder, norm='instance' if net.encoder.inorm else 'batch', flat=flat, cfg=net.backbone_cfg)
+        c, L = net.cre, self.L
+        k = (2 * c.radius + 1) ** 2
+        self.kcorr, self.corr_c = k, c.corr_channels
+        L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
+        L['wq'] = _ConvBN('wq', c.w_q[0], c.w_q[1], self.flat)
+        L['q'] = _ConvBN('q', c.q[0], c.q[1], self.flat, hole=(k, self.corr_c - k))
+        self.saved = None
+
+    @staticmethod
+    def of(net):
+        """The (cached) engine of `net`; rebuilt when the parameters were moved (e.g. net.to(other_device))."""
+        eng = net.__dict__.get('_b200_train_engine')
+        if eng is None or not eng.flat.attached():
+            eng = TrainEngine(net)
+            net.__dict__['_b200_train_engine'] = eng
+        return eng
+
     # ------------------------------------------------------------------ context-relation encoder
     def _cre_fwd(self, d4, mask, lo, hi, g0, gs):
         """ContextCorrelationEncoder.forward (net/rp_net.py:77-84) in train mode on images [lo, hi) of the batched cre
@@ -451,7 +519,7 @@ class TrainEngine:
         engine.WEIGHTS_EPOCH += 1          # BN running statistics are updated through raw pointers below
 
         imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
-        d4 = self._encoder_fwd(imgs, [0, n_supp, n_img])[0]          # two BN calls: support pass, query pass (D14); hi plane
+        d4 = self._encoder_fwd(imgs, self.groups_for([0, n_supp, n_img]))[0]   # two BN calls: support pass, query pass (D14); hi plane
         h, w, C = d4.shape[1:]
         if h * S != H or w * S != W:
             raise ValueError('scale=%d does not match the encoder stride' % S)
