@@ -293,6 +293,21 @@ int rpnet_upsample2x_f16(const void* x, void* y, int n, int h, int w, int c, voi
 int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask, int iters, long long pixels, int c,
                            void* dx, void* stream);
 
+/* Backward pieces of the VGG stack (net/vgg.py:22-58: conv + bias + ReLU, nn.MaxPool2d(3, stride, 1); no normalisation), for
+ * training RP_Net with `backbone: vgg` (the reference cannot run that backbone through RP_Net at all).
+ * rpnet_relu_bias_bwd: g = dy * [y > 0] (bf16 NHWC; y_f16 = null: no ReLU) and dbias[c] += sum_p g[p][c]; scratch_c: c doubles.
+ * rpnet_maxpool_idx_f16: rpnet_maxpool_split_f16 that also records the window position (dy * k + dx, uint8 [n][ho][wo][c]) of the first
+ *   maximum; rpnet_maxpool_bwd_bf16 routes dy back through those positions (every input pixel gathers from the windows covering it).
+ * rpnet_conv3x3_first_wgrad_cin: rpnet_conv3x3_first_wgrad for a Cin-channel (<= 4) image [n][cin][h][w]: grad [64][cin][3][3] +=. */
+int rpnet_relu_bias_bwd(const void* dy_bf16, const void* y_f16, long long pixels, int c, void* g_bf16, float* dbias, double* scratch_c,
+                        void* stream);
+int rpnet_maxpool_idx_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, void* idx_u8, int n, int h, int w, int c,
+                          int k, int stride, int pad, void* stream);
+int rpnet_maxpool_bwd_bf16(const void* dy_bf16, const void* idx_u8, void* dx_bf16, int n, int h, int w, int c, int k, int stride,
+                           int pad, void* stream);
+int rpnet_conv3x3_first_wgrad_cin(const float* img, int cin, const void* dz_bf16, int n, int h, int w, float* grad,
+                                  double* scratch576, void* stream);
+
 /* `soft_mask: True` training (net/rp_net.py:308-311 without the threshold): the recurrent mask m_{i+1} = avg_pool2d(p_fg(logits_i), scale)
  * stays in the autograd graph.
  * rpnet_premask_mask_bwd: dmask[p] = sum_c (dxfg[p][c] - dxbg[p][c]) * x[p][c] — the gradient of x_fg = x * m, x_bg = x * (1 - m) (:283)

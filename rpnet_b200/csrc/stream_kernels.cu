@@ -586,15 +586,17 @@ upsample_tail_kernel(const float* __restrict__ pred, float* __restrict__ logits,
 // net/vgg.py:24-30).  One thread per output pixel x 8 channels.
 // ---------------------------------------------------------------------------------------------------
 __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, uint4* __restrict__ out,
-                                   uint4* __restrict__ out_lo, int N, int H, int W, int c8, int Ho, int Wo, int k, int stride, int pad) {
+                                   uint4* __restrict__ out_lo, uint2* __restrict__ idx, int N, int H, int W, int c8, int Ho, int Wo, int k,
+                                   int stride, int pad) {
   const long long total = (long long)N * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % c8);
     long long pix = i / c8;
     const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
     float best[8];
+    unsigned arg[8];                       // window position dy * k + dx of the FIRST maximum (nn.MaxPool2d's backward routing)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0u; }
     for (int dy = 0; dy < k; ++dy) {
       const int y = yo * stride - pad + dy;
       if (y < 0 || y >= H) continue;
@@ -610,12 +612,14 @@ __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __
           for (int j = 0; j < 8; ++j) v[j] += l[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], v[j]);
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j]) { best[j] = v[j]; arg[j] = (unsigned)(dy * k + dx); }
       }
     }
     const uint4 hi = pack8(best);
     out[i] = hi;
     if (out_lo) out_lo[i] = residual8_f16(best, hi);
+    if (idx) idx[i] = make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24), arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24));
   }
 }
 
@@ -811,6 +815,8 @@ RPNET_API int rpnet_upsample_tail_f32(const float* pred, float* logits, float* m
 
 RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
                                        int stride, int pad, void* stream_);
+RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, void* idx_u8, int n, int h, int w, int c,
+                                     int k, int stride, int pad, void* stream_);
 
 RPNET_API int rpnet_maxpool_f16(const void* in, void* out, int n, int h, int w, int c, int k, int stride, int pad, void* stream_) {
   return rpnet_maxpool_split_f16(in, nullptr, out, nullptr, n, h, w, c, k, stride, pad, stream_);
@@ -818,7 +824,13 @@ RPNET_API int rpnet_maxpool_f16(const void* in, void* out, int n, int h, int w, 
 
 RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
                                        int stride, int pad, void* stream_) {
+  return rpnet_maxpool_idx_f16(in, in_lo, out, out_lo, nullptr, n, h, w, c, k, stride, pad, stream_);
+}
+
+RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, void* idx_u8, int n, int h, int w, int c,
+                                     int k, int stride, int pad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(k <= 15, "maxpool: window %d too large for the uint8 argmax positions", k);
   RPNET_REQUIRE(in && out, "maxpool: null pointer argument");
   RPNET_REQUIRE((in_lo == nullptr) == (out_lo == nullptr), "maxpool: residual planes go in and out together");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
@@ -826,7 +838,7 @@ RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* o
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
   maxpool_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<const uint4*>(in_lo),
-                                                                static_cast<uint4*>(out), static_cast<uint4*>(out_lo), n, h, w, c / 8, ho,
-                                                                wo, k, stride, pad);
+                                                                static_cast<uint4*>(out), static_cast<uint4*>(out_lo),
+                                                                static_cast<uint2*>(idx_u8), n, h, w, c / 8, ho, wo, k, stride, pad);
   return check_cuda(cudaGetLastError(), "maxpool launch");
 }

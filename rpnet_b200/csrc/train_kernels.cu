@@ -913,8 +913,8 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout,
 // pixel lanes of a warp are folded with shuffles, warps through shared-memory atomics, blocks through global atomics.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restrict__ dz, int N, int H, int W,
-                           double* __restrict__ acc64 /*[64][9], zeroed*/) {
+conv3x3_first_wgrad_kernel(const float* __restrict__ img /* plane ci of image 0 */, unsigned img_n_stride /* cin * H * W */,
+                           const uint4* __restrict__ dz, int N, int H, int W, double* __restrict__ acc64 /*[64][9], zeroed*/) {
   __shared__ double s_acc[64 * 9];      // fp32 warp partials added in fp64: exact, so the arrival order of warps / blocks is immaterial
   for (int i = threadIdx.x; i < 64 * 9; i += 256) s_acc[i] = 0.0;
   __syncthreads();
@@ -935,7 +935,7 @@ conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restric
       const unsigned p = p0 + u * stride;
       const bool ok = p < total;
       const unsigned x = p % (unsigned)W, y = (p / (unsigned)W) % (unsigned)H;
-      const unsigned base = p - y * W - x;                        // n * H * W
+      const unsigned base = (p / ((unsigned)H * (unsigned)W)) * img_n_stride;   // this image's plane
       dq[u] = ok ? __ldg(dz + (size_t)p * 8 + cg) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
@@ -974,6 +974,87 @@ conv3x3_first_wgrad_kernel(const float* __restrict__ img, const uint4* __restric
 __global__ void add_f64_to_f32_kernel(const double* __restrict__ acc, float* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] += (float)acc[i];
+}
+// grad[co][ci][t] += acc[co][t] for one input plane ci of a Cin-channel first conv
+__global__ void add_first_wgrad_kernel(const double* __restrict__ acc, float* __restrict__ grad, int cin, int ci) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 9) grad[((i / 9) * cin + ci) * 9 + i % 9] += (float)acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward pieces of the VGG stack (net/vgg.py:22-58: conv + bias + ReLU, nn.MaxPool2d(3, stride, 1), no normalisation).
+// (1) g = dy * [y > 0] (bf16) and dbias[c] += sum_p g[p][c]  (y = null: the last conv has no ReLU).  Thread = fixed 8-channel
+//     vector, fp32 partials, shared-memory tree over the pixel lanes, fp64 accumulation across blocks (exact, order independent).
+// (2) nn.MaxPool2d backward from the argmax positions recorded by the forward (uint8 window position of the first maximum):
+//     every input pixel gathers from the (at most ceil(k / stride)^2) windows that cover it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+relu_bias_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, long long pixels, int c8, uint4* __restrict__ g,
+                     double* __restrict__ dbias_acc) {
+  __shared__ float s_red[256 * 8];
+  const int lanes = 256 / c8;
+  const int v = threadIdx.x % c8, pl = threadIdx.x / c8;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < pixels; p += (long long)gridDim.x * lanes) {
+    float d[8];
+    unpack8_bf16(__ldg(dy + p * c8 + v), d);
+    if (y) {
+      float f[8];
+      unpack8_f16(__ldg(y + p * c8 + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = f[j] > 0.f ? d[j] : 0.f;
+    }
+    g[p * c8 + v] = pack8_bf16(d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += d[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_red[threadIdx.x * 8 + j] = s[j];
+  __syncthreads();
+  for (int st = lanes >> 1; st > 0; st >>= 1) {
+    if (pl < st) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_red[threadIdx.x * 8 + j] += s_red[(threadIdx.x + st * c8) * 8 + j];
+    }
+    __syncthreads();
+  }
+  if (pl == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dbias_acc + v * 8 + j, (double)s_red[threadIdx.x * 8 + j]);
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx, int N, int H, int W,
+                                   int c8, int Ho, int Wo, int k, int stride, int pad) {
+  const long long total = (long long)N * H * W * c8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % c8);
+    long long pix = i / c8;
+    const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows (yo, xo) with yo * stride - pad <= y <= yo * stride - pad + k - 1
+    int yo0 = y + pad - k + 1;  yo0 = yo0 <= 0 ? 0 : (yo0 + stride - 1) / stride;
+    int xo0 = x + pad - k + 1;  xo0 = xo0 <= 0 ? 0 : (xo0 + stride - 1) / stride;
+    const int yo1 = min((y + pad) / stride, Ho - 1), xo1 = min((x + pad) / stride, Wo - 1);
+    for (int yo = yo0; yo <= yo1; ++yo)
+      for (int xo = xo0; xo <= xo1; ++xo) {
+        const int pos = (y - (yo * stride - pad)) * k + (x - (xo * stride - pad));
+        const long long o = ((long long)(n * Ho + yo) * Wo + xo) * c8 + cv;
+        const uint2 id = __ldg(idx + o);
+        float d[8];
+        unpack8_bf16(__ldg(dy + o), d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned b = ((j < 4 ? id.x : id.y) >> (8 * (j & 3))) & 0xffu;
+          if ((int)b == pos) acc[j] += d[j];
+        }
+      }
+    dx[i] = pack8_bf16(acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1234,20 +1315,61 @@ RPNET_API int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, 
   return check_cuda(cudaGetLastError(), "pack_conv_weights launch");
 }
 
+RPNET_API int rpnet_conv3x3_first_wgrad_cin(const float* img, int cin, const void* dz_bf16, int n, int h, int w, float* grad,
+                                             double* scratch576, void* stream_);
+
 RPNET_API int rpnet_conv3x3_first_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch576,
                                          void* stream_) {
+  return rpnet_conv3x3_first_wgrad_cin(img, 1, dz_bf16, n, h, w, grad, scratch576, stream_);
+}
+
+RPNET_API int rpnet_conv3x3_first_wgrad_cin(const float* img, int cin, const void* dz_bf16, int n, int h, int w, float* grad,
+                                             double* scratch576, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && dz_bf16 && grad && scratch576, "conv3x3_first_wgrad: null pointer argument");
-  RPNET_CUDA_OK(cudaMemsetAsync(scratch576, 0, 576 * sizeof(double), stream));
+  RPNET_REQUIRE(cin >= 1 && cin <= 4, "conv3x3_first_wgrad: cin %d out of range [1, 4]", cin);
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && (long long)n * h * w < (1LL << 31), "conv3x3_first_wgrad: bad shape");
   const long long total = (long long)n * h * w * 8;
   long long blocks = (total + 256 * 16 - 1) / (256 * 16);
   if (blocks > 148LL * 4) blocks = 148LL * 4;
   if (blocks < 1) blocks = 1;
-  conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const uint4*>(dz_bf16), n, h, w, scratch576);
+  for (int ci = 0; ci < cin; ++ci) {                 // one pass per input plane: grad[co][ci][:] += sum dz[.., co] * img[.., ci, shifted]
+    RPNET_CUDA_OK(cudaMemsetAsync(scratch576, 0, 576 * sizeof(double), stream));
+    conv3x3_first_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img + (size_t)ci * h * w, (unsigned)(cin * h * w),
+                                                                     static_cast<const uint4*>(dz_bf16), n, h, w, scratch576);
+    RPNET_CUDA_OK(cudaGetLastError());
+    add_first_wgrad_kernel<<<3, 192, 0, stream>>>(scratch576, grad, cin, ci);
+    RPNET_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+RPNET_API int rpnet_relu_bias_bwd(const void* dy_bf16, const void* y_f16, long long pixels, int c, void* g_bf16, float* dbias,
+                                   double* scratch_c, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dy_bf16 && g_bf16 && dbias && scratch_c, "relu_bias_bwd: null pointer argument");
+  RPNET_REQUIRE(pixels > 0 && c >= 64 && c % 8 == 0 && 256 % (c / 8) == 0, "relu_bias_bwd: bad shape pixels=%lld c=%d", pixels, c);
+  RPNET_CUDA_OK(cudaMemsetAsync(scratch_c, 0, (size_t)c * sizeof(double), stream));
+  const int lanes = 256 / (c / 8);
+  long long blocks = (pixels + lanes * 8 - 1) / (lanes * 8);
+  if (blocks > 148LL * 4) blocks = 148LL * 4;
+  relu_bias_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(static_cast<const uint4*>(dy_bf16), static_cast<const uint4*>(y_f16), pixels, c / 8,
+                                                            static_cast<uint4*>(g_bf16), scratch_c);
   RPNET_CUDA_OK(cudaGetLastError());
-  add_f64_to_f32_kernel<<<3, 192, 0, stream>>>(scratch576, grad, 576);
-  return check_cuda(cudaGetLastError(), "conv3x3_first_wgrad launch");
+  add_f64_to_f32_kernel<<<(c + 255) / 256, 256, 0, stream>>>(scratch_c, dbias, c);
+  return check_cuda(cudaGetLastError(), "relu_bias_bwd launch");
+}
+
+RPNET_API int rpnet_maxpool_bwd_bf16(const void* dy_bf16, const void* idx_u8, void* dx_bf16, int n, int h, int w, int c, int k, int stride,
+                                      int pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(dy_bf16 && idx_u8 && dx_bf16, "maxpool_bwd: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && 2 * pad <= k,
+                "maxpool_bwd: bad shape / window");
+  const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(dy_bf16), static_cast<const uint2*>(idx_u8), static_cast<uint4*>(dx_bf16), n, h, w, c / 8, ho, wo, k, stride, pad);
+  return check_cuda(cudaGetLastError(), "maxpool_bwd launch");
 }
 
 RPNET_API int rpnet_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,

@@ -69,8 +69,10 @@ class Encoder(_PackedModule):
                         plan.append(('conv', m, engine.ConvPack(wp, taps, scale, shift, relu, split=self.split), relu))
         return plan
 
-    def encode_nhwc(self, x, tag='vgg'):
-        """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/8, W/8, 512]."""
+    def encode_nhwc(self, x, tag='vgg', trace=None):
+        """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/8, W/8, 512].  trace: optional list that receives one record per layer
+        (what the train-step backward needs: ('first' | 'conv', conv module, relu, input, output) / ('pool', (k, s, p), input, output,
+        argmax positions)) — the train-mode forward of this stack IS its eval forward (no normalisation layers)."""
         ws = self._ws
         cur = None
         for i, step in enumerate(self._packs()):
@@ -83,20 +85,29 @@ class Encoder(_PackedModule):
                 lo = ws.get(name + '.lo', (n, h, w, 64), torch.float16, x.device) if self.split else None
                 ops.conv3x3_first(x.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, step[3], cur, out_lo=lo)
                 cur = (cur, lo) if self.split else cur
+                if trace is not None:
+                    trace.append(('first', conv, step[3], x, cur))
             elif step[0] == 'conv':
+                prev = cur
                 cur, _ = engine.run_conv(step[2], cur, ws, name)
+                if trace is not None:
+                    trace.append(('conv', step[1], step[3], prev, cur))
             else:
                 _, k, s, p = step
                 n, h, w, c = engine.hi_of(cur).shape
                 shp = (n, (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1, c)
                 out = ws.get(name, shp, torch.float16, x.device)
+                idx = ws.get(name + '.idx', shp, torch.uint8, x.device) if trace is not None else None
+                prev = cur
                 if self.split:
                     out_lo = ws.get(name + '.lo', shp, torch.float16, x.device)
-                    ops.maxpool(cur[0], k, s, p, out, x_lo=cur[1], out_lo=out_lo)
+                    ops.maxpool(cur[0], k, s, p, out, x_lo=cur[1], out_lo=out_lo, idx=idx)
                     cur = (out, out_lo)
                 else:
-                    ops.maxpool(cur, k, s, p, out)
+                    ops.maxpool(cur, k, s, p, out, idx=idx)
                     cur = out
+                if trace is not None:
+                    trace.append(('pool', (k, s, p), prev, cur, idx))
         return cur
 
     def forward(self, x, mask=None):

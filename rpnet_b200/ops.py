@@ -280,8 +280,9 @@ def upsample_tail(pred, logits, mask_out, scale, soft_mask):
                                                _stream()), 'rpnet_upsample_tail_f32')
 
 
-def maxpool(x, k, stride, pad, out, x_lo=None, out_lo=None):
-    """x_lo / out_lo: residual planes of a split-fp16 activation (max of hi + lo, re-split)."""
+def maxpool(x, k, stride, pad, out, x_lo=None, out_lo=None, idx=None):
+    """x_lo / out_lo: residual planes of a split-fp16 activation (max of hi + lo, re-split); idx: optional uint8 tensor like `out`
+    that receives the window position of the first maximum (for maxpool_bwd)."""
     lib = _lib.load()
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
     n, h, w, c = x.shape
@@ -290,9 +291,12 @@ def maxpool(x, k, stride, pad, out, x_lo=None, out_lo=None):
     if x_lo is not None:
         _req(x_lo, torch.float16, 'x_lo'); _req(out_lo, torch.float16, 'out_lo')
         assert x_lo.shape == x.shape and out_lo.shape == out.shape
+    if idx is not None:
+        _req(idx, torch.uint8, 'idx')
+        assert idx.shape == out.shape
     with _Timed('maxpool', float((x.numel() * 2 + out.numel() * 2) * (1 if x_lo is None else 2))):
-        _lib.check(lib.rpnet_maxpool_split_f16(_ptr(x), _ptr(x_lo), _ptr(out), _ptr(out_lo), n, h, w, c, k, stride, pad, _stream()),
-                   'rpnet_maxpool_split_f16')
+        _lib.check(lib.rpnet_maxpool_idx_f16(_ptr(x), _ptr(x_lo), _ptr(out), _ptr(out_lo), _ptr(idx), n, h, w, c, k, stride, pad, _stream()),
+                   'rpnet_maxpool_idx_f16')
     
 
 # =====================================================================================================
@@ -403,13 +407,39 @@ def _scratch64(n, device, slot):
 
 
 def conv3x3_first_wgrad(img, dz, grad):
+    """grad fp32 [64, cin, 3, 3] += sum dz * shifted img; img fp32 NCHW [n, cin, h, w] (cin <= 4), dz bf16 NHWC [n, h, w, 64]."""
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
     n, cin, h, w = img.shape
-    assert cin == 1 and tuple(dz.shape) == (n, h, w, 64) and grad.numel() == 64 * 9
-    with _Timed('conv3x3_first_wgrad', float(img.numel() * 4 + dz.numel() * 2), n=2):
-        _lib.check(lib.rpnet_conv3x3_first_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _ptr(_scratch64(576, img.device, 'first_wgrad')),
-                                                 _stream()), 'rpnet_conv3x3_first_wgrad')
+    assert 1 <= cin <= 4 and tuple(dz.shape) == (n, h, w, 64) and grad.numel() == 64 * cin * 9
+    with _Timed('conv3x3_first_wgrad', float(img.numel() * 4 + dz.numel() * 2 * cin), n=2 * cin):
+        _lib.check(lib.rpnet_conv3x3_first_wgrad_cin(_ptr(img), cin, _ptr(dz), n, h, w, _ptr(grad),
+                                                     _ptr(_scratch64(576, img.device, 'first_wgrad')), _stream()), 'rpnet_conv3x3_first_wgrad_cin')
+
+
+def relu_bias_bwd(dy, y, g, dbias):
+    """g bf16 = dy * [y > 0] (y fp16 NHWC or None = no ReLU); dbias fp32 [c] += sum over pixels of g."""
+    lib = _lib.load()
+    _req(dy, bf16, 'dy'); _req(g, bf16, 'g'); _req(dbias, torch.float32, 'dbias')
+    c = dy.shape[-1]
+    pixels = dy.numel() // c
+    assert g.shape == dy.shape and dbias.numel() == c
+    if y is not None:
+        _req(y, torch.float16, 'y')
+        assert y.shape == dy.shape
+    with _Timed('relu_bias_bwd', float(dy.numel() * (6 if y is not None else 4)), n=2):
+        _lib.check(lib.rpnet_relu_bias_bwd(_ptr(dy), _ptr(y), pixels, c, _ptr(g), _ptr(dbias), _ptr(_scratch64(c, dy.device, 'relu_bias')),
+                                           _stream()), 'rpnet_relu_bias_bwd')
+
+
+def maxpool_bwd(dy, idx, k, stride, pad, dx):
+    """dx bf16 [n, h, w, c] from dy bf16 [n, ho, wo, c] and the argmax positions idx uint8 [n, ho, wo, c] of maxpool(..., idx=)."""
+    lib = _lib.load()
+    _req(dy, bf16, 'dy'); _req(idx, torch.uint8, 'idx'); _req(dx, bf16, 'dx')
+    n, h, w, c = dx.shape
+    assert idx.shape == dy.shape and tuple(dy.shape) == (n, (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1, c)
+    with _Timed('maxpool_bwd', float(dy.numel() * 3 + dx.numel() * 2)):
+        _lib.check(lib.rpnet_maxpool_bwd_bf16(_ptr(dy), _ptr(idx), _ptr(dx), n, h, w, c, k, stride, pad, _stream()), 'rpnet_maxpool_bwd_bf16')
 
 
 def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):

@@ -99,9 +99,9 @@ class GradBuckets:
     stream behind an event so that it overlaps the rest of the backward; `finish()` joins.  The 1/world averaging is
     folded into the Adam kernel's grad_scale."""
 
-    def __init__(self, flat, world_size, group=None):
+    def __init__(self, flat, world_size, group=None, groups=None):
         self.flat, self.world, self.group = flat, world_size, group
-        self.ranges = [flat.span(g) for g in BUCKET_GROUPS]
+        self.ranges = [flat.span(g) for g in (groups or BUCKET_GROUPS)]
         covered = sorted(self.ranges)
         assert covered[0][0] == 0 and covered[-1][1] == flat.numel and all(a[1] == b[0] for a, b in zip(covered, covered[1:])), \
             'gradient buckets must tile the flat buffer exactly once: %r' % (covered,)
@@ -477,7 +477,8 @@ class TrainEngine(EncoderEngine):
         """The (cached) engine of `net`; rebuilt when the parameters were moved (e.g. net.to(other_device))."""
         eng = net.__dict__.get('_b200_train_engine')
         if eng is None or not eng.flat.attached():
-            eng = TrainEngine(net)
+            from .nn.vgg import Encoder
+            eng = VggTrainEngine(net) if isinstance(net.encoder, Encoder) else TrainEngine(net)
             net.__dict__['_b200_train_engine'] = eng
         return eng
 
@@ -491,7 +492,7 @@ class TrainEngine(EncoderEngine):
         xfg, xbg = S['xfg'][lo:hi], S['xbg'][lo:hi]
         ops.premask(d4, mask, xfg, xbg)
         G = len(gs) - 1
-        sums = self.scratch('bn_sums', G * 256 * 2, torch.float64)
+        sums = self.scratch('bn_sums', G * max(256, d4.shape[-1]) * 2, torch.float64)
         P = lambda t: (t[lo:hi], None)                                # the cre convs are single-term fp16: no residual planes
         L['wk'].fwd((xfg, None), None, P(S['z1']), gs, sums, S['st1'][g0:g0 + G], y=P(S['fm1']))
         L['wq'].fwd((xbg, None), None, P(S['z2']), gs, sums, S['st2'][g0:g0 + G], y=P(S['fm2']))
@@ -676,6 +677,82 @@ class TrainEngine(EncoderEngine):
         self.flat.grad.zero_()
 
 
+class VggTrainEngine(TrainEngine):
+    """TrainEngine for `backbone: vgg` (`scale: 8`; net/vgg.py:22-58 — the reference raises TypeError when this backbone goes
+    through RP_Net; here it runs under the stated generalisation and trains).  The stack has no normalisation layers, so
+    its train-mode forward is the eval forward (conv + bias + ReLU epilogues, split precision, MaxPool2d(3, stride, 1)) with the
+    layer inputs / outputs kept; the backward walks the trace: ReLU mask + bias gradient (rpnet_relu_bias_bwd), weight gradient
+    and data gradient on the tcgen05 kernels, max-pool routing through the recorded argmax positions."""
+    bucket_groups = [('cre.',), ('encoder.',)]
+
+    def __init__(self, net):
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
+        self.net, self.dev, self.norm = net, dev, 'batch'
+        self.encoder = net.encoder
+        self.flat = FlatParams(net)
+        self.split = net.encoder.split
+        c, L = net.cre, {}
+        k = (2 * c.radius + 1) ** 2
+        self.kcorr, self.corr_c = k, c.corr_channels
+        L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], self.flat)
+        L['wq'] = _ConvBN('wq', c.w_q[0], c.w_q[1], self.flat)
+        L['q'] = _ConvBN('q', c.q[0], c.q[1], self.flat, hole=(k, self.corr_c - k))
+        self.L = L
+        self.ws = engine.Workspace()
+        self._scratch = {}
+        self.act = {}
+        self.saved = None
+        # bf16 [taps, cin, cout] data-gradient packs of the 12 tensor-core convs (the forward packs are the module's own)
+        self.wd = {}
+        for m in net.encoder.modules():
+            if isinstance(m, nn.Conv2d) and m.in_channels >= 64:
+                self.wd[m] = torch.empty(9, m.in_channels, m.out_channels, dtype=bf16, device=dev)
+        self._wd_table = ops.pack_conv_weights([(m.weight.data, None, wd, (0, 0), False) for m, wd in self.wd.items()])
+
+    def pack_weights(self):
+        super().pack_weights()                                  # the cre layers
+        ops.run_pack_conv_weights(*self._wd_table)
+
+    def _encoder_fwd(self, imgs, gs):
+        if imgs.shape[1] == 1:
+            imgs = imgs.expand(-1, 3, -1, -1).contiguous()       # net/rp_net.py:246-247
+        self.trace = []
+        self.imgs3 = imgs
+        out = self.encoder.encode_nhwc(imgs, 'train', trace=self.trace)
+        return (engine.hi_of(out), engine.lo_of(out))
+
+    def _encoder_bwd(self, g_d4, buckets=None):
+        g = g_d4                                                # bf16, gradient w.r.t. the output of the current layer
+        for rec in reversed(self.trace):
+            if rec[0] == 'pool':
+                _, (k, s, p), x, y, idx = rec
+                dx = self.buf('vgg.dpool.%d' % id(idx), tuple(engine.hi_of(x).shape), bf16)
+                ops.maxpool_bwd(g, idx, k, s, p, dx)
+                g = dx
+                continue
+            kind, conv, relu, x, y = rec
+            y_hi = engine.hi_of(y)
+            gz = self.scratch('vgg.gz', y_hi.numel(), bf16).view(y_hi.shape)
+            ops.relu_bias_bwd(g.contiguous(), y_hi if relu else None, gz, self.flat.grad_of(conv.bias))
+            gw = self.flat.grad_of(conv.weight)
+            if kind == 'first':
+                ops.conv3x3_first_wgrad(self.imgs3.float().contiguous(), gz, gw)
+                break
+            x_hi = engine.hi_of(x)
+            n, h, w, cin = x_hi.shape
+            d = conv.dilation[0]
+            taps = [((ky - 1) * d, (kx - 1) * d) for ky in range(3) for kx in range(3)]
+            nb = ops.conv_wgrad_workspace_bytes(cin, 0, n, h, w, 9, conv.out_channels)
+            ops.conv_wgrad(x_hi, gz, taps, gw, self.scratch('wgrad', nb // 4, f32), accumulate=False)
+            dx = self.buf('vgg.dx.%d' % id(conv), (n, h, w, cin), bf16)
+            ops.conv_dgrad(gz, self.wd[conv], taps, dx)
+            g = dx
+        if buckets:
+            buckets.ready(1)
+
+
 class TrainStep:
     """One optimisation step: pack weights -> forward -> dice_ce (+grad) -> backward -> all-reduce -> Adam."""
 
@@ -686,7 +763,7 @@ class TrainStep:
         self.net, self.world = net, world_size
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
         self.align_scaler = float(align_loss_scaler)
-        self.buckets = GradBuckets(self.eng.flat, world_size, process_group)
+        self.buckets = GradBuckets(self.eng.flat, world_size, process_group, getattr(self.eng, 'bucket_groups', None))
         self.t = 0
         self.last = {}
         if world_size > 1:

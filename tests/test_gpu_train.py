@@ -335,3 +335,58 @@ def test_backward_is_deterministic(dev):
     for lg, ls, g in runs[1:]:
         assert torch.equal(lg, runs[0][0]) and torch.equal(ls, runs[0][1])
         assert torch.equal(g, runs[0][2]), (g - runs[0][2]).abs().max().item()
+
+
+def test_vgg_backbone_train_step_vs_oracle(dev):
+    """`backbone: vgg` (`scale: 8`) through the train step: the VGG stack has no normalisation, its forward is the eval forward with
+    the layer inputs kept; backward = ReLU mask + bias gradient, tcgen05 weight / data gradients (incl. the dilation-2 block),
+    max-pool routing through recorded argmax positions (net/vgg.py:22-58; the reference raises TypeError for this backbone inside
+    RP_Net).  Logits 1e-3, loss 1e-3, gradients of every parameter against the oracle's autograd."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import parity
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep, VggTrainEngine
+    from net.rp_net import RP_Net
+    T = 2
+    cfg = dict(_cfg(T), scale=8)
+    torch.manual_seed(0)
+    net = RP_Net(in_channels=3, cfg={'align': True, 'backbone': 'vgg'}, backbone_cfg=cfg)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(dev).train()
+    ep = make_episode(2, 1, 2, 128, seed=7)
+    ts = TrainStep(net)
+    assert isinstance(ts.eng, VggTrainEngine)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    over = {i: O.recurrent_mask(ts.last['logits'][i - 1].float().cpu(), cfg, 8) for i in range(1, T)}
+    out = O.forward(sd, cfg, ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'], training=True,
+                    backbone='vgg', mask_override=over)
+    ref_loss = O.train_loss(out, ep['query_labels'])
+    ref_loss.backward()
+    for i in range(T):
+        r = parity.compare_logits(ts.last['logits'][i].cpu(), out['refinement'][i].detach())
+        assert r['rel_linf'] < LOGIT_TOL and r['margin_rel_err'] < 2 * LOGIT_TOL, (i, r)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    checked = 0
+    for name, p in net.named_parameters():
+        rg = params[name].grad
+        if rg is None:
+            assert p.grad is None, name
+            continue
+        if name in ('cre.w_k.0.bias', 'cre.w_q.0.bias', 'cre.q.0.bias'):        # in front of batch-statistics BN: exactly zero
+            continue
+        g = p.grad.float().cpu()
+        rel = ((g - rg).norm() / rg.norm().clamp_min(1e-12)).item()
+        assert rel < (5e-2 if name.startswith('cre.') else 0.1), (name, rel)
+        checked += 1
+    assert checked >= 26 + 9
+    # one optimizer step runs (packs, Adam on the flat buffer) and changes the encoder weights
+    w0 = net.encoder.features[0][0].weight.detach().clone()
+    ts.step(to_device(ep, dev))
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, net.encoder.features[0][0].weight.detach())
