@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header (bumped on any signature change). */
-int rpnet_abi_version(void);   /* currently 5 */
+int rpnet_abi_version(void);   /* currently 6 */
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* rpnet_last_error(void);
@@ -108,6 +108,17 @@ int rpnet_conv_split_f16(const void* src0_hi, const void* src0_lo, int c0, const
                          int out_w, int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                          void* out_pool_hi, void* out_pool_lo, float* out_f32, const int* group_start, int groups,
                          double* sums, int keep_sums, void* stream);
+/* rpnet_conv_split_res_f16: rpnet_conv_split_f16 with a residual (hi / lo planes, lo may be null) added after the affine and before
+ * the ReLU — torchvision BasicBlock's `out += identity; relu` (ResNet18 backbone, net/rp_net.py:19-42) in split precision.
+ * rpnet_conv7x7s2_stem_split_f16: rpnet_conv7x7s2_stem_f16 that also writes the residual plane of its output. */
+int rpnet_conv_split_res_f16(const void* src0_hi, const void* src0_lo, int c0, const void* src1_hi, const void* src1_lo, int c1,
+                             int n, int h, int w, const void* wpack, int w_split, int ntaps, const int* tap_dy, const int* tap_dx,
+                             int cout, const float* scale, const float* shift, const void* res_hi, const void* res_lo, int relu,
+                             void* out_hi, void* out_lo, int out_h, int out_w, int out_c, int out_coff, int oy_mul, int oy_off,
+                             int ox_mul, int ox_off, void* out_pool_hi, void* out_pool_lo, float* out_f32, const int* group_start,
+                             int groups, double* sums, int keep_sums, void* stream);
+int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
+                                   const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream);
 int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                   const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream);
 int rpnet_bn_stats_split_f16(const void* z_hi, const void* z_lo, int n, int h, int w, int c, const int* group_start, int groups,

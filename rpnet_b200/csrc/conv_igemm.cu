@@ -66,6 +66,7 @@ struct ConvParams {
   // optional residual (torchvision BasicBlock: out = relu(bn2(conv2(.)) + identity)): fp16 NHWC [N][H][W][res_C], added after the
   // affine and before the ReLU
   const __half* res;
+  const __half* res_lo;           // split-fp16 residual plane (null: the residual is plain fp16)
   int res_C;
   // optional fused calDist (net/rp_net.py:353-363) on the activated output of a 64-channel conv (the whole feature vector of
   // a pixel sits in one accumulator row): cos_pred[n][p][pixel] = cos_scaler * cos(y[n,pixel,:], cos_protos[n % cos_sets][p][:])
@@ -385,9 +386,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = 0.f;
           if (valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + (static_cast<size_t>(n * p.H + y) * p.W + x) * p.res_C + ct * BN + c0);
+            const size_t roff = (static_cast<size_t>(n * p.H + y) * p.W + x) * p.res_C + ct * BN + c0;
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff);
 #pragma unroll
             for (int j = 0; j < 4; ++j) unpack8_f16(__ldg(rp + j), r + 8 * j);
+            if (p.res_lo) {
+              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + roff);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float l[8];
+                unpack8_f16(__ldg(rl + j), l);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[8 * j + i] += l[i];
+              }
+            }
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -672,6 +684,14 @@ extern "C" int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, con
 extern "C" int rpnet_bn_stats_split_f16(const void* z_hi, const void* z_lo, int n, int h, int w, int c, const int* group_start,
                                         int groups, double* sums, void* stream);
 
+RPNET_API int rpnet_conv_split_res_f16(const void* src0_hi, const void* src0_lo, int c0, const void* src1_hi, const void* src1_lo, int c1,
+                                        int n, int h, int w, const void* wpack, int w_split, int ntaps, const int* tap_dy,
+                                        const int* tap_dx, int cout, const float* scale, const float* shift, const void* res_hi,
+                                        const void* res_lo, int relu, void* out_hi, void* out_lo, int out_h, int out_w, int out_c,
+                                        int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off, void* out_pool_hi,
+                                        void* out_pool_lo, float* out_f32, const int* group_start, int groups, double* sums,
+                                        int keep_sums, void* stream_);
+
 namespace {
 // One launch of conv_igemm_kernel, as the C-ABI entry points describe it.
 struct ConvCall {
@@ -693,6 +713,7 @@ struct ConvCall {
   const float* cos_protos = nullptr; int cos_P = 0, cos_sets = 0; float cos_scaler = 0.f; float* cos_pred = nullptr;
   const void* const* view_ptr = nullptr; const long long* view_strides = nullptr; const int* tap_src = nullptr;
   const void* res = nullptr;
+  const void* res_lo = nullptr;
 };
 }  // namespace
 
@@ -753,7 +774,8 @@ static int conv_igemm_run(const ConvCall& a) {
   p.out_f32 = a.out_f32; p.f32_C = cout;
   p.bn_sums = nullptr; p.bn_groups = 0;
   if (a.bn_fused) *a.bn_fused = 0;
-  p.res = static_cast<const __half*>(a.res); p.res_C = cout;
+  p.res = static_cast<const __half*>(a.res); p.res_lo = static_cast<const __half*>(a.res_lo); p.res_C = cout;
+  RPNET_REQUIRE(!a.res_lo || a.res, "conv_igemm: a residual lo plane needs the residual");
   p.cos_pred = nullptr; p.cos_protos = nullptr; p.cos_P = 0; p.cos_sets = 1; p.cos_scaler = 0.f;
   if (a.cos_pred) {
     RPNET_REQUIRE(cout == 64 && a.cos_protos && a.cos_P >= 1 && a.cos_P <= kMaxCosP && a.cos_sets >= 1,
@@ -890,7 +912,21 @@ RPNET_API int rpnet_conv_split_f16(const void* src0_hi, const void* src0_lo, int
                                     int out_w, int out_c, int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off,
                                     void* out_pool_hi, void* out_pool_lo, float* out_f32, const int* group_start, int groups,
                                     double* sums, int keep_sums, void* stream_) {
+  return rpnet_conv_split_res_f16(src0_hi, src0_lo, c0, src1_hi, src1_lo, c1, n, h, w, wpack, w_split, ntaps, tap_dy, tap_dx, cout, scale, shift,
+                                  nullptr, nullptr, relu, out_hi, out_lo, out_h, out_w, out_c, out_coff, oy_mul, oy_off, ox_mul, ox_off,
+                                  out_pool_hi, out_pool_lo, out_f32, group_start, groups, sums, keep_sums, stream_);
+}
+
+// See include/rpnet_b200.h for the contract.
+RPNET_API int rpnet_conv_split_res_f16(const void* src0_hi, const void* src0_lo, int c0, const void* src1_hi, const void* src1_lo, int c1,
+                                        int n, int h, int w, const void* wpack, int w_split, int ntaps, const int* tap_dy,
+                                        const int* tap_dx, int cout, const float* scale, const float* shift, const void* res_hi,
+                                        const void* res_lo, int relu, void* out_hi, void* out_lo, int out_h, int out_w, int out_c,
+                                        int out_coff, int oy_mul, int oy_off, int ox_mul, int ox_off, void* out_pool_hi,
+                                        void* out_pool_lo, float* out_f32, const int* group_start, int groups, double* sums,
+                                        int keep_sums, void* stream_) {
   ConvCall a = plain_call(false, src0_hi, c0, src1_hi, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
+  a.res = res_hi; a.res_lo = res_lo;
   a.src0_lo = src0_lo; a.src1_lo = src1_lo; a.w_split = w_split != 0;
   a.out = out_hi; a.out_lo = out_lo; a.out_h = out_h; a.out_w = out_w; a.out_c = out_c; a.out_coff = out_coff;
   a.oy_mul = oy_mul; a.oy_off = oy_off; a.ox_mul = ox_mul; a.ox_off = ox_off;

@@ -167,7 +167,7 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
 // weights live in shared memory as [tap][64], 8 threads per output pixel x 8 channels each.
 __global__ void __launch_bounds__(256)
 conv7x7s2_stem_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][3][7][7]*/, const float* __restrict__ scale,
-                      const float* __restrict__ shift, int relu, __half* __restrict__ out, int N, int H, int W) {
+                      const float* __restrict__ shift, int relu, __half* __restrict__ out, __half* __restrict__ out_lo, int N, int H, int W) {
   __shared__ float s_w[147][64];
   for (int i = threadIdx.x; i < 64 * 147; i += blockDim.x) s_w[i % 147][i / 147] = wgt[i];
   __syncthreads();
@@ -199,7 +199,9 @@ conv7x7s2_stem_kernel(const float* __restrict__ img, const float* __restrict__ w
       const float t = fmaf(acc[j], __ldg(scale + cg * 8 + j), __ldg(shift + cg * 8 + j));
       acc[j] = relu ? fmaxf(t, 0.f) : t;
     }
-    *reinterpret_cast<uint4*>(out + (size_t)p * 64 + cg * 8) = pack8(acc);
+    const uint4 hi = pack8(acc);
+    *reinterpret_cast<uint4*>(out + (size_t)p * 64 + cg * 8) = hi;
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + (size_t)p * 64 + cg * 8) = residual8_f16(acc, hi);
   }
 }
 
@@ -635,7 +637,7 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 5; }
+RPNET_API int rpnet_abi_version(void) { return 6; }
 
 RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_);
@@ -665,14 +667,23 @@ RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, in
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");
 }
 
+RPNET_API int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
+                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_);
+
 RPNET_API int rpnet_conv7x7s2_stem_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
                                         const float* shift, int relu, void* out_f16, void* stream_) {
+  return rpnet_conv7x7s2_stem_split_f16(img, n, h, w, weight, scale, shift, relu, out_f16, nullptr, stream_);
+}
+
+RPNET_API int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
+                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv7x7s2_stem: null pointer argument");
   RPNET_REQUIRE(n > 0 && h >= 7 && w >= 7 && (long long)n * h * w < (1LL << 31), "conv7x7s2_stem: bad shape %d x %d x %d", n, h, w);
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   conv7x7s2_stem_kernel<<<grid_for((long long)n * ho * wo * 8, 256), 256, 0, stream>>>(img, weight, scale, shift, relu,
-                                                                                    static_cast<__half*>(out_f16), n, h, w);
+                                                                                    static_cast<__half*>(out_f16),
+                                                                                    static_cast<__half*>(out_lo_f16), n, h, w);
   return check_cuda(cudaGetLastError(), "conv7x7s2_stem launch");
 }
 

@@ -26,7 +26,13 @@ class ResNet18(_PackedModule):
                 BasicBlock(cout, cout)))
         self.backbone = nn.Sequential(*modules)
         self.backbone.out_channels = 512
+        # arithmetic of the 15 tensor-core convs: 'split' (fp32-class, default) or 'fp16' — engine.PRECISIONS; the reference's
+        # constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False` (like nn/vgg.py)
+        self.split = engine.default_precision() == 'split'
         self._ws = engine.Workspace()
+
+    def _signature(self):
+        return super()._signature() + (self.split,)
 
     def _blocks(self):
         return [blk for stage in list(self.backbone)[4:] for blk in stage]
@@ -40,36 +46,49 @@ class ResNet18(_PackedModule):
             def cb(conv, bn, relu):
                 bias = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=conv.weight.device)
                 scale, shift = engine.fold_bn(bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-                wp, taps = engine.pack_weight_taps(conv.weight)
-                return engine.ConvPack(wp, taps, scale, shift, relu)
+                wp, taps = engine.pack_weight_taps(conv.weight, split=self.split)
+                return engine.ConvPack(wp, taps, scale, shift, relu, split=self.split)
             down = cb(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
             packs.append((cb(blk.conv1, blk.bn1, True), cb(blk.conv2, blk.bn2, True), down))
         return stem, packs
 
     def encode_nhwc(self, x, tag='res'):
-        """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/4, W/4, 512]."""
+        """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/4, W/4, 512] ((hi, lo) planes in split precision)."""
         if self.training:
             raise NotImplementedError("backbone 'resnet' is built for eval only (SURVEY §8f N3)")
         ws, dev = self._ws, x.device
         (s_scale, s_shift), packs = self._packs()
         n, _, H, W = x.shape
         h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        stem = ws.get(tag + '.stem', (n, h2, w2, 64), torch.float16, dev)
-        ops.conv7x7s2_stem(x.float().contiguous(), self.backbone[0].weight.detach().float().contiguous(), s_scale, s_shift, stem)
+        f16, sp = torch.float16, self.split
+
+        def buf(name, shape):                                            # hi plane (+ residual plane in split precision)
+            return ws.get(name, shape, f16, dev), (ws.get(name + '.lo', shape, f16, dev) if sp else None)
+
+        def conv(pk, src, dst, res=(None, None)):
+            if sp:
+                ops.conv_split(src[0], pk.wpack, pk.taps, pk.scale, pk.shift, pk.relu, src0_lo=src[1], w_split=True, out=dst[0],
+                               out_lo=dst[1], res=res[0], res_lo=res[1])
+            else:
+                ops.conv_res(src[0], pk.wpack, pk.taps, pk.scale, pk.shift, dst[0], res=res[0], relu=pk.relu)
+
+        stem = buf(tag + '.stem', (n, h2, w2, 64))
+        ops.conv7x7s2_stem(x.float().contiguous(), self.backbone[0].weight.detach().float().contiguous(), s_scale, s_shift, stem[0],
+                           out_lo=stem[1])
         h4, w4 = (h2 + 2 - 3) // 2 + 1, (w2 + 2 - 3) // 2 + 1
-        cur = ws.get(tag + '.pool', (n, h4, w4, 64), torch.float16, dev)
-        ops.maxpool(stem, 3, 2, 1, cur)                                  # nn.MaxPool2d(3, 2, 1)
+        cur = buf(tag + '.pool', (n, h4, w4, 64))
+        ops.maxpool(stem[0], 3, 2, 1, cur[0], x_lo=stem[1], out_lo=cur[1])   # nn.MaxPool2d(3, 2, 1)
         for i, (p1, p2, down) in enumerate(packs):                       # BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)
-            a = ws.get('%s.b%d.a' % (tag, i), (n, h4, w4, p1.cout), torch.float16, dev)
-            ops.conv_res(cur, p1.wpack, p1.taps, p1.scale, p1.shift, a, relu=True)
+            a = buf('%s.b%d.a' % (tag, i), (n, h4, w4, p1.cout))
+            conv(p1, cur, a)
             identity = cur
             if down is not None:
-                identity = ws.get('%s.b%d.d' % (tag, i), (n, h4, w4, down.cout), torch.float16, dev)
-                ops.conv_res(cur, down.wpack, down.taps, down.scale, down.shift, identity, relu=False)
-            out = ws.get('%s.b%d.o' % (tag, i), (n, h4, w4, p2.cout), torch.float16, dev)
-            ops.conv_res(a, p2.wpack, p2.taps, p2.scale, p2.shift, out, res=identity, relu=True)
+                identity = buf('%s.b%d.d' % (tag, i), (n, h4, w4, down.cout))
+                conv(down, cur, identity)
+            out = buf('%s.b%d.o' % (tag, i), (n, h4, w4, p2.cout))
+            conv(p2, a, out, res=identity)
             cur = out
-        return cur
+        return cur if sp else cur[0]
 
     def forward(self, x, mask=None):
         """Reference signature (net/rp_net.py:39-42): returns {'d4': NCHW fp32}."""

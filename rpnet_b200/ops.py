@@ -135,10 +135,11 @@ def conv3x3_first(img, weight, scale, shift, relu, out, out_lo=None):
 
 def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=None, src1_lo=None, w_split=True, out=None,
                out_lo=None, out_pool=None, out_pool_lo=None, out_f32=None, out_map=None, out_coff=0, group_start=None, sums=None,
-               keep_sums=False):
+               keep_sums=False, res=None, res_lo=None):
     """Split-fp16 tap-list conv (include/rpnet_b200.h, rpnet_conv_split_f16): sources and outputs as hi / lo fp16 planes,
     wpack fp16 [ntaps, cout, (c0 + c1) * (2 if w_split else 1)] = Wh | Wl.  sums (fp64) + group_start: train-mode BatchNorm
-    statistics of the fp32 accumulators (scale = 1, shift = 0, relu = False)."""
+    statistics of the fp32 accumulators (scale = 1, shift = 0, relu = False).  res / res_lo: residual planes [n, h, w, cout] added
+    after the affine and before the ReLU (BasicBlock)."""
     lib = _lib.load()
     _req(src0, torch.float16, 'src0'); _req(wpack, torch.float16, 'wpack')
     _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
@@ -184,11 +185,16 @@ def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=No
         assert sums.numel() >= g * cout * 2
     # `work` stays the reference's (algorithmic) FLOPs of the conv; the kernel executes 1 + (lo planes) + (Wl) passes of them
     with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
-        rc = lib.rpnet_conv_split_f16(_ptr(src0), _ptr(src0_lo), c0, _ptr(src1), _ptr(src1_lo), c1, n, h, w, _ptr(wpack), int(bool(w_split)),
-                                      ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out), _ptr(out_lo), oh, ow, oc,
-                                      out_coff, om[0], om[1], om[2], om[3], _ptr(out_pool), _ptr(out_pool_lo), _ptr(out_f32), gs, g,
-                                      _ptr(sums), int(bool(keep_sums)), _stream())
-    _lib.check(rc, 'rpnet_conv_split_f16')
+        for t, nm in ((res, 'res'), (res_lo, 'res_lo')):
+            if t is not None:
+                _req(t, torch.float16, nm)
+                assert tuple(t.shape) == (n, h, w, cout)
+        rc = lib.rpnet_conv_split_res_f16(_ptr(src0), _ptr(src0_lo), c0, _ptr(src1), _ptr(src1_lo), c1, n, h, w, _ptr(wpack),
+                                          int(bool(w_split)), ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_lo),
+                                          int(bool(relu)), _ptr(out), _ptr(out_lo), oh, ow, oc, out_coff, om[0], om[1], om[2], om[3],
+                                          _ptr(out_pool), _ptr(out_pool_lo), _ptr(out_f32), gs, g, _ptr(sums), int(bool(keep_sums)),
+                                          _stream())
+    _lib.check(rc, 'rpnet_conv_split_res_f16')
 
 
 def avgpool_mask(mask, s, out):
@@ -894,15 +900,18 @@ def conv_res(src, wpack, taps, scale, shift, out, res=None, relu=True):
     _lib.check(rc, 'rpnet_conv_res_f16')
 
 
-def conv7x7s2_stem(img, weight, scale, shift, out, relu=True):
-    """img fp32 NCHW [n, 3, H, W]; weight fp32 [64, 3, 7, 7]; out fp16 NHWC [n, (H-1)//2+1, (W-1)//2+1, 64]."""
+def conv7x7s2_stem(img, weight, scale, shift, out, relu=True, out_lo=None):
+    """img fp32 NCHW [n, 3, H, W]; weight fp32 [64, 3, 7, 7]; out fp16 NHWC [n, (H-1)//2+1, (W-1)//2+1, 64] (+ residual plane)."""
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')
     n, c, h, w = img.shape
     assert c == 3 and tuple(weight.shape) == (64, 3, 7, 7) and tuple(out.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
     with _Timed('conv7x7s2_stem', float(img.numel() * 4 + out.numel() * 2)):
-        _lib.check(lib.rpnet_conv7x7s2_stem_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(scale), _ptr(shift), int(bool(relu)), _ptr(out),
-                                                _stream()), 'rpnet_conv7x7s2_stem_f16')
+        if out_lo is not None:
+            _req(out_lo, torch.float16, 'out_lo')
+            assert out_lo.shape == out.shape
+        _lib.check(lib.rpnet_conv7x7s2_stem_split_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(scale), _ptr(shift), int(bool(relu)),
+                                                      _ptr(out), _ptr(out_lo), _stream()), 'rpnet_conv7x7s2_stem_split_f16')
 
 
 # =====================================================================================================

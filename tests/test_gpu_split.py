@@ -46,6 +46,61 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize('case', [(2, 64, 128, 16, 24, 3), (3, 128, 128, 8, 8, 3), (2, 64, 256, 16, 16, 1)])
+@pytest.mark.parametrize('res_split', [True, False])
+def test_conv_split_residual_vs_fp64(dev, case, res_split):
+    """rpnet_conv_split_res_f16: relu(affine(conv(x)) + identity), the BasicBlock tail (net/rp_net.py:24-35), identity as hi + lo
+    planes or a plain fp16 tensor."""
+    from rpnet_b200 import engine, ops
+    n, cin, cout, h, w, k = case
+    g = _gen(sum(case) + 7)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    res = torch.randn(n, cout, h, w, generator=g)
+    r = _pair(res, dev)
+    if not res_split:
+        r = (r[0], None)
+        res = r[0].float().permute(0, 3, 1, 2).cpu()
+    ref = F.relu(F.conv2d(x.double(), wt.double(), None, padding=k // 2) * scale[None, :, None, None].double()
+                 + shift[None, :, None, None].double() + res.double()).float()
+    wp, taps = engine.pack_weight_taps(wt.to(dev), split=True)
+    a = _pair(x, dev)
+    out = torch.empty(n, h, w, cout, dtype=torch.float16, device=dev)
+    out_lo = torch.empty_like(out)
+    ops.conv_split(a[0], wp, taps, scale.to(dev), shift.to(dev), True, src0_lo=a[1], out=out, out_lo=out_lo, res=r[0], res_lo=r[1])
+    torch.cuda.synchronize()
+    err = (_join(out, out_lo) - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_stem_and_maxpool_split_vs_fp64(dev):
+    """ResNet18 stem in split precision: 7x7/s2 conv + BN + ReLU writing hi + lo planes, then MaxPool2d(3, 2, 1) on the pair."""
+    from rpnet_b200 import ops
+    g = _gen(91)
+    n, H, W = 2, 64, 96
+    img = torch.randn(n, 3, H, W, generator=g)
+    wt = torch.randn(64, 3, 7, 7, generator=g) / math.sqrt(147)
+    scale = torch.rand(64, generator=g) + 0.5
+    shift = torch.randn(64, generator=g) * 0.1
+    ref = F.relu(F.conv2d(img.double(), wt.double(), None, stride=2, padding=3) * scale[None, :, None, None].double()
+                 + shift[None, :, None, None].double())
+    ref_pool = F.max_pool2d(ref, 3, 2, 1).float()
+    ref = ref.float()
+    h2, w2 = H // 2, W // 2
+    out = torch.empty(n, h2, w2, 64, dtype=torch.float16, device=dev)
+    out_lo = torch.empty_like(out)
+    ops.conv7x7s2_stem(img.to(dev), wt.to(dev), scale.to(dev), shift.to(dev), out, out_lo=out_lo)
+    pool = torch.empty(n, h2 // 2, w2 // 2, 64, dtype=torch.float16, device=dev)
+    pool_lo = torch.empty_like(pool)
+    ops.maxpool(out, 3, 2, 1, pool, x_lo=out_lo, out_lo=pool_lo)
+    torch.cuda.synchronize()
+    s = ref.abs().max().item()
+    assert (_join(out, out_lo) - ref).abs().max().item() / s < 2e-6
+    assert (_join(pool, pool_lo) - ref_pool).abs().max().item() / s < 2e-6
+
+
 @pytest.mark.parametrize('case', CASES)
 def test_conv_split_vs_fp64(dev, case):
     from rpnet_b200 import engine, ops

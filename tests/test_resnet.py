@@ -58,7 +58,7 @@ def test_resnet_eval_forward_vs_reference_golden(golden):
         out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
         d4 = net.encoder(d['qry_imgs'][0].expand(-1, 3, -1, -1).contiguous(), None)['d4'].cpu()
     want = torch.from_numpy(g['d4_qry'])
-    assert ((d4[:, ::16, ::2, ::2] - want).abs().max() / want.abs().max()).item() < 1e-2           # fp16 activations
+    assert ((d4[:, ::16, ::2, ::2] - want).abs().max() / want.abs().max()).item() < 1e-3           # split-fp16 (fp32-class) convs
     for i in range(int(g['T'])):
         ref = torch.from_numpy(g['ref%d' % i])
         rel = ((out['refinement'][i].cpu()[:, :, ::2, ::2] - ref).abs().max() / ref.abs().max()).item()
