@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header (bumped on any signature change). */
-int rpnet_abi_version(void);   /* currently 6 */
+int rpnet_abi_version(void);   /* currently 7 */
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* rpnet_last_error(void);
@@ -100,8 +100,21 @@ int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, cons
  * rpnet_conv3x3_first_split_f16: rpnet_conv3x3_first_f16 (fp32 arithmetic) that also writes the residual plane of its output.
  * rpnet_bn_stats_split_f16 / rpnet_bn_apply_split_f16: the train-mode BatchNorm passes on z = z_hi + z_lo, writing y (and the
  *   2x2 max-pooled y) as hi / lo planes.
- * rpnet_pack_conv_weight_split / rpnet_pack_upconv_weight_split: split != 0 packs the forward weights as
- *   [taps][cout][Wh (cin) | Wl (cin)] (the data-gradient packs are unchanged: the backward runs single-term). */
+ * rpnet_pack_conv_weight_split / rpnet_pack_upconv_weight_split: split = 1 packs the forward weights as
+ *   [taps][cout][Wh (cin) | Wl (cin)], split = 2 as [taps][cout][Wh (cin) | fp8 corrections (2 * cin bytes)] (the data-gradient
+ *   packs are unchanged: the backward runs single-term).
+ *
+ * fp8 corrections (the default precision, `b200_precision: split8`): x.w = hi.Wh + 2^-15 (lo8.Wh8 + x8.Wl8) — the main term on fp16
+ *   operands, the two first-order corrections on e4m3 operands at twice the MMA rate (kind::f8f6f4) into the same fp32 accumulator,
+ *   which the first main-term MMA scales by 2^-15 (tcgen05.mma scale-input-d).  A correction is 2^-11 of the main term, so its e4m3
+ *   rounding (2^-4) lands at 2^-15 of the product: the same logits error as the three-pass form for two thirds of the
+ *   tensor time.  Fixed scales: lo8 = e4m3((x - hi) * 2^11), x8 = e4m3(x), Wh8 = e4m3(Wh * 2^4), Wl8 = e4m3((w - Wh) * 2^15), saturating.
+ *   A "c8 plane" replaces the fp16 residual plane of an activation (same size): per pixel and 64-channel group 128 bytes = lo8 of the
+ *   64 channels | x8 of the 64 channels; the second half of a weight pack row holds, per 64 input channels, Wh8 (64) | Wl8 (64).
+ *   `lo_fmt` arguments: 0 = fp16 residual plane, 1 = c8 plane (channel counts must be multiples of 64).
+ *   `w_split` of the conv entry points: 0 fp16 weights, 1 Wh | Wl pack, 2 fp8-correction pack with c8 source planes (and residual
+ *   plane) writing c8 output planes, 3 the same inputs writing fp16 residual planes (the pre-BatchNorm z of the train path, whose
+ *   |mean| >> std needs the full residual). */
 int rpnet_conv_split_f16(const void* src0_hi, const void* src0_lo, int c0, const void* src1_hi, const void* src1_lo, int c1,
                          int n, int h, int w, const void* wpack, int w_split, int ntaps, const int* tap_dy, const int* tap_dx,
                          int cout, const float* scale, const float* shift, int relu, void* out_hi, void* out_lo, int out_h,
@@ -118,14 +131,14 @@ int rpnet_conv_split_res_f16(const void* src0_hi, const void* src0_lo, int c0, c
                              int ox_mul, int ox_off, void* out_pool_hi, void* out_pool_lo, float* out_f32, const int* group_start,
                              int groups, double* sums, int keep_sums, void* stream);
 int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
-                                   const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream);
+                                   const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream);
 int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
-                                  const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream);
+                                  const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream);
 int rpnet_bn_stats_split_f16(const void* z_hi, const void* z_lo, int n, int h, int w, int c, const int* group_start, int groups,
                              double* sums, void* stream);
 int rpnet_bn_apply_split_f16(const void* z_hi, const void* z_lo, const float* stats, int n, int h, int w, int c,
                              const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
-                             void* y_pool_lo_f16, float* y_f32, void* stream);
+                             void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream);
 int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_real, int ntaps, int hole_start, int hole_len,
                                  void* w_fwd_f16, int split, void* w_dgrad_bf16, void* stream);
 int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream);
@@ -137,8 +150,8 @@ typedef struct {
 } rpnet_pack_desc;
 int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, void* stream);
 /* rpnet_maxpool_f16 on a split-fp16 activation: the maximum of hi + lo, written back as hi / lo planes (VGG pools between split convs). */
-int rpnet_maxpool_split_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int n, int h, int w, int c, int k,
-                            int stride, int pad, void* stream);
+int rpnet_maxpool_split_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int lo_fmt, int n, int h, int w, int c,
+                            int k, int stride, int pad, void* stream);
 
 /* F.avg_pool2d(mask[:, None], s): fp32 [n][h][w] -> fp32 [n][h/s][w/s].  net/rp_net.py:270,272. */
 int rpnet_avgpool_mask_f32(const float* in, float* out, int n, int h, int w, int s, void* stream);
@@ -312,8 +325,8 @@ int rpnet_premask_bwd_bf16(const void* dxfg, const void* dxbg, const float* mask
  * rpnet_conv3x3_first_wgrad_cin: rpnet_conv3x3_first_wgrad for a Cin-channel (<= 4) image [n][cin][h][w]: grad [64][cin][3][3] +=. */
 int rpnet_relu_bias_bwd(const void* dy_bf16, const void* y_f16, long long pixels, int c, void* g_bf16, float* dbias, double* scratch_c,
                         void* stream);
-int rpnet_maxpool_idx_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, void* idx_u8, int n, int h, int w, int c,
-                          int k, int stride, int pad, void* stream);
+int rpnet_maxpool_idx_f16(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int lo_fmt, void* idx_u8, int n, int h, int w,
+                          int c, int k, int stride, int pad, void* stream);
 int rpnet_maxpool_bwd_bf16(const void* dy_bf16, const void* idx_u8, void* dx_bf16, int n, int h, int w, int c, int k, int stride,
                            int pad, void* stream);
 int rpnet_conv3x3_first_wgrad_cin(const float* img, int cin, const void* dz_bf16, int n, int h, int w, float* grad,

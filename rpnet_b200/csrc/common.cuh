@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -84,6 +85,70 @@ __device__ __forceinline__ uint4 residual8_f16(const float* v, const uint4& hi) 
   for (int i = 0; i < 8; ++i) r[i] = v[i] - r[i];
   return pack8_f16(r);
 }
+// ---- fp8 correction planes ("c8") --------------------------------------------------------------------
+// The tensor-core convs of the default precision compute x.w = hi.Wh + 2^-15 (lo8.Wh8 + x8.Wl8): the main term on fp16
+// operands, the two first-order corrections on e4m3 operands (twice the MMA rate; a correction is 2^-11 of the main term, so
+// its own 2^-4 rounding lands at 2^-15), with fixed power-of-two scales
+//   lo8 = e4m3((x - hi) * 2^11)   x8 = e4m3(x)   Wh8 = e4m3(Wh * 2^4)   Wl8 = e4m3((w - Wh) * 2^15)
+// so that both products carry 2^15, which tcgen05.mma's scale-input-d removes from the accumulator when the fp16 main term
+// starts.  Layout of a c8 plane (same bytes as an fp16 plane of the same shape): per pixel and 64-channel group, 128 bytes
+// = lo8 of the 64 channels, then x8 of the 64 channels — one 128-byte swizzle row, K = 128 for the e4m3 MMA.
+constexpr float kC8LoScale = 2048.f;          // 2^11
+constexpr float kC8WhScale = 16.f;            // 2^4
+constexpr float kC8WlScale = 32768.f;         // 2^15
+constexpr int kC8AccShift = 15;               // scale-input-d of the first main-term MMA
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t h = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return l | (h << 16);
+}
+__device__ __forceinline__ uint2 pack8_e4m3(const float* v) {
+  return make_uint2(pack4_e4m3(v[0], v[1], v[2], v[3]), pack4_e4m3(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8_e4m3(const uint2& u, float* v) {
+  const uint32_t w[2] = {u.x, u.y};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2_raw r = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i >> 1] >> (16 * (i & 1))) & 0xffffu), __NV_E4M3);
+    const float2 f = __half22float2(__half2(r));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+// byte address of the lo8 entry of the channel at fp16-element offset `off` (= pixel * C + channel) of a c8 plane; `cg` = that
+// channel's index inside its 64-channel group; the x8 entry sits 64 bytes further
+__device__ __forceinline__ uint8_t* c8_addr(void* plane, size_t off, int cg) {
+  return static_cast<uint8_t*>(plane) + 2 * off - cg;
+}
+__device__ __forceinline__ const uint8_t* c8_addr(const void* plane, size_t off, int cg) {
+  return static_cast<const uint8_t*>(plane) + 2 * off - cg;
+}
+// the c8 entries of 8 consecutive channels (fp32 values v, `hi` = their fp16 rounding) at dst = c8_addr(...)
+__device__ __forceinline__ void c8_store8(uint8_t* dst, const float* v, const uint4& hi) {
+  float r[8];
+  unpack8_f16(hi, r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = (v[i] - r[i]) * kC8LoScale;
+  *reinterpret_cast<uint2*>(dst) = pack8_e4m3(r);
+  *reinterpret_cast<uint2*>(dst + 64) = pack8_e4m3(v);
+}
+// lo plane of 8 consecutive channels, whichever format: r[i] += x - hi (c8: lo8 * 2^-11)
+__device__ __forceinline__ void lo8_add(const void* plane, int c8, size_t off, int cg, float* r) {
+  float l[8];
+  if (c8) {
+    unpack8_e4m3(__ldg(reinterpret_cast<const uint2*>(c8_addr(plane, off, cg))), l);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = fmaf(l[i], 1.f / kC8LoScale, r[i]);
+  } else {
+    unpack8_f16(__ldg(reinterpret_cast<const uint4*>(static_cast<const __half*>(plane) + off)), l);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] += l[i];
+  }
+}
+// write the lo plane of 8 consecutive channels, whichever format
+__device__ __forceinline__ void lo8_store(void* plane, int c8, size_t off, int cg, const float* v, const uint4& hi) {
+  if (c8) c8_store8(c8_addr(plane, off, cg), v, hi);
+  else *reinterpret_cast<uint4*>(static_cast<__half*>(plane) + off) = residual8_f16(v, hi);
+}
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* v) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -163,6 +228,22 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// e4m3 operands (kind::f8f6f4, K = 32 per instruction), same descriptors and fp32 accumulator
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = A * B + D * 2^-15 (scale-input-d): the first main-term MMA after the 2^15-scaled e4m3 corrections
+__device__ __forceinline__ void umma_f16_sd15(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 15;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
 // mbarrier arrive once all previously issued MMAs of this thread have completed (implies fence::before).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -225,6 +306,20 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, 
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair_sd15(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, 15;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
       : "memory");
 }
 // arrive on the barrier at this shared-memory offset in every CTA of `cta_mask` once all previously issued MMAs have completed

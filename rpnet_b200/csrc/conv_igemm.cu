@@ -19,6 +19,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <type_traits>
 
 namespace rpnet {
 
@@ -41,8 +42,12 @@ struct ConvParams {
   // seg_ach[s] on, against the weight chunks seg_wch[s].. of the packed weights.  Plain conv: (src0 | src1) channel concat.
   // Split-fp16 conv (x = hi + lo, w = Wh + Wl, all fp16): hi.Wh + lo.Wh + hi.Wl accumulated in fp32 — fp32-class products
   // from the fp16 tensor pipe (the dropped lo.Wl term is 2^-22 relative).
-  int nseg, kblocks_per_tap;
-  int seg_map[kMaxSeg], seg_ach[kMaxSeg], seg_wch[kMaxSeg], seg_n[kMaxSeg];
+  // fp8-correction conv (common.cuh, "c8"): hi.Wh on fp16 operands (kind 0 segments) + 2^-15 (lo8.Wh8 + x8.Wl8) on e4m3 operands
+  // (kind 1 segments: one 128-byte k-block of a c8 plane / pack = 64 channels of both corrections).  All kind 1 k-blocks of a tile
+  // run first (kb8_per_tap per tap); the first kind 0 MMA then scales the accumulator by 2^-15.
+  int nseg, kblocks_per_tap, kb8_per_tap;
+  int seg_map[kMaxSeg], seg_ach[kMaxSeg], seg_wch[kMaxSeg], seg_n[kMaxSeg], seg_kind[kMaxSeg];
+  int in_c8, out_c8;              // lo planes of the residual input / of the outputs are c8 planes instead of fp16 residuals
   int ntaps;
   int dy[kMaxTaps], dx[kMaxTaps];
   int tap_src[kMaxTaps];          // -1: channel concat of source 0 | source 1 (default); 0..3: the tap reads that source only
@@ -108,6 +113,42 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
                                     kMaxBnCout * 2 * 8 /*fused BN statistics*/;
 };
+
+// The MMAs of one k-block (one pipeline stage).  KIND 0: fp16 / bf16 operands; 1: e4m3 correction block; 2: the first fp16 block after
+// the corrections, whose first MMA scales the accumulator by 2^-15.  One straight-line instance per kind: predicating the kinds MMA by
+// MMA inside one loop cost the issuing thread a quarter of the tensor throughput.
+template <int CTAS, int HALO, int KIND, int STAGE_A_BYTES, int STAGE_B_BYTES>
+__device__ __forceinline__ void conv_issue_kblock(uint32_t a_addr, uint32_t b_addr, uint32_t d_tmem, uint32_t idesc, uint32_t acc_first) {
+  auto mma = [&](uint64_t a_desc, uint64_t b_desc, bool first) {
+    const uint32_t acc = first ? acc_first : 1u;
+    if (KIND == 1) {
+      if (CTAS == 2) umma_f8_pair(d_tmem, a_desc, b_desc, idesc, acc);
+      else           umma_f8(d_tmem, a_desc, b_desc, idesc, acc);
+    } else if (KIND == 2 && first) {
+      if (CTAS == 2) umma_f16_pair_sd15(d_tmem, a_desc, b_desc, idesc);
+      else           umma_f16_sd15(d_tmem, a_desc, b_desc, idesc);
+    } else {
+      if (CTAS == 2) umma_f16_pair(d_tmem, a_desc, b_desc, idesc, acc);
+      else           umma_f16(d_tmem, a_desc, b_desc, idesc, acc);
+    }
+  };
+  if (HALO) {
+    // three row offsets of the same halo box: 16 pixel rows = 2048 B apart (whole swizzle atoms), one weight tile each
+#pragma unroll
+    for (int dyi = 0; dyi < 3; ++dyi) {
+      const uint64_t a_desc = umma_desc_sw128(a_addr + dyi * 16 * 128, 1024);
+      const uint64_t b_desc = umma_desc_sw128(b_addr + dyi * STAGE_B_BYTES, 1024);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) mma(a_desc + 2 * k, b_desc + 2 * k, (dyi | k) == 0);
+    }
+  } else {
+    const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
+    const uint64_t b_desc = umma_desc_sw128(b_addr, 1024);
+    // advance 16 fp16 (32 e4m3) = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+#pragma unroll
+    for (int k = 0; k < kBK / 16; ++k) mma(a_desc + 2 * k, b_desc + 2 * k, k == 0);
+  }
+}
 
 template <int BN, int CTAS, int WS, int HALO = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -198,8 +239,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         const int tn = mt / p.tiles_y;
         const int x0 = tx * bw, y0 = ty * bh, n0 = tn * bn;
         if (HALO) {
+          for (int ph = p.kb8_per_tap ? 1 : 0; ph >= 0; --ph)
           for (int dxi = 0; dxi < 3; ++dxi) {
             for (int s = 0; s < p.nseg; ++s) {
+              if (p.seg_kind[s] != ph) continue;
               const int mi = p.seg_map[s];
               const CUtensorMap* tm = mi == 0 ? &tm_src0 : (mi == 1 ? &tm_src1 : (mi == 2 ? &tm_src2 : &tm_src3));
               const int ach0 = p.seg_ach[s], wch0 = p.seg_wch[s], sn = p.seg_n[s];
@@ -226,10 +269,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             }
           }
         } else
+        for (int ph = p.kb8_per_tap ? 1 : 0; ph >= 0; --ph)
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int xs = x0 + p.dx[tap], ys = y0 + p.dy[tap];
           const int ts = p.tap_src[tap];
           for (int s = 0; s < p.nseg; ++s) {
+            if (p.seg_kind[s] != ph) continue;
             const int mi = ts >= 0 ? ts : p.seg_map[s];
             const CUtensorMap* tm = mi == 0 ? &tm_src0 : (mi == 1 ? &tm_src1 : (mi == 2 ? &tm_src2 : &tm_src3));
             const int ach0 = p.seg_ach[s], wch0 = p.seg_wch[s], sn = p.seg_n[s];
@@ -256,7 +301,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0 && cta_rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(kBM * CTAS, BN) | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const uint32_t idesc8 = umma_idesc_f16(kBM * CTAS, BN);      // a / b format 0 = e4m3 for kind::f8f6f4 (F16 for kind::f16)
+      const uint32_t idesc = idesc8 | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
+      const int nkb8 = (HALO ? 3 : p.ntaps) * p.kb8_per_tap;       // leading e4m3 k-blocks of every tile
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -268,37 +315,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
         else           mbar_wait(&tempty_bar[as], aphase ^ 1);           // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        // one pipeline stage: wait for its operands, issue its MMAs (kind chosen at compile time), hand the slot back
+        auto kblock = [&](int kb, auto kind) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
-          if (HALO) {
-            // three row offsets of the same halo box: 16 pixel rows = 2048 B apart (whole swizzle atoms), one weight tile each
-#pragma unroll
-            for (int dyi = 0; dyi < 3; ++dyi) {
-              const uint64_t a_desc = umma_desc_sw128(a_addr + dyi * 16 * 128, 1024);
-              const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes + dyi * Cfg::kBBytes, 1024);
-#pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | dyi | k) != 0);
-                else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | dyi | k) != 0);
-              }
-            }
-          } else {
-          const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
-          const uint64_t b_desc = umma_desc_sw128(WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes, 1024);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-            if (CTAS == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            else           umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          }
-          }
+          const uint32_t b_addr = WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes;
+          conv_issue_kblock<CTAS, HALO, decltype(kind)::value, Cfg::kABytes, Cfg::kBBytes>(a_addr, b_addr, d_tmem,
+                                                                                           decltype(kind)::value == 1 ? idesc8 : idesc, kb != 0);
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
           if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3);
           else           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+        };
+        int kb = 0;
+        if (nkb8 > 0) {                                    // e4m3 corrections first, then the block that rescales the accumulator
+          for (; kb < nkb8; ++kb) kblock(kb, std::integral_constant<int, 1>());
+          kblock(kb++, std::integral_constant<int, 2>());
         }
+        for (; kb < num_kb; ++kb) kblock(kb, std::integral_constant<int, 0>());
         if (CTAS == 2) umma_commit_pair(&tfull_bar[as], 3);  // accumulator complete -> the epilogue of each CTA
         else           umma_commit(&tfull_bar[as]);
       }
@@ -391,14 +426,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) unpack8_f16(__ldg(rp + j), r + 8 * j);
             if (p.res_lo) {
-              const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + roff);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float l[8];
-                unpack8_f16(__ldg(rl + j), l);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) r[8 * j + i] += l[i];
-              }
+              for (int j = 0; j < 4; ++j) lo8_add(p.res_lo, p.in_c8, roff + 8 * j, (c0 + 8 * j) & 63, r + 8 * j);
             }
           }
 #pragma unroll
@@ -463,7 +492,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           for (int j = 0; j < 32; j += 8) {
             const uint4 hi = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
             *reinterpret_cast<uint4*>(o16 + c0 + j) = hi;
-            if (o16lo) *reinterpret_cast<uint4*>(o16lo + c0 + j) = residual8_f16(v + j, hi);
+            if (o16lo) lo8_store(p.out_lo, p.out_c8, static_cast<size_t>(o16lo - p.out_lo) + c0 + j, (c0 + j) & 63, v + j, hi);
           }
         }
         if (p.out_pool) {      // 2x2 max over (x, x^1) and (y, y^1): partner lanes lane^1 and lane^bw
@@ -477,7 +506,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             for (int j = 0; j < 32; j += 8) {
               const uint4 hi = p.out_bf16 ? pack8_bf16(v + j) : pack8_f16(v + j);
               *reinterpret_cast<uint4*>(opool + c0 + j) = hi;
-              if (opoollo) *reinterpret_cast<uint4*>(opoollo + c0 + j) = residual8_f16(v + j, hi);
+              if (opoollo) lo8_store(p.out_pool_lo, p.out_c8, static_cast<size_t>(opoollo - p.out_pool_lo) + c0 + j, (c0 + j) & 63, v + j, hi);
             }
           }
         }
@@ -701,7 +730,9 @@ struct ConvCall {
   // split-fp16: residual planes of the sources (same shapes) and a weight pack [ntaps][cout][2 * (c0 + c1)] = Wh | Wl
   const void* src0_lo = nullptr;
   const void* src1_lo = nullptr;
-  bool w_split = false;
+  // w_split: 0 fp16 weights; 1 pack [ntaps][cout][Wh | Wl] (three fp16 passes); 2 / 3 fp8 corrections: pack [ntaps][cout][Wh |
+  // per 64 channels (Wh8 | Wl8)], the sources' lo planes are c8 planes (common.cuh); 2 writes c8 lo planes, 3 fp16 residual planes
+  int w_split = 0;
   int n = 0, h = 0, w = 0;
   const void* wpack = nullptr; int ntaps = 0; const int* tap_dy = nullptr; const int* tap_dx = nullptr; int cout = 0;
   const float* scale = nullptr; const float* shift = nullptr; int relu = 0;
@@ -734,6 +765,10 @@ static int conv_igemm_run(const ConvCall& a) {
   RPNET_REQUIRE(!a_split || c1 == 0 || a.src1_lo, "conv_igemm: split sources need both residual planes");
   RPNET_REQUIRE(!(a_split || a.w_split) || (!a.tap_src && !bf16), "conv_igemm: split-fp16 operands are fp16, without per-tap views");
   const int BN = (cout % 256 == 0) ? 256 : (cout % 128 == 0 ? 128 : 64);
+  const bool c8 = a.w_split >= 2;
+  RPNET_REQUIRE(a.w_split >= 0 && a.w_split <= 3, "conv_igemm: w_split %d out of range [0, 3]", a.w_split);
+  RPNET_REQUIRE(!c8 || a_split, "conv_igemm: the fp8-correction pack needs the sources' c8 planes");
+  RPNET_REQUIRE(!c8 || !a.out_lo || (a.out_c % 64 == 0 && a.out_coff % 64 == 0), "conv_igemm: c8 output planes need 64-channel groups");
 
   ConvParams p{};
   p.N = n; p.H = h; p.W = w;
@@ -748,16 +783,22 @@ static int conv_igemm_run(const ConvCall& a) {
     // K segments of one tap: tensor maps 0 / 1 = the sources, 2 / 3 = their residual planes
     const int n0 = c0 / kBK, n1 = c1 / kBK, ncin = n0 + n1;
     int s = 0;
-    auto seg = [&](int map, int wch, int cnt) {
-      if (cnt > 0) { p.seg_map[s] = map; p.seg_ach[s] = 0; p.seg_wch[s] = wch; p.seg_n[s] = cnt; ++s; }
+    auto seg = [&](int map, int wch, int cnt, int kind) {
+      if (cnt > 0) { p.seg_map[s] = map; p.seg_ach[s] = 0; p.seg_wch[s] = wch; p.seg_n[s] = cnt; p.seg_kind[s] = kind; ++s; }
     };
-    seg(0, 0, n0);
-    seg(1, n0, n1);
-    if (a_split) { seg(2, 0, n0); seg(3, n0, n1); }
-    if (a.w_split) { seg(0, ncin, n0); seg(1, ncin + n0, n1); }
+    seg(0, 0, n0, 0);
+    seg(1, n0, n1, 0);
+    if (c8) {                                      // e4m3 corrections: c8 planes against the second half of the pack
+      seg(2, ncin, n0, 1);
+      seg(3, ncin + n0, n1, 1);
+    } else {
+      if (a_split) { seg(2, 0, n0, 0); seg(3, n0, n1, 0); }
+      if (a.w_split) { seg(0, ncin, n0, 0); seg(1, ncin + n0, n1, 0); }
+    }
     p.nseg = s;
-    p.kblocks_per_tap = 0;
-    for (int i = 0; i < s; ++i) p.kblocks_per_tap += p.seg_n[i];
+    p.kblocks_per_tap = 0; p.kb8_per_tap = 0;
+    for (int i = 0; i < s; ++i) { p.kblocks_per_tap += p.seg_n[i]; if (p.seg_kind[i]) p.kb8_per_tap += p.seg_n[i]; }
+    p.in_c8 = c8 ? 1 : 0; p.out_c8 = a.w_split == 2 ? 1 : 0;
   }
   p.ntaps = ntaps;
   for (int i = 0; i < ntaps; ++i) { p.dy[i] = a.tap_dy[i]; p.dx[i] = a.tap_dx[i]; p.tap_src[i] = a.tap_src ? a.tap_src[i] : -1; }
@@ -927,7 +968,7 @@ RPNET_API int rpnet_conv_split_res_f16(const void* src0_hi, const void* src0_lo,
                                         int keep_sums, void* stream_) {
   ConvCall a = plain_call(false, src0_hi, c0, src1_hi, c1, n, h, w, wpack, ntaps, tap_dy, tap_dx, cout, scale, shift, relu, stream_);
   a.res = res_hi; a.res_lo = res_lo;
-  a.src0_lo = src0_lo; a.src1_lo = src1_lo; a.w_split = w_split != 0;
+  a.src0_lo = src0_lo; a.src1_lo = src1_lo; a.w_split = w_split;
   a.out = out_hi; a.out_lo = out_lo; a.out_h = out_h; a.out_w = out_w; a.out_c = out_c; a.out_coff = out_coff;
   a.oy_mul = oy_mul; a.oy_off = oy_off; a.ox_mul = ox_mul; a.ox_off = ox_off;
   a.out_pool = out_pool_hi; a.out_pool_lo = out_pool_lo; a.out_f32 = out_f32;

@@ -54,7 +54,7 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][CIN][3][3]*/,
                      const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
-                     __half* __restrict__ out_lo, int N, int H, int W) {
+                     __half* __restrict__ out_lo, int lo_fmt, int N, int H, int W) {
   __shared__ float s_w[9 * CIN][64];      // [tap*CIN + ci][co]
   __shared__ float s_sc[64], s_sh[64];
   for (int i = threadIdx.x; i < 64 * CIN * 9; i += blockDim.x) {
@@ -97,7 +97,7 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
     }
     const uint4 hi = pack8(acc);
     *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = hi;
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 8) = residual8_f16(acc, hi);
+    if (out_lo) lo8_store(out_lo, lo_fmt, (size_t)pix * 64 + cg * 8, cg * 8, acc, hi);
   }
 }
 
@@ -107,7 +107,7 @@ conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wg
 __global__ void __launch_bounds__(256)
 conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][1][3][3]*/,
                         const float* __restrict__ scale, const float* __restrict__ shift, int relu, __half* __restrict__ out,
-                        __half* __restrict__ out_lo, int N, int H, int W) {
+                        __half* __restrict__ out_lo, int lo_fmt, int N, int H, int W) {
   const int cg = threadIdx.x & 7;
   float wr[9][8], sh[8];
 #pragma unroll
@@ -156,8 +156,8 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
     *reinterpret_cast<uint4*>(out + pix * 64 + cg * 8) = h0;
     if (x + 1 < W) *reinterpret_cast<uint4*>(out + (pix + 1) * 64 + cg * 8) = h1;
     if (out_lo) {                                                 // split-fp16 residual plane
-      *reinterpret_cast<uint4*>(out_lo + pix * 64 + cg * 8) = residual8_f16(a0, h0);
-      if (x + 1 < W) *reinterpret_cast<uint4*>(out_lo + (pix + 1) * 64 + cg * 8) = residual8_f16(a1, h1);
+      lo8_store(out_lo, lo_fmt, (size_t)pix * 64 + cg * 8, cg * 8, a0, h0);
+      if (x + 1 < W) lo8_store(out_lo, lo_fmt, (size_t)(pix + 1) * 64 + cg * 8, cg * 8, a1, h1);
     }
   }
 }
@@ -167,7 +167,7 @@ conv3x3_first_c1_kernel(const float* __restrict__ img, const float* __restrict__
 // weights live in shared memory as [tap][64], 8 threads per output pixel x 8 channels each.
 __global__ void __launch_bounds__(256)
 conv7x7s2_stem_kernel(const float* __restrict__ img, const float* __restrict__ wgt /*[64][3][7][7]*/, const float* __restrict__ scale,
-                      const float* __restrict__ shift, int relu, __half* __restrict__ out, __half* __restrict__ out_lo, int N, int H, int W) {
+                      const float* __restrict__ shift, int relu, __half* __restrict__ out, __half* __restrict__ out_lo, int lo_fmt, int N, int H, int W) {
   __shared__ float s_w[147][64];
   for (int i = threadIdx.x; i < 64 * 147; i += blockDim.x) s_w[i % 147][i / 147] = wgt[i];
   __syncthreads();
@@ -201,7 +201,7 @@ conv7x7s2_stem_kernel(const float* __restrict__ img, const float* __restrict__ w
     }
     const uint4 hi = pack8(acc);
     *reinterpret_cast<uint4*>(out + (size_t)p * 64 + cg * 8) = hi;
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + (size_t)p * 64 + cg * 8) = residual8_f16(acc, hi);
+    if (out_lo) lo8_store(out_lo, lo_fmt, (size_t)p * 64 + cg * 8, cg * 8, acc, hi);
   }
 }
 
@@ -588,7 +588,7 @@ upsample_tail_kernel(const float* __restrict__ pred, float* __restrict__ logits,
 // net/vgg.py:24-30).  One thread per output pixel x 8 channels.
 // ---------------------------------------------------------------------------------------------------
 __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __restrict__ in_lo, uint4* __restrict__ out,
-                                   uint4* __restrict__ out_lo, uint2* __restrict__ idx, int N, int H, int W, int c8, int Ho, int Wo, int k,
+                                   uint4* __restrict__ out_lo, uint2* __restrict__ idx, int lo_fmt, int N, int H, int W, int c8, int Ho, int Wo, int k,
                                    int stride, int pad) {
   const long long total = (long long)N * Ho * Wo * c8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -607,12 +607,8 @@ __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __
         if (x < 0 || x >= W) continue;
         float v[8];
         unpack8(__ldg(in + ((long long)(n * H + y) * W + x) * c8 + cv), v);
-        if (in_lo) {                              // split-fp16: the value is hi + lo (exact in fp32)
-          float l[8];
-          unpack8(__ldg(in_lo + ((long long)(n * H + y) * W + x) * c8 + cv), l);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += l[j];
-        }
+        if (in_lo)                                // split-fp16: the value is hi + lo (exact in fp32; c8 plane: lo8 * 2^-11)
+          lo8_add(in_lo, lo_fmt, (size_t)(((long long)(n * H + y) * W + x) * c8 + cv) * 8, (cv * 8) & 63, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (v[j] > best[j]) { best[j] = v[j]; arg[j] = (unsigned)(dy * k + dx); }
@@ -620,7 +616,7 @@ __global__ void maxpool_f16_kernel(const uint4* __restrict__ in, const uint4* __
     }
     const uint4 hi = pack8(best);
     out[i] = hi;
-    if (out_lo) out_lo[i] = residual8_f16(best, hi);
+    if (out_lo) lo8_store(out_lo, lo_fmt, (size_t)i * 8, (cv * 8) & 63, best, hi);
     if (idx) idx[i] = make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24), arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24));
   }
 }
@@ -637,53 +633,54 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 6; }
+RPNET_API int rpnet_abi_version(void) { return 7; }
 
 RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
-                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_);
+                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream_);
 
 RPNET_API int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                        const float* shift, int relu, void* out_f16, void* stream_) {
-  return rpnet_conv3x3_first_split_f16(img, n, cin, h, w, weight, scale, shift, relu, out_f16, nullptr, stream_);
+  return rpnet_conv3x3_first_split_f16(img, n, cin, h, w, weight, scale, shift, relu, out_f16, nullptr, 0, stream_);
 }
 
 RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
-                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_) {
+                                             const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv3x3_first: null pointer argument");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0, "conv3x3_first: bad shape %d x %d x %d", n, h, w);
   RPNET_REQUIRE(cin >= 1 && cin <= 3, "conv3x3_first: cin must be 1, 2 or 3 (got %d)", cin);
+  RPNET_REQUIRE(lo_fmt == 0 || lo_fmt == 1, "conv3x3_first: lo_fmt %d", lo_fmt);
   const long long total = (long long)n * h * w * 8;
   const int grid = grid_for(total, 256);
   if (cin == 1)
     conv3x3_first_c1_kernel<<<grid_for((long long)n * h * ((w + 1) / 2) * 8, 256), 256, 0, stream>>>(
-        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), n, h, w);
+        img, weight, scale, shift, relu, static_cast<__half*>(out_f16), static_cast<__half*>(out_lo_f16), lo_fmt, n, h, w);
   else if (cin == 2)      // mask_feature_map: x (net/unet.py:401-402, 437-438): image + mask channel
     conv3x3_first_kernel<2><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
-                                                      static_cast<__half*>(out_lo_f16), n, h, w);
+                                                      static_cast<__half*>(out_lo_f16), lo_fmt, n, h, w);
   else
     conv3x3_first_kernel<3><<<grid, 256, 0, stream>>>(img, weight, scale, shift, relu, static_cast<__half*>(out_f16),
-                                                      static_cast<__half*>(out_lo_f16), n, h, w);
+                                                      static_cast<__half*>(out_lo_f16), lo_fmt, n, h, w);
   return check_cuda(cudaGetLastError(), "conv3x3_first launch");
 }
 
 RPNET_API int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
-                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_);
+                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream_);
 
 RPNET_API int rpnet_conv7x7s2_stem_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
                                         const float* shift, int relu, void* out_f16, void* stream_) {
-  return rpnet_conv7x7s2_stem_split_f16(img, n, h, w, weight, scale, shift, relu, out_f16, nullptr, stream_);
+  return rpnet_conv7x7s2_stem_split_f16(img, n, h, w, weight, scale, shift, relu, out_f16, nullptr, 0, stream_);
 }
 
 RPNET_API int rpnet_conv7x7s2_stem_split_f16(const float* img, int n, int h, int w, const float* weight, const float* scale,
-                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, void* stream_) {
+                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(img && weight && scale && shift && out_f16, "conv7x7s2_stem: null pointer argument");
   RPNET_REQUIRE(n > 0 && h >= 7 && w >= 7 && (long long)n * h * w < (1LL << 31), "conv7x7s2_stem: bad shape %d x %d x %d", n, h, w);
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   conv7x7s2_stem_kernel<<<grid_for((long long)n * ho * wo * 8, 256), 256, 0, stream>>>(img, weight, scale, shift, relu,
                                                                                     static_cast<__half*>(out_f16),
-                                                                                    static_cast<__half*>(out_lo_f16), n, h, w);
+                                                                                    static_cast<__half*>(out_lo_f16), lo_fmt, n, h, w);
   return check_cuda(cudaGetLastError(), "conv7x7s2_stem launch");
 }
 
@@ -824,32 +821,33 @@ RPNET_API int rpnet_upsample_tail_f32(const float* pred, float* logits, float* m
   return check_cuda(cudaGetLastError(), "upsample_tail launch");
 }
 
-RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
-                                       int stride, int pad, void* stream_);
-RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, void* idx_u8, int n, int h, int w, int c,
-                                     int k, int stride, int pad, void* stream_);
+RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int lo_fmt, int n, int h, int w, int c,
+                                       int k, int stride, int pad, void* stream_);
+RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, int lo_fmt, void* idx_u8, int n, int h, int w,
+                                     int c, int k, int stride, int pad, void* stream_);
 
 RPNET_API int rpnet_maxpool_f16(const void* in, void* out, int n, int h, int w, int c, int k, int stride, int pad, void* stream_) {
-  return rpnet_maxpool_split_f16(in, nullptr, out, nullptr, n, h, w, c, k, stride, pad, stream_);
+  return rpnet_maxpool_split_f16(in, nullptr, out, nullptr, 0, n, h, w, c, k, stride, pad, stream_);
 }
 
-RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int n, int h, int w, int c, int k,
-                                       int stride, int pad, void* stream_) {
-  return rpnet_maxpool_idx_f16(in, in_lo, out, out_lo, nullptr, n, h, w, c, k, stride, pad, stream_);
+RPNET_API int rpnet_maxpool_split_f16(const void* in, const void* in_lo, void* out, void* out_lo, int lo_fmt, int n, int h, int w, int c,
+                                       int k, int stride, int pad, void* stream_) {
+  return rpnet_maxpool_idx_f16(in, in_lo, out, out_lo, lo_fmt, nullptr, n, h, w, c, k, stride, pad, stream_);
 }
 
-RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, void* idx_u8, int n, int h, int w, int c,
-                                     int k, int stride, int pad, void* stream_) {
+RPNET_API int rpnet_maxpool_idx_f16(const void* in, const void* in_lo, void* out, void* out_lo, int lo_fmt, void* idx_u8, int n, int h, int w,
+                                     int c, int k, int stride, int pad, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(k <= 15, "maxpool: window %d too large for the uint8 argmax positions", k);
   RPNET_REQUIRE(in && out, "maxpool: null pointer argument");
   RPNET_REQUIRE((in_lo == nullptr) == (out_lo == nullptr), "maxpool: residual planes go in and out together");
+  RPNET_REQUIRE(lo_fmt == 0 || (lo_fmt == 1 && c % 64 == 0), "maxpool: lo_fmt %d (c8 planes need c %% 64 == 0, c = %d)", lo_fmt, c);
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
   RPNET_REQUIRE(k >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= k, "maxpool: bad window k=%d stride=%d pad=%d", k, stride, pad);
   const int ho = (h + 2 * pad - k) / stride + 1, wo = (w + 2 * pad - k) / stride + 1;
   const long long total = (long long)n * ho * wo * (c / 8);
   maxpool_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(in), static_cast<const uint4*>(in_lo),
                                                                 static_cast<uint4*>(out), static_cast<uint4*>(out_lo),
-                                                                static_cast<uint2*>(idx_u8), n, h, w, c / 8, ho, wo, k, stride, pad);
+                                                                static_cast<uint2*>(idx_u8), lo_fmt, n, h, w, c / 8, ho, wo, k, stride, pad);
   return check_cuda(cudaGetLastError(), "maxpool launch");
 }

@@ -199,7 +199,7 @@ template <bool POOL>
 __global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, const float* __restrict__ stats, Groups gr, int N, int H,
                 int W, int c8, int relu, uint4* __restrict__ y16, uint4* __restrict__ y16_lo, float* __restrict__ y32,
-                uint4* __restrict__ ypool, uint4* __restrict__ ypool_lo) {
+                uint4* __restrict__ ypool, uint4* __restrict__ ypool_lo, int lo_fmt) {
   constexpr int U = POOL ? 2 : 4;
   const int C = c8 * 8;
   const int lanes = 256 / c8;
@@ -273,7 +273,7 @@ bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, con
         if (y16) {
           const uint4 hi = pack8_f16(f);
           y16[(size_t)pix[k][q] * c8 + v] = hi;
-          if (y16_lo) y16_lo[(size_t)pix[k][q] * c8 + v] = residual8_f16(f, hi);
+          if (y16_lo) lo8_store(y16_lo, lo_fmt, ((size_t)pix[k][q] * c8 + v) * 8, (v * 8) & 63, f, hi);
         }
         if (y32) {
           float4* d = reinterpret_cast<float4*>(y32 + ((size_t)pix[k][q] * c8 + v) * 8);
@@ -284,7 +284,7 @@ bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, con
       if (POOL) {
         const uint4 hi = pack8_f16(best);
         ypool[(size_t)u * c8 + v] = hi;
-        if (ypool_lo) ypool_lo[(size_t)u * c8 + v] = residual8_f16(best, hi);
+        if (ypool_lo) lo8_store(ypool_lo, lo_fmt, ((size_t)u * c8 + v) * 8, (v * 8) & 63, best, hi);
       }
     }
   }
@@ -790,6 +790,21 @@ __global__ void soft_mask_bwd_kernel(const float* __restrict__ logits, const flo
 // One block per 32 (cout) x 32 (cin) tile: the fp32 weights of the tile (32 x 32 x taps, contiguous runs of 32 * taps floats
 // per cout) are staged in shared memory, so that both packs leave as coalesced rows — wf rows run along cin, the transposed
 // wd rows along cout.
+// one weight of a split forward pack row [Wh (cin) | second half]: split 1 -> Wl fp16 (cin); split 2 -> the fp8 corrections, per 64
+// input channels 128 bytes = Wh8 (64) | Wl8 (64) (common.cuh, "c8")
+__device__ __forceinline__ void store_split_weight(__half* row, int cin, int ci, float val, int split) {
+  const __half hi = __float2half_rn(val);
+  const float lo = val - __half2float(hi);
+  row[ci] = hi;
+  if (split == 2) {
+    uint8_t* g = reinterpret_cast<uint8_t*>(row + cin) + (ci >> 6) * 128 + (ci & 63);
+    g[0] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * kC8WhScale, __NV_SATFINITE, __NV_E4M3);
+    g[64] = (uint8_t)__nv_cvt_float_to_fp8(lo * kC8WlScale, __NV_SATFINITE, __NV_E4M3);
+  } else {
+    row[cin + ci] = __float2half_rn(lo);
+  }
+}
+
 __device__ __forceinline__ void pack_conv_weight_tile(float (*s_w)[32 * 9 + 1], int tile, const float* __restrict__ w, int cout, int cin,
                                                       int ntaps, int hole_start, int hole_len, __half* __restrict__ wf,
                                                       __nv_bfloat16* __restrict__ wd, int split) {
@@ -813,14 +828,10 @@ __device__ __forceinline__ void pack_conv_weight_tile(float (*s_w)[32 * 9 + 1], 
     for (int r = rowi; r < 32; r += 8) {
       if (wf && co0 + r < cout && ci0 + lane < cin) {              // wf[t][co][ci]: lanes along ci
         const float val = s_w[r][lane * ntaps + t];
-        const __half hi = __float2half_rn(val);
-        if (split) {                                               // split-fp16 pack [t][co][Wh (cin) | Wl (cin)]
-          __half* row = wf + ((size_t)t * cout + co0 + r) * (2 * cin);
-          row[ci0 + lane] = hi;
-          row[cin + ci0 + lane] = __float2half_rn(val - __half2float(hi));
-        } else {
-          wf[((size_t)t * cout + co0 + r) * cin + ci0 + lane] = hi;
-        }
+        if (split)                                                 // split pack [t][co][Wh (cin) | Wl (cin) or fp8 corrections]
+          store_split_weight(wf + ((size_t)t * cout + co0 + r) * (2 * cin), cin, ci0 + lane, val, split);
+        else
+          wf[((size_t)t * cout + co0 + r) * cin + ci0 + lane] = __float2half_rn(val);
       }
       if (wd && ci0 + r < cin && co0 + lane < cout)                // wd[t][ci][co]: lanes along co
         wd[((size_t)t * cin + ci0 + r) * cout + co0 + lane] = __float2bfloat16_rn(s_w[lane][r * ntaps + t]);
@@ -879,14 +890,10 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, int cout,
                 const int ry = py == 0 ? (ky == 0 ? 0 : 1) : (ky == 2 ? 1 : 0), rx = px == 0 ? (kx == 0 ? 0 : 1) : (kx == 2 ? 1 : 0);
                 if (ry == ty && rx == tx) s += k[ky][kx];
               }
-            const __half hi = __float2half_rn(s);
-            if (split) {                                           // [phase][tap][co][Wh (cin) | Wl (cin)]
-              __half* row = wf + (((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * (2 * cin);
-              row[ci] = hi;
-              row[cin + ci] = __float2half_rn(s - __half2float(hi));
-            } else {
-              wf[(((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * cin + ci] = hi;
-            }
+            if (split)                                             // [phase][tap][co][Wh (cin) | Wl (cin) or fp8 corrections]
+              store_split_weight(wf + (((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * (2 * cin), cin, ci, s, split);
+            else
+              wf[(((size_t)(py * 2 + px) * 4 + ty * 2 + tx) * cout + co) * cin + ci] = __float2half_rn(s);
           }
     // data gradient: S(-1) = {2}, S(0) = {1, 2}, S(1) = {0, 1}, S(2) = {0}
 #pragma unroll
@@ -1083,7 +1090,7 @@ RPNET_API int rpnet_bn_stats_split_f16(const void* z, const void* z_lo, int n, i
                                         double* sums, void* stream_);
 RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
                                         const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
-                                        void* y_pool_lo_f16, float* y_f32, void* stream_);
+                                        void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream_);
 
 RPNET_API int rpnet_bn_stats_f16(const void* z, int n, int h, int w, int c, const int* group_start, int groups, double* sums,
                                   void* stream_) {
@@ -1122,14 +1129,15 @@ RPNET_API int rpnet_bn_finalize_f32(const double* sums, const int* group_start, 
 RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h, int w, int c, const int* group_start, int groups,
                                   int relu, void* y_f16, void* y_pool_f16, float* y_f32, void* stream_) {
   return rpnet_bn_apply_split_f16(z, nullptr, stats, n, h, w, c, group_start, groups, relu, y_f16, nullptr, y_pool_f16, nullptr, y_f32,
-                                  stream_);
+                                  0, stream_);
 }
 
 RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
                                         const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
-                                        void* y_pool_lo_f16, float* y_f32, void* stream_) {
+                                        void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE((!y_lo_f16 || y_f16) && (!y_pool_lo_f16 || y_pool_f16), "bn_apply: a residual output needs its main output");
+  RPNET_REQUIRE(lo_fmt == 0 || (lo_fmt == 1 && c % 64 == 0), "bn_apply: lo_fmt %d (c8 planes need c %% 64 == 0, c = %d)", lo_fmt, c);
   RPNET_REQUIRE(z && stats, "bn_apply: null pointer argument");
   RPNET_REQUIRE(y_f16 || y_pool_f16 || y_f32, "bn_apply: no output requested");
   RPNET_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "bn_apply: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
@@ -1148,11 +1156,11 @@ RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const fl
   if (y_pool_f16)
     bn_apply_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
                                                              h, w, c / 8, relu, static_cast<uint4*>(y_f16), static_cast<uint4*>(y_lo_f16),
-                                                             y_f32, static_cast<uint4*>(y_pool_f16), static_cast<uint4*>(y_pool_lo_f16));
+                                                             y_f32, static_cast<uint4*>(y_pool_f16), static_cast<uint4*>(y_pool_lo_f16), lo_fmt);
   else
     bn_apply_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
                                                               h, w, c / 8, relu, static_cast<uint4*>(y_f16),
-                                                              static_cast<uint4*>(y_lo_f16), y_f32, nullptr, nullptr);
+                                                              static_cast<uint4*>(y_lo_f16), y_f32, nullptr, nullptr, lo_fmt);
   return check_cuda(cudaGetLastError(), "bn_apply launch");
 }
 
@@ -1288,6 +1296,7 @@ RPNET_API int rpnet_pack_conv_weight_split(const float* w, int cout, int cin_rea
                 "pack_conv_weight: bad shape");
   const int cin = cin_real + hole_len;
   RPNET_REQUIRE(ntaps <= 9, "pack_conv_weight: at most 9 taps (got %d)", ntaps);
+  RPNET_REQUIRE(split >= 0 && split <= 2 && (split != 2 || cin % 64 == 0), "pack_conv_weight: split %d (fp8 corrections need cin %% 64 == 0)", split);
   const int tiles = ((cout + 31) / 32) * ((cin + 31) / 32);
   pack_conv_weight_kernel<<<tiles, 256, 0, stream>>>(w, cout, cin, ntaps, hole_start, hole_len, static_cast<__half*>(w_fwd_f16),
                                                      static_cast<__nv_bfloat16*>(w_dgrad_bf16), split);
@@ -1308,6 +1317,7 @@ RPNET_API int rpnet_pack_conv_weights(const rpnet_pack_desc* descs_host, int n, 
     PackLayer& L = t.l[i];
     L.w = d.w; L.wf = static_cast<__half*>(d.w_fwd_f16); L.wd = static_cast<__nv_bfloat16*>(d.w_dgrad_bf16);
     L.cout = d.cout; L.cin = d.cin_real + d.hole_len; L.ntaps = d.ntaps; L.hole_start = d.hole_start; L.hole_len = d.hole_len;
+    RPNET_REQUIRE(d.split >= 0 && d.split <= 2 && (d.split != 2 || L.cin % 64 == 0), "pack_conv_weights: layer %d: split %d", i, d.split);
     L.split = d.split; L.first_tile = tiles;
     tiles += ((L.cout + 31) / 32) * ((L.cin + 31) / 32);
   }
@@ -1393,6 +1403,7 @@ RPNET_API int rpnet_pack_upconv_weight(const float* w, int cout, int cin, void* 
 RPNET_API int rpnet_pack_upconv_weight_split(const float* w, int cout, int cin, void* wf_f16, int split, void* w16_bf16, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   RPNET_REQUIRE(w && wf_f16 && w16_bf16 && cout > 0 && cin > 0, "pack_upconv_weight: bad argument");
+  RPNET_REQUIRE(split >= 0 && split <= 2 && (split != 2 || cin % 64 == 0), "pack_upconv_weight: split %d (fp8 corrections need cin %% 64 == 0)", split);
   pack_upconv_weight_kernel<<<grid_for((long long)cout * cin, 256), 256, 0, stream>>>(w, cout, cin, static_cast<__half*>(wf_f16),
                                                                                     static_cast<__nv_bfloat16*>(w16_bf16), split);
   return check_cuda(cudaGetLastError(), "pack_upconv_weight launch");

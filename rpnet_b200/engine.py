@@ -14,16 +14,31 @@ WEIGHTS_EPOCH = 0
 TAPS_3X3 = [(ky - 1, kx - 1) for ky in range(3) for kx in range(3)]
 
 # Arithmetic of the encoder convs (yaml key `b200_precision`, default from the environment variable RPNET_PRECISION):
-#   'split' (default): split-fp16 - every encoder activation and weight travels as hi + lo fp16 planes and the tensor cores
-#                      accumulate hi.Wh + lo.Wh + hi.Wl in fp32: logits within 1e-3 (rel-Linf) of the reference's fp32 forward;
-#   'fp16'           : single-term fp16 operands (the 11-bit significand of a TF32 cuDNN conv): 3x fewer tensor-core passes,
+#   'split8' (default): x.w = hi.Wh + 2^-15 (lo8.Wh8 + x8.Wl8) - the main term on fp16 operands, the two first-order corrections on
+#                      e4m3 operands at twice the MMA rate (include/rpnet_b200.h "fp8 corrections"): every encoder activation
+#                      travels as an fp16 plane + a c8 plane.  Two units of tensor time per conv; logits within 1e-3 (rel-Linf)
+#                      of the reference's fp32 forward, the same error as 'split' (a correction is 2^-11 of the product, its
+#                      e4m3 rounding 2^-15);
+#   'split'          : split-fp16 - hi + lo fp16 planes and Wh | Wl packs, hi.Wh + lo.Wh + hi.Wl in fp32 (three units);
+#   'fp16'           : single-term fp16 operands (the 11-bit significand of a TF32 cuDNN conv): one unit of tensor time,
 #                      logits 2e-3 .. 5e-3 from the fp32 reference on unsaturated fixtures.
-PRECISIONS = ('split', 'fp16')
+PRECISIONS = ('split8', 'split', 'fp16')
+# weight-pack levels (the `w_split` of ConvPack / ops.conv_split / the pack kernels): fp16 weights, Wh | Wl, Wh | fp8 corrections
+W_FP16, W_SPLIT, W_C8 = 0, 1, 2
+
+
+def is_split(p):
+    """Activations of precision `p` travel as (hi, lo) plane pairs."""
+    return p in ('split8', 'split', 'split-a')
+
+
+def w_level(p):
+    return {'split8': W_C8, 'split': W_SPLIT}.get(p, W_FP16)
 
 
 def default_precision():
     import os
-    p = os.environ.get('RPNET_PRECISION', 'split')
+    p = os.environ.get('RPNET_PRECISION', 'split8')
     if p not in PRECISIONS:
         raise ValueError('RPNET_PRECISION=%r (expected one of %r)' % (p, PRECISIONS))
     return p
@@ -43,7 +58,7 @@ def decoder_precision(p):
     5.0e-4 .. 5.6e-4 instead of 3.5e-4 .. 4.9e-4 from the fp32 oracle on the 8 x 256 x 256 eval fixture (margin error 7.6e-4
     against the 1e-3 gate) — the default stays the full three-term product everywhere (margin over speed)."""
     import os
-    if p != 'split':
+    if p != 'split':                                   # 'split8' runs the same (two-unit) arithmetic everywhere
         return p
     return 'split-a' if os.environ.get('RPNET_SPLIT_DECODER', '3') == '2' else 'split'
 
@@ -71,9 +86,10 @@ class ConvPack:
     __slots__ = ('wpack', 'taps', 'scale', 'shift', 'relu', 'cout', 'cin', 'split', 'w_split')
 
     def __init__(self, wpack, taps, scale, shift, relu, split=False, w_split=None):
-        # split: activations travel as hi + lo planes; w_split: the pack carries Wl as well (three-term product)
+        # split: activations travel as hi + lo planes; w_split: weight-pack level (W_FP16 / W_SPLIT: Wl as well, three-term product /
+        # W_C8: fp8 corrections, the lo planes are c8 planes)
         self.wpack, self.taps, self.scale, self.shift, self.relu, self.split = wpack, taps, scale, shift, relu, split
-        self.w_split = split if w_split is None else w_split
+        self.w_split = int(split if w_split is None else w_split)
         self.cout, self.cin = wpack.shape[1], wpack.shape[2] // (2 if self.w_split else 1)
 
 
@@ -81,6 +97,63 @@ def split_f16(x):
     """fp32 tensor -> (hi, lo) fp16 pair with hi + lo == x to ~2^-22 relative."""
     hi = x.to(torch.float16)
     return hi, (x - hi.float()).to(torch.float16)
+
+
+C8_LO_SCALE, C8_WH_SCALE, C8_WL_SCALE = 2.0 ** 11, 2.0 ** 4, 2.0 ** 15      # csrc/common.cuh, "c8"
+
+
+def _e4m3(x):
+    return x.clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def _c8_interleave(a8, b8):
+    """two uint8 tensors [..., C] -> [..., 2 * C]: per 64 channels, 64 bytes of a8 then 64 bytes of b8."""
+    c = a8.shape[-1]
+    assert c % 64 == 0, 'c8 planes / packs need a multiple of 64 channels (got %d)' % c
+    lead = a8.shape[:-1]
+    return torch.stack((a8.reshape(*lead, c // 64, 64), b8.reshape(*lead, c // 64, 64)), dim=-2).reshape(*lead, 2 * c).contiguous()
+
+
+def split_c8(x):
+    """fp32 NHWC tensor -> (hi fp16 [..., C], c8 plane uint8 [..., 2 * C]): per 64 channels lo8 = e4m3((x - hi) * 2^11) | x8 = e4m3(x)."""
+    hi = x.to(torch.float16)
+    return hi, _c8_interleave(_e4m3((x - hi.float()) * C8_LO_SCALE), _e4m3(x))
+
+
+def split_planes(x, level):
+    return split_c8(x) if level == W_C8 else split_f16(x)
+
+
+def c8_lo(plane):
+    """fp32 residual x - hi held by a c8 plane [..., 2 * C] (to the 2^-4 relative precision of its e4m3 entries)."""
+    c = plane.shape[-1] // 2
+    lo8 = plane.reshape(*plane.shape[:-1], c // 64, 2, 64)[..., 0, :].reshape(*plane.shape[:-1], c).contiguous()
+    return lo8.view(torch.float8_e4m3fn).float() / C8_LO_SCALE
+
+
+def join_planes(hi, lo):
+    """fp32 value of a (hi, lo) activation pair, whichever format the lo plane has."""
+    if lo is None:
+        return hi.float()
+    return hi.float() + (c8_lo(lo) if lo.dtype == torch.uint8 else lo.float())
+
+
+def lo_buffer(ws, name, shape, device, level):
+    """Workspace buffer of the lo plane of an activation [n, h, w, C]: fp16 residual plane, or the c8 plane (uint8, 2 * C)."""
+    if level == W_C8:
+        return ws.get(name, tuple(shape[:-1]) + (2 * shape[-1],), torch.uint8, device)
+    return ws.get(name, shape, torch.float16, device)
+
+
+def split_weight(w32, level):
+    """fp32 [..., cin] (K innermost) -> fp16 pack row [..., cin] / [..., 2 * cin] of weight-pack level `level`."""
+    if level == W_FP16:
+        return w32.to(torch.float16).contiguous()
+    hi, lo = split_f16(w32)
+    if level == W_SPLIT:
+        return torch.cat((hi, lo), dim=-1).contiguous()
+    corr = _c8_interleave(_e4m3(hi.float() * C8_WH_SCALE), _e4m3((w32 - hi.float()) * C8_WL_SCALE))
+    return torch.cat((hi, corr.view(torch.float16)), dim=-1).contiguous()
 
 
 def hi_of(a):
@@ -104,11 +177,11 @@ def fold_bn(conv_bias, bn_weight=None, bn_bias=None, running_mean=None, running_
 
 
 def pack_weight_taps(weight, dilation=1, split=False):
-    """[cout, cin, k, k] fp32 -> fp16 [k*k, cout, cin] (split: [k*k, cout, 2*cin] = Wh | Wl) + tap offsets
-    (cross-correlation, 'same' padding)."""
+    """[cout, cin, k, k] fp32 -> fp16 [k*k, cout, cin] (split = W_SPLIT: [k*k, cout, 2*cin] = Wh | Wl; W_C8: Wh | fp8 corrections)
+    + tap offsets (cross-correlation, 'same' padding)."""
     cout, cin, kh, kw = weight.shape
     w32 = weight.detach().float().permute(2, 3, 0, 1).reshape(kh * kw, cout, cin)
-    w = (torch.cat(split_f16(w32), dim=2) if split else w32.to(torch.float16)).contiguous()
+    w = split_weight(w32, int(split))
     taps = [((ky - kh // 2) * dilation, (kx - kw // 2) * dilation) for ky in range(kh) for kx in range(kw)]
     return w, taps
 
@@ -131,7 +204,7 @@ def pack_upsample_phases(weight, split=False):
                     taps.append((dy, dx))
                     mats.append(m)
             m = torch.stack(mats, dim=0)
-            wp = (torch.cat(split_f16(m), dim=2) if split else m.to(torch.float16)).contiguous()
+            wp = split_weight(m, int(split))
             out.append((wp, taps, (py, px)))
     return out
 
@@ -161,8 +234,8 @@ def run_conv(pack, src0, ws, name, src1=None, want_out=True, want_pool=False, ou
     pool = ws.get(name + '.pool', (n, h // 2, w // 2, pack.cout), f16, dev) if want_pool else None
     o32 = ws.get(name + '.f32', (n, h, w, pack.cout), torch.float32, dev) if out_f32 else None
     if pack.split:
-        out_lo = ws.get(name + '.lo', (n, h, w, pack.cout), f16, dev) if out is not None else None
-        pool_lo = ws.get(name + '.pool.lo', (n, h // 2, w // 2, pack.cout), f16, dev) if want_pool else None
+        out_lo = lo_buffer(ws, name + '.lo', (n, h, w, pack.cout), dev, pack.w_split) if out is not None else None
+        pool_lo = lo_buffer(ws, name + '.pool.lo', (n, h // 2, w // 2, pack.cout), dev, pack.w_split) if want_pool else None
         ops.conv_split(hi_of(src0), pack.wpack, pack.taps, pack.scale, pack.shift, pack.relu, src0_lo=lo_of(src0),
                        src1=None if src1 is None else hi_of(src1), src1_lo=None if src1 is None else lo_of(src1), w_split=pack.w_split,
                        out=out, out_lo=out_lo, out_pool=pool, out_pool_lo=pool_lo, out_f32=o32)
@@ -183,9 +256,10 @@ def run_upconv(phases, scale, shift, src, ws, name, split=False, w_split=None):
     dev = hi_of(src).device
     out = ws.get(name, (n, 2 * h, 2 * w, cout), torch.float16, dev)
     if split:
-        out_lo = ws.get(name + '.lo', (n, 2 * h, 2 * w, cout), torch.float16, dev)
+        w_split = int(split if w_split is None else w_split)
+        out_lo = lo_buffer(ws, name + '.lo', (n, 2 * h, 2 * w, cout), dev, w_split)
         for wp, taps, (py, px) in phases:
-            ops.conv_split(hi_of(src), wp, taps, scale, shift, True, src0_lo=lo_of(src), w_split=split if w_split is None else w_split,
+            ops.conv_split(hi_of(src), wp, taps, scale, shift, True, src0_lo=lo_of(src), w_split=w_split,
                            out=out, out_lo=out_lo, out_map=(2, py, 2, px))
         return out, out_lo
     for wp, taps, (py, px) in phases:
@@ -198,6 +272,6 @@ def nchw_f32_to_nhwc_f16(x):
 
 
 def nhwc_to_nchw_f32(x):
-    if isinstance(x, tuple):                       # split-fp16 pair
-        x = x[0].float() + x[1].float() if x[1] is not None else x[0]
+    if isinstance(x, tuple):                       # split pair (fp16 residual or c8 plane)
+        x = join_planes(x[0], x[1])
     return x.permute(0, 3, 1, 2).float().contiguous()

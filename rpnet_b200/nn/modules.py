@@ -54,7 +54,8 @@ def run_conv_any(conv, bn, x_nhwc_or_img, ws, name, pack, relu=True, **kw):
                 if bn is not None else engine.fold_bn(conv.bias)
         n, _, h, w = x_nhwc_or_img.shape
         out = ws.get(name, (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device)
-        out_lo = ws.get(name + '.lo', (n, h, w, conv.out_channels), torch.float16, x_nhwc_or_img.device) if kw.get('split') else None
+        out_lo = engine.lo_buffer(ws, name + '.lo', (n, h, w, conv.out_channels), x_nhwc_or_img.device, kw.get('w_level', engine.W_SPLIT)) \
+            if kw.get('split') else None
         ops.conv3x3_first(x_nhwc_or_img.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, relu, out,
                           out_lo=out_lo)
         return ((out, out_lo) if out_lo is not None else out), None
@@ -66,7 +67,7 @@ class conv_block(_PackedModule):
         super(conv_block, self).__init__()
         _check_norm(normalization_type)
         pr = precision or engine.default_precision()                           # engine.PRECISIONS (+ 'split-a': fp16 weights)
-        self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
+        self.split, self.w_split = engine.is_split(pr), engine.w_level(pr)
         if kernel != 3 or padding != 1:
             raise NotImplementedError('conv_block: only kernel=3, padding=1 is used by RP-Net')
         self.inorm = normalization_type == 'InstanceNorm2d'
@@ -101,7 +102,7 @@ class conv_block(_PackedModule):
         _check_eval(self)
         p0, p1 = self._packs()
         if isinstance(p0, tuple):
-            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', p0, split=self.split)
+            a, _ = run_conv_any(self.conv[0], self.conv[1], x, ws, name + '.0', p0, split=self.split, w_level=self.w_split)
         else:
             a, _ = engine.run_conv(p0, x, ws, name + '.0', src1=x1)
         return engine.run_conv(p1, a, ws, name + '.3', want_out=want_out, want_pool=want_pool)
@@ -120,7 +121,7 @@ class up_conv(_PackedModule):
         _check_norm(normalization_type)
         self.inorm = normalization_type == 'InstanceNorm2d'
         pr = precision or engine.default_precision()
-        self.split, self.w_split = pr in ('split', 'split-a'), pr == 'split'
+        self.split, self.w_split = engine.is_split(pr), engine.w_level(pr)
         if kernel != 3 or padding != 1:
             raise NotImplementedError('up_conv: only kernel=3, padding=1 is used by RP-Net')
         self.ch_in = ch_in

@@ -26,13 +26,15 @@ class ResNet18(_PackedModule):
                 BasicBlock(cout, cout)))
         self.backbone = nn.Sequential(*modules)
         self.backbone.out_channels = 512
-        # arithmetic of the 15 tensor-core convs: 'split' (fp32-class, default) or 'fp16' — engine.PRECISIONS; the reference's
-        # constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False` (like nn/vgg.py)
-        self.split = engine.default_precision() == 'split'
+        # arithmetic of the 15 tensor-core convs: 'split8' (fp32-class, default), 'split' or 'fp16' — engine.PRECISIONS; the
+        # reference's constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False`
+        # (+ `encoder.w_level`), like nn/vgg.py
+        self.split = engine.is_split(engine.default_precision())
+        self.w_level = engine.w_level(engine.default_precision())
         self._ws = engine.Workspace()
 
     def _signature(self):
-        return super()._signature() + (self.split,)
+        return super()._signature() + (self.split, self.w_level)
 
     def _blocks(self):
         return [blk for stage in list(self.backbone)[4:] for blk in stage]
@@ -46,8 +48,9 @@ class ResNet18(_PackedModule):
             def cb(conv, bn, relu):
                 bias = conv.bias if conv.bias is not None else torch.zeros(conv.out_channels, device=conv.weight.device)
                 scale, shift = engine.fold_bn(bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-                wp, taps = engine.pack_weight_taps(conv.weight, split=self.split)
-                return engine.ConvPack(wp, taps, scale, shift, relu, split=self.split)
+                lvl = self.w_level if self.split else engine.W_FP16
+                wp, taps = engine.pack_weight_taps(conv.weight, split=lvl)
+                return engine.ConvPack(wp, taps, scale, shift, relu, split=self.split, w_split=lvl)
             down = cb(blk.downsample[0], blk.downsample[1], False) if blk.downsample is not None else None
             packs.append((cb(blk.conv1, blk.bn1, True), cb(blk.conv2, blk.bn2, True), down))
         return stem, packs
@@ -63,11 +66,11 @@ class ResNet18(_PackedModule):
         f16, sp = torch.float16, self.split
 
         def buf(name, shape):                                            # hi plane (+ residual plane in split precision)
-            return ws.get(name, shape, f16, dev), (ws.get(name + '.lo', shape, f16, dev) if sp else None)
+            return ws.get(name, shape, f16, dev), (engine.lo_buffer(ws, name + '.lo', shape, dev, self.w_level) if sp else None)
 
         def conv(pk, src, dst, res=(None, None)):
             if sp:
-                ops.conv_split(src[0], pk.wpack, pk.taps, pk.scale, pk.shift, pk.relu, src0_lo=src[1], w_split=True, out=dst[0],
+                ops.conv_split(src[0], pk.wpack, pk.taps, pk.scale, pk.shift, pk.relu, src0_lo=src[1], w_split=pk.w_split, out=dst[0],
                                out_lo=dst[1], res=res[0], res_lo=res[1])
             else:
                 ops.conv_res(src[0], pk.wpack, pk.taps, pk.scale, pk.shift, dst[0], res=res[0], relu=pk.relu)

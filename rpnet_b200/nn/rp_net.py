@@ -151,7 +151,8 @@ class RP_Net(nn.Module):
 
         if self.config['backbone'] == 'vgg':
             self.encoder = Encoder(in_channels, self.pretrained_path)
-            self.encoder.split = engine.precision_of(backbone_cfg) == 'split'
+            self.encoder.split = engine.is_split(engine.precision_of(backbone_cfg))
+            self.encoder.w_level = engine.w_level(engine.precision_of(backbone_cfg))
             num_feat = 512
         elif self.config['backbone'] == 'UNet':
             self.encoder = U_Net(backbone_cfg)
@@ -162,6 +163,8 @@ class RP_Net(nn.Module):
         elif self.config['backbone'] == 'resnet':
             from .resnet import ResNet18
             self.encoder = ResNet18(use_pretrained=False)                 # net/rp_net.py:208-209 (eval only here)
+            self.encoder.split = engine.is_split(engine.precision_of(backbone_cfg))
+            self.encoder.w_level = engine.w_level(engine.precision_of(backbone_cfg))
             num_feat = 512
         else:
             raise NotImplementedError(self.config['backbone'])              # net/rp_net.py:218-219

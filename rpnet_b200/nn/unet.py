@@ -43,7 +43,7 @@ class U_Net(Unet_2D):
         num_feats = [64, 128, 256, 512, 1024]
         norm = cfg['unet_normalize_type']
         self.inorm = norm == 'InstanceNorm2d'
-        pr = engine.precision_of(cfg)          # 'split' (fp32-class, default) or 'fp16' (engine.PRECISIONS)
+        pr = engine.precision_of(cfg)          # 'split8' (fp32-class, default), 'split' or 'fp16' (engine.PRECISIONS)
         pd = engine.decoder_precision(pr)      # decoder half: the same, or fp16 weights with RPNET_SPLIT_DECODER=2 (engine.decoder_precision)
         self.Conv1 = conv_block(ch_in=self.img_ch + (1 if self.mfm == 'x' else 0), ch_out=num_feats[0], normalization_type=norm, precision=pr)
         self.Conv2 = conv_block(ch_in=num_feats[0] + (1 if self.mfm == 'x2' else 0), ch_out=num_feats[1], normalization_type=norm, precision=pr)
@@ -58,15 +58,16 @@ class U_Net(Unet_2D):
 
     def _mask_source(self, mask, pool, ws, name, split):
         """The extra conv source of mask_feature_map x2 / x3: avg_pool2d(mask, pool) in channel 0 of a 64-channel fp16 NHWC tensor
-        (the packed weights are zero for the 63 padding channels).  Quarter / sixteenth steps are exact in fp16: lo plane = 0."""
+        (the packed weights are zero for the 63 padding channels).  Quarter / sixteenth steps are exact in fp16: the residual is 0
+        (a c8 plane still carries the e4m3 copy of the mask for the x8 . Wl8 correction)."""
         n, _, H, W = mask.shape
         m = ws.get(name, (n, H // pool, W // pool, 64), torch.float16, mask.device)
         m.zero_()
         m[..., 0] = F.avg_pool2d(mask.float(), pool)[:, 0].to(torch.float16)
         if not split:
             return m
-        lo = ws.get(name + '.lo', tuple(m.shape), torch.float16, mask.device)
-        lo.zero_()
+        lo = engine.lo_buffer(ws, name + '.lo', tuple(m.shape), mask.device, self.Conv1.w_split)
+        lo.copy_(engine.split_planes(m.float(), self.Conv1.w_split)[1])
         return m, lo
 
     def encode_nhwc(self, x, tag='enc', mask=None):

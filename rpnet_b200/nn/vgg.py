@@ -25,9 +25,11 @@ class Encoder(_PackedModule):
         )
         self._init_weights()
         self._ws = engine.Workspace()
-        # arithmetic of the 12 tensor-core convs: 'split' (fp32-class, default) or 'fp16' — engine.PRECISIONS; the reference's
-        # constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False`
-        self.split = engine.default_precision() == 'split'
+        # arithmetic of the 12 tensor-core convs: 'split8' (fp32-class, default), 'split' or 'fp16' — engine.PRECISIONS; the
+        # reference's constructor has no config argument, so the choice comes from RPNET_PRECISION / `encoder.split = False`
+        # (+ `encoder.w_level`, the weight-pack level engine.W_SPLIT / engine.W_C8)
+        self.split = engine.is_split(engine.default_precision())
+        self.w_level = engine.w_level(engine.default_precision())
 
     def _make_layer(self, n_convs, in_channels, out_channels, dilation=1, lastRelu=True):
         layer = []
@@ -51,6 +53,9 @@ class Encoder(_PackedModule):
                 new_dic[new_keys[i]] = dic[keys[i]]
             self.load_state_dict(new_dic)
 
+    def _signature(self):
+        return super()._signature() + (self.split, self.w_level)
+
     def _build_packs(self):
         plan = []       # ('conv', conv, pack-or-None, relu) | ('pool', k, s, p)
         for blk in self.features:
@@ -65,8 +70,9 @@ class Encoder(_PackedModule):
                         plan.append(('first', m, None, relu))
                     else:
                         scale, shift = engine.fold_bn(m.bias)
-                        wp, taps = engine.pack_weight_taps(m.weight, m.dilation[0], split=self.split)
-                        plan.append(('conv', m, engine.ConvPack(wp, taps, scale, shift, relu, split=self.split), relu))
+                        lvl = self.w_level if self.split else engine.W_FP16
+                        wp, taps = engine.pack_weight_taps(m.weight, m.dilation[0], split=lvl)
+                        plan.append(('conv', m, engine.ConvPack(wp, taps, scale, shift, relu, split=self.split, w_split=lvl), relu))
         return plan
 
     def encode_nhwc(self, x, tag='vgg', trace=None):
@@ -82,7 +88,7 @@ class Encoder(_PackedModule):
                 scale, shift = engine.fold_bn(conv.bias)
                 n, _, h, w = x.shape
                 cur = ws.get(name, (n, h, w, 64), torch.float16, x.device)
-                lo = ws.get(name + '.lo', (n, h, w, 64), torch.float16, x.device) if self.split else None
+                lo = engine.lo_buffer(ws, name + '.lo', (n, h, w, 64), x.device, self.w_level) if self.split else None
                 ops.conv3x3_first(x.float().contiguous(), conv.weight.detach().float().contiguous(), scale, shift, step[3], cur, out_lo=lo)
                 cur = (cur, lo) if self.split else cur
                 if trace is not None:
@@ -100,7 +106,7 @@ class Encoder(_PackedModule):
                 idx = ws.get(name + '.idx', shp, torch.uint8, x.device) if trace is not None else None
                 prev = cur
                 if self.split:
-                    out_lo = ws.get(name + '.lo', shp, torch.float16, x.device)
+                    out_lo = engine.lo_buffer(ws, name + '.lo', shp, x.device, self.w_level)
                     ops.maxpool(cur[0], k, s, p, out, x_lo=cur[1], out_lo=out_lo, idx=idx)
                     cur = (out, out_lo)
                 else:

@@ -59,6 +59,29 @@ def _req(t, dtype, name):
     return t
 
 
+def _lo_fmt(pairs):
+    """Format of the lo planes of a call (include/rpnet_b200.h `lo_fmt`): every (lo, hi, name) with lo not None must be either the
+    fp16 residual plane of hi (same shape; returns 0) or its c8 plane (uint8, last dim doubled; returns 1) — all the same."""
+    fmt = None
+    for t, ref, nm in pairs:
+        if t is None:
+            continue
+        if ref is None:
+            raise _lib.RpnetError('%s given without its main plane' % nm)
+        if t.dtype == torch.uint8:
+            _req(t, torch.uint8, nm)
+            ok, f = tuple(t.shape) == tuple(ref.shape[:-1]) + (2 * ref.shape[-1],) and ref.shape[-1] % 64 == 0, 1
+        else:
+            _req(t, torch.float16, nm)
+            ok, f = t.shape == ref.shape, 0
+        if not ok:
+            raise _lib.RpnetError('%s %s does not match its main plane %s' % (nm, tuple(t.shape), tuple(ref.shape)))
+        if fmt is not None and fmt != f:
+            raise _lib.RpnetError('%s: fp16 residual planes and c8 planes mixed in one call' % nm)
+        fmt = f
+    return fmt or 0
+
+
 def conv_igemm(src0, wpack, taps, scale, shift, relu=True, src1=None, out=None, out_pool=None, out_f32=None,
                out_map=None, out_coff=0):
     """src0/src1: fp16 NHWC [n,h,w,c]; wpack fp16 [ntaps,cout,cin]; taps: list of (dy, dx).
@@ -118,18 +141,17 @@ def conv_cos(src0, wpack, taps, scale, shift, protos, pred, relu=True, src1=None
 
 
 def conv3x3_first(img, weight, scale, shift, relu, out, out_lo=None):
-    """out_lo: optional residual plane fp16(y - fp16(y)) of the split-fp16 representation."""
+    """out_lo: optional lo plane of the split representation — the fp16 residual fp16(y - fp16(y)), or (a uint8 tensor with the last
+    dim doubled) the c8 plane of include/rpnet_b200.h "fp8 corrections"."""
     lib = _lib.load()
     _req(img, torch.float32, 'img'); _req(weight, torch.float32, 'weight'); _req(out, torch.float16, 'out')
     n, cin, h, w = img.shape
     assert tuple(weight.shape) == (64, cin, 3, 3) and tuple(out.shape) == (n, h, w, 64)
-    if out_lo is not None:
-        _req(out_lo, torch.float16, 'out_lo')
-        assert out_lo.shape == out.shape
+    lo_fmt = _lo_fmt([(out_lo, out, 'out_lo')])
     with _Timed('conv3x3_first', float(img.numel() * 4 + out.numel() * (2 if out_lo is None else 4))):
         rc = lib.rpnet_conv3x3_first_split_f16(_ptr(img), n, cin, h, w, _ptr(weight), _ptr(_req(scale, torch.float32, 'scale')),
                                                _ptr(_req(shift, torch.float32, 'shift')), int(bool(relu)), _ptr(out), _ptr(out_lo),
-                                               _stream())
+                                               int(lo_fmt), _stream())
     _lib.check(rc, 'rpnet_conv3x3_first_split_f16')
 
 
@@ -137,7 +159,9 @@ def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=No
                out_lo=None, out_pool=None, out_pool_lo=None, out_f32=None, out_map=None, out_coff=0, group_start=None, sums=None,
                keep_sums=False, res=None, res_lo=None):
     """Split-fp16 tap-list conv (include/rpnet_b200.h, rpnet_conv_split_f16): sources and outputs as hi / lo fp16 planes,
-    wpack fp16 [ntaps, cout, (c0 + c1) * (2 if w_split else 1)] = Wh | Wl.  sums (fp64) + group_start: train-mode BatchNorm
+    wpack fp16 [ntaps, cout, (c0 + c1) * (2 if w_split else 1)] = Wh | Wl.  w_split = 2: fp8 corrections — the lo planes (sources,
+    residual: uint8, last dim doubled) are c8 planes and the second half of the pack holds Wh8 | Wl8; the OUTPUT lo planes may be c8
+    planes or fp16 residuals (the pre-BatchNorm z of the train path).  sums (fp64) + group_start: train-mode BatchNorm
     statistics of the fp32 accumulators (scale = 1, shift = 0, relu = False).  res / res_lo: residual planes [n, h, w, cout] added
     after the affine and before the ReLU (BasicBlock)."""
     lib = _lib.load()
@@ -145,10 +169,9 @@ def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=No
     _req(scale, torch.float32, 'scale'); _req(shift, torch.float32, 'shift')
     n, h, w, c0 = src0.shape
     c1 = 0
-    for t, ref, nm in ((src0_lo, src0, 'src0_lo'), (src1_lo, src1, 'src1_lo')):
-        if t is not None:
-            _req(t, torch.float16, nm)
-            assert ref is not None and t.shape == ref.shape
+    in_fmt = _lo_fmt([(src0_lo, src0, 'src0_lo'), (src1_lo, src1, 'src1_lo'), (res_lo, res, 'res_lo')])
+    if (int(w_split) == 2) != (in_fmt == 1):
+        raise _lib.RpnetError('conv_split: w_split = %d needs %s source lo planes' % (int(w_split), 'c8' if int(w_split) == 2 else 'fp16'))
     if src1 is not None:
         _req(src1, torch.float16, 'src1')
         assert src1.shape[:3] == src0.shape[:3]
@@ -166,15 +189,14 @@ def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=No
         _req(out, torch.float16, 'out')
         assert out.shape[0] == n
         oh, ow, oc = out.shape[1:]
-        if out_lo is not None:
-            _req(out_lo, torch.float16, 'out_lo')
-            assert out_lo.shape == out.shape
     if out_pool is not None:
         _req(out_pool, torch.float16, 'out_pool')
         assert tuple(out_pool.shape) == (n, h // 2, w // 2, cout)
-        if out_pool_lo is not None:
-            _req(out_pool_lo, torch.float16, 'out_pool_lo')
-            assert out_pool_lo.shape == out_pool.shape
+    out_fmt = _lo_fmt([(out_lo, out, 'out_lo'), (out_pool_lo, out_pool, 'out_pool_lo')])
+    if out_fmt == 1 and int(w_split) != 2:
+        raise _lib.RpnetError('conv_split: c8 output planes need w_split = 2')
+    have_lo_out = out_lo is not None or out_pool_lo is not None
+    w_mode = (3 if (have_lo_out and out_fmt == 0) else 2) if int(w_split) == 2 else int(bool(w_split))
     if out_f32 is not None:
         _req(out_f32, torch.float32, 'out_f32')
         assert tuple(out_f32.shape) == (n, h, w, cout)
@@ -185,12 +207,11 @@ def conv_split(src0, wpack, taps, scale, shift, relu=True, src0_lo=None, src1=No
         assert sums.numel() >= g * cout * 2
     # `work` stays the reference's (algorithmic) FLOPs of the conv; the kernel executes 1 + (lo planes) + (Wl) passes of them
     with _Timed('conv_igemm', 2.0 * n * h * w * cout * cin * ntaps):
-        for t, nm in ((res, 'res'), (res_lo, 'res_lo')):
-            if t is not None:
-                _req(t, torch.float16, nm)
-                assert tuple(t.shape) == (n, h, w, cout)
+        if res is not None:
+            _req(res, torch.float16, 'res')
+            assert tuple(res.shape) == (n, h, w, cout)
         rc = lib.rpnet_conv_split_res_f16(_ptr(src0), _ptr(src0_lo), c0, _ptr(src1), _ptr(src1_lo), c1, n, h, w, _ptr(wpack),
-                                          int(bool(w_split)), ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_lo),
+                                          w_mode, ntaps, dy, dx, cout, _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_lo),
                                           int(bool(relu)), _ptr(out), _ptr(out_lo), oh, ow, oc, out_coff, om[0], om[1], om[2], om[3],
                                           _ptr(out_pool), _ptr(out_pool_lo), _ptr(out_f32), gs, g, _ptr(sums), int(bool(keep_sums)),
                                           _stream())
@@ -287,21 +308,20 @@ def upsample_tail(pred, logits, mask_out, scale, soft_mask):
 
 
 def maxpool(x, k, stride, pad, out, x_lo=None, out_lo=None, idx=None):
-    """x_lo / out_lo: residual planes of a split-fp16 activation (max of hi + lo, re-split); idx: optional uint8 tensor like `out`
+    """x_lo / out_lo: lo planes of a split activation, fp16 residuals or c8 planes (max of hi + lo, re-split); idx: optional uint8 tensor like `out`
     that receives the window position of the first maximum (for maxpool_bwd)."""
     lib = _lib.load()
     _req(x, torch.float16, 'x'); _req(out, torch.float16, 'out')
     n, h, w, c = x.shape
     ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
     assert tuple(out.shape) == (n, ho, wo, c) and (x_lo is None) == (out_lo is None)
-    if x_lo is not None:
-        _req(x_lo, torch.float16, 'x_lo'); _req(out_lo, torch.float16, 'out_lo')
-        assert x_lo.shape == x.shape and out_lo.shape == out.shape
+    lo_fmt = _lo_fmt([(x_lo, x, 'x_lo'), (out_lo, out, 'out_lo')])
     if idx is not None:
         _req(idx, torch.uint8, 'idx')
         assert idx.shape == out.shape
     with _Timed('maxpool', float((x.numel() * 2 + out.numel() * 2) * (1 if x_lo is None else 2))):
-        _lib.check(lib.rpnet_maxpool_idx_f16(_ptr(x), _ptr(x_lo), _ptr(out), _ptr(out_lo), _ptr(idx), n, h, w, c, k, stride, pad, _stream()),
+        _lib.check(lib.rpnet_maxpool_idx_f16(_ptr(x), _ptr(x_lo), _ptr(out), _ptr(out_lo), int(lo_fmt), _ptr(idx), n, h, w, c, k, stride, pad,
+                                             _stream()),
                    'rpnet_maxpool_idx_f16')
     
 
@@ -449,8 +469,8 @@ def maxpool_bwd(dy, idx, k, stride, pad, dx):
 
 
 def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):
-    """w fp32 [cout, cin_real, kh, kw] -> w_fwd fp16 [taps, cout, cin] (split: [taps, cout, 2 * cin] = Wh | Wl) /
-    w_dgrad bf16 [taps, cin, cout]."""
+    """w fp32 [cout, cin_real, kh, kw] -> w_fwd fp16 [taps, cout, cin] (split 1: [taps, cout, 2 * cin] = Wh | Wl; split 2: Wh | fp8
+    corrections, same shape) / w_dgrad bf16 [taps, cin, cout]."""
     lib = _lib.load()
     _req(w, torch.float32, 'w')
     cout, cin_real = w.shape[:2]
@@ -458,7 +478,7 @@ def pack_conv_weight(w, w_fwd=None, w_dgrad=None, hole=(0, 0), split=False):
     if w_fwd is not None:
         assert w_fwd.numel() == ntaps * cout * (cin_real + hole[1]) * (2 if split else 1)
     with _Timed('pack_conv_weight', float(w.numel() * 8)):
-        _lib.check(lib.rpnet_pack_conv_weight_split(_ptr(w), cout, cin_real, ntaps, hole[0], hole[1], _ptr(w_fwd), int(bool(split)),
+        _lib.check(lib.rpnet_pack_conv_weight_split(_ptr(w), cout, cin_real, ntaps, hole[0], hole[1], _ptr(w_fwd), int(split),
                                                     _ptr(w_dgrad), _stream()), 'rpnet_pack_conv_weight_split')
 
 
@@ -477,7 +497,7 @@ def pack_conv_weights(layers):
         _req(w, torch.float32, 'w')
         d.w, d.w_fwd_f16, d.w_dgrad_bf16 = w.data_ptr(), (wf.data_ptr() if wf is not None else None), (wd.data_ptr() if wd is not None else None)
         d.cout, d.cin_real, d.ntaps = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
-        d.hole_start, d.hole_len, d.split = int(hole[0]), int(hole[1]), int(bool(split))
+        d.hole_start, d.hole_len, d.split = int(hole[0]), int(hole[1]), int(split)
         nbytes += w.numel() * 8
     return arr, nbytes
 
@@ -535,19 +555,21 @@ def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, 
 
 
 def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None, z_lo=None, y_lo=None, y_pool_lo=None):
-    """z_lo / y_lo / y_pool_lo: residual planes of the split-fp16 representation (z = z + z_lo; y written as hi + lo)."""
+    """z_lo: fp16 residual plane of z (z = z + z_lo); y_lo / y_pool_lo: lo planes of the outputs — fp16 residual planes, or c8 planes
+    (uint8, last dim doubled; include/rpnet_b200.h "fp8 corrections")."""
     lib = _lib.load()
     _req(z, torch.float16, 'z')
     n, h, w, c = z.shape
     gs, g = _groups(group_start)
-    for t, ref in ((z_lo, z), (y_lo, y), (y_pool_lo, y_pool)):
-        if t is not None:
-            _req(t, torch.float16, 'residual plane')
-            assert ref is not None and t.shape == ref.shape
+    _lo_fmt([(z_lo, z, 'z_lo')])
+    if z_lo is not None and z_lo.dtype != torch.float16:
+        raise _lib.RpnetError('bn_apply: z_lo is the fp16 residual plane of the pre-BatchNorm conv output')
+    lo_fmt = _lo_fmt([(y_lo, y, 'y_lo'), (y_pool_lo, y_pool, 'y_pool_lo')])
     nb = sum(t.numel() * t.element_size() for t in (z, z_lo, y, y_lo, y_pool, y_pool_lo, y_f32) if t is not None)
     with _Timed('bn_apply', float(nb)):
         _lib.check(lib.rpnet_bn_apply_split_f16(_ptr(z), _ptr(z_lo), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(y), _ptr(y_lo),
-                                                _ptr(y_pool), _ptr(y_pool_lo), _ptr(y_f32), _stream()), 'rpnet_bn_apply_split_f16')
+                                                _ptr(y_pool), _ptr(y_pool_lo), _ptr(y_f32), int(lo_fmt), _stream()),
+                   'rpnet_bn_apply_split_f16')
 
 
 def bn_bwd(z, stats, group_start, dz, scratch, relu=True, direct=None, d_off=0, pooled=None, p_off=0, up=None, u_off=0,
@@ -825,7 +847,7 @@ def pack_upconv_weight(w, wf, w16, split=False):
     cout, cin = w.shape[:2]
     assert tuple(wf.shape) == (4, 4, cout, cin * (2 if split else 1)) and tuple(w16.shape) == (16, cin, cout)
     with _Timed('pack_conv_weight', float(w.numel() * 12)):
-        _lib.check(lib.rpnet_pack_upconv_weight_split(_ptr(w), cout, cin, _ptr(wf), int(bool(split)), _ptr(w16), _stream()),
+        _lib.check(lib.rpnet_pack_upconv_weight_split(_ptr(w), cout, cin, _ptr(wf), int(split), _ptr(w16), _stream()),
                    'rpnet_pack_upconv_weight_split')
 
 
@@ -907,11 +929,9 @@ def conv7x7s2_stem(img, weight, scale, shift, out, relu=True, out_lo=None):
     n, c, h, w = img.shape
     assert c == 3 and tuple(weight.shape) == (64, 3, 7, 7) and tuple(out.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64)
     with _Timed('conv7x7s2_stem', float(img.numel() * 4 + out.numel() * 2)):
-        if out_lo is not None:
-            _req(out_lo, torch.float16, 'out_lo')
-            assert out_lo.shape == out.shape
+        lo_fmt = _lo_fmt([(out_lo, out, 'out_lo')])
         _lib.check(lib.rpnet_conv7x7s2_stem_split_f16(_ptr(img), n, h, w, _ptr(weight), _ptr(scale), _ptr(shift), int(bool(relu)),
-                                                      _ptr(out), _ptr(out_lo), _stream()), 'rpnet_conv7x7s2_stem_split_f16')
+                                                      _ptr(out), _ptr(out_lo), int(lo_fmt), _stream()), 'rpnet_conv7x7s2_stem_split_f16')
 
 
 # =====================================================================================================

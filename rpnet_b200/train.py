@@ -155,10 +155,11 @@ class _ConvBN:
     """One conv (bias dropped: it cancels in batch- / instance-statistics normalisation) + BatchNorm(batch stats) + ReLU of the path."""
 
     def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False, w_split=None):
-        # split: the forward runs in split-fp16 (x = hi + lo planes; with w_split weights Wh | Wl: three tensor-core passes,
-        # fp32-class result; without: hi.W + lo.W); the backward is unchanged (it reads the hi planes).
+        # split: the forward runs on (hi, lo) plane pairs; w_split = weight-pack level: engine.W_C8 (fp8 corrections, two units of
+        # tensor time, the default), engine.W_SPLIT (Wh | Wl, three fp16 passes), engine.W_FP16 (hi.W + lo.W); all fp32-class but the
+        # last.  The backward is unchanged (it reads the hi planes).
         self.name, self.conv, self.bn, self.first, self.hole, self.up, self.split = name, conv, bn, first, hole, up, split
-        self.w_split = split if w_split is None else w_split
+        self.w_split = int(split if w_split is None else w_split)
         if not isinstance(bn, nn.BatchNorm2d):                 # nn.InstanceNorm2d: no parameters, no buffers
             self.bn = bn = _NoAffineNorm(conv.out_channels, conv.weight.device, getattr(bn, 'eps', 1e-5))
         affine = isinstance(bn, nn.BatchNorm2d)
@@ -272,16 +273,18 @@ class EncoderEngine:
         # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
         # train-mode logits 2e-3 .. 5e-3 from the fp32 reference)
         pr = engine.precision_of(cfg if cfg is not None else encoder.cfg)
-        self.split = sp = pr == 'split'
-        wd = engine.decoder_precision(pr) == 'split'     # decoder half: RPNET_SPLIT_DECODER=2 -> split activations, fp16 weights
+        self.split = sp = engine.is_split(pr)
+        lv = engine.w_level(pr)
+        self.lo_level = engine.W_C8 if lv == engine.W_C8 else engine.W_SPLIT      # format of the activations' lo planes
+        wd = engine.w_level(engine.decoder_precision(pr))  # decoder half: RPNET_SPLIT_DECODER=2 -> 'split' activations, fp16 weights
         e, L = encoder, {}
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
-            ws = sp and (wd or not nm.startswith('uc'))
+            ws = wd if nm.startswith('uc') else lv
             L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], flat, first=(nm == 'c1'), split=sp, w_split=ws)
             L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], flat, split=sp, w_split=ws)
-        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], flat, up=True, split=sp, w_split=sp and wd)
-        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], flat, up=True, split=sp, w_split=sp and wd)
+        L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], flat, up=True, split=sp, w_split=wd)
+        L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], flat, up=True, split=sp, w_split=wd)
         self.L = L
         self.ws = engine.Workspace()
         self._scratch = {}
@@ -343,9 +346,14 @@ class EncoderEngine:
                 ops.pack_upconv_weight(l.conv.weight.data, l.wf_up, l.w16_up, split=l.w_split)
 
     # ------------------------------------------------------------------ encoder
-    def pair(self, name, shape, lo):
-        """(hi, lo) fp16 planes of one activation; lo is None outside split mode."""
-        return (self.buf(name, shape, f16), self.buf(name + '.lo', shape, f16) if lo else None)
+    def pair(self, name, shape, lo, z=False):
+        """(hi, lo) planes of one activation; lo is None outside split mode, the fp16 residual plane for a pre-normalisation conv
+        output `z` (|mean| >> std: it needs the full residual) and in 'split' precision, the c8 plane in 'split8'."""
+        if not lo:
+            return self.buf(name, shape, f16), None
+        if z or self.lo_level != engine.W_C8:
+            return self.buf(name, shape, f16), self.buf(name + '.lo', shape, f16)
+        return self.buf(name, shape, f16), self.buf(name + '.lo', tuple(shape[:-1]) + (2 * shape[-1],), torch.uint8)
 
     def _layer_fwd(self, key, x0, x1, gs, want_y=True, want_pool=False):
         """x0 / x1: (hi, lo) pairs (x0 = the fp32 image batch for the first conv).  Returns the (hi, lo) pairs of y and of
@@ -353,7 +361,7 @@ class EncoderEngine:
         l = self.L[key]
         n, h, w = (x0.shape[0], x0.shape[2], x0.shape[3]) if l.first else x0[0].shape[:3]
         c = l.cout
-        z = self.pair(key + '.z', (n, h, w, c), l.split)
+        z = self.pair(key + '.z', (n, h, w, c), l.split, z=True)
         stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
         y = self.pair(key + '.y', (n, h, w, c), l.split) if want_y else None
         pool = self.pair(key + '.pool', (n, h // 2, w // 2, c), l.split) if want_pool else None
@@ -389,7 +397,7 @@ class EncoderEngine:
         n, h, w, cin = x_low[0].shape
         if ops.upconv_fusable(h, w):
             c = l.cout
-            z = self.pair(key + '.z', (n, 2 * h, 2 * w, c), l.split)
+            z = self.pair(key + '.z', (n, 2 * h, 2 * w, c), l.split, z=True)
             stats = self.buf(key + '.stats', (len(gs) - 1, c, 4), f32)
             y = self.pair(key + '.y', (n, 2 * h, 2 * w, c), l.split)
             l.fwd_up(x_low, z, gs, self.scratch('bn_sums', (len(gs) - 1) * c * 2, torch.float64), stats, y)
@@ -397,8 +405,8 @@ class EncoderEngine:
             return y
         u = self.pair(key + '.in', (n, 2 * h, 2 * w, cin), l.split)
         ops.upsample2x(x_low[0], u[0])                                # net/modules.py:67
-        if l.split:
-            ops.upsample2x(x_low[1], u[1])
+        if l.split:                                                   # a c8 plane is copied as the fp16 plane of the same bytes
+            ops.upsample2x(x_low[1].view(f16), u[1].view(f16))
         y, _ = self._layer_fwd(key, u, None, gs)
         return y
 
