@@ -532,9 +532,12 @@ def main():
     algo = fwd_algo * (2 if wl['train'] else 1)
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     achieved = algo / (conv_ms * 1e-3) / 1e12
-    # executed tensor-core FLOPs: the split-fp16 encoder forward runs three passes (hi.Wh + lo.Wh + hi.Wl) of its algorithmic FLOPs
+    # executed tensor-core FLOPs: the split-fp16 encoder forward runs three fp16 passes (hi.Wh + lo.Wh + hi.Wl) of its algorithmic
+    # FLOPs; 'split8' one fp16 pass + two e4m3 passes (lo8.Wh8 + x8.Wl8), the e4m3 ones at twice the MMA rate: `executed_flops`
+    # counts all of them, `executed_fp16_equiv` weighs an e4m3 FLOP as half (= units of fp16 tensor time, what the bf16 peak prices)
     enc_fwd = n_img * (E_FLOPS - FIRST_CONV_FLOPS) * scale
-    executed = algo + (2 * enc_fwd if precision == 'split' else 0)
+    executed = algo + (2 * enc_fwd if precision in ('split', 'split8') else 0)
+    executed_eq = algo + (2 * enc_fwd if precision == 'split' else (enc_fwd if precision == 'split8' else 0))
     burst_tf = peaks.get('bf16_tflops', 1590.0)
     roofline = {'bound': 'tensor', 'kernel': 'conv_igemm_kernel (tcgen05 implicit GEMM: forward%s)' % (' + data-gradient convs' if wl['train'] else ''),
                 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
@@ -542,9 +545,14 @@ def main():
                 'frac_of_burst_peak': achieved / burst_tf,
                 'algorithmic_flops_per_step': algo, 'launches_per_step': kern['conv_igemm']['launches'], 'kernel_ms_per_step': conv_ms,
                 'executed_flops_per_step': executed, 'executed_tflops': executed / (conv_ms * 1e-3) / 1e12,
-                'executed_frac': executed / (conv_ms * 1e-3) / 1e12 / peak_tf, 'executed_frac_of_burst_peak': executed / (conv_ms * 1e-3) / 1e12 / burst_tf,
-                'precision': precision + (': split-fp16 encoder forward = 3 tensor-core passes per algorithmic FLOP (fp32-class result); '
-                                          '`achieved` counts the algorithmic FLOPs once' if precision == 'split' else ''),
+                'executed_fp16_equiv_flops_per_step': executed_eq, 'executed_fp16_equiv_tflops': executed_eq / (conv_ms * 1e-3) / 1e12,
+                'executed_frac': executed_eq / (conv_ms * 1e-3) / 1e12 / peak_tf,
+                'executed_frac_of_burst_peak': executed_eq / (conv_ms * 1e-3) / 1e12 / burst_tf,
+                'precision': precision + {'split': ': split-fp16 encoder forward = 3 fp16 tensor-core passes per algorithmic FLOP (fp32-class result); '
+                                                   '`achieved` counts the algorithmic FLOPs once',
+                                          'split8': ': encoder forward = 1 fp16 pass + 2 e4m3 correction passes at twice the MMA rate = 2 units of fp16 '
+                                                    'tensor time per algorithmic FLOP (fp32-class result); `achieved` counts the algorithmic FLOPs '
+                                                    'once, `executed_frac*` the fp16-equivalent tensor time against the bf16 peak'}.get(precision, ''),
                 'kernel_share_of_step': conv_ms / (ms_total / args.steps)}
     # DRAM traffic per launch of the kernel: `dram__bytes_read.sum + dram__bytes_write.sum` from the committed `ncu --set full`
     # capture of the current build over the launches of one step (profiles/r02_ncu_conv_igemm_traffic.json)
@@ -579,7 +587,7 @@ def main():
     if not args.no_parity and world == 1:
         par = parity_field({k: v.detach().cpu().clone() for k, v in net.state_dict().items()}, wl, dev, precision)
     fast = None
-    if not args.no_fast_mode and world == 1 and precision == 'split' and wl['train']:
+    if not args.no_fast_mode and world == 1 and precision in ('split', 'split8') and wl['train']:
         # the same workload with `b200_precision: fp16`: single-term fp16 operands = the 11-bit significand of the library's
         # default TF32 convs.  Reported beside the headline (which is the fp32-class split mode): what relaxing the arithmetic to
         # the library's own default precision buys, and what it costs in parity.
@@ -601,7 +609,9 @@ def main():
     total_units = wl['slices'] if wl.get('volume') else world * B
     line = {'metric': METRIC, 'value': total_units / (ms_step * 1e-3), 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong' if wl.get('volume') else 'weak', 'vs_baseline': None,
-            'dtype': ('split-fp16 (hi + lo planes, 3 tensor-core passes) encoder forward, fp16 cre convs' if precision == 'split' else 'fp16 forward operands')
+            'dtype': {'split': 'split-fp16 (hi + lo planes, 3 tensor-core passes) encoder forward, fp16 cre convs',
+                      'split8': 'fp16 main term + e4m3 first-order corrections (hi.Wh + 2^-15 (lo8.Wh8 + x8.Wl8): fp16 + c8 planes, 1 fp16 + 2 e4m3 '
+                                'tensor-core passes) encoder forward, fp16 cre convs'}.get(precision, 'fp16 forward operands')
                      + '; fp32 accumulate; activations stored fp16 (hi [+ lo]), activation gradients bf16, dgrad / wgrad operands bf16, '
                        'BatchNorm statistics fp64, parameters / weight gradients / Adam / losses fp32', 'data': 'synthetic',
             'config': {'workload': wl['name'], 'ways': wl['ways'], 'shots': wl['shots'], 'batch_per_gpu': B,

@@ -84,14 +84,14 @@ def main():
         torch.backends.cudnn.allow_tf32 = True
     n_img = imgs.shape[0]
     algo = n_img * E_VGG * (args.size / 256.0) ** 2
-    split = engine.default_precision() == 'split'
+    units = {'split': 3, 'split8': 2}.get(engine.default_precision(), 1)      # fp16-equivalent tensor passes per conv
     line = {'metric': 'VGG backbone (net/vgg.py:22-58): encoder images/s and RP_Net(backbone=vgg, scale=8) eval forward slices/s', 'n_gpus': 1,
             'precision': engine.default_precision(),
             'encoder': {'images_per_s': n_img / (ms_enc * 1e-3), 'ms': ms_enc, 'images': n_img,
                         'roofline': {'bound': 'tensor', 'achieved': algo / (ms_enc * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                                      'frac': algo / (ms_enc * 1e-3) / 1e12 / peak,
-                                     'executed_tflops': algo * (3 if split else 1) / (ms_enc * 1e-3) / 1e12,
-                                     'note': 'algorithmic FLOPs of the 13 convs (first conv on CUDA cores included); split precision executes the 12 tensor-core convs three times'}},
+                                     'executed_fp16_equiv_tflops': algo * units / (ms_enc * 1e-3) / 1e12,
+                                     'note': 'algorithmic FLOPs of the 13 convs (first conv on CUDA cores included); split executes the 12 tensor-core convs three times, split8 once in fp16 plus two e4m3 passes at twice the rate (2 units)'}},
             'forward': {'slices_per_s': B / (ms_fwd * 1e-3), 'ms': ms_fwd, 'cuda_graph_slices_per_s': B / (ms_graph * 1e-3), 'batch': B, 'size': args.size, 'T': args.T},
             'parity': {'rel_linf': max(p['rel_linf'] for p in per), 'margin_rel_err': max(p['margin_rel_err'] for p in per),
                        'argmax_mismatch': max(p['argmax_mismatch'] for p in per), 'dice_vs_ref': min(p['dice_vs_ref'] for p in per),
