@@ -31,6 +31,7 @@ constexpr int kSmemBudget = 200 * 1024;
 constexpr int kMaxBnGroups = 64;
 constexpr int kMaxCosP = 8;       // prototypes of the fused calDist epilogue (1 + ways)
 constexpr int kMaxBnCout = 1024;  // per-CTA shared accumulators of the fused BatchNorm statistics: [cout][2] doubles
+constexpr int kMaxWsHaloKb = 12;  // stages per tile of the weights-stationary halo kernel (3 column offsets x k-blocks per tap)
 constexpr int kMaxSeg = 6;        // K segments per tap (split-fp16 convs: hi.Wh, lo.Wh, hi.Wl for up to two concat sources)
 
 struct ConvParams {
@@ -52,6 +53,10 @@ struct ConvParams {
   int dy[kMaxTaps], dx[kMaxTaps];
   int tap_src[kMaxTaps];          // -1: channel concat of source 0 | source 1 (default); 0..3: the tap reads that source only
   int halo_tap[9];                // HALO kernels: tap index of offset (dy, dx) = (i / 3 - 1, i % 3 - 1) in the weight pack
+  // weights-stationary HALO kernel: every 64-unit chunk of every tap of the pack is resident (chunk c of tap t at slot
+  // t * ws_wchunks + c); stage kb of a tile (producer order) uses column offset ws_dx[kb] and weight chunk ws_wch[kb]
+  int ws_wchunks;
+  int ws_dx[kMaxWsHaloKb], ws_wch[kMaxWsHaloKb];
   const float* scale;             // per-cout epilogue: y = acc * scale + shift
   const float* shift;
   int relu;
@@ -99,28 +104,37 @@ struct ConvParams {
 // (dy, dx), dy = -1, 0, 1; the three row offsets are views of the same box 16 rows (2048 B, swizzle-atom aligned) apart.  A
 // pixel tile then pulls 3 x 20 KB of activations per 64-channel chunk through the L2 -> SM path instead of 9 x 16 KB: the
 // small-channel full-resolution layers (Conv1.conv.3, Conv2.*) are bound by exactly that feed, three-fold so in split-fp16.
+// WS == 1 && HALO == 1: both — the 64 -> 64 full-resolution layers in split precisions and their data gradients.  The halo kernel
+// alone is bound by the aggregate L2 -> SM bandwidth (~30 B / clk / SM with all SMs pulling), and more than half of what a pixel
+// tile pulls is the same 72 KB (bf16 data gradient) / 144 KB (split packs) of weights: resident, a tile pulls its activation
+// boxes only (120 instead of 264 KB in split8).
 constexpr int kWsMaxKb = 9;
+constexpr int kWsHaloMaxKb = 18;  // resident weight k-blocks of the WS + HALO variant: 9 taps x 2 chunks (Wh | corrections, cin = 64)
 constexpr int kHaloRows = (8 + 2) * 16;
 template <int BN, int CTAS = 1, int WS = 0, int HALO = 0>
 struct ConvCfg {
   static constexpr int kABytes = (HALO ? kHaloRows : kBM) * kBK * 2;   // 16 KB (20 KB with the halo rows)
   static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
   static constexpr int kStageBytes = WS ? kABytes : kABytes + (HALO ? 3 : 1) * kBBytes;
-  static constexpr int kResidentBytes = WS ? kWsMaxKb * kBBytes : 0;
-  static constexpr int kStages = ((kSmemBudget - kResidentBytes) / kStageBytes) > 8 ? 8 : ((kSmemBudget - kResidentBytes) / kStageBytes);
+  static constexpr int kResidentBytes = WS ? (HALO ? kWsHaloMaxKb : kWsMaxKb) * kBBytes : 0;
+  static constexpr int kBnBytes = (WS ? 64 : kMaxBnCout) * 2 * 8;            // fused BN statistics (WS kernels: cout == 64)
+  static constexpr int kBudget = (WS && HALO) ? 227 * 1024 - 4096 - kBnBytes : kSmemBudget;
+  static constexpr int kStages = ((kBudget - kResidentBytes) / kStageBytes) > 8 ? 8 : ((kBudget - kResidentBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;                        // double-buffered accumulator (power of 2 >= 32)
   static constexpr int kTileBytes = kStages * kStageBytes + kResidentBytes;
-  static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 +
-                                    kMaxBnCout * 2 * 8 /*fused BN statistics*/;
+  static constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 2 * BN * 4 * 2 /*scale,shift x2*/ + 256 + kBnBytes;
+  static_assert(kSmemBytes <= 227 * 1024 && kStages >= 2, "shared-memory plan does not fit");
 };
 
 // The MMAs of one k-block (one pipeline stage).  KIND 0: fp16 / bf16 operands; 1: e4m3 correction block; 2: the first fp16 block after
 // the corrections, whose first MMA scales the accumulator by 2^-15.  One straight-line instance per kind: predicating the kinds MMA by
 // MMA inside one loop cost the issuing thread a quarter of the tensor throughput.
-template <int CTAS, int HALO, int KIND, int STAGE_A_BYTES, int STAGE_B_BYTES>
-__device__ __forceinline__ void conv_issue_kblock(uint32_t a_addr, uint32_t b_addr, uint32_t d_tmem, uint32_t idesc, uint32_t acc_first) {
+// b_addr[dyi]: the weight tile of row offset dyi (HALO), b_addr[0] the weight tile otherwise.
+template <int CTAS, int HALO, int KIND>
+__device__ __forceinline__ void conv_issue_kblock(uint32_t a_addr, const uint32_t (&b_addr)[3], uint32_t d_tmem, uint32_t idesc, uint32_t acc_first) {
   auto mma = [&](uint64_t a_desc, uint64_t b_desc, bool first) {
     const uint32_t acc = first ? acc_first : 1u;
+    if (!elect_one()) return;
     if (KIND == 1) {
       if (CTAS == 2) umma_f8_pair(d_tmem, a_desc, b_desc, idesc, acc);
       else           umma_f8(d_tmem, a_desc, b_desc, idesc, acc);
@@ -137,13 +151,13 @@ __device__ __forceinline__ void conv_issue_kblock(uint32_t a_addr, uint32_t b_ad
 #pragma unroll
     for (int dyi = 0; dyi < 3; ++dyi) {
       const uint64_t a_desc = umma_desc_sw128(a_addr + dyi * 16 * 128, 1024);
-      const uint64_t b_desc = umma_desc_sw128(b_addr + dyi * STAGE_B_BYTES, 1024);
+      const uint64_t b_desc = umma_desc_sw128(b_addr[dyi], 1024);
 #pragma unroll
       for (int k = 0; k < kBK / 16; ++k) mma(a_desc + 2 * k, b_desc + 2 * k, (dyi | k) == 0);
     }
   } else {
     const uint64_t a_desc = umma_desc_sw128(a_addr, 1024);
-    const uint64_t b_desc = umma_desc_sw128(b_addr, 1024);
+    const uint64_t b_desc = umma_desc_sw128(b_addr[0], 1024);
     // advance 16 fp16 (32 e4m3) = 32 bytes along K inside the 128B swizzle row: +2 in the (addr >> 4) field
 #pragma unroll
     for (int k = 0; k < kBK / 16; ++k) mma(a_desc + 2 * k, b_desc + 2 * k, k == 0);
@@ -156,7 +170,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
                   const __grid_constant__ CUtensorMap tm_src2, const __grid_constant__ CUtensorMap tm_src3,
                   const __grid_constant__ CUtensorMap tm_w, const ConvParams p) {
   using Cfg = ConvCfg<BN, CTAS, WS, HALO>;
-  static_assert(!(HALO && WS), "the halo variant streams its weights");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -172,7 +185,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ws_bar + 1);
   double* s_bn = reinterpret_cast<double*>(smem + Cfg::kTileBytes + 2 * BN * 4 * 2 + 256);   // [cout][2]
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: the compiler then knows the warp index (and every role branch on it) is warp-uniform
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int kblocks_per_tap = p.kblocks_per_tap;
   const int num_kb = (HALO ? 3 : p.ntaps) * kblocks_per_tap;      // stages per tile
@@ -219,7 +233,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (WS) {                                            // the whole weight tensor, once (n_tiles_c == 1, num_kb <= kWsMaxKb)
+      if (WS && HALO) {                                    // every chunk of every tap, once: slot tap * ws_wchunks + chunk
+        mbar_expect_tx(ws_bar, 9 * p.ws_wchunks * Cfg::kBBytes);
+        for (int t = 0; t < 9; ++t)
+          for (int c = 0; c < p.ws_wchunks; ++c)
+            tma_load_3d(&tm_w, ws_bar, w_res + (t * p.ws_wchunks + c) * Cfg::kBBytes, c * kBK, 0, t);
+      } else if (WS) {                                     // the whole weight tensor, once (n_tiles_c == 1, num_kb <= kWsMaxKb)
         if (CTAS == 2) {                                   // each CTA its half of the couts; both complete on the leader's barrier
           if (cta_rank == 0) mbar_expect_tx(ws_bar, 2 * num_kb * Cfg::kBBytes);
           for (int kb = 0; kb < num_kb; ++kb)
@@ -260,9 +279,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
                 } else {
                   mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                   tma_load_4d(tm, &full_bar[stage], a_dst, (ach0 + j) * kBK, x0 + dxi - 1, y0 - 1, n0);
+                  if (!WS) {
 #pragma unroll
-                  for (int dyi = 0; dyi < 3; ++dyi)
-                    tma_load_3d(&tm_w, &full_bar[stage], b_dst + dyi * Cfg::kBBytes, (wch0 + j) * kBK, ct * BN, p.halo_tap[dyi * 3 + dxi]);
+                    for (int dyi = 0; dyi < 3; ++dyi)
+                      tma_load_3d(&tm_w, &full_bar[stage], b_dst + dyi * Cfg::kBBytes, (wch0 + j) * kBK, ct * BN, p.halo_tap[dyi * 3 + dxi]);
+                  }
                 }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
@@ -299,8 +320,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the loop (warp-uniform control flow and operands: descriptors and addresses stay in uniform registers)
+    // and one elected lane issues each tcgen05 instruction.  Entering the loop with a single lane instead makes the compiler
+    // wrap every MMA in a vector-to-uniform register hand-over loop (ELECT / R2UR / BRA.U.ANY, ~14 instructions per MMA), which
+    // bounds the N = 64 / 128 tiles whose MMAs last 32 / 64 cycles.
+    if (cta_rank == 0) {
       const uint32_t idesc8 = umma_idesc_f16(kBM * CTAS, BN);      // a / b format 0 = e4m3 for kind::f8f6f4 (F16 for kind::f16)
       const uint32_t idesc = idesc8 | (p.in_bf16 ? ((1u << 7) | (1u << 10)) : 0u);
       const int nkb8 = (HALO ? 3 : p.ntaps) * p.kb8_per_tap;       // leading e4m3 k-blocks of every tile
@@ -320,12 +345,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(tiles + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes;
-          conv_issue_kblock<CTAS, HALO, decltype(kind)::value, Cfg::kABytes, Cfg::kBBytes>(a_addr, b_addr, d_tmem,
-                                                                                           decltype(kind)::value == 1 ? idesc8 : idesc, kb != 0);
+          uint32_t b_addr[3];
+          if (WS && HALO) {                                // resident weights: the three taps (dy, ws_dx[kb]) of chunk ws_wch[kb]
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              b_addr[dyi] = smem_u32(w_res + (p.halo_tap[dyi * 3 + p.ws_dx[kb]] * p.ws_wchunks + p.ws_wch[kb]) * Cfg::kBBytes);
+          } else {
+            const uint32_t b0 = WS ? smem_u32(w_res + kb * Cfg::kBBytes) : a_addr + Cfg::kABytes;
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) b_addr[dyi] = b0 + dyi * Cfg::kBBytes;
+          }
+          conv_issue_kblock<CTAS, HALO, decltype(kind)::value>(a_addr, b_addr, d_tmem, decltype(kind)::value == 1 ? idesc8 : idesc, kb != 0);
           // smem slot reusable once these MMAs retire (in both CTAs of a pair)
-          if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3);
-          else           umma_commit(&empty_bar[stage]);
+          if (elect_one()) {
+            if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3);
+            else           umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         };
         int kb = 0;
@@ -334,8 +370,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           kblock(kb++, std::integral_constant<int, 2>());
         }
         for (; kb < num_kb; ++kb) kblock(kb, std::integral_constant<int, 0>());
-        if (CTAS == 2) umma_commit_pair(&tfull_bar[as], 3);  // accumulator complete -> the epilogue of each CTA
-        else           umma_commit(&tfull_bar[as]);
+        if (elect_one()) {
+          if (CTAS == 2) umma_commit_pair(&tfull_bar[as], 3);  // accumulator complete -> the epilogue of each CTA
+          else           umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -378,14 +417,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           cur_g = g;
         }
       }
-      // stage this tile's per-channel scale/shift (buffer `as`: the other buffer may still be in use)
-      float* sc = s_scale + as * BN;
-      float* sh = s_shift + as * BN;
-      for (int i = et; i < BN; i += 128) {
-        sc[i] = __ldg(p.scale + ct * BN + i);
-        sh[i] = __ldg(p.shift + ct * BN + i);
+      // stage this tile's per-channel scale/shift (buffer `as`: the other buffer may still be in use); with a single cout tile
+      // they are staged once, before the first tile (the global-load latency + barrier per tile bounded the N = 64 layers)
+      float* sc = s_scale + (p.n_tiles_c == 1 ? 0 : as * BN);
+      float* sh = s_shift + (p.n_tiles_c == 1 ? 0 : as * BN);
+      if (p.n_tiles_c > 1 || it == 0) {
+        for (int i = et; i < BN; i += 128) {
+          sc[i] = __ldg(p.scale + ct * BN + i);
+          sh[i] = __ldg(p.shift + ct * BN + i);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
@@ -411,11 +453,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
 #pragma unroll
       for (int q2 = 0; q2 < kMaxCosP; ++q2) { cos_pn[q2] = 0.f; cos_dot[q2] = 0.f; }
       const float* cos_pr = p.cos_pred ? p.cos_protos + (size_t)((valid ? n : 0) % p.cos_sets) * p.cos_P * 64 : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
+      // one 32-channel chunk of the accumulator row, already in registers
+      auto chunk = [&](float* v, const int c0) {
         if (p.res) {
           float r[32];
 #pragma unroll
@@ -510,6 +549,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
             }
           }
         }
+      };
+      // the TMEM load of the next chunk is in flight while this one is processed; the accumulator buffer goes back to the MMA
+      // warp as soon as its last chunk sits in registers (before that chunk's math and stores)
+      auto release = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_rank0(&tempty_bar[as]);
+          else           mbar_arrive(&tempty_bar[as]);
+        }
+      };
+      {
+        float va[32], vb[32];
+        tmem_ld32(t_addr, va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld32(t_addr + c0 + 32, vb);
+          chunk(va, c0);
+          tmem_ld_wait();
+          if (c0 + 64 < BN) tmem_ld32(t_addr + c0 + 64, va);
+          else              release();
+          chunk(vb, c0 + 32);
+        }
       }
       if (BN == 64 && p.cos_pred && valid) {
         // torch's cosine_similarity: each norm clamped at 1e-8 separately
@@ -520,12 +583,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_src0, const __grid_cons
           if (q2 < p.cos_P)
             p.cos_pred[((size_t)n * p.cos_P + q2) * hw + (size_t)y * p.W + x] =
                 p.cos_scaler * (cos_dot[q2] / (xn * fmaxf(sqrtf(cos_pn[q2]), 1e-8f)));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_rank0(&tempty_bar[as]);
-        else           mbar_arrive(&tempty_bar[as]);
       }
     }
     if (p.bn_sums && cur_g >= 0) {
@@ -670,6 +727,21 @@ static int launch_halo64(const CUtensorMap& t0, const CUtensorMap& t1, const CUt
   const int grid = tiles < num_sms() ? tiles : num_sms();
   conv_igemm_kernel<64, 1, 0, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
   return check_cuda(cudaGetLastError(), "conv_igemm_kernel (halo) launch");
+}
+
+// Weights-stationary halo launch (cout == 64, one source, at most kWsHaloMaxKb resident weight k-blocks).
+static int launch_ws_halo64(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3, const CUtensorMap& tw,
+                            const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<64, 1, 1, 1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RPNET_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<64, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_igemm_kernel<64, 1, 1, 1><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(t0, t1, t2, t3, tw, p);
+  return check_cuda(cudaGetLastError(), "conv_igemm_kernel (weights-stationary halo) launch");
 }
 
 static int launch_halo128_pair(const CUtensorMap& t0, const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& t3,
@@ -893,6 +965,23 @@ static int conv_igemm_run(const ConvCall& a) {
     const uint32_t box[3] = {(uint32_t)kBK, (uint32_t)(pair ? BN / 2 : BN), 1};
     int rc = make_tmap_2b(&tw, a.wpack, 3, dims, str, box, bf16);
     if (rc) return rc;
+  }
+  if (halo && BN == 64) {
+    // weights-stationary when the whole pack fits beside the activation ring and there are enough tiles to amortise the preload
+    const int wchunks = (int)((uint64_t)(c0 + c1) * (a.w_split ? 2 : 1) / kBK);
+    const int nkb = 3 * p.kblocks_per_tap;
+    if (cout == 64 && c1 == 0 && 9 * wchunks <= kWsHaloMaxKb && nkb <= kMaxWsHaloKb && p.tiles_x * p.tiles_y * p.tiles_n >= 4 * num_sms() &&
+        !getenv("RPNET_CONV_NO_WS")) {
+      p.ws_wchunks = wchunks;
+      int kb = 0;                                          // replay the producer's stage order
+      for (int ph = p.kb8_per_tap ? 1 : 0; ph >= 0; --ph)
+        for (int dxi = 0; dxi < 3; ++dxi)
+          for (int sg = 0; sg < p.nseg; ++sg) {
+            if (p.seg_kind[sg] != ph) continue;
+            for (int j = 0; j < p.seg_n[sg]; ++j, ++kb) { p.ws_dx[kb] = dxi; p.ws_wch[kb] = p.seg_wch[sg] + j; }
+          }
+      return launch_ws_halo64(t0, t1, t2, t3, tw, p, stream);
+    }
   }
   if (halo) return BN == 128 ? launch_halo128_pair(t0, t1, t2, t3, tw, p, stream) : launch_halo64(t0, t1, t2, t3, tw, p, stream);
   if (pair) {

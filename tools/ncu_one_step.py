@@ -51,7 +51,7 @@ def main():
         fn = getattr(ops, name)
 
         def inner(*a, **kw):
-            ts_ = [t for t in list(a) + list(kw.values()) if torch.is_tensor(t) and t.dtype in (torch.float16, torch.bfloat16, torch.float32)
+            ts_ = [t for t in list(a) + list(kw.values()) if torch.is_tensor(t) and t.dtype in (torch.float16, torch.bfloat16, torch.float32, torch.uint8)
                    and t.numel() > 4096]
             conv_bytes.append(sum(t.numel() * t.element_size() for t in ts_))
             return fn(*a, **kw)

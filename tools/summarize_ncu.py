@@ -23,7 +23,10 @@ def launches(src, dst):
             f.write('%-92s %6d %12.1f %6.1f%%\n' % (k, n, t, 100 * t / tot))
 
 def raw(rep, dst, pattern=''):
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if rep.endswith('.csv'):                       # `ncu -i x.ncu-rep --page raw --csv` already exported on the GPU box
+        out = open(rep).read()
+    else:
+        out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
