@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 /* ABI version of this header (bumped on any signature change). */
-int rpnet_abi_version(void);   /* currently 7 */
+int rpnet_abi_version(void);   /* currently 8 */
 
 /* Message of the last failing call on this thread ("" if none). */
 const char* rpnet_last_error(void);
@@ -329,6 +329,19 @@ int rpnet_maxpool_idx_f16(const void* in_hi, const void* in_lo, void* out_hi, vo
                           int c, int k, int stride, int pad, void* stream);
 int rpnet_maxpool_bwd_bf16(const void* dy_bf16, const void* idx_u8, void* dx_bf16, int n, int h, int w, int c, int k, int stride,
                            int pad, void* stream);
+
+/* ---- ResNet18 backbone training (net/rp_net.py:19-42; torchvision BasicBlock: y = relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)).
+ * rpnet_bn_apply_res_f16: rpnet_bn_apply_split_f16 with the identity (hi plane + optional lo plane in `lo_fmt`) added before the ReLU.
+ * rpnet_add_relu_mask_bf16: out = (a + b) where y > 0, else 0 (b, y optional; bf16 gradients, fp16 activation, `elems` a multiple
+ *   of 8): the ReLU mask in front of both branches of a block and the sum of the two branches' input gradients.
+ * rpnet_conv7x7s2_stem_wgrad: grad [64][3][7][7] += weight gradient of the stem conv (7x7, stride 2, padding 3) from the fp32 NCHW
+ *   images and dz bf16 [n][(h-1)/2+1][(w-1)/2+1][64]; scratch9408: 64 * 147 doubles. */
+int rpnet_bn_apply_res_f16(const void* z_hi, const void* z_lo, const float* stats, int n, int h, int w, int c, const int* group_start,
+                           int groups, int relu, const void* res_f16, const void* res_lo, void* y_f16, void* y_lo_f16,
+                           void* y_pool_f16, void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream);
+int rpnet_add_relu_mask_bf16(const void* a_bf16, const void* b_bf16, const void* y_f16, void* out_bf16, long long elems, void* stream);
+int rpnet_conv7x7s2_stem_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch9408,
+                               void* stream);
 int rpnet_conv3x3_first_wgrad_cin(const float* img, int cin, const void* dz_bf16, int n, int h, int w, float* grad,
                                   double* scratch576, void* stream);
 

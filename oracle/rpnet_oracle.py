@@ -181,21 +181,32 @@ def _bn_eval(x, sd, bn):
     return F.batch_norm(x, sd[bn + '.running_mean'], sd[bn + '.running_var'], sd[bn + '.weight'], sd[bn + '.bias'], False, 0.0, BN_EPS)
 
 
-def resnet_encoder(x, sd, prefix='encoder.'):
-    """ResNet18 wrapper, net/rp_net.py:19-42 (eval): torchvision resnet18 conv1 (7x7 s2 p3, no bias) + bn1 + relu +
+def _bn(x, sd, bn, training):
+    """nn.BatchNorm2d: eval mode on the running statistics, train mode on the batch statistics of this call (running statistics
+    and num_batches_tracked updated in place, momentum 0.1 — SURVEY D14)."""
+    if not training:
+        return _bn_eval(x, sd, bn)
+    if (bn + '.num_batches_tracked') in sd:
+        sd[bn + '.num_batches_tracked'] += 1
+    return F.batch_norm(x, sd[bn + '.running_mean'], sd[bn + '.running_var'], sd[bn + '.weight'], sd[bn + '.bias'], True, BN_MOMENTUM,
+                        BN_EPS)
+
+
+def resnet_encoder(x, sd, prefix='encoder.', training=False):
+    """ResNet18 wrapper, net/rp_net.py:19-42: torchvision resnet18 conv1 (7x7 s2 p3, no bias) + bn1 + relu +
     maxpool(3, 2, 1) + layer1, then three stride-1 stages of [BasicBlock(cin, cout, downsample = 1x1 conv(bias) + BN),
     BasicBlock(cout, cout)] -> 512 ch @ H/4.  BasicBlock (torchvision): relu(bn2(conv2(relu(bn1(conv1(x))))) + identity)."""
     p = prefix + 'backbone.'
-    x = F.relu(_bn_eval(F.conv2d(x, sd[p + '0.weight'], None, stride=2, padding=3), sd, p + '1'))
+    x = F.relu(_bn(F.conv2d(x, sd[p + '0.weight'], None, stride=2, padding=3), sd, p + '1', training))
     x = F.max_pool2d(x, 3, 2, 1)
     for stage in (4, 5, 6, 7):
         for b in (0, 1):
             q = '%s%d.%d.' % (p, stage, b)
-            out = F.relu(_bn_eval(F.conv2d(x, sd[q + 'conv1.weight'], None, padding=1), sd, q + 'bn1'))
-            out = _bn_eval(F.conv2d(out, sd[q + 'conv2.weight'], None, padding=1), sd, q + 'bn2')
+            out = F.relu(_bn(F.conv2d(x, sd[q + 'conv1.weight'], None, padding=1), sd, q + 'bn1', training))
+            out = _bn(F.conv2d(out, sd[q + 'conv2.weight'], None, padding=1), sd, q + 'bn2', training)
             identity = x
             if (q + 'downsample.0.weight') in sd:
-                identity = _bn_eval(F.conv2d(x, sd[q + 'downsample.0.weight'], sd[q + 'downsample.0.bias']), sd, q + 'downsample.1')
+                identity = _bn(F.conv2d(x, sd[q + 'downsample.0.weight'], sd[q + 'downsample.0.bias']), sd, q + 'downsample.1', training)
             x = F.relu(out + identity)
     return x
 
@@ -375,8 +386,8 @@ def forward(sd, cfg, supp_imgs, fore_mask, back_mask, qry_imgs, appr_query_label
                                 mask_feature_map=cfg.get('mask_feature_map', False))
         if backbone == 'vgg':      # wiring per SURVEY D1: wrap as d4, caller passes scale=8
             return vgg_encoder(x.expand(-1, 3, -1, -1), sd, 'encoder.')
-        if backbone == 'resnet':   # net/rp_net.py:246-249 (eval only in this oracle)
-            return resnet_encoder(x.expand(-1, 3, -1, -1), sd, 'encoder.')
+        if backbone == 'resnet':   # net/rp_net.py:246-249
+            return resnet_encoder(x.expand(-1, 3, -1, -1), sd, 'encoder.', training)
         raise NotImplementedError(backbone)
 
     # :245-262 two separate encoder passes (BN batch statistics are per pass: D14)

@@ -5,7 +5,7 @@ import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'librpnet_sm100.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _c_int, _c_ll, _c_f, _vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 _ip = ctypes.POINTER(ctypes.c_int)

@@ -633,7 +633,7 @@ using namespace rpnet;
 
 RPNET_API const char* rpnet_last_error(void) { return g_last_error.c_str(); }
 
-RPNET_API int rpnet_abi_version(void) { return 7; }
+RPNET_API int rpnet_abi_version(void) { return 8; }
 
 RPNET_API int rpnet_conv3x3_first_split_f16(const float* img, int n, int cin, int h, int w, const float* weight, const float* scale,
                                              const float* shift, int relu, void* out_f16, void* out_lo_f16, int lo_fmt, void* stream_);

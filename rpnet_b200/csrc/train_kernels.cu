@@ -199,7 +199,8 @@ template <bool POOL>
 __global__ void __launch_bounds__(256, 2)
 bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, const float* __restrict__ stats, Groups gr, int N, int H,
                 int W, int c8, int relu, uint4* __restrict__ y16, uint4* __restrict__ y16_lo, float* __restrict__ y32,
-                uint4* __restrict__ ypool, uint4* __restrict__ ypool_lo, int lo_fmt) {
+                uint4* __restrict__ ypool, uint4* __restrict__ ypool_lo, int lo_fmt, const uint4* __restrict__ res,
+                const void* __restrict__ res_lo) {
   constexpr int U = POOL ? 2 : 4;
   const int C = c8 * 8;
   const int lanes = 256 / c8;
@@ -263,9 +264,16 @@ bn_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ z_lo, con
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += l[j];
         }
+        float idn[8];                             // BasicBlock: y = relu(bn2(z) + identity); identity as hi (+ lo) planes
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idn[j] = 0.f;
+        if (!POOL && res) {
+          unpack8_f16(__ldg(res + (size_t)pix[k][q] * c8 + v), idn);
+          if (res_lo) lo8_add(res_lo, lo_fmt, ((size_t)pix[k][q] * c8 + v) * 8, (v * 8) & 63, idn);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float r = fmaf(f[j], a[j], b[j]);
+          float r = fmaf(f[j], a[j], b[j]) + idn[j];
           r = relu ? fmaxf(r, 0.f) : r;
           f[j] = r;
           best[j] = fmaxf(best[j], r);
@@ -1033,6 +1041,86 @@ relu_bias_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ y, 
   }
 }
 
+// BasicBlock backward glue: out = (a + b) masked by y > 0 (b and y optional): the ReLU of `y = relu(bn2(z2) + identity)` in front
+// of both branches, and the sum of the main-branch and identity-branch input gradients.
+__global__ void add_relu_mask_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ y,
+                                     uint4* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float d[8];
+    unpack8_bf16(__ldg(a + i), d);
+    if (b) {
+      float e[8];
+      unpack8_bf16(__ldg(b + i), e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] += e[j];
+    }
+    if (y) {
+      float f[8];
+      unpack8_f16(__ldg(y + i), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = f[j] > 0.f ? d[j] : 0.f;
+    }
+    out[i] = pack8_bf16(d);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient of the ResNet stem conv (7x7, stride 2, padding 3, 3 -> 64; net/rp_net.py:19-23 = torchvision resnet18.conv1):
+//   grad[co][ci][ky][kx] = sum over (n, oy, ox) of dz[n][oy][ox][co] * img[n][ci][2 oy + ky - 3][2 ox + kx - 3]
+// One block per 8 x 8 tile of output pixels: the 21 x 21 x 3 input patch and the 64 x 64 dz tile are staged in shared memory;
+// thread t owns output channel t % 64 and the taps {t / 64 + 4 i} (37 of the 147 per thread) in registers across the tiles of its
+// block, block partials (fp32, fixed order) are accumulated in fp64 (deterministic, like every other reduction of the path).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStemTaps = 147, kStemTapsPerThread = 37, kStemTile = 8, kStemPatch = 2 * kStemTile + 5;
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ img, const __nv_bfloat16* __restrict__ dz, int N, int H, int W, int Ho, int Wo,
+                  double* __restrict__ acc64) {
+  __shared__ float s_in[3][kStemPatch][kStemPatch + 1];
+  __shared__ float s_dz[kStemTile * kStemTile][64];
+  const int co = threadIdx.x & 63, kg = threadIdx.x >> 6;
+  const int tiles_x = (Wo + kStemTile - 1) / kStemTile, tiles_y = (Ho + kStemTile - 1) / kStemTile;
+  const long long tiles = (long long)N * tiles_y * tiles_x;
+  float acc[kStemTapsPerThread];
+  int t_ci[kStemTapsPerThread], t_off[kStemTapsPerThread];
+#pragma unroll
+  for (int i = 0; i < kStemTapsPerThread; ++i) {
+    acc[i] = 0.f;
+    const int t = kg + 4 * i;                       // tap index ci * 49 + ky * 7 + kx (>= 147: idle slot)
+    const int tt = t < kStemTaps ? t : 0;
+    t_ci[i] = tt / 49;
+    t_off[i] = ((tt % 49) / 7) * (kStemPatch + 1) + (tt % 7);
+  }
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y), n = (int)(tile / ((long long)tiles_x * tiles_y));
+    const int oy0 = ty * kStemTile, ox0 = tx * kStemTile;
+    const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kStemPatch * kStemPatch; i += 256) {
+      const int ci = i / (kStemPatch * kStemPatch), r = i % (kStemPatch * kStemPatch);
+      const int y = iy0 + r / kStemPatch, x = ix0 + r % kStemPatch;
+      s_in[ci][r / kStemPatch][r % kStemPatch] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((size_t)(n * 3 + ci) * H + y) * W + x) : 0.f;
+    }
+    for (int i = threadIdx.x; i < kStemTile * kStemTile * 64; i += 256) {
+      const int p = i >> 6, c = i & 63;
+      const int oy = oy0 + p / kStemTile, ox = ox0 + p % kStemTile;
+      s_dz[p][c] = (oy < Ho && ox < Wo) ? __bfloat162float(dz[((size_t)(n * Ho + oy) * Wo + ox) * 64 + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int p = 0; p < kStemTile * kStemTile; ++p) {
+      const float g = s_dz[p][co];
+      const float* base = &s_in[0][2 * (p / kStemTile)][2 * (p % kStemTile)];
+#pragma unroll
+      for (int i = 0; i < kStemTapsPerThread; ++i)
+        acc[i] = fmaf(g, base[t_ci[i] * kStemPatch * (kStemPatch + 1) + t_off[i]], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kStemTapsPerThread; ++i) {
+    const int t = kg + 4 * i;
+    if (t < kStemTaps) atomicAdd(acc64 + (size_t)co * kStemTaps + t, (double)acc[i]);
+  }
+}
+
 __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx, int N, int H, int W,
                                    int c8, int Ho, int Wo, int k, int stride, int pad) {
   const long long total = (long long)N * H * W * c8;
@@ -1132,10 +1220,22 @@ RPNET_API int rpnet_bn_apply_f16(const void* z, const float* stats, int n, int h
                                   0, stream_);
 }
 
+RPNET_API int rpnet_bn_apply_res_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
+                                      const int* group_start, int groups, int relu, const void* res_f16, const void* res_lo, void* y_f16,
+                                      void* y_lo_f16, void* y_pool_f16, void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream_);
+
 RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
                                         const int* group_start, int groups, int relu, void* y_f16, void* y_lo_f16, void* y_pool_f16,
                                         void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream_) {
+  return rpnet_bn_apply_res_f16(z, z_lo, stats, n, h, w, c, group_start, groups, relu, nullptr, nullptr, y_f16, y_lo_f16, y_pool_f16,
+                                y_pool_lo_f16, y_f32, lo_fmt, stream_);
+}
+
+RPNET_API int rpnet_bn_apply_res_f16(const void* z, const void* z_lo, const float* stats, int n, int h, int w, int c,
+                                      const int* group_start, int groups, int relu, const void* res_f16, const void* res_lo, void* y_f16,
+                                      void* y_lo_f16, void* y_pool_f16, void* y_pool_lo_f16, float* y_f32, int lo_fmt, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE((!res_lo || res_f16) && (!res_f16 || !y_pool_f16), "bn_apply: the residual input goes with the unpooled output only");
   RPNET_REQUIRE((!y_lo_f16 || y_f16) && (!y_pool_lo_f16 || y_pool_f16), "bn_apply: a residual output needs its main output");
   RPNET_REQUIRE(lo_fmt == 0 || (lo_fmt == 1 && c % 64 == 0), "bn_apply: lo_fmt %d (c8 planes need c %% 64 == 0, c = %d)", lo_fmt, c);
   RPNET_REQUIRE(z && stats, "bn_apply: null pointer argument");
@@ -1156,11 +1256,11 @@ RPNET_API int rpnet_bn_apply_split_f16(const void* z, const void* z_lo, const fl
   if (y_pool_f16)
     bn_apply_kernel<true><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
                                                              h, w, c / 8, relu, static_cast<uint4*>(y_f16), static_cast<uint4*>(y_lo_f16),
-                                                             y_f32, static_cast<uint4*>(y_pool_f16), static_cast<uint4*>(y_pool_lo_f16), lo_fmt);
+                                                             y_f32, static_cast<uint4*>(y_pool_f16), static_cast<uint4*>(y_pool_lo_f16), lo_fmt, nullptr, nullptr);
   else
     bn_apply_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(static_cast<const uint4*>(z), static_cast<const uint4*>(z_lo), stats, gr, n,
                                                               h, w, c / 8, relu, static_cast<uint4*>(y_f16),
-                                                              static_cast<uint4*>(y_lo_f16), y_f32, nullptr, nullptr, lo_fmt);
+                                                              static_cast<uint4*>(y_lo_f16), y_f32, nullptr, nullptr, lo_fmt, static_cast<const uint4*>(res_f16), res_lo);
   return check_cuda(cudaGetLastError(), "bn_apply launch");
 }
 
@@ -1368,6 +1468,32 @@ RPNET_API int rpnet_relu_bias_bwd(const void* dy_bf16, const void* y_f16, long l
   RPNET_CUDA_OK(cudaGetLastError());
   add_f64_to_f32_kernel<<<(c + 255) / 256, 256, 0, stream>>>(scratch_c, dbias, c);
   return check_cuda(cudaGetLastError(), "relu_bias_bwd launch");
+}
+
+// See include/rpnet_b200.h for the contracts.
+RPNET_API int rpnet_add_relu_mask_bf16(const void* a_bf16, const void* b_bf16, const void* y_f16, void* out_bf16, long long elems,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(a_bf16 && out_bf16 && elems > 0 && elems % 8 == 0, "add_relu_mask: bad arguments (elems = %lld)", elems);
+  add_relu_mask_kernel<<<grid_for(elems / 8, 256), 256, 0, stream>>>(static_cast<const uint4*>(a_bf16), static_cast<const uint4*>(b_bf16),
+                                                                    static_cast<const uint4*>(y_f16), static_cast<uint4*>(out_bf16), elems / 8);
+  return check_cuda(cudaGetLastError(), "add_relu_mask launch");
+}
+
+RPNET_API int rpnet_conv7x7s2_stem_wgrad(const float* img, const void* dz_bf16, int n, int h, int w, float* grad, double* scratch9408,
+                                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  RPNET_REQUIRE(img && dz_bf16 && grad && scratch9408, "conv7x7s2_stem_wgrad: null pointer argument");
+  RPNET_REQUIRE(n > 0 && h >= 7 && w >= 7, "conv7x7s2_stem_wgrad: bad shape %d x %d x %d", n, h, w);
+  RPNET_REQUIRE(reinterpret_cast<uintptr_t>(scratch9408) % 8 == 0, "conv7x7s2_stem_wgrad: scratch must be 8-byte aligned");
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  RPNET_CUDA_OK(cudaMemsetAsync(scratch9408, 0, 64 * kStemTaps * sizeof(double), stream));
+  const long long tiles = (long long)n * ((ho + kStemTile - 1) / kStemTile) * ((wo + kStemTile - 1) / kStemTile);
+  const long long blocks = tiles < 148LL * 4 ? tiles : 148LL * 4;
+  stem_wgrad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, static_cast<const __nv_bfloat16*>(dz_bf16), n, h, w, ho, wo, scratch9408);
+  RPNET_CUDA_OK(cudaGetLastError());
+  add_f64_to_f32_kernel<<<(64 * kStemTaps + 255) / 256, 256, 0, stream>>>(scratch9408, grad, 64 * kStemTaps);
+  return check_cuda(cudaGetLastError(), "conv7x7s2_stem_wgrad launch");
 }
 
 RPNET_API int rpnet_maxpool_bwd_bf16(const void* dy_bf16, const void* idx_u8, void* dx_bf16, int n, int h, int w, int c, int k, int stride,

@@ -1,6 +1,7 @@
 """ResNet18 backbone wrapper with the reference's structure and state_dict keys (net/rp_net.py:19-42): torchvision's
 resnet18 stem + layer1 (stride 4) followed by three custom stride-1 BasicBlock stages -> 512 channels at H/4.
-"Next" row N3 of SURVEY §8(f): eval forward only (training is built for the U-Net backbone).
+"Next" row N3 of SURVEY §8(f).  This module runs the eval forward; the train step (batch-statistics BatchNorm, residual backward,
+stem weight gradient) is scheduled for the whole model by rpnet_b200.train.ResNetTrainEngine (RP_Net.forward in train mode / TrainStep).
 
 The torchvision modules are parameter containers: forward() never calls them — it runs the stem kernel, the max-pool kernel
 and the tcgen05 implicit-GEMM conv with the BasicBlock's residual add + ReLU fused into its epilogue."""
@@ -58,7 +59,8 @@ class ResNet18(_PackedModule):
     def encode_nhwc(self, x, tag='res'):
         """x fp32 NCHW [n, 3, H, W] -> fp16 NHWC [n, H/4, W/4, 512] ((hi, lo) planes in split precision)."""
         if self.training:
-            raise NotImplementedError("backbone 'resnet' is built for eval only (SURVEY §8f N3)")
+            raise NotImplementedError('ResNet18.forward on its own runs in eval mode only: the train-mode kernels are scheduled for the whole '
+                                      'model by RP_Net.forward / rpnet_b200.train.TrainStep (ResNetTrainEngine); call .eval() for the encoder alone')
         ws, dev = self._ws, x.device
         (s_scale, s_shift), packs = self._packs()
         n, _, H, W = x.shape

@@ -162,7 +162,7 @@ class RP_Net(nn.Module):
                 self.load_state_dict(dic)
         elif self.config['backbone'] == 'resnet':
             from .resnet import ResNet18
-            self.encoder = ResNet18(use_pretrained=False)                 # net/rp_net.py:208-209 (eval only here)
+            self.encoder = ResNet18(use_pretrained=False)                 # net/rp_net.py:208-209 (trains: ResNetTrainEngine)
             self.encoder.split = engine.is_split(engine.precision_of(backbone_cfg))
             self.encoder.w_level = engine.w_level(engine.precision_of(backbone_cfg))
             num_feat = 512

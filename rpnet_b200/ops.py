@@ -458,6 +458,30 @@ def relu_bias_bwd(dy, y, g, dbias):
                                            _stream()), 'rpnet_relu_bias_bwd')
 
 
+def add_relu_mask(a, out, b=None, y=None):
+    """out = (a + b) where y > 0 else 0 (b, y optional): a, b, out bf16, y fp16, same shapes."""
+    lib = _lib.load()
+    _req(a, bf16, 'a'); _req(out, bf16, 'out')
+    assert out.shape == a.shape and a.numel() % 8 == 0
+    if b is not None:
+        _req(b, bf16, 'b'); assert b.shape == a.shape
+    if y is not None:
+        _req(y, torch.float16, 'y'); assert y.shape == a.shape
+    with _Timed('add_relu_mask', float(a.numel() * (4 + (2 if b is not None else 0) + (2 if y is not None else 0)))):
+        _lib.check(lib.rpnet_add_relu_mask_bf16(_ptr(a), _ptr(b), _ptr(y), _ptr(out), a.numel(), _stream()), 'rpnet_add_relu_mask_bf16')
+
+
+def conv7x7s2_stem_wgrad(img, dz, grad):
+    """grad fp32 [64, 3, 7, 7] += weight gradient of the stem conv from img fp32 [n, 3, H, W] and dz bf16 [n, H/2, W/2, 64]."""
+    lib = _lib.load()
+    _req(img, torch.float32, 'img'); _req(dz, bf16, 'dz'); _req(grad, torch.float32, 'grad')
+    n, c, h, w = img.shape
+    assert c == 3 and tuple(dz.shape) == (n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 64) and grad.numel() == 64 * 147
+    with _Timed('conv7x7s2_stem_wgrad', float(img.numel() * 4 + dz.numel() * 2)):
+        _lib.check(lib.rpnet_conv7x7s2_stem_wgrad(_ptr(img), _ptr(dz), n, h, w, _ptr(grad), _ptr(_scratch64(64 * 147, img.device, 'stem_wgrad')),
+                                                  _stream()), 'rpnet_conv7x7s2_stem_wgrad')
+
+
 def maxpool_bwd(dy, idx, k, stride, pad, dx):
     """dx bf16 [n, h, w, c] from dy bf16 [n, ho, wo, c] and the argmax positions idx uint8 [n, ho, wo, c] of maxpool(..., idx=)."""
     lib = _lib.load()
@@ -554,7 +578,8 @@ def bn_finalize(sums, group_start, c, hw, gamma, beta, conv_bias, running_mean, 
                    'rpnet_bn_finalize_f32')
 
 
-def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None, z_lo=None, y_lo=None, y_pool_lo=None):
+def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None, z_lo=None, y_lo=None, y_pool_lo=None, res=None,
+             res_lo=None):
     """z_lo: fp16 residual plane of z (z = z + z_lo); y_lo / y_pool_lo: lo planes of the outputs — fp16 residual planes, or c8 planes
     (uint8, last dim doubled; include/rpnet_b200.h "fp8 corrections")."""
     lib = _lib.load()
@@ -564,12 +589,15 @@ def bn_apply(z, stats, group_start, relu=True, y=None, y_pool=None, y_f32=None, 
     _lo_fmt([(z_lo, z, 'z_lo')])
     if z_lo is not None and z_lo.dtype != torch.float16:
         raise _lib.RpnetError('bn_apply: z_lo is the fp16 residual plane of the pre-BatchNorm conv output')
-    lo_fmt = _lo_fmt([(y_lo, y, 'y_lo'), (y_pool_lo, y_pool, 'y_pool_lo')])
-    nb = sum(t.numel() * t.element_size() for t in (z, z_lo, y, y_lo, y_pool, y_pool_lo, y_f32) if t is not None)
+    lo_fmt = _lo_fmt([(y_lo, y, 'y_lo'), (y_pool_lo, y_pool, 'y_pool_lo'), (res_lo, res, 'res_lo')])
+    if res is not None:                      # BasicBlock: y = relu(bn(z) + identity)
+        _req(res, torch.float16, 'res')
+        assert res.shape == z.shape and y_pool is None
+    nb = sum(t.numel() * t.element_size() for t in (z, z_lo, y, y_lo, y_pool, y_pool_lo, y_f32, res, res_lo) if t is not None)
     with _Timed('bn_apply', float(nb)):
-        _lib.check(lib.rpnet_bn_apply_split_f16(_ptr(z), _ptr(z_lo), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(y), _ptr(y_lo),
-                                                _ptr(y_pool), _ptr(y_pool_lo), _ptr(y_f32), int(lo_fmt), _stream()),
-                   'rpnet_bn_apply_split_f16')
+        _lib.check(lib.rpnet_bn_apply_res_f16(_ptr(z), _ptr(z_lo), _ptr(stats), n, h, w, c, gs, g, int(bool(relu)), _ptr(res), _ptr(res_lo),
+                                              _ptr(y), _ptr(y_lo), _ptr(y_pool), _ptr(y_pool_lo), _ptr(y_f32), int(lo_fmt), _stream()),
+                   'rpnet_bn_apply_res_f16')
 
 
 def bn_bwd(z, stats, group_start, dz, scratch, relu=True, direct=None, d_off=0, pooled=None, p_off=0, up=None, u_off=0,

@@ -154,12 +154,15 @@ class _NoAffineNorm:
 class _ConvBN:
     """One conv (bias dropped: it cancels in batch- / instance-statistics normalisation) + BatchNorm(batch stats) + ReLU of the path."""
 
-    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False, w_split=None):
+    def __init__(self, name, conv, bn, flat, first=False, hole=(0, 0), up=False, split=False, w_split=None, relu=True, bwd_relu=None):
         # split: the forward runs on (hi, lo) plane pairs; w_split = weight-pack level: engine.W_C8 (fp8 corrections, two units of
         # tensor time, the default), engine.W_SPLIT (Wh | Wl, three fp16 passes), engine.W_FP16 (hi.W + lo.W); all fp32-class but the
         # last.  The backward is unchanged (it reads the hi planes).
         self.name, self.conv, self.bn, self.first, self.hole, self.up, self.split = name, conv, bn, first, hole, up, split
         self.w_split = int(split if w_split is None else w_split)
+        # relu: the activation of the forward apply pass; bwd_relu: whether the backward masks by bn(z) > 0 — False for a BasicBlock's
+        # second conv, whose ReLU follows the residual add and is applied to the incoming gradient instead (ResNetTrainEngine)
+        self.relu, self.bwd_relu = relu, relu if bwd_relu is None else bwd_relu
         if not isinstance(bn, nn.BatchNorm2d):                 # nn.InstanceNorm2d: no parameters, no buffers
             self.bn = bn = _NoAffineNorm(conv.out_channels, conv.weight.device, getattr(bn, 'eps', 1e-5))
         affine = isinstance(bn, nn.BatchNorm2d)
@@ -217,13 +220,15 @@ class _ConvBN:
         ops.upconv_dgrad(dz, self.w16_up, dx_low)
         return dx_low
 
-    def fwd(self, x0, x1, z, gs, sums, stats, y=None, pool=None, y32=None):
-        """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) + ReLU.
-        x0, x1, z, y, pool: (hi, lo) plane pairs (lo None outside split mode; x0 = the fp32 image for the first conv)."""
+    def fwd(self, x0, x1, z, gs, sums, stats, y=None, pool=None, y32=None, res=None):
+        """z = conv(x0 | x1) and its batch statistics (fused into the conv epilogue), then BatchNorm(train) (+ res) + ReLU.
+        x0, x1, z, y, pool, res: (hi, lo) plane pairs (lo None outside split mode; x0 = the fp32 image for the first conv)."""
         n, h, w, c = z[0].shape
         bn = self.bn
         y = y or (None, None)
         pool = pool or (None, None)
+        res = res or (None, None)
+        bias = self.conv.bias.data if self.conv.bias is not None else None
         if self.first:
             ops.conv3x3_first(x0, self.conv.weight.data, self.ones, self.zeros, False, z[0], out_lo=z[1])
             ops.bn_stats(z[0], gs, sums, z_lo=z[1])
@@ -232,16 +237,17 @@ class _ConvBN:
                            src1_lo=None if x1 is None else x1[1], w_split=self.w_split, out=z[0], out_lo=z[1], group_start=gs, sums=sums)
         else:
             ops.conv_bnstats(x0[0], self.wf, self.taps, self.ones, self.zeros, z[0], gs, sums, src1=None if x1 is None else x1[0])
-        ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, self.conv.bias.data, bn.running_mean, bn.running_var,
+        ops.bn_finalize(sums, gs, c, h * w, bn.weight.data, bn.bias.data, bias, bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, stats, eps=bn.eps, momentum=bn.momentum)
-        ops.bn_apply(z[0], stats, gs, True, y=y[0], y_pool=pool[0], y_f32=y32, z_lo=z[1], y_lo=y[1], y_pool_lo=pool[1])
+        ops.bn_apply(z[0], stats, gs, self.relu, y=y[0], y_pool=pool[0], y_f32=y32, z_lo=z[1], y_lo=y[1], y_pool_lo=pool[1], res=res[0],
+                     res_lo=res[1])
 
     def bwd(self, eng, x0, x1, z, stats, gs, dx=None, accumulate=False, **src):
         """BN+ReLU backward -> dz; weight gradient (= or += with `accumulate`); data gradient into `dx` (bf16 [n,h,w,cin_pack])
         when given."""
         n, h, w, c = z.shape
         dz = eng.scratch('dz', n * h * w * c, bf16).view(n, h, w, c)
-        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 6, f32), True,
+        ops.bn_bwd(z, stats, gs, dz, eng.scratch('bn_bwd', (len(gs) - 1) * c * 6, f32), self.bwd_relu,
                    dgamma=self.ggamma, dbeta=self.gbeta, **src)
         if self.first:
             ops.conv3x3_first_wgrad(x0, dz, self.gw)
@@ -463,7 +469,8 @@ class TrainEngine(EncoderEngine):
     def __init__(self, net):
         from .nn.unet import U_Net
         if not isinstance(net.encoder, U_Net):
-            raise NotImplementedError("training is built for backbone 'UNet' (the reference cannot train 'vgg': SURVEY D1)")
+            raise NotImplementedError("TrainEngine schedules backbone 'UNet'; 'vgg' / 'resnet' have VggTrainEngine / ResNetTrainEngine "
+                                      "(TrainEngine.of(net) picks the right one)")
         dev = next(net.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
@@ -485,8 +492,10 @@ class TrainEngine(EncoderEngine):
         """The (cached) engine of `net`; rebuilt when the parameters were moved (e.g. net.to(other_device))."""
         eng = net.__dict__.get('_b200_train_engine')
         if eng is None or not eng.flat.attached():
+            from .nn.resnet import ResNet18
             from .nn.vgg import Encoder
-            eng = VggTrainEngine(net) if isinstance(net.encoder, Encoder) else TrainEngine(net)
+            eng = VggTrainEngine(net) if isinstance(net.encoder, Encoder) else \
+                (ResNetTrainEngine(net) if isinstance(net.encoder, ResNet18) else TrainEngine(net))
             net.__dict__['_b200_train_engine'] = eng
         return eng
 
@@ -757,6 +766,126 @@ class VggTrainEngine(TrainEngine):
             dx = self.buf('vgg.dx.%d' % id(conv), (n, h, w, cin), bf16)
             ops.conv_dgrad(gz, self.wd[conv], taps, dx)
             g = dx
+        if buckets:
+            buckets.ready(1)
+
+
+class ResNetTrainEngine(TrainEngine):
+    """TrainEngine for `backbone: resnet` (net/rp_net.py:19-42: torchvision resnet18 stem + layer1, then three stride-1 stages of
+    BasicBlocks, 512 channels at H/4; all BatchNorm2d in train mode: batch statistics per encoder call, running statistics updated).
+    Forward: stem conv (CUDA cores) -> statistics -> apply (+ReLU) -> MaxPool2d(3, 2, 1) with recorded argmax positions; every
+    BasicBlock conv on the tcgen05 kernel with its statistics in the epilogue; the block tail y = relu(bn2(z2) + identity) is one
+    apply pass with the identity planes as a third input.  Backward per block: ReLU mask of y on the incoming gradient
+    (rpnet_add_relu_mask_bf16), BatchNorm backward + weight / data gradients of conv2, conv1 (and the 1x1 downsample branch), sum of
+    the two branches' input gradients; then max-pool routing, the stem's BatchNorm backward and its weight gradient
+    (rpnet_conv7x7s2_stem_wgrad)."""
+    bucket_groups = [('cre.',), ('encoder.',)]
+
+    def __init__(self, net):
+        dev = next(net.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('rpnet_b200 trains on CUDA (sm_100a) only; there is no CPU fallback')
+        self.net, self.dev, self.norm = net, dev, 'batch'
+        self.encoder = enc = net.encoder
+        self.flat = flat = FlatParams(net)
+        self.split = sp = bool(enc.split)
+        lv = int(enc.w_level) if sp else engine.W_FP16
+        self.lo_level = engine.W_C8 if lv == engine.W_C8 else engine.W_SPLIT
+        c, L = net.cre, {}
+        k = (2 * c.radius + 1) ** 2
+        self.kcorr, self.corr_c = k, c.corr_channels
+        L['wk'] = _ConvBN('wk', c.w_k[0], c.w_k[1], flat)
+        L['wq'] = _ConvBN('wq', c.w_q[0], c.w_q[1], flat)
+        L['q'] = _ConvBN('q', c.q[0], c.q[1], flat, hole=(k, self.corr_c - k))
+        bb = enc.backbone
+        self.stem_conv, self.stem_bn = bb[0], bb[1]
+        self.blocks = []
+        for si in (4, 5, 6, 7):
+            for bi, blk in enumerate(bb[si]):
+                nm = 'r%d%d' % (si, bi)
+                L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv1, blk.bn1, flat, split=sp, w_split=lv)
+                L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv2, blk.bn2, flat, split=sp, w_split=lv, relu=True, bwd_relu=False)
+                if blk.downsample is not None:
+                    L[nm + 'd'] = _ConvBN(nm + 'd', blk.downsample[0], blk.downsample[1], flat, split=sp, w_split=lv, relu=False)
+                self.blocks.append((nm, blk.downsample is not None))
+        self.L = L
+        self.ws = engine.Workspace()
+        self._scratch = {}
+        self.act = {}
+        self.saved = None
+        self.ones64 = torch.ones(64, dtype=f32, device=dev)
+        self.zeros64 = torch.zeros(64, dtype=f32, device=dev)
+
+    def _encoder_fwd(self, imgs, gs):
+        if imgs.shape[1] == 1:
+            imgs = imgs.expand(-1, 3, -1, -1)                     # net/rp_net.py:246-247
+        imgs = imgs.float().contiguous()
+        self.imgs3, self.gs = imgs, gs
+        n, _, H, W = imgs.shape
+        G, sp = len(gs) - 1, self.split
+        h2, w2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        h4, w4 = (h2 + 2 - 3) // 2 + 1, (w2 + 2 - 3) // 2 + 1
+        sums = lambda c: self.scratch('bn_sums', G * c * 2, torch.float64)
+        bn = self.stem_bn
+        z = self.pair('stem.z', (n, h2, w2, 64), sp, z=True)
+        ops.conv7x7s2_stem(imgs, self.stem_conv.weight.data, self.ones64, self.zeros64, z[0], relu=False, out_lo=z[1])
+        st = self.buf('stem.stats', (G, 64, 4), f32)
+        ops.bn_stats(z[0], gs, sums(64), z_lo=z[1])
+        ops.bn_finalize(sums(64), gs, 64, h2 * w2, bn.weight.data, bn.bias.data, None, bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, st, eps=bn.eps, momentum=bn.momentum)
+        y = self.pair('stem.y', (n, h2, w2, 64), sp)
+        ops.bn_apply(z[0], st, gs, True, y=y[0], z_lo=z[1], y_lo=y[1])
+        cur = self.pair('stem.p', (n, h4, w4, 64), sp)
+        idx = self.buf('stem.idx', (n, h4, w4, 64), torch.uint8)
+        ops.maxpool(y[0], 3, 2, 1, cur[0], x_lo=y[1], out_lo=cur[1], idx=idx)          # nn.MaxPool2d(3, 2, 1)
+        self.act = {'stem': dict(z=z[0], stats=st, idx=idx, y_shape=tuple(y[0].shape))}
+        for nm, down in self.blocks:
+            la, lb = self.L[nm + 'a'], self.L[nm + 'b']
+            shp = lambda c: (n, h4, w4, c)
+            za, sa = self.pair(nm + 'a.z', shp(la.cout), sp, z=True), self.buf(nm + 'a.stats', (G, la.cout, 4), f32)
+            a = self.pair(nm + 'a.y', shp(la.cout), sp)
+            la.fwd(cur, None, za, gs, sums(la.cout), sa, y=a)
+            rec = dict(x=cur[0], za=za[0], sa=sa, a=a[0])
+            idn = cur
+            if down:
+                ld = self.L[nm + 'd']
+                zd, sd = self.pair(nm + 'd.z', shp(ld.cout), sp, z=True), self.buf(nm + 'd.stats', (G, ld.cout, 4), f32)
+                idn = self.pair(nm + 'd.y', shp(ld.cout), sp)
+                ld.fwd(cur, None, zd, gs, sums(ld.cout), sd, y=idn)
+                rec.update(zd=zd[0], sd=sd)
+            zb, sb = self.pair(nm + 'b.z', shp(lb.cout), sp, z=True), self.buf(nm + 'b.stats', (G, lb.cout, 4), f32)
+            out = self.pair(nm + '.y', shp(lb.cout), sp)
+            lb.fwd(a, None, zb, gs, sums(lb.cout), sb, y=out, res=idn)             # relu(bn2(conv2(a)) + identity)
+            rec.update(zb=zb[0], sb=sb, y=out[0])
+            self.act[nm] = rec
+            cur = out
+        return cur
+
+    def _encoder_bwd(self, g_d4, buckets=None):
+        gs, g = self.gs, g_d4                                     # g: bf16 gradient w.r.t. the output of the current block
+        for nm, down in reversed(self.blocks):
+            A = self.act[nm]
+            la, lb = self.L[nm + 'a'], self.L[nm + 'b']
+            g1 = self.buf(nm + '.g1', tuple(g.shape), bf16)
+            ops.add_relu_mask(g.contiguous(), g1, y=A['y'])       # through the block's final ReLU: feeds bn2 and the identity branch
+            da = self.buf(nm + '.da', tuple(A['a'].shape), bf16)
+            lb.bwd(self, A['a'], None, A['zb'], A['sb'], gs, dx=da, direct=g1)
+            dx = self.buf(nm + '.dx', tuple(A['x'].shape), bf16)
+            la.bwd(self, A['x'], None, A['za'], A['sa'], gs, dx=dx, direct=da)
+            other = g1
+            if down:
+                other = self.buf(nm + '.dxd', tuple(A['x'].shape), bf16)
+                self.L[nm + 'd'].bwd(self, A['x'], None, A['zd'], A['sd'], gs, dx=other, direct=g1)
+            g = self.buf(nm + '.gin', tuple(A['x'].shape), bf16)
+            ops.add_relu_mask(dx, g, b=other)                     # the previous block's ReLU is applied when that block is visited
+        S = self.act['stem']
+        dy = self.buf('stem.dy', S['y_shape'], bf16)
+        ops.maxpool_bwd(g, S['idx'], 3, 2, 1, dy)
+        bn = self.stem_bn
+        dz = self.scratch('dz', dy.numel(), bf16).view(dy.shape)
+        ops.bn_bwd(S['z'], S['stats'], gs, dz, self.scratch('bn_bwd', (len(gs) - 1) * 64 * 6, f32), True,
+                   dgamma=self.flat.grad_of(bn.weight), dbeta=self.flat.grad_of(bn.bias), direct=dy)
+        ops.conv7x7s2_stem_wgrad(self.imgs3, dz, self.flat.grad_of(self.stem_conv.weight))
         if buckets:
             buckets.ready(1)
 

@@ -397,3 +397,67 @@ def test_vgg_backbone_train_step_vs_oracle(dev):
     ts.step(to_device(ep, dev))
     torch.cuda.synchronize()
     assert not torch.equal(w0, net.encoder.features[0][0].weight.detach())
+
+
+def test_resnet_backbone_train_step_vs_oracle(dev):
+    """`backbone: resnet` through the train step (net/rp_net.py:19-42): train-mode BatchNorm in the stem and every BasicBlock,
+    residual adds, the 1x1 downsample branches, MaxPool2d(3, 2, 1) routing and the 7x7 stem weight gradient.  Logits 1e-3 and loss
+    1e-3 against the fp32 oracle (teacher-forced), BN running statistics, gradients of every parameter against the oracle's autograd."""
+    from oracle import rpnet_oracle as O
+    from oracle import weights
+    from rpnet_b200 import parity
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import ResNetTrainEngine, TrainStep
+    from net.rp_net import RP_Net
+    T = 2
+    cfg = _cfg(T)
+    sd = weights.resnet_rpnet_state_dict(0)
+    net = RP_Net(cfg={'align': True, 'backbone': 'resnet'}, backbone_cfg=cfg)
+    net.load_state_dict(sd)
+    sd = {k: v.clone() for k, v in sd.items()}
+    net = net.to(dev).train()
+    ep = make_episode(4, 1, 1, 128, seed=7)
+    ts = TrainStep(net)
+    assert isinstance(ts.eng, ResNetTrainEngine)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    over = {i: O.recurrent_mask(ts.last['logits'][i - 1].float().cpu(), cfg) for i in range(1, T)}
+    out = O.forward(sd, cfg, ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'], training=True,
+                    backbone='resnet', mask_override=over)
+    ref_loss = O.train_loss(out, ep['query_labels'])
+    ref_loss.backward()
+    for i in range(T):
+        r = parity.compare_logits(ts.last['logits'][i].cpu(), out['refinement'][i].detach())
+        assert r['rel_linf'] < LOGIT_TOL and r['margin_rel_err'] < 2 * LOGIT_TOL, (i, r)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    for k, b in net.state_dict().items():
+        if 'running' in k:
+            torch.testing.assert_close(b.cpu(), sd[k], rtol=1e-3, atol=1e-4, msg=k)
+        elif 'num_batches_tracked' in k:
+            assert int(b) == int(sd[k]), k
+    worst, checked = {}, 0
+    for name, p in net.named_parameters():
+        rg = params[name].grad
+        if rg is None:
+            assert p.grad is None, name
+            continue
+        if name.endswith('downsample.0.bias') or name in ('cre.w_k.0.bias', 'cre.w_q.0.bias', 'cre.q.0.bias'):
+            continue                                                      # in front of batch-statistics BN: exactly zero
+        g = p.grad.float().cpu()
+        rel = ((g - rg).norm() / rg.norm().clamp_min(1e-12)).item()
+        worst[name] = rel
+        checked += 1
+    bad = {k: v for k, v in worst.items() if v >= (2e-2 if k.startswith('cre.') else 8e-2)}      # measured 5.4e-3 / 2.4e-2 (random init)
+    print('resnet train: worst gradient rel-L2 head %.2e encoder %.2e' % (max(v for k, v in worst.items() if k.startswith('cre.')),
+                                                                          max(v for k, v in worst.items() if k.startswith('encoder.'))))
+    assert not bad, bad
+    assert checked >= 60
+    w0 = net.encoder.backbone[0].weight.detach().clone()
+    ts.step(to_device(ep, dev))
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, net.encoder.backbone[0].weight.detach())

@@ -141,6 +141,71 @@ def test_first_conv_wgrad(dev):
     assert _rel(grad.cpu(), wt.grad) < 1e-5
 
 
+def test_stem_wgrad_vs_autograd(dev):
+    """rpnet_conv7x7s2_stem_wgrad: weight gradient of torchvision resnet18.conv1 (7x7, stride 2, padding 3; net/rp_net.py:19-23),
+    ragged tiles included; accumulates (+=) and is deterministic."""
+    from rpnet_b200 import ops
+    g = _gen(15)
+    n, h, w = 3, 52, 76
+    img = torch.randn(n, 3, h, w, generator=g)
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    dz = (torch.randn(n, 64, ho, wo, generator=g) * 0.1).to(bf16).float()
+    wt = torch.zeros(64, 3, 7, 7, requires_grad=True)
+    F.conv2d(img, wt, None, stride=2, padding=3).backward(dz)
+    grad = torch.ones(64, 3, 7, 7, device=dev)
+    ops.conv7x7s2_stem_wgrad(img.to(dev), _nhwc(dz, bf16, dev), grad)
+    g2 = torch.ones(64, 3, 7, 7, device=dev)
+    ops.conv7x7s2_stem_wgrad(img.to(dev), _nhwc(dz, bf16, dev), g2)
+    torch.cuda.synchronize()
+    assert _rel(grad.cpu() - 1.0, wt.grad) < 1e-5
+    assert torch.equal(grad, g2)
+
+
+def test_add_relu_mask(dev):
+    from rpnet_b200 import ops
+    g = _gen(16)
+    a = torch.randn(2, 8, 8, 64, generator=g).to(bf16)
+    b = torch.randn(2, 8, 8, 64, generator=g).to(bf16)
+    y = torch.randn(2, 8, 8, 64, generator=g).half()
+    out = torch.empty(2, 8, 8, 64, dtype=bf16, device=dev)
+    ops.add_relu_mask(a.to(dev), out, b=b.to(dev), y=y.to(dev))
+    torch.cuda.synchronize()
+    want = ((a.float() + b.float()) * (y.float() > 0)).to(bf16)
+    assert torch.equal(out.cpu(), want)
+    ops.add_relu_mask(a.to(dev), out, y=y.to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), (a.float() * (y.float() > 0)).to(bf16))
+    ops.add_relu_mask(a.to(dev), out, b=b.to(dev))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), (a.float() + b.float()).to(bf16))
+
+
+@pytest.mark.parametrize('level', [1, 2])
+def test_bn_apply_with_residual(dev, level):
+    """rpnet_bn_apply_res_f16: y = relu(bn(z) + identity), identity as hi + lo planes (BasicBlock tail in train mode)."""
+    from rpnet_b200 import engine, ops
+    g = _gen(17)
+    n, c, h, w, gs = 4, 128, 8, 8, [0, 3, 4]
+    z = torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3
+    res = torch.randn(n, c, h, w, generator=g)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.1
+    want = torch.cat([F.relu(F.batch_norm(z[a:b].double(), None, None, gamma.double(), beta.double(), True, 0.0, 1e-5) + res[a:b].double())
+                      for a, b in ((0, 3), (3, 4))]).float()
+    zh, zl = (t.to(dev) for t in engine.split_f16(z.permute(0, 2, 3, 1).contiguous()))
+    rh, rl = (t.to(dev) for t in engine.split_planes(res.permute(0, 2, 3, 1).contiguous(), level))
+    G = len(gs) - 1
+    sums = torch.empty(G, c, 2, device=dev, dtype=torch.float64); stats = torch.empty(G, c, 4, device=dev)
+    rm, rv, nbt = torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.zeros((), dtype=torch.int64, device=dev)
+    ops.bn_stats(zh, gs, sums, z_lo=zl)
+    ops.bn_finalize(sums, gs, c, h * w, gamma.to(dev), beta.to(dev), None, rm, rv, nbt, stats)
+    y = torch.empty(n, h, w, c, dtype=torch.float16, device=dev)
+    y_lo = torch.empty(n, h, w, 2 * c, dtype=torch.uint8, device=dev) if level == 2 else torch.empty_like(y)
+    ops.bn_apply(zh, stats, gs, True, y=y, z_lo=zl, y_lo=y_lo, res=rh, res_lo=rl)
+    torch.cuda.synchronize()
+    got = engine.join_planes(y, y_lo).permute(0, 3, 1, 2).cpu()
+    assert (got - want).abs().max().item() / want.abs().max().item() < (1e-5 if level == 1 else 1e-4)
+
+
 # ------------------------------------------------------------------------------------------- batch norm
 @pytest.mark.parametrize('case', [(6, 64, 16, 16, [0, 4, 6], True), (4, 256, 8, 8, [0, 4], False), (3, 1024, 4, 4, [0, 1, 2, 3], False)])
 def test_bn_train_forward(dev, case):

@@ -32,6 +32,35 @@ def test_resnet_oracle_and_init_vs_reference_golden(golden):
     assert torch.equal(out['output'][:, :, ::2, ::2], torch.from_numpy(g['output']))
 
 
+def test_resnet_oracle_train_mode_vs_torchvision_modules():
+    """Train-mode restatement (batch-statistics BatchNorm, running statistics, num_batches_tracked) and its gradients against the
+    torch modules themselves: rpnet_b200.nn.resnet.ResNet18.backbone is the nn.Sequential of torchvision conv / bn / BasicBlock
+    modules the reference builds (net/rp_net.py:19-36); forward() of the wrapper never calls it, here it is the independent check."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200.nn.resnet import ResNet18
+    torch.manual_seed(3)
+    enc = ResNet18().train()
+    x = torch.randn(3, 3, 64, 64)
+    sd = {'encoder.' + k: v.clone() for k, v in enc.state_dict().items()}
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    want = enc.backbone(x)
+    got = O.resnet_encoder(x, sd, 'encoder.', training=True)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+    w = torch.randn_like(want)
+    (want * w).sum().backward()
+    (got * w).sum().backward()
+    for k, p in enc.named_parameters():
+        g, rg = params['encoder.' + k].grad, p.grad
+        assert ((g - rg).norm() / rg.norm().clamp_min(1e-12)).item() < 1e-4, k
+    for k, b in enc.state_dict().items():
+        if 'running' in k or 'num_batches' in k:
+            torch.testing.assert_close(sd['encoder.' + k].float(), b.float(), rtol=1e-5, atol=1e-6, msg=k)
+
+
 def test_resnet_module_state_dict_keys(golden):
     from rpnet_b200.nn.rp_net import RP_Net
     g = golden('resnet')
