@@ -273,8 +273,9 @@ class EncoderEngine:
         dev = next(encoder.parameters()).device
         if dev.type != 'cuda':
             raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback')
-        if getattr(encoder, 'mfm', False):
-            raise NotImplementedError('mask_feature_map=%r is built for the eval forward with BatchNorm2d only' % (encoder.mfm,))
+        self.mfm = getattr(encoder, 'mfm', False)
+        if self.mfm and norm == 'instance':
+            raise NotImplementedError('InstanceNorm2d together with mask_feature_map=%r is not built' % (self.mfm,))
         self.encoder, self.dev, self.norm, self.flat = encoder, dev, norm, flat
         # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
         # train-mode logits 2e-3 .. 5e-3 from the fp32 reference)
@@ -287,7 +288,10 @@ class EncoderEngine:
         for nm, blk in (('c1', e.Conv1), ('c2', e.Conv2), ('c3', e.Conv3), ('c4', e.Conv4), ('c5', e.Conv5),
                         ('uc5', e.Up_conv5), ('uc4', e.Up_conv4)):
             ws = wd if nm.startswith('uc') else lv
-            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], flat, first=(nm == 'c1'), split=sp, w_split=ws)
+            # mask_feature_map x2 / x3 (net/unet.py:401-424): the 65- / 129-channel conv runs as 128 / 192 packed channels, the mask
+            # travels in channel 0 of a 64-channel extra source and the 63 padding channels are a hole of the packs
+            hole = (blk.conv[0].in_channels, 63) if (nm, self.mfm) in (('c2', 'x2'), ('c3', 'x3')) else (0, 0)
+            L[nm + 'a'] = _ConvBN(nm + 'a', blk.conv[0], blk.conv[1], flat, first=(nm == 'c1'), hole=hole, split=sp, w_split=ws)
             L[nm + 'b'] = _ConvBN(nm + 'b', blk.conv[3], blk.conv[4], flat, split=sp, w_split=ws)
         L['up5'] = _ConvBN('up5', e.Up5.up[1], e.Up5.up[2], flat, up=True, split=sp, w_split=wd)
         L['up4'] = _ConvBN('up4', e.Up4.up[1], e.Up4.up[2], flat, up=True, split=sp, w_split=wd)
@@ -375,14 +379,25 @@ class EncoderEngine:
         self.act[key] = dict(x0=x0 if l.first else x0[0], x1=None if x1 is None else x1[0], z=z[0], stats=stats, gs=gs)
         return y, pool
 
-    def _encoder_fwd(self, imgs, gs):
-        """net/unet.py:435-467 in train mode; `gs` = BatchNorm call groups (support pass, query pass: net/rp_net.py:248,257)."""
+    def _encoder_fwd(self, imgs, gs, mask=None):
+        """net/unet.py:435-467 in train mode; `gs` = BatchNorm call groups (support pass, query pass: net/rp_net.py:248,257);
+        mask [n, 1, H, W]: only read by the mask_feature_map variants (net/unet.py:437-449)."""
         f = self._layer_fwd
+        m2 = m3 = None
+        if self.mfm:
+            if mask is None or mask.shape[0] != imgs.shape[0]:
+                raise ValueError('mask_feature_map=%r needs one mask per image' % (self.mfm,))
+            src = lambda pool, nm: (lambda m: m if isinstance(m, tuple) else (m, None))(
+                self.encoder._mask_source(mask, pool, self.ws, nm, self.split))
+            if self.mfm == 'x':
+                imgs = torch.cat([imgs, mask.float()], dim=1).contiguous()            # net/unet.py:437-438
+            m2 = src(2, 'mfm.m2') if self.mfm == 'x2' else None                        # :442-443
+            m3 = src(4, 'mfm.m3') if self.mfm == 'x3' else None                        # :446-447
         a, _ = f('c1a', imgs, None, gs)
         _, p1 = f('c1b', a, None, gs, want_y=False, want_pool=True)
-        a, _ = f('c2a', p1, None, gs)
+        a, _ = f('c2a', p1, m2, gs)
         _, p2 = f('c2b', a, None, gs, want_y=False, want_pool=True)
-        a, _ = f('c3a', p2, None, gs)
+        a, _ = f('c3a', p2, m3, gs)
         x3, p3 = f('c3b', a, None, gs, want_pool=True)
         a, _ = f('c4a', p3, None, gs)
         x4, p4 = f('c4b', a, None, gs, want_pool=True)
@@ -454,9 +469,10 @@ class EncoderEngine:
         g = b('c4b', shp('c4b'), direct=dcat5, d_off=0, pooled=dp4)
         dp3 = b('c4a', shp('c4a'), direct=g)
         g = b('c3b', shp('c3b'), direct=dcat4, d_off=0, pooled=dp3)
-        dp2 = b('c3a', shp('c3a'), direct=g)
+        full = lambda key: cat(key) if A[key]['x1'] is not None else shp(key)     # mask_feature_map x2 / x3: gradient of the packed
+        dp2 = b('c3a', full('c3a'), direct=g)                                      # input; the consumer reads its first 64 / 128 channels
         g = b('c2b', shp('c2b'), pooled=dp2)
-        dp1 = b('c2a', shp('c2a'), direct=g)
+        dp1 = b('c2a', full('c2a'), direct=g)
         n, _, H, W = A['c1a']['x0'].shape
         g = b('c1b', (n, H, W, 64), pooled=dp1)
         b('c1a', None, direct=g)
@@ -537,12 +553,13 @@ class TrainEngine(EncoderEngine):
         engine.WEIGHTS_EPOCH += 1          # BN running statistics are updated through raw pointers below
 
         imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
-        d4 = self._encoder_fwd(imgs, self.groups_for([0, n_supp, n_img]))[0]   # two BN calls: support pass, query pass (D14); hi plane
+        fore = torch.stack([torch.stack(way, dim=0) for way in d['fore_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
+        back = torch.stack([torch.stack(way, dim=0) for way in d['back_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
+        emask = net._encoder_mask(fore, Wa, Sh, B)                     # fore_mask[0][0] for both passes (mask_feature_map variants only)
+        d4 = self._encoder_fwd(imgs, self.groups_for([0, n_supp, n_img]), emask)[0]   # two BN calls: support, query pass (D14); hi plane
         h, w, C = d4.shape[1:]
         if h * S != H or w * S != W:
             raise ValueError('scale=%d does not match the encoder stride' % S)
-        fore = torch.stack([torch.stack(way, dim=0) for way in d['fore_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
-        back = torch.stack([torch.stack(way, dim=0) for way in d['back_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()
 
         n_tot = n_supp + T * B
         G_tot = Wa * Sh + T
@@ -732,7 +749,7 @@ class VggTrainEngine(TrainEngine):
         super().pack_weights()                                  # the cre layers
         ops.run_pack_conv_weights(*self._wd_table)
 
-    def _encoder_fwd(self, imgs, gs):
+    def _encoder_fwd(self, imgs, gs, mask=None):
         if imgs.shape[1] == 1:
             imgs = imgs.expand(-1, 3, -1, -1).contiguous()       # net/rp_net.py:246-247
         self.trace = []
@@ -816,7 +833,7 @@ class ResNetTrainEngine(TrainEngine):
         self.ones64 = torch.ones(64, dtype=f32, device=dev)
         self.zeros64 = torch.zeros(64, dtype=f32, device=dev)
 
-    def _encoder_fwd(self, imgs, gs):
+    def _encoder_fwd(self, imgs, gs, mask=None):
         if imgs.shape[1] == 1:
             imgs = imgs.expand(-1, 3, -1, -1)                     # net/rp_net.py:246-247
         imgs = imgs.float().contiguous()

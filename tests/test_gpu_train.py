@@ -461,3 +461,46 @@ def test_resnet_backbone_train_step_vs_oracle(dev):
     ts.step(to_device(ep, dev))
     torch.cuda.synchronize()
     assert not torch.equal(w0, net.encoder.backbone[0].weight.detach())
+
+
+@pytest.mark.parametrize('mfm', ['x', 'x2', 'x3'])
+def test_mask_feature_map_train_step_vs_oracle(dev, mfm):
+    """`mask_feature_map: x | x2 | x3` (net/unet.py:401-424, 437-449) through the train step, 1-way 1-shot (the only shape the
+    reference's concatenation accepts): the mask enters Conv1 as a second image channel (Cin = 2 first conv and weight gradient) or
+    Conv2 / Conv3 as channel 0 of a 64-channel extra source against packs with a 63-channel hole.  Logits, loss, every gradient."""
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import parity
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    from net.rp_net import RP_Net
+    T = 2
+    cfg = dict(_cfg(T), mask_feature_map=mfm)
+    torch.manual_seed(1)
+    net = RP_Net(cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(dev).train()
+    ep = make_episode(2, 1, 1, 64, seed=9)
+    ts = TrainStep(net)
+    loss = ts.forward_backward(to_device(ep, dev))
+    torch.cuda.synchronize()
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    over = {i: O.recurrent_mask(ts.last['logits'][i - 1].float().cpu(), cfg) for i in range(1, T)}
+    out = O.forward(sd, cfg, ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'], training=True,
+                    mask_override=over)
+    ref_loss = O.train_loss(out, ep['query_labels'])
+    ref_loss.backward()
+    for i in range(T):
+        r = parity.compare_logits(ts.last['logits'][i].cpu(), out['refinement'][i].detach())
+        assert r['rel_linf'] < LOGIT_TOL and r['margin_rel_err'] < 2 * LOGIT_TOL, (i, r)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    # random init, 2 x 64 x 64: the ill-conditioned fixture class of test_train_grads_random_init (head 5e-2, encoder 0.15)
+    _check_grads(net, {k: p.grad for k, p in params.items()}, enc_tol=0.15, head_tol=5e-2)
+    key = {'x': 'encoder.Conv1.conv.0.weight', 'x2': 'encoder.Conv2.conv.0.weight', 'x3': 'encoder.Conv3.conv.0.weight'}[mfm]
+    g, rg = dict(net.named_parameters())[key].grad.float().cpu(), params[key].grad
+    assert g.shape == rg.shape and g.shape[1] in (2, 65, 129)
+    m_rel = ((g[:, -1] - rg[:, -1]).norm() / rg[:, -1].norm()).item()              # the mask channel's own weights
+    assert m_rel < 0.15, m_rel
