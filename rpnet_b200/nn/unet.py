@@ -82,14 +82,12 @@ class U_Net(Unet_2D):
             raise ValueError('mask_feature_map=%r needs one mask per image (got %s for %d images)'
                              % (self.mfm, None if mask is None else tuple(mask.shape), n))
         if self.inorm:
-            if self.mfm:
-                raise NotImplementedError('InstanceNorm2d together with mask_feature_map is not built')
             from ..train import EncoderEngine
             eng = self.__dict__.get('_in_engine')
             if eng is None or not eng.attached():
                 eng = EncoderEngine(self, norm='instance')
                 self.__dict__['_in_engine'] = eng
-            return eng.encode(x.float().contiguous())
+            return eng.encode(x.float().contiguous(), mask if self.mfm else None)
         ws = self._ws
         split = self.Conv1.split
         if self.mfm == 'x':

@@ -274,8 +274,6 @@ class EncoderEngine:
         if dev.type != 'cuda':
             raise RuntimeError('rpnet_b200 runs on CUDA (sm_100a) only; there is no CPU fallback')
         self.mfm = getattr(encoder, 'mfm', False)
-        if self.mfm and norm == 'instance':
-            raise NotImplementedError('InstanceNorm2d together with mask_feature_map=%r is not built' % (self.mfm,))
         self.encoder, self.dev, self.norm, self.flat = encoder, dev, norm, flat
         # encoder forward in split-fp16 (fp32-class, the default) or plain fp16 (`b200_precision: fp16`, TF32-class: faster,
         # train-mode logits 2e-3 .. 5e-3 from the fp32 reference)
@@ -316,8 +314,9 @@ class EncoderEngine:
             return list(range(n + 1))
         return calls
 
-    def encode(self, imgs):
-        """Eval forward (InstanceNorm2d): fp32 NCHW images -> d4 fp16 NHWC, in passes of at most MAX_GROUPS images."""
+    def encode(self, imgs, mask=None):
+        """Eval forward (InstanceNorm2d): fp32 NCHW images -> d4 fp16 NHWC, in passes of at most MAX_GROUPS images (mask: one per
+        image, only read by the mask_feature_map variants)."""
         sig = (engine.WEIGHTS_EPOCH,) + tuple((p.data_ptr(), p._version) for p in self.encoder.parameters())
         if sig != self._pack_sig:
             self.pack_weights()
@@ -327,7 +326,8 @@ class EncoderEngine:
         for lo in range(0, n, self.MAX_GROUPS):
             hi = min(n, lo + self.MAX_GROUPS)
             self.act = {}
-            d4 = self._encoder_fwd(imgs[lo:hi].contiguous(), self.groups_for([0, hi - lo]))[0]
+            d4 = self._encoder_fwd(imgs[lo:hi].contiguous(), self.groups_for([0, hi - lo]),
+                                   None if mask is None else mask[lo:hi].contiguous())[0]
             out[lo:hi].copy_(d4)
         self.act = {}
         return out

@@ -120,3 +120,53 @@ def test_instance_norm_train_step_vs_oracle():
         g, rg = named[name].grad.float().cpu(), params[name].grad
         rel = ((g - rg).norm() / rg.norm()).item()
         assert rel < (5e-2 if name.startswith('cre') else 0.15), (name, rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mfm', ['x', 'x3'])
+def test_instance_norm_with_mask_feature_map_vs_oracle(mfm):
+    """Both yaml variants together (`unet_normalize_type: InstanceNorm2d` + `mask_feature_map`), eval forward and train step against
+    the oracle (which restates both branches, each pinned to the reference on its own above)."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from net.model import model_factory
+    from oracle import rpnet_oracle as O
+    from rpnet_b200 import parity
+    from rpnet_b200.synthetic import make_episode, to_device
+    from rpnet_b200.train import TrainStep
+    T = 2
+    cfg = _cfg(T, unet_normalize_type='InstanceNorm2d', mask_feature_map=mfm)
+    torch.manual_seed(2)
+    net = model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=cfg)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    dev = torch.device('cuda:0')
+    ep = make_episode(2, 1, 1, 64, seed=5)
+    d = to_device(ep, dev)
+    a = (ep['supp_imgs'], ep['fore_mask'], ep['back_mask'], ep['qry_imgs'], ep['appr_query_labels'])
+    net = net.to(dev).eval()
+    with torch.no_grad():
+        out = net(d['supp_imgs'], d['fore_mask'], d['back_mask'], d['qry_imgs'], appr_query_labels=d['appr_query_labels'])
+        ref = O.forward({k: v.clone() for k, v in sd.items()}, cfg, *a)
+    r = parity.compare_logits(out['refinement'][0].cpu(), ref['refinement'][0])
+    assert r['rel_linf'] < 1e-3, r
+    net.train()
+    ts = TrainStep(net)
+    loss = ts.forward_backward(d)
+    torch.cuda.synchronize()
+    params = {}
+    for k, v in sd.items():
+        if v.is_floating_point() and 'running' not in k:
+            sd[k] = v.clone().requires_grad_(True)
+            params[k] = sd[k]
+    over = {i: O.recurrent_mask(ts.last['logits'][i - 1].float().cpu(), cfg) for i in range(1, T)}
+    tr = O.forward(sd, cfg, *a, training=True, mask_override=over)
+    ref_loss = O.train_loss(tr, ep['query_labels'])
+    ref_loss.backward()
+    for i in range(T):
+        r = parity.compare_logits(ts.last['logits'][i].cpu(), tr['refinement'][i].detach())
+        assert r['rel_linf'] < 1e-3 and r['margin_rel_err'] < 2e-3, (i, r)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * abs(ref_loss.item())
+    named = dict(net.named_parameters())
+    for name in ('cre.q.0.weight', 'encoder.Conv3.conv.0.weight', 'encoder.Conv1.conv.0.weight'):
+        g, rg = named[name].grad.float().cpu(), params[name].grad
+        assert ((g - rg).norm() / rg.norm()).item() < (5e-2 if name.startswith('cre') else 0.15), name
