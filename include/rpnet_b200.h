@@ -108,7 +108,8 @@ int rpnet_conv3x3_first_f16(const float* img, int n, int cin, int h, int w, cons
  *   operands, the two first-order corrections on e4m3 operands at twice the MMA rate (kind::f8f6f4) into the same fp32 accumulator,
  *   which the first main-term MMA scales by 2^-15 (tcgen05.mma scale-input-d).  A correction is 2^-11 of the main term, so its e4m3
  *   rounding (2^-4) lands at 2^-15 of the product: the same logits error as the three-pass form for two thirds of the
- *   tensor time.  Fixed scales: lo8 = e4m3((x - hi) * 2^11), x8 = e4m3(x), Wh8 = e4m3(Wh * 2^4), Wl8 = e4m3((w - Wh) * 2^15), saturating.
+ *   tensor time.  Fixed scales: lo8 = e4m3((x - hi) * 2^9), x8 = e4m3(x * 2^-2), Wh8 = e4m3(Wh * 2^6), Wl8 = e4m3((w - Wh) * 2^17), saturating
+ *   (exact corrections for |x| < 1792, |w| < 7; beyond, that element falls back to single-term accuracy).
  *   A "c8 plane" replaces the fp16 residual plane of an activation (same size): per pixel and 64-channel group 128 bytes = lo8 of the
  *   64 channels | x8 of the 64 channels; the second half of a weight pack row holds, per 64 input channels, Wh8 (64) | Wl8 (64).
  *   `lo_fmt` arguments: 0 = fp16 residual plane, 1 = c8 plane (channel counts must be multiples of 64).

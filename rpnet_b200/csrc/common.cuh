@@ -89,13 +89,15 @@ __device__ __forceinline__ uint4 residual8_f16(const float* v, const uint4& hi) 
 // The tensor-core convs of the default precision compute x.w = hi.Wh + 2^-15 (lo8.Wh8 + x8.Wl8): the main term on fp16
 // operands, the two first-order corrections on e4m3 operands (twice the MMA rate; a correction is 2^-11 of the main term, so
 // its own 2^-4 rounding lands at 2^-15), with fixed power-of-two scales
-//   lo8 = e4m3((x - hi) * 2^11)   x8 = e4m3(x)   Wh8 = e4m3(Wh * 2^4)   Wl8 = e4m3((w - Wh) * 2^15)
+//   lo8 = e4m3((x - hi) * 2^9)   x8 = e4m3(x * 2^-2)   Wh8 = e4m3(Wh * 2^6)   Wl8 = e4m3((w - Wh) * 2^17)
+// (saturating: exact corrections for |x| < 1792 and |w| < 7, beyond that the element falls back to single-term accuracy)
 // so that both products carry 2^15, which tcgen05.mma's scale-input-d removes from the accumulator when the fp16 main term
 // starts.  Layout of a c8 plane (same bytes as an fp16 plane of the same shape): per pixel and 64-channel group, 128 bytes
 // = lo8 of the 64 channels, then x8 of the 64 channels — one 128-byte swizzle row, K = 128 for the e4m3 MMA.
-constexpr float kC8LoScale = 2048.f;          // 2^11
-constexpr float kC8WhScale = 16.f;            // 2^4
-constexpr float kC8WlScale = 32768.f;         // 2^15
+constexpr float kC8LoScale = 512.f;           // 2^9
+constexpr float kC8XScale = 0.25f;            // 2^-2
+constexpr float kC8WhScale = 64.f;            // 2^6:  kC8LoScale * kC8WhScale = 2^15
+constexpr float kC8WlScale = 131072.f;        // 2^17: kC8XScale * kC8WlScale = 2^15
 constexpr int kC8AccShift = 15;               // scale-input-d of the first main-term MMA
 __device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
   const uint32_t l = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
@@ -129,9 +131,11 @@ __device__ __forceinline__ void c8_store8(uint8_t* dst, const float* v, const ui
 #pragma unroll
   for (int i = 0; i < 8; ++i) r[i] = (v[i] - r[i]) * kC8LoScale;
   *reinterpret_cast<uint2*>(dst) = pack8_e4m3(r);
-  *reinterpret_cast<uint2*>(dst + 64) = pack8_e4m3(v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = v[i] * kC8XScale;
+  *reinterpret_cast<uint2*>(dst + 64) = pack8_e4m3(r);
 }
-// lo plane of 8 consecutive channels, whichever format: r[i] += x - hi (c8: lo8 * 2^-11)
+// lo plane of 8 consecutive channels, whichever format: r[i] += x - hi (c8: lo8 * 2^-9)
 __device__ __forceinline__ void lo8_add(const void* plane, int c8, size_t off, int cg, float* r) {
   float l[8];
   if (c8) {

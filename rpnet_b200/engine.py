@@ -99,7 +99,7 @@ def split_f16(x):
     return hi, (x - hi.float()).to(torch.float16)
 
 
-C8_LO_SCALE, C8_WH_SCALE, C8_WL_SCALE = 2.0 ** 11, 2.0 ** 4, 2.0 ** 15      # csrc/common.cuh, "c8"
+C8_LO_SCALE, C8_X_SCALE, C8_WH_SCALE, C8_WL_SCALE = 2.0 ** 9, 2.0 ** -2, 2.0 ** 6, 2.0 ** 17      # csrc/common.cuh, "c8"
 
 
 def _e4m3(x):
@@ -115,9 +115,9 @@ def _c8_interleave(a8, b8):
 
 
 def split_c8(x):
-    """fp32 NHWC tensor -> (hi fp16 [..., C], c8 plane uint8 [..., 2 * C]): per 64 channels lo8 = e4m3((x - hi) * 2^11) | x8 = e4m3(x)."""
+    """fp32 NHWC tensor -> (hi fp16 [..., C], c8 plane uint8 [..., 2 * C]): per 64 channels lo8 = e4m3((x - hi) * 2^9) | x8 = e4m3(x / 4)."""
     hi = x.to(torch.float16)
-    return hi, _c8_interleave(_e4m3((x - hi.float()) * C8_LO_SCALE), _e4m3(x))
+    return hi, _c8_interleave(_e4m3((x - hi.float()) * C8_LO_SCALE), _e4m3(x * C8_X_SCALE))
 
 
 def split_planes(x, level):
