@@ -1,5 +1,5 @@
-"""Episode builder for the eval driver ("next" row N4 of SURVEY §8f): the three nested readers of
-dataset/few_shot_reader.py restated for `mode='eval'`.
+"""Episode builder ("next" row N4 of SURVEY §8f): the three nested readers of dataset/few_shot_reader.py restated, `mode='eval'`
+(the eval driver) and `mode='train'` (random slice per block + augmentations).
 
     FewshotVolumeReader  (:233-409)  class CSVs -> (query volume, support volume) pairs; NRRD load, centre truncate,
                                      pad to a multiple of 16, keep the annotated z range, centre crop/pad, HU normalise
@@ -15,9 +15,11 @@ branch, :523-548; `k` shrinks persistently, :466; the label pad of make_support_
 (50 Adam iterations of tiny ops each, :121-188); here all slices of the volume are registered by one kernel launch and the
 registration outputs stay on the device (`.cuda()` in the caller is then a no-op).
 
-`mode='train'` is not built: its augmentation calls `transforms.RandomAffine(..., fillcolor=None)` (:30-31), a keyword
-torchvision removed, so the reference's own train branch cannot run against the torchvision of this image and there is
-nothing to pin it to.  `do_deformable: True` runs the one-launch demons registration (rpnet_b200/registration.py)."""
+`mode='train'` (:306-307, 482-515): a random query slice per z-block, optional gamma / elastic augmentation, one random affine per
+slice, a shuffle of the k pairs (rpnet_b200/dataset/augment.py).  The reference's own train branch passes `fillcolor=None` to
+`transforms.RandomAffine` (:30-31), a keyword torchvision removed; the goldens were recorded from the unmodified reference classes
+with that one keyword mapped to today's spelling (`fill=0`, tests/golden/make_golden_dataset.py).
+`do_deformable: True` runs the one-launch demons registration (rpnet_b200/registration.py)."""
 import csv
 import math
 import os
@@ -26,7 +28,7 @@ import random
 import numpy as np
 import torch
 
-from . import nrrd_io
+from . import augment, nrrd_io
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -157,17 +159,20 @@ class FewshotVolumeReader(torch.utils.data.Dataset):
         support_images = [[torch.from_numpy(shots[j]['image']) for j in range(n_shots)] for _ in range(n_ways)]
         support_labels = [[torch.from_numpy(shots[j]['mask']) for j in range(n_shots)] for _ in range(n_ways)]
         qry = self.load_image_and_mask(self.data_info[c][d]['pid'], self.classes[c])
+        if self.mode == 'train' and self.cfg['do_elastic'] and np.random.randint(2, size=1).item():      # :306-307
+            qry['image'], qry['mask'] = augment.elastic_transform_all(qry['image'], qry['mask'])
         return {'support_images': support_images, 'support_labels': support_labels,
                 'query_images': [[torch.from_numpy(qry['image'])]], 'query_labels': [[torch.from_numpy(qry['mask'])]],
                 'class_id': c, 'pid': self.data_info[c][d]['pid'], 'supp_pids': support_idx}
 
 
 class FewshotSliceReader(torch.utils.data.Dataset):
-    """:448-589, eval branch.  Extra config keys: k, test_shot, use_registration_loss, use_registration_mask, do_deformable."""
+    """:448-589.  Extra config keys: k, test_shot, use_registration_loss, use_registration_mask, do_deformable; train mode:
+    do_intaug, gamma_range, do_elastic."""
 
     def __init__(self, data_dir, set_name, config, mode='eval'):
-        if mode != 'eval':
-            raise NotImplementedError("FewshotSliceReader: only mode='eval' is built (see the module docstring)")
+        if mode not in ('eval', 'train'):
+            raise NotImplementedError('FewshotSliceReader: mode=%r' % (mode,))
         self.cfg, self.k, self.mode = config, config['k'], mode
         self.fewshot_volume_reader = FewshotVolumeReader(data_dir, set_name, config, mode=mode)
 
@@ -182,6 +187,30 @@ class FewshotSliceReader(torch.utils.data.Dataset):
         query = np.floor(np.array(np.arange(0, nq, nq / k).tolist() + [nq])).astype(np.int32)
         return support, query
 
+    def _train_pairs(self, supp_vols, supp_labs, q_vol, q_lab, s_idx, q_idx, k):
+        """:482-515 — k (support slice, query slice) pairs: the centre slice of every support block against a RANDOM slice of the
+        matching query block; the query slice gets an optional random gamma and one random affine (image and label together); the
+        pairs are shuffled.  Only the first support volume reaches the network (:513-514).  Generators in the reference's order:
+        `random.randint`, `np.random.randint`, `np.random.rand` (gamma), torch (affine), then `np.random.shuffle`."""
+        supp_img = supp_vols[0][:, s_idx[0], :, :].permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1).clone()
+        supp_lab = supp_labs[0][0, s_idx[0], :, :].clone()
+        for i in range(1, len(supp_vols)):               # the other shots are sliced (and discarded) like the reference does
+            supp_vols[i][:, s_idx[i], :, :]
+        q_imgs, q_labs = [], []
+        for j in range(k):
+            z = random.randint(int(q_idx[j]), int(q_idx[j + 1]) - 1)
+            q, lab = q_vol[:, z, :, :].clone(), q_lab[:, z, :, :].clone()
+            if self.cfg['do_intaug'] and np.random.randint(2, size=1).item():
+                q = torch.from_numpy(augment.gamma_tansform(q.numpy(), self.cfg.get('gamma_range', [0.5, 1.5])))
+            q, lab = augment.random_transform(q[None, ...], lab)
+            q_imgs.append(q[0])
+            q_labs.append(lab)
+        q_imgs = torch.cat(q_imgs, dim=0).unsqueeze(1).expand(-1, 3, -1, -1)
+        q_labs = torch.cat(q_labs, dim=0)
+        order = np.arange(k)
+        np.random.shuffle(order)
+        return [supp_img[order, ...]], [supp_lab[order, ...]], q_imgs[order, ...], q_labs[order, ...]      # [[tensor]] nesting (:513-514)
+
     def __getitem__(self, idx):
         vol = self.fewshot_volume_reader[idx]
         support_images, support_labels = vol['support_images'], vol['support_labels']
@@ -193,9 +222,13 @@ class FewshotSliceReader(torch.utils.data.Dataset):
         s_idx, q_idx = self.slice_blocks(num_slices, k)
         n_test_shots = self.cfg.get('test_shot', self.cfg['n_shot'])
         q_vol, q_lab = query_images[0][0], query_labels[0][0]                  # [1, D, H, W] each
-        new_query_images = q_vol.permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1)   # slices become the batch, 3 channels (:517)
-        new_query_labels = q_lab[0]
-        for i in range(len(support_images[0])):                                # the last support volume wins (:523-548)
+        if self.mode == 'train':
+            shot_images, shot_labels, new_query_images, new_query_labels = self._train_pairs(support_images[0], support_labels[0], q_vol,
+                                                                                            q_lab, s_idx, q_idx, k)
+        else:
+            new_query_images = q_vol.permute(1, 0, 2, 3).contiguous().expand(-1, 3, -1, -1)   # slices become the batch, 3 channels (:517)
+            new_query_labels = q_lab[0]
+        for i in range(len(support_images[0]) if self.mode == 'eval' else 0):  # the last support volume wins (:523-548)
             vol_i, lab_i = support_images[0][i], support_labels[0][i]
             per_shot_img, per_shot_lab = [], []
             for m in range(n_test_shots):

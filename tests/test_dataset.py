@@ -121,10 +121,63 @@ def test_slice_blocks_edge_cases():
     assert s[0].max() < 17 and s[1].max() < 5
 
 
-def test_reg_reader_requires_registration_and_eval_mode(tmp_path):
+def test_train_mode_items_match_reference_golden(tmp_path):
+    """`mode='train'` (dataset/few_shot_reader.py:482-515): random query slice per block, gamma augmentation, one random affine per
+    slice (image and label together), shuffle of the k pairs — bit for bit the items of the reference classes under the same
+    `random` / `np.random` / torch seeds (elastic off: the reference seeds that one from OS entropy)."""
+    g = np.load(GOLD)
+    data_dir, set_name, cfg = make_synthetic_dataset(str(tmp_path))
+    cfg = dict(cfg, use_registration_loss=False, train_classes=cfg['eval_classes'], do_elastic=False, do_intaug=True)
+    ds = FewshotSliceReader(data_dir, set_name, cfg, mode='train')
+    for i in (0, 1, 3):
+        random.seed(200 + i); np.random.seed(300 + i); torch.manual_seed(400 + i)
+        it = ds[i]
+        assert ds.k == int(g['train%d_k' % i])
+        np.testing.assert_array_equal(np.array(it['supp_pids'][0]), g['train%d_supp_pid' % i])
+        shapes = list(it['support_images'][0][0].shape) + list(it['query_images'].shape) + list(it['query_labels'].shape)
+        np.testing.assert_array_equal(np.array(shapes), g['train%d_shapes' % i])
+        dtypes = [str(it['query_images'].dtype), str(it['query_labels'].dtype), str(it['support_images'][0][0].dtype)]
+        assert dtypes == [str(d) for d in g['train%d_dtypes' % i]]
+        np.testing.assert_array_equal(it['query_images'][:, 0, ::2, ::2].numpy().astype(np.float32), g['train%d_query_images' % i])
+        np.testing.assert_array_equal(np.packbits(it['query_labels'].numpy().astype(np.uint8)), g['train%d_query_labels' % i])
+        np.testing.assert_array_equal(it['support_images'][0][0][:, 0, ::2, ::2].numpy().astype(np.float32), g['train%d_support_images' % i])
+        np.testing.assert_array_equal(np.packbits(it['support_labels'][0][0].numpy().astype(np.uint8)), g['train%d_support_labels' % i])
+        assert it['query_images'].shape[1] == 3 and it['support_images'][0][0].shape == it['query_images'].shape
+
+
+def test_elastic_transform_matches_reference_golden():
+    """dataset/brain_reader.py:248-293 with an explicit generator (the reference's own call seeds from OS entropy, so the train
+    readers' elastic branch is checked for shape / label preservation only)."""
+    from rpnet_b200.dataset import augment
+    g = np.load(GOLD)
+    rs = np.random.RandomState(11)
+    vol = (rs.rand(1, 3, 96, 128).astype(np.float32) * 2 - 1)
+    msk = np.zeros((2, 3, 96, 128), np.float32); msk[0, :, 30:70, 40:90] = 1; msk[1, 1, 25:45, 30:60] = 1
+    ei, em = augment.elastic_transform(vol, msk, alpha=100, sigma=6, alpha_affine=3.0, random_state=np.random.RandomState(5))
+    np.testing.assert_array_equal(ei.astype(np.float32), g['elastic_image'])
+    # masks: interior only — the reference warps them with BORDER_TRANSPARENT into an uninitialised destination (garbage in the
+    # strip the warp uncovers); here that strip is zero
+    np.testing.assert_array_equal(np.packbits(em[:, :, 20:-20, 20:-20].astype(np.uint8)), g['elastic_mask_interior'])
+    assert set(np.unique(em)) <= {0.0, 1.0}
+    ei2, em2 = augment.elastic_transform_all(vol, msk)                  # OS-entropy seeded, like the reference
+    assert ei2.shape == vol.shape and em2.shape == msk.shape and set(np.unique(em2)) <= {0.0, 1.0}
+    assert abs(float(em2[0].sum()) / float(msk[0].sum()) - 1.0) < 0.5
+
+
+def test_train_mode_with_elastic_runs(tmp_path):
+    data_dir, set_name, cfg = make_synthetic_dataset(str(tmp_path), n_patients=2)
+    cfg = dict(cfg, use_registration_loss=False, train_classes=cfg['eval_classes'], do_elastic=True, do_intaug=True)
+    ds = FewshotSliceReader(data_dir, set_name, cfg, mode='train')
+    np.random.seed(1)                                                   # the coin of :306 comes up 1 for this seed
+    it = ds[0]
+    assert it['query_images'].shape[1] == 3 and it['query_images'].shape[0] == ds.k
+    assert torch.isfinite(it['query_images']).all()
+
+
+def test_reg_reader_requires_registration(tmp_path):
     data_dir, set_name, cfg = make_synthetic_dataset(str(tmp_path), n_patients=2)
     with pytest.raises(NotImplementedError):
-        FewshotRegReader(data_dir, set_name, cfg, mode='train')
+        FewshotRegReader(data_dir, set_name, cfg, mode='test')
     ds = FewshotRegReader(data_dir, set_name, dict(cfg, use_registration_loss=False), mode='eval')
     with pytest.raises(TypeError):
         ds[0]
@@ -192,3 +245,40 @@ def test_reg_reader_item_matches_reference_golden(tmp_path):
                   grid=it['grid'].cuda(), query_labels=it['query_labels'].long().cuda(),
                   appr_query_labels=it['appr_query_labels'].cuda())
     assert out['output'].shape == (S, 2, H, W) and torch.isfinite(out['output']).all()
+
+
+@pytest.mark.gpu
+def test_reg_reader_train_item_feeds_a_train_step(tmp_path):
+    """FewshotRegReader(mode='train'): the k augmented (support, query) pairs, registered on the device, against the reference's item
+    (CPU registration; same tolerances as the eval item), then one train step of the network on it (what a train loop would do —
+    the reference ships none)."""
+    g = np.load(GOLD)
+    data_dir, set_name, cfg = make_synthetic_dataset(str(tmp_path))
+    ds = FewshotRegReader(data_dir, set_name, dict(cfg, train_classes=cfg['eval_classes'], do_elastic=False, do_intaug=True), mode='train')
+    random.seed(210); np.random.seed(310); torch.manual_seed(410)
+    it = ds[1]
+    S = it['query_images'].shape[0]
+    shapes = list(it['support_images'][0][0].shape) + list(it['query_images'].shape) + list(it['appr_query_labels'].shape) + list(it['grid'].shape)
+    np.testing.assert_array_equal(np.array(shapes), g['regtrain_shapes'])
+    np.testing.assert_array_equal(it['query_images'][:, 0, ::2, ::2].cpu().numpy().astype(np.float32), g['regtrain_query_images'])
+    np.testing.assert_array_equal(np.packbits(it['query_labels'].cpu().numpy().astype(np.uint8)), g['regtrain_query_labels'])
+    theta = torch.stack([t for t, _ in it['registration_field']]).cpu().numpy()
+    np.testing.assert_allclose(theta, g['regtrain_theta'], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(it['support_images'][0][0][:, 0, ::2, ::2].cpu().numpy(), g['regtrain_support_images'], atol=5e-2)
+    H, W = it['appr_query_labels'].shape[1:]
+    for key, val in (('appr', it['appr_query_labels']), ('support_labels', it['support_labels'][0][0])):
+        ref = np.unpackbits(g['regtrain_%s' % key])[:S * H * W].reshape(S, H, W)
+        got = val.cpu().numpy().astype(np.uint8)
+        assert (got != ref).mean() < 5e-3, (key, (got != ref).mean())
+    from rpnet_b200.nn.rp_net import RP_Net
+    from rpnet_b200.train import TrainStep
+    net = RP_Net(cfg={'align': True, 'backbone': 'UNet'}, backbone_cfg=dict(
+        unet_normalize_type='BatchNorm2d', final_activation='sigmoid', mask_feature_map=False, n_iter_refinement=2, soft_mask=False,
+        mask_refinement_correlation_radius=5)).cuda().train()
+    fg = it['support_labels'][0][0].float().cuda()
+    d = {'supp_imgs': [[it['support_images'][0][0].float().cuda()]], 'fore_mask': [[fg]], 'back_mask': [[1 - fg]],
+         'qry_imgs': [it['query_images'].float().cuda()], 'query_labels': it['query_labels'].long().cuda(),
+         'appr_query_labels': it['appr_query_labels'].float().cuda()}
+    loss = TrainStep(net, lr=1e-4).step(d)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all()
