@@ -89,7 +89,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
   uint64_t* conv_bar = tempty_bar + 2;                   // [kStages] fp16 -> bf16 conversion of the x boxes done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kStages);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // lane-0 broadcast: provably warp-uniform role branches
   const int lane = threadIdx.x & 31;
   const int tiles_mn = p.n_mtiles * p.n_ntiles;
   const int num_items = tiles_mn * p.splits;
@@ -161,8 +161,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp runs the loop (uniform operands), one elected lane issues =====================
+    {
       const uint32_t idesc = umma_idesc_f16(128, BN) | (1u << 15) | (1u << 16) | (1u << 7) | (1u << 10);   // both operands bf16 at MMA time
       int stage = 0;
       uint32_t phase = 0;
@@ -186,13 +186,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_consta
 #pragma unroll
             for (int h = 0; h < kWgAcc; ++h) {
               const uint64_t a_desc = umma_desc_sw128_mn(a_addr + h * 2 * kWgBoxBytes + k * 2048, kWgBoxBytes, 1024);
-              umma_f16(tmem_base + h * BN, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+              if (elect_one()) umma_f16(tmem_base + h * BN, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if (elect_one()) umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[0]);
+        if (elect_one()) umma_commit(&tfull_bar[0]);
+        __syncwarp();
       }
     }
   } else {
@@ -281,7 +283,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
   uint64_t* conv_bar = tempty_bar + 1;                   // [kWhStages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(conv_bar + kWhStages);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform role branches
   const int nch = p.chunks0 + p.chunks1;
   const int tiles_mn = nch * p.n_ntiles;                // (input chunk, cout tile) pairs
   const int num_items = tiles_mn * p.splits;
@@ -328,7 +330,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // the whole warp runs the loop (uniform operands), one elected lane issues
       const uint32_t idesc = umma_idesc_f16(128, 64) | (1u << 15) | (1u << 16) | (1u << 7) | (1u << 10);   // MN-major, bf16
       int stage = 0;
       uint32_t phase = 0;
@@ -353,13 +355,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_c
               const int sa = 2 * j, sb = 2 * j + 1 < 9 ? 2 * j + 1 : 2 * j;
               const uint32_t off_a = (sa / 3) * kWhBoxA + (sa % 3) * 1024, off_b = (sb / 3) * kWhBoxA + (sb % 3) * 1024;
               const uint64_t a_desc = umma_desc_sw128_mn(a_addr + off_a + k * 2048, off_b - off_a, 1024);
-              umma_f16(tmem_base + j * 64, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
+              if (elect_one()) umma_f16(tmem_base + j * 64, a_desc, b_desc, idesc, (pt != k0 || k != 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if (elect_one()) umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kWhStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar);
+        if (elect_one()) umma_commit(tfull_bar);
+        __syncwarp();
       }
     }
   } else {
