@@ -1,21 +1,24 @@
-// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, kind::f16, fp32 accumulation
-// in TMEM) for the RP-Net conv stacks: every 3x3 / dilated 3x3 / 1x1 / sub-pixel 2x2 "tap list"
-// convolution of the U-Net / VGG encoders and of the context-relation encoder.
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulation in TMEM) for the RP-Net conv stacks: every
+// 3x3 / dilated 3x3 / 1x1 / sub-pixel 2x2 "tap list" convolution of the U-Net / VGG / ResNet18 encoders and of the context-relation
+// encoder, forward and data gradient.
 //
-//   reference ops replaced: nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU (+ nn.MaxPool2d(2,2),
-//   + torch.cat on channels, + nn.Upsample(x2) via sub-pixel taps)
-//   net/modules.py:42-75, net/unet.py:435-467, net/vgg.py:22-58, net/rp_net.py:50-69.
+//   reference ops replaced: nn.Conv2d + nn.BatchNorm2d(eval) + nn.ReLU (+ nn.MaxPool2d(2,2), + torch.cat on channels,
+//   + nn.Upsample(x2) via sub-pixel taps, + the BasicBlock residual add), or in train mode the conv + the batch statistics
+//   net/modules.py:42-75, net/unet.py:435-467, net/vgg.py:22-58, net/rp_net.py:19-42,50-69.
 //
-// GEMM view: M = output pixels (128 per tile: a bn x bh x bw box of the NHWC activation),
-//            N = output channels (BN per tile), K = taps x input channels (64 per k-block).
-// A operand: fp16 NHWC activations; one TMA box load per (tap, 64-channel chunk) at the tap-shifted
-//            pixel origin — TMA out-of-bounds zero fill IS the conv zero padding.
-// B operand: fp16 weights packed [tap][cout][cin] (K-major); one TMA box per k-block.
+// GEMM view: M = output pixels (128 per tile: a bn x bh x bw box of the NHWC activation; 256 for a CTA pair),
+//            N = output channels (BN per tile), K = taps x input channels (one 128-byte swizzle row per k-block).
+// A operand: NHWC activations; one TMA box load per (tap, 64-channel chunk) at the tap-shifted pixel origin - TMA out-of-bounds
+//            zero fill IS the conv zero padding.  B operand: weights packed [tap][cout][cin] (K-major); one TMA box per k-block.
 // Both land in 128B-swizzled K-major shared-memory tiles consumed directly by tcgen05.mma.
-// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// MMA issuer, warps 2..5 = epilogue (TMEM -> registers -> scale/shift/ReLU [-> 2x2 max-pool via
-// warp shuffles] -> fp16/fp32 NHWC stores).  Two TMEM accumulator buffers overlap the epilogue of
-// tile i with the main loop of tile i+1.
+// Arithmetic (include/rpnet_b200.h): plain fp16 / bf16 operands (kind::f16); split-fp16 hi.Wh + lo.Wh + hi.Wl as three k-block
+// segments; or - the default - the fp16 main term plus two e4m3 first-order corrections (kind::f8f6f4, K = 128 per k-block) into the
+// SAME accumulator: the e4m3 k-blocks of a tile go first and the first kind::f16 MMA scales the accumulator by 2^-15 (scale-input-d).
+// Warp roles (192 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (warp-uniform loop,
+// one elected lane issues), warps 2..5 = epilogue (TMEM -> registers, next chunk prefetched -> scale/shift/(+residual)/ReLU or the
+// BatchNorm statistics [-> 2x2 max-pool via warp shuffles] -> hi / lo plane stores).  Two TMEM accumulator buffers overlap the
+// epilogue of tile i with the main loop of tile i+1; a buffer is handed back as soon as its last chunk sits in registers.
+// Variants: CTA pair (cta_group::2), weights-stationary, halo-sharing (one activation box per column offset), both together.
 #include "common.cuh"
 
 #include <mutex>
