@@ -64,10 +64,14 @@ def decoder_precision(p):
 
 
 class Workspace:
-    """Named, shape-keyed persistent device buffers (stable pointers: CUDA-graph friendly)."""
+    """Named, shape-keyed persistent device buffers (stable pointers: CUDA-graph friendly).  A buffer set exists per distinct
+    activation shape; owners bound the number of shapes they keep with ShapeBudget and call clear() when it is exceeded."""
 
     def __init__(self):
         self._bufs = {}
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
 
     def get(self, name, shape, dtype, device):
         key = (name, tuple(shape), dtype, str(device))
@@ -265,6 +269,25 @@ def run_upconv(phases, scale, shift, src, ws, name, split=False, w_split=None):
     for wp, taps, (py, px) in phases:
         ops.conv_igemm(hi_of(src), wp, taps, scale, shift, True, out=out, out_map=(2, py, 2, px))
     return out
+
+
+class ShapeBudget:
+    """Bounds the device memory held for past input shapes: every distinct shape key allocates its own workspace buffers (and
+    CUDA-graph capture), so a long run over heterogeneous volumes / batch sizes would grow without bound.  note(key) returns True
+    when `key` is new and the number of shapes seen since the last reset exceeds `limit` — the owner then drops its workspaces and
+    graphs (they are re-created on demand)."""
+
+    def __init__(self, limit=8):
+        self.limit, self.seen = limit, set()
+
+    def note(self, key):
+        if key in self.seen:
+            return False
+        self.seen.add(key)
+        if len(self.seen) > self.limit:
+            self.seen = {key}
+            return True
+        return False
 
 
 def nchw_f32_to_nhwc_f16(x):

@@ -224,6 +224,8 @@ class RP_Net(nn.Module):
         pdev = next(self.parameters()).device
         if pdev != dev:
             raise RuntimeError('RP_Net parameters are on %s but the inputs are on %s' % (pdev, dev))
+        if self._shape_budget().note((tuple(imgs.shape), n_ways, n_shots)):
+            self.release_workspaces()                # a long eval over heterogeneous shapes must not grow device memory without bound
         with torch.cuda.device(dev):             # kernels launch on the current device's stream: make the model's device current
             if getattr(self, '_use_graph', False):
                 logits = self._forward_eval_graphed(imgs, fore, back, appr, n_ways, n_shots, B)
@@ -276,6 +278,28 @@ class RP_Net(nn.Module):
         return logits
 
     # ------------------------------------------------------------------ CUDA-graph replay of the eval schedule
+    def _shape_budget(self):
+        b = self.__dict__.get('_shapes')
+        if b is None:
+            b = self.__dict__['_shapes'] = engine.ShapeBudget()
+        return b
+
+    def release_workspaces(self):
+        """Drop every cached activation buffer and CUDA-graph capture of the eval path (they are re-created on demand).  Called
+        automatically once more than ShapeBudget.limit distinct input shapes have been seen."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self._graphs = {}
+        self._ws.clear()
+        for m in self.modules():
+            ws = m.__dict__.get('_ws')
+            if isinstance(ws, engine.Workspace):
+                ws.clear()
+            eng = m.__dict__.get('_in_engine')
+            if eng is not None:
+                eng.ws.clear()
+                eng._scratch.clear()
+
     def enable_cuda_graph(self, flag=True):
         """Replay the eval forward as one CUDA graph per input shape (the recurrent loop is ~60 small launches per
         iteration: launch latency dominates at small batches).  Captured graphs are dropped when the

@@ -551,6 +551,12 @@ class TrainEngine(EncoderEngine):
         n_img = n_supp + B
         self.act = {}
         engine.WEIGHTS_EPOCH += 1          # BN running statistics are updated through raw pointers below
+        budget = self.__dict__.setdefault('_shapes', engine.ShapeBudget())
+        if budget.note((Wa, Sh, B, H, W)):                # varying batch / crop sizes must not grow device memory without bound
+            torch.cuda.synchronize()
+            self.ws.clear()
+            self._scratch.clear()
+            self.saved = None
 
         imgs = torch.cat([torch.cat(way, dim=0) for way in supp_imgs] + [qry_imgs[0]], dim=0).float().contiguous()
         fore = torch.stack([torch.stack(way, dim=0) for way in d['fore_mask']], dim=0).float().reshape(n_supp, H, W).contiguous()

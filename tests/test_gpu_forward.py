@@ -216,3 +216,26 @@ def test_forward_edge_cases_vs_oracle(dev):
     from net.model import model_factory
     with pytest.raises(NotImplementedError):
         model_factory['RP_Net'](pretrained_path=None, cfg={'align': True, 'backbone': 'densenet'}, backbone_cfg=cfg)
+
+
+def test_workspace_growth_is_bounded(dev):
+    """Every distinct input shape owns a workspace buffer set (and a CUDA-graph capture); engine.ShapeBudget drops them all once more
+    than `limit` shapes have been seen, so a long eval over heterogeneous volumes cannot grow device memory without bound — and the
+    results after a release are the results before it."""
+    from oracle import weights
+    from rpnet_b200 import engine
+    from rpnet_b200.synthetic import make_episode, perturb_bn_stats
+    sd = perturb_bn_stats(weights.unet_rpnet_state_dict(0))
+    net = _model(sd, _cfg(2), dev)
+    net.enable_cuda_graph(True)
+    first = _run(net, make_episode(1, 1, 1, 64, seed=3), dev)['output'].clone()
+    peak = 0
+    for b in range(1, 14):                                           # 13 distinct shapes > the budget of 8
+        _run(net, make_episode(b, 1, 1, 64, seed=3), dev)
+        held = net._ws.nbytes() + net.encoder._ws.nbytes()
+        peak = max(peak, held)
+        assert len(net._graphs) <= engine.ShapeBudget().limit
+    one = net._ws.nbytes() + net.encoder._ws.nbytes()                 # what the shapes since the last release hold
+    assert peak < 9 * 13 * (one // max(1, len(net._shapes.seen))) and len(net._shapes.seen) <= 8
+    again = _run(net, make_episode(1, 1, 1, 64, seed=3), dev)['output']
+    assert torch.equal(first, again)
